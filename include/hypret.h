@@ -1,0 +1,108 @@
+/* hypret -- C ABI of the B200-native hyperbolic / cosine retrieval hot path.
+ *
+ * One shared library (libhypret.so), plain pointers and sizes, no torch or C++
+ * types in any signature.  The reference (Alvarodelamaza/patent-image-retrieval)
+ * has no FFI of its own: its hot path is plain Python calling geoopt / sklearn.
+ * Each entry point below therefore names the reference *call site* it replaces
+ * (file:line under /root/reference); INTEGRATION.md shows the ctypes binding a
+ * maintainer would add on the reference side.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless its name ends in _host;
+ *   - every buffer (outputs and workspaces included) is allocated by the caller;
+ *   - row-major, contiguous; rows of fp32 matrices 16-byte aligned (D % 4 == 0);
+ *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*);
+ *   - return value: 0 = ok, negative = HYPRET_E* argument error, positive = cudaError_t;
+ *   - no C++ exception crosses the boundary; there is no CPU fallback.
+ */
+#ifndef HYPRET_H_
+#define HYPRET_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HYPRET_OK 0
+#define HYPRET_EINVAL (-1)      /* bad argument (shape, alignment, enum)            */
+#define HYPRET_EUNSUPPORTED (-2) /* valid request this build cannot serve (e.g. D)   */
+#define HYPRET_EDRIVER (-3)     /* driver entry point (cuTensorMapEncodeTiled) missing */
+#define HYPRET_ENOTSM100 (-4)   /* device is not compute capability 10.x             */
+
+/* projection modes (hypret_project_rows) */
+#define HYPRET_MODE_EXPMAP0 0 /* u Euclidean  -> y = project(expmap0(u))             */
+#define HYPRET_MODE_ONBALL 1  /* u on the ball -> y = project(u)                      */
+#define HYPRET_MODE_COSINE 2  /* u Euclidean  -> y = u / ||u||  (zero rows stay zero) */
+#define HYPRET_SIDE_QUERY 0
+#define HYPRET_SIDE_GALLERY 1
+
+/* scoring metrics (hypret_rerank) */
+#define HYPRET_METRIC_COSINE 0
+#define HYPRET_METRIC_HYPERBOLIC 1
+
+const char* hypret_strerror(int rc);
+int hypret_version(void);
+
+/* Row length (elements) of the bf16 GEMM operand for feature dimension d:
+ * roundup(d, 64) + 16 extension columns. */
+int64_t hypret_operand_kpad(int d);
+
+/* Fused projection + operand build, one pass over the rows.
+ * Replaces pmath.expmap0 -> pmath.project (src/models.py:310,317), the final
+ * pmath.project of DeeperHyperbolicEncoder.forward (src/models.py:504), and the row
+ * normalisation inside sklearn cosine_similarity (notebooks/retrieval.ipynb:368).
+ *   u        [n,d] fp32 in
+ *   y32      [n,d] fp32 out or NULL  (the point; exact-rerank operand)
+ *   op_bf16  [n,kpad] bf16 out or NULL (tensor-core operand, see csrc/project.cu)
+ *   sqnorm   [n] fp32 out or NULL    (||y||^2)
+ * d % 4 == 0, d <= 2048. */
+int hypret_project_rows(const float* u, int64_t n, int d, float c, int mode, int side, float* y32, void* op_bf16,
+                        float* sqnorm, void* stream);
+
+/* Work decomposition of hypret_score_topk for a problem size on the current device. */
+typedef struct {
+  int32_t n_qtiles;        /* ceil(Q / 128)                                  */
+  int32_t n_gtiles;        /* ceil(N / 256)                                  */
+  int32_t n_splits;        /* gallery splits; candidate lists per query      */
+  int32_t tiles_per_split; /* gallery tiles per split                        */
+  int32_t grid;            /* persistent CTAs launched                       */
+  int32_t stages;          /* shared-memory pipeline stages                  */
+  int32_t resident;        /* 1: query tile resident in shared memory        */
+  int32_t smem_bytes;      /* dynamic shared memory per CTA                  */
+} hypret_score_plan_t;
+
+int hypret_score_plan(int64_t Q, int64_t N, int d, int kprime, int n_splits_hint, hypret_score_plan_t* plan);
+
+/* Scoring GEMM + fused streaming top-k' (tcgen05 / TMEM / TMA).
+ * Replaces the one-vs-all scoring loops  pmath.dist(q[1,D], G[P,D])  (src/train.py:3259)
+ * and  cosine_similarity(Q, G)  (notebooks/retrieval.ipynb:368) together with the ranking
+ * that follows them (np.argsort, retrieval.ipynb:383,202; torch.topk, src/auxiliary.py:374)
+ * as a *candidate filter*: per query and gallery split it keeps the kprime smallest
+ * bf16-operand surrogate scores.  The [Q,N] matrix is never written to memory.
+ *   q_op [Q,kpad] bf16, g_op [N,kpad] bf16   operands from hypret_project_rows
+ *   cand_score [Q, n_splits, kprime] fp32 out, cand_idx same shape int32 out (-1 = empty)
+ *   n_splits  must equal plan.n_splits of hypret_score_plan(Q, N, d, kprime, hint)
+ *   debug_scores  NULL, or [Q,N] fp32 that receives every surrogate score (tests only)
+ * 1 <= kprime <= 32. */
+int hypret_score_topk(const void* q_op, int64_t Q, const void* g_op, int64_t N, int d, int kprime, int n_splits,
+                      float* cand_score, int32_t* cand_idx, float* debug_scores, void* stream);
+
+/* Candidate merge + exact rerank.  For each query: keep the kprime best of its
+ * n_splits*kprime candidates by surrogate score, recompute their distance exactly from the
+ * fp32 rows (differences formed explicitly, fp64 accumulation, arccosh closed form ==
+ * pmath.dist, src/train.py:3259; or the cosine similarity, retrieval.ipynb:368), sort
+ * (ascending distance / descending similarity, ties -> lower index) and emit the first k.
+ *   q32 [Q,d], g32 [N,d] fp32   (hyperbolic: points on the ball; cosine: raw features)
+ *   out_score [Q,k] fp32, out_idx [Q,k] int64 (+ idx_offset; -1 when fewer than k rows)
+ *   out_margin [Q] fp32 or NULL: (worst kept surrogate) - (exact surrogate of the k-th result)
+ * 1 <= k <= kprime <= 32. */
+int hypret_rerank(const float* q32, const float* g32, int64_t Q, int64_t N, int d, float c, int metric,
+                  const float* cand_score, const int32_t* cand_idx, int n_splits, int kprime, int k,
+                  int64_t idx_offset, float* out_score, int64_t* out_idx, float* out_margin, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HYPRET_H_ */

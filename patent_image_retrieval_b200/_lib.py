@@ -1,0 +1,68 @@
+"""ctypes binding of libhypret.so (include/hypret.h).
+
+The product path has no CPU fallback: if the library cannot be built or loaded the
+first call raises.  Every wrapper checks the integer status and raises
+``RuntimeError(hypret_strerror(rc))``.
+"""
+from __future__ import annotations
+
+import ctypes
+from ctypes import c_char_p, c_float, c_int, c_int32, c_int64, c_void_p, POINTER, Structure
+
+from . import build as _build
+
+_LIB = None
+
+
+class ScorePlan(Structure):
+    _fields_ = [
+        ("n_qtiles", c_int32),
+        ("n_gtiles", c_int32),
+        ("n_splits", c_int32),
+        ("tiles_per_split", c_int32),
+        ("grid", c_int32),
+        ("stages", c_int32),
+        ("resident", c_int32),
+        ("smem_bytes", c_int32),
+    ]
+
+    def asdict(self):
+        return {name: int(getattr(self, name)) for name, _ in self._fields_}
+
+
+# symbol -> (restype, argtypes); must list every function include/hypret.h declares
+SIGNATURES = {
+    "hypret_strerror": (c_char_p, [c_int]),
+    "hypret_version": (c_int, []),
+    "hypret_operand_kpad": (c_int64, [c_int]),
+    "hypret_project_rows": (c_int, [c_void_p, c_int64, c_int, c_float, c_int, c_int, c_void_p, c_void_p, c_void_p,
+                                    c_void_p]),
+    "hypret_score_plan": (c_int, [c_int64, c_int64, c_int, c_int, c_int, POINTER(ScorePlan)]),
+    "hypret_score_topk": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int, c_int, c_int, c_void_p, c_void_p,
+                                  c_void_p, c_void_p]),
+    "hypret_rerank": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int, c_float, c_int, c_void_p, c_void_p, c_int,
+                              c_int, c_int, c_int64, c_void_p, c_void_p, c_void_p, c_void_p]),
+}
+
+
+def load() -> ctypes.CDLL:
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    try:
+        path = _build.build()
+    except Exception as exc:  # no silent fallback: surface the build failure
+        raise RuntimeError(f"libhypret.so is not built and cannot be built here: {exc}") from exc
+    lib = ctypes.CDLL(str(path))
+    for name, (restype, argtypes) in SIGNATURES.items():
+        fn = getattr(lib, name)   # AttributeError if the library lacks a declared symbol
+        fn.restype = restype
+        fn.argtypes = argtypes
+    _LIB = lib
+    return lib
+
+
+def check(rc: int) -> None:
+    if rc != 0:
+        msg = load().hypret_strerror(rc)
+        raise RuntimeError(f"{msg.decode() if msg else 'hypret error'} (rc={rc})")

@@ -1,0 +1,80 @@
+// extern "C" boundary of libhypret.so -- argument validation and dispatch only.
+// Signatures and the reference call sites they replace are documented in include/hypret.h.
+#include "common.cuh"
+
+namespace {
+
+int check_device() {
+  int dev = 0, major = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return (int)e;
+  e = cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
+  if (e != cudaSuccess) return (int)e;
+  return major == 10 ? HYPRET_OK : HYPRET_ENOTSM100;
+}
+
+bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+}  // namespace
+
+extern "C" {
+
+const char* hypret_strerror(int rc) {
+  switch (rc) {
+    case HYPRET_OK: return "ok";
+    case HYPRET_EINVAL: return "hypret: invalid argument (shape, alignment or enum)";
+    case HYPRET_EUNSUPPORTED: return "hypret: request not supported by this build (size or dimension limit)";
+    case HYPRET_EDRIVER: return "hypret: CUDA driver entry point cuTensorMapEncodeTiled unavailable";
+    case HYPRET_ENOTSM100: return "hypret: device is not compute capability 10.x (sm_100a kernels only; no fallback)";
+    default: break;
+  }
+  if (rc > 0) return cudaGetErrorString(static_cast<cudaError_t>(rc));
+  return "hypret: unknown error";
+}
+
+int hypret_version(void) { return 100; }
+
+int64_t hypret_operand_kpad(int d) { return d > 0 ? (int64_t)hypret_kpad(d) : 0; }
+
+int hypret_project_rows(const float* u, int64_t n, int d, float c, int mode, int side, float* y32, void* op_bf16,
+                        float* sqnorm, void* stream) {
+  if (n < 0 || d < 4 || (d & 3) || d > 2048) return HYPRET_EINVAL;
+  if (mode < HYPRET_MODE_EXPMAP0 || mode > HYPRET_MODE_COSINE) return HYPRET_EINVAL;
+  if (side != HYPRET_SIDE_QUERY && side != HYPRET_SIDE_GALLERY) return HYPRET_EINVAL;
+  if (mode != HYPRET_MODE_COSINE && !(c > 0.f)) return HYPRET_EINVAL;
+  if (n == 0) return HYPRET_OK;
+  if (u == nullptr || !aligned16(u) || !aligned16(y32) || !aligned16(op_bf16)) return HYPRET_EINVAL;
+  int rc = check_device();
+  if (rc != HYPRET_OK) return rc;
+  return hypret_launch_project_rows(u, n, d, c, mode, side, y32, op_bf16, sqnorm, static_cast<cudaStream_t>(stream));
+}
+
+int hypret_score_topk(const void* q_op, int64_t Q, const void* g_op, int64_t N, int d, int kprime, int n_splits,
+                      float* cand_score, int32_t* cand_idx, float* debug_scores, void* stream) {
+  if (Q < 1 || N < 1 || d < 4 || (d & 3) || d > 2048) return HYPRET_EINVAL;
+  if (kprime < 1 || kprime > 32 || n_splits < 1) return HYPRET_EINVAL;
+  if (q_op == nullptr || g_op == nullptr || cand_score == nullptr || cand_idx == nullptr) return HYPRET_EINVAL;
+  int rc = check_device();
+  if (rc != HYPRET_OK) return rc;
+  return hypret_launch_score_topk(q_op, Q, g_op, N, d, kprime, n_splits, cand_score, cand_idx, debug_scores,
+                                  static_cast<cudaStream_t>(stream));
+}
+
+int hypret_rerank(const float* q32, const float* g32, int64_t Q, int64_t N, int d, float c, int metric,
+                  const float* cand_score, const int32_t* cand_idx, int n_splits, int kprime, int k,
+                  int64_t idx_offset, float* out_score, int64_t* out_idx, float* out_margin, void* stream) {
+  if (Q < 0 || N < 1 || d < 4 || (d & 3)) return HYPRET_EINVAL;
+  if (metric != HYPRET_METRIC_COSINE && metric != HYPRET_METRIC_HYPERBOLIC) return HYPRET_EINVAL;
+  if (metric == HYPRET_METRIC_HYPERBOLIC && !(c > 0.f)) return HYPRET_EINVAL;
+  if (kprime < 1 || kprime > 32 || k < 1 || k > kprime || n_splits < 1) return HYPRET_EINVAL;
+  if (Q == 0) return HYPRET_OK;
+  if (q32 == nullptr || g32 == nullptr || cand_score == nullptr || cand_idx == nullptr || out_score == nullptr ||
+      out_idx == nullptr || !aligned16(q32) || !aligned16(g32))
+    return HYPRET_EINVAL;
+  int rc = check_device();
+  if (rc != HYPRET_OK) return rc;
+  return hypret_launch_rerank(q32, g32, Q, N, d, c, metric, cand_score, cand_idx, n_splits * kprime, kprime, k,
+                              idx_offset, out_score, out_idx, out_margin, static_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

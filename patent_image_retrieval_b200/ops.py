@@ -1,0 +1,111 @@
+"""Torch-facing wrappers over the C ABI (include/hypret.h).
+
+PyTorch is plumbing here: it owns device memory and streams; every operator below
+passes raw device pointers into libhypret.so.  CUDA tensors only -- there is no CPU
+or eager fallback, a CPU tensor raises.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Optional, Tuple
+
+import torch
+
+from . import _lib
+
+MODE = {"expmap0": 0, "onball": 1, "cosine": 2}
+SIDE = {"query": 0, "gallery": 1}
+METRIC = {"cosine": 0, "hyperbolic": 1}
+MAX_KPRIME = 32
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _need_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("hypret operators run on CUDA tensors only (no CPU fallback)")
+
+
+def operand_kpad(d: int) -> int:
+    return int(_lib.load().hypret_operand_kpad(int(d)))
+
+
+def project_rows(u: torch.Tensor, c: float = 1.0, mode: str = "expmap0", side: str = "query",
+                 want_point: bool = True, want_operand: bool = True, want_sqnorm: bool = False):
+    """Fused expmap0/project (or project only, or L2-normalise) + bf16 GEMM operand + ||y||^2.
+
+    Returns ``(y32 | None, operand | None, sqnorm | None)``.
+    Mirrors pmath.expmap0 -> pmath.project (reference src/models.py:310,317)."""
+    _need_cuda(u)
+    if u.dtype != torch.float32 or u.dim() != 2:
+        raise ValueError("u must be a [n, d] float32 tensor")
+    u = u.contiguous()
+    n, d = u.shape
+    y = torch.empty_like(u) if want_point else None
+    op = torch.empty(n, operand_kpad(d), dtype=torch.bfloat16, device=u.device) if want_operand else None
+    sq = torch.empty(n, dtype=torch.float32, device=u.device) if want_sqnorm else None
+    with torch.cuda.device(u.device):
+        _lib.check(_lib.load().hypret_project_rows(_ptr(u), n, d, float(c), MODE[mode], SIDE[side], _ptr(y), _ptr(op),
+                                                   _ptr(sq), _stream()))
+    return y, op, sq
+
+
+def score_plan(Q: int, N: int, d: int, kprime: int, n_splits_hint: int = 0) -> dict:
+    plan = _lib.ScorePlan()
+    _lib.check(_lib.load().hypret_score_plan(int(Q), int(N), int(d), int(kprime), int(n_splits_hint),
+                                             ctypes.byref(plan)))
+    return plan.asdict()
+
+
+def score_topk(q_op: torch.Tensor, g_op: torch.Tensor, d: int, kprime: int, n_splits_hint: int = 0,
+               debug: bool = False, out: Optional[Tuple[torch.Tensor, torch.Tensor]] = None):
+    """tcgen05 scoring GEMM + streaming top-k'.  Returns ``(cand_score [Q,S,k'], cand_idx [Q,S,k'] int32)``
+    (+ the full ``[Q,N]`` surrogate matrix when ``debug`` -- tests only)."""
+    _need_cuda(q_op, g_op)
+    if q_op.dtype != torch.bfloat16 or g_op.dtype != torch.bfloat16:
+        raise ValueError("operands must be bf16 rows from project_rows")
+    kpad = operand_kpad(d)
+    if q_op.shape[1] != kpad or g_op.shape[1] != kpad or not q_op.is_contiguous() or not g_op.is_contiguous():
+        raise ValueError(f"operands must be contiguous [rows, {kpad}]")
+    Q, N = q_op.shape[0], g_op.shape[0]
+    with torch.cuda.device(q_op.device):
+        plan = score_plan(Q, N, d, kprime, n_splits_hint)
+        S = plan["n_splits"]
+        if out is None:
+            cs = torch.empty(Q, S, kprime, dtype=torch.float32, device=q_op.device)
+            ci = torch.empty(Q, S, kprime, dtype=torch.int32, device=q_op.device)
+        else:
+            cs, ci = out
+            if tuple(cs.shape) != (Q, S, kprime) or tuple(ci.shape) != (Q, S, kprime):
+                raise ValueError("preallocated candidate buffers do not match the score plan")
+        dbg = torch.empty(Q, N, dtype=torch.float32, device=q_op.device) if debug else None
+        _lib.check(_lib.load().hypret_score_topk(_ptr(q_op), Q, _ptr(g_op), N, int(d), int(kprime), S, _ptr(cs),
+                                                 _ptr(ci), _ptr(dbg), _stream()))
+    return (cs, ci, dbg) if debug else (cs, ci)
+
+
+def rerank(q32: torch.Tensor, g32: torch.Tensor, cand_score: torch.Tensor, cand_idx: torch.Tensor, c: float,
+           metric: str, k: int, idx_offset: int = 0, want_margin: bool = False):
+    """Merge candidate lists, exact fp64-accumulated rescoring, sorted top-k.
+    Returns ``(score [Q,k] f32, idx [Q,k] i64[, margin [Q] f32])``."""
+    _need_cuda(q32, g32, cand_score, cand_idx)
+    q32 = q32.contiguous()
+    g32 = g32.contiguous()
+    Q, d = q32.shape
+    N = g32.shape[0]
+    _, S, kprime = cand_score.shape
+    out_s = torch.empty(Q, k, dtype=torch.float32, device=q32.device)
+    out_i = torch.empty(Q, k, dtype=torch.int64, device=q32.device)
+    margin = torch.empty(Q, dtype=torch.float32, device=q32.device) if want_margin else None
+    with torch.cuda.device(q32.device):
+        _lib.check(_lib.load().hypret_rerank(_ptr(q32), _ptr(g32), Q, N, d, float(c), METRIC[metric],
+                                             _ptr(cand_score), _ptr(cand_idx), S, kprime, int(k), int(idx_offset),
+                                             _ptr(out_s), _ptr(out_i), _ptr(margin), _stream()))
+    return (out_s, out_i, margin) if want_margin else (out_s, out_i)

@@ -1,0 +1,93 @@
+"""GPU parity: fused projection kernel vs the oracle (reference src/models.py:310,317; 504)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import head, pmath
+from patent_image_retrieval_b200 import ops, synth
+
+pytestmark = pytest.mark.gpu
+
+
+def _bf16_split3(v):
+    a = v.to(torch.bfloat16).float()
+    b = (v - a).to(torch.bfloat16).float()
+    c = (v - a - b).to(torch.bfloat16).float()
+    return a, b, c
+
+
+@pytest.mark.parametrize("d", [128, 512, 768, 2048, 100])
+@pytest.mark.parametrize("c", [1.0, 0.5, 2.0])
+def test_expmap0_project_matches_oracle(d, c):
+    u = synth.gaussian_features(777, d, seed=3)
+    u[0] = 0.0                                    # zero row: clamp_min(1e-15) path
+    u[1] *= 60.0                                  # far outside: project clip, tanh clamp
+    u[2] *= 6.0
+    want32 = head.embed_rows(u, c)
+    want64 = head.embed_rows(u.double(), c)
+    y, op, sq = ops.project_rows(u.cuda(), c, "expmap0", "query", want_sqnorm=True)
+    y = y.cpu()
+    # tolerance: 1e-6 relative to the row norm (fp32 rounding of an HBM-bound elementwise chain)
+    scale = want32.norm(dim=1, keepdim=True).clamp_min(1e-30)
+    assert float(((y - want32).abs() / scale).max()) < 1e-6
+    # clipped rows sit on the fp32 clip sphere (eps = 4e-3), never outside the ball
+    assert float(y.norm(dim=1).max()) <= (1 - 4e-3) / c ** 0.5 * (1 + 1e-6)
+    assert torch.equal(y[0], torch.zeros(d))
+    # fp64 truth (except clipped rows, whose fp64 clip radius differs by design)
+    unclipped = want64.norm(dim=1) < (1 - 5e-3) / c ** 0.5
+    assert float(((y.double() - want64)[unclipped].abs().max())) < 1e-6
+    torch.testing.assert_close(sq.cpu(), y.pow(2).sum(1), rtol=2e-6, atol=1e-12)
+    # operand row: main columns = bf16(y), padding zero, extension = 3-way split of ||y||^2 and ones
+    kpad = ops.operand_kpad(d)
+    op = op.cpu().float()
+    assert op.shape == (777, kpad)
+    torch.testing.assert_close(op[:, :d], y.to(torch.bfloat16).float(), rtol=0, atol=0)
+    assert float(op[:, d:kpad - 16].abs().max() if kpad - 16 > d else 0.0) == 0.0
+    x1, x2, x3 = _bf16_split3(sq.cpu())
+    ext = op[:, kpad - 16:]
+    want_ext = torch.stack([x1, x1, x2, x1, x2, x3] + [torch.ones_like(x1)] * 3 + [torch.zeros_like(x1)] * 7, 1)
+    torch.testing.assert_close(ext, want_ext, rtol=0, atol=0)
+
+
+def test_gallery_operand_is_surrogate():
+    """<query operand, gallery operand> == rb_j * ||x_i - y_j||^2 up to bf16 rounding of the main columns."""
+    c, d = 1.0, 512
+    u = synth.gaussian_features(64, d, seed=1)
+    v = synth.gaussian_features(96, d, seed=0)
+    x, q_op, _ = ops.project_rows(u.cuda(), c, "expmap0", "query")
+    y, g_op, _ = ops.project_rows(v.cuda(), c, "expmap0", "gallery")
+    s = q_op.double() @ g_op.double().t()
+    xd, yd = x.double(), y.double()
+    want = torch.cdist(xd, yd).pow(2) / (1 - c * yd.pow(2).sum(1))[None]
+    # error budget: bf16 rounding of both operands on the 2*rb*<x,y> term only
+    assert float((s - want).abs().max()) < 2e-3
+    ext_only = q_op[:, -16:].double() @ g_op[:, -16:].double().t()
+    want_ext = (xd.pow(2).sum(1)[:, None] + yd.pow(2).sum(1)[None]) / (1 - c * yd.pow(2).sum(1))[None]
+    assert float(((ext_only - want_ext).abs() / want_ext).max()) < 2e-6
+
+
+def test_onball_and_cosine_modes():
+    d = 256
+    u = synth.gaussian_features(300, d, seed=5, scale=3.0)
+    x = head.embed_rows(u, 1.0)
+    y, _, _ = ops.project_rows(x.cuda(), 1.0, "onball", "query")
+    torch.testing.assert_close(y.cpu(), pmath.project(x, torch.tensor(-1.0)), rtol=1e-6, atol=1e-9)
+    raw = synth.gaussian_features(300, d, seed=6, scale=5.0)
+    raw[4] = 0.0
+    _, opq, sq = ops.project_rows(raw.cuda(), 1.0, "cosine", "query", want_point=False, want_sqnorm=True)
+    _, opg, _ = ops.project_rows(raw.cuda(), 1.0, "cosine", "gallery", want_point=False)
+    nrm = raw.norm(dim=1, keepdim=True)
+    unit = raw / torch.where(nrm == 0, torch.ones_like(nrm), nrm)
+    torch.testing.assert_close(opq.cpu().float()[:, :d], unit.to(torch.bfloat16).float(), rtol=1e-2, atol=1e-6)
+    torch.testing.assert_close(opg.cpu().float()[:, :d], -opq.cpu().float()[:, :d], rtol=0, atol=0)
+    assert float(opq.cpu().float()[:, d:].abs().max()) == 0.0
+    assert sq.cpu()[4] == 0.0 and float((sq.cpu()[5:] - 1).abs().max()) == 0.0
+
+
+def test_argument_errors():
+    with pytest.raises(RuntimeError, match="invalid argument"):
+        ops.project_rows(torch.zeros(4, 6, device="cuda"))          # d % 4 != 0
+    with pytest.raises(RuntimeError, match="invalid argument"):
+        ops.project_rows(torch.zeros(4, 64, device="cuda"), c=-1.0)
+    y, op, _ = ops.project_rows(torch.zeros(0, 64, device="cuda"))   # empty input is fine
+    assert y.shape == (0, 64) and op.shape == (0, 80)
