@@ -61,36 +61,51 @@ int64_t hypret_operand_kpad(int d);
 int hypret_project_rows(const float* u, int64_t n, int d, float c, int mode, int side, float* y32, void* op_bf16,
                         float* sqnorm, void* stream);
 
-/* Work decomposition of hypret_score_topk for a problem size on the current device. */
+/* Work decomposition of hypret_score_topk for a problem size on the current device.
+ * The gallery is swept in "strips" (query tile x contiguous gallery-tile range); a query
+ * receives one candidate list per strip that visits it.  See csrc/score_topk.cu. */
 typedef struct {
-  int32_t n_qtiles;        /* ceil(Q / 128)                                  */
-  int32_t n_gtiles;        /* ceil(N / 256)                                  */
-  int32_t n_splits;        /* gallery splits; candidate lists per query      */
-  int32_t tiles_per_split; /* gallery tiles per split                        */
-  int32_t grid;            /* persistent CTAs launched                       */
-  int32_t stages;          /* shared-memory pipeline stages                  */
-  int32_t resident;        /* 1: query tile resident in shared memory        */
-  int32_t smem_bytes;      /* dynamic shared memory per CTA                  */
+  int32_t n_qtiles;   /* T = ceil(Q / 128)                                               */
+  int32_t n_gtiles;   /* G = ceil(N / 256)                                               */
+  int32_t n_lists;    /* candidate lists (slots) per query in cand_score / cand_idx      */
+  int32_t grid;       /* P = persistent CTAs launched                                    */
+  int32_t stages;     /* shared-memory pipeline stages                                   */
+  int32_t resident;   /* 1: query tile resident in shared memory for a whole strip       */
+  int32_t smem_bytes; /* dynamic shared memory per CTA                                   */
+  int32_t n_full;     /* full waves: every CTA takes one whole gallery row of tiles      */
+  int32_t tail_rows;  /* T' = T mod P query tiles left for phase 1 / phase 2             */
+  int32_t a, b;       /* phase 1: rows < b get a+1 strips, the others a                  */
+  int32_t l1;         /* phase-1 strip length in gallery tiles                           */
+  int32_t rem_rows;   /* rows whose range [rem_g0, G) is finished in phase 2             */
+  int32_t rem_g0;
+  int32_t m, l2;      /* phase 2: m pieces per remaining row, l2 tiles each              */
+  int32_t n_steps;    /* strips a CTA walks through at most: n_full + phases             */
 } hypret_score_plan_t;
 
-int hypret_score_plan(int64_t Q, int64_t N, int d, int kprime, int n_splits_hint, hypret_score_plan_t* plan);
+/* max_ctas: 0 = one CTA per SM; >0 caps the grid (tests use it to force multi-wave schedules). */
+int hypret_score_plan(int64_t Q, int64_t N, int d, int kprime, int max_ctas, hypret_score_plan_t* plan);
+
+/* Strip of CTA `cta` at step `step` of `plan`: out4 = {query tile, first gallery tile, end gallery
+ * tile, list slot}.  Returns 1 if the CTA has work at that step, 0 if idle, <0 on bad arguments.
+ * Host-only (no GPU needed); the kernel evaluates the same closed form on the device. */
+int hypret_score_strip(const hypret_score_plan_t* plan, int cta, int step, int32_t* out4);
 
 /* Scoring GEMM + fused streaming top-k' (tcgen05 / TMEM / TMA).
  * Replaces the one-vs-all scoring loops  pmath.dist(q[1,D], G[P,D])  (src/train.py:3259)
  * and  cosine_similarity(Q, G)  (notebooks/retrieval.ipynb:368) together with the ranking
  * that follows them (np.argsort, retrieval.ipynb:383,202; torch.topk, src/auxiliary.py:374)
- * as a *candidate filter*: per query and gallery split it keeps the kprime smallest
- * bf16-operand surrogate scores.  The [Q,N] matrix is never written to memory.
+ * as a *candidate filter*: per query and strip it keeps the kprime smallest bf16-operand
+ * surrogate scores.  The [Q,N] matrix is never written to memory.
  *   q_op [Q,kpad] bf16, g_op [N,kpad] bf16   operands from hypret_project_rows
- *   cand_score [Q, n_splits, kprime] fp32 out, cand_idx same shape int32 out (-1 = empty)
- *   n_splits  must equal plan.n_splits of hypret_score_plan(Q, N, d, kprime, hint)
+ *   cand_score [Q, n_lists, kprime] fp32 out, cand_idx same shape int32 out (-1 = empty)
+ *   n_lists   must equal plan.n_lists of hypret_score_plan(Q, N, d, kprime, max_ctas)
  *   debug_scores  NULL, or [Q,N] fp32 that receives every surrogate score (tests only)
  * 1 <= kprime <= 32. */
-int hypret_score_topk(const void* q_op, int64_t Q, const void* g_op, int64_t N, int d, int kprime, int n_splits,
-                      float* cand_score, int32_t* cand_idx, float* debug_scores, void* stream);
+int hypret_score_topk(const void* q_op, int64_t Q, const void* g_op, int64_t N, int d, int kprime, int n_lists,
+                      int max_ctas, float* cand_score, int32_t* cand_idx, float* debug_scores, void* stream);
 
 /* Candidate merge + exact rerank.  For each query: keep the kprime best of its
- * n_splits*kprime candidates by surrogate score, recompute their distance exactly from the
+ * n_lists*kprime candidates by surrogate score, recompute their distance exactly from the
  * fp32 rows (differences formed explicitly, fp64 accumulation, arccosh closed form ==
  * pmath.dist, src/train.py:3259; or the cosine similarity, retrieval.ipynb:368), sort
  * (ascending distance / descending similarity, ties -> lower index) and emit the first k.
@@ -99,8 +114,17 @@ int hypret_score_topk(const void* q_op, int64_t Q, const void* g_op, int64_t N, 
  *   out_margin [Q] fp32 or NULL: (worst kept surrogate) - (exact surrogate of the k-th result)
  * 1 <= k <= kprime <= 32. */
 int hypret_rerank(const float* q32, const float* g32, int64_t Q, int64_t N, int d, float c, int metric,
-                  const float* cand_score, const int32_t* cand_idx, int n_splits, int kprime, int k,
+                  const float* cand_score, const int32_t* cand_idx, int n_lists, int kprime, int k,
                   int64_t idx_offset, float* out_score, int64_t* out_idx, float* out_margin, void* stream);
+
+/* Multi-GPU exchange step: merge the per-shard top-k lists of every query (after an
+ * all-gather of [Q,k] scores + global indices) into the global top-k, with the ordering of the
+ * reference's single-device ranking (notebooks/retrieval.ipynb:383, src/auxiliary.py:374):
+ * ascending (descending != 0: descending) score, ties -> lower index.
+ *   scores [n_shards, Q, k] fp32, idx [n_shards, Q, k] int64 (-1 = empty)
+ *   out_score [Q,k], out_idx [Q,k];  n_shards * k <= 256. */
+int hypret_merge_topk(const float* scores, const int64_t* idx, int n_shards, int64_t Q, int k, int descending,
+                      float* out_score, int64_t* out_idx, void* stream);
 
 #ifdef __cplusplus
 }

@@ -18,12 +18,21 @@ class ScorePlan(Structure):
     _fields_ = [
         ("n_qtiles", c_int32),
         ("n_gtiles", c_int32),
-        ("n_splits", c_int32),
-        ("tiles_per_split", c_int32),
+        ("n_lists", c_int32),
         ("grid", c_int32),
         ("stages", c_int32),
         ("resident", c_int32),
         ("smem_bytes", c_int32),
+        ("n_full", c_int32),
+        ("tail_rows", c_int32),
+        ("a", c_int32),
+        ("b", c_int32),
+        ("l1", c_int32),
+        ("rem_rows", c_int32),
+        ("rem_g0", c_int32),
+        ("m", c_int32),
+        ("l2", c_int32),
+        ("n_steps", c_int32),
     ]
 
     def asdict(self):
@@ -38,10 +47,12 @@ SIGNATURES = {
     "hypret_project_rows": (c_int, [c_void_p, c_int64, c_int, c_float, c_int, c_int, c_void_p, c_void_p, c_void_p,
                                     c_void_p]),
     "hypret_score_plan": (c_int, [c_int64, c_int64, c_int, c_int, c_int, POINTER(ScorePlan)]),
-    "hypret_score_topk": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int, c_int, c_int, c_void_p, c_void_p,
-                                  c_void_p, c_void_p]),
+    "hypret_score_strip": (c_int, [POINTER(ScorePlan), c_int, c_int, POINTER(c_int32)]),
+    "hypret_score_topk": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int, c_int, c_int, c_int, c_void_p,
+                                  c_void_p, c_void_p, c_void_p]),
     "hypret_rerank": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int, c_float, c_int, c_void_p, c_void_p, c_int,
                               c_int, c_int, c_int64, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "hypret_merge_topk": (c_int, [c_void_p, c_void_p, c_int, c_int64, c_int, c_int, c_void_p, c_void_p, c_void_p]),
 }
 
 

@@ -49,32 +49,43 @@ int hypret_project_rows(const float* u, int64_t n, int d, float c, int mode, int
   return hypret_launch_project_rows(u, n, d, c, mode, side, y32, op_bf16, sqnorm, static_cast<cudaStream_t>(stream));
 }
 
-int hypret_score_topk(const void* q_op, int64_t Q, const void* g_op, int64_t N, int d, int kprime, int n_splits,
-                      float* cand_score, int32_t* cand_idx, float* debug_scores, void* stream) {
+int hypret_score_topk(const void* q_op, int64_t Q, const void* g_op, int64_t N, int d, int kprime, int n_lists,
+                      int max_ctas, float* cand_score, int32_t* cand_idx, float* debug_scores, void* stream) {
   if (Q < 1 || N < 1 || d < 4 || (d & 3) || d > 2048) return HYPRET_EINVAL;
-  if (kprime < 1 || kprime > 32 || n_splits < 1) return HYPRET_EINVAL;
+  if (kprime < 1 || kprime > 32 || n_lists < 1 || max_ctas < 0) return HYPRET_EINVAL;
   if (q_op == nullptr || g_op == nullptr || cand_score == nullptr || cand_idx == nullptr) return HYPRET_EINVAL;
   int rc = check_device();
   if (rc != HYPRET_OK) return rc;
-  return hypret_launch_score_topk(q_op, Q, g_op, N, d, kprime, n_splits, cand_score, cand_idx, debug_scores,
-                                  static_cast<cudaStream_t>(stream));
+  return hypret_launch_score_topk(q_op, Q, g_op, N, d, kprime, n_lists, max_ctas, cand_score, cand_idx,
+                                  debug_scores, static_cast<cudaStream_t>(stream));
 }
 
 int hypret_rerank(const float* q32, const float* g32, int64_t Q, int64_t N, int d, float c, int metric,
-                  const float* cand_score, const int32_t* cand_idx, int n_splits, int kprime, int k,
+                  const float* cand_score, const int32_t* cand_idx, int n_lists, int kprime, int k,
                   int64_t idx_offset, float* out_score, int64_t* out_idx, float* out_margin, void* stream) {
   if (Q < 0 || N < 1 || d < 4 || (d & 3)) return HYPRET_EINVAL;
   if (metric != HYPRET_METRIC_COSINE && metric != HYPRET_METRIC_HYPERBOLIC) return HYPRET_EINVAL;
   if (metric == HYPRET_METRIC_HYPERBOLIC && !(c > 0.f)) return HYPRET_EINVAL;
-  if (kprime < 1 || kprime > 32 || k < 1 || k > kprime || n_splits < 1) return HYPRET_EINVAL;
+  if (kprime < 1 || kprime > 32 || k < 1 || k > kprime || n_lists < 1) return HYPRET_EINVAL;
   if (Q == 0) return HYPRET_OK;
   if (q32 == nullptr || g32 == nullptr || cand_score == nullptr || cand_idx == nullptr || out_score == nullptr ||
       out_idx == nullptr || !aligned16(q32) || !aligned16(g32))
     return HYPRET_EINVAL;
   int rc = check_device();
   if (rc != HYPRET_OK) return rc;
-  return hypret_launch_rerank(q32, g32, Q, N, d, c, metric, cand_score, cand_idx, n_splits * kprime, kprime, k,
+  return hypret_launch_rerank(q32, g32, Q, N, d, c, metric, cand_score, cand_idx, n_lists * kprime, kprime, k,
                               idx_offset, out_score, out_idx, out_margin, static_cast<cudaStream_t>(stream));
+}
+
+int hypret_merge_topk(const float* scores, const int64_t* idx, int n_shards, int64_t Q, int k, int descending,
+                      float* out_score, int64_t* out_idx, void* stream) {
+  if (n_shards < 1 || Q < 0 || k < 1 || k > 32 || n_shards * k > 256) return HYPRET_EINVAL;
+  if (Q == 0) return HYPRET_OK;
+  if (scores == nullptr || idx == nullptr || out_score == nullptr || out_idx == nullptr) return HYPRET_EINVAL;
+  int rc = check_device();
+  if (rc != HYPRET_OK) return rc;
+  return hypret_launch_merge_topk(scores, idx, n_shards, Q, k, descending != 0, out_score, out_idx,
+                                  static_cast<cudaStream_t>(stream));
 }
 
 }  // extern "C"

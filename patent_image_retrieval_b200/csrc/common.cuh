@@ -160,6 +160,19 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
                : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// Same wait, but with the 32 destination registers of a preceding tmem_ld_32x32 tied to the
+// statement as in/out operands: no consumer of v[] can be scheduled above the wait.
+__device__ __forceinline__ void tmem_ld_wait(float (&v)[32]) {
+  uint32_t* r = reinterpret_cast<uint32_t*>(v);
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+                 "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]),
+                 "+r"(r[16]), "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]),
+                 "+r"(r[23]), "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]),
+                 "+r"(r[30]), "+r"(r[31])
+               :
+               : "memory");
+}
 
 // 32 lanes x 32 consecutive fp32 columns: thread t of the warp receives row (lane base + t).
 __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, float (&v)[32]) {
@@ -218,9 +231,11 @@ __device__ __forceinline__ double warp_sum(double v) {
 int hypret_launch_project_rows(const float* u, int64_t n, int d, float c, int mode, int side, float* y32,
                                void* op_bf16, float* sqnorm, cudaStream_t stream);
 int hypret_launch_score_topk(const void* q_op, int64_t Q, const void* g_op, int64_t N, int d, int kprime,
-                             int n_splits, float* cand_score, int32_t* cand_idx, float* debug_scores,
+                             int n_lists, int max_ctas, float* cand_score, int32_t* cand_idx, float* debug_scores,
                              cudaStream_t stream);
 int hypret_launch_rerank(const float* q32, const float* g32, int64_t Q, int64_t N, int d, float c, int metric,
                          const float* cand_score, const int32_t* cand_idx, int n_cand, int kprime, int k,
                          int64_t idx_offset, float* out_score, int64_t* out_idx, float* out_margin,
                          cudaStream_t stream);
+int hypret_launch_merge_topk(const float* scores, const int64_t* idx, int W, int64_t Q, int k, int descending,
+                             float* out_score, int64_t* out_idx, cudaStream_t stream);

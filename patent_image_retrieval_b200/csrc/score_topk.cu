@@ -6,23 +6,36 @@
 //   np.argsort / torch.topk               retrieval.ipynb:383,202 ; src/auxiliary.py:374
 // as a candidate filter: S[i,j] = <q_op[i,:], g_op[j,:]> is the ranking surrogate built by
 // project.cu (rb_j * ||x_i - y_j||^2 for the Poincare ball, -cos for cosine); per query the
-// kernel keeps the k' smallest S per gallery split.  S lives only in TMEM and registers.
+// kernel keeps the k' smallest S of every gallery strip it visits.  S lives only in TMEM and
+// registers.
 //
 // Structure (one persistent CTA per SM, 192 threads, warp-specialised):
 //   warp 0   TMA producer   gallery K-blocks (256 rows x 64 bf16, 128B swizzle) into a
-//                           shared-memory ring; the 128-row query tile is loaded ONCE per work
-//                           item and stays resident in shared memory when D <= 512 (RESIDENT),
+//                           shared-memory ring; the 128-row query tile is loaded ONCE per strip
+//                           and stays resident in shared memory when D <= 512 (RESIDENT),
 //                           otherwise it streams through the ring next to the gallery block
 //   warp 1   MMA issuer     one thread issues tcgen05.mma (M=128, N=256, K=16, bf16 -> fp32)
 //                           into one of two 256-column TMEM accumulators; tcgen05.commit
 //                           releases ring stages and publishes finished accumulators
-//   warps 2-5 epilogue      tcgen05.ld 32x32b: thread t owns query row t of the tile, so the
-//                           running top-k' of a query is thread-private: register threshold,
-//                           min-tree fast reject, rare insert into a per-thread list in
-//                           shared memory (conflict-free [slot][thread] layout)
-// Work item = (query tile, gallery split); items are ordered split-major and dealt
-// round-robin so the CTAs that run concurrently stream the SAME gallery range through L2
-// (the gallery is read from HBM about once per pass instead of once per query tile).
+//   warps 2-5 epilogue      tcgen05.ld 32x32b: lane t of a warp owns query row t of its TMEM
+//                           quadrant, so the running k'-th best score of a query is a private
+//                           register.  Fast path: 3-input min tree + one ballot per 32 columns.
+//                           Slow path (rare): the warp inserts cooperatively -- the owner lane
+//                           overwrites its worst slot in shared memory, all lanes re-read the
+//                           row's slots (one word each) and a single redux.max finds the new
+//                           threshold.
+//
+// Strip schedule.  Work unit = (query tile, contiguous range of gallery tiles) = "strip"; a
+// strip owns one candidate list per query row, so every strip start is a cold threshold and a
+// cold list.  With T query tiles, G gallery tiles and P CTAs:
+//   * full waves   while >= P query tiles remain, every CTA takes one whole row (strip = G);
+//   * phase 1      the T' < P remaining rows get a = P / T' strips each (the first b = P % T'
+//                  rows one more), all of length L1 = ceil(G/(a+1)) -- exactly P strips;
+//   * phase 2      rows with only `a` strips still miss [a*L1, G); that remainder is cut into
+//                  m = P / (T'-b) pieces per row so that again (almost) every CTA is busy.
+// CTAs with consecutive ids run the same gallery range at the same time (lock-step through
+// L2: the gallery is read from HBM about once per phase instead of once per query tile), the
+// load balance is within one small piece, and a query sees only a handful of cold starts.
 #include <cuda.h>
 #include <math.h>
 
@@ -43,6 +56,92 @@ constexpr int NUM_EPI_THREADS = 128;
 constexpr int MAX_STAGES = 8;
 constexpr int SMEM_LIMIT = 232448;                        // 227 KB opt-in maximum per CTA
 constexpr int BAR_BYTES = 256;
+constexpr int MIN_STRIP_TILES = 4;                        // do not spread tiny problems over all SMs
+constexpr unsigned FULL = 0xffffffffu;
+
+struct Sched {
+  int T, G, P;
+  int n_full, tail_rows, a, b, L1, rem_rows, rem_g0, m, L2, n_steps, n_lists;
+};
+
+__host__ __device__ inline bool strip_at(const Sched& s, int cta, int step, int& qt, int& g0, int& g1, int& slot) {
+  if (step < s.n_full) {
+    qt = step * s.P + cta;
+    g0 = 0;
+    g1 = s.G;
+    slot = 0;
+    return true;
+  }
+  step -= s.n_full;
+  if (s.tail_rows == 0) return false;
+  const int row0 = s.n_full * s.P;
+  if (step == 0) {
+    int j, row;
+    if (cta < s.a * s.tail_rows) {
+      j = cta / s.tail_rows;
+      row = cta - j * s.tail_rows;
+    } else {
+      j = s.a;
+      row = cta - s.a * s.tail_rows;
+      if (row >= s.b) return false;
+    }
+    qt = row0 + row;
+    g0 = j * s.L1;
+    g1 = g0 + s.L1 < s.G ? g0 + s.L1 : s.G;
+    slot = j;
+    return g0 < g1;
+  }
+  if (step == 1 && s.rem_rows > 0) {
+    if (cta >= s.m * s.rem_rows) return false;
+    const int e = cta / s.rem_rows;
+    const int row = s.b + (cta - e * s.rem_rows);
+    qt = row0 + row;
+    g0 = s.rem_g0 + e * s.L2;
+    g1 = g0 + s.L2 < s.G ? g0 + s.L2 : s.G;
+    slot = s.a + e;
+    return g0 < g1;
+  }
+  return false;
+}
+
+Sched make_sched(int64_t T, int64_t G, int sms, int max_ctas) {
+  Sched s{};
+  int64_t P = sms;
+  if (max_ctas > 0 && max_ctas < P) P = max_ctas;
+  int64_t cap = (T * G) / MIN_STRIP_TILES;
+  if (cap < 1) cap = 1;
+  if (cap < P) P = cap;
+  s.T = (int)T;
+  s.G = (int)G;
+  s.P = (int)P;
+  s.n_full = (int)(T / P);
+  s.tail_rows = (int)(T % P);
+  s.n_lists = 1;
+  s.n_steps = s.n_full;
+  if (s.tail_rows > 0) {
+    s.a = s.P / s.tail_rows;
+    s.b = s.P % s.tail_rows;
+    if (s.b == 0) {
+      s.L1 = (int)((G + s.a - 1) / s.a);
+      s.n_lists = s.a;
+    } else {
+      s.L1 = (int)((G + s.a) / (s.a + 1));
+      s.n_lists = s.a + 1;
+      s.rem_g0 = s.a * s.L1;
+      if (s.rem_g0 < G) {
+        s.rem_rows = s.tail_rows - s.b;
+        s.m = s.P / s.rem_rows;
+        if (s.m < 1) s.m = 1;
+        const int rem = (int)G - s.rem_g0;
+        if (s.m > rem) s.m = rem;
+        s.L2 = (rem + s.m - 1) / s.m;
+        if (s.a + s.m > s.n_lists) s.n_lists = s.a + s.m;
+      }
+    }
+    s.n_steps += 1 + (s.rem_rows > 0 ? 1 : 0);
+  }
+  return s;
+}
 
 struct Params {
   int64_t Q;
@@ -50,13 +149,13 @@ struct Params {
   int kb_main;          // number of 64-wide K blocks (Dpad / 64)
   int has_ext;          // 1: extension K block present (hyperbolic surrogate constants)
   int dpad;
-  int n_qtiles, n_gtiles, n_splits, tiles_per_split, n_items;
   int kprime;
   int stages;
   int stage_bytes;
   int ring_off;         // byte offsets from the 1024-aligned shared-memory base
   int lists_off;
   int bar_off;
+  Sched sched;
   float* cand_score;
   int32_t* cand_idx;
   float* debug_scores;
@@ -73,7 +172,60 @@ struct Barriers {
 };
 static_assert(sizeof(Barriers) <= BAR_BYTES, "barrier block too large");
 
-template <bool RESIDENT>
+// monotone float <-> uint32 map so that redux.max on the keys is a float max
+__device__ __forceinline__ uint32_t f2key(float x) {
+  const uint32_t u = __float_as_uint(x);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float key2f(uint32_t k) {
+  return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
+}
+
+// One 32-column chunk of the accumulator: fast reject, else warp-cooperative inserts.
+template <int KPP>
+__device__ __forceinline__ void process_chunk(const float (&v)[32], int64_t cbase, int64_t N, int lane, float& thr,
+                                              int& maxpos, float* ls_q, int* li_q) {
+  float mg[4];
+#pragma unroll
+  for (int g = 0; g < 4; ++g) {
+    float m = v[g * 8];
+#pragma unroll
+    for (int j = 1; j < 8; ++j) m = fminf(m, v[g * 8 + j]);
+    mg[g] = m;
+  }
+  const float m = fminf(fminf(mg[0], mg[1]), fminf(mg[2], mg[3]));
+  if (__ballot_sync(FULL, m < thr) == 0u) return;   // warp-uniform fast reject
+#pragma unroll
+  for (int g = 0; g < 4; ++g) {
+    if (__ballot_sync(FULL, mg[g] < thr) == 0u) continue;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float x = v[g * 8 + j];
+      const int64_t col = cbase + g * 8 + j;
+      unsigned hb = __ballot_sync(FULL, x < thr && col < N);
+      while (hb) {
+        const int L = __ffs(hb) - 1;       // warp-uniform: lane (= row of this quadrant) that inserts
+        hb &= hb - 1;
+        float* lr = ls_q + L * KPP;
+        if (lane == L) {                   // the owner replaces its current worst slot
+          lr[maxpos] = x;
+          li_q[L * KPP + maxpos] = (int)col;
+        }
+        __syncwarp();
+        const float y = (lane < KPP) ? lr[lane] : -INFINITY;
+        const uint32_t key = f2key(y);
+        const uint32_t mx = __reduce_max_sync(FULL, key);          // new k'-th best of row L
+        const int pos = __ffs(__ballot_sync(FULL, key == mx)) - 1;
+        if (lane == L) {
+          thr = key2f(mx);
+          maxpos = pos;
+        }
+      }
+    }
+  }
+}
+
+template <bool RESIDENT, int KPP>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 score_topk_kernel(const __grid_constant__ CUtensorMap map_q_main, const __grid_constant__ CUtensorMap map_q_ext,
                   const __grid_constant__ CUtensorMap map_g_main, const __grid_constant__ CUtensorMap map_g_ext,
@@ -83,14 +235,16 @@ score_topk_kernel(const __grid_constant__ CUtensorMap map_q_main, const __grid_c
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* a_res = smem;                                   // RESIDENT: kb_main blocks + ext block
   uint8_t* ring = smem + p.ring_off;
-  float* list_s = reinterpret_cast<float*>(smem + p.lists_off);
-  int* list_i = reinterpret_cast<int*>(list_s + p.kprime * TILE_M);
+  float* list_s = reinterpret_cast<float*>(smem + p.lists_off);   // [128 rows][KPP slots]
+  int* list_i = reinterpret_cast<int*>(list_s + KPP * TILE_M);
   Barriers* bars = reinterpret_cast<Barriers*>(smem + p.bar_off);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int KB = p.kb_main;
   const int KSTEPS = KB + (p.has_ext ? 1 : 0);
+  const Sched& sc = p.sched;
+  const int cta = blockIdx.x;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&map_q_main);
@@ -121,17 +275,16 @@ score_topk_kernel(const __grid_constant__ CUtensorMap map_q_main, const __grid_c
     // ======================================================================= TMA producer
     if (lane == 0) {
       uint32_t stage = 0, phase = 0, a_par = 0;
-      int it = 0;
-      for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++it) {
-        const int split = item / p.n_qtiles;
-        const int qt = item - split * p.n_qtiles;
-        const int gt0 = split * p.tiles_per_split;
-        const int gt1 = min(p.n_gtiles, gt0 + p.tiles_per_split);
+      bool first = true;
+      for (int step = 0; step < sc.n_steps; ++step) {
+        int qt, gt0, gt1, slot;
+        if (!strip_at(sc, cta, step, qt, gt0, gt1, slot)) continue;
         if (RESIDENT) {
-          if (it > 0) {  // the previous item's MMAs must be done reading the resident tile
+          if (!first) {  // the previous strip's MMAs must be done reading the resident tile
             mbar_wait(&bars->a_empty, a_par);
             a_par ^= 1;
           }
+          first = false;
           mbar_arrive_expect_tx(&bars->a_full, KB * A_BLK_BYTES + (p.has_ext ? A_EXT_BYTES : 0));
           for (int kb = 0; kb < KB; ++kb)
             tma_load_2d_hint(a_res + kb * A_BLK_BYTES, &map_q_main, &bars->a_full, kb * HYPRET_KBLK, qt * TILE_M,
@@ -169,10 +322,9 @@ score_topk_kernel(const __grid_constant__ CUtensorMap map_q_main, const __grid_c
     if (lane == 0) {
       constexpr uint32_t idesc = umma_idesc_bf16(TILE_M, TILE_N);
       uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0, a_par = 0;
-      for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
-        const int split = item / p.n_qtiles;
-        const int gt0 = split * p.tiles_per_split;
-        const int gt1 = min(p.n_gtiles, gt0 + p.tiles_per_split);
+      for (int step = 0; step < sc.n_steps; ++step) {
+        int qt, gt0, gt1, slot;
+        if (!strip_at(sc, cta, step, qt, gt0, gt1, slot)) continue;
         if (RESIDENT) {
           mbar_wait(&bars->a_full, a_par);
           a_par ^= 1;
@@ -215,72 +367,66 @@ score_topk_kernel(const __grid_constant__ CUtensorMap map_q_main, const __grid_c
   } else {
     // ======================================================================= epilogue / top-k'
     const int quad = warp & 3;                 // TMEM lane quadrant this warp may read
-    const int row = quad * 32 + lane;          // query row inside the tile == TMEM lane
-    float* ls = list_s + row;                  // [slot][thread] layout: stride TILE_M
-    int* li = list_i + row;
+    float* ls_q = list_s + quad * 32 * KPP;    // this warp's 32 rows, KPP slots each
+    int* li_q = list_i + quad * 32 * KPP;
     const int KP = p.kprime;
     const int64_t N = p.N;
     uint32_t acc = 0, acc_phase = 0;
-    for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
-      const int split = item / p.n_qtiles;
-      const int qt = item - split * p.n_qtiles;
-      const int gt0 = split * p.tiles_per_split;
-      const int gt1 = min(p.n_gtiles, gt0 + p.tiles_per_split);
-      const int64_t qrow = (int64_t)qt * TILE_M + row;
+    for (int step = 0; step < sc.n_steps; ++step) {
+      int qt, gt0, gt1, slot;
+      if (!strip_at(sc, cta, step, qt, gt0, gt1, slot)) continue;
+      const int64_t qrow = (int64_t)qt * TILE_M + quad * 32 + lane;
+      // cold lists: active slots +inf (threshold stays +inf until k' scores are in),
+      // inactive slots -inf (never the maximum)
       float thr = INFINITY;
       int maxpos = 0;
-      for (int s = 0; s < KP; ++s) {
-        ls[s * TILE_M] = INFINITY;
-        li[s * TILE_M] = -1;
+#pragma unroll
+      for (int s = 0; s < KPP; ++s) {
+        ls_q[lane * KPP + s] = (s < KP) ? INFINITY : -INFINITY;
+        li_q[lane * KPP + s] = -1;
       }
+      __syncwarp();
       for (int gt = gt0; gt < gt1; ++gt) {
         mbar_wait(&bars->tmem_full[acc], acc_phase);
         tcgen05_fence_after();
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * TILE_N;
         const int64_t col0 = (int64_t)gt * TILE_N;
+        float va[32], vb[32];
+        tmem_ld_32x32(taddr, va);
 #pragma unroll 1
-        for (int cc = 0; cc < TILE_N / 32; ++cc) {
-          float v[32];
-          tmem_ld_32x32(taddr + cc * 32, v);
-          tmem_ld_wait();
-          const int64_t cbase = col0 + cc * 32;
+        for (int cc = 0; cc < TILE_N / 32; cc += 2) {
+          tmem_ld_wait(va);
+          tmem_ld_32x32(taddr + (cc + 1) * 32, vb);           // next chunk in flight while this one is scanned
           if (p.debug_scores != nullptr && qrow < p.Q) {
 #pragma unroll
             for (int j = 0; j < 32; ++j)
-              if (cbase + j < N) p.debug_scores[qrow * N + cbase + j] = v[j];
+              if (col0 + cc * 32 + j < N) p.debug_scores[qrow * N + col0 + cc * 32 + j] = va[j];
           }
-          float m = v[0];
+          process_chunk<KPP>(va, col0 + cc * 32, N, lane, thr, maxpos, ls_q, li_q);
+          tmem_ld_wait(vb);
+          if (cc + 2 < TILE_N / 32) tmem_ld_32x32(taddr + (cc + 2) * 32, va);
+          if (p.debug_scores != nullptr && qrow < p.Q) {
 #pragma unroll
-          for (int j = 1; j < 32; ++j) m = fminf(m, v[j]);
-          if (m < thr) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              if (v[j] < thr && cbase + j < N) {
-                ls[maxpos * TILE_M] = v[j];
-                li[maxpos * TILE_M] = static_cast<int>(cbase + j);
-                float mx = -INFINITY;
-                int mp = 0;
-                for (int s = 0; s < KP; ++s) {
-                  const float x = ls[s * TILE_M];
-                  if (x > mx) { mx = x; mp = s; }
-                }
-                thr = mx;
-                maxpos = mp;
-              }
-            }
+            for (int j = 0; j < 32; ++j)
+              if (col0 + (cc + 1) * 32 + j < N) p.debug_scores[qrow * N + col0 + (cc + 1) * 32 + j] = vb[j];
           }
+          process_chunk<KPP>(vb, col0 + (cc + 1) * 32, N, lane, thr, maxpos, ls_q, li_q);
         }
         tcgen05_fence_before();
         mbar_arrive(&bars->tmem_empty[acc]);
         if (++acc == NUM_ACC) { acc = 0; acc_phase ^= 1; }
       }
-      if (qrow < p.Q) {
-        const int64_t base = (qrow * p.n_splits + split) * KP;
-        for (int s = 0; s < KP; ++s) {
-          p.cand_score[base + s] = ls[s * TILE_M];
-          p.cand_idx[base + s] = li[s * TILE_M];
+      // publish this strip's lists: one coalesced row of k' entries per query
+      __syncwarp();
+      for (int r = 0; r < 32; ++r) {
+        const int64_t qr = (int64_t)qt * TILE_M + quad * 32 + r;
+        if (qr < p.Q && lane < KP) {
+          const int64_t o = (qr * sc.n_lists + slot) * KP + lane;
+          p.cand_score[o] = ls_q[r * KPP + lane];
+          p.cand_idx[o] = li_q[r * KPP + lane];
         }
       }
+      __syncwarp();
     }
   }
 
@@ -331,11 +477,33 @@ int device_sms() {
   return sms;
 }
 
+Sched sched_from_plan(const hypret_score_plan_t& pl) {
+  Sched s{};
+  s.T = pl.n_qtiles; s.G = pl.n_gtiles; s.P = pl.grid;
+  s.n_full = pl.n_full; s.tail_rows = pl.tail_rows; s.a = pl.a; s.b = pl.b; s.L1 = pl.l1;
+  s.rem_rows = pl.rem_rows; s.rem_g0 = pl.rem_g0; s.m = pl.m; s.L2 = pl.l2; s.n_steps = pl.n_steps;
+  s.n_lists = pl.n_lists;
+  return s;
+}
+
+int kpp_of(int kprime) { return kprime <= 16 ? 16 : 32; }
+
+template <bool RESIDENT, int KPP>
+int launch_variant(const hypret_score_plan_t& plan, const CUtensorMap& mq_main, const CUtensorMap& mq_ext,
+                   const CUtensorMap& mg_main, const CUtensorMap& mg_ext, const Params& p, cudaStream_t stream) {
+  cudaError_t e = cudaFuncSetAttribute(score_topk_kernel<RESIDENT, KPP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       plan.smem_bytes);
+  if (e != cudaSuccess) return (int)e;
+  score_topk_kernel<RESIDENT, KPP><<<plan.grid, NUM_THREADS, plan.smem_bytes, stream>>>(mq_main, mq_ext, mg_main,
+                                                                                       mg_ext, p);
+  return (int)cudaGetLastError();
+}
+
 }  // namespace
 
-extern "C" int hypret_score_plan(int64_t Q, int64_t N, int d, int kprime, int n_splits_hint,
+extern "C" int hypret_score_plan(int64_t Q, int64_t N, int d, int kprime, int max_ctas,
                                  hypret_score_plan_t* plan) {
-  if (plan == nullptr || Q < 1 || N < 1 || d < 1 || kprime < 1 || kprime > 32) return HYPRET_EINVAL;
+  if (plan == nullptr || Q < 1 || N < 1 || d < 1 || kprime < 1 || kprime > 32 || max_ctas < 0) return HYPRET_EINVAL;
   if (N > 0x7fffffffll - TILE_N) return HYPRET_EUNSUPPORTED;   // int32 candidate indices per shard
   const int sms = device_sms();
   const int kb = hypret_dpad(d) / HYPRET_KBLK;
@@ -344,7 +512,7 @@ extern "C" int hypret_score_plan(int64_t Q, int64_t N, int d, int kprime, int n_
   if (n_qtiles > (1 << 24)) return HYPRET_EUNSUPPORTED;
 
   // shared-memory carve-up
-  const int lists = kprime * TILE_M * 8;
+  const int lists = kpp_of(kprime) * TILE_M * 8;
   const int a_res_bytes = kb * A_BLK_BYTES + A_EXT_BYTES;
   int resident = 0, stages = 0, stage_bytes = 0;
   {
@@ -360,45 +528,44 @@ extern "C" int hypret_score_plan(int64_t Q, int64_t N, int d, int kprime, int n_
     if (stages > MAX_STAGES) stages = MAX_STAGES;
     if (stages < 2) return HYPRET_EUNSUPPORTED;
   }
-
-  // gallery splits: minimise (waves) x (tiles per item + fixed per-item cost)
-  int64_t best_s = 1, best_tps = n_gtiles;
-  if (n_splits_hint > 0) {
-    int64_t s = n_splits_hint < n_gtiles ? n_splits_hint : n_gtiles;
-    best_tps = (n_gtiles + s - 1) / s;
-    best_s = (n_gtiles + best_tps - 1) / best_tps;
-  } else {
-    double best_cost = 1e300;
-    const int64_t smax = n_gtiles < 64 ? n_gtiles : 64;
-    for (int64_t s = 1; s <= smax; ++s) {
-      const int64_t tps = (n_gtiles + s - 1) / s;
-      const int64_t s2 = (n_gtiles + tps - 1) / tps;
-      const int64_t items = n_qtiles * s2;
-      const int64_t waves = (items + sms - 1) / sms;
-      const double cost = (double)waves * ((double)tps + 3.0) + 0.02 * (double)s2;
-      if (cost < best_cost) { best_cost = cost; best_s = s2; best_tps = tps; }
-    }
-  }
-  const int64_t items = n_qtiles * best_s;
-  if (items > 0x7fffffffll) return HYPRET_EUNSUPPORTED;
+  const Sched s = make_sched(n_qtiles, n_gtiles, sms, max_ctas);
   plan->n_qtiles = (int32_t)n_qtiles;
   plan->n_gtiles = (int32_t)n_gtiles;
-  plan->n_splits = (int32_t)best_s;
-  plan->tiles_per_split = (int32_t)best_tps;
-  plan->grid = (int32_t)(items < sms ? items : sms);
+  plan->n_lists = s.n_lists;
+  plan->grid = s.P;
   plan->stages = stages;
   plan->resident = resident;
   plan->smem_bytes = 1024 + (resident ? a_res_bytes : 0) + stages * stage_bytes + lists + BAR_BYTES;
+  plan->n_full = s.n_full;
+  plan->tail_rows = s.tail_rows;
+  plan->a = s.a;
+  plan->b = s.b;
+  plan->l1 = s.L1;
+  plan->rem_rows = s.rem_rows;
+  plan->rem_g0 = s.rem_g0;
+  plan->m = s.m;
+  plan->l2 = s.L2;
+  plan->n_steps = s.n_steps;
   return HYPRET_OK;
 }
 
+extern "C" int hypret_score_strip(const hypret_score_plan_t* plan, int cta, int step, int32_t* out4) {
+  if (plan == nullptr || out4 == nullptr || cta < 0 || cta >= plan->grid || step < 0 || step >= plan->n_steps)
+    return HYPRET_EINVAL;
+  const Sched s = sched_from_plan(*plan);
+  int qt = 0, g0 = 0, g1 = 0, slot = 0;
+  const bool ok = strip_at(s, cta, step, qt, g0, g1, slot);
+  out4[0] = qt; out4[1] = g0; out4[2] = g1; out4[3] = slot;
+  return ok ? 1 : 0;
+}
+
 int hypret_launch_score_topk(const void* q_op, int64_t Q, const void* g_op, int64_t N, int d, int kprime,
-                             int n_splits, float* cand_score, int32_t* cand_idx, float* debug_scores,
+                             int n_lists, int max_ctas, float* cand_score, int32_t* cand_idx, float* debug_scores,
                              cudaStream_t stream) {
   hypret_score_plan_t plan;
-  int rc = hypret_score_plan(Q, N, d, kprime, n_splits, &plan);
+  int rc = hypret_score_plan(Q, N, d, kprime, max_ctas, &plan);
   if (rc != HYPRET_OK) return rc;
-  if (plan.n_splits != n_splits) return HYPRET_EINVAL;   // caller sized cand_* for a different plan
+  if (plan.n_lists != n_lists) return HYPRET_EINVAL;   // caller sized cand_* for a different plan
   if ((reinterpret_cast<uintptr_t>(q_op) & 15) || (reinterpret_cast<uintptr_t>(g_op) & 15)) return HYPRET_EINVAL;
 
   const int dpad = hypret_dpad(d);
@@ -415,30 +582,25 @@ int hypret_launch_score_topk(const void* q_op, int64_t Q, const void* g_op, int6
   p.kb_main = dpad / HYPRET_KBLK;
   p.has_ext = 1;
   p.dpad = dpad;
-  p.n_qtiles = plan.n_qtiles;
-  p.n_gtiles = plan.n_gtiles;
-  p.n_splits = plan.n_splits;
-  p.tiles_per_split = plan.tiles_per_split;
-  p.n_items = plan.n_qtiles * plan.n_splits;
   p.kprime = kprime;
   p.stages = plan.stages;
   p.stage_bytes = plan.resident ? B_BLK_BYTES : A_BLK_BYTES + B_BLK_BYTES;
   p.ring_off = plan.resident ? p.kb_main * A_BLK_BYTES + A_EXT_BYTES : 0;
   p.lists_off = p.ring_off + plan.stages * p.stage_bytes;
-  p.bar_off = p.lists_off + kprime * TILE_M * 8;
+  p.bar_off = p.lists_off + kpp_of(kprime) * TILE_M * 8;
+  p.sched = sched_from_plan(plan);
   p.cand_score = cand_score;
   p.cand_idx = cand_idx;
   p.debug_scores = debug_scores;
 
-  cudaError_t e;
-  if (plan.resident) {
-    e = cudaFuncSetAttribute(score_topk_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, plan.smem_bytes);
-    if (e != cudaSuccess) return (int)e;
-    score_topk_kernel<true><<<plan.grid, NUM_THREADS, plan.smem_bytes, stream>>>(mq_main, mq_ext, mg_main, mg_ext, p);
-  } else {
-    e = cudaFuncSetAttribute(score_topk_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, plan.smem_bytes);
-    if (e != cudaSuccess) return (int)e;
-    score_topk_kernel<false><<<plan.grid, NUM_THREADS, plan.smem_bytes, stream>>>(mq_main, mq_ext, mg_main, mg_ext, p);
-  }
-  return (int)cudaGetLastError();
+  // list slots that no strip writes (rows with fewer strips than n_lists) must read as empty
+  cudaError_t e = cudaMemsetAsync(cand_idx, 0xFF, (size_t)Q * n_lists * kprime * sizeof(int32_t), stream);
+  if (e != cudaSuccess) return (int)e;
+
+  const bool k16 = kpp_of(kprime) == 16;
+  if (plan.resident)
+    return k16 ? launch_variant<true, 16>(plan, mq_main, mq_ext, mg_main, mg_ext, p, stream)
+               : launch_variant<true, 32>(plan, mq_main, mq_ext, mg_main, mg_ext, p, stream);
+  return k16 ? launch_variant<false, 16>(plan, mq_main, mq_ext, mg_main, mg_ext, p, stream)
+             : launch_variant<false, 32>(plan, mq_main, mq_ext, mg_main, mg_ext, p, stream);
 }

@@ -57,17 +57,37 @@ def project_rows(u: torch.Tensor, c: float = 1.0, mode: str = "expmap0", side: s
     return y, op, sq
 
 
-def score_plan(Q: int, N: int, d: int, kprime: int, n_splits_hint: int = 0) -> dict:
+def score_plan(Q: int, N: int, d: int, kprime: int, max_ctas: int = 0) -> dict:
+    """Strip schedule + shared-memory plan of ``score_topk`` (host-only; works without a GPU)."""
+    return _score_plan_struct(Q, N, d, kprime, max_ctas).asdict()
+
+
+def _score_plan_struct(Q, N, d, kprime, max_ctas=0):
     plan = _lib.ScorePlan()
-    _lib.check(_lib.load().hypret_score_plan(int(Q), int(N), int(d), int(kprime), int(n_splits_hint),
-                                             ctypes.byref(plan)))
-    return plan.asdict()
+    _lib.check(_lib.load().hypret_score_plan(int(Q), int(N), int(d), int(kprime), int(max_ctas), ctypes.byref(plan)))
+    return plan
 
 
-def score_topk(q_op: torch.Tensor, g_op: torch.Tensor, d: int, kprime: int, n_splits_hint: int = 0,
+def score_strips(Q: int, N: int, d: int, kprime: int, max_ctas: int = 0):
+    """All strips of the schedule as ``(cta, step, query_tile, g0, g1, slot)`` tuples (host-only)."""
+    plan = _score_plan_struct(Q, N, d, kprime, max_ctas)
+    out = (ctypes.c_int32 * 4)()
+    strips = []
+    lib = _lib.load()
+    for cta in range(plan.grid):
+        for step in range(plan.n_steps):
+            rc = lib.hypret_score_strip(ctypes.byref(plan), cta, step, out)
+            if rc < 0:
+                _lib.check(rc)
+            if rc == 1:
+                strips.append((cta, step, int(out[0]), int(out[1]), int(out[2]), int(out[3])))
+    return strips
+
+
+def score_topk(q_op: torch.Tensor, g_op: torch.Tensor, d: int, kprime: int, max_ctas: int = 0,
                debug: bool = False, out: Optional[Tuple[torch.Tensor, torch.Tensor]] = None):
-    """tcgen05 scoring GEMM + streaming top-k'.  Returns ``(cand_score [Q,S,k'], cand_idx [Q,S,k'] int32)``
-    (+ the full ``[Q,N]`` surrogate matrix when ``debug`` -- tests only)."""
+    """tcgen05 scoring GEMM + streaming top-k'.  Returns ``(cand_score [Q,L,k'], cand_idx [Q,L,k'] int32)``
+    with L = plan["n_lists"] (+ the full ``[Q,N]`` surrogate matrix when ``debug`` -- tests only)."""
     _need_cuda(q_op, g_op)
     if q_op.dtype != torch.bfloat16 or g_op.dtype != torch.bfloat16:
         raise ValueError("operands must be bf16 rows from project_rows")
@@ -76,8 +96,8 @@ def score_topk(q_op: torch.Tensor, g_op: torch.Tensor, d: int, kprime: int, n_sp
         raise ValueError(f"operands must be contiguous [rows, {kpad}]")
     Q, N = q_op.shape[0], g_op.shape[0]
     with torch.cuda.device(q_op.device):
-        plan = score_plan(Q, N, d, kprime, n_splits_hint)
-        S = plan["n_splits"]
+        plan = score_plan(Q, N, d, kprime, max_ctas)
+        S = plan["n_lists"]
         if out is None:
             cs = torch.empty(Q, S, kprime, dtype=torch.float32, device=q_op.device)
             ci = torch.empty(Q, S, kprime, dtype=torch.int32, device=q_op.device)
@@ -86,8 +106,8 @@ def score_topk(q_op: torch.Tensor, g_op: torch.Tensor, d: int, kprime: int, n_sp
             if tuple(cs.shape) != (Q, S, kprime) or tuple(ci.shape) != (Q, S, kprime):
                 raise ValueError("preallocated candidate buffers do not match the score plan")
         dbg = torch.empty(Q, N, dtype=torch.float32, device=q_op.device) if debug else None
-        _lib.check(_lib.load().hypret_score_topk(_ptr(q_op), Q, _ptr(g_op), N, int(d), int(kprime), S, _ptr(cs),
-                                                 _ptr(ci), _ptr(dbg), _stream()))
+        _lib.check(_lib.load().hypret_score_topk(_ptr(q_op), Q, _ptr(g_op), N, int(d), int(kprime), S,
+                                                 int(max_ctas), _ptr(cs), _ptr(ci), _ptr(dbg), _stream()))
     return (cs, ci, dbg) if debug else (cs, ci)
 
 
@@ -109,3 +129,17 @@ def rerank(q32: torch.Tensor, g32: torch.Tensor, cand_score: torch.Tensor, cand_
                                              _ptr(cand_score), _ptr(cand_idx), S, kprime, int(k), int(idx_offset),
                                              _ptr(out_s), _ptr(out_i), _ptr(margin), _stream()))
     return (out_s, out_i, margin) if want_margin else (out_s, out_i)
+
+
+def merge_topk(scores: torch.Tensor, idx: torch.Tensor, descending: bool = False):
+    """Merge per-shard lists ``scores/idx [W,Q,k]`` (global indices) into the global top-k ``[Q,k]``."""
+    _need_cuda(scores, idx)
+    scores = scores.contiguous()
+    idx = idx.contiguous()
+    W, Q, k = scores.shape
+    out_s = torch.empty(Q, k, dtype=torch.float32, device=scores.device)
+    out_i = torch.empty(Q, k, dtype=torch.int64, device=scores.device)
+    with torch.cuda.device(scores.device):
+        _lib.check(_lib.load().hypret_merge_topk(_ptr(scores), _ptr(idx), W, Q, k, int(bool(descending)), _ptr(out_s),
+                                                 _ptr(out_i), _stream()))
+    return out_s, out_i

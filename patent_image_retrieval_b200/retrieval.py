@@ -63,9 +63,11 @@ class GalleryIndex:
         return "expmap0" if self.space == "euclidean" else "onball"
 
     def search(self, queries: torch.Tensor, k: int = 10, kprime: Optional[int] = None, return_margin: bool = False,
-               n_splits_hint: int = 0):
+               max_ctas: int = 0, kernel_events: Optional[list] = None):
         """queries [Q,D] fp32 (host or device) -> (score [Q,k] f32, idx [Q,k] i64) on the device.
-        score = Poincare distance ascending, or cosine similarity descending; ties -> lower index."""
+        score = Poincare distance ascending, or cosine similarity descending; ties -> lower index.
+        ``kernel_events``: if a list, a (start, end) CUDA-event pair bracketing the scoring kernel
+        on the launching stream is appended per call (bench.py's roofline measurement)."""
         kprime = default_kprime(k) if kprime is None else int(kprime)
         kprime = min(kprime, ops.MAX_KPRIME)
         if k > kprime:
@@ -78,14 +80,20 @@ class GalleryIndex:
         else:
             q32 = q.contiguous()
             _, q_op, _ = ops.project_rows(q, 1.0, mode="cosine", side="query", want_point=False)
-        key = (q.shape[0], kprime, n_splits_hint)
-        plan = ops.score_plan(q.shape[0], self.n, self.d, kprime, n_splits_hint)
+        key = (q.shape[0], kprime, max_ctas)
+        plan = ops.score_plan(q.shape[0], self.n, self.d, kprime, max_ctas)
         buf = self._cand.get(key)
         if buf is None:
             self._cand.clear()
-            buf = (torch.empty(q.shape[0], plan["n_splits"], kprime, dtype=torch.float32, device=self.device),
-                   torch.empty(q.shape[0], plan["n_splits"], kprime, dtype=torch.int32, device=self.device))
+            buf = (torch.empty(q.shape[0], plan["n_lists"], kprime, dtype=torch.float32, device=self.device),
+                   torch.empty(q.shape[0], plan["n_lists"], kprime, dtype=torch.int32, device=self.device))
             self._cand[key] = buf
-        cs, ci = ops.score_topk(q_op, self.operand, self.d, kprime, n_splits_hint, out=buf)
+        if kernel_events is not None:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+        cs, ci = ops.score_topk(q_op, self.operand, self.d, kprime, max_ctas, out=buf)
+        if kernel_events is not None:
+            e1.record()
+            kernel_events.append((e0, e1))
         return ops.rerank(q32, self.rows32, cs, ci, self.c, self.metric, k, idx_offset=self.idx_offset,
                           want_margin=return_margin)

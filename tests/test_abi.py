@@ -35,20 +35,72 @@ def test_host_only_entry_points():
     assert ops.operand_kpad(512) == 528 and ops.operand_kpad(768) == 784 and ops.operand_kpad(100) == 144
 
 
-def test_score_plan_is_balanced_and_covers_gallery():
+SCHED_CASES = [
+    # Q, N, d, kprime, max_ctas
+    (10000, 300000, 512, 16, 0),        # C2: 79 query tiles on 148 CTAs -> phase 1 + phase 2
+    (1000, 10000, 2048, 16, 0),         # C1
+    (100000, 1000000, 768, 32, 0),      # C3: full waves + tail
+    (10000, 10_000_000, 512, 16, 0),    # C4 on one GPU
+    (10000, 1_250_000, 512, 16, 0),     # C4 shard on 8 GPUs
+    (1, 1, 128, 4, 0),
+    (129, 257, 768, 32, 0),
+    (900, 5000, 128, 8, 5),             # forced small grid: full waves + both phases
+    (700, 3000, 64, 16, 7),
+    (128 * 6, 256 * 9, 64, 16, 6),      # T == P exactly: only full waves
+    (128 * 3, 256 * 40, 64, 16, 6),     # b == 0: phase 1 only
+]
+
+
+@pytest.mark.parametrize("Q,N,d,kp,cap", SCHED_CASES)
+def test_strip_schedule_covers_every_tile_once(Q, N, d, kp, cap):
+    """Every (query tile, gallery tile) pair is visited by exactly one strip, list slots of a
+    query tile are distinct and < n_lists, a CTA has at most one strip per step, and the
+    busiest CTA is within a few percent of the ideal share."""
     from patent_image_retrieval_b200 import ops
-    for (Q, N, d, kp) in [(10000, 300000, 512, 16), (1000, 10000, 2048, 16), (10000, 10_000_000, 512, 16),
-                          (1, 1, 128, 4), (129, 257, 768, 32)]:
-        p = ops.score_plan(Q, N, d, kp)
-        assert p["n_qtiles"] == -(-Q // 128) and p["n_gtiles"] == -(-N // 256)
-        assert p["n_splits"] * p["tiles_per_split"] >= p["n_gtiles"]
-        assert (p["n_splits"] - 1) * p["tiles_per_split"] < p["n_gtiles"]       # no empty split
-        assert 2 <= p["stages"] <= 8 and p["smem_bytes"] <= 232448
-        assert p["resident"] == (1 if d <= 512 else 0)
+    p = ops.score_plan(Q, N, d, kp, cap)
+    T, G, P = p["n_qtiles"], p["n_gtiles"], p["grid"]
+    assert T == -(-Q // 128) and G == -(-N // 256)
+    assert 2 <= p["stages"] <= 8 and p["smem_bytes"] <= 232448
+    strips = ops.score_strips(Q, N, d, kp, cap)
+    seen = {}
+    per_cta = {}
+    steps = set()
+    for cta, step, qt, g0, g1, slot in strips:
+        assert 0 <= qt < T and 0 <= g0 < g1 <= G and 0 <= slot < p["n_lists"] and 0 <= cta < P
+        assert (cta, step) not in steps
+        steps.add((cta, step))
+        assert (qt, slot) not in seen
+        seen[(qt, slot)] = (g0, g1)
+        per_cta[cta] = per_cta.get(cta, 0) + (g1 - g0)
+    if T * G <= 200000:                   # exhaustive coverage check on the small cases
+        cover = {}
+        for (qt, slot), (g0, g1) in seen.items():
+            for g in range(g0, g1):
+                assert (qt, g) not in cover
+                cover[(qt, g)] = 1
+        assert len(cover) == T * G
+    else:                                 # interval check on the big ones
+        by_qt = {}
+        for (qt, slot), (g0, g1) in seen.items():
+            by_qt.setdefault(qt, []).append((g0, g1))
+        assert len(by_qt) == T
+        for qt, iv in by_qt.items():
+            iv.sort()
+            assert iv[0][0] == 0 and iv[-1][1] == G
+            assert all(a[1] == b[0] for a, b in zip(iv, iv[1:]))
+    ideal = T * G / P
+    if ideal >= 64:
+        assert max(per_cta.values()) <= 1.03 * ideal + 2
+    # query tiles of consecutive CTAs in the same step share the gallery range (L2 lock-step)
+    assert p["resident"] == (1 if (d <= 512 and kp <= 16) or d <= 384 else 0) or d > 512
+
+
+def test_c2_plan_numbers():
+    from patent_image_retrieval_b200 import ops
     p = ops.score_plan(10000, 300000, 512, 16)
-    items = p["n_qtiles"] * p["n_splits"]
-    waves = -(-items // 148)
-    assert items / (waves * 148) > 0.9           # wave quantisation loss < 10 %
+    assert (p["grid"], p["n_full"], p["tail_rows"], p["a"], p["b"]) == (148, 0, 79, 1, 69)
+    assert p["l1"] == 586 and p["rem_rows"] == 10 and p["m"] == 14 and p["l2"] == 42
+    assert p["n_lists"] == 15 and p["resident"] == 1
     with pytest.raises(RuntimeError):
         ops.score_plan(10, 10, 512, 64)          # kprime > 32
 

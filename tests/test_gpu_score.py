@@ -19,40 +19,50 @@ def _operands(Q, N, d, c=1.0, metric="hyperbolic"):
 
 
 CASES = [
-    # Q, N, d, kprime, split hint
+    # Q, N, d, kprime, max_ctas
     (200, 1000, 512, 16, 0),     # resident query tile, ragged last tiles
     (128, 256, 512, 16, 0),      # exactly one tile
     (1, 1, 128, 4, 0),           # degenerate
-    (300, 3000, 128, 8, 3),      # several splits, small d (deep ring)
+    (300, 3000, 128, 8, 0),      # many short strips, small d (deep ring)
     (130, 700, 768, 32, 0),      # streamed query tile (d > 512)
-    (64, 520, 2048, 16, 2),      # C1-style d
-    (257, 5000, 256, 20, 5),
+    (64, 520, 2048, 16, 0),      # C1-style d
+    (257, 5000, 256, 20, 0),     # 32-slot lists
+    (900, 5000, 128, 8, 5),      # forced small grid: full wave + phase 1 + phase 2 in one CTA
+    (700, 9000, 512, 16, 7),     # resident tile reloaded between strips
+    (128 * 3, 256 * 40, 64, 16, 6),
 ]
 
 
-@pytest.mark.parametrize("Q,N,d,kprime,hint", CASES)
-def test_scores_and_lists(Q, N, d, kprime, hint):
+@pytest.mark.parametrize("Q,N,d,kprime,cap", CASES)
+def test_scores_and_lists(Q, N, d, kprime, cap):
     q_op, g_op = _operands(Q, N, d)
-    cs, ci, dbg = ops.score_topk(q_op, g_op, d, kprime, hint, debug=True)
+    cs, ci, dbg = ops.score_topk(q_op, g_op, d, kprime, cap, debug=True)
     ref = q_op.float() @ g_op.float().t()
     scale = float(ref.abs().max())
     assert float((dbg - ref).abs().max()) <= 2e-5 * scale + 1e-6
-    plan = ops.score_plan(Q, N, d, kprime, hint)
-    S, span = plan["n_splits"], plan["tiles_per_split"] * 256
-    assert cs.shape == (Q, S, kprime)
-    for s in range(S):
-        lo, hi = s * span, min(N, (s + 1) * span)
+    plan = ops.score_plan(Q, N, d, kprime, cap)
+    assert cs.shape == (Q, plan["n_lists"], kprime)
+    written = set()
+    for cta, step, qt, g0, g1, slot in ops.score_strips(Q, N, d, kprime, cap):
+        r0, r1 = qt * 128, min(Q, qt * 128 + 128)
+        lo, hi = g0 * 256, min(N, g1 * 256)
+        written.add((qt, slot))
         kk = min(kprime, hi - lo)
-        want_v, _ = torch.topk(dbg[:, lo:hi], kk, dim=1, largest=False)
-        got_v, order = cs[:, s, :].sort(dim=1)
-        got_i = torch.gather(ci[:, s, :], 1, order)
+        want_v, _ = torch.topk(dbg[r0:r1, lo:hi], kk, dim=1, largest=False)
+        got_v, order = cs[r0:r1, slot, :].sort(dim=1)
+        got_i = torch.gather(ci[r0:r1, slot, :], 1, order)
         assert torch.equal(got_v[:, :kk], want_v.sort(dim=1).values)
-        # indices point at the scores they claim, inside the split; unused slots are (-1, +inf)
-        picked = torch.gather(dbg, 1, got_i[:, :kk].long())
+        # indices point at the scores they claim, inside the strip; unused slots are (-1, +inf)
+        picked = torch.gather(dbg[r0:r1], 1, got_i[:, :kk].long())
         assert torch.equal(picked, got_v[:, :kk])
         assert int(got_i[:, :kk].min()) >= lo and int(got_i[:, :kk].max()) < hi
         if kk < kprime:
             assert bool((got_i[:, kk:] == -1).all()) and bool(torch.isinf(got_v[:, kk:]).all())
+    # list slots that no strip owns read as empty
+    for qt in range(plan["n_qtiles"]):
+        for slot in range(plan["n_lists"]):
+            if (qt, slot) not in written:
+                assert bool((ci[qt * 128:qt * 128 + 128, slot, :] == -1).all())
 
 
 def test_cosine_operands_give_minus_cosine():
@@ -67,7 +77,7 @@ def test_cosine_operands_give_minus_cosine():
 
 def test_plan_mismatch_is_an_error():
     q_op, g_op = _operands(64, 2048, 128)
-    cs = torch.empty(64, 7, 16, device="cuda")
-    ci = torch.empty(64, 7, 16, device="cuda", dtype=torch.int32)
+    cs = torch.empty(64, 77, 16, device="cuda")
+    ci = torch.empty(64, 77, 16, device="cuda", dtype=torch.int32)
     with pytest.raises(ValueError):
-        ops.score_topk(q_op, g_op, 128, 16, 2, out=(cs, ci))
+        ops.score_topk(q_op, g_op, 128, 16, 0, out=(cs, ci))

@@ -49,14 +49,13 @@ def check(Q, N, d, kprime=16, hint=0, label=""):
                 print(f"      ({i},{j}) got {float(dbg[i, j]):.6e} want {float(ref[i, j]):.6e}")
         if name == "all":
             # candidate lists vs torch.topk on the kernel's own score matrix
-            S = plan["n_splits"]
-            tps = plan["tiles_per_split"] * 256
             miss = 0
-            for s in range(S):
-                lo, hi = s * tps, min(N, (s + 1) * tps)
+            for cta, step, qt, g0, g1, slot in ops.score_strips(Q, N, d, kprime, hint):
+                r0, r1 = qt * 128, min(Q, qt * 128 + 128)
+                lo, hi = g0 * 256, min(N, g1 * 256)
                 kk = min(kprime, hi - lo)
-                want = torch.topk(dbg[:, lo:hi], kk, dim=1, largest=False).values.sort(dim=1).values
-                got = cs[:, s, :].sort(dim=1).values[:, :kk]
+                want = torch.topk(dbg[r0:r1, lo:hi], kk, dim=1, largest=False).values.sort(dim=1).values
+                got = cs[r0:r1, slot, :].sort(dim=1).values[:, :kk]
                 miss += int((want != got).sum())
             print(f"   top-k' lists vs torch.topk(debug matrix): mismatching entries = {miss}", flush=True)
             ok_all &= miss == 0
@@ -70,8 +69,8 @@ def bench(Q, N, d, kprime=16, iters=5):
     _, q_op, _ = ops.project_rows(u, 1.0, "expmap0", "query")
     _, g_op, _ = ops.project_rows(v, 1.0, "expmap0", "gallery")
     plan = ops.score_plan(Q, N, d, kprime)
-    cs = torch.empty(Q, plan["n_splits"], kprime, device=dev)
-    ci = torch.empty(Q, plan["n_splits"], kprime, device=dev, dtype=torch.int32)
+    cs = torch.empty(Q, plan["n_lists"], kprime, device=dev)
+    ci = torch.empty(Q, plan["n_lists"], kprime, device=dev, dtype=torch.int32)
     for _ in range(2):
         ops.score_topk(q_op, g_op, d, kprime, out=(cs, ci))
     torch.cuda.synchronize()
@@ -91,9 +90,9 @@ if __name__ == "__main__":
     t0 = time.time()
     print(torch.cuda.get_device_name(0), flush=True)
     ok = check(200, 1000, 512, label="resident-small")
-    ok &= check(300, 3000, 128, label="resident-d128", hint=3)
+    ok &= check(900, 5000, 128, label="resident-d128-3phase", kprime=8, hint=5)
     ok &= check(130, 700, 768, label="stream-d768")
-    ok &= check(64, 520, 2048, label="stream-d2048", hint=2)
+    ok &= check(64, 520, 2048, label="stream-d2048")
     print("DIAG", "PASS" if ok else "FAIL", f"{time.time() - t0:.1f}s", flush=True)
     if ok and "--quick" not in sys.argv:
         bench(10000, 300000, 512)
