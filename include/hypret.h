@@ -99,10 +99,16 @@ int hypret_score_strip(const hypret_score_plan_t* plan, int cta, int step, int32
  *   q_op [Q,kpad] bf16, g_op [N,kpad] bf16   operands from hypret_project_rows
  *   cand_score [Q, n_lists, kprime] fp32 out, cand_idx same shape int32 out (-1 = empty)
  *   n_lists   must equal plan.n_lists of hypret_score_plan(Q, N, d, kprime, max_ctas)
+ *   thr_workspace  [Q] uint32 scratch, or NULL.  When given, the strips of a query exchange
+ *             their running k'-th best score through it (L2 atomics), so later / concurrent
+ *             strips start warm: the UNION of a query's lists still contains its global
+ *             top-kprime, but a single list is no longer the top-kprime of its own strip.
+ *             With NULL every list is exactly its strip's top-kprime (slower; tests).
  *   debug_scores  NULL, or [Q,N] fp32 that receives every surrogate score (tests only)
  * 1 <= kprime <= 32. */
 int hypret_score_topk(const void* q_op, int64_t Q, const void* g_op, int64_t N, int d, int kprime, int n_lists,
-                      int max_ctas, float* cand_score, int32_t* cand_idx, float* debug_scores, void* stream);
+                      int max_ctas, float* cand_score, int32_t* cand_idx, uint32_t* thr_workspace,
+                      float* debug_scores, void* stream);
 
 /* Candidate merge + exact rerank.  For each query: keep the kprime best of its
  * n_lists*kprime candidates by surrogate score, recompute their distance exactly from the

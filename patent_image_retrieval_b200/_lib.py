@@ -49,7 +49,7 @@ SIGNATURES = {
     "hypret_score_plan": (c_int, [c_int64, c_int64, c_int, c_int, c_int, POINTER(ScorePlan)]),
     "hypret_score_strip": (c_int, [POINTER(ScorePlan), c_int, c_int, POINTER(c_int32)]),
     "hypret_score_topk": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int, c_int, c_int, c_int, c_void_p,
-                                  c_void_p, c_void_p, c_void_p]),
+                                  c_void_p, c_void_p, c_void_p, c_void_p]),
     "hypret_rerank": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int, c_float, c_int, c_void_p, c_void_p, c_int,
                               c_int, c_int, c_int64, c_void_p, c_void_p, c_void_p, c_void_p]),
     "hypret_merge_topk": (c_int, [c_void_p, c_void_p, c_int, c_int64, c_int, c_int, c_void_p, c_void_p, c_void_p]),

@@ -50,14 +50,15 @@ int hypret_project_rows(const float* u, int64_t n, int d, float c, int mode, int
 }
 
 int hypret_score_topk(const void* q_op, int64_t Q, const void* g_op, int64_t N, int d, int kprime, int n_lists,
-                      int max_ctas, float* cand_score, int32_t* cand_idx, float* debug_scores, void* stream) {
+                      int max_ctas, float* cand_score, int32_t* cand_idx, uint32_t* thr_workspace, float* debug_scores,
+                      void* stream) {
   if (Q < 1 || N < 1 || d < 4 || (d & 3) || d > 2048) return HYPRET_EINVAL;
   if (kprime < 1 || kprime > 32 || n_lists < 1 || max_ctas < 0) return HYPRET_EINVAL;
   if (q_op == nullptr || g_op == nullptr || cand_score == nullptr || cand_idx == nullptr) return HYPRET_EINVAL;
   int rc = check_device();
   if (rc != HYPRET_OK) return rc;
   return hypret_launch_score_topk(q_op, Q, g_op, N, d, kprime, n_lists, max_ctas, cand_score, cand_idx,
-                                  debug_scores, static_cast<cudaStream_t>(stream));
+                                  thr_workspace, debug_scores, static_cast<cudaStream_t>(stream));
 }
 
 int hypret_rerank(const float* q32, const float* g32, int64_t Q, int64_t N, int d, float c, int metric,

@@ -38,6 +38,7 @@
 // load balance is within one small piece, and a query sees only a handful of cold starts.
 #include <cuda.h>
 #include <math.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -159,6 +160,7 @@ struct Params {
   float* cand_score;
   int32_t* cand_idx;
   float* debug_scores;
+  uint32_t* shared_thr;   // [Q] ordered-uint keys of the best known k'-th score per query, or NULL
 };
 
 struct Barriers {
@@ -181,10 +183,55 @@ __device__ __forceinline__ float key2f(uint32_t k) {
   return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
 }
 
-// One 32-column chunk of the accumulator: fast reject, else warp-cooperative inserts.
+__device__ __forceinline__ uint32_t ld_cg_u32(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.global.cg.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");   // L2 (coherent), not L1
+  return v;
+}
+constexpr uint32_t KEY_INF = 0xff800000u;   // f2key(+inf)
+
+// Lists live in shared memory as [slot][row] (row = thread of the epilogue, 0..127): when all
+// lanes of a warp touch the same slot the access is conflict-free.  Shared-state-space
+// addresses (32-bit) + explicit ld/st.shared keep the non-inlined helper free of generic loads.
+__device__ __forceinline__ float lds_f32(uint32_t a) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a) : "memory");
+  return v;
+}
+__device__ __forceinline__ void sts_f32(uint32_t a, float v) {
+  asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(v) : "memory");
+}
+__device__ __forceinline__ void sts_b32(uint32_t a, int v) {
+  asm volatile("st.shared.b32 [%0], %1;" ::"r"(a), "r"(v) : "memory");
+}
+constexpr int LIST_SLOT_STRIDE = TILE_M * 4;   // bytes between consecutive slots of one row
+
+// Thread-private insert: overwrite the row's worst slot, rescan the KPP slots (independent
+// loads, compile-time unrolled) and return (new worst score, its slot).  One call site per
+// column of a chunk, so it is deliberately NOT inlined.
 template <int KPP>
-__device__ __forceinline__ void process_chunk(const float (&v)[32], int64_t cbase, int64_t N, int lane, float& thr,
-                                              int& maxpos, float* ls_q, int* li_q) {
+__device__ __noinline__ uint2 list_insert(uint32_t s_addr, uint32_t i_addr, float x, int col, int maxpos) {
+  sts_f32(s_addr + maxpos * LIST_SLOT_STRIDE, x);
+  sts_b32(i_addr + maxpos * LIST_SLOT_STRIDE, col);
+  float w[KPP];
+#pragma unroll
+  for (int s = 0; s < KPP; ++s) w[s] = lds_f32(s_addr + s * LIST_SLOT_STRIDE);
+  float mx = w[0];
+#pragma unroll
+  for (int s = 1; s < KPP; ++s) mx = fmaxf(mx, w[s]);
+  int pos = 0;
+#pragma unroll
+  for (int s = KPP - 1; s >= 0; --s) pos = (w[s] == mx) ? s : pos;
+  return make_uint2(__float_as_uint(mx), (uint32_t)pos);
+}
+
+// One 32-column chunk of the accumulator.  Every lane owns one query row: `thr` is that row's
+// effective threshold = min(worst kept score, bound shared by the query's other strips).
+// Fast path: 3-input min tree + one compare.  Slow path: plain SIMT divergence -- only lanes
+// with a hit walk their group / column and call the private insert; no cross-lane traffic.
+template <int KPP>
+__device__ __forceinline__ void process_chunk(const float (&v)[32], int cbase, float& thr, float& thr_list,
+                                              const float thr_g, int& maxpos, uint32_t s_addr, uint32_t i_addr) {
   float mg[4];
 #pragma unroll
   for (int g = 0; g < 4; ++g) {
@@ -194,31 +241,19 @@ __device__ __forceinline__ void process_chunk(const float (&v)[32], int64_t cbas
     mg[g] = m;
   }
   const float m = fminf(fminf(mg[0], mg[1]), fminf(mg[2], mg[3]));
-  if (__ballot_sync(FULL, m < thr) == 0u) return;   // warp-uniform fast reject
+  if (m < thr) {
 #pragma unroll
-  for (int g = 0; g < 4; ++g) {
-    if (__ballot_sync(FULL, mg[g] < thr) == 0u) continue;
+    for (int g = 0; g < 4; ++g) {
+      if (mg[g] < thr) {
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const float x = v[g * 8 + j];
-      const int64_t col = cbase + g * 8 + j;
-      unsigned hb = __ballot_sync(FULL, x < thr && col < N);
-      while (hb) {
-        const int L = __ffs(hb) - 1;       // warp-uniform: lane (= row of this quadrant) that inserts
-        hb &= hb - 1;
-        float* lr = ls_q + L * KPP;
-        if (lane == L) {                   // the owner replaces its current worst slot
-          lr[maxpos] = x;
-          li_q[L * KPP + maxpos] = (int)col;
-        }
-        __syncwarp();
-        const float y = (lane < KPP) ? lr[lane] : -INFINITY;
-        const uint32_t key = f2key(y);
-        const uint32_t mx = __reduce_max_sync(FULL, key);          // new k'-th best of row L
-        const int pos = __ffs(__ballot_sync(FULL, key == mx)) - 1;
-        if (lane == L) {
-          thr = key2f(mx);
-          maxpos = pos;
+        for (int j = 0; j < 8; ++j) {
+          const float x = v[g * 8 + j];
+          if (x < thr) {
+            const uint2 r = list_insert<KPP>(s_addr, i_addr, x, cbase + g * 8 + j, maxpos);
+            thr_list = __uint_as_float(r.x);
+            maxpos = (int)r.y;
+            thr = fminf(thr_list, thr_g);
+          }
         }
       }
     }
@@ -235,7 +270,7 @@ score_topk_kernel(const __grid_constant__ CUtensorMap map_q_main, const __grid_c
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* a_res = smem;                                   // RESIDENT: kb_main blocks + ext block
   uint8_t* ring = smem + p.ring_off;
-  float* list_s = reinterpret_cast<float*>(smem + p.lists_off);   // [128 rows][KPP slots]
+  float* list_s = reinterpret_cast<float*>(smem + p.lists_off);   // [KPP slots][128 rows]
   int* list_i = reinterpret_cast<int*>(list_s + KPP * TILE_M);
   Barriers* bars = reinterpret_cast<Barriers*>(smem + p.bar_off);
 
@@ -367,54 +402,91 @@ score_topk_kernel(const __grid_constant__ CUtensorMap map_q_main, const __grid_c
   } else {
     // ======================================================================= epilogue / top-k'
     const int quad = warp & 3;                 // TMEM lane quadrant this warp may read
-    float* ls_q = list_s + quad * 32 * KPP;    // this warp's 32 rows, KPP slots each
-    int* li_q = list_i + quad * 32 * KPP;
+    const int row = quad * 32 + lane;          // query row inside the tile == TMEM lane
+    float* my_s = list_s + row;                // [slot][row] layout, slot stride TILE_M
+    int* my_i = list_i + row;
+    const uint32_t s_addr = smem_u32(my_s), i_addr = smem_u32(my_i);
     const int KP = p.kprime;
-    const int64_t N = p.N;
+    const int N = (int)p.N;
     uint32_t acc = 0, acc_phase = 0;
     for (int step = 0; step < sc.n_steps; ++step) {
       int qt, gt0, gt1, slot;
       if (!strip_at(sc, cta, step, qt, gt0, gt1, slot)) continue;
       const int64_t qrow = (int64_t)qt * TILE_M + quad * 32 + lane;
-      // cold lists: active slots +inf (threshold stays +inf until k' scores are in),
+      uint32_t* gthr = (p.shared_thr != nullptr && qrow < p.Q) ? p.shared_thr + qrow : nullptr;
+      // cold list: active slots +inf (the list threshold stays +inf until k' scores are in),
       // inactive slots -inf (never the maximum)
-      float thr = INFINITY;
+      float thr_list = INFINITY;
       int maxpos = 0;
 #pragma unroll
       for (int s = 0; s < KPP; ++s) {
-        ls_q[lane * KPP + s] = (s < KP) ? INFINITY : -INFINITY;
-        li_q[lane * KPP + s] = -1;
+        my_s[s * TILE_M] = (s < KP) ? INFINITY : -INFINITY;
+        my_i[s * TILE_M] = -1;
       }
+      // warm threshold: what other strips of this query have already established.  Any bound
+      // published there is >= the query's final k'-th best score, so filtering with the next
+      // float above it can only drop rows that are not in the final top-k'.
+      float thr_g = INFINITY, published = INFINITY;
+      if (gthr != nullptr) {
+        const uint32_t gk = ld_cg_u32(gthr);
+        if (gk < KEY_INF) thr_g = nextafterf(key2f(gk), INFINITY);
+      }
+      float thr = fminf(thr_list, thr_g);
       __syncwarp();
       for (int gt = gt0; gt < gt1; ++gt) {
         mbar_wait(&bars->tmem_full[acc], acc_phase);
         tcgen05_fence_after();
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * TILE_N;
-        const int64_t col0 = (int64_t)gt * TILE_N;
+        const int col0 = gt * TILE_N;
+        const bool ragged = col0 + TILE_N > N;               // last gallery tile: TMA zero-filled rows
         float va[32], vb[32];
+        __syncwarp();
         tmem_ld_32x32(taddr, va);
 #pragma unroll 1
         for (int cc = 0; cc < TILE_N / 32; cc += 2) {
           tmem_ld_wait(va);
           tmem_ld_32x32(taddr + (cc + 1) * 32, vb);           // next chunk in flight while this one is scanned
+          if (ragged) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (col0 + cc * 32 + j >= N) va[j] = INFINITY;
+          }
           if (p.debug_scores != nullptr && qrow < p.Q) {
 #pragma unroll
             for (int j = 0; j < 32; ++j)
-              if (col0 + cc * 32 + j < N) p.debug_scores[qrow * N + col0 + cc * 32 + j] = va[j];
+              if (col0 + cc * 32 + j < N) p.debug_scores[qrow * p.N + col0 + cc * 32 + j] = va[j];
           }
-          process_chunk<KPP>(va, col0 + cc * 32, N, lane, thr, maxpos, ls_q, li_q);
+          process_chunk<KPP>(va, col0 + cc * 32, thr, thr_list, thr_g, maxpos, s_addr, i_addr);
+          __syncwarp();                                       // tcgen05.ld/wait are warp-collective
           tmem_ld_wait(vb);
           if (cc + 2 < TILE_N / 32) tmem_ld_32x32(taddr + (cc + 2) * 32, va);
+          if (ragged) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (col0 + (cc + 1) * 32 + j >= N) vb[j] = INFINITY;
+          }
           if (p.debug_scores != nullptr && qrow < p.Q) {
 #pragma unroll
             for (int j = 0; j < 32; ++j)
-              if (col0 + (cc + 1) * 32 + j < N) p.debug_scores[qrow * N + col0 + (cc + 1) * 32 + j] = vb[j];
+              if (col0 + (cc + 1) * 32 + j < N) p.debug_scores[qrow * p.N + col0 + (cc + 1) * 32 + j] = vb[j];
           }
-          process_chunk<KPP>(vb, col0 + (cc + 1) * 32, N, lane, thr, maxpos, ls_q, li_q);
+          process_chunk<KPP>(vb, col0 + (cc + 1) * 32, thr, thr_list, thr_g, maxpos, s_addr, i_addr);
+          __syncwarp();
         }
         tcgen05_fence_before();
         mbar_arrive(&bars->tmem_empty[acc]);
         if (++acc == NUM_ACC) { acc = 0; acc_phase ^= 1; }
+        // exchange thresholds with the other strips of this query (L2 atomics, off the
+        // critical path: the accumulator has already been released)
+        if (gthr != nullptr) {
+          if (thr_list < published) {
+            atomicMin(gthr, f2key(thr_list));
+            published = thr_list;
+          }
+          const uint32_t gk = ld_cg_u32(gthr);
+          if (gk < KEY_INF) thr_g = fminf(thr_g, nextafterf(key2f(gk), INFINITY));
+          thr = fminf(thr_list, thr_g);
+        }
       }
       // publish this strip's lists: one coalesced row of k' entries per query
       __syncwarp();
@@ -422,8 +494,8 @@ score_topk_kernel(const __grid_constant__ CUtensorMap map_q_main, const __grid_c
         const int64_t qr = (int64_t)qt * TILE_M + quad * 32 + r;
         if (qr < p.Q && lane < KP) {
           const int64_t o = (qr * sc.n_lists + slot) * KP + lane;
-          p.cand_score[o] = ls_q[r * KPP + lane];
-          p.cand_idx[o] = li_q[r * KPP + lane];
+          p.cand_score[o] = list_s[lane * TILE_M + quad * 32 + r];
+          p.cand_idx[o] = list_i[lane * TILE_M + quad * 32 + r];
         }
       }
       __syncwarp();
@@ -517,7 +589,8 @@ extern "C" int hypret_score_plan(int64_t Q, int64_t N, int d, int kprime, int ma
   int resident = 0, stages = 0, stage_bytes = 0;
   {
     const int avail = SMEM_LIMIT - 1024 - BAR_BYTES - lists - a_res_bytes;
-    if (kb <= 8 && avail >= 2 * B_BLK_BYTES) {
+    const char* force = getenv("HYPRET_FORCE_STREAM");   // experiments only
+    if (kb <= 8 && avail >= 2 * B_BLK_BYTES && !(force != nullptr && force[0] == '1')) {
       resident = 1;
       stage_bytes = B_BLK_BYTES;
       stages = avail / B_BLK_BYTES;
@@ -560,8 +633,8 @@ extern "C" int hypret_score_strip(const hypret_score_plan_t* plan, int cta, int 
 }
 
 int hypret_launch_score_topk(const void* q_op, int64_t Q, const void* g_op, int64_t N, int d, int kprime,
-                             int n_lists, int max_ctas, float* cand_score, int32_t* cand_idx, float* debug_scores,
-                             cudaStream_t stream) {
+                             int n_lists, int max_ctas, float* cand_score, int32_t* cand_idx, uint32_t* thr_ws,
+                             float* debug_scores, cudaStream_t stream) {
   hypret_score_plan_t plan;
   int rc = hypret_score_plan(Q, N, d, kprime, max_ctas, &plan);
   if (rc != HYPRET_OK) return rc;
@@ -592,10 +665,15 @@ int hypret_launch_score_topk(const void* q_op, int64_t Q, const void* g_op, int6
   p.cand_score = cand_score;
   p.cand_idx = cand_idx;
   p.debug_scores = debug_scores;
+  p.shared_thr = thr_ws;
 
   // list slots that no strip writes (rows with fewer strips than n_lists) must read as empty
   cudaError_t e = cudaMemsetAsync(cand_idx, 0xFF, (size_t)Q * n_lists * kprime * sizeof(int32_t), stream);
   if (e != cudaSuccess) return (int)e;
+  if (thr_ws != nullptr) {   // 0xFFFFFFFF > f2key(+inf): "no bound published yet"
+    e = cudaMemsetAsync(thr_ws, 0xFF, (size_t)Q * sizeof(uint32_t), stream);
+    if (e != cudaSuccess) return (int)e;
+  }
 
   const bool k16 = kpp_of(kprime) == 16;
   if (plan.resident)

@@ -85,9 +85,12 @@ def score_strips(Q: int, N: int, d: int, kprime: int, max_ctas: int = 0):
 
 
 def score_topk(q_op: torch.Tensor, g_op: torch.Tensor, d: int, kprime: int, max_ctas: int = 0,
-               debug: bool = False, out: Optional[Tuple[torch.Tensor, torch.Tensor]] = None):
+               debug: bool = False, out: Optional[Tuple[torch.Tensor, torch.Tensor]] = None,
+               share_thresholds: bool = True, thr_workspace: Optional[torch.Tensor] = None):
     """tcgen05 scoring GEMM + streaming top-k'.  Returns ``(cand_score [Q,L,k'], cand_idx [Q,L,k'] int32)``
-    with L = plan["n_lists"] (+ the full ``[Q,N]`` surrogate matrix when ``debug`` -- tests only)."""
+    with L = plan["n_lists"] (+ the full ``[Q,N]`` surrogate matrix when ``debug`` -- tests only).
+    ``share_thresholds``: strips of a query exchange their running k'-th best score (fast path);
+    off, every list is exactly the top-k' of its own strip."""
     _need_cuda(q_op, g_op)
     if q_op.dtype != torch.bfloat16 or g_op.dtype != torch.bfloat16:
         raise ValueError("operands must be bf16 rows from project_rows")
@@ -106,8 +109,13 @@ def score_topk(q_op: torch.Tensor, g_op: torch.Tensor, d: int, kprime: int, max_
             if tuple(cs.shape) != (Q, S, kprime) or tuple(ci.shape) != (Q, S, kprime):
                 raise ValueError("preallocated candidate buffers do not match the score plan")
         dbg = torch.empty(Q, N, dtype=torch.float32, device=q_op.device) if debug else None
+        ws = None
+        if share_thresholds:
+            ws = thr_workspace if thr_workspace is not None else torch.empty(Q, dtype=torch.int32, device=q_op.device)
+            if ws.numel() < Q or ws.element_size() != 4 or not ws.is_cuda:
+                raise ValueError("thr_workspace must be a CUDA tensor of >= Q 32-bit elements")
         _lib.check(_lib.load().hypret_score_topk(_ptr(q_op), Q, _ptr(g_op), N, int(d), int(kprime), S,
-                                                 int(max_ctas), _ptr(cs), _ptr(ci), _ptr(dbg), _stream()))
+                                                 int(max_ctas), _ptr(cs), _ptr(ci), _ptr(ws), _ptr(dbg), _stream()))
     return (cs, ci, dbg) if debug else (cs, ci)
 
 

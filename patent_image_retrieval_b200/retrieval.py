@@ -86,12 +86,13 @@ class GalleryIndex:
         if buf is None:
             self._cand.clear()
             buf = (torch.empty(q.shape[0], plan["n_lists"], kprime, dtype=torch.float32, device=self.device),
-                   torch.empty(q.shape[0], plan["n_lists"], kprime, dtype=torch.int32, device=self.device))
+                   torch.empty(q.shape[0], plan["n_lists"], kprime, dtype=torch.int32, device=self.device),
+                   torch.empty(q.shape[0], dtype=torch.int32, device=self.device))
             self._cand[key] = buf
         if kernel_events is not None:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-        cs, ci = ops.score_topk(q_op, self.operand, self.d, kprime, max_ctas, out=buf)
+        cs, ci = ops.score_topk(q_op, self.operand, self.d, kprime, max_ctas, out=buf[:2], thr_workspace=buf[2])
         if kernel_events is not None:
             e1.record()
             kernel_events.append((e0, e1))

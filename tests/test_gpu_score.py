@@ -36,7 +36,7 @@ CASES = [
 @pytest.mark.parametrize("Q,N,d,kprime,cap", CASES)
 def test_scores_and_lists(Q, N, d, kprime, cap):
     q_op, g_op = _operands(Q, N, d)
-    cs, ci, dbg = ops.score_topk(q_op, g_op, d, kprime, cap, debug=True)
+    cs, ci, dbg = ops.score_topk(q_op, g_op, d, kprime, cap, debug=True, share_thresholds=False)
     ref = q_op.float() @ g_op.float().t()
     scale = float(ref.abs().max())
     assert float((dbg - ref).abs().max()) <= 2e-5 * scale + 1e-6
@@ -63,6 +63,34 @@ def test_scores_and_lists(Q, N, d, kprime, cap):
         for slot in range(plan["n_lists"]):
             if (qt, slot) not in written:
                 assert bool((ci[qt * 128:qt * 128 + 128, slot, :] == -1).all())
+
+
+@pytest.mark.parametrize("Q,N,d,kprime,cap", CASES)
+def test_shared_thresholds_keep_the_global_topk(Q, N, d, kprime, cap):
+    """Production mode: strips of a query exchange thresholds.  Lists are then only subsets of
+    their strip's top-k', but (a) every entry is a genuine (score, index) pair of its strip, with
+    no duplicates, and (b) the union of a query's lists contains its global top-k'."""
+    q_op, g_op = _operands(Q, N, d)
+    cs, ci, dbg = ops.score_topk(q_op, g_op, d, kprime, cap, debug=True, share_thresholds=True)
+    plan = ops.score_plan(Q, N, d, kprime, cap)
+    L = plan["n_lists"]
+    for cta, step, qt, g0, g1, slot in ops.score_strips(Q, N, d, kprime, cap):
+        r0, r1 = qt * 128, min(Q, qt * 128 + 128)
+        lo, hi = g0 * 256, min(N, g1 * 256)
+        idx = ci[r0:r1, slot, :].long()
+        valid = idx >= 0
+        assert bool(((idx >= lo) & (idx < hi))[valid].all())
+        picked = torch.gather(dbg[r0:r1], 1, idx.clamp_min(0))
+        assert torch.equal(picked[valid], cs[r0:r1, slot, :][valid])
+    flat_i = ci.reshape(Q, L * kprime).long()
+    flat_s = torch.where(flat_i >= 0, cs.reshape(Q, L * kprime), torch.full_like(cs.reshape(Q, -1), float("inf")))
+    srt = flat_i.sort(dim=1).values
+    dup = (srt[:, 1:] == srt[:, :-1]) & (srt[:, 1:] >= 0)
+    assert not bool(dup.any())
+    kk = min(kprime, N)
+    want = torch.topk(dbg, kk, dim=1, largest=False).values.sort(dim=1).values
+    got = flat_s.sort(dim=1).values[:, :kk]
+    assert torch.equal(got, want)
 
 
 def test_cosine_operands_give_minus_cosine():

@@ -32,7 +32,7 @@ def check(Q, N, d, kprime=16, hint=0, label=""):
         gm = torch.zeros_like(g_op)
         qm[:, c0:c1] = q_op[:, c0:c1]
         gm[:, c0:c1] = g_op[:, c0:c1]
-        cs, ci, dbg = ops.score_topk(qm, gm, d, kprime, hint, debug=True)
+        cs, ci, dbg = ops.score_topk(qm, gm, d, kprime, hint, debug=True, share_thresholds=False)
         torch.cuda.synchronize()
         ref = ref_scores(qm, gm)
         err = (dbg - ref).abs()
@@ -71,22 +71,30 @@ def bench(Q, N, d, kprime=16, iters=5):
     plan = ops.score_plan(Q, N, d, kprime)
     cs = torch.empty(Q, plan["n_lists"], kprime, device=dev)
     ci = torch.empty(Q, plan["n_lists"], kprime, device=dev, dtype=torch.int32)
-    for _ in range(2):
-        ops.score_topk(q_op, g_op, d, kprime, out=(cs, ci))
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
-    e0.record()
-    for _ in range(iters):
-        ops.score_topk(q_op, g_op, d, kprime, out=(cs, ci))
-    e1.record()
-    torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / iters
-    tf = 2.0 * Q * N * d / ms / 1e9
-    print(f"[bench] Q={Q} N={N} d={d} plan={plan}: {ms:.3f} ms  {tf:.1f} TFLOP/s (algorithmic)  {Q / ms * 1e3:.0f} q/s",
-          flush=True)
+    ws = torch.empty(Q, device=dev, dtype=torch.int32)
+    for share in (False, True):
+        for _ in range(2):
+            ops.score_topk(q_op, g_op, d, kprime, out=(cs, ci), share_thresholds=share, thr_workspace=ws)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
+        e0.record()
+        for _ in range(iters):
+            ops.score_topk(q_op, g_op, d, kprime, out=(cs, ci), share_thresholds=share, thr_workspace=ws)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / iters
+        tf = 2.0 * Q * N * d / ms / 1e9
+        print(f"[bench share={int(share)}] Q={Q} N={N} d={d} grid={plan['grid']} lists={plan['n_lists']} "
+              f"stages={plan['stages']} resident={plan['resident']}: {ms:.3f} ms  {tf:.1f} TFLOP/s (algorithmic)  "
+              f"{Q / ms * 1e3:.0f} q/s", flush=True)
 
 
 if __name__ == "__main__":
+    if "--bench" in sys.argv:
+        i = sys.argv.index("--bench")
+        Q, N, d = (int(x) for x in sys.argv[i + 1:i + 4])
+        bench(Q, N, d, iters=int(sys.argv[i + 4]) if len(sys.argv) > i + 4 else 5)
+        sys.exit(0)
     t0 = time.time()
     print(torch.cuda.get_device_name(0), flush=True)
     ok = check(200, 1000, 512, label="resident-small")
@@ -96,4 +104,7 @@ if __name__ == "__main__":
     print("DIAG", "PASS" if ok else "FAIL", f"{time.time() - t0:.1f}s", flush=True)
     if ok and "--quick" not in sys.argv:
         bench(10000, 300000, 512)
-        bench(1000, 10000, 2048)
+        bench(10000, 300000, 256)
+        bench(10000, 300000, 128)
+        bench(10000, 300000, 768)
+        bench(1000, 10000, 2048, iters=20)
