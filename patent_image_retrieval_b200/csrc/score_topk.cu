@@ -260,7 +260,7 @@ __device__ __forceinline__ void process_chunk(const float (&v)[32], int cbase, f
   }
 }
 
-template <bool RESIDENT, int KPP>
+template <bool RESIDENT, int KPP, bool DEBUG>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 score_topk_kernel(const __grid_constant__ CUtensorMap map_q_main, const __grid_constant__ CUtensorMap map_q_ext,
                   const __grid_constant__ CUtensorMap map_g_main, const __grid_constant__ CUtensorMap map_g_ext,
@@ -427,6 +427,7 @@ score_topk_kernel(const __grid_constant__ CUtensorMap map_q_main, const __grid_c
       // published there is >= the query's final k'-th best score, so filtering with the next
       // float above it can only drop rows that are not in the final top-k'.
       float thr_g = INFINITY, published = INFINITY;
+      uint32_t gk_inflight = 0xffffffffu;      // bound loaded during the previous tile, consumed one tile later
       if (gthr != nullptr) {
         const uint32_t gk = ld_cg_u32(gthr);
         if (gk < KEY_INF) thr_g = nextafterf(key2f(gk), INFINITY);
@@ -451,7 +452,7 @@ score_topk_kernel(const __grid_constant__ CUtensorMap map_q_main, const __grid_c
             for (int j = 0; j < 32; ++j)
               if (col0 + cc * 32 + j >= N) va[j] = INFINITY;
           }
-          if (p.debug_scores != nullptr && qrow < p.Q) {
+          if (DEBUG && qrow < p.Q) {
 #pragma unroll
             for (int j = 0; j < 32; ++j)
               if (col0 + cc * 32 + j < N) p.debug_scores[qrow * p.N + col0 + cc * 32 + j] = va[j];
@@ -465,7 +466,7 @@ score_topk_kernel(const __grid_constant__ CUtensorMap map_q_main, const __grid_c
             for (int j = 0; j < 32; ++j)
               if (col0 + (cc + 1) * 32 + j >= N) vb[j] = INFINITY;
           }
-          if (p.debug_scores != nullptr && qrow < p.Q) {
+          if (DEBUG && qrow < p.Q) {
 #pragma unroll
             for (int j = 0; j < 32; ++j)
               if (col0 + (cc + 1) * 32 + j < N) p.debug_scores[qrow * p.N + col0 + (cc + 1) * 32 + j] = vb[j];
@@ -483,9 +484,11 @@ score_topk_kernel(const __grid_constant__ CUtensorMap map_q_main, const __grid_c
             atomicMin(gthr, f2key(thr_list));
             published = thr_list;
           }
-          const uint32_t gk = ld_cg_u32(gthr);
-          if (gk < KEY_INF) thr_g = fminf(thr_g, nextafterf(key2f(gk), INFINITY));
+          // consume the load issued one tile ago (its latency is hidden behind a whole tile),
+          // then put the next one in flight
+          if (gk_inflight < KEY_INF) thr_g = fminf(thr_g, nextafterf(key2f(gk_inflight), INFINITY));
           thr = fminf(thr_list, thr_g);
+          gk_inflight = ld_cg_u32(gthr);
         }
       }
       // publish this strip's lists: one coalesced row of k' entries per query
@@ -560,15 +563,22 @@ Sched sched_from_plan(const hypret_score_plan_t& pl) {
 
 int kpp_of(int kprime) { return kprime <= 16 ? 16 : 32; }
 
+template <bool RESIDENT, int KPP, bool DEBUG>
+int launch_one(const hypret_score_plan_t& plan, const CUtensorMap& mq_main, const CUtensorMap& mq_ext,
+               const CUtensorMap& mg_main, const CUtensorMap& mg_ext, const Params& p, cudaStream_t stream) {
+  cudaError_t e = cudaFuncSetAttribute(score_topk_kernel<RESIDENT, KPP, DEBUG>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, plan.smem_bytes);
+  if (e != cudaSuccess) return (int)e;
+  score_topk_kernel<RESIDENT, KPP, DEBUG><<<plan.grid, NUM_THREADS, plan.smem_bytes, stream>>>(mq_main, mq_ext,
+                                                                                              mg_main, mg_ext, p);
+  return (int)cudaGetLastError();
+}
 template <bool RESIDENT, int KPP>
 int launch_variant(const hypret_score_plan_t& plan, const CUtensorMap& mq_main, const CUtensorMap& mq_ext,
                    const CUtensorMap& mg_main, const CUtensorMap& mg_ext, const Params& p, cudaStream_t stream) {
-  cudaError_t e = cudaFuncSetAttribute(score_topk_kernel<RESIDENT, KPP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       plan.smem_bytes);
-  if (e != cudaSuccess) return (int)e;
-  score_topk_kernel<RESIDENT, KPP><<<plan.grid, NUM_THREADS, plan.smem_bytes, stream>>>(mq_main, mq_ext, mg_main,
-                                                                                       mg_ext, p);
-  return (int)cudaGetLastError();
+  return p.debug_scores != nullptr
+             ? launch_one<RESIDENT, KPP, true>(plan, mq_main, mq_ext, mg_main, mg_ext, p, stream)
+             : launch_one<RESIDENT, KPP, false>(plan, mq_main, mq_ext, mg_main, mg_ext, p, stream);
 }
 
 }  // namespace
@@ -590,7 +600,10 @@ extern "C" int hypret_score_plan(int64_t Q, int64_t N, int d, int kprime, int ma
   {
     const int avail = SMEM_LIMIT - 1024 - BAR_BYTES - lists - a_res_bytes;
     const char* force = getenv("HYPRET_FORCE_STREAM");   // experiments only
-    if (kb <= 8 && avail >= 2 * B_BLK_BYTES && !(force != nullptr && force[0] == '1')) {
+    // Resident query tile only when the gallery ring is still >= 4 stages deep; with the two
+    // stages that D=512 leaves, the MMA pipe starves (measured 863 vs 1103 TFLOP/s).
+    const bool force_res = force != nullptr && force[0] == '0';
+    if (kb <= 8 && avail >= (force_res ? 2 : 4) * B_BLK_BYTES && !(force != nullptr && force[0] == '1')) {
       resident = 1;
       stage_bytes = B_BLK_BYTES;
       stages = avail / B_BLK_BYTES;

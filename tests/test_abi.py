@@ -91,8 +91,8 @@ def test_strip_schedule_covers_every_tile_once(Q, N, d, kp, cap):
     ideal = T * G / P
     if ideal >= 64:
         assert max(per_cta.values()) <= 1.03 * ideal + 2
-    # query tiles of consecutive CTAs in the same step share the gallery range (L2 lock-step)
-    assert p["resident"] == (1 if (d <= 512 and kp <= 16) or d <= 384 else 0) or d > 512
+    # resident query tile only while the gallery ring stays >= 4 stages deep
+    assert p["resident"] == 0 or p["stages"] >= 4
 
 
 def test_c2_plan_numbers():
@@ -100,7 +100,7 @@ def test_c2_plan_numbers():
     p = ops.score_plan(10000, 300000, 512, 16)
     assert (p["grid"], p["n_full"], p["tail_rows"], p["a"], p["b"]) == (148, 0, 79, 1, 69)
     assert p["l1"] == 586 and p["rem_rows"] == 10 and p["m"] == 14 and p["l2"] == 42
-    assert p["n_lists"] == 15 and p["resident"] == 1
+    assert p["n_lists"] == 15 and p["resident"] == 0 and p["stages"] == 4
     with pytest.raises(RuntimeError):
         ops.score_plan(10, 10, 512, 64)          # kprime > 32
 
