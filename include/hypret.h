@@ -132,6 +132,43 @@ int hypret_rerank(const float* q32, const float* g32, int64_t Q, int64_t N, int 
 int hypret_merge_topk(const float* scores, const int64_t* idx, int n_shards, int64_t Q, int k, int descending,
                       float* out_score, int64_t* out_idx, void* stream);
 
+/* Exact pairwise Poincare distance matrix out[i,j] = dist(a_i, p_j), fp32 [n,m].
+ * Replaces the Python loops of 1x1 / 1xN pmath.dist calls (src/train.py:1832-1840, 2304-2320,
+ * 3259, 1033).  Differences formed explicitly in fp32, transcendental tail in fp64. */
+int hypret_pairdist(const float* a, const float* p, int64_t n, int64_t m, int d, float c, float* out, void* stream);
+
+/* Backward of hypret_pairdist (the reference differentiates through ~40 elementwise autograd
+ * nodes per pair, src/train.py:1846).  Given grad_out = dL/dD [n,m] and the forward matrix dmat:
+ *   w_out [n,m]              W (see csrc/pairdist.cu)
+ *   row_sum [n]              sum_j W_ij (1 + c s_ij / alpha_i)
+ *   col_partial [n_partial,m]  partial column sums of W_ij (1 + c s_ij / beta_j); sum over dim 0
+ * so that  dA = a * row_sum[:,None] - W P,  dP = p * col_sum[:,None] - W^T A  (two plain GEMMs
+ * left to the caller).  asq / psq = squared norms of the rows of a / p. */
+int hypret_pairdist_bwd(const float* grad_out, const float* dmat, const float* asq, const float* psq, int64_t n,
+                        int64_t m, float c, float* w_out, float* row_sum, float* col_partial, int n_partial,
+                        void* stream);
+
+/* Metrics of ranked lists, restating the per-query loops of notebooks/retrieval.ipynb:310-324
+ * (MRR@k, Precision@k), :411-420 (AP), :430-437 (nDCG), :439-443 (Recall@k), :446-456 (means).
+ *   ranked       [Q,K] int64 gallery ids, best first, -1 padded
+ *   pos_offsets  [Q+1] int64, pos_items [nnz] int64: CSR of each query's positives in the gallery
+ *   n_pos_total  [Q] int32 or NULL: |P| including positives absent from the gallery (NULL: CSR count)
+ *   ks_host      HOST array of n_ks (<= 8) cut-offs, e.g. {5, 10, 20}
+ *   per_query    [Q, 3 + 3*n_ks] fp64: mrr, ap, ndcg, then (mrr@k, precision@k, recall@k) per k
+ *   means        [3 + 3*n_ks] fp64 or NULL: column means in a fixed (deterministic) order */
+int hypret_retrieval_metrics(const int64_t* ranked, int64_t Q, int K, const int64_t* pos_offsets,
+                             const int64_t* pos_items, const int32_t* n_pos_total, const int32_t* ks_host, int n_ks,
+                             double* per_query, double* means, void* stream);
+
+/* Average precision over FULL score rows (higher = better) by rank counting, no sort.
+ * grouped_ties != 0: sklearn.average_precision_score semantics (src/train.py:3285,
+ * src/auxiliary.py:200-224); == 0: ranking order with lower-index tie-break
+ * (notebooks/retrieval.ipynb:411-420).  Rows without an in-range positive or with a NaN/inf
+ * score get valid = 0 and are left out of the mean (src/train.py:3244-3262).
+ *   scores [Q,N] fp32, ap [Q] fp64, valid [Q] int32, mean_ap [1] fp64 or NULL */
+int hypret_ap_full(const float* scores, int64_t Q, int64_t N, const int64_t* pos_offsets, const int64_t* pos_items,
+                   int grouped_ties, double* ap, int32_t* valid, double* mean_ap, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

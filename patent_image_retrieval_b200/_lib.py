@@ -52,6 +52,13 @@ SIGNATURES = {
                                   c_void_p, c_void_p, c_void_p, c_void_p]),
     "hypret_rerank": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int, c_float, c_int, c_void_p, c_void_p, c_int,
                               c_int, c_int, c_int64, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "hypret_pairdist": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int, c_float, c_void_p, c_void_p]),
+    "hypret_pairdist_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_float, c_void_p,
+                                    c_void_p, c_void_p, c_int, c_void_p]),
+    "hypret_retrieval_metrics": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p, POINTER(c_int32),
+                                         c_int, c_void_p, c_void_p, c_void_p]),
+    "hypret_ap_full": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p,
+                               c_void_p]),
     "hypret_merge_topk": (c_int, [c_void_p, c_void_p, c_int, c_int64, c_int, c_int, c_void_p, c_void_p, c_void_p]),
 }
 

@@ -89,4 +89,50 @@ int hypret_merge_topk(const float* scores, const int64_t* idx, int n_shards, int
                                   static_cast<cudaStream_t>(stream));
 }
 
+int hypret_pairdist(const float* a, const float* p, int64_t n, int64_t m, int d, float c, float* out, void* stream) {
+  if (n < 0 || m < 0 || d < 4 || (d & 3) || !(c > 0.f)) return HYPRET_EINVAL;
+  if (n == 0 || m == 0) return HYPRET_OK;
+  if (a == nullptr || p == nullptr || out == nullptr || !aligned16(a) || !aligned16(p)) return HYPRET_EINVAL;
+  int rc = check_device();
+  if (rc != HYPRET_OK) return rc;
+  return hypret_launch_pairdist(a, p, n, m, d, c, out, static_cast<cudaStream_t>(stream));
+}
+
+int hypret_pairdist_bwd(const float* grad_out, const float* dmat, const float* asq, const float* psq, int64_t n,
+                        int64_t m, float c, float* w_out, float* row_sum, float* col_partial, int n_partial,
+                        void* stream) {
+  if (n < 0 || m < 0 || !(c > 0.f) || n_partial < 1 || n_partial > 65535) return HYPRET_EINVAL;
+  if (n == 0 || m == 0) return HYPRET_OK;
+  if (grad_out == nullptr || dmat == nullptr || asq == nullptr || psq == nullptr || w_out == nullptr ||
+      row_sum == nullptr || col_partial == nullptr)
+    return HYPRET_EINVAL;
+  int rc = check_device();
+  if (rc != HYPRET_OK) return rc;
+  return hypret_launch_pairdist_bwd(grad_out, dmat, asq, psq, n, m, c, w_out, row_sum, col_partial, n_partial,
+                                    static_cast<cudaStream_t>(stream));
+}
+
+int hypret_retrieval_metrics(const int64_t* ranked, int64_t Q, int K, const int64_t* pos_offsets,
+                             const int64_t* pos_items, const int32_t* n_pos_total, const int32_t* ks_host, int n_ks,
+                             double* per_query, double* means, void* stream) {
+  if (Q < 0 || K < 1 || n_ks < 0 || n_ks > 8 || (n_ks > 0 && ks_host == nullptr)) return HYPRET_EINVAL;
+  for (int i = 0; i < n_ks; ++i)
+    if (ks_host[i] < 1) return HYPRET_EINVAL;
+  if (ranked == nullptr || pos_offsets == nullptr || per_query == nullptr) return HYPRET_EINVAL;
+  int rc = check_device();
+  if (rc != HYPRET_OK) return rc;
+  return hypret_launch_retrieval_metrics(ranked, Q, K, pos_offsets, pos_items, n_pos_total, ks_host, n_ks, per_query,
+                                         means, static_cast<cudaStream_t>(stream));
+}
+
+int hypret_ap_full(const float* scores, int64_t Q, int64_t N, const int64_t* pos_offsets, const int64_t* pos_items,
+                   int grouped_ties, double* ap, int32_t* valid, double* mean_ap, void* stream) {
+  if (Q < 0 || N < 1) return HYPRET_EINVAL;
+  if (scores == nullptr || pos_offsets == nullptr || ap == nullptr || valid == nullptr) return HYPRET_EINVAL;
+  int rc = check_device();
+  if (rc != HYPRET_OK) return rc;
+  return hypret_launch_ap_full(scores, Q, N, pos_offsets, pos_items, grouped_ties != 0, ap, valid, mean_ap,
+                               static_cast<cudaStream_t>(stream));
+}
+
 }  // extern "C"

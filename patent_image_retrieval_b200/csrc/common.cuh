@@ -239,3 +239,13 @@ int hypret_launch_rerank(const float* q32, const float* g32, int64_t Q, int64_t 
                          cudaStream_t stream);
 int hypret_launch_merge_topk(const float* scores, const int64_t* idx, int W, int64_t Q, int k, int descending,
                              float* out_score, int64_t* out_idx, cudaStream_t stream);
+int hypret_launch_pairdist(const float* a, const float* p, int64_t n, int64_t m, int d, float c, float* out,
+                           cudaStream_t stream);
+int hypret_launch_retrieval_metrics(const int64_t* ranked, int64_t Q, int K, const int64_t* pos_off,
+                                    const int64_t* pos_items, const int32_t* n_pos_total, const int32_t* ks_host,
+                                    int n_ks, double* per_query, double* means, cudaStream_t stream);
+int hypret_launch_ap_full(const float* scores, int64_t Q, int64_t N, const int64_t* pos_off, const int64_t* pos_items,
+                          int grouped_ties, double* ap, int32_t* valid, double* mean_ap, cudaStream_t stream);
+int hypret_launch_pairdist_bwd(const float* g, const float* dmat, const float* asq, const float* psq, int64_t n,
+                               int64_t m, float c, float* w_out, float* row_sum, float* col_partial, int n_partial,
+                               cudaStream_t stream);

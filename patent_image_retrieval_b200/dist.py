@@ -30,11 +30,12 @@ def gather_candidates(score: torch.Tensor, idx: torch.Tensor, group=None):
     """all_gather the per-shard ``[Q,k]`` lists -> ``([W,Q,k] scores, [W,Q,k] global idx)``.
     Backend-agnostic (NCCL on GPUs, gloo in the CPU tests)."""
     world = dist.get_world_size(group)
-    gs = torch.empty((world,) + tuple(score.shape), dtype=score.dtype, device=score.device)
-    gi = torch.empty((world,) + tuple(idx.shape), dtype=idx.dtype, device=idx.device)
-    dist.all_gather_into_tensor(gs, score.contiguous(), group=group)
+    Q = score.shape[0]
+    gs = torch.empty((world * Q,) + tuple(score.shape[1:]), dtype=score.dtype, device=score.device)
+    gi = torch.empty((world * Q,) + tuple(idx.shape[1:]), dtype=idx.dtype, device=idx.device)
+    dist.all_gather_into_tensor(gs, score.contiguous(), group=group)     # concatenated along dim 0
     dist.all_gather_into_tensor(gi, idx.contiguous(), group=group)
-    return gs, gi
+    return gs.view((world,) + tuple(score.shape)), gi.view((world,) + tuple(idx.shape))
 
 
 class ShardedGalleryIndex:

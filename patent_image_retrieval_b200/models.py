@@ -1,0 +1,195 @@
+"""Drop-in hyperbolic projection head: the reference's ``models.py`` classes with their
+signatures, attribute names and state-dict keys, minus the geoopt dependency.
+
+    MobiusLinear / mobius_linear          /root/reference/src/models.py:255-318
+    DeeperHyperbolicEncoder               src/models.py:447-505
+    HyperbolicEmbeddingModel              src/models.py:507-784
+    FigureOnlyHyperbolicModel             src/models.py:788-838
+
+State-dict keys are the reference's: ``encoder.first_layer.{weight,bias}``,
+``encoder.final_layer.{weight,bias}``, ``label_emb`` -- checkpoints such as
+``best_retrieval_model_c{c}_e{dim}.pt`` (src/train.py:1631) round-trip.  ``k`` stays a plain
+attribute (a 1-element fp32 tensor ``[-c]``), not a buffer, exactly as in the reference.
+
+Differences that restate intended behaviour instead of a crash / an accident:
+  * src/models.py:306 applies ``F.dropout(weight, dropout)`` with ``dropout`` undefined
+    (NameError as shipped): weight dropout is the identity here;
+  * the reference flips torch's default dtype to float64 at import (src/models.py:248-249);
+    this module does not touch global state -- construct under ``torch.set_default_dtype`` if the
+    accidental fp64 parameters are wanted;
+  * the per-pair Python loops of ``calculate_pair_loss`` are evaluated as one batched distance
+    (same arithmetic per pair).
+The hierarchy / regulariser losses (src/models.py:550-674) are outside the retrieval hot path
+and are not provided.
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import geoopt_shim as gt
+from .geoopt_shim import pmath
+
+DROPOUT_RATE = 0.1      # src/models.py:16
+
+
+class MobiusLinear(nn.Linear):
+    def __init__(self, *args, hyperbolic_input=True, hyperbolic_bias=True, nonlin=None, c=1.0, **kwargs):
+        super().__init__(*args, **kwargs)
+        self.ball = gt.PoincareBall(c=c)
+        if self.bias is not None:
+            if hyperbolic_bias:
+                self.bias = gt.ManifoldParameter(self.bias, manifold=self.ball)
+                with torch.no_grad():
+                    self.bias.set_(pmath.expmap0(self.bias.normal_() * 1e-3, k=self.ball.k))
+        with torch.no_grad():
+            fin, fout = self.weight.size()
+            k = (6 / (fin + fout)) ** 0.5  # xavier uniform
+            self.weight.uniform_(-k, k)
+        self.hyperbolic_bias = hyperbolic_bias
+        self.hyperbolic_input = hyperbolic_input
+        self.nonlin = nonlin
+
+    def forward(self, input):
+        return mobius_linear(input, weight=self.weight, bias=self.bias, hyperbolic_input=self.hyperbolic_input,
+                             nonlin=self.nonlin, hyperbolic_bias=self.hyperbolic_bias, k=self.ball.k)
+
+    def extra_repr(self):
+        info = super().extra_repr()
+        info += ", hyperbolic_input={}".format(self.hyperbolic_input)
+        if self.bias is not None:
+            info += ", hyperbolic_bias={}".format(self.hyperbolic_bias)
+        return info
+
+
+def mobius_linear(input, weight, bias=None, hyperbolic_input=True, hyperbolic_bias=True, nonlin=None, k=-1.0):
+    weight = weight.to(input.dtype)
+    if bias is not None:
+        bias = bias.to(input.dtype)
+    if hyperbolic_input:
+        output = pmath.mobius_matvec(weight, input, k=k)
+    else:
+        output = F.linear(input, weight)
+        output = pmath.expmap0(output, k=k)
+    if bias is not None:
+        if not hyperbolic_bias:
+            bias = pmath.expmap0(bias, k=k)
+        output = pmath.mobius_add(output, bias, k=k)
+    if nonlin is not None:
+        output = pmath.mobius_fn_apply(nonlin, output, k=k)
+    return pmath.project(output, k=k)
+
+
+class DeeperHyperbolicEncoder(nn.Module):
+    def __init__(self, input_dim, hidden_dims, output_dim, c=1.0, dropout_rate=0.3):
+        super().__init__()
+        self.c = c
+        self.ball = gt.PoincareBall(c=c)
+        self.k = torch.tensor([-c], dtype=torch.float32)
+        self.dropout_rate = dropout_rate
+        self.first_layer = MobiusLinear(input_dim, hidden_dims[0], hyperbolic_input=False, c=c)
+        self.final_layer = MobiusLinear(hidden_dims[0], output_dim, hyperbolic_input=True, c=c)
+
+    def forward(self, x):
+        self.k = self.k.to(x.device)
+        x = F.dropout(x, p=self.dropout_rate, training=self.training)
+        x = self.first_layer(x)
+        x = pmath.mobius_fn_apply(torch.tanh, x, k=self.k)
+        x = F.dropout(x, p=self.dropout_rate, training=self.training)
+        x = self.final_layer(x)
+        return pmath.project(x, k=self.k)
+
+
+def _pair_distances(figure_embeddings, all_pairs, k):
+    """Batched replacement of the per-pair loop (src/models.py:712-719, 824-829)."""
+    return pmath.dist(figure_embeddings[all_pairs[:, 0]], figure_embeddings[all_pairs[:, 1]], k=k)
+
+
+def _all_pairs(figure_embeddings, positive_pairs, negative_pairs):
+    if positive_pairs.dim() == 1:
+        positive_pairs = positive_pairs.view(-1, 2)
+    all_pairs = positive_pairs
+    if negative_pairs is not None and negative_pairs.numel() > 0:
+        if negative_pairs.dim() == 1:
+            negative_pairs = negative_pairs.view(-1, 2)
+        all_pairs = torch.cat([positive_pairs, negative_pairs], dim=0)
+    labels = torch.zeros(len(all_pairs), device=figure_embeddings.device)
+    labels[:len(positive_pairs)] = 1.0
+    return all_pairs, labels
+
+
+class HyperbolicEmbeddingModel(nn.Module):
+    def __init__(self, feature_num, embed_dim, label_num, hidden_dims=[256, 128], c=1.0, **kwargs):
+        super().__init__(**kwargs)
+        self.c = c
+        self.embed_dim = embed_dim
+        self.k = torch.tensor([-c], dtype=torch.float32)
+        self.ball = gt.PoincareBall(c=self.c)
+        self.temperature = 0.07
+        label_points = torch.randn(label_num, embed_dim) * 0.1
+        label_points = pmath.expmap0(label_points, k=self.k)
+        self.label_emb = gt.ManifoldParameter(label_points, manifold=self.ball)
+        self.encoder = DeeperHyperbolicEncoder(input_dim=feature_num, hidden_dims=hidden_dims, output_dim=embed_dim,
+                                               c=c, dropout_rate=DROPOUT_RATE)
+
+    def encode_figures(self, features):
+        """Encodes Euclidean figure features into the hyperbolic space (src/models.py:537-548)."""
+        features = torch.as_tensor(features, dtype=torch.float32)
+        features = F.dropout(features, p=DROPOUT_RATE, training=self.training)
+        encoded = self.encoder(features)
+        self.ball.assert_check_point_on_manifold(encoded)
+        return encoded
+
+    def calculate_pair_loss(self, figure_embeddings, positive_pairs, negative_pairs):
+        """Per query figure: cross-entropy of -d/T over its pairs, positive first (src/models.py:676-757)."""
+        self.k = self.k.to(figure_embeddings.device)
+        if positive_pairs is None or positive_pairs.numel() == 0:
+            return torch.tensor(0.0, device=figure_embeddings.device)
+        all_pairs, labels = _all_pairs(figure_embeddings, positive_pairs, negative_pairs)
+        similarities = -_pair_distances(figure_embeddings, all_pairs, self.k) / self.temperature
+        total_loss, num_queries = 0.0, 0
+        for query_idx in torch.unique(all_pairs[:, 0]):
+            mask = all_pairs[:, 0] == query_idx
+            q_lab = labels[mask]
+            if not q_lab.any():
+                continue
+            total_loss = total_loss + F.cross_entropy(similarities[mask].unsqueeze(0), q_lab.argmax().unsqueeze(0))
+            num_queries += 1
+        if num_queries > 0:
+            return total_loss / num_queries
+        return torch.tensor(0.0, device=figure_embeddings.device)
+
+    def forward(self, figure_features, implication_pairs=None, exclusion_pairs=None):
+        self.k = self.k.to(figure_features.device)
+        return self.encode_figures(figure_features)
+
+
+class FigureOnlyHyperbolicModel(nn.Module):
+    def __init__(self, feature_num, embed_dim, hidden_dims=[256, 128], c=1.0, dropout_rate=0.3):
+        super().__init__()
+        self.c = c
+        self.embed_dim = embed_dim
+        self.k = torch.tensor([-c], dtype=torch.float32)
+        self.ball = gt.PoincareBall(c=self.c)
+        self.encoder = DeeperHyperbolicEncoder(input_dim=feature_num, hidden_dims=hidden_dims, output_dim=embed_dim,
+                                               c=c, dropout_rate=dropout_rate)
+
+    def encode_figures(self, features):
+        features = F.dropout(features, p=self.encoder.dropout_rate, training=self.training)
+        encoded = self.encoder(features)
+        self.ball.assert_check_point_on_manifold(encoded)
+        return encoded
+
+    def calculate_pair_loss(self, figure_embeddings, positive_pairs, negative_pairs, temperature=0.07):
+        """BCE-with-logits on -d/T over positive + negative pairs (src/models.py:809-832)."""
+        self.k = self.k.to(figure_embeddings.device)
+        if positive_pairs is None or positive_pairs.numel() == 0:
+            return torch.tensor(0.0, device=figure_embeddings.device)
+        all_pairs, labels = _all_pairs(figure_embeddings, positive_pairs, negative_pairs)
+        similarities = -_pair_distances(figure_embeddings, all_pairs, self.k) / temperature
+        return F.binary_cross_entropy_with_logits(similarities, labels.float())
+
+    def forward(self, features):
+        self.k = self.k.to(features.device)
+        return self.encode_figures(features)

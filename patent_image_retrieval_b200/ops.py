@@ -151,3 +151,89 @@ def merge_topk(scores: torch.Tensor, idx: torch.Tensor, descending: bool = False
         _lib.check(_lib.load().hypret_merge_topk(_ptr(scores), _ptr(idx), W, Q, k, int(bool(descending)), _ptr(out_s),
                                                  _ptr(out_i), _stream()))
     return out_s, out_i
+
+
+def pairdist(a: torch.Tensor, p: torch.Tensor, c: float) -> torch.Tensor:
+    """Exact Poincare distance matrix ``[n,m]`` (fp32) between on-ball points ``a [n,d]`` and ``p [m,d]``."""
+    _need_cuda(a, p)
+    a = a.contiguous().float()
+    p = p.contiguous().float()
+    n, d = a.shape
+    m = p.shape[0]
+    out = torch.empty(n, m, dtype=torch.float32, device=a.device)
+    with torch.cuda.device(a.device):
+        _lib.check(_lib.load().hypret_pairdist(_ptr(a), _ptr(p), n, m, d, float(c), _ptr(out), _stream()))
+    return out
+
+
+METRIC_COLUMNS = ("mrr", "ap", "ndcg")
+
+
+def metric_names(ks):
+    names = list(METRIC_COLUMNS)
+    for k in ks:
+        names += [f"mrr@{k}", f"precision@{k}", f"recall@{k}"]
+    return names
+
+
+def retrieval_metrics(ranked: torch.Tensor, pos_offsets: torch.Tensor, pos_items: torch.Tensor, ks=(5, 10, 20),
+                      n_pos_total: Optional[torch.Tensor] = None):
+    """Metrics of ranked lists ``[Q,K]`` (reference notebooks/retrieval.ipynb:310-324,411-456).
+    Returns ``(means: dict name -> float, per_query [Q, 3+3*len(ks)] fp64 on the device)``."""
+    _need_cuda(ranked, pos_offsets, pos_items, n_pos_total)
+    ranked = ranked.contiguous().to(torch.int64)
+    pos_offsets = pos_offsets.contiguous().to(torch.int64)
+    pos_items = pos_items.contiguous().to(torch.int64)
+    if n_pos_total is not None:
+        n_pos_total = n_pos_total.contiguous().to(torch.int32)
+    Q, K = ranked.shape
+    ks = [int(k) for k in ks]
+    ncol = 3 + 3 * len(ks)
+    per_query = torch.empty(Q, ncol, dtype=torch.float64, device=ranked.device)
+    means = torch.zeros(ncol, dtype=torch.float64, device=ranked.device)
+    ks_arr = (ctypes.c_int32 * max(1, len(ks)))(*ks)
+    with torch.cuda.device(ranked.device):
+        _lib.check(_lib.load().hypret_retrieval_metrics(_ptr(ranked), Q, K, _ptr(pos_offsets), _ptr(pos_items),
+                                                        _ptr(n_pos_total), ks_arr, len(ks), _ptr(per_query),
+                                                        _ptr(means), _stream()))
+    return dict(zip(metric_names(ks), means.tolist())), per_query
+
+
+def ap_full(scores: torch.Tensor, pos_offsets: torch.Tensor, pos_items: torch.Tensor, grouped_ties: bool = True):
+    """AP over full score rows ``[Q,N]`` (higher = better).  ``grouped_ties`` = sklearn semantics
+    (reference src/train.py:3285).  Returns ``(mean_ap float, ap [Q] fp64, valid [Q] int32)``."""
+    _need_cuda(scores, pos_offsets, pos_items)
+    scores = scores.contiguous().float()
+    pos_offsets = pos_offsets.contiguous().to(torch.int64)
+    pos_items = pos_items.contiguous().to(torch.int64)
+    Q, N = scores.shape
+    ap = torch.empty(Q, dtype=torch.float64, device=scores.device)
+    valid = torch.empty(Q, dtype=torch.int32, device=scores.device)
+    mean = torch.zeros(1, dtype=torch.float64, device=scores.device)
+    with torch.cuda.device(scores.device):
+        _lib.check(_lib.load().hypret_ap_full(_ptr(scores), Q, N, _ptr(pos_offsets), _ptr(pos_items),
+                                              int(bool(grouped_ties)), _ptr(ap), _ptr(valid), _ptr(mean), _stream()))
+    return float(mean.item()), ap, valid
+
+
+def pairdist_bwd(grad_out: torch.Tensor, dmat: torch.Tensor, asq: torch.Tensor, psq: torch.Tensor, c: float,
+                 n_partial: int = 32):
+    """Weights of the distance-matrix backward: returns ``(W [n,m], row_sum [n], col_sum [m])``."""
+    _need_cuda(grad_out, dmat, asq, psq)
+    grad_out = grad_out.contiguous().float()
+    dmat = dmat.contiguous()
+    n, m = dmat.shape
+    n_partial = max(1, min(n_partial, n))
+    w = torch.empty_like(dmat)
+    rs = torch.empty(n, dtype=torch.float32, device=dmat.device)
+    cp = torch.empty(n_partial, m, dtype=torch.float32, device=dmat.device)
+    with torch.cuda.device(dmat.device):
+        _lib.check(_lib.load().hypret_pairdist_bwd(_ptr(grad_out), _ptr(dmat), _ptr(asq.contiguous()),
+                                                   _ptr(psq.contiguous()), n, m, float(c), _ptr(w), _ptr(rs), _ptr(cp),
+                                                   n_partial, _stream()))
+    return w, rs, cp.sum(dim=0)
+
+
+def row_sqnorm(x: torch.Tensor) -> torch.Tensor:
+    """||x_i||^2 per row ([n,D] reduction; negligible next to the [n,n] work)."""
+    return x.float().pow(2).sum(dim=1)

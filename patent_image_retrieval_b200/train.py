@@ -1,0 +1,143 @@
+"""Drop-in ``train_hyp`` losses of the reference on the CUDA path.
+
+    hyperbolic_contrastive_loss(anchor, positive, k, temperature)     /root/reference/src/train.py:2291-2336
+    in-batch loss of train_hyperbolic_contrastive                     src/train.py:1832-1844
+    sample_to_prototype_loss(...)                                     src/train.py:1010-1045
+    train_hyperbolic_contrastive(...)                                 src/train.py:1792-1910
+
+The reference builds the n x n matrix with an O(n^2) Python double loop of 1x1 ``pmath.dist``
+calls (~40 kernel launches each) and differentiates through all of them.  Here the matrix is one
+exact CUDA kernel (``hypret_pairdist``) and its backward is closed-form (``hypret_pairdist_bwd``
++ two dense products), wrapped in one autograd Function.  CUDA tensors only.
+"""
+from __future__ import annotations
+
+import random
+from typing import Optional
+
+import torch
+import torch.nn.functional as F
+
+from . import ops
+from .geoopt_shim import pmath
+
+
+def _c_of(k) -> float:
+    return float(-torch.as_tensor(k).reshape(-1)[0])
+
+
+class PairwiseDistance(torch.autograd.Function):
+    """D[i,j] = dist(a_i, p_j) on the Poincare ball, exact fp32, with the analytic backward."""
+
+    @staticmethod
+    def forward(ctx, a, p, c: float):
+        a32, p32 = a.contiguous().float(), p.contiguous().float()
+        d = ops.pairdist(a32, p32, c)
+        ctx.save_for_backward(a32, p32, d)
+        ctx.c = c
+        ctx.in_dtypes = (a.dtype, p.dtype)
+        return d
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        a, p, d = ctx.saved_tensors
+        w, rs, cs = ops.pairdist_bwd(grad_out, d, ops.row_sqnorm(a), ops.row_sqnorm(p), ctx.c)
+        da = a * rs[:, None] - w @ p          # plain GEMMs (cuBLAS fp32)
+        dp = p * cs[:, None] - w.t() @ a
+        return da.to(ctx.in_dtypes[0]), dp.to(ctx.in_dtypes[1]), None
+
+
+def pairwise_dist(a, p, k):
+    """[n,D] x [m,D] -> [n,m] Poincare distances (differentiable)."""
+    return PairwiseDistance.apply(a, p, _c_of(k))
+
+
+def in_batch_contrastive_loss(anchors, positives, k, temperature=0.1):
+    """The loss inside train_hyperbolic_contrastive (src/train.py:1832-1844): CE over rows."""
+    sim = -pairwise_dist(anchors, positives, k) / temperature
+    return F.cross_entropy(sim, torch.arange(anchors.shape[0], device=sim.device))
+
+
+def hyperbolic_contrastive_loss(anchor_embeddings, positive_embeddings, k, temperature=0.07):
+    """Symmetric InfoNCE in hyperbolic space (src/train.py:2291-2336)."""
+    n = anchor_embeddings.shape[0]
+    similarities = -pairwise_dist(anchor_embeddings, positive_embeddings, k) / temperature
+    labels = torch.arange(n, device=similarities.device)
+    return (F.cross_entropy(similarities, labels) + F.cross_entropy(similarities.t(), labels)) / 2
+
+
+def sample_to_prototype_loss(samples, pos_prototypes, neg_prototypes, num_neg_samples, k, margin=0.1,
+                             temperature=0.07):
+    """src/train.py:1010-1045, including its (probably unintended) [B,B] positive matrix
+    (line 1033 broadcasts [B,1,D] against [1,B,D])."""
+    batch_size, embed_dim = samples.shape
+    neg = neg_prototypes.view(batch_size, num_neg_samples, embed_dim)
+    pos_distances = pairwise_dist(samples, pos_prototypes.to(samples.dtype), k)                    # [B,B]
+    neg_distances = pmath.dist(samples.unsqueeze(1), neg.to(samples.dtype), k=k).mean(dim=1)       # [B]
+    return torch.relu(pos_distances.unsqueeze(1) - neg_distances + margin).mean()
+
+
+def create_n_pair_batch(indices, batch_size, figure_to_pos_figures, X_figures_tensor, device):
+    """src/train.py:1758-1789 (host-side sampling; unchanged semantics)."""
+    random.shuffle(indices)
+    for i in range(0, len(indices), batch_size):
+        anchors = indices[i:i + batch_size]
+        positives, valid_anchors = [], []
+        for anchor in anchors:
+            cand = figure_to_pos_figures.get(anchor, [])
+            if cand:
+                positives.append(random.choice(cand))
+                valid_anchors.append(anchor)
+        pairs = [(a, p) for a, p in zip(valid_anchors, positives) if a != p]
+        if not pairs:
+            continue
+        a_idx, p_idx = zip(*pairs)
+        batch_x = X_figures_tensor[list(a_idx) + list(p_idx)].to(device)
+        yield batch_x, len(a_idx), list(a_idx), list(p_idx)
+
+
+def train_hyperbolic_contrastive(model, X_figures, figure_to_pos_figures, train_indices, val_indices, epochs=1,
+                                 batch_size=128, lr=1e-3, temperature=0.07, device=None, save_path="best_model.pt",
+                                 patience=5):
+    """src/train.py:1792-1910 with the double loop replaced by the CUDA distance matrix."""
+    device = torch.device(device) if device is not None else torch.device("cuda")
+    model = model.to(device)
+    model.k = model.k.to(device)
+    X = torch.as_tensor(X_figures, dtype=torch.float32)
+    optimizer = torch.optim.Adam(model.parameters(), lr=lr)
+    best_val, bad_epochs = float("inf"), 0
+    history = []
+    for epoch in range(1, epochs + 1):
+        model.train()
+        tot, nb = 0.0, 0
+        for batch_x, n, _, _ in create_n_pair_batch(list(train_indices), batch_size, figure_to_pos_figures, X, device):
+            enc = model.encode_figures(batch_x)
+            loss = in_batch_contrastive_loss(enc[:n], enc[n:], model.k, temperature)
+            optimizer.zero_grad()
+            loss.backward()
+            optimizer.step()
+            tot += float(loss.item())
+            nb += 1
+        model.eval()
+        vtot, vb = 0.0, 0
+        with torch.no_grad():
+            for batch_x, n, _, _ in create_n_pair_batch(list(val_indices), batch_size, figure_to_pos_figures, X, device):
+                enc = model.encode_figures(batch_x)
+                vtot += float(in_batch_contrastive_loss(enc[:n], enc[n:], model.k, temperature).item())
+                vb += 1
+        train_loss, val_loss = tot / max(nb, 1), vtot / max(vb, 1)
+        history.append((epoch, train_loss, val_loss))
+        if val_loss < best_val:
+            best_val, bad_epochs = val_loss, 0
+            if save_path:
+                torch.save(model.state_dict(), save_path)
+        else:
+            bad_epochs += 1
+            if bad_epochs >= patience:
+                break
+    if save_path:
+        try:
+            model.load_state_dict(torch.load(save_path))
+        except Exception:
+            pass
+    return model, history

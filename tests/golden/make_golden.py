@@ -67,6 +67,101 @@ def run_notebook_metrics(ranked_names, positives_sets):
     return {n: np.asarray(ns[n], dtype=np.float64) for n in names}
 
 
+def reference_code_with_shim():
+    """Run the REFERENCE'S OWN ``models.py`` / ``train.py`` functions (imported from
+    /root/reference/src) with geoopt replaced by this repo's shim -- geoopt itself is not
+    installable.  This pins the reference's call order, reductions, sentinels and metric
+    conventions around the (unpinned) hyperbolic arithmetic.  ``refshim_*`` keys.
+
+    Patches needed to make the shipped code run at all:
+      * ``models.dropout = 0.0``   (src/models.py:306 uses an undefined global ``dropout``)
+      * ``self.temperature`` is never set in HyperbolicEmbeddingModel (src/models.py:725) -- that
+        method is not exercised here
+      * missing optional imports (torch_geometric, matplotlib, seaborn) are stubbed
+    """
+    import types
+    from patent_image_retrieval_b200 import geoopt_shim
+    geoopt_shim.install()
+    for name in ["torch_geometric", "torch_geometric.utils", "matplotlib", "matplotlib.pyplot", "matplotlib.patches",
+                 "matplotlib.cm", "seaborn", "geoopt.optim.radam"]:
+        if name not in sys.modules:
+            m = types.ModuleType(name)
+            m.__path__ = []
+            def _ga(a):
+                if a.startswith("__"):
+                    raise AttributeError(a)
+                return lambda *x, **k: None
+            m.__getattr__ = _ga
+            sys.modules[name] = m
+    sys.path.insert(0, str(REF / "src"))
+    import models as ref_models          # flips the default dtype to float64 (src/models.py:248-249)
+    import train as ref_train
+    ref_models.dropout = 0.0
+    out = {}
+    torch.manual_seed(11)
+    # ---- projection head (models.py:291-318, 481-505, 803-807), fp64 as the reference really runs ----
+    for c in (1.0, 0.5):
+        tag = str(c).replace(".", "p")
+        model = ref_models.FigureOnlyHyperbolicModel(32, 16, hidden_dims=[24], c=c, dropout_rate=0.3).eval()
+        x = torch.randn(10, 32, dtype=torch.float32) * 0.5
+        x[0] = 0
+        with torch.no_grad():
+            y = model(x)
+        sd = model.state_dict()
+        out[f"refshim_head_x_c{tag}"] = x.numpy()
+        out[f"refshim_head_y_c{tag}"] = y.numpy()
+        for key, v in sd.items():
+            out[f"refshim_head_{key}_c{tag}"] = v.numpy()
+    # ---- evaluate_retrieval (train.py:3108-3296) incl. multi-positive, out-of-range, sentinels ---------
+    c = 2.0
+    model = ref_models.HyperbolicEmbeddingModel(32, 16, label_num=60, hidden_dims=[24], c=c).eval()
+    X = torch.randn(40, 32, dtype=torch.float32) * 0.5
+    label_offsets = {"patents": 0, "medium_cpcs": 45, "big_cpcs": 55, "main_cpcs": 58}
+    rng = np.random.default_rng(5)
+    f2p = {}
+    for i in range(40):
+        r = rng.random()
+        if r < 0.5:
+            f2p[i] = int(rng.integers(0, 45))
+        elif r < 0.8:
+            f2p[i] = [int(v) for v in rng.choice(50, size=3, replace=False)]     # some >= 45: out of range
+        elif r < 0.9:
+            f2p[i] = [50, 57]                                                      # no valid positive
+    eval_indices = list(range(40))
+    import io, contextlib
+    with contextlib.redirect_stdout(io.StringIO()):
+        m_ap = ref_train.evaluate_retrieval(model, X, eval_indices, f2p, label_offsets, "cpu", 16)
+        empty = ref_train.evaluate_retrieval(model, X, [], f2p, label_offsets, "cpu", 16)
+        noff = ref_train.evaluate_retrieval(model, X, eval_indices, f2p, {"cpcs": 3}, "cpu", 16)
+    out["refshim_eval_map"] = np.asarray(m_ap)
+    out["refshim_eval_empty"] = np.asarray(empty)
+    out["refshim_eval_no_offset"] = np.asarray(noff)
+    out["refshim_eval_X"] = X.numpy()
+    for key, v in model.state_dict().items():
+        out[f"refshim_eval_{key}"] = v.numpy()
+    out["refshim_eval_f2p_json"] = np.frombuffer(json.dumps({str(k): v for k, v in f2p.items()}).encode(), dtype=np.uint8)
+    # ---- in-batch losses (train.py:2291-2336, 1010-1045), autograd through the double loop ---------------
+    k = torch.tensor([-0.5], dtype=torch.float64)
+    a = pmath_pts(7, 12, 0.25).requires_grad_(True)
+    p = pmath_pts(7, 12, 0.25).requires_grad_(True)
+    loss = ref_train.hyperbolic_contrastive_loss(a, p, k, temperature=0.07)
+    loss.backward()
+    out["refshim_hcl_a"], out["refshim_hcl_p"] = a.detach().numpy(), p.detach().numpy()
+    out["refshim_hcl_loss"] = loss.detach().numpy()
+    out["refshim_hcl_da"], out["refshim_hcl_dp"] = a.grad.numpy(), p.grad.numpy()
+    s_, pos, neg = pmath_pts(5, 12, 0.25), pmath_pts(5, 12, 0.25), pmath_pts(15, 12, 0.25)
+    out["refshim_s2p_s"], out["refshim_s2p_pos"], out["refshim_s2p_neg"] = s_.numpy(), pos.numpy(), neg.numpy()
+    out["refshim_s2p_loss"] = ref_train.sample_to_prototype_loss(s_, pos, neg, 3, k, margin=0.1).numpy()
+    torch.set_default_dtype(torch.float32)
+    return out
+
+
+def pmath_pts(n, d, scale):
+    from oracle import pmath
+    k = torch.tensor(-0.5, dtype=torch.float64)
+    return pmath.project(pmath.expmap0(torch.randn(n, d, dtype=torch.float64) * scale, k=k), k=k)
+
+
 def main():
     rng = np.random.default_rng(1234)
     out = {}
@@ -135,6 +230,7 @@ def main():
         out[f"kat_mlin_c{tag}"] = head.mobius_linear(x, w, b, hyperbolic_input=True, k=k).numpy()
         out[f"kat_mlin_e_c{tag}"] = head.mobius_linear(u, w, b, hyperbolic_input=False, k=k).numpy()
 
+    out.update(reference_code_with_shim())
     np.savez_compressed(HERE / "golden.npz", **out)
     print("wrote", HERE / "golden.npz", {k: v.shape for k, v in out.items() if k.startswith("ref_")})
 

@@ -1,0 +1,198 @@
+"""GPU parity: metric kernels against vectors produced by the reference's own notebook code /
+sklearn (ref_*), and the evaluation drop-ins against the reference's own train.py (refshim_*)."""
+import json
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import retrieval
+from patent_image_retrieval_b200 import evaluation, models, ops, synth
+
+pytestmark = pytest.mark.gpu
+
+
+def _nb_case(golden):
+    order = torch.from_numpy(golden["ref_cos_order"].copy()).cuda()
+    off = torch.from_numpy(golden["ref_nb_pos_offsets"]).cuda()
+    items_all = golden["ref_nb_pos_items"]
+    # positives >= 300 are ground-truth names that are not in the gallery: they count in |P| only
+    n_tot = torch.tensor(np.diff(golden["ref_nb_pos_offsets"]), dtype=torch.int32).cuda()
+    return order, off, torch.from_numpy(items_all).cuda(), n_tot
+
+
+def test_notebook_metrics_full_ranking(golden):
+    order, off, items, n_tot = _nb_case(golden)
+    means, per = ops.retrieval_metrics(order, off, items, ks=(5, 10, 20), n_pos_total=n_tot)
+    per = per.cpu().numpy()
+    names = ops.metric_names((5, 10, 20))
+    col = {n: per[:, i] for i, n in enumerate(names)}
+    tol = dict(rtol=1e-12, atol=1e-15)
+    np.testing.assert_allclose(col["ap"], golden["ref_nb_ap_scores"], **tol)
+    np.testing.assert_allclose(col["ndcg"], golden["ref_nb_ndcg_scores"], **tol)
+    np.testing.assert_allclose(col["mrr"], golden["ref_nb_reciprocal_ranks"], **tol)
+    np.testing.assert_allclose(col["mrr@5"], golden["ref_nb_reciprocal_ranks_5"], **tol)
+    np.testing.assert_allclose(col["mrr@20"], golden["ref_nb_reciprocal_ranks_20"], **tol)
+    for k in (5, 10, 20):
+        np.testing.assert_allclose(col[f"recall@{k}"], golden[f"ref_nb_recall_{k}"], **tol)
+        np.testing.assert_allclose(col[f"precision@{k}"], golden[f"ref_nb_precision_{k}"], **tol)
+    # means == np.mean of the notebook lists (retrieval.ipynb:446-456)
+    np.testing.assert_allclose(means["ap"], golden["ref_nb_ap_scores"].mean(), rtol=1e-12)
+    np.testing.assert_allclose(means["recall@10"], golden["ref_nb_recall_10"].mean(), rtol=1e-12)
+
+
+def test_metrics_on_truncated_lists_match_oracle(golden):
+    order, off, items, n_tot = _nb_case(golden)
+    K = 20
+    means, per = ops.retrieval_metrics(order[:, :K].contiguous(), off, items, ks=(5, 10, 20), n_pos_total=n_tot)
+    o, it = golden["ref_nb_pos_offsets"], golden["ref_nb_pos_items"]
+    pos = [it[o[i]:o[i + 1]] for i in range(len(o) - 1)]
+    want, _ = retrieval.notebook_metrics(golden["ref_cos_order"][:, :K], pos, ks=(5, 10, 20))
+    for name, v in means.items():
+        assert abs(v - want[name]) < 1e-12, name
+    # padded (-1) entries and empty positives
+    ranked = torch.tensor([[3, -1, -1, -1], [1, 2, 3, 4]], device="cuda")
+    off2 = torch.tensor([0, 1, 1], device="cuda")
+    m2, p2 = ops.retrieval_metrics(ranked, off2, torch.tensor([3], device="cuda"), ks=(2, 4))
+    p2 = p2.cpu()
+    assert p2[0, 0] == 1.0 and p2[0, 1] == 1.0 and p2[0, 4] == 0.0      # precision@2: only 1 valid entry -> 0
+    assert float(p2[1].abs().sum()) == 0.0
+
+
+def test_ap_full_matches_sklearn_and_ranking_conventions(golden):
+    s = torch.from_numpy(golden["ref_ap_scores"]).cuda()
+    t = golden["ref_ap_target"]
+    lists = [np.nonzero(t[i])[0].tolist() for i in range(t.shape[0])]
+    off, items = evaluation._csr_from_lists(lists, "cuda")
+    mean, ap, valid = ops.ap_full(s, off, items, grouped_ties=True)
+    np.testing.assert_allclose(ap.cpu().numpy(), golden["ref_ap_values"], rtol=1e-12)
+    np.testing.assert_allclose(mean, float(golden["ref_aux_map"]), rtol=1e-12)     # auxiliary.mean_average_precision
+    assert int(valid.sum()) == 20
+    _, ap2, _ = ops.ap_full(s, off, items, grouped_ties=False)
+    sc = golden["ref_ap_scores"]
+    want = [retrieval.average_precision_ranked(list(np.argsort(-sc[i], kind="stable")), set(lists[i])) for i in range(20)]
+    np.testing.assert_allclose(ap2.cpu().numpy(), want, rtol=1e-12)
+    # rows the reference skips: no positive, NaN score
+    s3 = s[:3].clone()
+    s3[1, 5] = float("nan")
+    off3, items3 = evaluation._csr_from_lists([[], [0], [2, 999]], "cuda")
+    mean3, ap3, valid3 = ops.ap_full(s3, off3, items3)
+    assert valid3.tolist() == [0, 0, 1]
+    assert mean3 == pytest.approx(float(ap3[2]))
+
+
+@pytest.mark.parametrize("n,m,d,c", [(70, 130, 128, 1.0), (33, 65, 256, 0.5), (64, 64, 20, 2.0)])
+def test_pairdist_matches_oracle(n, m, d, c):
+    from oracle import head
+    a = head.embed_rows(synth.gaussian_features(n, d, seed=1, scale=1.0), c)
+    p = head.embed_rows(synth.gaussian_features(m, d, seed=0, scale=1.0), c)
+    p[:5] = a[:5] * (1 + 1e-4)                                   # near duplicates: the cancellation case
+    got = ops.pairdist(a.cuda(), p.cuda(), c).cpu()
+    d32 = retrieval.hyperbolic_dist_rows(a, p, c, form="geoopt")
+    d64 = retrieval.hyperbolic_dist_rows(a.double(), p.double(), c, form="arcosh")
+    far = d64 > 1e-2
+    assert float(((got.double() - d64).abs() / d64)[far].max()) < 2e-6
+    assert float(((got - d32).abs() / d32)[far].max()) < 1e-5
+    # near-duplicate pairs: the explicit-difference kernel keeps RELATIVE accuracy that the geoopt fp32 form loses
+    near = ~far
+    assert float(((got.double() - d64).abs() / d64)[near].max()) < 1e-3
+
+
+def test_contrastive_loss_and_gradients_match_reference_train_py(golden):
+    from patent_image_retrieval_b200 import train
+    k = torch.tensor([-0.5])
+    a = torch.from_numpy(golden["refshim_hcl_a"]).float().cuda().requires_grad_(True)
+    p = torch.from_numpy(golden["refshim_hcl_p"]).float().cuda().requires_grad_(True)
+    loss = train.hyperbolic_contrastive_loss(a, p, k, temperature=0.07)
+    loss.backward()
+    np.testing.assert_allclose(loss.item(), float(golden["refshim_hcl_loss"]), rtol=2e-5)
+    da, dp = golden["refshim_hcl_da"], golden["refshim_hcl_dp"]
+    assert np.abs(a.grad.cpu().numpy() - da).max() < 2e-4 * np.abs(da).max()
+    assert np.abs(p.grad.cpu().numpy() - dp).max() < 2e-4 * np.abs(dp).max()
+    s2p = train.sample_to_prototype_loss(torch.from_numpy(golden["refshim_s2p_s"]).float().cuda(),
+                                         torch.from_numpy(golden["refshim_s2p_pos"]).float().cuda(),
+                                         torch.from_numpy(golden["refshim_s2p_neg"]).float().cuda(), 3, k, margin=0.1)
+    np.testing.assert_allclose(s2p.item(), float(golden["refshim_s2p_loss"]), rtol=2e-5)
+
+
+def test_pairdist_backward_vs_autograd_oracle():
+    from oracle import contrastive, head
+    from patent_image_retrieval_b200 import train
+    c, n, d = 1.0, 96, 128
+    mu = synth.gaussian_features(n, d, seed=2, scale=1.0)
+    a0 = head.embed_rows(mu + 0.1 * synth.gaussian_features(n, d, seed=3, scale=1.0), c)
+    p0 = head.embed_rows(mu + 0.1 * synth.gaussian_features(n, d, seed=4, scale=1.0), c)
+    k = torch.tensor([-c], dtype=torch.float64)
+    a64, p64 = a0.double().requires_grad_(True), p0.double().requires_grad_(True)
+    contrastive.contrastive_loss(a64, p64, k, temperature=0.1).backward()
+    ag, pg = a0.cuda().requires_grad_(True), p0.cuda().requires_grad_(True)
+    loss = train.in_batch_contrastive_loss(ag, pg, torch.tensor([-c]), temperature=0.1)
+    loss.backward()
+    for got, want in ((ag.grad, a64.grad), (pg.grad, p64.grad)):
+        err = (got.cpu().double() - want).abs().max() / want.abs().max()
+        assert float(err) < 1e-4
+
+
+def test_evaluate_retrieval_dropin_matches_reference(golden):
+    f2p = {int(k): v for k, v in json.loads(bytes(golden["refshim_eval_f2p_json"]).decode()).items()}
+    X = torch.from_numpy(golden["refshim_eval_X"])
+    model = models.HyperbolicEmbeddingModel(32, 16, label_num=60, hidden_dims=[24], c=2.0)
+    sd = {k: torch.from_numpy(np.array(golden["refshim_eval_" + k])).float() for k in model.state_dict().keys()}
+    model.load_state_dict(sd)
+    model = model.cuda()
+    offsets = {"patents": 0, "medium_cpcs": 45, "big_cpcs": 55, "main_cpcs": 58}
+    got = evaluation.evaluate_retrieval(model, X, list(range(40)), f2p, offsets, "cuda", 16)
+    # the reference mixed fp32 queries with fp64 label embeddings; the CUDA path is fp32 throughout
+    assert abs(got - float(golden["refshim_eval_map"])) < 2e-6
+    assert evaluation.evaluate_retrieval(model, X, [], f2p, offsets, "cuda", 16) == 0.0
+    assert evaluation.evaluate_retrieval(model, X, list(range(40)), f2p, {"cpcs": 3}, "cuda", 16) == -1.0
+    assert evaluation.evaluate_retrieval(model, X[:, :8], list(range(40)), f2p, offsets, "cuda", 16) == -1.0
+
+
+def test_image_retrieval_and_query_evaluation(golden):
+    g, q = golden["ref_cos_g"], golden["ref_cos_q"]
+    paths = [f"gallery/fig_{i:05d}.png" for i in range(g.shape[0])]
+    ir = evaluation.ImageRetrieval(g, paths)
+    res = ir.retrieve_similar_images(q[0], k=20)
+    order = golden["ref_cos_order"]
+    assert [p for p, _ in res] == [paths[j] for j in order[0, :20]]
+    np.testing.assert_allclose([s for _, s in res], golden["ref_cos_sim"][0, order[0, :20]], atol=2e-6)
+    o, it = golden["ref_nb_pos_offsets"], golden["ref_nb_pos_items"]
+    gt = {f"q{i}.png": {"patent_positives": [f"fig_{j:05d}.png" for j in it[o[i]:o[i + 1]]]} for i in range(12)}
+    names = [f"queries/q{i}.png" for i in range(12)] + ["queries/not_in_gt.png"]
+    qq = np.concatenate([q, q[:1]], 0)
+    got = evaluation.evaluate_queries(ir, qq, names, gt, k=20, ks=(5, 10, 20))
+    want, _ = retrieval.notebook_metrics(order[:, :20], [it[o[i]:o[i + 1]] for i in range(12)], ks=(5, 10, 20))
+    for name in ("mrr", "ap", "ndcg", "recall@5", "recall@10", "recall@20", "precision@5", "mrr@5"):
+        assert abs(got[name] - want[name]) < 1e-12, name
+
+
+def test_merge_topk():
+    torch.manual_seed(0)
+    W, Q, k = 4, 300, 10
+    s = torch.rand(W, Q, k, device="cuda").sort(dim=2).values
+    i = torch.randperm(W * Q * k, device="cuda").view(W, Q, k)
+    s[1, :, 3] = s[0, :, 2]                                   # exact ties across shards
+    i[2, 5, 7:] = -1                                          # short list
+    got_s, got_i = ops.merge_topk(s, i)
+    fs = s.permute(1, 0, 2).reshape(Q, -1).cpu().numpy()
+    fi = i.permute(1, 0, 2).reshape(Q, -1).cpu().numpy()
+    fs = np.where(fi < 0, np.inf, fs)
+    order = np.lexsort((fi, fs), axis=1)[:, :k]
+    np.testing.assert_array_equal(got_i.cpu().numpy(), np.take_along_axis(fi, order, 1))
+    np.testing.assert_array_equal(got_s.cpu().numpy(), np.take_along_axis(fs, order, 1))
+    d_s, d_i = ops.merge_topk(s, i, descending=True)
+    order = np.lexsort((fi, np.where(fi < 0, np.inf, -fs)), axis=1)[:, :k]
+    np.testing.assert_array_equal(d_i.cpu().numpy(), np.take_along_axis(fi, order, 1))
+
+
+def test_sharded_index_single_process_equals_plain_index():
+    from patent_image_retrieval_b200 import GalleryIndex
+    from patent_image_retrieval_b200.dist import ShardedGalleryIndex
+    u = synth.gaussian_features(50, 128, seed=1).cuda()
+    v = synth.gaussian_features(3000, 128, seed=0).cuda()
+    a = GalleryIndex(v).search(u, k=10)
+    # two "ranks" emulated in one process: search each shard, then the merge kernel
+    parts = [ShardedGalleryIndex(v[lo:hi], lo, 3000).search(u, k=10) for lo, hi in ((0, 1500), (1500, 3000))]
+    ms, mi = ops.merge_topk(torch.stack([p[0] for p in parts]), torch.stack([p[1] for p in parts]))
+    assert torch.equal(mi, a[1]) and torch.equal(ms, a[0])
