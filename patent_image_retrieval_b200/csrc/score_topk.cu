@@ -40,6 +40,8 @@
 #include <math.h>
 #include <stdlib.h>
 
+#include <vector>
+
 #include "common.cuh"
 
 namespace {
@@ -161,7 +163,36 @@ struct Params {
   int32_t* cand_idx;
   float* debug_scores;
   uint32_t* shared_thr;   // [Q] ordered-uint keys of the best known k'-th score per query, or NULL
+  unsigned long long* stats;   // DEBUG builds: [grid][8] wait-cycle counters per warp role, or NULL
+  int wait_mode;          // experiments: 0 = try_wait + suspend hint, 1 = plain try_wait, 2 = test_wait spin
 };
+
+// mbarrier wait with optional cycle accounting (DEBUG kernels only)
+template <bool DEBUG>
+__device__ __forceinline__ void timed_wait(uint64_t* bar, uint32_t parity, unsigned long long& acc_cycles,
+                                           int wait_mode) {
+  if (DEBUG) {
+    const long long t0 = clock64();
+    if (wait_mode == 2) {
+      uint32_t ok = 0;
+      while (!ok) {
+        asm volatile("{ .reg .pred p; mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                     : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+      }
+    } else if (wait_mode == 1) {
+      uint32_t ok = 0;
+      while (!ok) {
+        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                     : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+      }
+    } else {
+      mbar_wait(bar, parity);
+    }
+    acc_cycles += (unsigned long long)(clock64() - t0);
+  } else {
+    mbar_wait(bar, parity);
+  }
+}
 
 struct Barriers {
   uint64_t full[MAX_STAGES];
@@ -308,19 +339,22 @@ score_topk_kernel(const __grid_constant__ CUtensorMap map_q_main, const __grid_c
 
   if (warp == 0) {
     // ======================================================================= TMA producer
-    if (lane == 0) {
-      uint32_t stage = 0, phase = 0, a_par = 0;
-      bool first = true;
-      for (int step = 0; step < sc.n_steps; ++step) {
-        int qt, gt0, gt1, slot;
-        if (!strip_at(sc, cta, step, qt, gt0, gt1, slot)) continue;
-        if (RESIDENT) {
-          if (!first) {  // the previous strip's MMAs must be done reading the resident tile
-            mbar_wait(&bars->a_empty, a_par);
-            a_par ^= 1;
-          }
-          first = false;
-          mbar_arrive_expect_tx(&bars->a_full, KB * A_BLK_BYTES + (p.has_ext ? A_EXT_BYTES : 0));
+    // The whole warp runs the (warp-uniform) control flow; one elected lane issues the copies.
+    uint32_t stage = 0, phase = 0, a_par = 0;
+    bool first = true;
+    unsigned long long w_empty = 0, t_begin = DEBUG ? clock64() : 0;
+    const uint32_t a_tile_bytes = KB * A_BLK_BYTES + (p.has_ext ? A_EXT_BYTES : 0);
+    for (int step = 0; step < sc.n_steps; ++step) {
+      int qt, gt0, gt1, slot;
+      if (!strip_at(sc, cta, step, qt, gt0, gt1, slot)) continue;
+      if (RESIDENT) {
+        if (!first) {  // the previous strip's MMAs must be done reading the resident tile
+          mbar_wait(&bars->a_empty, a_par);
+          a_par ^= 1;
+        }
+        first = false;
+        if (elect_one()) {
+          mbar_arrive_expect_tx(&bars->a_full, a_tile_bytes);
           for (int kb = 0; kb < KB; ++kb)
             tma_load_2d_hint(a_res + kb * A_BLK_BYTES, &map_q_main, &bars->a_full, kb * HYPRET_KBLK, qt * TILE_M,
                              TMA_EVICT_LAST);
@@ -328,77 +362,95 @@ score_topk_kernel(const __grid_constant__ CUtensorMap map_q_main, const __grid_c
             tma_load_2d_hint(a_res + KB * A_BLK_BYTES, &map_q_ext, &bars->a_full, p.dpad, qt * TILE_M,
                              TMA_EVICT_LAST);
         }
-        for (int gt = gt0; gt < gt1; ++gt) {
-          for (int ks = 0; ks < KSTEPS; ++ks) {
-            mbar_wait(&bars->empty[stage], phase ^ 1);
+        __syncwarp();
+      }
+      const int q_row = qt * TILE_M;
+      for (int gt = gt0; gt < gt1; ++gt) {
+        const int g_row = gt * TILE_N;
+        for (int ks = 0; ks < KSTEPS; ++ks) {
+          timed_wait<DEBUG>(&bars->empty[stage], phase ^ 1, w_empty, p.wait_mode);
+          if (elect_one()) {
             uint8_t* st = ring + stage * p.stage_bytes;
             uint8_t* st_b = RESIDENT ? st : st + A_BLK_BYTES;
-            const bool ext = (ks == KB);
-            uint32_t bytes = ext ? B_EXT_BYTES : B_BLK_BYTES;
-            if (!RESIDENT) bytes += ext ? A_EXT_BYTES : A_BLK_BYTES;
-            mbar_arrive_expect_tx(&bars->full[stage], bytes);
-            if (!ext) {
-              tma_load_2d(st_b, &map_g_main, &bars->full[stage], ks * HYPRET_KBLK, gt * TILE_N);
-              if (!RESIDENT)
-                tma_load_2d_hint(st, &map_q_main, &bars->full[stage], ks * HYPRET_KBLK, qt * TILE_M, TMA_EVICT_LAST);
+            uint64_t* full = &bars->full[stage];
+            if (ks < KB) {
+              mbar_arrive_expect_tx(full, RESIDENT ? B_BLK_BYTES : A_BLK_BYTES + B_BLK_BYTES);
+              tma_load_2d(st_b, &map_g_main, full, ks * HYPRET_KBLK, g_row);
+              if (!RESIDENT) tma_load_2d_hint(st, &map_q_main, full, ks * HYPRET_KBLK, q_row, TMA_EVICT_LAST);
             } else {
-              tma_load_2d(st_b, &map_g_ext, &bars->full[stage], p.dpad, gt * TILE_N);
-              if (!RESIDENT)
-                tma_load_2d_hint(st, &map_q_ext, &bars->full[stage], p.dpad, qt * TILE_M, TMA_EVICT_LAST);
+              mbar_arrive_expect_tx(full, RESIDENT ? B_EXT_BYTES : A_EXT_BYTES + B_EXT_BYTES);
+              tma_load_2d(st_b, &map_g_ext, full, p.dpad, g_row);
+              if (!RESIDENT) tma_load_2d_hint(st, &map_q_ext, full, p.dpad, q_row, TMA_EVICT_LAST);
             }
-            if (++stage == (uint32_t)p.stages) { stage = 0; phase ^= 1; }
           }
+          __syncwarp();
+          if (++stage == (uint32_t)p.stages) { stage = 0; phase ^= 1; }
         }
       }
     }
-    __syncwarp();
+    if (DEBUG && p.stats != nullptr && lane == 0) {
+      p.stats[cta * 8 + 0] = w_empty;
+      p.stats[cta * 8 + 1] = (unsigned long long)clock64() - t_begin;
+    }
   } else if (warp == 1) {
     // ======================================================================= MMA issuer
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(TILE_M, TILE_N);
-      uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0, a_par = 0;
-      for (int step = 0; step < sc.n_steps; ++step) {
-        int qt, gt0, gt1, slot;
-        if (!strip_at(sc, cta, step, qt, gt0, gt1, slot)) continue;
-        if (RESIDENT) {
-          mbar_wait(&bars->a_full, a_par);
-          a_par ^= 1;
+    // Warp-uniform control flow; one elected lane issues tcgen05.mma / tcgen05.commit.  The
+    // shared-memory descriptors are a constant high word plus (address >> 4): stepping K by 16
+    // elements inside the 128-byte swizzle span is "+2" on the low word.
+    constexpr uint32_t idesc = umma_idesc_bf16(TILE_M, TILE_N);
+    constexpr uint64_t DESC_SW128 = (uint64_t(1) << 16) | (uint64_t(1024 >> 4) << 32) | (uint64_t(1) << 46) |
+                                    (UMMA_LAYOUT_SW128 << 61);
+    constexpr uint64_t DESC_SW32 = (uint64_t(1) << 16) | (uint64_t(256 >> 4) << 32) | (uint64_t(1) << 46) |
+                                   (UMMA_LAYOUT_SW32 << 61);
+    const uint32_t ring_lo = smem_u32(ring) >> 4, ares_lo = smem_u32(a_res) >> 4;
+    const uint32_t stage_lo = (uint32_t)p.stage_bytes >> 4;
+    uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0, a_par = 0;
+    unsigned long long w_full = 0, w_tmem = 0, t_begin = DEBUG ? clock64() : 0;
+    for (int step = 0; step < sc.n_steps; ++step) {
+      int qt, gt0, gt1, slot;
+      if (!strip_at(sc, cta, step, qt, gt0, gt1, slot)) continue;
+      if (RESIDENT) {
+        mbar_wait(&bars->a_full, a_par);
+        a_par ^= 1;
+      }
+      for (int gt = gt0; gt < gt1; ++gt) {
+        timed_wait<DEBUG>(&bars->tmem_empty[acc], acc_phase ^ 1, w_tmem, p.wait_mode);   // epilogue drained it
+        tcgen05_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * TILE_N;
+        for (int ks = 0; ks < KSTEPS; ++ks) {
+          timed_wait<DEBUG>(&bars->full[stage], phase, w_full, p.wait_mode);
           tcgen05_fence_after();
-        }
-        for (int gt = gt0; gt < gt1; ++gt) {
-          mbar_wait(&bars->tmem_empty[acc], acc_phase ^ 1);   // epilogue drained this accumulator
-          tcgen05_fence_after();
-          const uint32_t d_tmem = tmem_base + acc * TILE_N;
-          for (int ks = 0; ks < KSTEPS; ++ks) {
-            mbar_wait(&bars->full[stage], phase);
-            tcgen05_fence_after();
-            uint8_t* st = ring + stage * p.stage_bytes;
-            const uint32_t b_addr = smem_u32(RESIDENT ? st : st + A_BLK_BYTES);
+          if (elect_one()) {
+            const uint32_t st_lo = ring_lo + stage * stage_lo;
+            const uint32_t b_lo = RESIDENT ? st_lo : st_lo + (A_BLK_BYTES >> 4);
             if (ks < KB) {
-              const uint32_t a_addr = smem_u32(RESIDENT ? a_res + ks * A_BLK_BYTES : st);
+              const uint32_t a_lo = RESIDENT ? ares_lo + ks * (A_BLK_BYTES >> 4) : st_lo;
 #pragma unroll
-              for (int k = 0; k < HYPRET_KBLK / 16; ++k) {
-                // +32 bytes per UMMA_K step inside the 128-byte swizzle span
-                const uint64_t ad = umma_smem_desc(a_addr + k * 32, 1024, UMMA_LAYOUT_SW128);
-                const uint64_t bd = umma_smem_desc(b_addr + k * 32, 1024, UMMA_LAYOUT_SW128);
-                umma_bf16_ss(d_tmem, ad, bd, idesc, (ks | k) != 0 ? 1u : 0u);
-              }
+              for (int k = 0; k < HYPRET_KBLK / 16; ++k)
+                umma_bf16_ss(d_tmem, DESC_SW128 | (a_lo + 2 * k), DESC_SW128 | (b_lo + 2 * k), idesc,
+                             (ks | k) != 0 ? 1u : 0u);
             } else {
-              const uint32_t a_addr = smem_u32(RESIDENT ? a_res + KB * A_BLK_BYTES : st);
-              const uint64_t ad = umma_smem_desc(a_addr, 256, UMMA_LAYOUT_SW32);
-              const uint64_t bd = umma_smem_desc(b_addr, 256, UMMA_LAYOUT_SW32);
-              umma_bf16_ss(d_tmem, ad, bd, idesc, 1u);
+              const uint32_t a_lo = RESIDENT ? ares_lo + KB * (A_BLK_BYTES >> 4) : st_lo;
+              umma_bf16_ss(d_tmem, DESC_SW32 | a_lo, DESC_SW32 | b_lo, idesc, 1u);
             }
-            umma_commit(&bars->empty[stage]);                  // ring stage reusable once these MMAs retire
-            if (++stage == (uint32_t)p.stages) { stage = 0; phase ^= 1; }
+            umma_commit(&bars->empty[stage]);                          // ring stage reusable once these MMAs retire
+            if (ks == KSTEPS - 1) umma_commit(&bars->tmem_full[acc]);  // accumulator complete -> epilogue
           }
-          umma_commit(&bars->tmem_full[acc]);                  // accumulator complete -> epilogue
-          if (++acc == NUM_ACC) { acc = 0; acc_phase ^= 1; }
+          __syncwarp();
+          if (++stage == (uint32_t)p.stages) { stage = 0; phase ^= 1; }
         }
-        if (RESIDENT) umma_commit(&bars->a_empty);
+        if (++acc == NUM_ACC) { acc = 0; acc_phase ^= 1; }
+      }
+      if (RESIDENT) {
+        if (elect_one()) umma_commit(&bars->a_empty);
+        __syncwarp();
       }
     }
-    __syncwarp();
+    if (DEBUG && p.stats != nullptr && lane == 0) {
+      p.stats[cta * 8 + 2] = w_full;
+      p.stats[cta * 8 + 3] = w_tmem;
+      p.stats[cta * 8 + 4] = (unsigned long long)clock64() - t_begin;
+    }
   } else {
     // ======================================================================= epilogue / top-k'
     const int quad = warp & 3;                 // TMEM lane quadrant this warp may read
@@ -409,6 +461,7 @@ score_topk_kernel(const __grid_constant__ CUtensorMap map_q_main, const __grid_c
     const int KP = p.kprime;
     const int N = (int)p.N;
     uint32_t acc = 0, acc_phase = 0;
+    unsigned long long w_acc = 0, t_begin = DEBUG ? clock64() : 0;
     for (int step = 0; step < sc.n_steps; ++step) {
       int qt, gt0, gt1, slot;
       if (!strip_at(sc, cta, step, qt, gt0, gt1, slot)) continue;
@@ -435,7 +488,7 @@ score_topk_kernel(const __grid_constant__ CUtensorMap map_q_main, const __grid_c
       float thr = fminf(thr_list, thr_g);
       __syncwarp();
       for (int gt = gt0; gt < gt1; ++gt) {
-        mbar_wait(&bars->tmem_full[acc], acc_phase);
+        timed_wait<DEBUG>(&bars->tmem_full[acc], acc_phase, w_acc, p.wait_mode);
         tcgen05_fence_after();
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * TILE_N;
         const int col0 = gt * TILE_N;
@@ -452,7 +505,7 @@ score_topk_kernel(const __grid_constant__ CUtensorMap map_q_main, const __grid_c
             for (int j = 0; j < 32; ++j)
               if (col0 + cc * 32 + j >= N) va[j] = INFINITY;
           }
-          if (DEBUG && qrow < p.Q) {
+          if (DEBUG && p.debug_scores != nullptr && qrow < p.Q) {
 #pragma unroll
             for (int j = 0; j < 32; ++j)
               if (col0 + cc * 32 + j < N) p.debug_scores[qrow * p.N + col0 + cc * 32 + j] = va[j];
@@ -466,7 +519,7 @@ score_topk_kernel(const __grid_constant__ CUtensorMap map_q_main, const __grid_c
             for (int j = 0; j < 32; ++j)
               if (col0 + (cc + 1) * 32 + j >= N) vb[j] = INFINITY;
           }
-          if (DEBUG && qrow < p.Q) {
+          if (DEBUG && p.debug_scores != nullptr && qrow < p.Q) {
 #pragma unroll
             for (int j = 0; j < 32; ++j)
               if (col0 + (cc + 1) * 32 + j < N) p.debug_scores[qrow * p.N + col0 + (cc + 1) * 32 + j] = vb[j];
@@ -502,6 +555,10 @@ score_topk_kernel(const __grid_constant__ CUtensorMap map_q_main, const __grid_c
         }
       }
       __syncwarp();
+    }
+    if (DEBUG && p.stats != nullptr && warp == 2 && lane == 0) {
+      p.stats[cta * 8 + 5] = w_acc;
+      p.stats[cta * 8 + 6] = (unsigned long long)clock64() - t_begin;
     }
   }
 
@@ -576,7 +633,7 @@ int launch_one(const hypret_score_plan_t& plan, const CUtensorMap& mq_main, cons
 template <bool RESIDENT, int KPP>
 int launch_variant(const hypret_score_plan_t& plan, const CUtensorMap& mq_main, const CUtensorMap& mq_ext,
                    const CUtensorMap& mg_main, const CUtensorMap& mg_ext, const Params& p, cudaStream_t stream) {
-  return p.debug_scores != nullptr
+  return (p.debug_scores != nullptr || p.stats != nullptr)
              ? launch_one<RESIDENT, KPP, true>(plan, mq_main, mq_ext, mg_main, mg_ext, p, stream)
              : launch_one<RESIDENT, KPP, false>(plan, mq_main, mq_ext, mg_main, mg_ext, p, stream);
 }
@@ -679,6 +736,17 @@ int hypret_launch_score_topk(const void* q_op, int64_t Q, const void* g_op, int6
   p.cand_idx = cand_idx;
   p.debug_scores = debug_scores;
   p.shared_thr = thr_ws;
+  p.stats = nullptr;
+  p.wait_mode = 0;
+  // Experiments only: HYPRET_STATS=1 runs the instrumented kernel variant, synchronises and prints
+  // per-role wait-cycle totals to stderr.  HYPRET_WAIT_MODE selects the wait flavour in that variant.
+  const char* stats_env = getenv("HYPRET_STATS");
+  const bool want_stats = stats_env != nullptr && stats_env[0] == '1' && debug_scores == nullptr;
+  if (const char* wm = getenv("HYPRET_WAIT_MODE")) p.wait_mode = atoi(wm);
+  if (want_stats) {
+    if (cudaMalloc(&p.stats, (size_t)plan.grid * 8 * sizeof(unsigned long long)) != cudaSuccess) p.stats = nullptr;
+    if (p.stats != nullptr) cudaMemsetAsync(p.stats, 0, (size_t)plan.grid * 8 * sizeof(unsigned long long), stream);
+  }
 
   // list slots that no strip writes (rows with fewer strips than n_lists) must read as empty
   cudaError_t e = cudaMemsetAsync(cand_idx, 0xFF, (size_t)Q * n_lists * kprime * sizeof(int32_t), stream);
@@ -690,8 +758,23 @@ int hypret_launch_score_topk(const void* q_op, int64_t Q, const void* g_op, int6
 
   const bool k16 = kpp_of(kprime) == 16;
   if (plan.resident)
-    return k16 ? launch_variant<true, 16>(plan, mq_main, mq_ext, mg_main, mg_ext, p, stream)
-               : launch_variant<true, 32>(plan, mq_main, mq_ext, mg_main, mg_ext, p, stream);
-  return k16 ? launch_variant<false, 16>(plan, mq_main, mq_ext, mg_main, mg_ext, p, stream)
+    rc = k16 ? launch_variant<true, 16>(plan, mq_main, mq_ext, mg_main, mg_ext, p, stream)
+             : launch_variant<true, 32>(plan, mq_main, mq_ext, mg_main, mg_ext, p, stream);
+  else
+    rc = k16 ? launch_variant<false, 16>(plan, mq_main, mq_ext, mg_main, mg_ext, p, stream)
              : launch_variant<false, 32>(plan, mq_main, mq_ext, mg_main, mg_ext, p, stream);
+  if (p.stats != nullptr) {
+    std::vector<unsigned long long> h((size_t)plan.grid * 8);
+    cudaStreamSynchronize(stream);
+    cudaMemcpy(h.data(), p.stats, h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+    cudaFree(p.stats);
+    double s[8] = {0};
+    for (int c = 0; c < plan.grid; ++c)
+      for (int i = 0; i < 8; ++i) s[i] += (double)h[(size_t)c * 8 + i] / plan.grid;
+    fprintf(stderr,
+            "hypret stats (mean cycles per CTA, wait_mode %d): producer wait-empty %.0f of %.0f | mma wait-full %.0f "
+            "wait-tmem-empty %.0f of %.0f | epilogue(warp2) wait-tmem-full %.0f of %.0f\n",
+            p.wait_mode, s[0], s[1], s[2], s[3], s[4], s[5], s[6]);
+  }
+  return rc;
 }
