@@ -68,7 +68,7 @@ typedef struct {
   int32_t n_qtiles;   /* T = ceil(Q / 128)                                               */
   int32_t n_gtiles;   /* G = ceil(N / 256)                                               */
   int32_t n_lists;    /* candidate lists (slots) per query in cand_score / cand_idx      */
-  int32_t grid;       /* P = persistent CTAs launched                                    */
+  int32_t grid;       /* persistent CTAs launched (P = grid / pair scheduling units)     */
   int32_t stages;     /* shared-memory pipeline stages                                   */
   int32_t resident;   /* 1: query tile resident in shared memory for a whole strip       */
   int32_t smem_bytes; /* dynamic shared memory per CTA                                   */
@@ -80,12 +80,15 @@ typedef struct {
   int32_t rem_g0;
   int32_t m, l2;      /* phase 2: m pieces per remaining row, l2 tiles each              */
   int32_t n_steps;    /* strips a CTA walks through at most: n_full + phases             */
+  int32_t pair;       /* 2: CTA pairs (tcgen05 cta_group::2) -- a scheduling unit is a cluster of 2 CTAs and a
+                         strip covers 2 consecutive query tiles; 1: single-CTA MMAs            */
 } hypret_score_plan_t;
 
 /* max_ctas: 0 = one CTA per SM; >0 caps the grid (tests use it to force multi-wave schedules). */
 int hypret_score_plan(int64_t Q, int64_t N, int d, int kprime, int max_ctas, hypret_score_plan_t* plan);
 
-/* Strip of CTA `cta` at step `step` of `plan`: out4 = {query tile, first gallery tile, end gallery
+/* Strip of scheduling unit `cta` (0 <= cta < grid / pair) at step `step` of `plan`:
+ * out4 = {first query tile (the strip covers `pair` consecutive tiles), first gallery tile, end gallery
  * tile, list slot}.  Returns 1 if the CTA has work at that step, 0 if idle, <0 on bad arguments.
  * Host-only (no GPU needed); the kernel evaluates the same closed form on the device. */
 int hypret_score_strip(const hypret_score_plan_t* plan, int cta, int step, int32_t* out4);

@@ -33,6 +33,7 @@ class ScorePlan(Structure):
         ("m", c_int32),
         ("l2", c_int32),
         ("n_steps", c_int32),
+        ("pair", c_int32),
     ]
 
     def asdict(self):

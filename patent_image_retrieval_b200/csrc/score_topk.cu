@@ -291,7 +291,12 @@ __device__ __forceinline__ void process_chunk(const float (&v)[32], int cbase, f
   }
 }
 
-template <bool RESIDENT, int KPP, bool DEBUG>
+// PAIR: two CTAs of a cluster (one TPC) share every gallery tile through tcgen05 cta_group::2 --
+// each CTA keeps its OWN 128-row query tile and loads only HALF (128 rows) of the 256-row gallery
+// tile; the leader CTA issues one M=256 MMA for both.  Halves the L2->shared-memory traffic per
+// SM (the measured limiter of the single-CTA kernel at D=512) and leaves room for a resident
+// query tile plus a 4-stage ring.
+template <bool RESIDENT, int KPP, bool DEBUG, bool PAIR>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 score_topk_kernel(const __grid_constant__ CUtensorMap map_q_main, const __grid_constant__ CUtensorMap map_q_ext,
                   const __grid_constant__ CUtensorMap map_g_main, const __grid_constant__ CUtensorMap map_g_ext,
@@ -310,7 +315,10 @@ score_topk_kernel(const __grid_constant__ CUtensorMap map_q_main, const __grid_c
   const int KB = p.kb_main;
   const int KSTEPS = KB + (p.has_ext ? 1 : 0);
   const Sched& sc = p.sched;
-  const int cta = blockIdx.x;
+  const uint32_t rank = PAIR ? cluster_ctarank() : 0u;          // 0 = leader (issues the MMAs)
+  const int cta = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;   // scheduling unit: CTA or CTA pair
+  constexpr int B_ROWS = PAIR ? TILE_N / 2 : TILE_N;            // gallery rows this CTA stages per tile
+  constexpr uint32_t B_BLK = B_ROWS * HYPRET_KBLK * 2, B_EXT = B_ROWS * HYPRET_KEXT * 2;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&map_q_main);
@@ -325,15 +333,19 @@ score_topk_kernel(const __grid_constant__ CUtensorMap map_q_main, const __grid_c
     }
     for (int a = 0; a < NUM_ACC; ++a) {
       mbar_init(&bars->tmem_full[a], 1);
-      mbar_init(&bars->tmem_empty[a], NUM_EPI_THREADS);
+      mbar_init(&bars->tmem_empty[a], PAIR ? 2 * NUM_EPI_THREADS : NUM_EPI_THREADS);
     }
     mbar_init(&bars->a_full, 1);
     mbar_init(&bars->a_empty, 1);
     fence_barrier_init();
   }
-  if (warp == 2) tmem_alloc(&bars->tmem_ptr, TMEM_COLS);
+  if (warp == 2) {
+    if (PAIR) tmem_alloc_2cta(&bars->tmem_ptr, TMEM_COLS);
+    else tmem_alloc(&bars->tmem_ptr, TMEM_COLS);
+  }
   tcgen05_fence_before();
-  __syncthreads();
+  if (PAIR) cluster_sync_all();   // the peer's barriers must exist before any remote arrive / TMA credit
+  else __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = bars->tmem_ptr;
 
@@ -347,6 +359,10 @@ score_topk_kernel(const __grid_constant__ CUtensorMap map_q_main, const __grid_c
     for (int step = 0; step < sc.n_steps; ++step) {
       int qt, gt0, gt1, slot;
       if (!strip_at(sc, cta, step, qt, gt0, gt1, slot)) continue;
+      const int q_row = (PAIR ? 2 * qt + (int)rank : qt) * TILE_M;   // this CTA's own query tile
+      // In PAIR mode both CTAs issue copies into their own shared memory, all transaction bytes are
+      // credited to the LEADER's barriers, and only the leader posts the expected byte count.
+      constexpr uint32_t NCTA = PAIR ? 2u : 1u;
       if (RESIDENT) {
         if (!first) {  // the previous strip's MMAs must be done reading the resident tile
           mbar_wait(&bars->a_empty, a_par);
@@ -354,19 +370,23 @@ score_topk_kernel(const __grid_constant__ CUtensorMap map_q_main, const __grid_c
         }
         first = false;
         if (elect_one()) {
-          mbar_arrive_expect_tx(&bars->a_full, a_tile_bytes);
-          for (int kb = 0; kb < KB; ++kb)
-            tma_load_2d_hint(a_res + kb * A_BLK_BYTES, &map_q_main, &bars->a_full, kb * HYPRET_KBLK, qt * TILE_M,
-                             TMA_EVICT_LAST);
-          if (p.has_ext)
-            tma_load_2d_hint(a_res + KB * A_BLK_BYTES, &map_q_ext, &bars->a_full, p.dpad, qt * TILE_M,
-                             TMA_EVICT_LAST);
+          if (rank == 0) mbar_arrive_expect_tx(&bars->a_full, a_tile_bytes * NCTA);
+          for (int kb = 0; kb < KB; ++kb) {
+            if (PAIR) tma_load_2d_pair(a_res + kb * A_BLK_BYTES, &map_q_main, &bars->a_full, kb * HYPRET_KBLK, q_row,
+                                       TMA_EVICT_LAST);
+            else tma_load_2d_hint(a_res + kb * A_BLK_BYTES, &map_q_main, &bars->a_full, kb * HYPRET_KBLK, q_row,
+                                  TMA_EVICT_LAST);
+          }
+          if (p.has_ext) {
+            if (PAIR) tma_load_2d_pair(a_res + KB * A_BLK_BYTES, &map_q_ext, &bars->a_full, p.dpad, q_row,
+                                       TMA_EVICT_LAST);
+            else tma_load_2d_hint(a_res + KB * A_BLK_BYTES, &map_q_ext, &bars->a_full, p.dpad, q_row, TMA_EVICT_LAST);
+          }
         }
         __syncwarp();
       }
-      const int q_row = qt * TILE_M;
       for (int gt = gt0; gt < gt1; ++gt) {
-        const int g_row = gt * TILE_N;
+        const int g_row = gt * TILE_N + (int)rank * B_ROWS;          // this CTA's half of the gallery tile
         for (int ks = 0; ks < KSTEPS; ++ks) {
           timed_wait<DEBUG>(&bars->empty[stage], phase ^ 1, w_empty, p.wait_mode);
           if (elect_one()) {
@@ -374,13 +394,23 @@ score_topk_kernel(const __grid_constant__ CUtensorMap map_q_main, const __grid_c
             uint8_t* st_b = RESIDENT ? st : st + A_BLK_BYTES;
             uint64_t* full = &bars->full[stage];
             if (ks < KB) {
-              mbar_arrive_expect_tx(full, RESIDENT ? B_BLK_BYTES : A_BLK_BYTES + B_BLK_BYTES);
-              tma_load_2d(st_b, &map_g_main, full, ks * HYPRET_KBLK, g_row);
-              if (!RESIDENT) tma_load_2d_hint(st, &map_q_main, full, ks * HYPRET_KBLK, q_row, TMA_EVICT_LAST);
+              if (rank == 0) mbar_arrive_expect_tx(full, (RESIDENT ? B_BLK : A_BLK_BYTES + B_BLK) * NCTA);
+              if (PAIR) {
+                tma_load_2d_pair(st_b, &map_g_main, full, ks * HYPRET_KBLK, g_row, TMA_EVICT_NORMAL);
+                if (!RESIDENT) tma_load_2d_pair(st, &map_q_main, full, ks * HYPRET_KBLK, q_row, TMA_EVICT_LAST);
+              } else {
+                tma_load_2d(st_b, &map_g_main, full, ks * HYPRET_KBLK, g_row);
+                if (!RESIDENT) tma_load_2d_hint(st, &map_q_main, full, ks * HYPRET_KBLK, q_row, TMA_EVICT_LAST);
+              }
             } else {
-              mbar_arrive_expect_tx(full, RESIDENT ? B_EXT_BYTES : A_EXT_BYTES + B_EXT_BYTES);
-              tma_load_2d(st_b, &map_g_ext, full, p.dpad, g_row);
-              if (!RESIDENT) tma_load_2d_hint(st, &map_q_ext, full, p.dpad, q_row, TMA_EVICT_LAST);
+              if (rank == 0) mbar_arrive_expect_tx(full, (RESIDENT ? B_EXT : A_EXT_BYTES + B_EXT) * NCTA);
+              if (PAIR) {
+                tma_load_2d_pair(st_b, &map_g_ext, full, p.dpad, g_row, TMA_EVICT_NORMAL);
+                if (!RESIDENT) tma_load_2d_pair(st, &map_q_ext, full, p.dpad, q_row, TMA_EVICT_LAST);
+              } else {
+                tma_load_2d(st_b, &map_g_ext, full, p.dpad, g_row);
+                if (!RESIDENT) tma_load_2d_hint(st, &map_q_ext, full, p.dpad, q_row, TMA_EVICT_LAST);
+              }
             }
           }
           __syncwarp();
@@ -389,15 +419,15 @@ score_topk_kernel(const __grid_constant__ CUtensorMap map_q_main, const __grid_c
       }
     }
     if (DEBUG && p.stats != nullptr && lane == 0) {
-      p.stats[cta * 8 + 0] = w_empty;
-      p.stats[cta * 8 + 1] = (unsigned long long)clock64() - t_begin;
+      p.stats[blockIdx.x * 8 + 0] = w_empty;
+      p.stats[blockIdx.x * 8 + 1] = (unsigned long long)clock64() - t_begin;
     }
-  } else if (warp == 1) {
+  } else if (warp == 1 && rank == 0) {
     // ======================================================================= MMA issuer
     // Warp-uniform control flow; one elected lane issues tcgen05.mma / tcgen05.commit.  The
     // shared-memory descriptors are a constant high word plus (address >> 4): stepping K by 16
     // elements inside the 128-byte swizzle span is "+2" on the low word.
-    constexpr uint32_t idesc = umma_idesc_bf16(TILE_M, TILE_N);
+    constexpr uint32_t idesc = umma_idesc_bf16(PAIR ? 2 * TILE_M : TILE_M, TILE_N);
     constexpr uint64_t DESC_SW128 = (uint64_t(1) << 16) | (uint64_t(1024 >> 4) << 32) | (uint64_t(1) << 46) |
                                     (UMMA_LAYOUT_SW128 << 61);
     constexpr uint64_t DESC_SW32 = (uint64_t(1) << 16) | (uint64_t(256 >> 4) << 32) | (uint64_t(1) << 46) |
@@ -426,15 +456,26 @@ score_topk_kernel(const __grid_constant__ CUtensorMap map_q_main, const __grid_c
             if (ks < KB) {
               const uint32_t a_lo = RESIDENT ? ares_lo + ks * (A_BLK_BYTES >> 4) : st_lo;
 #pragma unroll
-              for (int k = 0; k < HYPRET_KBLK / 16; ++k)
-                umma_bf16_ss(d_tmem, DESC_SW128 | (a_lo + 2 * k), DESC_SW128 | (b_lo + 2 * k), idesc,
-                             (ks | k) != 0 ? 1u : 0u);
+              for (int k = 0; k < HYPRET_KBLK / 16; ++k) {
+                if (PAIR) umma_bf16_ss_pair(d_tmem, DESC_SW128 | (a_lo + 2 * k), DESC_SW128 | (b_lo + 2 * k), idesc,
+                                            (ks | k) != 0 ? 1u : 0u);
+                else umma_bf16_ss(d_tmem, DESC_SW128 | (a_lo + 2 * k), DESC_SW128 | (b_lo + 2 * k), idesc,
+                                  (ks | k) != 0 ? 1u : 0u);
+              }
             } else {
               const uint32_t a_lo = RESIDENT ? ares_lo + KB * (A_BLK_BYTES >> 4) : st_lo;
-              umma_bf16_ss(d_tmem, DESC_SW32 | a_lo, DESC_SW32 | b_lo, idesc, 1u);
+              if (PAIR) umma_bf16_ss_pair(d_tmem, DESC_SW32 | a_lo, DESC_SW32 | b_lo, idesc, 1u);
+              else umma_bf16_ss(d_tmem, DESC_SW32 | a_lo, DESC_SW32 | b_lo, idesc, 1u);
             }
-            umma_commit(&bars->empty[stage]);                          // ring stage reusable once these MMAs retire
-            if (ks == KSTEPS - 1) umma_commit(&bars->tmem_full[acc]);  // accumulator complete -> epilogue
+            // ring stage reusable once these MMAs retire; last K step: accumulator complete -> epilogue
+            // (PAIR: the arrivals are multicast to the same barriers of both CTAs)
+            if (PAIR) {
+              umma_commit_pair(&bars->empty[stage]);
+              if (ks == KSTEPS - 1) umma_commit_pair(&bars->tmem_full[acc]);
+            } else {
+              umma_commit(&bars->empty[stage]);
+              if (ks == KSTEPS - 1) umma_commit(&bars->tmem_full[acc]);
+            }
           }
           __syncwarp();
           if (++stage == (uint32_t)p.stages) { stage = 0; phase ^= 1; }
@@ -442,16 +483,19 @@ score_topk_kernel(const __grid_constant__ CUtensorMap map_q_main, const __grid_c
         if (++acc == NUM_ACC) { acc = 0; acc_phase ^= 1; }
       }
       if (RESIDENT) {
-        if (elect_one()) umma_commit(&bars->a_empty);
+        if (elect_one()) {
+          if (PAIR) umma_commit_pair(&bars->a_empty);
+          else umma_commit(&bars->a_empty);
+        }
         __syncwarp();
       }
     }
     if (DEBUG && p.stats != nullptr && lane == 0) {
-      p.stats[cta * 8 + 2] = w_full;
-      p.stats[cta * 8 + 3] = w_tmem;
-      p.stats[cta * 8 + 4] = (unsigned long long)clock64() - t_begin;
+      p.stats[blockIdx.x * 8 + 2] = w_full;
+      p.stats[blockIdx.x * 8 + 3] = w_tmem;
+      p.stats[blockIdx.x * 8 + 4] = (unsigned long long)clock64() - t_begin;
     }
-  } else {
+  } else if (warp >= 2) {
     // ======================================================================= epilogue / top-k'
     const int quad = warp & 3;                 // TMEM lane quadrant this warp may read
     const int row = quad * 32 + lane;          // query row inside the tile == TMEM lane
@@ -465,6 +509,7 @@ score_topk_kernel(const __grid_constant__ CUtensorMap map_q_main, const __grid_c
     for (int step = 0; step < sc.n_steps; ++step) {
       int qt, gt0, gt1, slot;
       if (!strip_at(sc, cta, step, qt, gt0, gt1, slot)) continue;
+      if (PAIR) qt = 2 * qt + (int)rank;         // this CTA's own query tile of the pair
       const int64_t qrow = (int64_t)qt * TILE_M + quad * 32 + lane;
       uint32_t* gthr = (p.shared_thr != nullptr && qrow < p.Q) ? p.shared_thr + qrow : nullptr;
       // cold list: active slots +inf (the list threshold stays +inf until k' scores are in),
@@ -528,7 +573,8 @@ score_topk_kernel(const __grid_constant__ CUtensorMap map_q_main, const __grid_c
           __syncwarp();
         }
         tcgen05_fence_before();
-        mbar_arrive(&bars->tmem_empty[acc]);
+        if (PAIR) mbar_arrive_cluster(&bars->tmem_empty[acc], 0);   // the leader waits for both CTAs' epilogues
+        else mbar_arrive(&bars->tmem_empty[acc]);
         if (++acc == NUM_ACC) { acc = 0; acc_phase ^= 1; }
         // exchange thresholds with the other strips of this query (L2 atomics, off the
         // critical path: the accumulator has already been released)
@@ -557,14 +603,18 @@ score_topk_kernel(const __grid_constant__ CUtensorMap map_q_main, const __grid_c
       __syncwarp();
     }
     if (DEBUG && p.stats != nullptr && warp == 2 && lane == 0) {
-      p.stats[cta * 8 + 5] = w_acc;
-      p.stats[cta * 8 + 6] = (unsigned long long)clock64() - t_begin;
+      p.stats[blockIdx.x * 8 + 5] = w_acc;
+      p.stats[blockIdx.x * 8 + 6] = (unsigned long long)clock64() - t_begin;
     }
   }
 
   tcgen05_fence_before();
-  __syncthreads();
-  if (warp == 2) tmem_dealloc(tmem_base, TMEM_COLS);
+  if (PAIR) cluster_sync_all();   // neither CTA may exit while its peer can still reach its barriers / smem
+  else __syncthreads();
+  if (warp == 2) {
+    if (PAIR) tmem_dealloc_2cta(tmem_base, TMEM_COLS);
+    else tmem_dealloc(tmem_base, TMEM_COLS);
+  }
 }
 
 // ----------------------------------------------------------------------------- host side
@@ -611,7 +661,7 @@ int device_sms() {
 
 Sched sched_from_plan(const hypret_score_plan_t& pl) {
   Sched s{};
-  s.T = pl.n_qtiles; s.G = pl.n_gtiles; s.P = pl.grid;
+  s.T = (pl.n_qtiles + pl.pair - 1) / pl.pair; s.G = pl.n_gtiles; s.P = pl.grid / pl.pair;
   s.n_full = pl.n_full; s.tail_rows = pl.tail_rows; s.a = pl.a; s.b = pl.b; s.L1 = pl.l1;
   s.rem_rows = pl.rem_rows; s.rem_g0 = pl.rem_g0; s.m = pl.m; s.L2 = pl.l2; s.n_steps = pl.n_steps;
   s.n_lists = pl.n_lists;
@@ -620,22 +670,37 @@ Sched sched_from_plan(const hypret_score_plan_t& pl) {
 
 int kpp_of(int kprime) { return kprime <= 16 ? 16 : 32; }
 
-template <bool RESIDENT, int KPP, bool DEBUG>
+template <bool RESIDENT, int KPP, bool DEBUG, bool PAIR>
 int launch_one(const hypret_score_plan_t& plan, const CUtensorMap& mq_main, const CUtensorMap& mq_ext,
                const CUtensorMap& mg_main, const CUtensorMap& mg_ext, const Params& p, cudaStream_t stream) {
-  cudaError_t e = cudaFuncSetAttribute(score_topk_kernel<RESIDENT, KPP, DEBUG>,
-                                       cudaFuncAttributeMaxDynamicSharedMemorySize, plan.smem_bytes);
+  auto kern = score_topk_kernel<RESIDENT, KPP, DEBUG, PAIR>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, plan.smem_bytes);
   if (e != cudaSuccess) return (int)e;
-  score_topk_kernel<RESIDENT, KPP, DEBUG><<<plan.grid, NUM_THREADS, plan.smem_bytes, stream>>>(mq_main, mq_ext,
-                                                                                              mg_main, mg_ext, p);
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)plan.grid);
+  cfg.blockDim = dim3(NUM_THREADS);
+  cfg.dynamicSmemBytes = (size_t)plan.smem_bytes;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = PAIR ? 2 : 1;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  e = cudaLaunchKernelEx(&cfg, kern, mq_main, mq_ext, mg_main, mg_ext, p);
+  if (e != cudaSuccess) return (int)e;
   return (int)cudaGetLastError();
 }
 template <bool RESIDENT, int KPP>
 int launch_variant(const hypret_score_plan_t& plan, const CUtensorMap& mq_main, const CUtensorMap& mq_ext,
                    const CUtensorMap& mg_main, const CUtensorMap& mg_ext, const Params& p, cudaStream_t stream) {
-  return (p.debug_scores != nullptr || p.stats != nullptr)
-             ? launch_one<RESIDENT, KPP, true>(plan, mq_main, mq_ext, mg_main, mg_ext, p, stream)
-             : launch_one<RESIDENT, KPP, false>(plan, mq_main, mq_ext, mg_main, mg_ext, p, stream);
+  const bool dbg = p.debug_scores != nullptr || p.stats != nullptr;
+  if (plan.pair == 2)
+    return dbg ? launch_one<RESIDENT, KPP, true, true>(plan, mq_main, mq_ext, mg_main, mg_ext, p, stream)
+               : launch_one<RESIDENT, KPP, false, true>(plan, mq_main, mq_ext, mg_main, mg_ext, p, stream);
+  return dbg ? launch_one<RESIDENT, KPP, true, false>(plan, mq_main, mq_ext, mg_main, mg_ext, p, stream)
+             : launch_one<RESIDENT, KPP, false, false>(plan, mq_main, mq_ext, mg_main, mg_ext, p, stream);
 }
 
 }  // namespace
@@ -650,6 +715,13 @@ extern "C" int hypret_score_plan(int64_t Q, int64_t N, int d, int kprime, int ma
   const int64_t n_gtiles = (N + TILE_N - 1) / TILE_N;
   if (n_qtiles > (1 << 24)) return HYPRET_EUNSUPPORTED;
 
+  // CTA pairs (tcgen05 cta_group::2) whenever there are at least two query tiles to pair up
+  int ctas = sms;
+  if (max_ctas > 0 && max_ctas < ctas) ctas = max_ctas;
+  const char* pair_env = getenv("HYPRET_PAIR");                  // experiments: 0 forces single-CTA MMAs
+  const bool pair = n_qtiles >= 2 && ctas >= 2 && !(pair_env != nullptr && pair_env[0] == '0');
+  const int b_blk = pair ? B_BLK_BYTES / 2 : B_BLK_BYTES;
+
   // shared-memory carve-up
   const int lists = kpp_of(kprime) * TILE_M * 8;
   const int a_res_bytes = kb * A_BLK_BYTES + A_EXT_BYTES;
@@ -658,24 +730,25 @@ extern "C" int hypret_score_plan(int64_t Q, int64_t N, int d, int kprime, int ma
     const int avail = SMEM_LIMIT - 1024 - BAR_BYTES - lists - a_res_bytes;
     const char* force = getenv("HYPRET_FORCE_STREAM");   // experiments only
     // Resident query tile only when the gallery ring is still >= 4 stages deep; with the two
-    // stages that D=512 leaves, the MMA pipe starves (measured 863 vs 1103 TFLOP/s).
+    // stages that D=512 leaves in single-CTA mode the MMA pipe starves (measured 863 vs 1103 TFLOP/s).
     const bool force_res = force != nullptr && force[0] == '0';
-    if (kb <= 8 && avail >= (force_res ? 2 : 4) * B_BLK_BYTES && !(force != nullptr && force[0] == '1')) {
+    if (kb <= 8 && avail >= (force_res ? 2 : 4) * b_blk && !(force != nullptr && force[0] == '1')) {
       resident = 1;
-      stage_bytes = B_BLK_BYTES;
-      stages = avail / B_BLK_BYTES;
+      stage_bytes = b_blk;
+      stages = avail / b_blk;
     } else {
-      stage_bytes = A_BLK_BYTES + B_BLK_BYTES;
+      stage_bytes = A_BLK_BYTES + b_blk;
       stages = (SMEM_LIMIT - 1024 - BAR_BYTES - lists) / stage_bytes;
     }
     if (stages > MAX_STAGES) stages = MAX_STAGES;
     if (stages < 2) return HYPRET_EUNSUPPORTED;
   }
-  const Sched s = make_sched(n_qtiles, n_gtiles, sms, max_ctas);
+  const int64_t rows = pair ? (n_qtiles + 1) / 2 : n_qtiles;     // scheduling rows: query tiles or tile pairs
+  const Sched s = make_sched(rows, n_gtiles, pair ? ctas / 2 : ctas, 0);
   plan->n_qtiles = (int32_t)n_qtiles;
   plan->n_gtiles = (int32_t)n_gtiles;
   plan->n_lists = s.n_lists;
-  plan->grid = s.P;
+  plan->grid = pair ? 2 * s.P : s.P;
   plan->stages = stages;
   plan->resident = resident;
   plan->smem_bytes = 1024 + (resident ? a_res_bytes : 0) + stages * stage_bytes + lists + BAR_BYTES;
@@ -689,16 +762,18 @@ extern "C" int hypret_score_plan(int64_t Q, int64_t N, int d, int kprime, int ma
   plan->m = s.m;
   plan->l2 = s.L2;
   plan->n_steps = s.n_steps;
+  plan->pair = pair ? 2 : 1;
   return HYPRET_OK;
 }
 
 extern "C" int hypret_score_strip(const hypret_score_plan_t* plan, int cta, int step, int32_t* out4) {
-  if (plan == nullptr || out4 == nullptr || cta < 0 || cta >= plan->grid || step < 0 || step >= plan->n_steps)
+  if (plan == nullptr || out4 == nullptr || cta < 0 || cta >= plan->grid / plan->pair || step < 0 ||
+      step >= plan->n_steps)
     return HYPRET_EINVAL;
   const Sched s = sched_from_plan(*plan);
   int qt = 0, g0 = 0, g1 = 0, slot = 0;
   const bool ok = strip_at(s, cta, step, qt, g0, g1, slot);
-  out4[0] = qt; out4[1] = g0; out4[2] = g1; out4[3] = slot;
+  out4[0] = qt * plan->pair; out4[1] = g0; out4[2] = g1; out4[3] = slot;
   return ok ? 1 : 0;
 }
 
@@ -716,8 +791,9 @@ int hypret_launch_score_topk(const void* q_op, int64_t Q, const void* g_op, int6
   CUtensorMap mq_main, mq_ext, mg_main, mg_ext;
   if ((rc = make_map(&mq_main, q_op, Q, kpad, HYPRET_KBLK, TILE_M, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
   if ((rc = make_map(&mq_ext, q_op, Q, kpad, HYPRET_KEXT, TILE_M, CU_TENSOR_MAP_SWIZZLE_32B))) return rc;
-  if ((rc = make_map(&mg_main, g_op, N, kpad, HYPRET_KBLK, TILE_N, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
-  if ((rc = make_map(&mg_ext, g_op, N, kpad, HYPRET_KEXT, TILE_N, CU_TENSOR_MAP_SWIZZLE_32B))) return rc;
+  const int g_box = TILE_N / plan.pair;   // CTA pairs: each CTA stages half of the gallery tile
+  if ((rc = make_map(&mg_main, g_op, N, kpad, HYPRET_KBLK, g_box, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
+  if ((rc = make_map(&mg_ext, g_op, N, kpad, HYPRET_KEXT, g_box, CU_TENSOR_MAP_SWIZZLE_32B))) return rc;
 
   Params p;
   p.Q = Q;
@@ -727,7 +803,7 @@ int hypret_launch_score_topk(const void* q_op, int64_t Q, const void* g_op, int6
   p.dpad = dpad;
   p.kprime = kprime;
   p.stages = plan.stages;
-  p.stage_bytes = plan.resident ? B_BLK_BYTES : A_BLK_BYTES + B_BLK_BYTES;
+  p.stage_bytes = plan.resident ? B_BLK_BYTES / plan.pair : A_BLK_BYTES + B_BLK_BYTES / plan.pair;
   p.ring_off = plan.resident ? p.kb_main * A_BLK_BYTES + A_EXT_BYTES : 0;
   p.lists_off = p.ring_off + plan.stages * p.stage_bytes;
   p.bar_off = p.lists_off + kpp_of(kprime) * TILE_M * 8;

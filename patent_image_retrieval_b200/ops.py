@@ -69,12 +69,13 @@ def _score_plan_struct(Q, N, d, kprime, max_ctas=0):
 
 
 def score_strips(Q: int, N: int, d: int, kprime: int, max_ctas: int = 0):
-    """All strips of the schedule as ``(cta, step, query_tile, g0, g1, slot)`` tuples (host-only)."""
+    """All strips of the schedule as ``(unit, step, first_query_tile, g0, g1, slot)`` tuples (host-only).
+    A strip covers ``plan["pair"]`` consecutive query tiles."""
     plan = _score_plan_struct(Q, N, d, kprime, max_ctas)
     out = (ctypes.c_int32 * 4)()
     strips = []
     lib = _lib.load()
-    for cta in range(plan.grid):
+    for cta in range(plan.grid // plan.pair):
         for step in range(plan.n_steps):
             rc = lib.hypret_score_strip(ctypes.byref(plan), cta, step, out)
             if rc < 0:

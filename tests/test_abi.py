@@ -58,37 +58,40 @@ def test_strip_schedule_covers_every_tile_once(Q, N, d, kp, cap):
     busiest CTA is within a few percent of the ideal share."""
     from patent_image_retrieval_b200 import ops
     p = ops.score_plan(Q, N, d, kp, cap)
-    T, G, P = p["n_qtiles"], p["n_gtiles"], p["grid"]
+    pair = p["pair"]
+    T, G, P = p["n_qtiles"], p["n_gtiles"], p["grid"] // pair      # P scheduling units (CTAs or CTA pairs)
+    TR = -(-T // pair)                                              # scheduling rows (query tiles or tile pairs)
     assert T == -(-Q // 128) and G == -(-N // 256)
+    assert pair in (1, 2) and p["grid"] % pair == 0
     assert 2 <= p["stages"] <= 8 and p["smem_bytes"] <= 232448
     strips = ops.score_strips(Q, N, d, kp, cap)
     seen = {}
     per_cta = {}
     steps = set()
     for cta, step, qt, g0, g1, slot in strips:
-        assert 0 <= qt < T and 0 <= g0 < g1 <= G and 0 <= slot < p["n_lists"] and 0 <= cta < P
+        assert 0 <= qt < T and qt % pair == 0 and 0 <= g0 < g1 <= G and 0 <= slot < p["n_lists"] and 0 <= cta < P
         assert (cta, step) not in steps
         steps.add((cta, step))
         assert (qt, slot) not in seen
         seen[(qt, slot)] = (g0, g1)
         per_cta[cta] = per_cta.get(cta, 0) + (g1 - g0)
-    if T * G <= 200000:                   # exhaustive coverage check on the small cases
+    if TR * G <= 200000:                  # exhaustive coverage check on the small cases
         cover = {}
         for (qt, slot), (g0, g1) in seen.items():
             for g in range(g0, g1):
                 assert (qt, g) not in cover
                 cover[(qt, g)] = 1
-        assert len(cover) == T * G
+        assert len(cover) == TR * G
     else:                                 # interval check on the big ones
         by_qt = {}
         for (qt, slot), (g0, g1) in seen.items():
             by_qt.setdefault(qt, []).append((g0, g1))
-        assert len(by_qt) == T
+        assert len(by_qt) == TR
         for qt, iv in by_qt.items():
             iv.sort()
             assert iv[0][0] == 0 and iv[-1][1] == G
             assert all(a[1] == b[0] for a, b in zip(iv, iv[1:]))
-    ideal = T * G / P
+    ideal = TR * G / P
     if ideal >= 64:
         assert max(per_cta.values()) <= 1.03 * ideal + 2
     # resident query tile only while the gallery ring stays >= 4 stages deep
@@ -98,9 +101,10 @@ def test_strip_schedule_covers_every_tile_once(Q, N, d, kp, cap):
 def test_c2_plan_numbers():
     from patent_image_retrieval_b200 import ops
     p = ops.score_plan(10000, 300000, 512, 16)
-    assert (p["grid"], p["n_full"], p["tail_rows"], p["a"], p["b"]) == (148, 0, 79, 1, 69)
-    assert p["l1"] == 586 and p["rem_rows"] == 10 and p["m"] == 14 and p["l2"] == 42
-    assert p["n_lists"] == 15 and p["resident"] == 0 and p["stages"] == 4
+    # 79 query tiles -> 40 tile pairs on 74 CTA pairs: 1 strip each + 34 rows with a second strip, rest in phase 2
+    assert (p["grid"], p["pair"], p["n_full"], p["tail_rows"], p["a"], p["b"]) == (148, 2, 0, 40, 1, 34)
+    assert p["l1"] == 586 and p["rem_rows"] == 6 and p["m"] == 12 and p["l2"] == 49
+    assert p["n_lists"] == 13 and p["resident"] == 1 and p["stages"] == 4
     with pytest.raises(RuntimeError):
         ops.score_plan(10, 10, 512, 64)          # kprime > 32
 

@@ -43,10 +43,12 @@ def test_scores_and_lists(Q, N, d, kprime, cap):
     plan = ops.score_plan(Q, N, d, kprime, cap)
     assert cs.shape == (Q, plan["n_lists"], kprime)
     written = set()
+    pair = plan["pair"]
     for cta, step, qt, g0, g1, slot in ops.score_strips(Q, N, d, kprime, cap):
-        r0, r1 = qt * 128, min(Q, qt * 128 + 128)
+        r0, r1 = qt * 128, min(Q, (qt + pair) * 128)
         lo, hi = g0 * 256, min(N, g1 * 256)
-        written.add((qt, slot))
+        for t in range(pair):
+            written.add((qt + t, slot))
         kk = min(kprime, hi - lo)
         want_v, _ = torch.topk(dbg[r0:r1, lo:hi], kk, dim=1, largest=False)
         got_v, order = cs[r0:r1, slot, :].sort(dim=1)
@@ -75,7 +77,7 @@ def test_shared_thresholds_keep_the_global_topk(Q, N, d, kprime, cap):
     plan = ops.score_plan(Q, N, d, kprime, cap)
     L = plan["n_lists"]
     for cta, step, qt, g0, g1, slot in ops.score_strips(Q, N, d, kprime, cap):
-        r0, r1 = qt * 128, min(Q, qt * 128 + 128)
+        r0, r1 = qt * 128, min(Q, (qt + plan["pair"]) * 128)
         lo, hi = g0 * 256, min(N, g1 * 256)
         idx = ci[r0:r1, slot, :].long()
         valid = idx >= 0

@@ -51,7 +51,7 @@ def check(Q, N, d, kprime=16, hint=0, label=""):
             # candidate lists vs torch.topk on the kernel's own score matrix
             miss = 0
             for cta, step, qt, g0, g1, slot in ops.score_strips(Q, N, d, kprime, hint):
-                r0, r1 = qt * 128, min(Q, qt * 128 + 128)
+                r0, r1 = qt * 128, min(Q, (qt + plan["pair"]) * 128)
                 lo, hi = g0 * 256, min(N, g1 * 256)
                 kk = min(kprime, hi - lo)
                 want = torch.topk(dbg[r0:r1, lo:hi], kk, dim=1, largest=False).values.sort(dim=1).values
@@ -85,7 +85,7 @@ def bench(Q, N, d, kprime=16, iters=5):
         ms = e0.elapsed_time(e1) / iters
         tf = 2.0 * Q * N * d / ms / 1e9
         print(f"[bench share={int(share)}] Q={Q} N={N} d={d} grid={plan['grid']} lists={plan['n_lists']} "
-              f"stages={plan['stages']} resident={plan['resident']}: {ms:.3f} ms  {tf:.1f} TFLOP/s (algorithmic)  "
+              f"stages={plan['stages']} resident={plan['resident']} pair={plan['pair']}: {ms:.3f} ms  {tf:.1f} TFLOP/s (algorithmic)  "
               f"{Q / ms * 1e3:.0f} q/s", flush=True)
 
 
