@@ -27,6 +27,7 @@ __device__ __forceinline__ bool key_less(double a, int ia, double b, int ib) {
   return (a < b) || (a == b && ia < ib);
 }
 
+template <int NV>   // float4 chunks of a row per lane: D <= NV * 128
 __global__ void __launch_bounds__(RR_WARPS * 32)
 rerank_kernel(const float* __restrict__ q32, const float* __restrict__ g32, int64_t Q, int64_t N, int d, float c,
               int metric, const float* __restrict__ cand_score, const int32_t* __restrict__ cand_idx, int n_cand,
@@ -48,7 +49,6 @@ rerank_kernel(const float* __restrict__ q32, const float* __restrict__ g32, int6
   }
   __syncwarp();
   int my_idx = -1;          // lane r holds the r-th selected candidate
-  float my_approx = INFINITY;
   float worst_approx = -INFINITY;
   for (int r = 0; r < kprime; ++r) {
     float bs = INFINITY;
@@ -66,72 +66,86 @@ rerank_kernel(const float* __restrict__ q32, const float* __restrict__ g32, int6
       if (op >= 0 && (bpos < 0 || os < bs || (os == bs && oi < bi))) { bs = os; bi = oi; bpos = op; }
     }
     if (bpos < 0) break;      // fewer than k' valid candidates (warp-uniform)
-    if (lane == r) { my_idx = bi; my_approx = bs; }
+    if (lane == r) my_idx = bi;
     worst_approx = bs;
     if ((bpos & 31) == lane) ci[bpos] = -1;
     __syncwarp();
   }
 
   // ---- 2. exact scores of the survivors ---------------------------------------------------
+  // the query row stays in registers; four gallery rows are streamed per pass (independent
+  // 128-bit loads in flight), fp64 accumulation of explicitly formed differences
   const int nvec = d >> 2;
   const float4* qrow = reinterpret_cast<const float4*>(q32 + q * d);
+  float4 qv[NV];
   double xsq = 0.0;
-  for (int j = lane; j < nvec; j += 32) {
-    const float4 a = __ldg(qrow + j);
-    xsq += (double)a.x * a.x + (double)a.y * a.y + (double)a.z * a.z + (double)a.w * a.w;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int j = i * 32 + lane;
+    qv[i] = (j < nvec) ? __ldg(qrow + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+    xsq += (double)qv[i].x * qv[i].x + (double)qv[i].y * qv[i].y + (double)qv[i].z * qv[i].z +
+           (double)qv[i].w * qv[i].w;
   }
   xsq = warp_sum(xsq);
 
   double my_key = INFINITY;     // sort key (distance, or minus similarity)
   double my_sur = INFINITY;     // exact surrogate, comparable with the approximate scores
-  for (int r0 = 0; r0 < kprime; r0 += 2) {
-    // two candidates per pass: independent row streams in flight
-    const int i0 = __shfl_sync(0xffffffffu, my_idx, r0);
-    const int i1 = (r0 + 1 < 32) ? __shfl_sync(0xffffffffu, my_idx, (r0 + 1) & 31) : -1;
-    const bool v0 = i0 >= 0, v1 = (r0 + 1 < kprime) && i1 >= 0;
-    if (!v0 && !v1) continue;
-    const float4* g0 = reinterpret_cast<const float4*>(g32 + (int64_t)(v0 ? i0 : 0) * d);
-    const float4* g1 = reinterpret_cast<const float4*>(g32 + (int64_t)(v1 ? i1 : 0) * d);
-    double s0 = 0.0, y0 = 0.0, s1 = 0.0, y1 = 0.0;   // hyperbolic: sum (x-y)^2 ; cosine: sum x*y
-    for (int j = lane; j < nvec; j += 32) {
-      const float4 a = __ldg(qrow + j);
-      const float4 b0 = __ldg(g0 + j);
-      const float4 b1 = __ldg(g1 + j);
-      if (metric == HYPRET_METRIC_HYPERBOLIC) {
-        const float e0 = a.x - b0.x, e1 = a.y - b0.y, e2 = a.z - b0.z, e3 = a.w - b0.w;
-        const float f0 = a.x - b1.x, f1 = a.y - b1.y, f2 = a.z - b1.z, f3 = a.w - b1.w;
-        s0 += (double)e0 * e0 + (double)e1 * e1 + (double)e2 * e2 + (double)e3 * e3;
-        s1 += (double)f0 * f0 + (double)f1 * f1 + (double)f2 * f2 + (double)f3 * f3;
-      } else {
-        s0 += (double)a.x * b0.x + (double)a.y * b0.y + (double)a.z * b0.z + (double)a.w * b0.w;
-        s1 += (double)a.x * b1.x + (double)a.y * b1.y + (double)a.z * b1.z + (double)a.w * b1.w;
+  constexpr int PASS = 4;
+  for (int r0 = 0; r0 < kprime; r0 += PASS) {
+    int idx[PASS];
+    bool val[PASS];
+    const float4* g[PASS];
+    bool any = false;
+#pragma unroll
+    for (int t = 0; t < PASS; ++t) {
+      idx[t] = __shfl_sync(0xffffffffu, my_idx, (r0 + t) & 31);
+      val[t] = (r0 + t < kprime) && idx[t] >= 0;
+      any |= val[t];
+      g[t] = reinterpret_cast<const float4*>(g32 + (int64_t)(val[t] ? idx[t] : 0) * d);
+    }
+    if (!any) continue;
+    double sacc[PASS], yacc[PASS];
+#pragma unroll
+    for (int t = 0; t < PASS; ++t) { sacc[t] = 0.0; yacc[t] = 0.0; }
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int j = i * 32 + lane;
+      if (j < nvec) {
+        float4 b[PASS];
+#pragma unroll
+        for (int t = 0; t < PASS; ++t) b[t] = __ldg(g[t] + j);
+#pragma unroll
+        for (int t = 0; t < PASS; ++t) {
+          if (metric == HYPRET_METRIC_HYPERBOLIC) {
+            const float e0 = qv[i].x - b[t].x, e1 = qv[i].y - b[t].y, e2 = qv[i].z - b[t].z, e3 = qv[i].w - b[t].w;
+            sacc[t] += (double)e0 * e0 + (double)e1 * e1 + (double)e2 * e2 + (double)e3 * e3;
+          } else {
+            sacc[t] += (double)qv[i].x * b[t].x + (double)qv[i].y * b[t].y + (double)qv[i].z * b[t].z +
+                       (double)qv[i].w * b[t].w;
+          }
+          yacc[t] += (double)b[t].x * b[t].x + (double)b[t].y * b[t].y + (double)b[t].z * b[t].z +
+                     (double)b[t].w * b[t].w;
+        }
       }
-      y0 += (double)b0.x * b0.x + (double)b0.y * b0.y + (double)b0.z * b0.z + (double)b0.w * b0.w;
-      y1 += (double)b1.x * b1.x + (double)b1.y * b1.y + (double)b1.z * b1.z + (double)b1.w * b1.w;
     }
-    s0 = warp_sum(s0); y0 = warp_sum(y0);
-    s1 = warp_sum(s1); y1 = warp_sum(y1);
-    double key0, sur0, key1, sur1;
-    if (metric == HYPRET_METRIC_HYPERBOLIC) {
-      const double cc = (double)c;
-      const double al = 1.0 - cc * xsq;
-      const double t0 = 2.0 * cc * s0 / (al * (1.0 - cc * y0));
-      const double t1 = 2.0 * cc * s1 / (al * (1.0 - cc * y1));
-      key0 = log1p(t0 + sqrt(t0 * (t0 + 2.0))) / sqrt(cc);
-      key1 = log1p(t1 + sqrt(t1 * (t1 + 2.0))) / sqrt(cc);
-      sur0 = s0 / (1.0 - cc * y0);
-      sur1 = s1 / (1.0 - cc * y1);
-    } else {
-      const double nx = sqrt(xsq);
-      const double d0 = (nx == 0.0 ? 1.0 : nx) * (y0 == 0.0 ? 1.0 : sqrt(y0));
-      const double d1 = (nx == 0.0 ? 1.0 : nx) * (y1 == 0.0 ? 1.0 : sqrt(y1));
-      key0 = -(s0 / d0);
-      key1 = -(s1 / d1);
-      sur0 = key0;
-      sur1 = key1;
+#pragma unroll
+    for (int t = 0; t < PASS; ++t) {
+      const double s0 = warp_sum(sacc[t]), y0 = warp_sum(yacc[t]);
+      double key0, sur0;
+      if (metric == HYPRET_METRIC_HYPERBOLIC) {
+        const double cc = (double)c;
+        const double al = 1.0 - cc * xsq;
+        const double t0 = 2.0 * cc * s0 / (al * (1.0 - cc * y0));
+        key0 = log1p(t0 + sqrt(t0 * (t0 + 2.0))) / sqrt(cc);
+        sur0 = s0 / (1.0 - cc * y0);
+      } else {
+        const double nx = sqrt(xsq);
+        const double d0 = (nx == 0.0 ? 1.0 : nx) * (y0 == 0.0 ? 1.0 : sqrt(y0));
+        key0 = -(s0 / d0);
+        sur0 = key0;
+      }
+      if (val[t] && lane == r0 + t) { my_key = key0; my_sur = sur0; }
     }
-    if (v0 && lane == r0) { my_key = key0; my_sur = sur0; }
-    if (v1 && lane == r0 + 1) { my_key = key1; my_sur = sur1; }
   }
 
   // ---- 3. warp bitonic sort by (key, index) -----------------------------------------------
@@ -175,13 +189,26 @@ int hypret_launch_rerank(const float* q32, const float* g32, int64_t Q, int64_t 
   if (Q == 0) return HYPRET_OK;
   const size_t smem = (size_t)RR_WARPS * n_cand * 8;
   if (smem > 200 * 1024) return HYPRET_EUNSUPPORTED;
-  if (smem > 48 * 1024) {
-    cudaError_t e = cudaFuncSetAttribute(rerank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return (int)e;
-  }
   const int64_t grid = (Q + RR_WARPS - 1) / RR_WARPS;
-  rerank_kernel<<<(unsigned)grid, RR_WARPS * 32, smem, stream>>>(q32, g32, Q, N, d, c, metric, cand_score, cand_idx,
-                                                                n_cand, kprime, k, idx_offset, out_score, out_idx,
-                                                                out_margin);
-  return (int)cudaGetLastError();
+  const int need = (d + 127) / 128;
+#define HYPRET_RERANK_LAUNCH(NV)                                                                                    \
+  do {                                                                                                              \
+    if (smem > 48 * 1024) {                                                                                         \
+      cudaError_t e =                                                                                               \
+          cudaFuncSetAttribute(rerank_kernel<NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);          \
+      if (e != cudaSuccess) return (int)e;                                                                          \
+    }                                                                                                               \
+    rerank_kernel<NV><<<(unsigned)grid, RR_WARPS * 32, smem, stream>>>(q32, g32, Q, N, d, c, metric, cand_score,    \
+                                                                      cand_idx, n_cand, kprime, k, idx_offset,      \
+                                                                      out_score, out_idx, out_margin);              \
+    return (int)cudaGetLastError();                                                                                 \
+  } while (0)
+  if (need <= 1) HYPRET_RERANK_LAUNCH(1);
+  if (need <= 2) HYPRET_RERANK_LAUNCH(2);
+  if (need <= 4) HYPRET_RERANK_LAUNCH(4);
+  if (need <= 6) HYPRET_RERANK_LAUNCH(6);
+  if (need <= 8) HYPRET_RERANK_LAUNCH(8);
+  if (need <= 16) HYPRET_RERANK_LAUNCH(16);
+#undef HYPRET_RERANK_LAUNCH
+  return HYPRET_EUNSUPPORTED;
 }

@@ -98,3 +98,66 @@ class GalleryIndex:
             kernel_events.append((e0, e1))
         return ops.rerank(q32, self.rows32, cs, ci, self.c, self.metric, k, idx_offset=self.idx_offset,
                           want_margin=return_margin)
+
+
+class SearchPipeline:
+    """Host-buffer serving loop: pinned-host query batches in, pinned-host ``[Q,k]`` results out,
+    with the H2D copy of batch i+1 and the D2H copy of batch i-1 overlapping the search of batch i
+    (three streams, double-buffered device and host buffers).  ``index`` is a ``GalleryIndex`` or a
+    ``dist.ShardedGalleryIndex``.
+
+        pipe = SearchPipeline(index, Q, k)
+        slot = pipe.submit(q_host_pinned)          # asynchronous
+        score, idx = pipe.result(slot)             # blocks until that batch's results are on the host
+    """
+
+    def __init__(self, index, n_queries: int, k: int = 10, kprime: Optional[int] = None, depth: int = 2):
+        local = getattr(index, "local", index)
+        self.index = index
+        self.k, self.kprime, self.depth = k, kprime, depth
+        self.device = local.device
+        self.copy_in = torch.cuda.Stream(device=self.device)
+        self.compute = torch.cuda.Stream(device=self.device)
+        self.copy_out = torch.cuda.Stream(device=self.device)
+        self.q_dev = [torch.empty(n_queries, local.d, dtype=torch.float32, device=self.device) for _ in range(depth)]
+        self.out_s = [torch.empty(n_queries, k, dtype=torch.float32, pin_memory=True) for _ in range(depth)]
+        self.out_i = [torch.empty(n_queries, k, dtype=torch.int64, pin_memory=True) for _ in range(depth)]
+        self.ev_in = [torch.cuda.Event() for _ in range(depth)]
+        self.ev_done = [torch.cuda.Event() for _ in range(depth)]
+        self.ev_out = [torch.cuda.Event() for _ in range(depth)]
+        self.n = 0
+        self.bytes_in = n_queries * local.d * 4
+        self.bytes_out = n_queries * k * 12
+
+    def submit(self, q_host: torch.Tensor, kernel_events: Optional[list] = None) -> int:
+        slot = self.n % self.depth
+        if self.n >= self.depth:
+            # the device query buffer of this slot was last read by the search submitted `depth` steps ago,
+            # and its host result buffers by the caller: both must be done
+            self.copy_in.wait_event(self.ev_done[slot])
+            self.ev_out[slot].synchronize()
+        with torch.cuda.stream(self.copy_in):
+            self.q_dev[slot].copy_(q_host, non_blocking=True)
+            self.ev_in[slot].record(self.copy_in)
+        self.compute.wait_event(self.ev_in[slot])
+        with torch.cuda.stream(self.compute):
+            kw = {"kernel_events": kernel_events} if kernel_events is not None else {}
+            score, idx = self.index.search(self.q_dev[slot], k=self.k, kprime=self.kprime, **kw)
+            self.ev_done[slot].record(self.compute)
+        score.record_stream(self.copy_out)
+        idx.record_stream(self.copy_out)
+        self.copy_out.wait_event(self.ev_done[slot])
+        with torch.cuda.stream(self.copy_out):
+            self.out_s[slot].copy_(score, non_blocking=True)
+            self.out_i[slot].copy_(idx, non_blocking=True)
+            self.ev_out[slot].record(self.copy_out)
+        self.n += 1
+        return slot
+
+    def result(self, slot: int):
+        self.ev_out[slot].synchronize()
+        return self.out_s[slot], self.out_i[slot]
+
+    def drain(self):
+        for ev in self.ev_out:
+            ev.synchronize()
