@@ -256,13 +256,60 @@ __device__ __noinline__ uint2 list_insert(uint32_t s_addr, uint32_t i_addr, floa
   return make_uint2(__float_as_uint(mx), (uint32_t)pos);
 }
 
-// One 32-column chunk of the accumulator.  Every lane owns one query row: `thr` is that row's
-// effective threshold = min(worst kept score, bound shared by the query's other strips).
-// Fast path: 3-input min tree + one compare.  Slow path: plain SIMT divergence -- only lanes
-// with a hit walk their group / column and call the private insert; no cross-lane traffic.
+// Pending-hit queue.  A hit is usually confined to one or two lanes of the warp, so inserting it
+// on the spot costs a whole SIMT pass (one list rescan) per hit -- ~2400 passes per strip, almost
+// all of them in the cold phase after a strip start, 0.29 ms per launch.  Instead each lane
+// appends its hits to a small private queue ([slot][row] in shared memory, two predicated
+// stores) and the warp drains all queues together: one rescan pass then serves up to 32 lanes'
+// inserts.  The threshold a lane filters with is refreshed at every drain, so it is at most a
+// few hits stale -- that only lets a few extra candidates into the queue, never drops one.
+constexpr int QCAP = 12;   // queue slots per lane (12 x 8 B x 128 rows = 12 KB)
+
+struct RowState {
+  float thr;        // effective filter threshold = min(thr_list, thr_g)
+  float thr_list;   // worst score currently kept (+inf until the list is full)
+  float thr_g;      // bound shared by the query's other strips
+  int maxpos;       // slot of the worst kept score
+  int cnt;          // pending hits in the queue
+  int n_ins;        // DEBUG statistics: list inserts done by this lane
+  int n_drain;      // DEBUG statistics: drain-loop passes of the warp
+  int n_now;        // DEBUG statistics: inserts that bypassed the (full) queue
+};
+
 template <int KPP>
-__device__ __forceinline__ void process_chunk(const float (&v)[32], int cbase, float& thr, float& thr_list,
-                                              const float thr_g, int& maxpos, uint32_t s_addr, uint32_t i_addr) {
+__device__ __forceinline__ void insert_now(RowState& st, float x, int col, uint32_t s_addr, uint32_t i_addr) {
+  const uint2 r = list_insert<KPP>(s_addr, i_addr, x, col, st.maxpos);
+  st.n_ins += 1;
+  st.thr_list = __uint_as_float(r.x);
+  st.maxpos = (int)r.y;
+  st.thr = fminf(st.thr_list, st.thr_g);
+}
+
+// warp-uniform: every lane pops its own queue; lanes that run dry idle until the longest is empty
+template <int KPP>
+__device__ __forceinline__ void drain_queue(RowState& st, uint32_t s_addr, uint32_t i_addr, uint32_t qs_addr,
+                                            uint32_t qi_addr) {
+  while (__any_sync(FULL, st.cnt > 0)) {
+    st.n_drain += 1;
+    if (st.cnt > 0) {
+      st.cnt -= 1;
+      const float x = lds_f32(qs_addr + st.cnt * LIST_SLOT_STRIDE);
+      if (x < st.thr) {   // the threshold may have tightened since the hit was queued
+        int col;
+        asm volatile("ld.shared.b32 %0, [%1];" : "=r"(col) : "r"(qi_addr + st.cnt * LIST_SLOT_STRIDE) : "memory");
+        insert_now<KPP>(st, x, col, s_addr, i_addr);
+      }
+    }
+  }
+}
+
+// One 32-column chunk of the accumulator.  Every lane owns one query row.  Fast path: 3-input min
+// tree + one compare.  Slow path: plain SIMT divergence -- only lanes with a hit walk their group
+// and queue the hit (or insert it at once when the queue is full, which only happens in the
+// first tile of a cold strip).
+template <int KPP>
+__device__ __forceinline__ void process_chunk(const float (&v)[32], int cbase, RowState& st, uint32_t s_addr,
+                                              uint32_t i_addr, uint32_t qs_addr, uint32_t qi_addr) {
   float mg[4];
 #pragma unroll
   for (int g = 0; g < 4; ++g) {
@@ -272,18 +319,22 @@ __device__ __forceinline__ void process_chunk(const float (&v)[32], int cbase, f
     mg[g] = m;
   }
   const float m = fminf(fminf(mg[0], mg[1]), fminf(mg[2], mg[3]));
-  if (m < thr) {
+  if (m < st.thr) {
 #pragma unroll
     for (int g = 0; g < 4; ++g) {
-      if (mg[g] < thr) {
+      if (mg[g] < st.thr) {
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           const float x = v[g * 8 + j];
-          if (x < thr) {
-            const uint2 r = list_insert<KPP>(s_addr, i_addr, x, cbase + g * 8 + j, maxpos);
-            thr_list = __uint_as_float(r.x);
-            maxpos = (int)r.y;
-            thr = fminf(thr_list, thr_g);
+          if (x < st.thr) {
+            if (st.cnt < QCAP) {
+              sts_f32(qs_addr + st.cnt * LIST_SLOT_STRIDE, x);
+              sts_b32(qi_addr + st.cnt * LIST_SLOT_STRIDE, cbase + g * 8 + j);
+              st.cnt += 1;
+            } else {
+              st.n_now += 1;
+              insert_now<KPP>(st, x, cbase + g * 8 + j, s_addr, i_addr);
+            }
           }
         }
       }
@@ -308,6 +359,8 @@ score_topk_kernel(const __grid_constant__ CUtensorMap map_q_main, const __grid_c
   uint8_t* ring = smem + p.ring_off;
   float* list_s = reinterpret_cast<float*>(smem + p.lists_off);   // [KPP slots][128 rows]
   int* list_i = reinterpret_cast<int*>(list_s + KPP * TILE_M);
+  float* queue_s = reinterpret_cast<float*>(list_i + KPP * TILE_M);   // [QCAP slots][128 rows]
+  int* queue_i = reinterpret_cast<int*>(queue_s + QCAP * TILE_M);
   Barriers* bars = reinterpret_cast<Barriers*>(smem + p.bar_off);
 
   const int warp = threadIdx.x >> 5;
@@ -502,10 +555,12 @@ score_topk_kernel(const __grid_constant__ CUtensorMap map_q_main, const __grid_c
     float* my_s = list_s + row;                // [slot][row] layout, slot stride TILE_M
     int* my_i = list_i + row;
     const uint32_t s_addr = smem_u32(my_s), i_addr = smem_u32(my_i);
+    const uint32_t qs_addr = smem_u32(queue_s + row), qi_addr = smem_u32(queue_i + row);
     const int KP = p.kprime;
     const int N = (int)p.N;
     uint32_t acc = 0, acc_phase = 0;
     unsigned long long w_acc = 0, t_begin = DEBUG ? clock64() : 0;
+    int tot_ins = 0, tot_drain = 0, tot_now = 0;
     for (int step = 0; step < sc.n_steps; ++step) {
       int qt, gt0, gt1, slot;
       if (!strip_at(sc, cta, step, qt, gt0, gt1, slot)) continue;
@@ -514,8 +569,11 @@ score_topk_kernel(const __grid_constant__ CUtensorMap map_q_main, const __grid_c
       uint32_t* gthr = (p.shared_thr != nullptr && qrow < p.Q) ? p.shared_thr + qrow : nullptr;
       // cold list: active slots +inf (the list threshold stays +inf until k' scores are in),
       // inactive slots -inf (never the maximum)
-      float thr_list = INFINITY;
-      int maxpos = 0;
+      RowState st;
+      st.thr_list = INFINITY;
+      st.maxpos = 0;
+      st.cnt = 0;
+      st.n_ins = st.n_drain = st.n_now = 0;
 #pragma unroll
       for (int s = 0; s < KPP; ++s) {
         my_s[s * TILE_M] = (s < KP) ? INFINITY : -INFINITY;
@@ -524,13 +582,14 @@ score_topk_kernel(const __grid_constant__ CUtensorMap map_q_main, const __grid_c
       // warm threshold: what other strips of this query have already established.  Any bound
       // published there is >= the query's final k'-th best score, so filtering with the next
       // float above it can only drop rows that are not in the final top-k'.
-      float thr_g = INFINITY, published = INFINITY;
+      st.thr_g = INFINITY;
+      float published = INFINITY;
       uint32_t gk_inflight = 0xffffffffu;      // bound loaded during the previous tile, consumed one tile later
       if (gthr != nullptr) {
         const uint32_t gk = ld_cg_u32(gthr);
-        if (gk < KEY_INF) thr_g = nextafterf(key2f(gk), INFINITY);
+        if (gk < KEY_INF) st.thr_g = nextafterf(key2f(gk), INFINITY);
       }
-      float thr = fminf(thr_list, thr_g);
+      st.thr = fminf(st.thr_list, st.thr_g);
       __syncwarp();
       for (int gt = gt0; gt < gt1; ++gt) {
         timed_wait<DEBUG>(&bars->tmem_full[acc], acc_phase, w_acc, p.wait_mode);
@@ -555,7 +614,7 @@ score_topk_kernel(const __grid_constant__ CUtensorMap map_q_main, const __grid_c
             for (int j = 0; j < 32; ++j)
               if (col0 + cc * 32 + j < N) p.debug_scores[qrow * p.N + col0 + cc * 32 + j] = va[j];
           }
-          process_chunk<KPP>(va, col0 + cc * 32, thr, thr_list, thr_g, maxpos, s_addr, i_addr);
+          process_chunk<KPP>(va, col0 + cc * 32, st, s_addr, i_addr, qs_addr, qi_addr);
           __syncwarp();                                       // tcgen05.ld/wait are warp-collective
           tmem_ld_wait(vb);
           if (cc + 2 < TILE_N / 32) tmem_ld_32x32(taddr + (cc + 2) * 32, va);
@@ -569,27 +628,31 @@ score_topk_kernel(const __grid_constant__ CUtensorMap map_q_main, const __grid_c
             for (int j = 0; j < 32; ++j)
               if (col0 + (cc + 1) * 32 + j < N) p.debug_scores[qrow * p.N + col0 + (cc + 1) * 32 + j] = vb[j];
           }
-          process_chunk<KPP>(vb, col0 + (cc + 1) * 32, thr, thr_list, thr_g, maxpos, s_addr, i_addr);
+          process_chunk<KPP>(vb, col0 + (cc + 1) * 32, st, s_addr, i_addr, qs_addr, qi_addr);
           __syncwarp();
+          // drain early when a queue is half full, so that thresholds do not go stale in the cold phase
+          if (__any_sync(FULL, st.cnt >= QCAP / 2)) drain_queue<KPP>(st, s_addr, i_addr, qs_addr, qi_addr);
         }
         tcgen05_fence_before();
         if (PAIR) mbar_arrive_cluster(&bars->tmem_empty[acc], 0);   // the leader waits for both CTAs' epilogues
         else mbar_arrive(&bars->tmem_empty[acc]);
         if (++acc == NUM_ACC) { acc = 0; acc_phase ^= 1; }
-        // exchange thresholds with the other strips of this query (L2 atomics, off the
-        // critical path: the accumulator has already been released)
+        // the accumulator is released: fold the pending hits in (off the MMA's critical path)
+        drain_queue<KPP>(st, s_addr, i_addr, qs_addr, qi_addr);
+        // exchange thresholds with the other strips of this query (L2 atomics)
         if (gthr != nullptr) {
-          if (thr_list < published) {
-            atomicMin(gthr, f2key(thr_list));
-            published = thr_list;
+          if (st.thr_list < published) {
+            atomicMin(gthr, f2key(st.thr_list));
+            published = st.thr_list;
           }
           // consume the load issued one tile ago (its latency is hidden behind a whole tile),
           // then put the next one in flight
-          if (gk_inflight < KEY_INF) thr_g = fminf(thr_g, nextafterf(key2f(gk_inflight), INFINITY));
-          thr = fminf(thr_list, thr_g);
+          if (gk_inflight < KEY_INF) st.thr_g = fminf(st.thr_g, nextafterf(key2f(gk_inflight), INFINITY));
+          st.thr = fminf(st.thr_list, st.thr_g);
           gk_inflight = ld_cg_u32(gthr);
         }
       }
+      tot_ins += st.n_ins; tot_drain += st.n_drain; tot_now += st.n_now;
       // publish this strip's lists: one coalesced row of k' entries per query
       __syncwarp();
       for (int r = 0; r < 32; ++r) {
@@ -605,6 +668,8 @@ score_topk_kernel(const __grid_constant__ CUtensorMap map_q_main, const __grid_c
     if (DEBUG && p.stats != nullptr && warp == 2 && lane == 0) {
       p.stats[blockIdx.x * 8 + 5] = w_acc;
       p.stats[blockIdx.x * 8 + 6] = (unsigned long long)clock64() - t_begin;
+      p.stats[blockIdx.x * 8 + 7] = ((unsigned long long)tot_ins << 40) | ((unsigned long long)tot_drain << 20) |
+                                    (unsigned long long)tot_now;
     }
   }
 
@@ -723,7 +788,7 @@ extern "C" int hypret_score_plan(int64_t Q, int64_t N, int d, int kprime, int ma
   const int b_blk = pair ? B_BLK_BYTES / 2 : B_BLK_BYTES;
 
   // shared-memory carve-up
-  const int lists = kpp_of(kprime) * TILE_M * 8;
+  const int lists = kpp_of(kprime) * TILE_M * 8 + QCAP * TILE_M * 8;   // candidate lists + pending-hit queues
   const int a_res_bytes = kb * A_BLK_BYTES + A_EXT_BYTES;
   int resident = 0, stages = 0, stage_bytes = 0;
   {
@@ -806,7 +871,7 @@ int hypret_launch_score_topk(const void* q_op, int64_t Q, const void* g_op, int6
   p.stage_bytes = plan.resident ? B_BLK_BYTES / plan.pair : A_BLK_BYTES + B_BLK_BYTES / plan.pair;
   p.ring_off = plan.resident ? p.kb_main * A_BLK_BYTES + A_EXT_BYTES : 0;
   p.lists_off = p.ring_off + plan.stages * p.stage_bytes;
-  p.bar_off = p.lists_off + kpp_of(kprime) * TILE_M * 8;
+  p.bar_off = p.lists_off + kpp_of(kprime) * TILE_M * 8 + QCAP * TILE_M * 8;
   p.sched = sched_from_plan(plan);
   p.cand_score = cand_score;
   p.cand_idx = cand_idx;
@@ -845,8 +910,16 @@ int hypret_launch_score_topk(const void* q_op, int64_t Q, const void* g_op, int6
     cudaMemcpy(h.data(), p.stats, h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
     cudaFree(p.stats);
     double s[8] = {0};
-    for (int c = 0; c < plan.grid; ++c)
-      for (int i = 0; i < 8; ++i) s[i] += (double)h[(size_t)c * 8 + i] / plan.grid;
+    double ins = 0, drains = 0, nows = 0;
+    for (int c = 0; c < plan.grid; ++c) {
+      for (int i = 0; i < 7; ++i) s[i] += (double)h[(size_t)c * 8 + i] / plan.grid;
+      const unsigned long long pk = h[(size_t)c * 8 + 7];
+      ins += (double)(pk >> 40) / plan.grid;
+      drains += (double)((pk >> 20) & 0xfffff) / plan.grid;
+      nows += (double)(pk & 0xfffff) / plan.grid;
+    }
+    fprintf(stderr, "hypret stats: per CTA (warp 2 lane 0): list inserts %.0f, drain passes %.0f, queue-bypass inserts %.0f\n",
+            ins, drains, nows);
     fprintf(stderr,
             "hypret stats (mean cycles per CTA, wait_mode %d): producer wait-empty %.0f of %.0f | mma wait-full %.0f "
             "wait-tmem-empty %.0f of %.0f | epilogue(warp2) wait-tmem-full %.0f of %.0f\n",
