@@ -135,6 +135,17 @@ int hypret_rerank(const float* q32, const float* g32, int64_t Q, int64_t N, int 
 int hypret_merge_topk(const float* scores, const int64_t* idx, int n_shards, int64_t Q, int k, int descending,
                       float* out_score, int64_t* out_idx, void* stream);
 
+/* Fused epilogue of one MobiusLinear layer, applied to mx = x W^T (the GEMM itself is left to the
+ * caller).  Replaces, in one pass over [n,d]:
+ *   hyperbolic_input == 0:  pmath.expmap0(mx)                              src/models.py:309-310
+ *   hyperbolic_input != 0:  the rescale of pmath.mobius_matvec(W, x)       src/models.py:307  (needs xsq = ||x||^2 [n])
+ *   bias != NULL:           pmath.mobius_add(., bias)  (bias on the ball)  src/models.py:314
+ *   n_project (0..2):       pmath.project, repeated                        src/models.py:317, 504
+ *   post_tanh != 0:         pmath.mobius_fn_apply(tanh, .)                 src/models.py:491
+ * y [n,d] fp32 out, sqnorm [n] fp32 out or NULL (||y||^2, the next layer's xsq).  d % 4 == 0, d <= 2048. */
+int hypret_mobius_epilogue(const float* mx, int64_t n, int d, const float* xsq, const float* bias, float c,
+                           int hyperbolic_input, int post_tanh, int n_project, float* y, float* sqnorm, void* stream);
+
 /* Exact pairwise Poincare distance matrix out[i,j] = dist(a_i, p_j), fp32 [n,m].
  * Replaces the Python loops of 1x1 / 1xN pmath.dist calls (src/train.py:1832-1840, 2304-2320,
  * 3259, 1033).  Differences formed explicitly in fp32, transcendental tail in fp64. */

@@ -53,6 +53,8 @@ SIGNATURES = {
                                   c_void_p, c_void_p, c_void_p, c_void_p]),
     "hypret_rerank": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int, c_float, c_int, c_void_p, c_void_p, c_int,
                               c_int, c_int, c_int64, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "hypret_mobius_epilogue": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_void_p, c_float, c_int, c_int, c_int,
+                                       c_void_p, c_void_p, c_void_p]),
     "hypret_pairdist": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int, c_float, c_void_p, c_void_p]),
     "hypret_pairdist_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_float, c_void_p,
                                     c_void_p, c_void_p, c_int, c_void_p]),

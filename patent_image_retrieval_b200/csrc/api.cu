@@ -89,6 +89,18 @@ int hypret_merge_topk(const float* scores, const int64_t* idx, int n_shards, int
                                   static_cast<cudaStream_t>(stream));
 }
 
+int hypret_mobius_epilogue(const float* mx, int64_t n, int d, const float* xsq, const float* bias, float c,
+                           int hyperbolic_input, int post_tanh, int n_project, float* y, float* sqnorm, void* stream) {
+  if (n < 0 || d < 4 || (d & 3) || d > 2048 || !(c > 0.f) || n_project < 0 || n_project > 2) return HYPRET_EINVAL;
+  if (n == 0) return HYPRET_OK;
+  if (mx == nullptr || y == nullptr || !aligned16(mx) || !aligned16(y) || !aligned16(bias)) return HYPRET_EINVAL;
+  if (hyperbolic_input && xsq == nullptr) return HYPRET_EINVAL;
+  int rc = check_device();
+  if (rc != HYPRET_OK) return rc;
+  return hypret_launch_mobius_epilogue(mx, n, d, xsq, bias, c, hyperbolic_input != 0, post_tanh != 0, n_project, y,
+                                       sqnorm, static_cast<cudaStream_t>(stream));
+}
+
 int hypret_pairdist(const float* a, const float* p, int64_t n, int64_t m, int d, float c, float* out, void* stream) {
   if (n < 0 || m < 0 || d < 4 || (d & 3) || !(c > 0.f)) return HYPRET_EINVAL;
   if (n == 0 || m == 0) return HYPRET_OK;

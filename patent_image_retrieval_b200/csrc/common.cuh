@@ -319,3 +319,6 @@ int hypret_launch_ap_full(const float* scores, int64_t Q, int64_t N, const int64
 int hypret_launch_pairdist_bwd(const float* g, const float* dmat, const float* asq, const float* psq, int64_t n,
                                int64_t m, float c, float* w_out, float* row_sum, float* col_partial, int n_partial,
                                cudaStream_t stream);
+int hypret_launch_mobius_epilogue(const float* mx, int64_t n, int d, const float* xsq, const float* bias, float c,
+                                  int hyperbolic_input, int post_tanh, int n_project, float* y, float* sqnorm,
+                                  cudaStream_t stream);

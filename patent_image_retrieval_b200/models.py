@@ -91,8 +91,24 @@ class DeeperHyperbolicEncoder(nn.Module):
         self.first_layer = MobiusLinear(input_dim, hidden_dims[0], hyperbolic_input=False, c=c)
         self.final_layer = MobiusLinear(hidden_dims[0], output_dim, hyperbolic_input=True, c=c)
 
+    def _fused_ok(self, x):
+        return (x.is_cuda and x.dtype == torch.float32 and x.dim() == 2 and not self.training
+                and not (torch.is_grad_enabled() and (x.requires_grad or self.first_layer.weight.requires_grad))
+                and self.first_layer.bias is not None and self.final_layer.bias is not None
+                and self.first_layer.out_features % 4 == 0 and self.final_layer.out_features % 4 == 0)
+
     def forward(self, x):
         self.k = self.k.to(x.device)
+        if self._fused_ok(x):
+            # inference on the GPU: two GEMMs + two fused epilogue kernels (csrc/head.cu) instead of ~75
+            # elementwise launches; same arithmetic order as the op-by-op path below
+            from . import ops
+            c = float(self.c)
+            h, hsq = ops.mobius_epilogue(F.linear(x, self.first_layer.weight.to(x.dtype)), c,
+                                         bias=self.first_layer.bias, post_tanh=True, n_project=1)
+            y, _ = ops.mobius_epilogue(F.linear(h, self.final_layer.weight.to(x.dtype)), c,
+                                       bias=self.final_layer.bias, xsq=hsq, n_project=2, want_sqnorm=False)
+            return y
         x = F.dropout(x, p=self.dropout_rate, training=self.training)
         x = self.first_layer(x)
         x = pmath.mobius_fn_apply(torch.tanh, x, k=self.k)

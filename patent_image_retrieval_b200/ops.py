@@ -238,3 +238,22 @@ def pairdist_bwd(grad_out: torch.Tensor, dmat: torch.Tensor, asq: torch.Tensor, 
 def row_sqnorm(x: torch.Tensor) -> torch.Tensor:
     """||x_i||^2 per row ([n,D] reduction; negligible next to the [n,n] work)."""
     return x.float().pow(2).sum(dim=1)
+
+
+def mobius_epilogue(mx: torch.Tensor, c: float, bias: Optional[torch.Tensor] = None,
+                    xsq: Optional[torch.Tensor] = None, post_tanh: bool = False, n_project: int = 1,
+                    want_sqnorm: bool = True):
+    """Everything a MobiusLinear layer does after its GEMM, in one kernel (inference path).
+    ``xsq`` given -> hyperbolic input (mobius_matvec rescale), else expmap0.  Returns ``(y, ||y||^2 | None)``."""
+    _need_cuda(mx, bias, xsq)
+    mx = mx.contiguous().float()
+    n, d = mx.shape
+    y = torch.empty_like(mx)
+    sq = torch.empty(n, dtype=torch.float32, device=mx.device) if want_sqnorm else None
+    b = bias.detach().contiguous().float() if bias is not None else None
+    xs = xsq.contiguous().float() if xsq is not None else None
+    with torch.cuda.device(mx.device):
+        _lib.check(_lib.load().hypret_mobius_epilogue(_ptr(mx), n, d, _ptr(xs), _ptr(b), float(c), int(xs is not None),
+                                                      int(bool(post_tanh)), int(n_project), _ptr(y), _ptr(sq),
+                                                      _stream()))
+    return y, sq

@@ -210,3 +210,44 @@ def test_sharded_index_single_process_equals_plain_index():
     parts = [ShardedGalleryIndex(v[lo:hi], lo, 3000).search(u, k=10) for lo, hi in ((0, 1500), (1500, 3000))]
     ms, mi = ops.merge_topk(torch.stack([p[0] for p in parts]), torch.stack([p[1] for p in parts]))
     assert torch.equal(mi, a[1]) and torch.equal(ms, a[0])
+
+
+@pytest.mark.parametrize("c", [1.0, 0.5])
+def test_fused_head_matches_reference_models_py(golden, c):
+    """Inference path of the drop-in encoder = 2 GEMMs + 2 fused epilogue kernels; must reproduce the
+    output of the reference's own models.py (refshim golden) and of the op-by-op torch path."""
+    tag = str(c).replace(".", "p")
+    m = models.FigureOnlyHyperbolicModel(32, 16, hidden_dims=[24], c=c, dropout_rate=0.3).eval()
+    m.load_state_dict({k: torch.from_numpy(np.array(golden[f"refshim_head_{k}_c{tag}"])).float()
+                       for k in m.state_dict().keys()})
+    m = m.cuda()
+    x = torch.from_numpy(golden[f"refshim_head_x_c{tag}"]).cuda()
+    with torch.no_grad():
+        assert m.encoder._fused_ok(x)
+        y_fused = m(x)
+    want = torch.from_numpy(golden[f"refshim_head_y_c{tag}"])
+    torch.testing.assert_close(y_fused.cpu(), want, rtol=5e-6, atol=2e-7)
+    y_ops = m(x.clone().requires_grad_(True))               # autograd on -> op-by-op shim path
+    torch.testing.assert_close(y_fused, y_ops.detach(), rtol=5e-6, atol=2e-7)
+
+
+def test_fused_head_large_and_clipped_rows():
+    from oracle import head
+    torch.manual_seed(5)
+    c = 2.0
+    m = models.HyperbolicEmbeddingModel(512, 128, label_num=4, hidden_dims=[256], c=c).eval()
+    with torch.no_grad():
+        m.encoder.first_layer.weight.mul_(6.0)              # push many rows onto the project clip
+    x = torch.randn(1000, 512)
+    x[3] = 0.0
+    sd = m.state_dict()
+    k = torch.tensor([-c])
+    want = head.encoder_forward(x, sd["encoder.first_layer.weight"], sd["encoder.first_layer.bias"],
+                                sd["encoder.final_layer.weight"], sd["encoder.final_layer.bias"], k)
+    m = m.cuda()
+    with torch.no_grad():
+        got = m.encode_figures(x.cuda()).cpu()
+    # GEMM summation order differs between cuBLAS and the CPU oracle; rows near the clip amplify that slightly
+    scale = want.norm(dim=1, keepdim=True).clamp_min(1e-20)
+    assert float(((got - want).abs() / scale).max()) < 2e-5
+    assert float(got.norm(dim=1).max()) <= (1 - 4e-3) / c ** 0.5 * (1 + 1e-6)
