@@ -80,12 +80,17 @@ typedef struct {
   int32_t rem_g0;
   int32_t m, l2;      /* phase 2: m pieces per remaining row, l2 tiles each              */
   int32_t n_steps;    /* strips a CTA walks through at most: n_full + phases             */
+  int32_t sub;        /* wide top-k: full-wave strips are cut into `sub` sub-strips with their own list slots */
+  int32_t sub_tail;   /* ... and phase-1 / phase-2 strips into `sub_tail`                                  */
   int32_t pair;       /* 2: CTA pairs (tcgen05 cta_group::2) -- a scheduling unit is a cluster of 2 CTAs and a
                          strip covers 2 consecutive query tiles; 1: single-CTA MMAs            */
 } hypret_score_plan_t;
 
-/* max_ctas: 0 = one CTA per SM; >0 caps the grid (tests use it to force multi-wave schedules). */
-int hypret_score_plan(int64_t Q, int64_t N, int d, int kprime, int max_ctas, hypret_score_plan_t* plan);
+/* max_ctas: 0 = one CTA per SM; >0 caps the grid (tests use it to force multi-wave schedules).
+ * min_lists: 0/1 = no constraint; >1 = every query gets at least that many independent candidate lists
+ * (used for top-k with k > kprime: the union of the lists must contain the top-k, see hypret_rerank). */
+int hypret_score_plan(int64_t Q, int64_t N, int d, int kprime, int max_ctas, int min_lists,
+                      hypret_score_plan_t* plan);
 
 /* Strip of scheduling unit `cta` (0 <= cta < grid / pair) at step `step` of `plan`:
  * out4 = {first query tile (the strip covers `pair` consecutive tiles), first gallery tile, end gallery
@@ -101,16 +106,16 @@ int hypret_score_strip(const hypret_score_plan_t* plan, int cta, int step, int32
  * surrogate scores.  The [Q,N] matrix is never written to memory.
  *   q_op [Q,kpad] bf16, g_op [N,kpad] bf16   operands from hypret_project_rows
  *   cand_score [Q, n_lists, kprime] fp32 out, cand_idx same shape int32 out (-1 = empty)
- *   n_lists   must equal plan.n_lists of hypret_score_plan(Q, N, d, kprime, max_ctas)
+ *   n_lists   must equal plan.n_lists of hypret_score_plan(Q, N, d, kprime, max_ctas, min_lists)
  *   thr_workspace  [Q] uint32 scratch, or NULL.  When given, the strips of a query exchange
  *             their running k'-th best score through it (L2 atomics), so later / concurrent
  *             strips start warm: the UNION of a query's lists still contains its global
  *             top-kprime, but a single list is no longer the top-kprime of its own strip.
  *             With NULL every list is exactly its strip's top-kprime (slower; tests).
  *   debug_scores  NULL, or [Q,N] fp32 that receives every surrogate score (tests only)
- * 1 <= kprime <= 32. */
+ * 1 <= kprime <= 64. */
 int hypret_score_topk(const void* q_op, int64_t Q, const void* g_op, int64_t N, int d, int kprime, int n_lists,
-                      int max_ctas, float* cand_score, int32_t* cand_idx, uint32_t* thr_workspace,
+                      int max_ctas, int min_lists, float* cand_score, int32_t* cand_idx, uint32_t* thr_workspace,
                       float* debug_scores, void* stream);
 
 /* Candidate merge + exact rerank.  For each query: keep the kprime best of its
@@ -120,8 +125,12 @@ int hypret_score_topk(const void* q_op, int64_t Q, const void* g_op, int64_t N, 
  * (ascending distance / descending similarity, ties -> lower index) and emit the first k.
  *   q32 [Q,d], g32 [N,d] fp32   (hyperbolic: points on the ball; cosine: raw features)
  *   out_score [Q,k] fp32, out_idx [Q,k] int64 (+ idx_offset; -1 when fewer than k rows)
- *   out_margin [Q] fp32 or NULL: (worst kept surrogate) - (exact surrogate of the k-th result)
- * 1 <= k <= kprime <= 32. */
+ *   out_margin [Q] fp32 or NULL: (smallest surrogate a NON-candidate can have) - (exact surrogate of the
+ *              k-th result); > 0 certifies that no gallery row outside the candidate set can beat the result
+ *              up to the bf16 filter error
+ * k <= kprime <= 32: one warp per query.  Wide top-k (kprime <= 64, k <= 128, n_lists*kprime <= 16384,
+ * k <= n_lists*kprime): one CTA per query; requires lists built WITHOUT threshold sharing and
+ * min_lists >= 3 so that the union of a query's lists contains its top-k (certified by out_margin). */
 int hypret_rerank(const float* q32, const float* g32, int64_t Q, int64_t N, int d, float c, int metric,
                   const float* cand_score, const int32_t* cand_idx, int n_lists, int kprime, int k,
                   int64_t idx_offset, float* out_score, int64_t* out_idx, float* out_margin, void* stream);

@@ -33,6 +33,8 @@ class ScorePlan(Structure):
         ("m", c_int32),
         ("l2", c_int32),
         ("n_steps", c_int32),
+        ("sub", c_int32),
+        ("sub_tail", c_int32),
         ("pair", c_int32),
     ]
 
@@ -47,9 +49,9 @@ SIGNATURES = {
     "hypret_operand_kpad": (c_int64, [c_int]),
     "hypret_project_rows": (c_int, [c_void_p, c_int64, c_int, c_float, c_int, c_int, c_void_p, c_void_p, c_void_p,
                                     c_void_p]),
-    "hypret_score_plan": (c_int, [c_int64, c_int64, c_int, c_int, c_int, POINTER(ScorePlan)]),
+    "hypret_score_plan": (c_int, [c_int64, c_int64, c_int, c_int, c_int, c_int, POINTER(ScorePlan)]),
     "hypret_score_strip": (c_int, [POINTER(ScorePlan), c_int, c_int, POINTER(c_int32)]),
-    "hypret_score_topk": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int, c_int, c_int, c_int, c_void_p,
+    "hypret_score_topk": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int, c_int, c_int, c_int, c_int, c_void_p,
                                   c_void_p, c_void_p, c_void_p, c_void_p]),
     "hypret_rerank": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int, c_float, c_int, c_void_p, c_void_p, c_int,
                               c_int, c_int, c_int64, c_void_p, c_void_p, c_void_p, c_void_p]),

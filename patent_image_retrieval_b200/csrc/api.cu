@@ -50,14 +50,14 @@ int hypret_project_rows(const float* u, int64_t n, int d, float c, int mode, int
 }
 
 int hypret_score_topk(const void* q_op, int64_t Q, const void* g_op, int64_t N, int d, int kprime, int n_lists,
-                      int max_ctas, float* cand_score, int32_t* cand_idx, uint32_t* thr_workspace, float* debug_scores,
-                      void* stream) {
+                      int max_ctas, int min_lists, float* cand_score, int32_t* cand_idx, uint32_t* thr_workspace,
+                      float* debug_scores, void* stream) {
   if (Q < 1 || N < 1 || d < 4 || (d & 3) || d > 2048) return HYPRET_EINVAL;
-  if (kprime < 1 || kprime > 32 || n_lists < 1 || max_ctas < 0) return HYPRET_EINVAL;
+  if (kprime < 1 || kprime > 64 || n_lists < 1 || max_ctas < 0 || min_lists < 0) return HYPRET_EINVAL;
   if (q_op == nullptr || g_op == nullptr || cand_score == nullptr || cand_idx == nullptr) return HYPRET_EINVAL;
   int rc = check_device();
   if (rc != HYPRET_OK) return rc;
-  return hypret_launch_score_topk(q_op, Q, g_op, N, d, kprime, n_lists, max_ctas, cand_score, cand_idx,
+  return hypret_launch_score_topk(q_op, Q, g_op, N, d, kprime, n_lists, max_ctas, min_lists, cand_score, cand_idx,
                                   thr_workspace, debug_scores, static_cast<cudaStream_t>(stream));
 }
 
@@ -67,7 +67,8 @@ int hypret_rerank(const float* q32, const float* g32, int64_t Q, int64_t N, int 
   if (Q < 0 || N < 1 || d < 4 || (d & 3)) return HYPRET_EINVAL;
   if (metric != HYPRET_METRIC_COSINE && metric != HYPRET_METRIC_HYPERBOLIC) return HYPRET_EINVAL;
   if (metric == HYPRET_METRIC_HYPERBOLIC && !(c > 0.f)) return HYPRET_EINVAL;
-  if (kprime < 1 || kprime > 32 || k < 1 || k > kprime || n_lists < 1) return HYPRET_EINVAL;
+  if (kprime < 1 || kprime > 64 || k < 1 || k > 128 || n_lists < 1) return HYPRET_EINVAL;
+  if (k > kprime * n_lists || (int64_t)n_lists * kprime > 16384) return HYPRET_EINVAL;
   if (Q == 0) return HYPRET_OK;
   if (q32 == nullptr || g32 == nullptr || cand_score == nullptr || cand_idx == nullptr || out_score == nullptr ||
       out_idx == nullptr || !aligned16(q32) || !aligned16(g32))

@@ -301,8 +301,8 @@ __device__ __forceinline__ double warp_sum(double v) {
 int hypret_launch_project_rows(const float* u, int64_t n, int d, float c, int mode, int side, float* y32,
                                void* op_bf16, float* sqnorm, cudaStream_t stream);
 int hypret_launch_score_topk(const void* q_op, int64_t Q, const void* g_op, int64_t N, int d, int kprime,
-                             int n_lists, int max_ctas, float* cand_score, int32_t* cand_idx, uint32_t* thr_ws,
-                             float* debug_scores, cudaStream_t stream);
+                             int n_lists, int max_ctas, int min_lists, float* cand_score, int32_t* cand_idx,
+                             uint32_t* thr_ws, float* debug_scores, cudaStream_t stream);
 int hypret_launch_rerank(const float* q32, const float* g32, int64_t Q, int64_t N, int d, float c, int metric,
                          const float* cand_score, const int32_t* cand_idx, int n_cand, int kprime, int k,
                          int64_t idx_offset, float* out_score, int64_t* out_idx, float* out_margin,

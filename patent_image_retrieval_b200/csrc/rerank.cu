@@ -180,6 +180,198 @@ rerank_kernel(const float* __restrict__ q32, const float* __restrict__ g32, int6
   }
 }
 
+// ----------------------------------------------------------------------------- wide top-k (k up to 128)
+// One CTA (128 threads) per query.  The candidate lists (n_lists x kprime, built WITHOUT threshold
+// sharing so that each list is exactly its strip's top-kprime) are sorted by surrogate score with a
+// block bitonic network in shared memory; the best 256 survive, are rescored exactly (one warp per
+// 64 survivors, same fp64 arithmetic as above), sorted again by (score, index), and the first k are
+// written.  out_margin = (smallest surrogate a non-candidate can have) - (exact surrogate of the
+// k-th result): a non-candidate is either cut by the 256-survivor truncation or hidden behind a FULL
+// list's worst entry.
+constexpr int RW_THREADS = 128;
+constexpr int RW_SURV = 256;   // survivors rescored exactly: 2x the largest k, the bf16 filter error is comparable
+                               // with the score gap between rank k and rank 1.3k on concentrated data
+
+__device__ __forceinline__ unsigned ordered_key(float x) {   // monotone float -> uint map
+  const unsigned u = __float_as_uint(x);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float ordered_val(unsigned k) {
+  return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
+}
+
+__device__ __forceinline__ bool pair_less(float a, int ia, float b, int ib) {
+  if (ia < 0) return false;
+  if (ib < 0) return true;
+  return (a < b) || (a == b && ia < ib);
+}
+
+template <int NV>
+__global__ void __launch_bounds__(RW_THREADS)
+rerank_wide_kernel(const float* __restrict__ q32, const float* __restrict__ g32, int64_t Q, int64_t N, int d, float c,
+                   int metric, const float* __restrict__ cand_score, const int32_t* __restrict__ cand_idx, int n_lists,
+                   int kprime, int n_pad, int k, int64_t idx_offset, float* __restrict__ out_score,
+                   int64_t* __restrict__ out_idx, float* __restrict__ out_margin) {
+  extern __shared__ uint8_t smem_raw[];
+  float* ks = reinterpret_cast<float*>(smem_raw);            // [n_pad] surrogate scores
+  int* ki = reinterpret_cast<int*>(ks + n_pad);              // [n_pad] gallery ids
+  __shared__ double ekey[RW_SURV];
+  __shared__ double esur[RW_SURV];
+  __shared__ int eidx[RW_SURV];
+  __shared__ unsigned hidden_key;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int64_t q = blockIdx.x;
+  const int n_cand = n_lists * kprime;
+
+  __shared__ int n_valid_s;
+  if (tid == 0) { hidden_key = 0xffffffffu; n_valid_s = 0; }
+  __syncthreads();
+  // a FULL list may hide rows no better than its worst entry
+  for (int l = tid; l < n_lists; l += RW_THREADS) {
+    bool full = true;
+    float worst = -INFINITY;
+    for (int e = 0; e < kprime; ++e) {
+      const int id = cand_idx[q * n_cand + l * kprime + e];
+      full &= id >= 0;
+      if (id >= 0) worst = fmaxf(worst, cand_score[q * n_cand + l * kprime + e]);
+    }
+    if (full) atomicMin(&hidden_key, ordered_key(worst));
+  }
+  // compact the valid candidates to the front (most list slots of a query are empty: slots belong to
+  // strips of other query tiles); the order is fixed by the sort below
+  for (int t = tid; t < n_cand; t += RW_THREADS) {
+    const int id = cand_idx[q * n_cand + t];
+    if (id >= 0) {
+      const int pos = atomicAdd(&n_valid_s, 1);
+      ks[pos] = cand_score[q * n_cand + t];
+      ki[pos] = id;
+    }
+  }
+  __syncthreads();
+  const int n_valid = n_valid_s;
+  int n_sort = RW_SURV;
+  while (n_sort < n_valid) n_sort <<= 1;                 // block-uniform, <= n_pad
+  for (int t = n_valid + tid; t < n_sort; t += RW_THREADS) { ks[t] = INFINITY; ki[t] = -1; }
+  __syncthreads();
+  // ---- block bitonic sort of the candidates by (surrogate, id) -------------------------------------------
+  for (int size = 2; size <= n_sort; size <<= 1) {
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      for (int t = tid; t < (n_sort >> 1); t += RW_THREADS) {
+        const int lo = 2 * t - (t & (stride - 1));
+        const int hi = lo + stride;
+        const bool asc = (lo & size) == 0;
+        const float a = ks[lo], b = ks[hi];
+        const int ia = ki[lo], ib = ki[hi];
+        const bool swap = asc ? pair_less(b, ib, a, ia) : pair_less(a, ia, b, ib);
+        if (swap) { ks[lo] = b; ks[hi] = a; ki[lo] = ib; ki[hi] = ia; }
+      }
+      __syncthreads();
+    }
+  }
+  const int n_surv = RW_SURV;
+  const float cut = (n_sort > RW_SURV && ki[RW_SURV] >= 0) ? ks[RW_SURV] : INFINITY;   // first row cut by truncation
+
+  // ---- exact rescoring: warp w takes survivors [64w, 64w+64) --------------------------------------------------
+  const int nvec = d >> 2;
+  const float4* qrow = reinterpret_cast<const float4*>(q32 + q * d);
+  float4 qv[NV];
+  double xsq = 0.0;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int j = i * 32 + lane;
+    qv[i] = (j < nvec) ? __ldg(qrow + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+    xsq += (double)qv[i].x * qv[i].x + (double)qv[i].y * qv[i].y + (double)qv[i].z * qv[i].z +
+           (double)qv[i].w * qv[i].w;
+  }
+  xsq = warp_sum(xsq);
+  constexpr int PASS = 4;
+  constexpr int PER_WARP = RW_SURV / (RW_THREADS / 32);
+  for (int r0 = warp * PER_WARP; r0 < (warp + 1) * PER_WARP && r0 < n_surv; r0 += PASS) {
+    int idx[PASS];
+    bool val[PASS];
+    const float4* g[PASS];
+#pragma unroll
+    for (int t = 0; t < PASS; ++t) {
+      idx[t] = (r0 + t < n_surv) ? ki[r0 + t] : -1;
+      val[t] = idx[t] >= 0;
+      g[t] = reinterpret_cast<const float4*>(g32 + (int64_t)(val[t] ? idx[t] : 0) * d);
+    }
+    double sacc[PASS], yacc[PASS];
+#pragma unroll
+    for (int t = 0; t < PASS; ++t) { sacc[t] = 0.0; yacc[t] = 0.0; }
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int j = i * 32 + lane;
+      if (j < nvec) {
+        float4 b[PASS];
+#pragma unroll
+        for (int t = 0; t < PASS; ++t) b[t] = __ldg(g[t] + j);
+#pragma unroll
+        for (int t = 0; t < PASS; ++t) {
+          if (metric == HYPRET_METRIC_HYPERBOLIC) {
+            const float e0 = qv[i].x - b[t].x, e1 = qv[i].y - b[t].y, e2 = qv[i].z - b[t].z, e3 = qv[i].w - b[t].w;
+            sacc[t] += (double)e0 * e0 + (double)e1 * e1 + (double)e2 * e2 + (double)e3 * e3;
+          } else {
+            sacc[t] += (double)qv[i].x * b[t].x + (double)qv[i].y * b[t].y + (double)qv[i].z * b[t].z +
+                       (double)qv[i].w * b[t].w;
+          }
+          yacc[t] += (double)b[t].x * b[t].x + (double)b[t].y * b[t].y + (double)b[t].z * b[t].z +
+                     (double)b[t].w * b[t].w;
+        }
+      }
+    }
+#pragma unroll
+    for (int t = 0; t < PASS; ++t) {
+      const double s0 = warp_sum(sacc[t]), y0 = warp_sum(yacc[t]);
+      double key0 = INFINITY, sur0 = INFINITY;
+      if (val[t]) {
+        if (metric == HYPRET_METRIC_HYPERBOLIC) {
+          const double cc = (double)c;
+          const double al = 1.0 - cc * xsq;
+          const double t0 = 2.0 * cc * s0 / (al * (1.0 - cc * y0));
+          key0 = log1p(t0 + sqrt(t0 * (t0 + 2.0))) / sqrt(cc);
+          sur0 = s0 / (1.0 - cc * y0);
+        } else {
+          const double nx = sqrt(xsq);
+          const double d0 = (nx == 0.0 ? 1.0 : nx) * (y0 == 0.0 ? 1.0 : sqrt(y0));
+          key0 = -(s0 / d0);
+          sur0 = key0;
+        }
+      }
+      if (lane == 0 && r0 + t < RW_SURV) { ekey[r0 + t] = key0; esur[r0 + t] = sur0; eidx[r0 + t] = val[t] ? idx[t] : -1; }
+    }
+  }
+  __syncthreads();
+  // ---- sort the exact scores by (key, id): one compare-exchange pair per thread -----------------------------------
+  for (int size = 2; size <= RW_SURV; size <<= 1) {
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      if (tid < RW_SURV / 2) {
+        const int lo = 2 * tid - (tid & (stride - 1));
+        const int hi = lo + stride;
+        const bool asc = (lo & size) == 0;
+        const double a = ekey[lo], b = ekey[hi];
+        const int ia = eidx[lo], ib = eidx[hi];
+        const bool swap = asc ? key_less(b, ib, a, ia) : key_less(a, ia, b, ib);
+        if (swap) {
+          ekey[lo] = b; ekey[hi] = a; eidx[lo] = ib; eidx[hi] = ia;
+          const double sa = esur[lo]; esur[lo] = esur[hi]; esur[hi] = sa;
+        }
+      }
+      __syncthreads();
+    }
+  }
+  if (tid < k) {
+    const bool valid = eidx[tid] >= 0;
+    const double val = (metric == HYPRET_METRIC_HYPERBOLIC) ? ekey[tid] : -ekey[tid];
+    out_score[q * k + tid] = valid ? (float)val : ((metric == HYPRET_METRIC_HYPERBOLIC) ? INFINITY : -INFINITY);
+    out_idx[q * k + tid] = valid ? (int64_t)eidx[tid] + idx_offset : (int64_t)-1;
+  }
+  if (out_margin != nullptr && tid == 0) {
+    const float hb = fminf(hidden_key == 0xffffffffu ? INFINITY : ordered_val(hidden_key), cut);
+    out_margin[q] = (eidx[k - 1] < 0 || hb == INFINITY) ? INFINITY : (float)((double)hb - esur[k - 1]);
+  }
+}
+
 }  // namespace
 
 int hypret_launch_rerank(const float* q32, const float* g32, int64_t Q, int64_t N, int d, float c, int metric,
@@ -187,6 +379,33 @@ int hypret_launch_rerank(const float* q32, const float* g32, int64_t Q, int64_t 
                          int64_t idx_offset, float* out_score, int64_t* out_idx, float* out_margin,
                          cudaStream_t stream) {
   if (Q == 0) return HYPRET_OK;
+  if (kprime > 32 || k > 32 || k > kprime) {
+    const int n_lists = n_cand / kprime;
+    int n_pad = RW_SURV;
+    while (n_pad < n_cand) n_pad <<= 1;
+    const size_t smem_w = (size_t)n_pad * 8;
+    const int need_w = (d + 127) / 128;
+#define HYPRET_RERANK_WIDE(NV)                                                                                      \
+  do {                                                                                                              \
+    if (smem_w > 40 * 1024) {                                                                                       \
+      cudaError_t e = cudaFuncSetAttribute(rerank_wide_kernel<NV>, cudaFuncAttributeMaxDynamicSharedMemorySize,     \
+                                           (int)smem_w);                                                            \
+      if (e != cudaSuccess) return (int)e;                                                                          \
+    }                                                                                                               \
+    rerank_wide_kernel<NV><<<(unsigned)Q, RW_THREADS, smem_w, stream>>>(q32, g32, Q, N, d, c, metric, cand_score,   \
+                                                                       cand_idx, n_lists, kprime, n_pad, k,         \
+                                                                       idx_offset, out_score, out_idx, out_margin); \
+    return (int)cudaGetLastError();                                                                                 \
+  } while (0)
+    if (need_w <= 1) HYPRET_RERANK_WIDE(1);
+    if (need_w <= 2) HYPRET_RERANK_WIDE(2);
+    if (need_w <= 4) HYPRET_RERANK_WIDE(4);
+    if (need_w <= 6) HYPRET_RERANK_WIDE(6);
+    if (need_w <= 8) HYPRET_RERANK_WIDE(8);
+    if (need_w <= 16) HYPRET_RERANK_WIDE(16);
+#undef HYPRET_RERANK_WIDE
+    return HYPRET_EUNSUPPORTED;
+  }
   const size_t smem = (size_t)RR_WARPS * n_cand * 8;
   if (smem > 200 * 1024) return HYPRET_EUNSUPPORTED;
   const int64_t grid = (Q + RR_WARPS - 1) / RR_WARPS;

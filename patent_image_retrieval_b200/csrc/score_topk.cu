@@ -65,9 +65,12 @@ constexpr unsigned FULL = 0xffffffffu;
 struct Sched {
   int T, G, P;
   int n_full, tail_rows, a, b, L1, rem_rows, rem_g0, m, L2, n_steps, n_lists;
+  // wide top-k: base strips are cut into consecutive sub-strips with their own list slots -- `sub` pieces for
+  // full-wave strips (one strip per row otherwise), `sub_tail` pieces for phase-1 / phase-2 strips
+  int sub, sub_tail;
 };
 
-__host__ __device__ inline bool strip_at(const Sched& s, int cta, int step, int& qt, int& g0, int& g1, int& slot) {
+__host__ __device__ inline bool strip_at_base(const Sched& s, int cta, int step, int& qt, int& g0, int& g1, int& slot) {
   if (step < s.n_full) {
     qt = step * s.P + cta;
     g0 = 0;
@@ -107,6 +110,32 @@ __host__ __device__ inline bool strip_at(const Sched& s, int cta, int step, int&
   return false;
 }
 
+__host__ __device__ inline bool strip_at_base(const Sched& s, int cta, int step, int& qt, int& g0, int& g1, int& slot);
+
+// Public schedule = base schedule with every strip cut into s.sub sub-strips.  s.n_steps / s.n_lists
+// are the PUBLIC counts (base counts x sub).
+__host__ __device__ inline bool strip_at(const Sched& s, int cta, int step, int& qt, int& g0, int& g1, int& slot) {
+  if (s.sub <= 1 && s.sub_tail <= 1) return strip_at_base(s, cta, step, qt, g0, g1, slot);
+  int base, j, sub;
+  const int full_steps = s.n_full * s.sub;
+  if (step < full_steps) {
+    sub = s.sub;
+    base = step / sub;
+    j = step - base * sub;
+  } else {
+    sub = s.sub_tail;
+    const int t = step - full_steps;
+    base = s.n_full + t / sub;
+    j = t - (t / sub) * sub;
+  }
+  if (!strip_at_base(s, cta, base, qt, g0, g1, slot)) return false;
+  const int piece = (g1 - g0 + sub - 1) / sub;
+  g0 += j * piece;
+  g1 = g0 + piece < g1 ? g0 + piece : g1;
+  slot = slot * sub + j;
+  return g0 < g1;
+}
+
 Sched make_sched(int64_t T, int64_t G, int sms, int max_ctas) {
   Sched s{};
   int64_t P = sms;
@@ -121,6 +150,8 @@ Sched make_sched(int64_t T, int64_t G, int sms, int max_ctas) {
   s.tail_rows = (int)(T % P);
   s.n_lists = 1;
   s.n_steps = s.n_full;
+  s.sub = 1;
+  s.sub_tail = 1;
   if (s.tail_rows > 0) {
     s.a = s.P / s.tail_rows;
     s.b = s.P % s.tail_rows;
@@ -657,10 +688,12 @@ score_topk_kernel(const __grid_constant__ CUtensorMap map_q_main, const __grid_c
       __syncwarp();
       for (int r = 0; r < 32; ++r) {
         const int64_t qr = (int64_t)qt * TILE_M + quad * 32 + r;
-        if (qr < p.Q && lane < KP) {
-          const int64_t o = (qr * sc.n_lists + slot) * KP + lane;
-          p.cand_score[o] = list_s[lane * TILE_M + quad * 32 + r];
-          p.cand_idx[o] = list_i[lane * TILE_M + quad * 32 + r];
+        if (qr < p.Q) {
+          for (int e = lane; e < KP; e += 32) {
+            const int64_t o = (qr * sc.n_lists + slot) * KP + e;
+            p.cand_score[o] = list_s[e * TILE_M + quad * 32 + r];
+            p.cand_idx[o] = list_i[e * TILE_M + quad * 32 + r];
+          }
         }
       }
       __syncwarp();
@@ -730,10 +763,12 @@ Sched sched_from_plan(const hypret_score_plan_t& pl) {
   s.n_full = pl.n_full; s.tail_rows = pl.tail_rows; s.a = pl.a; s.b = pl.b; s.L1 = pl.l1;
   s.rem_rows = pl.rem_rows; s.rem_g0 = pl.rem_g0; s.m = pl.m; s.L2 = pl.l2; s.n_steps = pl.n_steps;
   s.n_lists = pl.n_lists;
+  s.sub = pl.sub;
+  s.sub_tail = pl.sub_tail;
   return s;
 }
 
-int kpp_of(int kprime) { return kprime <= 16 ? 16 : 32; }
+int kpp_of(int kprime) { return kprime <= 16 ? 16 : (kprime <= 32 ? 32 : 64); }
 
 template <bool RESIDENT, int KPP, bool DEBUG, bool PAIR>
 int launch_one(const hypret_score_plan_t& plan, const CUtensorMap& mq_main, const CUtensorMap& mq_ext,
@@ -770,9 +805,11 @@ int launch_variant(const hypret_score_plan_t& plan, const CUtensorMap& mq_main, 
 
 }  // namespace
 
-extern "C" int hypret_score_plan(int64_t Q, int64_t N, int d, int kprime, int max_ctas,
+extern "C" int hypret_score_plan(int64_t Q, int64_t N, int d, int kprime, int max_ctas, int min_lists,
                                  hypret_score_plan_t* plan) {
-  if (plan == nullptr || Q < 1 || N < 1 || d < 1 || kprime < 1 || kprime > 32 || max_ctas < 0) return HYPRET_EINVAL;
+  if (plan == nullptr || Q < 1 || N < 1 || d < 1 || kprime < 1 || kprime > 64 || max_ctas < 0 || min_lists < 0 ||
+      min_lists > 64)
+    return HYPRET_EINVAL;
   if (N > 0x7fffffffll - TILE_N) return HYPRET_EUNSUPPORTED;   // int32 candidate indices per shard
   const int sms = device_sms();
   const int kb = hypret_dpad(d) / HYPRET_KBLK;
@@ -809,7 +846,19 @@ extern "C" int hypret_score_plan(int64_t Q, int64_t N, int d, int kprime, int ma
     if (stages < 2) return HYPRET_EUNSUPPORTED;
   }
   const int64_t rows = pair ? (n_qtiles + 1) / 2 : n_qtiles;     // scheduling rows: query tiles or tile pairs
-  const Sched s = make_sched(rows, n_gtiles, pair ? ctas / 2 : ctas, 0);
+  Sched s = make_sched(rows, n_gtiles, pair ? ctas / 2 : ctas, 0);
+  {
+    // wide top-k (k > kprime): every query needs at least min_lists independent candidate lists
+    if (min_lists > 1) {
+      const int tail_steps = s.n_steps - s.n_full;          // 0, 1 or 2 base phases after the full waves
+      const int tail_lists = s.tail_rows > 0 ? s.n_lists : 0;
+      s.sub = s.n_full > 0 ? min_lists : 1;
+      s.sub_tail = (s.tail_rows > 0 && s.a < min_lists) ? (min_lists + s.a - 1) / s.a : 1;
+      s.n_steps = s.n_full * s.sub + tail_steps * s.sub_tail;
+      const int full_lists = s.n_full > 0 ? s.sub : 0;
+      s.n_lists = full_lists > tail_lists * s.sub_tail ? full_lists : tail_lists * s.sub_tail;
+    }
+  }
   plan->n_qtiles = (int32_t)n_qtiles;
   plan->n_gtiles = (int32_t)n_gtiles;
   plan->n_lists = s.n_lists;
@@ -828,6 +877,8 @@ extern "C" int hypret_score_plan(int64_t Q, int64_t N, int d, int kprime, int ma
   plan->l2 = s.L2;
   plan->n_steps = s.n_steps;
   plan->pair = pair ? 2 : 1;
+  plan->sub = s.sub;
+  plan->sub_tail = s.sub_tail;
   return HYPRET_OK;
 }
 
@@ -843,10 +894,10 @@ extern "C" int hypret_score_strip(const hypret_score_plan_t* plan, int cta, int 
 }
 
 int hypret_launch_score_topk(const void* q_op, int64_t Q, const void* g_op, int64_t N, int d, int kprime,
-                             int n_lists, int max_ctas, float* cand_score, int32_t* cand_idx, uint32_t* thr_ws,
-                             float* debug_scores, cudaStream_t stream) {
+                             int n_lists, int max_ctas, int min_lists, float* cand_score, int32_t* cand_idx,
+                             uint32_t* thr_ws, float* debug_scores, cudaStream_t stream) {
   hypret_score_plan_t plan;
-  int rc = hypret_score_plan(Q, N, d, kprime, max_ctas, &plan);
+  int rc = hypret_score_plan(Q, N, d, kprime, max_ctas, min_lists, &plan);
   if (rc != HYPRET_OK) return rc;
   if (plan.n_lists != n_lists) return HYPRET_EINVAL;   // caller sized cand_* for a different plan
   if ((reinterpret_cast<uintptr_t>(q_op) & 15) || (reinterpret_cast<uintptr_t>(g_op) & 15)) return HYPRET_EINVAL;
@@ -897,13 +948,15 @@ int hypret_launch_score_topk(const void* q_op, int64_t Q, const void* g_op, int6
     if (e != cudaSuccess) return (int)e;
   }
 
-  const bool k16 = kpp_of(kprime) == 16;
+  const int kpp = kpp_of(kprime);
   if (plan.resident)
-    rc = k16 ? launch_variant<true, 16>(plan, mq_main, mq_ext, mg_main, mg_ext, p, stream)
-             : launch_variant<true, 32>(plan, mq_main, mq_ext, mg_main, mg_ext, p, stream);
+    rc = kpp == 16   ? launch_variant<true, 16>(plan, mq_main, mq_ext, mg_main, mg_ext, p, stream)
+         : kpp == 32 ? launch_variant<true, 32>(plan, mq_main, mq_ext, mg_main, mg_ext, p, stream)
+                     : launch_variant<true, 64>(plan, mq_main, mq_ext, mg_main, mg_ext, p, stream);
   else
-    rc = k16 ? launch_variant<false, 16>(plan, mq_main, mq_ext, mg_main, mg_ext, p, stream)
-             : launch_variant<false, 32>(plan, mq_main, mq_ext, mg_main, mg_ext, p, stream);
+    rc = kpp == 16   ? launch_variant<false, 16>(plan, mq_main, mq_ext, mg_main, mg_ext, p, stream)
+         : kpp == 32 ? launch_variant<false, 32>(plan, mq_main, mq_ext, mg_main, mg_ext, p, stream)
+                     : launch_variant<false, 64>(plan, mq_main, mq_ext, mg_main, mg_ext, p, stream);
   if (p.stats != nullptr) {
     std::vector<unsigned long long> h((size_t)plan.grid * 8);
     cudaStreamSynchronize(stream);

@@ -16,7 +16,8 @@ from . import _lib
 MODE = {"expmap0": 0, "onball": 1, "cosine": 2}
 SIDE = {"query": 0, "gallery": 1}
 METRIC = {"cosine": 0, "hyperbolic": 1}
-MAX_KPRIME = 32
+MAX_KPRIME = 64      # list slots per strip
+MAX_K = 128          # results per query (k > 32 uses the wide rerank kernel)
 
 
 def _ptr(t: Optional[torch.Tensor]):
@@ -57,21 +58,22 @@ def project_rows(u: torch.Tensor, c: float = 1.0, mode: str = "expmap0", side: s
     return y, op, sq
 
 
-def score_plan(Q: int, N: int, d: int, kprime: int, max_ctas: int = 0) -> dict:
+def score_plan(Q: int, N: int, d: int, kprime: int, max_ctas: int = 0, min_lists: int = 0) -> dict:
     """Strip schedule + shared-memory plan of ``score_topk`` (host-only; works without a GPU)."""
-    return _score_plan_struct(Q, N, d, kprime, max_ctas).asdict()
+    return _score_plan_struct(Q, N, d, kprime, max_ctas, min_lists).asdict()
 
 
-def _score_plan_struct(Q, N, d, kprime, max_ctas=0):
+def _score_plan_struct(Q, N, d, kprime, max_ctas=0, min_lists=0):
     plan = _lib.ScorePlan()
-    _lib.check(_lib.load().hypret_score_plan(int(Q), int(N), int(d), int(kprime), int(max_ctas), ctypes.byref(plan)))
+    _lib.check(_lib.load().hypret_score_plan(int(Q), int(N), int(d), int(kprime), int(max_ctas), int(min_lists),
+                                             ctypes.byref(plan)))
     return plan
 
 
-def score_strips(Q: int, N: int, d: int, kprime: int, max_ctas: int = 0):
+def score_strips(Q: int, N: int, d: int, kprime: int, max_ctas: int = 0, min_lists: int = 0):
     """All strips of the schedule as ``(unit, step, first_query_tile, g0, g1, slot)`` tuples (host-only).
     A strip covers ``plan["pair"]`` consecutive query tiles."""
-    plan = _score_plan_struct(Q, N, d, kprime, max_ctas)
+    plan = _score_plan_struct(Q, N, d, kprime, max_ctas, min_lists)
     out = (ctypes.c_int32 * 4)()
     strips = []
     lib = _lib.load()
@@ -87,7 +89,7 @@ def score_strips(Q: int, N: int, d: int, kprime: int, max_ctas: int = 0):
 
 def score_topk(q_op: torch.Tensor, g_op: torch.Tensor, d: int, kprime: int, max_ctas: int = 0,
                debug: bool = False, out: Optional[Tuple[torch.Tensor, torch.Tensor]] = None,
-               share_thresholds: bool = True, thr_workspace: Optional[torch.Tensor] = None):
+               share_thresholds: bool = True, thr_workspace: Optional[torch.Tensor] = None, min_lists: int = 0):
     """tcgen05 scoring GEMM + streaming top-k'.  Returns ``(cand_score [Q,L,k'], cand_idx [Q,L,k'] int32)``
     with L = plan["n_lists"] (+ the full ``[Q,N]`` surrogate matrix when ``debug`` -- tests only).
     ``share_thresholds``: strips of a query exchange their running k'-th best score (fast path);
@@ -100,7 +102,7 @@ def score_topk(q_op: torch.Tensor, g_op: torch.Tensor, d: int, kprime: int, max_
         raise ValueError(f"operands must be contiguous [rows, {kpad}]")
     Q, N = q_op.shape[0], g_op.shape[0]
     with torch.cuda.device(q_op.device):
-        plan = score_plan(Q, N, d, kprime, max_ctas)
+        plan = score_plan(Q, N, d, kprime, max_ctas, min_lists)
         S = plan["n_lists"]
         if out is None:
             cs = torch.empty(Q, S, kprime, dtype=torch.float32, device=q_op.device)
@@ -116,7 +118,8 @@ def score_topk(q_op: torch.Tensor, g_op: torch.Tensor, d: int, kprime: int, max_
             if ws.numel() < Q or ws.element_size() != 4 or not ws.is_cuda:
                 raise ValueError("thr_workspace must be a CUDA tensor of >= Q 32-bit elements")
         _lib.check(_lib.load().hypret_score_topk(_ptr(q_op), Q, _ptr(g_op), N, int(d), int(kprime), S,
-                                                 int(max_ctas), _ptr(cs), _ptr(ci), _ptr(ws), _ptr(dbg), _stream()))
+                                                 int(max_ctas), int(min_lists), _ptr(cs), _ptr(ci), _ptr(ws),
+                                                 _ptr(dbg), _stream()))
     return (cs, ci, dbg) if debug else (cs, ci)
 
 

@@ -20,10 +20,17 @@ import torch
 from . import ops
 
 
+WIDE_MIN_LISTS = 4     # wide top-k: candidate lists per query (4 x 64 = 256 candidates for k <= 128)
+
+
 def default_kprime(k: int) -> int:
-    if k > ops.MAX_KPRIME:
-        raise ValueError(f"k={k} exceeds the supported maximum {ops.MAX_KPRIME}")
-    return min(ops.MAX_KPRIME, max(16, k + 6))
+    """List slots per strip.  k <= 26: one list of k+6 (>= 16) slots suffices (threshold sharing keeps the
+    union equal to the global approximate top-k').  Larger k ("wide", up to 128): 64-slot lists, at least
+    ``WIDE_MIN_LISTS`` independent lists per query, no threshold sharing -- the top-k is in the union unless
+    one strip holds more than 64 of the k best rows, which ``margin`` certifies per query."""
+    if k > ops.MAX_K:
+        raise ValueError(f"k={k} exceeds the supported maximum {ops.MAX_K}")
+    return max(16, k + 6) if k <= 26 else 64
 
 
 class GalleryIndex:
@@ -70,8 +77,8 @@ class GalleryIndex:
         on the launching stream is appended per call (bench.py's roofline measurement)."""
         kprime = default_kprime(k) if kprime is None else int(kprime)
         kprime = min(kprime, ops.MAX_KPRIME)
-        if k > kprime:
-            raise ValueError("k must be <= kprime")
+        wide = k > kprime or k > 32 or kprime > 32
+        min_lists = WIDE_MIN_LISTS if wide else 0
         q = queries.to(device=self.device, dtype=torch.float32, non_blocking=True)
         if q.dim() != 2 or q.shape[1] != self.d:
             raise ValueError(f"queries must be [Q, {self.d}]")
@@ -80,8 +87,10 @@ class GalleryIndex:
         else:
             q32 = q.contiguous()
             _, q_op, _ = ops.project_rows(q, 1.0, mode="cosine", side="query", want_point=False)
-        key = (q.shape[0], kprime, max_ctas)
-        plan = ops.score_plan(q.shape[0], self.n, self.d, kprime, max_ctas)
+        key = (q.shape[0], kprime, max_ctas, min_lists)
+        plan = ops.score_plan(q.shape[0], self.n, self.d, kprime, max_ctas, min_lists)
+        if k > plan["n_lists"] * kprime:
+            raise ValueError("k exceeds the number of candidates the plan can hold")
         buf = self._cand.get(key)
         if buf is None:
             self._cand.clear()
@@ -92,7 +101,8 @@ class GalleryIndex:
         if kernel_events is not None:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-        cs, ci = ops.score_topk(q_op, self.operand, self.d, kprime, max_ctas, out=buf[:2], thr_workspace=buf[2])
+        cs, ci = ops.score_topk(q_op, self.operand, self.d, kprime, max_ctas, out=buf[:2], thr_workspace=buf[2],
+                                share_thresholds=not wide, min_lists=min_lists)
         if kernel_events is not None:
             e1.record()
             kernel_events.append((e0, e1))

@@ -98,6 +98,28 @@ def test_strip_schedule_covers_every_tile_once(Q, N, d, kp, cap):
     assert p["resident"] == 0 or p["stages"] >= 4
 
 
+@pytest.mark.parametrize("Q,N,d,kp,min_lists", [(64, 20000, 768, 64, 4), (2000, 60000, 768, 64, 4),
+                                                 (100000, 1000000, 768, 64, 4), (300, 3000, 128, 64, 3)])
+def test_wide_topk_schedule_gives_every_query_enough_lists(Q, N, d, kp, min_lists):
+    """Wide top-k (k > kprime): every strip is cut into sub-strips so that each query tile owns at least
+    ``min_lists`` disjoint candidate lists which together still cover the gallery exactly once."""
+    from patent_image_retrieval_b200 import ops
+    p = ops.score_plan(Q, N, d, kp, 0, min_lists)
+    pair, G = p["pair"], p["n_gtiles"]
+    by_qt = {}
+    slots = set()
+    for cta, step, qt, g0, g1, slot in ops.score_strips(Q, N, d, kp, 0, min_lists):
+        assert (qt, slot) not in slots and slot < p["n_lists"]
+        slots.add((qt, slot))
+        by_qt.setdefault(qt, []).append((g0, g1))
+    assert len(by_qt) == -(-p["n_qtiles"] // pair)
+    for qt, iv in by_qt.items():
+        iv.sort()
+        assert iv[0][0] == 0 and iv[-1][1] == G and all(a[1] == b[0] for a, b in zip(iv, iv[1:]))
+        assert len(iv) >= min(min_lists, G)
+    assert p["smem_bytes"] <= 232448 and p["stages"] >= 2
+
+
 def test_c2_plan_numbers():
     from patent_image_retrieval_b200 import ops
     p = ops.score_plan(10000, 300000, 512, 16)
@@ -106,7 +128,7 @@ def test_c2_plan_numbers():
     assert p["l1"] == 586 and p["rem_rows"] == 6 and p["m"] == 12 and p["l2"] == 49
     assert p["n_lists"] == 13 and p["resident"] == 1 and p["stages"] == 4
     with pytest.raises(RuntimeError):
-        ops.score_plan(10, 10, 512, 64)          # kprime > 32
+        ops.score_plan(10, 10, 512, 65)          # kprime > 64
 
 
 def test_cpu_tensor_is_rejected():

@@ -107,3 +107,41 @@ def test_small_gallery_pads_with_minus_one():
     dist, idx = index.search(synth.gaussian_features(3, 64, seed=1).cuda(), k=10)
     assert bool((idx[:, 5:] == -1).all()) and bool(torch.isinf(dist[:, 5:]).all())
     assert sorted(idx[0, :5].tolist()) == [0, 1, 2, 3, 4]
+
+
+@pytest.mark.parametrize("metric,d", [("hyperbolic", 768), ("cosine", 768), ("hyperbolic", 128)])
+def test_wide_topk_100_matches_oracle(metric, d):
+    """C3-shaped case (BASELINE.json configs[2]: top-100, cosine and hyperbolic, D=768) at oracle-checkable size."""
+    Q, N, k, c = 150, 20000, 100, 1.0
+    u = synth.gaussian_features(Q, d, seed=1, scale=1.0 if metric == "cosine" else 0.45)
+    v = synth.gaussian_features(N, d, seed=0, scale=1.0 if metric == "cosine" else 0.45)
+    index = GalleryIndex(v.cuda(), c=c, metric=metric)
+    score, idx, margin = index.search(u.cuda(), k=k, return_margin=True)
+    score, idx = score.cpu(), idx.cpu()
+    if metric == "hyperbolic":
+        q32, g32 = head.embed_rows(u, c), head.embed_rows(v, c)
+        truth = retrieval.hyperbolic_dist_rows(q32.double(), g32.double(), c, form="arcosh")
+        tie_rows = _compare_topk(idx, score, truth, k)
+        ref = torch.gather(truth, 1, idx)
+        assert float(((score.double() - ref).abs() / ref).max()) < 2e-6
+    else:
+        full = torch.from_numpy(retrieval.cosine_similarity(u.double().numpy(), v.double().numpy()))
+        tie_rows = _compare_topk(idx, -score, -full, k)
+        assert float((score.double() - torch.gather(full, 1, idx)).abs().max()) < 2e-6
+    assert tie_rows <= 2
+    assert bool((idx.sort(dim=1).values[:, 1:] != idx.sort(dim=1).values[:, :-1]).all())
+    assert bool((margin.cpu() > -1e-3).all())       # certificate: nothing outside the candidate set can matter
+
+
+def test_wide_topk_k33_to_k128_and_short_galleries():
+    index = GalleryIndex(synth.gaussian_features(5000, 256, seed=0).cuda())
+    u = synth.gaussian_features(70, 256, seed=1).cuda()
+    d128, i128 = index.search(u, k=128)
+    for k in (33, 64, 100):
+        dk, ik = index.search(u, k=k)
+        assert torch.equal(ik, i128[:, :k]) and torch.equal(dk, d128[:, :k])
+    d20, i20 = index.search(u, k=20)                     # narrow path (k' = 26, one warp per query) agrees
+    assert torch.equal(i20, i128[:, :20]) and torch.equal(d20, d128[:, :20])
+    small = GalleryIndex(synth.gaussian_features(40, 64, seed=0).cuda())
+    ds, is_ = small.search(synth.gaussian_features(3, 64, seed=1).cuda(), k=100)
+    assert bool((is_[:, 40:] == -1).all()) and sorted(is_[0, :40].tolist()) == list(range(40))
