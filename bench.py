@@ -18,9 +18,15 @@ against a gallery index that is resident in HBM (built once, untimed, like the r
 * ``cpu_baseline``  the oracle (reference torch-fp32 path restated, oracle/) timed on this
              box's host cores on a bounded sample of the same workload (rank 0, N=1 only)
 
-Multi-GPU (torchrun, one rank per GPU): the SAME global workload with the gallery row-sharded
-across ranks ("strong" scaling), queries replicated, [Q,k] candidate lists all-gathered over
-NCCL and merged.  ``--impl reference`` times the CPU oracle alone (rank 0 only).
+Multi-GPU (torchrun, one rank per GPU), gallery row-sharded across the ranks in both modes:
+* ``--scaling weak`` (default): the serving layout.  Every rank is fed its OWN batch of Q queries
+  per step (W*Q queries per step in total, per-GPU work = Q x N pairs whatever W is); batches are
+  all-gathered over NVLink, each rank scores all W*Q queries against its N/W-row shard, and an
+  all_to_all returns the per-shard [Q,k] lists to the query owners, which merge them.
+  ``value`` = W*Q / step time.
+* ``--scaling strong``: the SAME global workload (Q queries, replicated), [Q,k] candidate lists
+  all-gathered and merged on every rank (BASELINE config 4 = ``--workload c4 --scaling strong``).
+``--impl reference`` times the CPU oracle alone (rank 0 only).
 """
 from __future__ import annotations
 
@@ -137,6 +143,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "native" else max(args.warmup, 0)
@@ -149,7 +156,7 @@ def main():
     if args.impl == "reference":
         return run_reference(args, Q, N, D, k, c, desc, world, rank)
 
-    from patent_image_retrieval_b200 import SearchPipeline, ops, synth
+    from patent_image_retrieval_b200 import SearchPipeline, StageEvents, ops, synth
     from patent_image_retrieval_b200.dist import ShardedGalleryIndex, shard_range
     import torch.distributed as dist
 
@@ -163,16 +170,19 @@ def main():
     lo, hi = shard_range(N, rank, world)
     t_build = time.perf_counter()
     g_u = synth.gaussian_features(hi - lo, D, seed=synth.SEED_GALLERY + 1000 * rank, device=dev)
-    index = ShardedGalleryIndex(g_u, row_offset=lo, n_total=N, c=c, metric="hyperbolic", space="euclidean")
+    weak = world > 1 and args.scaling == "weak"
+    index = ShardedGalleryIndex(g_u, row_offset=lo, n_total=N, c=c, metric="hyperbolic", space="euclidean",
+                                queries="sharded" if weak else "replicated")
     torch.cuda.synchronize()
     build_s = time.perf_counter() - t_build
-    q_dev = synth.gaussian_features(Q, D, seed=synth.SEED_QUERY, device=dev)
+    q_dev = synth.gaussian_features(Q, D, seed=synth.SEED_QUERY + (100 * rank if weak else 0), device=dev)
+    q_total = Q * world if weak else Q          # queries the whole job answers per step
     q_host = torch.empty(Q, D, dtype=torch.float32, pin_memory=True)
     q_host.copy_(q_dev)
     out_d_host = torch.empty(Q, k, dtype=torch.float32, pin_memory=True)
     out_i_host = torch.empty(Q, k, dtype=torch.int64, pin_memory=True)
     kprime = 16
-    plan = ops.score_plan(Q, hi - lo, D, kprime)
+    plan = ops.score_plan(q_total if weak else Q, hi - lo, D, kprime)
 
     def barrier():
         if world > 1:
@@ -195,7 +205,7 @@ def main():
     sampler = ClockSampler(local_rank) if rank == 0 else None
 
     # ---- timed: device-resident ------------------------------------------------------------------
-    kernel_events = []
+    kernel_events = StageEvents()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record()
@@ -204,7 +214,7 @@ def main():
     e1.record()
     barrier()
     ms_resident = e0.elapsed_time(e1) / args.steps
-    score_ms = statistics.mean(a.elapsed_time(b) for a, b in kernel_events)
+    score_ms, project_ms, rerank_ms = (kernel_events.ms(n_) for n_ in ("score", "project", "rerank"))
 
     # ---- timed: end to end with host buffers, no overlap ----------------------------------------------
     for _ in range(2):
@@ -241,9 +251,10 @@ def main():
     clocks = sampler.stop() if sampler is not None else None
 
     if world > 1:
-        t = torch.tensor([ms_resident, ms_e2e, score_ms, ms_e2e_serial], device=dev, dtype=torch.float64)
+        t = torch.tensor([ms_resident, ms_e2e, score_ms, ms_e2e_serial, project_ms, rerank_ms], device=dev,
+                         dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_resident, ms_e2e, score_ms, ms_e2e_serial = (float(x) for x in t.tolist())
+        ms_resident, ms_e2e, score_ms, ms_e2e_serial, project_ms, rerank_ms = (float(x) for x in t.tolist())
 
     # ---- size-independent result properties at full size ----------------------------------------------
     dd, ii = step_resident()
@@ -251,6 +262,15 @@ def main():
     props_ok = bool((dd[:, 1:] >= dd[:, :-1]).all()) and bool((ii >= 0).all()) and bool((ii < N).all())
     props_ok &= bool((ii.sort(dim=1).values[:, 1:] != ii.sort(dim=1).values[:, :-1]).all())   # no duplicates
     props_ok &= bool(torch.equal(out_i_host.to(dev), ii)) and e2e_ok                          # e2e == resident
+    if weak:
+        # the two exchange patterns must agree: rank 0's batch through the replicated path
+        # (shard-local search -> all_gather -> merge on every rank) == its result through the sharded path
+        q0 = q_dev.clone()
+        dist.broadcast(q0, src=0)
+        dd2, ii2 = index.search_replicated(q0, k=k, kprime=kprime)
+        torch.cuda.synchronize()
+        if rank == 0:
+            props_ok &= bool(torch.equal(ii2, ii)) and bool(torch.equal(dd2, dd))
 
     if rank != 0:
         if world > 1:
@@ -260,7 +280,12 @@ def main():
 
     peaks = load_peaks()
     n_local = hi - lo
-    flops = 2.0 * Q * n_local * D
+    q_scored = q_total if weak else Q           # query rows one rank's scoring kernel sees per step
+    flops = 2.0 * q_scored * n_local * D
+    kpad = ops.operand_kpad(D)
+    project_bytes = q_scored * (4 * D + 4 * D + 2 * kpad)          # read f32 row, write f32 point + bf16 operand row
+    rerank_bytes = q_scored * kprime * D * 4                       # exact rescoring: k' gathered fp32 rows per query
+    n_coll = 0 if world == 1 else (4 if weak else 3)               # NCCL kernels + merge per step
     achieved = flops / (score_ms * 1e-3) / 1e12
     traffic = None
     tp = ROOT / "profiles" / "score_topk_traffic.json"
@@ -270,24 +295,41 @@ def main():
         except Exception:
             traffic = None
     line = {
-        "metric": METRIC, "value": Q / (ms_resident * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": ms_resident, "higher_is_better": True, "scaling": "strong",
+        "metric": METRIC, "value": q_total / (ms_resident * 1e-3), "unit": UNIT, "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_resident, "higher_is_better": True,
+        "scaling": "weak" if (weak or world == 1) else "strong",
         "vs_baseline": None, "dtype": "bf16 tensor-core filter + fp32/fp64 exact rerank", "data": "synthetic",
         "config": {"workload": desc, "Q": Q, "N": N, "D": D, "k": k, "c": c, "kprime": kprime,
-                   "gallery_rows_per_gpu": n_local, "parallelism": f"gallery row-shard x{world}",
+                   "queries_per_step_total": q_total, "gallery_rows_per_gpu": n_local,
+                   "parallelism": (f"gallery row-shard x{world}; " +
+                                   ("each rank fed its own Q-query batch per step: all_gather(queries) -> shard-local "
+                                    "search of all W*Q -> all_to_all([Q,k] lists) -> merge at the owner" if weak else
+                                    "queries replicated: shard-local search -> all_gather([Q,k] lists) -> merge"))
+                   if world > 1 else "single GPU",
                    "cache": "inputs larger than L2 (bf16 gallery operand %.0f MB vs 126 MB L2); no flush" %
                             (n_local * ops.operand_kpad(D) * 2 / 1e6),
                    "plan": {kk: plan[kk] for kk in ("grid", "n_lists", "stages", "resident", "l1", "l2")},
                    "index_build_s": round(build_s, 3)},
-        "e2e": {"value": Q / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e, "h2d_bytes_per_step": Q * D * 4,
-                "d2h_bytes_per_step": Q * k * 12,
+        "e2e": {"value": q_total / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e,
+                "h2d_bytes_per_step": Q * D * 4, "d2h_bytes_per_step": Q * k * 12, "bytes_are": "per rank",
                 "mode": "SearchPipeline: per-step H2D + search + D2H, copies of neighbouring steps overlapped",
-                "serial": {"value": Q / (ms_e2e_serial * 1e-3), "ms_per_step": ms_e2e_serial}},
+                "serial": {"value": q_total / (ms_e2e_serial * 1e-3), "ms_per_step": ms_e2e_serial}},
         "gpu_launches": args.steps * (3 + (1 if world > 1 else 0)),
+        "gpu_launches_note": "own kernels per step per rank: project_rows, score_topk, rerank" +
+                             (", merge_topk (+ %d NCCL kernels)" % (n_coll - 1) if world > 1 else ""),
         "roofline": {"bound": "tensor", "achieved": achieved, "peak": peaks["tflops_sustained"], "unit": "TFLOP/s",
                      "frac": achieved / peaks["tflops_sustained"], "traffic": traffic,
                      "kernel": "score_topk_kernel", "kernel_ms": score_ms, "algorithmic_flops": flops,
                      "peak_source": peaks["source"] + ", sustained figure (kernel timed inside a long step)"},
+        "roofline_hbm": [
+            {"kernel": "project_rows_kernel", "bound": "hbm", "kernel_ms": project_ms, "algorithmic_bytes": project_bytes,
+             "achieved": project_bytes / (project_ms * 1e-3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+             "frac": project_bytes / (project_ms * 1e-3) / 1e9 / peaks["hbm_gbs"],
+             "note": "query side only (%d rows): launch-latency sized at this Q" % q_scored},
+            {"kernel": "rerank_kernel", "bound": "hbm", "kernel_ms": rerank_ms, "algorithmic_bytes": rerank_bytes,
+             "achieved": rerank_bytes / (rerank_ms * 1e-3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+             "frac": rerank_bytes / (rerank_ms * 1e-3) / 1e9 / peaks["hbm_gbs"],
+             "note": "gather of k' random fp32 gallery rows per query"}],
         "clocks": clocks,
         "result_properties_ok": props_ok,
     }

@@ -135,6 +135,25 @@ int hypret_rerank(const float* q32, const float* g32, int64_t Q, int64_t N, int 
                   const float* cand_score, const int32_t* cand_idx, int n_lists, int kprime, int k,
                   int64_t idx_offset, float* out_score, int64_t* out_idx, float* out_margin, void* stream);
 
+/* Multi-GPU pruning (sharded serving; the reference has no distributed path).  A query's exact
+ * rescoring needs only its GLOBAL approximate top-kprime, of which a shard holds kprime / n_shards on average:
+ *   hypret_cand_select    the kprime best candidates of each query by surrogate score, ascending (surrogate,
+ *                         index), padded with (+inf, -1): sel_score [Q,kprime] fp32, sel_idx [Q,kprime] int32.
+ *                         Surrogates of different shards are comparable (same query operand, same formula).
+ *   hypret_kth_smallest   out[q] = kth smallest (1-based) of the n_parts*m values vals[n_parts, Q, m] (after the
+ *                         owner of a query has received every shard's sel_score); +inf if fewer exist.
+ *   hypret_rerank_pruned  hypret_rerank that skips every candidate whose surrogate exceeds prune_thr[q]
+ *                         (the global kprime-th best): results of the shards then merge to exactly the list a
+ *                         single-GPU hypret_rerank over the whole gallery returns (ties at the threshold kept).
+ *                         k <= kprime <= 32 only. */
+int hypret_cand_select(const float* cand_score, const int32_t* cand_idx, int64_t Q, int n_lists, int kprime,
+                       float* sel_score, int32_t* sel_idx, void* stream);
+int hypret_kth_smallest(const float* vals, int n_parts, int64_t Q, int m, int kth, float* out, void* stream);
+int hypret_rerank_pruned(const float* q32, const float* g32, int64_t Q, int64_t N, int d, float c, int metric,
+                         const float* cand_score, const int32_t* cand_idx, int n_lists, int kprime, int k,
+                         int64_t idx_offset, const float* prune_thr, float* out_score, int64_t* out_idx,
+                         void* stream);
+
 /* Multi-GPU exchange step: merge the per-shard top-k lists of every query (after an
  * all-gather of [Q,k] scores + global indices) into the global top-k, with the ordering of the
  * reference's single-device ranking (notebooks/retrieval.ipynb:383, src/auxiliary.py:374):

@@ -8,6 +8,6 @@ recall@k / mAP, as hand-written sm_100a CUDA (tcgen05 / TMEM / TMA) behind a C A
 package: a hyphen is not importable.)
 """
 from . import ops, synth  # noqa: F401
-from .retrieval import GalleryIndex, SearchPipeline, default_kprime  # noqa: F401
+from .retrieval import GalleryIndex, SearchPipeline, StageEvents, default_kprime  # noqa: F401
 
-__all__ = ["ops", "synth", "GalleryIndex", "SearchPipeline", "default_kprime"]
+__all__ = ["ops", "synth", "GalleryIndex", "SearchPipeline", "StageEvents", "default_kprime"]

@@ -55,6 +55,10 @@ SIGNATURES = {
                                   c_void_p, c_void_p, c_void_p, c_void_p]),
     "hypret_rerank": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int, c_float, c_int, c_void_p, c_void_p, c_int,
                               c_int, c_int, c_int64, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "hypret_rerank_pruned": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int, c_float, c_int, c_void_p, c_void_p,
+                                     c_int, c_int, c_int, c_int64, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "hypret_cand_select": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    "hypret_kth_smallest": (c_int, [c_void_p, c_int, c_int64, c_int, c_int, c_void_p, c_void_p]),
     "hypret_mobius_epilogue": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_void_p, c_float, c_int, c_int, c_int,
                                        c_void_p, c_void_p, c_void_p]),
     "hypret_pairdist": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int, c_float, c_void_p, c_void_p]),

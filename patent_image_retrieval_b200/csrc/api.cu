@@ -61,9 +61,10 @@ int hypret_score_topk(const void* q_op, int64_t Q, const void* g_op, int64_t N, 
                                   thr_workspace, debug_scores, static_cast<cudaStream_t>(stream));
 }
 
-int hypret_rerank(const float* q32, const float* g32, int64_t Q, int64_t N, int d, float c, int metric,
-                  const float* cand_score, const int32_t* cand_idx, int n_lists, int kprime, int k,
-                  int64_t idx_offset, float* out_score, int64_t* out_idx, float* out_margin, void* stream) {
+static int rerank_common(const float* q32, const float* g32, int64_t Q, int64_t N, int d, float c, int metric,
+                         const float* cand_score, const int32_t* cand_idx, int n_lists, int kprime, int k,
+                         int64_t idx_offset, const float* prune_thr, float* out_score, int64_t* out_idx,
+                         float* out_margin, void* stream) {
   if (Q < 0 || N < 1 || d < 4 || (d & 3)) return HYPRET_EINVAL;
   if (metric != HYPRET_METRIC_COSINE && metric != HYPRET_METRIC_HYPERBOLIC) return HYPRET_EINVAL;
   if (metric == HYPRET_METRIC_HYPERBOLIC && !(c > 0.f)) return HYPRET_EINVAL;
@@ -76,7 +77,44 @@ int hypret_rerank(const float* q32, const float* g32, int64_t Q, int64_t N, int 
   int rc = check_device();
   if (rc != HYPRET_OK) return rc;
   return hypret_launch_rerank(q32, g32, Q, N, d, c, metric, cand_score, cand_idx, n_lists * kprime, kprime, k,
-                              idx_offset, out_score, out_idx, out_margin, static_cast<cudaStream_t>(stream));
+                              idx_offset, prune_thr, out_score, out_idx, out_margin,
+                              static_cast<cudaStream_t>(stream));
+}
+
+int hypret_rerank(const float* q32, const float* g32, int64_t Q, int64_t N, int d, float c, int metric,
+                  const float* cand_score, const int32_t* cand_idx, int n_lists, int kprime, int k,
+                  int64_t idx_offset, float* out_score, int64_t* out_idx, float* out_margin, void* stream) {
+  return rerank_common(q32, g32, Q, N, d, c, metric, cand_score, cand_idx, n_lists, kprime, k, idx_offset, nullptr,
+                       out_score, out_idx, out_margin, stream);
+}
+
+int hypret_rerank_pruned(const float* q32, const float* g32, int64_t Q, int64_t N, int d, float c, int metric,
+                         const float* cand_score, const int32_t* cand_idx, int n_lists, int kprime, int k,
+                         int64_t idx_offset, const float* prune_thr, float* out_score, int64_t* out_idx,
+                         void* stream) {
+  if (prune_thr == nullptr || kprime > 32 || k > 32 || k > kprime) return HYPRET_EINVAL;
+  return rerank_common(q32, g32, Q, N, d, c, metric, cand_score, cand_idx, n_lists, kprime, k, idx_offset, prune_thr,
+                       out_score, out_idx, nullptr, stream);
+}
+
+int hypret_cand_select(const float* cand_score, const int32_t* cand_idx, int64_t Q, int n_lists, int kprime,
+                       float* sel_score, int32_t* sel_idx, void* stream) {
+  if (Q < 0 || n_lists < 1 || kprime < 1 || kprime > 32 || (int64_t)n_lists * kprime > 16384) return HYPRET_EINVAL;
+  if (Q == 0) return HYPRET_OK;
+  if (cand_score == nullptr || cand_idx == nullptr || sel_score == nullptr || sel_idx == nullptr) return HYPRET_EINVAL;
+  int rc = check_device();
+  if (rc != HYPRET_OK) return rc;
+  return hypret_launch_cand_select(cand_score, cand_idx, Q, n_lists * kprime, kprime, sel_score, sel_idx,
+                                   static_cast<cudaStream_t>(stream));
+}
+
+int hypret_kth_smallest(const float* vals, int n_parts, int64_t Q, int m, int kth, float* out, void* stream) {
+  if (n_parts < 1 || Q < 0 || m < 1 || kth < 1 || (int64_t)n_parts * m > 2048) return HYPRET_EINVAL;
+  if (Q == 0) return HYPRET_OK;
+  if (vals == nullptr || out == nullptr) return HYPRET_EINVAL;
+  int rc = check_device();
+  if (rc != HYPRET_OK) return rc;
+  return hypret_launch_kth_smallest(vals, n_parts, Q, m, kth, out, static_cast<cudaStream_t>(stream));
 }
 
 int hypret_merge_topk(const float* scores, const int64_t* idx, int n_shards, int64_t Q, int k, int descending,

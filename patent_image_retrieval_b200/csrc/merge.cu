@@ -69,7 +69,47 @@ merge_topk_kernel(const float* __restrict__ scores, const int64_t* __restrict__ 
   }
 }
 
+// out[q] = the kth smallest (1-based) of the n_parts * m values of query q, vals [n_parts, Q, m]; +inf when
+// fewer than kth finite values exist.  Rank counting in shared memory, one warp per query (n <= 2048).
+__global__ void __launch_bounds__(MG_WARPS * 32)
+kth_smallest_kernel(const float* __restrict__ vals, int n_parts, int64_t Q, int m, int kth, float* __restrict__ out) {
+  extern __shared__ float sm_vals[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t q = (int64_t)blockIdx.x * MG_WARPS + warp;
+  if (q >= Q) return;
+  const int n = n_parts * m;
+  float* v = sm_vals + (size_t)warp * n;
+  for (int t = lane; t < n; t += 32) {
+    const int w = t / m, j = t - w * m;
+    const float x = vals[((int64_t)w * Q + q) * m + j];
+    v[t] = (x == x) ? x : INFINITY;            // NaN counts as +inf
+  }
+  __syncwarp();
+  if (kth > n) {
+    if (lane == 0) out[q] = INFINITY;
+    return;
+  }
+  for (int t = lane; t < n; t += 32) {
+    const float x = v[t];
+    int rank = 0;
+    for (int u = 0; u < n; ++u) {
+      const float y = v[u];
+      rank += (y < x) || (y == x && u < t);
+    }
+    if (rank == kth - 1) out[q] = x;           // exactly one t has this rank
+  }
+}
+
 }  // namespace
+
+int hypret_launch_kth_smallest(const float* vals, int n_parts, int64_t Q, int m, int kth, float* out,
+                               cudaStream_t stream) {
+  if (Q == 0) return HYPRET_OK;
+  const size_t smem = (size_t)MG_WARPS * n_parts * m * sizeof(float);
+  kth_smallest_kernel<<<(unsigned)((Q + MG_WARPS - 1) / MG_WARPS), MG_WARPS * 32, smem, stream>>>(vals, n_parts, Q, m,
+                                                                                                 kth, out);
+  return (int)cudaGetLastError();
+}
 
 int hypret_launch_merge_topk(const float* scores, const int64_t* idx, int W, int64_t Q, int k, int descending,
                              float* out_score, int64_t* out_idx, cudaStream_t stream) {

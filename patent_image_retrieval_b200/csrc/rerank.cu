@@ -27,12 +27,61 @@ __device__ __forceinline__ bool key_less(double a, int ia, double b, int ib) {
   return (a < b) || (a == b && ia < ib);
 }
 
+__device__ __forceinline__ unsigned ordered_key(float x) {   // monotone float -> uint map
+  const unsigned u = __float_as_uint(x);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float ordered_val(unsigned k) {
+  return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
+}
+
+// Approximate merge of one query's candidate lists (warp-cooperative): selects, in ascending (surrogate, index)
+// order, up to `kprime` valid candidates from cs/ci[0..n_cand) (shared memory, consumed: selected slots get
+// index -1), stopping early at the first candidate whose surrogate exceeds `prune`.  Lane r returns the r-th
+// selected candidate (index -1 beyond the count); *worst = surrogate of the last one selected.
+// Each lane caches the best of its own slots (t = lane, lane+32, ...); a round is two hardware warp
+// reductions (redux.sync.min on the ordered key, then on the index among the lanes that tie) and a rescan of
+// the winning lane's slots only.
+__device__ __forceinline__ int select_candidates(float* cs, int* ci, int n_cand, int kprime, float prune, int lane,
+                                                 float* my_score, float* worst) {
+  unsigned bk = 0xffffffffu;   // ordered key of this lane's best slot (0xffffffff: none)
+  int bi = 0x7fffffff, bpos = -1;
+  for (int t = lane; t < n_cand; t += 32) {
+    const int i = ci[t];
+    const unsigned kk = ordered_key(cs[t]);
+    if (i >= 0 && (bpos < 0 || kk < bk || (kk == bk && i < bi))) { bk = kk; bi = i; bpos = t; }
+  }
+  if (bpos < 0) bk = 0xffffffffu;
+  int my_idx = -1;
+  *my_score = INFINITY;
+  *worst = -INFINITY;
+  for (int r = 0; r < kprime; ++r) {
+    const unsigned mk = __reduce_min_sync(0xffffffffu, bpos >= 0 ? bk : 0xffffffffu);
+    const unsigned mi = __reduce_min_sync(0xffffffffu, (bpos >= 0 && bk == mk) ? (unsigned)bi : 0xffffffffu);
+    if (mi == 0xffffffffu) break;                       // no valid candidate left (warp-uniform)
+    const float ms = ordered_val(mk);
+    if (ms > prune) break;                              // everything left is worse than the global k'-th best
+    if (lane == r) { my_idx = (int)mi; *my_score = ms; }
+    *worst = ms;
+    if (bpos >= 0 && bk == mk && bi == (int)mi) {       // the winning lane retires the slot and rescans its own
+      ci[bpos] = -1;
+      bk = 0xffffffffu; bi = 0x7fffffff; bpos = -1;
+      for (int t = lane; t < n_cand; t += 32) {
+        const int i = ci[t];
+        const unsigned kk = ordered_key(cs[t]);
+        if (i >= 0 && (bpos < 0 || kk < bk || (kk == bk && i < bi))) { bk = kk; bi = i; bpos = t; }
+      }
+    }
+  }
+  return my_idx;
+}
+
 template <int NV>   // float4 chunks of a row per lane: D <= NV * 128
-__global__ void __launch_bounds__(RR_WARPS * 32)
+__global__ void __launch_bounds__(RR_WARPS * 32, NV <= 4 ? 4 : 1)
 rerank_kernel(const float* __restrict__ q32, const float* __restrict__ g32, int64_t Q, int64_t N, int d, float c,
               int metric, const float* __restrict__ cand_score, const int32_t* __restrict__ cand_idx, int n_cand,
-              int kprime, int k, int64_t idx_offset, float* __restrict__ out_score, int64_t* __restrict__ out_idx,
-              float* __restrict__ out_margin) {
+              int kprime, int k, int64_t idx_offset, const float* __restrict__ prune_thr,
+              float* __restrict__ out_score, int64_t* __restrict__ out_idx, float* __restrict__ out_margin) {
   extern __shared__ uint8_t smem_raw[];
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -42,110 +91,104 @@ rerank_kernel(const float* __restrict__ q32, const float* __restrict__ g32, int6
   int* ci = reinterpret_cast<int*>(reinterpret_cast<float*>(smem_raw) + (size_t)RR_WARPS * n_cand) +
             (size_t)warp * n_cand;
 
-  // ---- 1. approximate merge: k' rounds of warp arg-min over the candidates ---------------
+  // the query row is requested first so that its latency hides behind the candidate merge
+  const int nvec = d >> 2;
+  const float4* qrow = reinterpret_cast<const float4*>(q32 + q * d);
+  float4 qv[NV];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int j = i * 32 + lane;
+    qv[i] = (j < nvec) ? __ldg(qrow + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+
+  // ---- 1. approximate merge: the k' best candidates by surrogate score --------------------
   for (int t = lane; t < n_cand; t += 32) {
     cs[t] = cand_score[q * n_cand + t];
     ci[t] = cand_idx[q * n_cand + t];
   }
   __syncwarp();
-  int my_idx = -1;          // lane r holds the r-th selected candidate
-  float worst_approx = -INFINITY;
-  for (int r = 0; r < kprime; ++r) {
-    float bs = INFINITY;
-    int bi = 0x7fffffff, bpos = -1;
-    for (int t = lane; t < n_cand; t += 32) {
-      const float s = cs[t];
-      const int i = ci[t];
-      if (i >= 0 && (s < bs || (s == bs && i < bi))) { bs = s; bi = i; bpos = t; }
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      const float os = __shfl_xor_sync(0xffffffffu, bs, o);
-      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-      const int op = __shfl_xor_sync(0xffffffffu, bpos, o);
-      if (op >= 0 && (bpos < 0 || os < bs || (os == bs && oi < bi))) { bs = os; bi = oi; bpos = op; }
-    }
-    if (bpos < 0) break;      // fewer than k' valid candidates (warp-uniform)
-    if (lane == r) my_idx = bi;
-    worst_approx = bs;
-    if ((bpos & 31) == lane) ci[bpos] = -1;
-    __syncwarp();
-  }
+  float my_approx, worst_approx;
+  int my_idx = select_candidates(cs, ci, n_cand, kprime, prune_thr != nullptr ? prune_thr[q] : INFINITY, lane,
+                                 &my_approx, &worst_approx);
+  const int n_sel = __popc(__ballot_sync(0xffffffffu, my_idx >= 0));
 
   // ---- 2. exact scores of the survivors ---------------------------------------------------
-  // the query row stays in registers; four gallery rows are streamed per pass (independent
-  // 128-bit loads in flight), fp64 accumulation of explicitly formed differences
-  const int nvec = d >> 2;
-  const float4* qrow = reinterpret_cast<const float4*>(q32 + q * d);
-  float4 qv[NV];
+  // four gallery rows per pass, all their 128-bit loads issued before the first use (memory-level
+  // parallelism: the kernel is a latency-bound gather otherwise); fp64 accumulation of explicitly
+  // formed differences; lane r keeps the sums of survivor r and evaluates its own distance afterwards
   double xsq = 0.0;
 #pragma unroll
-  for (int i = 0; i < NV; ++i) {
-    const int j = i * 32 + lane;
-    qv[i] = (j < nvec) ? __ldg(qrow + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int i = 0; i < NV; ++i)
     xsq += (double)qv[i].x * qv[i].x + (double)qv[i].y * qv[i].y + (double)qv[i].z * qv[i].z +
            (double)qv[i].w * qv[i].w;
-  }
   xsq = warp_sum(xsq);
 
-  double my_key = INFINITY;     // sort key (distance, or minus similarity)
-  double my_sur = INFINITY;     // exact surrogate, comparable with the approximate scores
+  double my_s = 0.0, my_y = 0.0;
   constexpr int PASS = 4;
-  for (int r0 = 0; r0 < kprime; r0 += PASS) {
-    int idx[PASS];
-    bool val[PASS];
+  constexpr int CH = NV < 4 ? NV : 4;            // float4 chunks per lane and row in flight at once
+  for (int r0 = 0; r0 < n_sel; r0 += PASS) {
     const float4* g[PASS];
-    bool any = false;
+    bool val[PASS];
 #pragma unroll
     for (int t = 0; t < PASS; ++t) {
-      idx[t] = __shfl_sync(0xffffffffu, my_idx, (r0 + t) & 31);
-      val[t] = (r0 + t < kprime) && idx[t] >= 0;
-      any |= val[t];
-      g[t] = reinterpret_cast<const float4*>(g32 + (int64_t)(val[t] ? idx[t] : 0) * d);
+      const int id = __shfl_sync(0xffffffffu, my_idx, (r0 + t) & 31);
+      val[t] = (r0 + t < n_sel);
+      g[t] = reinterpret_cast<const float4*>(g32 + (int64_t)(val[t] ? id : 0) * d);
     }
-    if (!any) continue;
     double sacc[PASS], yacc[PASS];
 #pragma unroll
     for (int t = 0; t < PASS; ++t) { sacc[t] = 0.0; yacc[t] = 0.0; }
 #pragma unroll
-    for (int i = 0; i < NV; ++i) {
-      const int j = i * 32 + lane;
-      if (j < nvec) {
-        float4 b[PASS];
+    for (int i0 = 0; i0 < NV; i0 += CH) {
+      float4 b[PASS][CH];
 #pragma unroll
-        for (int t = 0; t < PASS; ++t) b[t] = __ldg(g[t] + j);
+      for (int t = 0; t < PASS; ++t)
+#pragma unroll
+        for (int ii = 0; ii < CH; ++ii) {
+          const int j = (i0 + ii) * 32 + lane;
+          b[t][ii] = (val[t] && j < nvec) ? __ldg(g[t] + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+      for (int ii = 0; ii < CH; ++ii) {
+        const int i = i0 + ii;
 #pragma unroll
         for (int t = 0; t < PASS; ++t) {
+          const float4 bb = b[t][ii];
           if (metric == HYPRET_METRIC_HYPERBOLIC) {
-            const float e0 = qv[i].x - b[t].x, e1 = qv[i].y - b[t].y, e2 = qv[i].z - b[t].z, e3 = qv[i].w - b[t].w;
+            const float e0 = qv[i].x - bb.x, e1 = qv[i].y - bb.y, e2 = qv[i].z - bb.z, e3 = qv[i].w - bb.w;
             sacc[t] += (double)e0 * e0 + (double)e1 * e1 + (double)e2 * e2 + (double)e3 * e3;
           } else {
-            sacc[t] += (double)qv[i].x * b[t].x + (double)qv[i].y * b[t].y + (double)qv[i].z * b[t].z +
-                       (double)qv[i].w * b[t].w;
+            sacc[t] += (double)qv[i].x * bb.x + (double)qv[i].y * bb.y + (double)qv[i].z * bb.z +
+                       (double)qv[i].w * bb.w;
           }
-          yacc[t] += (double)b[t].x * b[t].x + (double)b[t].y * b[t].y + (double)b[t].z * b[t].z +
-                     (double)b[t].w * b[t].w;
+          yacc[t] += (double)bb.x * bb.x + (double)bb.y * bb.y + (double)bb.z * bb.z + (double)bb.w * bb.w;
         }
       }
     }
 #pragma unroll
     for (int t = 0; t < PASS; ++t) {
       const double s0 = warp_sum(sacc[t]), y0 = warp_sum(yacc[t]);
-      double key0, sur0;
-      if (metric == HYPRET_METRIC_HYPERBOLIC) {
-        const double cc = (double)c;
-        const double al = 1.0 - cc * xsq;
-        const double t0 = 2.0 * cc * s0 / (al * (1.0 - cc * y0));
-        key0 = log1p(t0 + sqrt(t0 * (t0 + 2.0))) / sqrt(cc);
-        sur0 = s0 / (1.0 - cc * y0);
-      } else {
-        const double nx = sqrt(xsq);
-        const double d0 = (nx == 0.0 ? 1.0 : nx) * (y0 == 0.0 ? 1.0 : sqrt(y0));
-        key0 = -(s0 / d0);
-        sur0 = key0;
-      }
-      if (val[t] && lane == r0 + t) { my_key = key0; my_sur = sur0; }
+      if (lane == r0 + t) { my_s = s0; my_y = y0; }
     }
+  }
+  double my_key = INFINITY;     // sort key (distance, or minus similarity)
+  double my_sur = INFINITY;     // exact surrogate, comparable with the approximate scores
+  if (my_idx >= 0) {
+    if (metric == HYPRET_METRIC_HYPERBOLIC) {
+      const double cc = (double)c;
+      const double al = 1.0 - cc * xsq;
+      const double t0 = 2.0 * cc * my_s / (al * (1.0 - cc * my_y));
+      my_key = log1p(t0 + sqrt(t0 * (t0 + 2.0))) / sqrt(cc);
+      my_sur = my_s / (1.0 - cc * my_y);
+    } else {
+      const double nx = sqrt(xsq);
+      const double d0 = (nx == 0.0 ? 1.0 : nx) * (my_y == 0.0 ? 1.0 : sqrt(my_y));
+      my_key = -(my_s / d0);
+      my_sur = my_key;
+    }
+    // order by the fp32 value that is written out (ties -> lower index): the result is then a function of the
+    // emitted (score, index) pairs alone, so per-shard lists merge to exactly the single-GPU list
+    my_key = (double)(float)my_key;
   }
 
   // ---- 3. warp bitonic sort by (key, index) -----------------------------------------------
@@ -180,6 +223,32 @@ rerank_kernel(const float* __restrict__ q32, const float* __restrict__ g32, int6
   }
 }
 
+// Approximate merge only: the k' best candidates of every query by surrogate score, ascending (surrogate, index),
+// padded with (+inf, -1).  Multi-GPU pruning step: the surrogates of different gallery shards are comparable, so
+// the owner of a query can find its GLOBAL k'-th best surrogate from W such lists before any exact rescoring.
+__global__ void __launch_bounds__(RR_WARPS * 32)
+cand_select_kernel(const float* __restrict__ cand_score, const int32_t* __restrict__ cand_idx, int64_t Q, int n_cand,
+                   int kprime, float* __restrict__ sel_score, int32_t* __restrict__ sel_idx) {
+  extern __shared__ uint8_t smem_raw[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t q = (int64_t)blockIdx.x * RR_WARPS + warp;
+  if (q >= Q) return;
+  float* cs = reinterpret_cast<float*>(smem_raw) + (size_t)warp * n_cand;
+  int* ci = reinterpret_cast<int*>(reinterpret_cast<float*>(smem_raw) + (size_t)RR_WARPS * n_cand) +
+            (size_t)warp * n_cand;
+  for (int t = lane; t < n_cand; t += 32) {
+    cs[t] = cand_score[q * n_cand + t];
+    ci[t] = cand_idx[q * n_cand + t];
+  }
+  __syncwarp();
+  float my_score, worst;
+  const int my_idx = select_candidates(cs, ci, n_cand, kprime, INFINITY, lane, &my_score, &worst);
+  if (lane < kprime) {
+    sel_score[q * kprime + lane] = my_score;
+    sel_idx[q * kprime + lane] = my_idx;
+  }
+}
+
 // ----------------------------------------------------------------------------- wide top-k (k up to 128)
 // One CTA (128 threads) per query.  The candidate lists (n_lists x kprime, built WITHOUT threshold
 // sharing so that each list is exactly its strip's top-kprime) are sorted by surrogate score with a
@@ -191,14 +260,6 @@ rerank_kernel(const float* __restrict__ q32, const float* __restrict__ g32, int6
 constexpr int RW_THREADS = 128;
 constexpr int RW_SURV = 256;   // survivors rescored exactly: 2x the largest k, the bf16 filter error is comparable
                                // with the score gap between rank k and rank 1.3k on concentrated data
-
-__device__ __forceinline__ unsigned ordered_key(float x) {   // monotone float -> uint map
-  const unsigned u = __float_as_uint(x);
-  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
-}
-__device__ __forceinline__ float ordered_val(unsigned k) {
-  return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
-}
 
 __device__ __forceinline__ bool pair_less(float a, int ia, float b, int ib) {
   if (ia < 0) return false;
@@ -337,6 +398,7 @@ rerank_wide_kernel(const float* __restrict__ q32, const float* __restrict__ g32,
           key0 = -(s0 / d0);
           sur0 = key0;
         }
+        key0 = (double)(float)key0;      // order by the emitted fp32 value, ties -> lower index (see rerank_kernel)
       }
       if (lane == 0 && r0 + t < RW_SURV) { ekey[r0 + t] = key0; esur[r0 + t] = sur0; eidx[r0 + t] = val[t] ? idx[t] : -1; }
     }
@@ -374,12 +436,27 @@ rerank_wide_kernel(const float* __restrict__ q32, const float* __restrict__ g32,
 
 }  // namespace
 
+int hypret_launch_cand_select(const float* cand_score, const int32_t* cand_idx, int64_t Q, int n_cand, int kprime,
+                              float* sel_score, int32_t* sel_idx, cudaStream_t stream) {
+  if (Q == 0) return HYPRET_OK;
+  const size_t smem = (size_t)RR_WARPS * n_cand * 8;
+  if (smem > 200 * 1024) return HYPRET_EUNSUPPORTED;
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(cand_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+  }
+  cand_select_kernel<<<(unsigned)((Q + RR_WARPS - 1) / RR_WARPS), RR_WARPS * 32, smem, stream>>>(
+      cand_score, cand_idx, Q, n_cand, kprime, sel_score, sel_idx);
+  return (int)cudaGetLastError();
+}
+
 int hypret_launch_rerank(const float* q32, const float* g32, int64_t Q, int64_t N, int d, float c, int metric,
                          const float* cand_score, const int32_t* cand_idx, int n_cand, int kprime, int k,
-                         int64_t idx_offset, float* out_score, int64_t* out_idx, float* out_margin,
-                         cudaStream_t stream) {
+                         int64_t idx_offset, const float* prune_thr, float* out_score, int64_t* out_idx,
+                         float* out_margin, cudaStream_t stream) {
   if (Q == 0) return HYPRET_OK;
   if (kprime > 32 || k > 32 || k > kprime) {
+    if (prune_thr != nullptr) return HYPRET_EUNSUPPORTED;
     const int n_lists = n_cand / kprime;
     int n_pad = RW_SURV;
     while (n_pad < n_cand) n_pad <<= 1;
@@ -419,7 +496,7 @@ int hypret_launch_rerank(const float* q32, const float* g32, int64_t Q, int64_t 
     }                                                                                                               \
     rerank_kernel<NV><<<(unsigned)grid, RR_WARPS * 32, smem, stream>>>(q32, g32, Q, N, d, c, metric, cand_score,    \
                                                                       cand_idx, n_cand, kprime, k, idx_offset,      \
-                                                                      out_score, out_idx, out_margin);              \
+                                                                      prune_thr, out_score, out_idx, out_margin);   \
     return (int)cudaGetLastError();                                                                                 \
   } while (0)
   if (need <= 1) HYPRET_RERANK_LAUNCH(1);

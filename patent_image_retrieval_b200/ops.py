@@ -124,10 +124,30 @@ def score_topk(q_op: torch.Tensor, g_op: torch.Tensor, d: int, kprime: int, max_
 
 
 def rerank(q32: torch.Tensor, g32: torch.Tensor, cand_score: torch.Tensor, cand_idx: torch.Tensor, c: float,
-           metric: str, k: int, idx_offset: int = 0, want_margin: bool = False):
+           metric: str, k: int, idx_offset: int = 0, want_margin: bool = False,
+           prune_thr: Optional[torch.Tensor] = None):
     """Merge candidate lists, exact fp64-accumulated rescoring, sorted top-k.
-    Returns ``(score [Q,k] f32, idx [Q,k] i64[, margin [Q] f32])``."""
-    _need_cuda(q32, g32, cand_score, cand_idx)
+    Returns ``(score [Q,k] f32, idx [Q,k] i64[, margin [Q] f32])``.
+    ``prune_thr [Q]`` (multi-GPU): candidates whose surrogate exceeds it are skipped (``hypret_rerank_pruned``)."""
+    _need_cuda(q32, g32, cand_score, cand_idx, prune_thr)
+    if prune_thr is not None:
+        if want_margin:
+            raise ValueError("the margin certificate is not defined for a pruned rerank")
+        q32, g32 = q32.contiguous(), g32.contiguous()
+        Q, d = q32.shape
+        _, S, kprime = cand_score.shape
+        out_s = torch.empty(Q, k, dtype=torch.float32, device=q32.device)
+        out_i = torch.empty(Q, k, dtype=torch.int64, device=q32.device)
+        thr = prune_thr.contiguous().float()
+        if thr.numel() != Q:
+            raise ValueError("prune_thr must hold one threshold per query")
+        with torch.cuda.device(q32.device):
+            _lib.check(_lib.load().hypret_rerank_pruned(_ptr(q32), _ptr(g32), Q, g32.shape[0], d, float(c),
+                                                        METRIC[metric], _ptr(cand_score.contiguous()),
+                                                        _ptr(cand_idx.contiguous()), S, kprime, int(k),
+                                                        int(idx_offset), _ptr(thr), _ptr(out_s), _ptr(out_i),
+                                                        _stream()))
+        return out_s, out_i
     q32 = q32.contiguous()
     g32 = g32.contiguous()
     Q, d = q32.shape
@@ -141,6 +161,30 @@ def rerank(q32: torch.Tensor, g32: torch.Tensor, cand_score: torch.Tensor, cand_
                                              _ptr(cand_score), _ptr(cand_idx), S, kprime, int(k), int(idx_offset),
                                              _ptr(out_s), _ptr(out_i), _ptr(margin), _stream()))
     return (out_s, out_i, margin) if want_margin else (out_s, out_i)
+
+
+def cand_select(cand_score: torch.Tensor, cand_idx: torch.Tensor):
+    """The k' best candidates of each query by surrogate score: ``[Q,L,k'] -> ([Q,k'] f32 ascending, [Q,k'] i32)``,
+    padded with (+inf, -1)."""
+    _need_cuda(cand_score, cand_idx)
+    Q, S, kprime = cand_score.shape
+    ss = torch.empty(Q, kprime, dtype=torch.float32, device=cand_score.device)
+    si = torch.empty(Q, kprime, dtype=torch.int32, device=cand_score.device)
+    with torch.cuda.device(cand_score.device):
+        _lib.check(_lib.load().hypret_cand_select(_ptr(cand_score.contiguous()), _ptr(cand_idx.contiguous()), Q, S,
+                                                  kprime, _ptr(ss), _ptr(si), _stream()))
+    return ss, si
+
+
+def kth_smallest(vals: torch.Tensor, kth: int) -> torch.Tensor:
+    """``vals [W,Q,m]`` fp32 -> ``[Q]``: the kth smallest (1-based) of each query's W*m values (+inf if fewer)."""
+    _need_cuda(vals)
+    vals = vals.contiguous().float()
+    W, Q, m = vals.shape
+    out = torch.empty(Q, dtype=torch.float32, device=vals.device)
+    with torch.cuda.device(vals.device):
+        _lib.check(_lib.load().hypret_kth_smallest(_ptr(vals), W, Q, m, int(kth), _ptr(out), _stream()))
+    return out
 
 
 def merge_topk(scores: torch.Tensor, idx: torch.Tensor, descending: bool = False):

@@ -13,11 +13,50 @@ in libhypret.so; torch only owns the buffers.
 """
 from __future__ import annotations
 
+import contextlib
 from typing import Optional
 
 import torch
 
 from . import ops
+
+
+class StageEvents:
+    """CUDA-event pairs around the three kernels of a search, recorded on the launching stream
+    (bench.py's roofline measurements).  ``ms(name)`` = mean duration after a synchronize."""
+
+    STAGES = ("project", "score", "rerank")
+
+    def __init__(self):
+        self.pairs = {s: [] for s in self.STAGES}
+
+    @contextlib.contextmanager
+    def span(self, name):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        yield
+        e1.record()
+        self.pairs[name].append((e0, e1))
+
+    def ms(self, name):
+        p = self.pairs[name]
+        return sum(a.elapsed_time(b) for a, b in p) / len(p) if p else float("nan")
+
+
+@contextlib.contextmanager
+def _span(events, name):
+    """``events``: None, a list (receives the scoring kernel's pair only) or a ``StageEvents``."""
+    if isinstance(events, StageEvents):
+        with events.span(name):
+            yield
+    elif events is not None and name == "score":
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        yield
+        e1.record()
+        events.append((e0, e1))
+    else:
+        yield
 
 
 WIDE_MIN_LISTS = 4     # wide top-k: candidate lists per query (4 x 64 = 256 candidates for k <= 128)
@@ -73,8 +112,17 @@ class GalleryIndex:
                max_ctas: int = 0, kernel_events: Optional[list] = None):
         """queries [Q,D] fp32 (host or device) -> (score [Q,k] f32, idx [Q,k] i64) on the device.
         score = Poincare distance ascending, or cosine similarity descending; ties -> lower index.
-        ``kernel_events``: if a list, a (start, end) CUDA-event pair bracketing the scoring kernel
-        on the launching stream is appended per call (bench.py's roofline measurement)."""
+        ``kernel_events``: a list (receives a (start, end) CUDA-event pair bracketing the scoring kernel
+        on the launching stream per call) or a ``StageEvents`` (all three kernels): bench.py's rooflines."""
+        q32, cs, ci = self.score_candidates(queries, k=k, kprime=kprime, max_ctas=max_ctas,
+                                            kernel_events=kernel_events)
+        return self.rerank_candidates(q32, cs, ci, k, return_margin=return_margin, kernel_events=kernel_events)
+
+    def score_candidates(self, queries: torch.Tensor, k: int = 10, kprime: Optional[int] = None, max_ctas: int = 0,
+                         kernel_events: Optional[list] = None):
+        """First half of ``search``: projection + tcgen05 scoring / streaming top-k'.
+        Returns ``(q32 [Q,D] exact-rerank operand, cand_score [Q,L,k'], cand_idx [Q,L,k'] int32)``; the candidate
+        buffers are reused by the next call."""
         kprime = default_kprime(k) if kprime is None else int(kprime)
         kprime = min(kprime, ops.MAX_KPRIME)
         wide = k > kprime or k > 32 or kprime > 32
@@ -82,11 +130,12 @@ class GalleryIndex:
         q = queries.to(device=self.device, dtype=torch.float32, non_blocking=True)
         if q.dim() != 2 or q.shape[1] != self.d:
             raise ValueError(f"queries must be [Q, {self.d}]")
-        if self.metric == "hyperbolic":
-            q32, q_op, _ = ops.project_rows(q, self.c, mode=self._query_mode(), side="query")
-        else:
-            q32 = q.contiguous()
-            _, q_op, _ = ops.project_rows(q, 1.0, mode="cosine", side="query", want_point=False)
+        with _span(kernel_events, "project"):
+            if self.metric == "hyperbolic":
+                q32, q_op, _ = ops.project_rows(q, self.c, mode=self._query_mode(), side="query")
+            else:
+                q32 = q.contiguous()
+                _, q_op, _ = ops.project_rows(q, 1.0, mode="cosine", side="query", want_point=False)
         key = (q.shape[0], kprime, max_ctas, min_lists)
         plan = ops.score_plan(q.shape[0], self.n, self.d, kprime, max_ctas, min_lists)
         if k > plan["n_lists"] * kprime:
@@ -98,16 +147,18 @@ class GalleryIndex:
                    torch.empty(q.shape[0], plan["n_lists"], kprime, dtype=torch.int32, device=self.device),
                    torch.empty(q.shape[0], dtype=torch.int32, device=self.device))
             self._cand[key] = buf
-        if kernel_events is not None:
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-        cs, ci = ops.score_topk(q_op, self.operand, self.d, kprime, max_ctas, out=buf[:2], thr_workspace=buf[2],
-                                share_thresholds=not wide, min_lists=min_lists)
-        if kernel_events is not None:
-            e1.record()
-            kernel_events.append((e0, e1))
-        return ops.rerank(q32, self.rows32, cs, ci, self.c, self.metric, k, idx_offset=self.idx_offset,
-                          want_margin=return_margin)
+        with _span(kernel_events, "score"):
+            cs, ci = ops.score_topk(q_op, self.operand, self.d, kprime, max_ctas, out=buf[:2], thr_workspace=buf[2],
+                                    share_thresholds=not wide, min_lists=min_lists)
+        return q32, cs, ci
+
+    def rerank_candidates(self, q32, cand_score, cand_idx, k: int, return_margin: bool = False,
+                          prune_thr: Optional[torch.Tensor] = None, kernel_events: Optional[list] = None):
+        """Second half of ``search``: candidate merge + exact rerank against this shard's fp32 rows."""
+        with _span(kernel_events, "rerank"):
+            out = ops.rerank(q32, self.rows32, cand_score, cand_idx, self.c, self.metric, k,
+                             idx_offset=self.idx_offset, want_margin=return_margin, prune_thr=prune_thr)
+        return out
 
 
 class SearchPipeline:

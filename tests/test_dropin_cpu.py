@@ -168,6 +168,50 @@ def test_two_rank_shard_gather_merge_equals_single_shard():
     np.testing.assert_array_equal(merged_i, want.numpy())
 
 
+def _gloo_sharded_queries_worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from patent_image_retrieval_b200.dist import gather_queries, return_lists_to_owners, shard_range
+    Ql, N, D, k, c = 7, 203, 16, 5, 1.0
+    gu = torch.randn(N, D, generator=torch.Generator().manual_seed(5)) * 0.2
+    qu = torch.randn(Ql, D, generator=torch.Generator().manual_seed(10 + rank)) * 0.2     # this rank's own batch
+    lo, hi = shard_range(N, rank, world)
+    q_all = gather_queries(qu)                                                            # [W*Ql, D], rank-major
+    d, i = retrieval.hyperbolic_topk(head.embed_rows(q_all, c), head.embed_rows(gu[lo:hi], c), c, k, form="arcosh")
+    rs, ri = return_lists_to_owners(d, i + lo)                                            # [W, Ql, k] for own queries
+    q.put((rank, q_all.numpy(), rs.numpy(), ri.numpy()))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_sharded_queries_alltoall_equals_single_shard():
+    """Serving layout (dist.ShardedGalleryIndex.search_sharded): all_gather(query batches) -> shard-local
+    search -> all_to_all(lists) -> merge at the owner == searching the whole gallery for the owner's batch."""
+    world, port = 2, 29741 + os.getpid() % 200
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_gloo_sharded_queries_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=60) for _ in range(world)], key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    gu = torch.randn(203, 16, generator=torch.Generator().manual_seed(5)) * 0.2
+    g = head.embed_rows(gu, 1.0)
+    np.testing.assert_array_equal(res[0][1], res[1][1])                   # same gathered batch everywhere
+    for rank, q_all, rs, ri in res:
+        W, Ql, k = rs.shape
+        own = torch.randn(Ql, 16, generator=torch.Generator().manual_seed(10 + rank)) * 0.2
+        np.testing.assert_array_equal(q_all[rank * Ql:(rank + 1) * Ql], own.numpy())
+        flat_s = np.transpose(rs, (1, 0, 2)).reshape(Ql, W * k)
+        flat_i = np.transpose(ri, (1, 0, 2)).reshape(Ql, W * k)
+        order = np.lexsort((flat_i, flat_s), axis=1)[:, :k]
+        _, want = retrieval.hyperbolic_topk(head.embed_rows(own, 1.0), g, 1.0, k, form="arcosh")
+        np.testing.assert_array_equal(np.take_along_axis(flat_i, order, 1), want.numpy())
+
+
 def test_shard_range_partitions():
     from patent_image_retrieval_b200.dist import shard_range
     for n, w in [(10, 3), (300000, 8), (7, 8), (10_000_000, 4)]:

@@ -1,0 +1,57 @@
+"""Multi-GPU parity (needs >= 2 GPUs; skipped on a single-GPU box): both exchange patterns of
+dist.ShardedGalleryIndex over NCCL must reproduce the single-GPU search of the whole gallery
+(the reference has no distributed path)."""
+import os
+import subprocess
+import sys
+from pathlib import Path
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+ROOT = Path(__file__).resolve().parents[1]
+
+WORKER = r"""
+import os, sys, torch, torch.distributed as dist
+sys.path.insert(0, os.environ["HYPRET_ROOT"])
+from patent_image_retrieval_b200 import GalleryIndex, synth
+from patent_image_retrieval_b200.dist import ShardedGalleryIndex, shard_range
+rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+torch.cuda.set_device(rank)
+dev = torch.device("cuda", rank)
+dist.init_process_group("nccl", device_id=dev)
+N, D, Ql, k = 20011, 256, 301, 10
+g = synth.gaussian_features(N, D, seed=0).to(dev)
+lo, hi = shard_range(N, rank, world)
+full = GalleryIndex(g, c=1.0)
+for metric in ("hyperbolic", "cosine"):
+    full = GalleryIndex(g, c=1.0, metric=metric)
+    rep = ShardedGalleryIndex(g[lo:hi], lo, N, metric=metric, queries="replicated")
+    shd = ShardedGalleryIndex(g[lo:hi], lo, N, metric=metric, queries="sharded")
+    q_same = synth.gaussian_features(Ql, D, seed=1).to(dev)
+    q_own = synth.gaussian_features(Ql, D, seed=10 + rank).to(dev)
+    d0, i0 = full.search(q_same, k=k)
+    d1, i1 = rep.search(q_same, k=k)
+    assert torch.equal(i0, i1) and torch.equal(d0, d1), metric + " replicated"
+    d2, i2 = full.search(q_own, k=k)
+    d3, i3 = shd.search(q_own, k=k)
+    assert torch.equal(i2, i3) and torch.equal(d2, d3), metric + " sharded"
+torch.cuda.synchronize()
+dist.barrier()
+dist.destroy_process_group()
+print("OK", rank)
+"""
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_two_gpu_exchange_patterns_equal_single_gpu(tmp_path):
+    script = tmp_path / "worker.py"
+    script.write_text(WORKER)
+    env = dict(os.environ, HYPRET_ROOT=str(ROOT))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr",
+           "127.0.0.1", "--master-port", str(29800 + os.getpid() % 100), str(script)]
+    out = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+    assert out.stdout.count("OK") == 2
