@@ -153,8 +153,18 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
 
+    # stdout carries exactly ONE JSON line: everything else that writes to fd 1 (NCCL's version banner, library
+    # chatter) is sent to stderr, and the line is written to the saved descriptor at the end
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(line: dict) -> None:
+        sys.stdout.flush()
+        os.write(json_fd, (json.dumps(line) + "\n").encode())
+
     if args.impl == "reference":
-        return run_reference(args, Q, N, D, k, c, desc, world, rank)
+        return run_reference(args, Q, N, D, k, c, desc, world, rank, emit)
 
     from patent_image_retrieval_b200 import SearchPipeline, StageEvents, ops, synth
     from patent_image_retrieval_b200.dist import ShardedGalleryIndex, shard_range
@@ -284,8 +294,11 @@ def main():
     flops = 2.0 * q_scored * n_local * D
     kpad = ops.operand_kpad(D)
     project_bytes = q_scored * (4 * D + 4 * D + 2 * kpad)          # read f32 row, write f32 point + bf16 operand row
-    rerank_bytes = q_scored * kprime * D * 4                       # exact rescoring: k' gathered fp32 rows per query
-    n_coll = 0 if world == 1 else (4 if weak else 3)               # NCCL kernels + merge per step
+    # exact rescoring: k' gathered fp32 rows per query; with the cross-shard surrogate threshold (weak mode) the
+    # W shards share one query's k' rows between them
+    rerank_bytes = q_scored * kprime * D * 4 // (world if weak else 1)
+    n_own = 3 if world == 1 else (6 if weak else 4)                # own kernels per step (see gpu_launches_note)
+    n_nccl = 0 if world == 1 else (6 if weak else 2)
     achieved = flops / (score_ms * 1e-3) / 1e12
     traffic = None
     tp = ROOT / "profiles" / "score_topk_traffic.json"
@@ -314,9 +327,11 @@ def main():
                 "h2d_bytes_per_step": Q * D * 4, "d2h_bytes_per_step": Q * k * 12, "bytes_are": "per rank",
                 "mode": "SearchPipeline: per-step H2D + search + D2H, copies of neighbouring steps overlapped",
                 "serial": {"value": q_total / (ms_e2e_serial * 1e-3), "ms_per_step": ms_e2e_serial}},
-        "gpu_launches": args.steps * (3 + (1 if world > 1 else 0)),
-        "gpu_launches_note": "own kernels per step per rank: project_rows, score_topk, rerank" +
-                             (", merge_topk (+ %d NCCL kernels)" % (n_coll - 1) if world > 1 else ""),
+        "gpu_launches": args.steps * n_own,
+        "gpu_launches_note": "own kernels per step per rank: project_rows, score_topk, " +
+                             ("cand_select, kth_smallest, rerank (pruned), merge_topk" if weak else
+                              "rerank, merge_topk" if world > 1 else "rerank") +
+                             (" (+ %d NCCL collectives)" % n_nccl if world > 1 else ""),
         "roofline": {"bound": "tensor", "achieved": achieved, "peak": peaks["tflops_sustained"], "unit": "TFLOP/s",
                      "frac": achieved / peaks["tflops_sustained"], "traffic": traffic,
                      "kernel": "score_topk_kernel", "kernel_ms": score_ms, "algorithmic_flops": flops,
@@ -343,14 +358,14 @@ def main():
                                 "sample": f"first {n_q} queries of the same workload against the full {N}-row "
                                           f"gallery (points pre-embedded), {secs:.1f} s",
                                 "topk_lists_identical_frac": same, "max_rel_dist_diff": rel}
-    print(json.dumps(line))
+    emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
     return 0
 
 
-def run_reference(args, Q, N, D, k, c, desc, world, rank):
+def run_reference(args, Q, N, D, k, c, desc, world, rank, emit):
     """CPU arm: the oracle port of the reference path on this box's host cores (geoopt is not
     installable, so the unmodified reference cannot run)."""
     if rank != 0:
@@ -386,7 +401,7 @@ def run_reference(args, Q, N, D, k, c, desc, world, rank):
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    emit(line)
     return 0
 
 

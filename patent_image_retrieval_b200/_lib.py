@@ -36,6 +36,7 @@ class ScorePlan(Structure):
         ("sub", c_int32),
         ("sub_tail", c_int32),
         ("pair", c_int32),
+        ("epi_groups", c_int32),
     ]
 
     def asdict(self):

@@ -90,8 +90,8 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
     if ((++spins & 0x3ffu) == 0 && global_timer_ns() - t0 > 4000000000ull) {
-      printf("hypret: mbarrier wait timed out (block %d thread %d bar@%u parity %u)\n", blockIdx.x, threadIdx.x,
-             smem_u32(bar), parity);
+      // no printf here: a call inside the wait forces every value that is live across it (the epilogue's
+      // register-resident candidate lists) onto the stack
       __trap();
     }
   }
@@ -215,6 +215,13 @@ __device__ __forceinline__ void tmem_dealloc_2cta(uint32_t taddr, uint32_t ncols
 }
 // TMA load issued by either CTA of the pair; the transaction bytes are credited to the LEADER's
 // mbarrier at the same shared-memory offset (rank bit cleared).
+// L2 prefetch of a 2-D tile (no shared-memory destination, no completion tracking)
+__device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap* map, int32_t c0, int32_t c1) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];"
+               :
+               : "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1)
+               : "memory");
+}
 __device__ __forceinline__ void tma_load_2d_pair(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int32_t c0,
                                                  int32_t c1, uint64_t policy) {
   asm volatile(

@@ -196,6 +196,8 @@ struct Params {
   uint32_t* shared_thr;   // [Q] ordered-uint keys of the best known k'-th score per query, or NULL
   unsigned long long* stats;   // DEBUG builds: [grid][8] wait-cycle counters per warp role, or NULL
   int wait_mode;          // experiments: 0 = try_wait + suspend hint, 1 = plain try_wait, 2 = test_wait spin
+  int pf_tiles;           // producer: L2 prefetch distance in gallery tiles (0 = off)
+  int wg_off;             // REGLIST: byte offset of the warpgroup-exchange words [2][128] x 8 B
 };
 
 // mbarrier wait with optional cycle accounting (DEBUG kernels only)
@@ -295,6 +297,9 @@ __device__ __noinline__ uint2 list_insert(uint32_t s_addr, uint32_t i_addr, floa
 // inserts.  The threshold a lane filters with is refreshed at every drain, so it is at most a
 // few hits stale -- that only lets a few extra candidates into the queue, never drops one.
 constexpr int QCAP = 12;   // queue slots per lane (12 x 8 B x 128 rows = 12 KB)
+constexpr int QCAP_R = 12; // ... of the register-list epilogue, per warpgroup.  (4 slots would buy a fifth ring stage:
+                           // measured 2.09 vs 2.08 ms at C2 and 2.73 vs 2.51 ms on 37.5k-row shards -- the overflow
+                           // path and the poorer drain batching cost more than the stage gains)
 
 struct RowState {
   float thr;        // effective filter threshold = min(thr_list, thr_g)
@@ -373,13 +378,149 @@ __device__ __forceinline__ void process_chunk(const float (&v)[32], int cbase, R
   }
 }
 
+// ----------------------------------------------------------------------------- k' <= 16: lists in registers
+// For k' <= 16 (top-10 retrieval, the headline configuration) a row's candidate list lives in the owning
+// thread's REGISTERS as 16 (score, index) pairs sorted ascending.  An insert is a branch-free
+// compare-and-shift over the 16 slots (each slot's new value depends only on old values: 16-way ILP, no
+// shared-memory round trip, no rescan for the new worst entry -- it is simply the last slot), and the
+// 16 KB of shared memory the lists used to occupy pays for the pending-hit queue of a SECOND epilogue
+// warpgroup: warpgroup g consumes accumulator g, i.e. every other gallery tile, so each SM sub-partition
+// has two epilogue warps to hide each other's latencies and each warpgroup has two MMA tile times per tile.
+// A row therefore owns two lists per strip (slot 2*s+g); the two halves exchange their k'-th best through
+// the same L2 threshold word the strips of a query already share.
+constexpr int RL = 16;
+constexpr int WG_X_BYTES = 2 * TILE_M * 8;   // warpgroup exchange: [2][128] x {strip tag, score bits}
+constexpr int OVF = 64;      // per-thread overflow of the pending queue (local memory; cold phase only)
+
+// The list is a struct of 32 NAMED scalars, not two arrays: with arrays the compiler front end left the scores
+// in a local-memory depot (the L1 that would back it is almost entirely carved out as shared memory here).
+#define RL_FOR_EACH(M) M(0) M(1) M(2) M(3) M(4) M(5) M(6) M(7) M(8) M(9) M(10) M(11) M(12) M(13) M(14) M(15)
+#define RL_FOR_EACH_DOWN(M)                                                                                        \
+  M(15, 14) M(14, 13) M(13, 12) M(12, 11) M(11, 10) M(10, 9) M(9, 8) M(8, 7) M(7, 6) M(6, 5) M(5, 4) M(4, 3) M(3, 2) \
+      M(2, 1) M(1, 0)
+struct RegList {
+#define RL_DECL(t) float s##t; int i##t;
+  RL_FOR_EACH(RL_DECL)
+#undef RL_DECL
+};
+
+__device__ __forceinline__ void reg_init(RegList& L) {
+#define RL_INIT(t) L.s##t = INFINITY; L.i##t = -1;
+  RL_FOR_EACH(RL_INIT)
+#undef RL_INIT
+}
+
+__device__ __forceinline__ void reg_insert(RegList& L, float x, int col) {
+#define RL_STEP(t, u)                                    \
+  {                                                      \
+    const bool up = x < L.s##u; /* better neighbour moves down one slot */ \
+    const bool in = x < L.s##t; /* ... or x lands here */ \
+    L.s##t = up ? L.s##u : (in ? x : L.s##t);            \
+    L.i##t = up ? L.i##u : (in ? col : L.i##t);          \
+  }
+  RL_FOR_EACH_DOWN(RL_STEP)
+#undef RL_STEP
+  const bool in0 = x < L.s0;
+  L.s0 = in0 ? x : L.s0;
+  L.i0 = in0 ? col : L.i0;
+}
+
+__device__ __forceinline__ float reg_kth(const RegList& L, int kp) {   // kp-th best (1-based), kp <= RL
+  float v = L.s15;
+#define RL_KTH(t) v = (kp - 1 == t) ? L.s##t : v;
+  RL_FOR_EACH(RL_KTH)
+#undef RL_KTH
+  return v;
+}
+
+__device__ __forceinline__ void reg_publish(const RegList& L, int kp, float* cs, int32_t* ci) {
+#define RL_PUB(t)        \
+  if (t < kp) {          \
+    cs[t] = L.s##t;      \
+    ci[t] = L.i##t;      \
+  }
+  RL_FOR_EACH(RL_PUB)
+#undef RL_PUB
+}
+
+struct RowStateR {
+  float thr;        // effective filter threshold = min(thr_list, thr_g)
+  float thr_list;   // k'-th best score currently kept (+inf until k' scores are in)
+  float thr_g;      // bound shared by the query's other lists
+  int cnt;          // pending hits (queue + overflow)
+  int n_ins, n_drain, n_now;   // DEBUG statistics
+};
+
+// warp-uniform and branch-free per pass: every lane pops one pending hit (+inf when it has none) and runs
+// the register insert; lanes that run dry idle until the longest queue is empty
+__device__ __forceinline__ void drain_queue_reg(RowStateR& st, RegList& L, int kp, uint32_t qs_addr, uint32_t qi_addr,
+                                                const float* ovf_s, const int* ovf_i) {
+  while (__any_sync(FULL, st.cnt > 0)) {
+    st.n_drain += 1;
+    float x = INFINITY;
+    int col = -1;
+    if (st.cnt > 0) {
+      st.cnt -= 1;
+      if (st.cnt >= QCAP_R) {
+        x = ovf_s[st.cnt - QCAP_R];
+        col = ovf_i[st.cnt - QCAP_R];
+      } else {
+        x = lds_f32(qs_addr + st.cnt * LIST_SLOT_STRIDE);
+        asm volatile("ld.shared.b32 %0, [%1];" : "=r"(col) : "r"(qi_addr + st.cnt * LIST_SLOT_STRIDE) : "memory");
+      }
+      st.n_ins += (x < st.thr) ? 1 : 0;
+    }
+    x = (x < st.thr) ? x : INFINITY;          // the threshold may have tightened since the hit was queued
+    reg_insert(L, x, col);
+    st.thr_list = reg_kth(L, kp);
+    st.thr = fminf(st.thr_list, st.thr_g);
+  }
+}
+
+// One 32-column chunk, lists in registers: same fast path; hits go to the pending queue (shared memory) or,
+// when that is full (first tiles of a cold list only), to the thread's overflow array.
+__device__ __forceinline__ void process_chunk_reg(const float (&v)[32], int cbase, RowStateR& st, uint32_t qs_addr,
+                                                  uint32_t qi_addr, float* ovf_s, int* ovf_i) {
+  float mg[4];
+#pragma unroll
+  for (int g = 0; g < 4; ++g) {
+    float m = v[g * 8];
+#pragma unroll
+    for (int j = 1; j < 8; ++j) m = fminf(m, v[g * 8 + j]);
+    mg[g] = m;
+  }
+  const float m = fminf(fminf(mg[0], mg[1]), fminf(mg[2], mg[3]));
+  if (m < st.thr) {
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      if (mg[g] < st.thr) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float x = v[g * 8 + j];
+          if (x < st.thr) {
+            if (st.cnt < QCAP_R) {
+              sts_f32(qs_addr + st.cnt * LIST_SLOT_STRIDE, x);
+              sts_b32(qi_addr + st.cnt * LIST_SLOT_STRIDE, cbase + g * 8 + j);
+            } else {
+              st.n_now += 1;
+              ovf_s[st.cnt - QCAP_R] = x;
+              ovf_i[st.cnt - QCAP_R] = cbase + g * 8 + j;
+            }
+            st.cnt += 1;
+          }
+        }
+      }
+    }
+  }
+}
+
 // PAIR: two CTAs of a cluster (one TPC) share every gallery tile through tcgen05 cta_group::2 --
 // each CTA keeps its OWN 128-row query tile and loads only HALF (128 rows) of the 256-row gallery
 // tile; the leader CTA issues one M=256 MMA for both.  Halves the L2->shared-memory traffic per
 // SM (the measured limiter of the single-CTA kernel at D=512) and leaves room for a resident
 // query tile plus a 4-stage ring.
 template <bool RESIDENT, int KPP, bool DEBUG, bool PAIR>
-__global__ void __launch_bounds__(NUM_THREADS, 1)
+__global__ void __launch_bounds__(KPP == RL ? NUM_THREADS + NUM_EPI_THREADS : NUM_THREADS, 1)
 score_topk_kernel(const __grid_constant__ CUtensorMap map_q_main, const __grid_constant__ CUtensorMap map_q_ext,
                   const __grid_constant__ CUtensorMap map_g_main, const __grid_constant__ CUtensorMap map_g_ext,
                   const Params p) {
@@ -388,10 +529,11 @@ score_topk_kernel(const __grid_constant__ CUtensorMap map_q_main, const __grid_c
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* a_res = smem;                                   // RESIDENT: kb_main blocks + ext block
   uint8_t* ring = smem + p.ring_off;
-  float* list_s = reinterpret_cast<float*>(smem + p.lists_off);   // [KPP slots][128 rows]
+  constexpr bool REGLIST = KPP == RL;                      // k' <= 16: lists in registers, two epilogue warpgroups
+  float* list_s = reinterpret_cast<float*>(smem + p.lists_off);   // [KPP slots][128 rows]   (unused when REGLIST)
   int* list_i = reinterpret_cast<int*>(list_s + KPP * TILE_M);
-  float* queue_s = reinterpret_cast<float*>(list_i + KPP * TILE_M);   // [QCAP slots][128 rows]
-  int* queue_i = reinterpret_cast<int*>(queue_s + QCAP * TILE_M);
+  float* queue_s = REGLIST ? list_s : reinterpret_cast<float*>(list_i + KPP * TILE_M);   // [QCAP slots][128 rows]
+  int* queue_i = reinterpret_cast<int*>(queue_s + (REGLIST ? QCAP_R : QCAP) * TILE_M);   // REGLIST: one block per warpgroup
   Barriers* bars = reinterpret_cast<Barriers*>(smem + p.bar_off);
 
   const int warp = threadIdx.x >> 5;
@@ -477,6 +619,13 @@ score_topk_kernel(const __grid_constant__ CUtensorMap map_q_main, const __grid_c
             uint8_t* st = ring + stage * p.stage_bytes;
             uint8_t* st_b = RESIDENT ? st : st + A_BLK_BYTES;
             uint64_t* full = &bars->full[stage];
+            // pull the same K-block of the tile PF_TILES ahead into L2: the ring only looks half a tile ahead
+            // (4 x 16 KB), less than an HBM round trip when the whole lock-step group misses together
+            if (p.pf_tiles > 0 && gt + p.pf_tiles < gt1) {
+              const int pf_row = (gt + p.pf_tiles) * TILE_N + (int)rank * B_ROWS;
+              if (ks < KB) tma_prefetch_2d(&map_g_main, ks * HYPRET_KBLK, pf_row);
+              else tma_prefetch_2d(&map_g_ext, p.dpad, pf_row);
+            }
             if (ks < KB) {
               if (rank == 0) mbar_arrive_expect_tx(full, (RESIDENT ? B_BLK : A_BLK_BYTES + B_BLK) * NCTA);
               if (PAIR) {
@@ -578,6 +727,136 @@ score_topk_kernel(const __grid_constant__ CUtensorMap map_q_main, const __grid_c
       p.stats[blockIdx.x * 8 + 2] = w_full;
       p.stats[blockIdx.x * 8 + 3] = w_tmem;
       p.stats[blockIdx.x * 8 + 4] = (unsigned long long)clock64() - t_begin;
+    }
+  } else if (REGLIST && warp >= 2) {
+    // ======================================================================= epilogue / top-k', lists in registers
+    const int wg = (warp - 2) >> 2;            // epilogue warpgroup 0 / 1 <-> TMEM accumulator 0 / 1
+    const int quad = warp & 3;                 // TMEM lane quadrant this warp may read
+    const int row = quad * 32 + lane;          // query row inside the tile == TMEM lane
+    const uint32_t qs_addr = smem_u32(queue_s + wg * 2 * QCAP_R * TILE_M + row);
+    const uint32_t qi_addr = smem_u32(queue_i + wg * 2 * QCAP_R * TILE_M + row);
+    float ovf_s[OVF];
+    int ovf_i[OVF];
+    const int KP = p.kprime;
+    const int N = (int)p.N;
+    uint32_t my_phase = 0;                     // parity of tmem_full[wg] for the next tile of this warpgroup
+    uint32_t tile_ctr = 0;                     // running tile count of this CTA == the MMA issuer's accumulator toggle
+    unsigned long long w_acc = 0, t_begin = DEBUG ? clock64() : 0;
+    int tot_ins = 0, tot_drain = 0, tot_now = 0;
+    for (int step = 0; step < sc.n_steps; ++step) {
+      int qt, gt0, gt1, slot;
+      if (!strip_at(sc, cta, step, qt, gt0, gt1, slot)) continue;
+      if (PAIR) qt = 2 * qt + (int)rank;         // this CTA's own query tile of the pair
+      const int64_t qrow = (int64_t)qt * TILE_M + row;
+      uint32_t* gthr = (p.shared_thr != nullptr && qrow < p.Q) ? p.shared_thr + qrow : nullptr;
+      RegList L;
+      reg_init(L);
+      // exchange word of this row: {strip tag, bits of this warpgroup's ceil(k'/2)-th best}.  The two lists of
+      // a row hold disjoint columns, so max(half-th best of one, half-th best of the other) bounds the k'-th
+      // best of their union -- about half the hits of filtering with min(k'-th best, k'-th best).
+      const uint32_t my_x = smem_u32(smem + p.wg_off) + (uint32_t)(wg * TILE_M + row) * 8u;
+      const uint32_t peer_x = smem_u32(smem + p.wg_off) + (uint32_t)((wg ^ 1) * TILE_M + row) * 8u;
+      const int half_k = (KP + 1) >> 1;
+      asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(my_x), "r"(step), "r"(0x7f800000u) : "memory");
+      RowStateR st;
+      st.thr_list = INFINITY;
+      st.cnt = 0;
+      st.n_ins = st.n_drain = st.n_now = 0;
+      st.thr_g = INFINITY;
+      float published = INFINITY;
+      uint32_t gk_inflight = 0xffffffffu;
+      if (gthr != nullptr) {
+        const uint32_t gk = ld_cg_u32(gthr);
+        if (gk < KEY_INF) st.thr_g = nextafterf(key2f(gk), INFINITY);
+      }
+      st.thr = fminf(st.thr_list, st.thr_g);
+      for (int gt = gt0; gt < gt1; ++gt) {
+        const uint32_t acc = tile_ctr & 1u;
+        tile_ctr += 1;
+        if (acc != (uint32_t)wg) continue;       // the other warpgroup's tile
+        timed_wait<DEBUG>(&bars->tmem_full[acc], my_phase, w_acc, p.wait_mode);
+        my_phase ^= 1;
+        tcgen05_fence_after();
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * TILE_N;
+        const int col0 = gt * TILE_N;
+        const bool ragged = col0 + TILE_N > N;               // last gallery tile: TMA zero-filled rows
+        float va[32], vb[32];
+        __syncwarp();
+        tmem_ld_32x32(taddr, va);
+#pragma unroll 1
+        for (int cc = 0; cc < TILE_N / 32; cc += 2) {
+          tmem_ld_wait(va);
+          tmem_ld_32x32(taddr + (cc + 1) * 32, vb);           // next chunk in flight while this one is scanned
+          if (ragged) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (col0 + cc * 32 + j >= N) va[j] = INFINITY;
+          }
+          if (DEBUG && p.debug_scores != nullptr && qrow < p.Q) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (col0 + cc * 32 + j < N) p.debug_scores[qrow * p.N + col0 + cc * 32 + j] = va[j];
+          }
+          process_chunk_reg(va, col0 + cc * 32, st, qs_addr, qi_addr, ovf_s, ovf_i);
+          __syncwarp();                                       // tcgen05.ld/wait are warp-collective
+          tmem_ld_wait(vb);
+          if (cc + 2 < TILE_N / 32) tmem_ld_32x32(taddr + (cc + 2) * 32, va);
+          if (ragged) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (col0 + (cc + 1) * 32 + j >= N) vb[j] = INFINITY;
+          }
+          if (DEBUG && p.debug_scores != nullptr && qrow < p.Q) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (col0 + (cc + 1) * 32 + j < N) p.debug_scores[qrow * p.N + col0 + (cc + 1) * 32 + j] = vb[j];
+          }
+          process_chunk_reg(vb, col0 + (cc + 1) * 32, st, qs_addr, qi_addr, ovf_s, ovf_i);
+          __syncwarp();
+          // drain early when a queue is half full, so that thresholds do not go stale in the cold phase
+          if (__any_sync(FULL, st.cnt >= QCAP_R / 2)) drain_queue_reg(st, L, KP, qs_addr, qi_addr, ovf_s, ovf_i);
+        }
+        tcgen05_fence_before();
+        if (PAIR) mbar_arrive_cluster(&bars->tmem_empty[acc], 0);   // the leader waits for both CTAs' epilogues
+        else mbar_arrive(&bars->tmem_empty[acc]);
+        // the accumulator is released: fold the pending hits in (off the MMA's critical path)
+        drain_queue_reg(st, L, KP, qs_addr, qi_addr, ovf_s, ovf_i);
+        // exchange thresholds with the query's other lists (other warpgroup, other strips) through L2
+        if (gthr != nullptr) {
+          if (st.thr_list < published) {
+            atomicMin(gthr, f2key(st.thr_list));
+            published = st.thr_list;
+          }
+          if (gk_inflight < KEY_INF) st.thr_g = fminf(st.thr_g, nextafterf(key2f(gk_inflight), INFINITY));
+          gk_inflight = ld_cg_u32(gthr);
+          // ... and with the other warpgroup of this CTA through shared memory
+          const float mine = reg_kth(L, half_k);
+          uint32_t tag, bits;
+          asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(my_x), "r"(step), "r"(__float_as_uint(mine)) : "memory");
+          asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(tag), "=r"(bits) : "r"(peer_x) : "memory");
+          if (tag == (uint32_t)step) {                 // the peer is on the same strip (same query rows)
+            const float both = fmaxf(mine, __uint_as_float(bits));
+            if (both < INFINITY) st.thr_g = fminf(st.thr_g, nextafterf(both, INFINITY));
+            if (both < published) {                    // also a bound for the query's other strips
+              atomicMin(gthr, f2key(both));
+              published = both;
+            }
+          }
+          st.thr = fminf(st.thr_list, st.thr_g);
+        }
+      }
+      tot_ins += st.n_ins; tot_drain += st.n_drain; tot_now += st.n_now;
+      // publish this warpgroup's list of the strip: the first k' entries of the sorted register list
+      if (qrow < p.Q) {
+        const int64_t o = (qrow * sc.n_lists + (slot * 2 + wg)) * KP;
+        reg_publish(L, KP, p.cand_score + o, p.cand_idx + o);
+      }
+    }
+    if (DEBUG && p.stats != nullptr && warp == 2 && lane == 0) {
+      p.stats[blockIdx.x * 8 + 5] = w_acc;
+      p.stats[blockIdx.x * 8 + 6] = (unsigned long long)clock64() - t_begin;
+      p.stats[blockIdx.x * 8 + 7] = ((unsigned long long)tot_ins << 40) | ((unsigned long long)tot_drain << 20) |
+                                    (unsigned long long)tot_now;
     }
   } else if (warp >= 2) {
     // ======================================================================= epilogue / top-k'
@@ -762,7 +1041,7 @@ Sched sched_from_plan(const hypret_score_plan_t& pl) {
   s.T = (pl.n_qtiles + pl.pair - 1) / pl.pair; s.G = pl.n_gtiles; s.P = pl.grid / pl.pair;
   s.n_full = pl.n_full; s.tail_rows = pl.tail_rows; s.a = pl.a; s.b = pl.b; s.L1 = pl.l1;
   s.rem_rows = pl.rem_rows; s.rem_g0 = pl.rem_g0; s.m = pl.m; s.L2 = pl.l2; s.n_steps = pl.n_steps;
-  s.n_lists = pl.n_lists;
+  s.n_lists = pl.n_lists;          // PUBLIC count (x epi_groups): the stride of a query's list slots
   s.sub = pl.sub;
   s.sub_tail = pl.sub_tail;
   return s;
@@ -778,7 +1057,7 @@ int launch_one(const hypret_score_plan_t& plan, const CUtensorMap& mq_main, cons
   if (e != cudaSuccess) return (int)e;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3((unsigned)plan.grid);
-  cfg.blockDim = dim3(NUM_THREADS);
+  cfg.blockDim = dim3(KPP == RL ? NUM_THREADS + NUM_EPI_THREADS : NUM_THREADS);
   cfg.dynamicSmemBytes = (size_t)plan.smem_bytes;
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
@@ -825,7 +1104,10 @@ extern "C" int hypret_score_plan(int64_t Q, int64_t N, int d, int kprime, int ma
   const int b_blk = pair ? B_BLK_BYTES / 2 : B_BLK_BYTES;
 
   // shared-memory carve-up
-  const int lists = kpp_of(kprime) * TILE_M * 8 + QCAP * TILE_M * 8;   // candidate lists + pending-hit queues
+  // candidate lists + pending-hit queues; k' <= 16: lists in registers, one queue per epilogue warpgroup
+  const int epi_groups = kpp_of(kprime) == RL ? 2 : 1;
+  const int lists = epi_groups == 2 ? 2 * QCAP_R * TILE_M * 8 + WG_X_BYTES
+                                    : kpp_of(kprime) * TILE_M * 8 + QCAP * TILE_M * 8;
   const int a_res_bytes = kb * A_BLK_BYTES + A_EXT_BYTES;
   int resident = 0, stages = 0, stage_bytes = 0;
   {
@@ -861,7 +1143,8 @@ extern "C" int hypret_score_plan(int64_t Q, int64_t N, int d, int kprime, int ma
   }
   plan->n_qtiles = (int32_t)n_qtiles;
   plan->n_gtiles = (int32_t)n_gtiles;
-  plan->n_lists = s.n_lists;
+  plan->n_lists = s.n_lists * epi_groups;
+  plan->epi_groups = epi_groups;
   plan->grid = pair ? 2 * s.P : s.P;
   plan->stages = stages;
   plan->resident = resident;
@@ -889,7 +1172,7 @@ extern "C" int hypret_score_strip(const hypret_score_plan_t* plan, int cta, int 
   const Sched s = sched_from_plan(*plan);
   int qt = 0, g0 = 0, g1 = 0, slot = 0;
   const bool ok = strip_at(s, cta, step, qt, g0, g1, slot);
-  out4[0] = qt * plan->pair; out4[1] = g0; out4[2] = g1; out4[3] = slot;
+  out4[0] = qt * plan->pair; out4[1] = g0; out4[2] = g1; out4[3] = slot * plan->epi_groups;
   return ok ? 1 : 0;
 }
 
@@ -922,7 +1205,8 @@ int hypret_launch_score_topk(const void* q_op, int64_t Q, const void* g_op, int6
   p.stage_bytes = plan.resident ? B_BLK_BYTES / plan.pair : A_BLK_BYTES + B_BLK_BYTES / plan.pair;
   p.ring_off = plan.resident ? p.kb_main * A_BLK_BYTES + A_EXT_BYTES : 0;
   p.lists_off = p.ring_off + plan.stages * p.stage_bytes;
-  p.bar_off = p.lists_off + kpp_of(kprime) * TILE_M * 8 + QCAP * TILE_M * 8;
+  p.bar_off = p.lists_off + (plan.epi_groups == 2 ? 2 * QCAP_R * TILE_M * 8 + WG_X_BYTES
+                                                  : kpp_of(kprime) * TILE_M * 8 + QCAP * TILE_M * 8);
   p.sched = sched_from_plan(plan);
   p.cand_score = cand_score;
   p.cand_idx = cand_idx;
@@ -930,6 +1214,9 @@ int hypret_launch_score_topk(const void* q_op, int64_t Q, const void* g_op, int6
   p.shared_thr = thr_ws;
   p.stats = nullptr;
   p.wait_mode = 0;
+  p.pf_tiles = 0;      // measured at C2 and on 37.5k-row shards: no gain from 2 or 4 tiles of L2 lookahead
+  if (const char* pf = getenv("HYPRET_PF_TILES")) p.pf_tiles = atoi(pf);     // experiments
+  p.wg_off = p.bar_off - WG_X_BYTES;
   // Experiments only: HYPRET_STATS=1 runs the instrumented kernel variant, synchronises and prints
   // per-role wait-cycle totals to stderr.  HYPRET_WAIT_MODE selects the wait flavour in that variant.
   const char* stats_env = getenv("HYPRET_STATS");

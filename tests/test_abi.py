@@ -126,7 +126,9 @@ def test_c2_plan_numbers():
     # 79 query tiles -> 40 tile pairs on 74 CTA pairs: 1 strip each + 34 rows with a second strip, rest in phase 2
     assert (p["grid"], p["pair"], p["n_full"], p["tail_rows"], p["a"], p["b"]) == (148, 2, 0, 40, 1, 34)
     assert p["l1"] == 586 and p["rem_rows"] == 6 and p["m"] == 12 and p["l2"] == 49
-    assert p["n_lists"] == 13 and p["resident"] == 1 and p["stages"] == 4
+    # k' = 16: lists in registers, two epilogue warpgroups -> two list slots per strip (13 strips per query at most)
+    assert p["epi_groups"] == 2 and p["n_lists"] == 26 and p["resident"] == 1 and p["stages"] == 4
+    assert ops.score_plan(10000, 300000, 512, 26)["epi_groups"] == 1
     with pytest.raises(RuntimeError):
         ops.score_plan(10, 10, 512, 65)          # kprime > 64
 

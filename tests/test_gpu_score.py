@@ -44,22 +44,32 @@ def test_scores_and_lists(Q, N, d, kprime, cap):
     assert cs.shape == (Q, plan["n_lists"], kprime)
     written = set()
     pair = plan["pair"]
+    eg = plan["epi_groups"]      # a strip owns eg consecutive list slots: one per epilogue warpgroup (alternate tiles)
     for cta, step, qt, g0, g1, slot in ops.score_strips(Q, N, d, kprime, cap):
         r0, r1 = qt * 128, min(Q, (qt + pair) * 128)
         lo, hi = g0 * 256, min(N, g1 * 256)
         for t in range(pair):
-            written.add((qt + t, slot))
+            for e in range(eg):
+                written.add((qt + t, slot + e))
         kk = min(kprime, hi - lo)
         want_v, _ = torch.topk(dbg[r0:r1, lo:hi], kk, dim=1, largest=False)
-        got_v, order = cs[r0:r1, slot, :].sort(dim=1)
-        got_i = torch.gather(ci[r0:r1, slot, :], 1, order)
+        un_s = cs[r0:r1, slot:slot + eg, :].reshape(r1 - r0, -1)
+        un_i = ci[r0:r1, slot:slot + eg, :].reshape(r1 - r0, -1)
+        un_s = torch.where(un_i >= 0, un_s, torch.full_like(un_s, float("inf")))
+        got_v, order = un_s.sort(dim=1)
+        got_i = torch.gather(un_i, 1, order)
+        # the union of the strip's lists holds exactly the strip's top-k' at its head
         assert torch.equal(got_v[:, :kk], want_v.sort(dim=1).values)
         # indices point at the scores they claim, inside the strip; unused slots are (-1, +inf)
         picked = torch.gather(dbg[r0:r1], 1, got_i[:, :kk].long())
         assert torch.equal(picked, got_v[:, :kk])
         assert int(got_i[:, :kk].min()) >= lo and int(got_i[:, :kk].max()) < hi
-        if kk < kprime:
+        n_valid = (un_i >= 0).sum(dim=1)
+        assert bool((n_valid <= hi - lo).all())
+        if eg == 1 and kk < kprime:
             assert bool((got_i[:, kk:] == -1).all()) and bool(torch.isinf(got_v[:, kk:]).all())
+        if hi - lo <= kprime:        # short strip: every column is kept exactly once
+            assert bool((n_valid == hi - lo).all())
     # list slots that no strip owns read as empty
     for qt in range(plan["n_qtiles"]):
         for slot in range(plan["n_lists"]):
@@ -76,14 +86,16 @@ def test_shared_thresholds_keep_the_global_topk(Q, N, d, kprime, cap):
     cs, ci, dbg = ops.score_topk(q_op, g_op, d, kprime, cap, debug=True, share_thresholds=True)
     plan = ops.score_plan(Q, N, d, kprime, cap)
     L = plan["n_lists"]
+    eg = plan["epi_groups"]
     for cta, step, qt, g0, g1, slot in ops.score_strips(Q, N, d, kprime, cap):
         r0, r1 = qt * 128, min(Q, (qt + plan["pair"]) * 128)
         lo, hi = g0 * 256, min(N, g1 * 256)
-        idx = ci[r0:r1, slot, :].long()
-        valid = idx >= 0
-        assert bool(((idx >= lo) & (idx < hi))[valid].all())
-        picked = torch.gather(dbg[r0:r1], 1, idx.clamp_min(0))
-        assert torch.equal(picked[valid], cs[r0:r1, slot, :][valid])
+        for e in range(eg):
+            idx = ci[r0:r1, slot + e, :].long()
+            valid = idx >= 0
+            assert bool(((idx >= lo) & (idx < hi))[valid].all())
+            picked = torch.gather(dbg[r0:r1], 1, idx.clamp_min(0))
+            assert torch.equal(picked[valid], cs[r0:r1, slot + e, :][valid])
     flat_i = ci.reshape(Q, L * kprime).long()
     flat_s = torch.where(flat_i >= 0, cs.reshape(Q, L * kprime), torch.full_like(cs.reshape(Q, -1), float("inf")))
     srt = flat_i.sort(dim=1).values

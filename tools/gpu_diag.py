@@ -55,7 +55,8 @@ def check(Q, N, d, kprime=16, hint=0, label=""):
                 lo, hi = g0 * 256, min(N, g1 * 256)
                 kk = min(kprime, hi - lo)
                 want = torch.topk(dbg[r0:r1, lo:hi], kk, dim=1, largest=False).values.sort(dim=1).values
-                got = cs[r0:r1, slot, :].sort(dim=1).values[:, :kk]
+                eg = plan.get("epi_groups", 1)      # a strip owns eg consecutive list slots (one per epilogue warpgroup)
+                got = cs[r0:r1, slot:slot + eg, :].reshape(r1 - r0, -1).sort(dim=1).values[:, :kk]
                 miss += int((want != got).sum())
             print(f"   top-k' lists vs torch.topk(debug matrix): mismatching entries = {miss}", flush=True)
             ok_all &= miss == 0
