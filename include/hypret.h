@@ -214,6 +214,30 @@ int hypret_retrieval_metrics(const int64_t* ranked, int64_t Q, int K, const int6
 int hypret_ap_full(const float* scores, int64_t Q, int64_t N, const int64_t* pos_offsets, const int64_t* pos_items,
                    int grouped_ties, double* ap, int32_t* valid, double* mean_ap, void* stream);
 
+/* Exact full-ranking AP WITHOUT the [Q,N] score matrix, shardable over gallery rows (multi-GPU "collective 2").
+ * Same reference semantics as hypret_ap_full (src/train.py:3259-3293; notebooks/retrieval.ipynb:383,411-420), from
+ * rank counts per (query, positive) pair.  key = Poincare distance (metric HYPERBOLIC, the arithmetic of
+ * hypret_pairdist bit for bit) or minus cosine similarity (metric COSINE): smaller = better.
+ *   q32 [Q,d] fp32 (on-ball points / raw features), g32 [n_local,d] fp32: this shard's gallery rows, whose global
+ *   ids are idx_offset .. idx_offset+n_local-1;  pos_offsets [Q+1], pos_items [nnz]: CSR of GLOBAL positive ids.
+ * 1. hypret_pair_keys: keys[t] = key(query of t, positive t) if this shard owns the positive, else 0
+ *    -> sum over shards (all-reduce) gives every shard all keys.
+ * 2. hypret_rank_count: ADDS to counts[t*3 + {0,1,2}] the number of this shard's rows that score strictly better
+ *    than positive t / tie with it and have a lower global id / tie with it (itself included on the owner), and to
+ *    bad[q] the number of non-finite scores of query q (queries with >= 1 positive).  Caller zeroes counts [nnz*3]
+ *    (uint64) and bad [Q] (int32) first -> sum over shards (all-reduce).
+ * 3. hypret_ap_from_counts: ap [Q] fp64, valid [Q] int32 (0: no in-range positive or a non-finite score), mean_ap
+ *    [1] fp64 or NULL over the valid queries.  grouped_ties as in hypret_ap_full. */
+int hypret_pair_keys(const float* q32, const float* g32, int64_t Q, int64_t n_local, int d, float c, int metric,
+                     const int64_t* pos_offsets, const int64_t* pos_items, int64_t idx_offset, float* keys,
+                     void* stream);
+int hypret_rank_count(const float* q32, const float* g32, int64_t Q, int64_t n_local, int d, float c, int metric,
+                      const int64_t* pos_offsets, const int64_t* pos_items, const float* pos_keys, int64_t idx_offset,
+                      uint64_t* counts, int32_t* bad, void* stream);
+int hypret_ap_from_counts(const int64_t* pos_offsets, const int64_t* pos_items, const float* pos_keys,
+                          const uint64_t* counts, const int32_t* bad, int64_t Q, int64_t n_total, int grouped_ties,
+                          double* ap, int32_t* valid, double* mean_ap, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -69,6 +69,12 @@ SIGNATURES = {
                                          c_int, c_void_p, c_void_p, c_void_p]),
     "hypret_ap_full": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p,
                                c_void_p]),
+    "hypret_pair_keys": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int, c_float, c_int, c_void_p, c_void_p,
+                                 c_int64, c_void_p, c_void_p]),
+    "hypret_rank_count": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int, c_float, c_int, c_void_p, c_void_p,
+                                  c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
+    "hypret_ap_from_counts": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int,
+                                      c_void_p, c_void_p, c_void_p, c_void_p]),
     "hypret_merge_topk": (c_int, [c_void_p, c_void_p, c_int, c_int64, c_int, c_int, c_void_p, c_void_p, c_void_p]),
 }
 

@@ -186,4 +186,48 @@ int hypret_ap_full(const float* scores, int64_t Q, int64_t N, const int64_t* pos
                                static_cast<cudaStream_t>(stream));
 }
 
+int hypret_pair_keys(const float* q32, const float* g32, int64_t Q, int64_t n_local, int d, float c, int metric,
+                     const int64_t* pos_offsets, const int64_t* pos_items, int64_t idx_offset, float* keys,
+                     void* stream) {
+  if (Q < 0 || n_local < 0 || d < 4 || (d & 3)) return HYPRET_EINVAL;
+  if (metric != HYPRET_METRIC_COSINE && metric != HYPRET_METRIC_HYPERBOLIC) return HYPRET_EINVAL;
+  if (metric == HYPRET_METRIC_HYPERBOLIC && !(c > 0.f)) return HYPRET_EINVAL;
+  if (Q == 0) return HYPRET_OK;
+  if (q32 == nullptr || (g32 == nullptr && n_local > 0) || pos_offsets == nullptr || keys == nullptr)
+    return HYPRET_EINVAL;
+  int rc = check_device();
+  if (rc != HYPRET_OK) return rc;
+  return hypret_launch_pair_keys(q32, g32, Q, n_local, d, c, metric, pos_offsets, pos_items, idx_offset, keys,
+                                 static_cast<cudaStream_t>(stream));
+}
+
+int hypret_rank_count(const float* q32, const float* g32, int64_t Q, int64_t n_local, int d, float c, int metric,
+                      const int64_t* pos_offsets, const int64_t* pos_items, const float* pos_keys, int64_t idx_offset,
+                      uint64_t* counts, int32_t* bad, void* stream) {
+  if (Q < 0 || n_local < 0 || d < 4 || (d & 3)) return HYPRET_EINVAL;
+  if (metric != HYPRET_METRIC_COSINE && metric != HYPRET_METRIC_HYPERBOLIC) return HYPRET_EINVAL;
+  if (metric == HYPRET_METRIC_HYPERBOLIC && !(c > 0.f)) return HYPRET_EINVAL;
+  if (Q == 0 || n_local == 0) return HYPRET_OK;
+  if (q32 == nullptr || g32 == nullptr || pos_offsets == nullptr || pos_keys == nullptr || counts == nullptr ||
+      bad == nullptr || !aligned16(q32) || !aligned16(g32))
+    return HYPRET_EINVAL;
+  int rc = check_device();
+  if (rc != HYPRET_OK) return rc;
+  return hypret_launch_rank_count(q32, g32, Q, n_local, d, c, metric, pos_offsets, pos_items, pos_keys, idx_offset,
+                                  reinterpret_cast<unsigned long long*>(counts), bad,
+                                  static_cast<cudaStream_t>(stream));
+}
+
+int hypret_ap_from_counts(const int64_t* pos_offsets, const int64_t* pos_items, const float* pos_keys,
+                          const uint64_t* counts, const int32_t* bad, int64_t Q, int64_t n_total, int grouped_ties,
+                          double* ap, int32_t* valid, double* mean_ap, void* stream) {
+  if (Q < 0 || n_total < 1) return HYPRET_EINVAL;
+  if (pos_offsets == nullptr || ap == nullptr || valid == nullptr) return HYPRET_EINVAL;
+  int rc = check_device();
+  if (rc != HYPRET_OK) return rc;
+  return hypret_launch_ap_from_counts(pos_offsets, pos_items, pos_keys,
+                                      reinterpret_cast<const unsigned long long*>(counts), bad, Q, n_total,
+                                      grouped_ties != 0, ap, valid, mean_ap, static_cast<cudaStream_t>(stream));
+}
+
 }  // extern "C"

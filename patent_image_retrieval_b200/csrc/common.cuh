@@ -327,6 +327,15 @@ int hypret_launch_retrieval_metrics(const int64_t* ranked, int64_t Q, int K, con
                                     int n_ks, double* per_query, double* means, cudaStream_t stream);
 int hypret_launch_ap_full(const float* scores, int64_t Q, int64_t N, const int64_t* pos_off, const int64_t* pos_items,
                           int grouped_ties, double* ap, int32_t* valid, double* mean_ap, cudaStream_t stream);
+int hypret_launch_pair_keys(const float* q32, const float* g32, int64_t Q, int64_t n_local, int d, float c, int metric,
+                            const int64_t* pos_off, const int64_t* pos_items, int64_t idx_offset, float* keys,
+                            cudaStream_t stream);
+int hypret_launch_rank_count(const float* q32, const float* g32, int64_t Q, int64_t n_local, int d, float c, int metric,
+                             const int64_t* pos_off, const int64_t* pos_items, const float* pos_keys,
+                             int64_t idx_offset, unsigned long long* counts, int32_t* bad, cudaStream_t stream);
+int hypret_launch_ap_from_counts(const int64_t* pos_off, const int64_t* pos_items, const float* pos_keys,
+                                 const unsigned long long* counts, const int32_t* bad, int64_t Q, int64_t n_total,
+                                 int grouped_ties, double* ap, int32_t* valid, double* mean_ap, cudaStream_t stream);
 int hypret_launch_pairdist_bwd(const float* g, const float* dmat, const float* asq, const float* psq, int64_t n,
                                int64_t m, float c, float* w_out, float* row_sum, float* col_partial, int n_partial,
                                cudaStream_t stream);

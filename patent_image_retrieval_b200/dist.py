@@ -132,3 +132,26 @@ class ShardedGalleryIndex:
         score, idx = self.local.rerank_candidates(q32, cs, ci, k, prune_thr=thr_all, kernel_events=kernel_events)
         rs, ri = return_lists_to_owners(score, idx, self.group)
         return ops.merge_topk(rs, ri, descending=(self.metric == "cosine"))
+
+
+def full_ranking_ap(q32: torch.Tensor, shard_rows32: torch.Tensor, pos_offsets: torch.Tensor, pos_items: torch.Tensor,
+                    c: float = 1.0, metric: str = "hyperbolic", row_offset: int = 0, n_total: Optional[int] = None,
+                    grouped_ties: bool = True, group=None):
+    """Exact AP over the FULL ranking of every query (reference src/train.py:3259-3293, grouped ties; or
+    notebooks/retrieval.ipynb:411-420, index tie-break) without ever forming the [Q,N] score matrix, with the
+    gallery row-sharded across ranks ("collective 2").
+
+    ``q32`` [Q,D] replicated exact query rows (points on the ball / raw features), ``shard_rows32`` this rank's
+    gallery rows (global ids ``row_offset ..``), positives as a CSR of GLOBAL gallery ids.  Two all-reduces cross
+    NVLink: the [nnz] keys of the (query, positive) pairs (each computed by the shard that owns the positive) and
+    the [nnz,3] rank counts.  Works unsharded too (no process group).  Returns ``(mean_ap, ap [Q], valid [Q])``."""
+    sharded = dist.is_initialized() and dist.get_world_size(group) > 1
+    n_total = int(n_total) if n_total is not None else int(shard_rows32.shape[0])
+    keys = ops.pair_keys(q32, shard_rows32, pos_offsets, pos_items, c, metric, idx_offset=row_offset)
+    if sharded:
+        dist.all_reduce(keys, op=dist.ReduceOp.SUM, group=group)          # exactly one shard contributes per pair
+    counts, bad = ops.rank_count(q32, shard_rows32, pos_offsets, pos_items, keys, c, metric, idx_offset=row_offset)
+    if sharded:
+        dist.all_reduce(counts, op=dist.ReduceOp.SUM, group=group)
+        dist.all_reduce(bad, op=dist.ReduceOp.SUM, group=group)
+    return ops.ap_from_counts(pos_offsets, pos_items, keys, counts, bad, n_total, grouped_ties=grouped_ties)

@@ -6,9 +6,10 @@
 
 ``evaluate_retrieval`` keeps the reference's signature and sentinel returns (0.0 for an empty
 evaluation set / no patents, -1.0 for encoding or shape errors).  The per-query Python loop
-(``pmath.dist`` one-vs-all -> D2H -> sklearn AP, with a host sync per query) becomes: one exact
-distance-matrix kernel per query chunk and one rank-counting AP kernel with sklearn's
-tie-grouping semantics -- no sort, no host round trip per query.
+(``pmath.dist`` one-vs-all -> D2H -> sklearn AP, with a host sync per query) becomes: the exact keys of
+the (query, positive) pairs, one sweep of exact distance tiles whose epilogue only counts ranks
+(``hypret_rank_count``), and AP from the counts with sklearn's tie-grouping semantics -- no sort, no
+[Q,P] matrix, no host round trip per query, and shardable over gallery rows (``dist.full_ranking_ap``).
 """
 from __future__ import annotations
 
@@ -91,20 +92,13 @@ def evaluate_retrieval(model, X_figures_tensor, eval_indices, figure_to_pos_pate
         pos_lists.append([int(p) for p in cand if 0 <= p < num_patents])
     offsets, items = _csr_from_lists(pos_lists, device)
 
-    # ---- exact one-vs-all distances + sklearn-style AP, chunked over queries -------------------------
-    ap_sum, n_valid = 0.0, 0
-    rows_per_chunk = max(1, min(len(eval_indices), (1 << 28) // max(1, num_patents)))
-    for r0 in range(0, len(eval_indices), rows_per_chunk):
-        r1 = min(len(eval_indices), r0 + rows_per_chunk)
-        d = ops.pairdist(figure_embeddings[r0:r1].contiguous(), patents, c)
-        off = (offsets[r0:r1 + 1] - offsets[r0]).contiguous()
-        it = items[int(offsets[r0]):int(offsets[r1])].contiguous()
-        if it.numel() == 0:
-            it = torch.zeros(1, dtype=torch.int64, device=device)
-        _, ap, valid = ops.ap_full(-d, off, it, grouped_ties=True)
-        ap_sum += float((ap * valid).sum().item())
-        n_valid += int(valid.sum().item())
-    return ap_sum / n_valid if n_valid > 0 else 0.0
+    # ---- exact one-vs-all distances + sklearn-style AP: rank counting, no [Q,P] matrix, no per-query sync ----
+    from .dist import full_ranking_ap
+    if items.numel() == 0:
+        return 0.0
+    mean_ap, _, valid = full_ranking_ap(figure_embeddings.contiguous(), patents, offsets, items, c=c,
+                                        metric="hyperbolic", n_total=num_patents, grouped_ties=True)
+    return mean_ap if int(valid.sum().item()) > 0 else 0.0
 
 
 class ImageRetrieval:

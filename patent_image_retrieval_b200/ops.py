@@ -264,6 +264,64 @@ def ap_full(scores: torch.Tensor, pos_offsets: torch.Tensor, pos_items: torch.Te
     return float(mean.item()), ap, valid
 
 
+def pair_keys(q32: torch.Tensor, g32: torch.Tensor, pos_offsets: torch.Tensor, pos_items: torch.Tensor, c: float,
+              metric: str, idx_offset: int = 0) -> torch.Tensor:
+    """Key (distance / minus cosine) of every (query, positive) pair whose gallery row is on this shard
+    (global ids ``idx_offset .. idx_offset + len(g32) - 1``), 0 elsewhere: sum over shards = all keys."""
+    _need_cuda(q32, g32, pos_offsets, pos_items)
+    q32, g32 = q32.contiguous().float(), g32.contiguous().float()
+    pos_offsets, pos_items = pos_offsets.contiguous().to(torch.int64), pos_items.contiguous().to(torch.int64)
+    keys = torch.zeros(max(1, pos_items.numel()), dtype=torch.float32, device=q32.device)
+    with torch.cuda.device(q32.device):
+        _lib.check(_lib.load().hypret_pair_keys(_ptr(q32), _ptr(g32), q32.shape[0], g32.shape[0], q32.shape[1],
+                                                float(c), METRIC[metric], _ptr(pos_offsets), _ptr(pos_items),
+                                                int(idx_offset), _ptr(keys), _stream()))
+    return keys[:pos_items.numel()]
+
+
+def rank_count(q32: torch.Tensor, g32: torch.Tensor, pos_offsets: torch.Tensor, pos_items: torch.Tensor,
+               pos_keys: torch.Tensor, c: float, metric: str, idx_offset: int = 0):
+    """This shard's rank counts of every (query, positive) pair: ``counts [nnz,3]`` int64
+    {#better, #tied with a lower global id, #tied} and ``bad [Q]`` int32 (non-finite scores); sum over shards."""
+    _need_cuda(q32, g32, pos_offsets, pos_items, pos_keys)
+    q32, g32 = q32.contiguous().float(), g32.contiguous().float()
+    pos_offsets, pos_items = pos_offsets.contiguous().to(torch.int64), pos_items.contiguous().to(torch.int64)
+    nnz = pos_items.numel()
+    counts = torch.zeros(max(1, nnz), 3, dtype=torch.int64, device=q32.device)
+    bad = torch.zeros(q32.shape[0], dtype=torch.int32, device=q32.device)
+    keys = pos_keys.contiguous().float()
+    if keys.numel() == 0:
+        keys = torch.zeros(1, dtype=torch.float32, device=q32.device)
+    with torch.cuda.device(q32.device):
+        _lib.check(_lib.load().hypret_rank_count(_ptr(q32), _ptr(g32), q32.shape[0], g32.shape[0], q32.shape[1],
+                                                 float(c), METRIC[metric], _ptr(pos_offsets), _ptr(pos_items),
+                                                 _ptr(keys), int(idx_offset), _ptr(counts), _ptr(bad), _stream()))
+    return counts[:nnz], bad
+
+
+def ap_from_counts(pos_offsets: torch.Tensor, pos_items: torch.Tensor, pos_keys: torch.Tensor, counts: torch.Tensor,
+                   bad: torch.Tensor, n_total: int, grouped_ties: bool = True):
+    """AP per query from global rank counts.  Returns ``(mean_ap float, ap [Q] fp64, valid [Q] int32)``."""
+    _need_cuda(pos_offsets, pos_items, pos_keys, counts, bad)
+    pos_offsets, pos_items = pos_offsets.contiguous().to(torch.int64), pos_items.contiguous().to(torch.int64)
+    Q = pos_offsets.numel() - 1
+    dev = pos_offsets.device
+    ap = torch.empty(Q, dtype=torch.float64, device=dev)
+    valid = torch.empty(Q, dtype=torch.int32, device=dev)
+    mean = torch.zeros(1, dtype=torch.float64, device=dev)
+    keys = pos_keys.contiguous().float()
+    cnt = counts.contiguous().to(torch.int64)
+    if keys.numel() == 0:
+        keys = torch.zeros(1, dtype=torch.float32, device=dev)
+        cnt = torch.zeros(1, 3, dtype=torch.int64, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.load().hypret_ap_from_counts(_ptr(pos_offsets), _ptr(pos_items), _ptr(keys), _ptr(cnt),
+                                                     _ptr(bad.contiguous().to(torch.int32)), Q, int(n_total),
+                                                     int(bool(grouped_ties)), _ptr(ap), _ptr(valid), _ptr(mean),
+                                                     _stream()))
+    return float(mean.item()), ap, valid
+
+
 def pairdist_bwd(grad_out: torch.Tensor, dmat: torch.Tensor, asq: torch.Tensor, psq: torch.Tensor, c: float,
                  n_partial: int = 32):
     """Weights of the distance-matrix backward: returns ``(W [n,m], row_sum [n], col_sum [m])``."""

@@ -38,6 +38,22 @@ for metric in ("hyperbolic", "cosine"):
     d2, i2 = full.search(q_own, k=k)
     d3, i3 = shd.search(q_own, k=k)
     assert torch.equal(i2, i3) and torch.equal(d2, d3), metric + " sharded"
+# collective 2: exact full-ranking AP from all-reduced keys / rank counts == the unsharded computation
+from patent_image_retrieval_b200.dist import full_ranking_ap
+from patent_image_retrieval_b200 import ops
+pts, _, _ = ops.project_rows(g, 1.0, mode="expmap0", side="gallery", want_operand=False)
+qp, _, _ = ops.project_rows(synth.gaussian_features(Ql, D, seed=1).to(dev), 1.0, mode="expmap0", side="query",
+                            want_operand=False)
+gen = torch.Generator().manual_seed(4)
+items = torch.randint(0, N, (Ql * 3,), generator=gen).to(dev)
+off = torch.arange(0, Ql * 3 + 1, 3, dtype=torch.int64, device=dev)
+for grouped in (True, False):
+    want = full_ranking_ap(qp, pts, off, items, grouped_ties=grouped, group=None) if False else None
+    single_keys = ops.pair_keys(qp, pts, off, items, 1.0, "hyperbolic")
+    c1, b1 = ops.rank_count(qp, pts, off, items, single_keys, 1.0, "hyperbolic")
+    want = ops.ap_from_counts(off, items, single_keys, c1, b1, N, grouped_ties=grouped)
+    got = full_ranking_ap(qp, pts[lo:hi].contiguous(), off, items, row_offset=lo, n_total=N, grouped_ties=grouped)
+    assert torch.equal(got[1], want[1]) and torch.equal(got[2], want[2]) and got[0] == want[0], "full_ranking_ap"
 torch.cuda.synchronize()
 dist.barrier()
 dist.destroy_process_group()
