@@ -165,3 +165,80 @@ def evaluate_queries(retrieval: ImageRetrieval, query_embeddings, query_names: S
     means, _ = ops.retrieval_metrics(idx, off, items, ks=ks, n_pos_total=torch.tensor(n_pos, dtype=torch.int32,
                                                                                     device=idx.device))
     return means
+
+
+def full_ranking_metrics(query_rows: torch.Tensor, gallery_rows: torch.Tensor, pos_offsets: torch.Tensor,
+                         pos_items: torch.Tensor, n_pos_total: Optional[torch.Tensor] = None, metric: str = "cosine",
+                         c: float = 1.0, ks=(5, 10, 20), row_offset: int = 0, n_total: Optional[int] = None,
+                         group=None):
+    """The notebook's whole metric suite over the FULL ranking (retrieval.ipynb:383-456: MRR, MRR@k, Precision@k,
+    AP, nDCG, Recall@k) without ranking anything: every one of them is a function of the RANKS of a query's
+    positives, and a rank is a count -- ``hypret_rank_count`` (ranking convention: descending similarity /
+    ascending distance, ties -> lower gallery index).  Works on a gallery row-shard per rank (two all-reduces,
+    ``dist.full_ranking_ap``'s collectives).  ``query_rows`` / ``gallery_rows``: raw features (cosine) or points on
+    the ball (hyperbolic).  Returns ``(means: dict, per_query [Q, 3+3*len(ks)] fp64)`` with the columns of
+    ``ops.metric_names(ks)`` -- the layout ``io.evaluation_results`` turns into the reference's results JSON."""
+    import torch.distributed as dist
+    dev = query_rows.device
+    Q = query_rows.shape[0]
+    n_total = int(n_total) if n_total is not None else int(gallery_rows.shape[0])
+    off = pos_offsets.to(dev, torch.int64)
+    items = pos_items.to(dev, torch.int64)
+    sharded = dist.is_initialized() and dist.get_world_size(group) > 1
+    keys = ops.pair_keys(query_rows, gallery_rows, off, items, c, metric, idx_offset=row_offset)
+    if sharded:
+        dist.all_reduce(keys, op=dist.ReduceOp.SUM, group=group)
+    counts, _ = ops.rank_count(query_rows, gallery_rows, off, items, keys, c, metric, idx_offset=row_offset)
+    if sharded:
+        dist.all_reduce(counts, op=dist.ReduceOp.SUM, group=group)
+    seg = torch.repeat_interleave(torch.arange(Q, device=dev), off[1:] - off[:-1])
+    ok = (items >= 0) & (items < n_total)
+    seg, rank = seg[ok], (counts[ok, 0] + counts[ok, 1] + 1)
+    n_pos = (off[1:] - off[:-1]).to(torch.float64) if n_pos_total is None else n_pos_total.to(dev, torch.float64)
+    order = torch.argsort(seg * (n_total + 2) + rank)                 # by query, then by rank
+    seg, rank = seg[order], rank[order].to(torch.float64)
+    first = torch.zeros(Q, dtype=torch.int64, device=dev)
+    first[1:] = torch.cumsum(torch.bincount(seg, minlength=Q), 0)[:-1]
+    nth = (torch.arange(seg.numel(), device=dev) - first[seg] + 1).to(torch.float64)     # 1-based hit number
+
+    def seg_sum(v):
+        return torch.zeros(Q, dtype=torch.float64, device=dev).index_add_(0, seg, v)
+
+    has = torch.bincount(seg, minlength=Q) > 0
+    best = torch.full((Q,), float("inf"), dtype=torch.float64, device=dev).scatter_reduce_(0, seg, rank, "amin")
+    safe_n = torch.where(n_pos > 0, n_pos, torch.ones_like(n_pos))
+    # ideal DCG over |P| positions (positives missing from the gallery included, retrieval.ipynb:430-437)
+    max_p = int(n_pos.max().item()) if Q else 0
+    disc = torch.cumsum(1.0 / torch.log2(torch.arange(max_p, device=dev, dtype=torch.float64) + 2.0), 0)
+    idcg = torch.where(n_pos > 0, disc[(n_pos.long() - 1).clamp(min=0)] if max_p else n_pos, torch.ones_like(n_pos))
+    cols = [torch.where(has, 1.0 / best, torch.zeros_like(best)),
+            torch.where(n_pos > 0, seg_sum(nth / rank) / safe_n, torch.zeros_like(n_pos)),
+            torch.where(n_pos > 0, seg_sum(1.0 / torch.log2(rank + 1.0)) / idcg, torch.zeros_like(n_pos))]
+    for k in ks:
+        hits = seg_sum((rank <= k).to(torch.float64))
+        cols.append(torch.where(has & (best <= k), 1.0 / best, torch.zeros_like(best)))
+        cols.append(hits / k if k <= n_total else torch.zeros_like(hits))
+        cols.append(torch.where(n_pos > 0, hits / safe_n, torch.zeros_like(n_pos)))
+    per_query = torch.stack(cols, dim=1)
+    names = ops.metric_names(ks)
+    means = {n: (float(per_query[:, i].mean()) if Q else 0.0) for i, n in enumerate(names)}
+    return means, per_query
+
+
+def evaluate_test_set(gallery_embeddings, gallery_paths: Sequence[str], query_embeddings, query_names: Sequence[str],
+                      ground_truth, results_path=None, key: str = "patent_positives", device=None):
+    """The notebook's "Test" cell end to end (retrieval.ipynb:190-507): ground-truth JSON (path or dict) + cached
+    gallery embeddings -> exact full-ranking metrics on the GPU -> the reference's results JSON (optional).
+    Queries missing from the ground truth are skipped, as in the notebook."""
+    from . import io as pio
+    gt = pio.load_ground_truth(ground_truth) if not isinstance(ground_truth, dict) else ground_truth
+    keep, off, items, n_tot = pio.positives_csr(gt, query_names, gallery_paths, key=key)
+    device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+    q = torch.as_tensor(np.asarray(query_embeddings), dtype=torch.float32)[keep].to(device)
+    g = torch.as_tensor(np.asarray(gallery_embeddings), dtype=torch.float32).to(device)
+    means, per_query = full_ranking_metrics(q, g, torch.from_numpy(off), torch.from_numpy(items),
+                                            n_pos_total=torch.from_numpy(n_tot), metric="cosine")
+    names = ops.metric_names((5, 10, 20))
+    res = (pio.save_evaluation_results(results_path, per_query, names) if results_path is not None
+           else pio.evaluation_results(per_query, names))
+    return res

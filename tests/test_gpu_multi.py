@@ -48,7 +48,6 @@ gen = torch.Generator().manual_seed(4)
 items = torch.randint(0, N, (Ql * 3,), generator=gen).to(dev)
 off = torch.arange(0, Ql * 3 + 1, 3, dtype=torch.int64, device=dev)
 for grouped in (True, False):
-    want = full_ranking_ap(qp, pts, off, items, grouped_ties=grouped, group=None) if False else None
     single_keys = ops.pair_keys(qp, pts, off, items, 1.0, "hyperbolic")
     c1, b1 = ops.rank_count(qp, pts, off, items, single_keys, 1.0, "hyperbolic")
     want = ops.ap_from_counts(off, items, single_keys, c1, b1, N, grouped_ties=grouped)

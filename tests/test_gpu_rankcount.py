@@ -139,3 +139,56 @@ def test_cosine_full_ranking_ap_matches_oracle_notebook_ap():
     assert bool(valid.bool().all())
     np.testing.assert_allclose(ap.cpu().numpy(), np.array(want), rtol=0, atol=2e-3)
     assert abs(float(ap.mean()) - float(np.mean(want))) < 2e-4
+
+
+def test_full_ranking_metric_suite_matches_notebook_loops(tmp_path):
+    """Every metric of the notebook's evaluation cell from rank counts == the notebook loops (oracle restatement,
+    pinned to the notebook's own code by the ref_nb_* goldens) over the fully sorted lists; plus the results JSON."""
+    import json
+    from patent_image_retrieval_b200 import evaluation, io as pio
+    Q, N, D = 40, 700, 64
+    g = torch.Generator().manual_seed(11)
+    gal = torch.randn(N, D, generator=g)
+    qry = torch.randn(Q, D, generator=g)
+    gal[9] = gal[4]                                                # a tie: lower index first
+    gallery_paths = [f"/gallery/p{i // 3}/img_{i}.png" for i in range(N)]
+    query_names = [f"/queries/q_{i}.png" for i in range(Q)]
+    gt = {}
+    for i in range(Q):
+        if i == 7:
+            continue                                              # no ground truth: skipped
+        ids = torch.randint(0, N, (int(torch.randint(1, 6, (1,), generator=g)),), generator=g).tolist()
+        if i % 5 == 0:
+            ids += [4, 9]
+        names = [f"img_{j}.png" for j in ids] + (["not_in_gallery.png"] if i % 4 == 0 else [])
+        gt[f"q_{i}.png"] = {"patent_positives": names}
+    (tmp_path / "gt.json").write_text(json.dumps(gt))
+    res = evaluation.evaluate_test_set(gal.numpy(), gallery_paths, qry.numpy(), query_names, tmp_path / "gt.json",
+                                       results_path=tmp_path / "results" / "evaluation_results_test.json")
+    sim = retrieval.cosine_similarity(qry.double().numpy(), gal.double().numpy())
+    keep = [i for i in range(Q) if i != 7]
+    ranked = [np.lexsort((np.arange(N), -sim[i])).tolist() for i in keep]
+    row_of = {f"img_{j}.png": j for j in range(N)}
+    want = {"mrr": [], "ap": [], "ndcg": []}
+    for k in (5, 10, 20):
+        want.update({f"mrr@{k}": [], f"precision@{k}": [], f"recall@{k}": []})
+    for r, i in zip(ranked, keep):
+        names = set(gt[f"q_{i}.png"]["patent_positives"])
+        pos = {row_of.get(n, N + 1000 + hash(n) % 1000) for n in names}      # missing names never match a row
+        assert len(pos) == len(names)
+        want["mrr"].append(retrieval.mrr_at_k(r, pos, N))
+        want["ap"].append(retrieval.average_precision_ranked(r, pos))
+        want["ndcg"].append(retrieval.ndcg_ranked(r, pos))
+        for k in (5, 10, 20):
+            want[f"mrr@{k}"].append(retrieval.mrr_at_k(r, pos, k))
+            want[f"precision@{k}"].append(retrieval.precision_at_k(r, pos, k))
+            want[f"recall@{k}"].append(retrieval.recall_at_k(r, pos, k))
+    qw = res["query_wise_metrics"]
+    pairs = [("reciprocal_ranks", "mrr"), ("reciprocal_ranks@5", "mrr@5"), ("reciprocal_ranks@20", "mrr@20"),
+             ("ap_scores", "ap"), ("ndcg_scores", "ndcg"), ("recall_5", "recall@5"), ("recall_10", "recall@10"),
+             ("recall_20", "recall@20"), ("precision_5", "precision@5"), ("precision_10", "precision@10"),
+             ("precision_20", "precision@20")]
+    for js_name, name in pairs:
+        np.testing.assert_allclose(qw[js_name], want[name], rtol=1e-12, atol=1e-15, err_msg=name)
+    assert res["summary_metrics"]["mAP"] == pytest.approx(np.mean(want["ap"]), rel=1e-12)
+    assert json.load(open(tmp_path / "results" / "evaluation_results_test.json")) == res
