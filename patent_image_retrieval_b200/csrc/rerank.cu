@@ -146,11 +146,12 @@ rerank_kernel(const float* __restrict__ q32, const float* __restrict__ g32, int6
 #pragma unroll
         for (int ii = 0; ii < CH; ++ii) {
           const int j = (i0 + ii) * 32 + lane;
-          b[t][ii] = (val[t] && j < nvec) ? __ldg(g[t] + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+          b[t][ii] = (i0 + ii < NV && val[t] && j < nvec) ? __ldg(g[t] + j) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
 #pragma unroll
       for (int ii = 0; ii < CH; ++ii) {
-        const int i = i0 + ii;
+        const int i = i0 + ii < NV ? i0 + ii : NV - 1;      // NV = 6: the last chunk is half empty (b == 0 there,
+        if (i0 + ii >= NV) continue;                        // and the compile-time guard keeps qv[] in range)
 #pragma unroll
         for (int t = 0; t < PASS; ++t) {
           const float4 bb = b[t][ii];
@@ -360,24 +361,32 @@ rerank_wide_kernel(const float* __restrict__ q32, const float* __restrict__ g32,
     double sacc[PASS], yacc[PASS];
 #pragma unroll
     for (int t = 0; t < PASS; ++t) { sacc[t] = 0.0; yacc[t] = 0.0; }
+    constexpr int CH = NV < 4 ? NV : 4;          // all loads of a chunk are issued before their first use
 #pragma unroll
-    for (int i = 0; i < NV; ++i) {
-      const int j = i * 32 + lane;
-      if (j < nvec) {
-        float4 b[PASS];
+    for (int i0 = 0; i0 < NV; i0 += CH) {
+      float4 b[PASS][CH];
 #pragma unroll
-        for (int t = 0; t < PASS; ++t) b[t] = __ldg(g[t] + j);
+      for (int t = 0; t < PASS; ++t)
+#pragma unroll
+        for (int ii = 0; ii < CH; ++ii) {
+          const int j = (i0 + ii) * 32 + lane;
+          b[t][ii] = (i0 + ii < NV && val[t] && j < nvec) ? __ldg(g[t] + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+      for (int ii = 0; ii < CH; ++ii) {
+        const int i = i0 + ii < NV ? i0 + ii : NV - 1;
+        if (i0 + ii >= NV) continue;
 #pragma unroll
         for (int t = 0; t < PASS; ++t) {
+          const float4 bb = b[t][ii];
           if (metric == HYPRET_METRIC_HYPERBOLIC) {
-            const float e0 = qv[i].x - b[t].x, e1 = qv[i].y - b[t].y, e2 = qv[i].z - b[t].z, e3 = qv[i].w - b[t].w;
+            const float e0 = qv[i].x - bb.x, e1 = qv[i].y - bb.y, e2 = qv[i].z - bb.z, e3 = qv[i].w - bb.w;
             sacc[t] += (double)e0 * e0 + (double)e1 * e1 + (double)e2 * e2 + (double)e3 * e3;
           } else {
-            sacc[t] += (double)qv[i].x * b[t].x + (double)qv[i].y * b[t].y + (double)qv[i].z * b[t].z +
-                       (double)qv[i].w * b[t].w;
+            sacc[t] += (double)qv[i].x * bb.x + (double)qv[i].y * bb.y + (double)qv[i].z * bb.z +
+                       (double)qv[i].w * bb.w;
           }
-          yacc[t] += (double)b[t].x * b[t].x + (double)b[t].y * b[t].y + (double)b[t].z * b[t].z +
-                     (double)b[t].w * b[t].w;
+          yacc[t] += (double)bb.x * bb.x + (double)bb.y * bb.y + (double)bb.z * bb.z + (double)bb.w * bb.w;
         }
       }
     }

@@ -29,7 +29,7 @@ def _compare_topk(idx_gpu, d_gpu, d64_full, k):
     return n_tie_rows
 
 
-@pytest.mark.parametrize("d,c", [(512, 1.0), (2048, 1.0), (128, 0.5)])
+@pytest.mark.parametrize("d,c", [(512, 1.0), (2048, 1.0), (128, 0.5), (768, 1.0), (640, 1.0), (1024, 2.0)])
 def test_hyperbolic_search_matches_oracle(d, c):
     Q, N, k = 96, 6000, 10
     u = synth.gaussian_features(Q, d, seed=1)
