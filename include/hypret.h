@@ -183,15 +183,31 @@ int hypret_mobius_epilogue(const float* mx, int64_t n, int d, const float* xsq, 
 int hypret_pairdist(const float* a, const float* p, int64_t n, int64_t m, int d, float c, float* out, void* stream);
 
 /* Backward of hypret_pairdist (the reference differentiates through ~40 elementwise autograd
- * nodes per pair, src/train.py:1846).  Given grad_out = dL/dD [n,m] and the forward matrix dmat:
+ * nodes per pair, src/train.py:1846).  Given grad_out = dL/dD [n,m] and the forward matrix dmat, ONE fp32 pass:
  *   w_out [n,m]              W (see csrc/pairdist.cu)
  *   row_sum [n]              sum_j W_ij (1 + c s_ij / alpha_i)
- *   col_partial [n_partial,m]  partial column sums of W_ij (1 + c s_ij / beta_j); sum over dim 0
+ *   col_partial [n_partial,m]  partial column sums of W_ij (1 + c s_ij / beta_j), one row per 32 matrix rows:
+ *                            n_partial >= ceil(n/32); sum over dim 0
  * so that  dA = a * row_sum[:,None] - W P,  dP = p * col_sum[:,None] - W^T A  (two plain GEMMs
  * left to the caller).  asq / psq = squared norms of the rows of a / p. */
 int hypret_pairdist_bwd(const float* grad_out, const float* dmat, const float* asq, const float* psq, int64_t n,
                         int64_t m, float c, float* w_out, float* row_sum, float* col_partial, int n_partial,
                         void* stream);
+
+/* In-batch InfoNCE over the distance matrix, forward and backward, without torch passes over [n,m]
+ * (src/train.py:1832-1844 rows only; 2304-2334 symmetric).  sim = -D * inv_tau.
+ * hypret_pairdist_ce_fwd: dmat [n,m] = hypret_pairdist with an fp32 arccosh tail (training accuracy), row_lse [n] =
+ *   logsumexp_j sim_ij, and (want_col_lse) col_lse [m] = logsumexp_i sim_ij; scratch [2*n_part*m] fp32.  The loss is
+ *   mean_i(row_lse_i - sim_ii) (+ mean_j(col_lse_j - sim_jj), halved) -- O(n) work left to the caller.
+ * hypret_pairdist_ce_bwd: like hypret_pairdist_bwd, but the upstream gradient is formed on the fly:
+ *   g_ij = -(gs * inv_tau / n) [ w_rows (exp(sim_ij - row_lse_i) - [i==j]) + w_cols (exp(sim_ij - col_lse_j) - [i==j]) ]
+ *   with gs = *grad_scale (device scalar, NULL = 1).  col_partial [ceil(n/32), m]; row_sum [n]. */
+int hypret_pairdist_ce_fwd(const float* a, const float* p, int64_t n, int64_t m, int d, float c, float inv_tau,
+                           int want_col_lse, float* dmat, float* row_lse, float* col_lse, float* scratch,
+                           int n_part, void* stream);
+int hypret_pairdist_ce_bwd(const float* dmat, const float* asq, const float* psq, int64_t n, int64_t m, float c,
+                           const float* row_lse, const float* col_lse, float inv_tau, float w_rows, float w_cols,
+                           const float* grad_scale, float* w_out, float* row_sum, float* col_partial, void* stream);
 
 /* Metrics of ranked lists, restating the per-query loops of notebooks/retrieval.ipynb:310-324
  * (MRR@k, Precision@k), :411-420 (AP), :430-437 (nDCG), :439-443 (Recall@k), :446-456 (means).

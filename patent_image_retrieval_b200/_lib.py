@@ -65,6 +65,10 @@ SIGNATURES = {
     "hypret_pairdist": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int, c_float, c_void_p, c_void_p]),
     "hypret_pairdist_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_float, c_void_p,
                                     c_void_p, c_void_p, c_int, c_void_p]),
+    "hypret_pairdist_ce_fwd": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int, c_float, c_float, c_int, c_void_p,
+                                       c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
+    "hypret_pairdist_ce_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_float, c_void_p, c_void_p,
+                                       c_float, c_float, c_float, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "hypret_retrieval_metrics": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p, POINTER(c_int32),
                                          c_int, c_void_p, c_void_p, c_void_p]),
     "hypret_ap_full": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p,

@@ -163,6 +163,36 @@ int hypret_pairdist_bwd(const float* grad_out, const float* dmat, const float* a
                                     static_cast<cudaStream_t>(stream));
 }
 
+int hypret_pairdist_ce_fwd(const float* a, const float* p, int64_t n, int64_t m, int d, float c, float inv_tau,
+                           int want_col_lse, float* dmat, float* row_lse, float* col_lse, float* scratch,
+                           int n_part, void* stream) {
+  if (n < 0 || m < 0 || d < 4 || (d & 3) || !(c > 0.f) || !(inv_tau > 0.f) || n_part < 1 || n_part > 65535)
+    return HYPRET_EINVAL;
+  if (n == 0 || m == 0) return HYPRET_OK;
+  if (a == nullptr || p == nullptr || dmat == nullptr || row_lse == nullptr || !aligned16(a) || !aligned16(p) ||
+      !aligned16(dmat))
+    return HYPRET_EINVAL;
+  if (want_col_lse && (col_lse == nullptr || scratch == nullptr)) return HYPRET_EINVAL;
+  int rc = check_device();
+  if (rc != HYPRET_OK) return rc;
+  return hypret_launch_pairdist_ce_fwd(a, p, n, m, d, c, inv_tau, want_col_lse, dmat, row_lse, col_lse, scratch, n_part,
+                                       static_cast<cudaStream_t>(stream));
+}
+
+int hypret_pairdist_ce_bwd(const float* dmat, const float* asq, const float* psq, int64_t n, int64_t m, float c,
+                           const float* row_lse, const float* col_lse, float inv_tau, float w_rows, float w_cols,
+                           const float* grad_scale, float* w_out, float* row_sum, float* col_partial, void* stream) {
+  if (n < 0 || m < 0 || !(c > 0.f) || !(inv_tau > 0.f)) return HYPRET_EINVAL;
+  if (n == 0 || m == 0) return HYPRET_OK;
+  if (dmat == nullptr || asq == nullptr || psq == nullptr || row_lse == nullptr || w_out == nullptr ||
+      row_sum == nullptr || col_partial == nullptr || (w_cols != 0.f && col_lse == nullptr))
+    return HYPRET_EINVAL;
+  int rc = check_device();
+  if (rc != HYPRET_OK) return rc;
+  return hypret_launch_pairdist_ce_bwd(dmat, asq, psq, n, m, c, row_lse, col_lse, inv_tau, w_rows, w_cols, grad_scale,
+                                       w_out, row_sum, col_partial, static_cast<cudaStream_t>(stream));
+}
+
 int hypret_retrieval_metrics(const int64_t* ranked, int64_t Q, int K, const int64_t* pos_offsets,
                              const int64_t* pos_items, const int32_t* n_pos_total, const int32_t* ks_host, int n_ks,
                              double* per_query, double* means, void* stream) {

@@ -21,6 +21,9 @@ namespace {
 constexpr int PD_TILE = 64;
 constexpr int PD_K = 16;
 
+// FAST_TAIL: arccosh tail in fp32 (training path: ~3e-7 relative, next to the ~1e-6 of the fp32 accumulation
+// itself); otherwise fp64 (evaluation path; hypret_rank_count reproduces that arithmetic bit for bit).
+template <bool FAST_TAIL>
 __global__ void __launch_bounds__(256)
 pairdist_kernel(const float* __restrict__ a, const float* __restrict__ p, int64_t n, int64_t m, int d, float c,
                 float* __restrict__ out) {
@@ -68,6 +71,31 @@ pairdist_kernel(const float* __restrict__ a, const float* __restrict__ p, int64_
       for (int s = 0; s < 4; ++s) np_[s] = fmaf(pv[s], pv[s], np_[s]);
     }
   }
+  if (FAST_TAIL) {
+    const float rs = 1.0f / sqrtf(c);
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const int64_t i = i0 + ty * 4 + r;
+      if (i >= n) continue;
+      const float al = 1.0f - c * na[r];
+      float o[4];
+#pragma unroll
+      for (int s = 0; s < 4; ++s) {
+        const float be = 1.0f - c * np_[s];
+        const float t = 2.0f * c * acc[r][s] / (al * be);
+        o[s] = log1pf(t + sqrtf(t * (t + 2.0f))) * rs;
+      }
+      const int64_t j = j0 + tx * 4;
+      if (j + 3 < m && (m & 3) == 0) {
+        *reinterpret_cast<float4*>(out + i * m + j) = make_float4(o[0], o[1], o[2], o[3]);
+      } else {
+#pragma unroll
+        for (int s = 0; s < 4; ++s)
+          if (j + s < m) out[i * m + j + s] = o[s];
+      }
+    }
+    return;
+  }
   const double cc = (double)c, rs = 1.0 / sqrt(cc);
 #pragma unroll
   for (int r = 0; r < 4; ++r) {
@@ -87,56 +115,145 @@ pairdist_kernel(const float* __restrict__ a, const float* __restrict__ p, int64_
 
 // Backward of the distance matrix (reference: autograd through ~40 elementwise ops per pair,
 // /root/reference/src/train.py:1846).  With g = dL/dD and, for the pair (i,j),
-//   alpha = 1 - c|a_i|^2, beta = 1 - c|p_j|^2, z = cosh(sqrt(c) d), s = (z - 1) alpha beta / (2c),
-//   w = g * 4 sqrt(c) / (alpha beta sinh(sqrt(c) d))
+//   alpha = 1 - c|a_i|^2, beta = 1 - c|p_j|^2, x = sqrt(c) d, h = sinh(x/2), s = h^2 alpha beta / c (= |a_i - p_j|^2),
+//   sinh x = 2 h sqrt(1 + h^2),  w = g * 4 sqrt(c) / (alpha beta sinh x)
 // the gradients are  dA_i = a_i * sum_j w (1 + c s / alpha) - (W P)_i  and
 //                    dP_j = p_j * sum_i w (1 + c s / beta)  - (W^T A)_j   (SURVEY.md 7.4).
-// Kernel A (one warp per row, coalesced along j) writes W and the row sums; kernel B (one
-// thread per column, coalesced across the warp) re-reads W, D for the column sums.  The two
-// dense products W P and W^T A are left to the caller (plain GEMMs).
+// ONE pass over the matrix (fp32 math: one sinhf and one sqrtf per element; HBM-bound): a CTA owns BW_ROWS
+// rows and walks all columns in blocks of 256 -- a thread owns one column of the block (coalesced rows), keeps
+// the BW_ROWS row accumulators in registers and the column accumulator of the block in one register.  Row sums
+// are reduced in a fixed order at the end (deterministic); column sums leave as one partial row per CTA.
+// CE: the upstream gradient is not read from memory but formed on the fly from the row / column log-sum-exps of
+// sim = -D / tau (the in-batch InfoNCE losses of src/train.py:1832-1844 and 2304-2334):
+//   g_ij = -(gs / tau / n) * [ wr (exp(sim_ij - lse_r[i]) - [i==j]) + wc (exp(sim_ij - lse_c[j]) - [i==j]) ].
+// The two dense products W P and W^T A are left to the caller (plain GEMMs).
+constexpr int BW_ROWS = 32;
+
+template <bool CE>
 __global__ void __launch_bounds__(256)
-pairdist_bwd_rows_kernel(const float* __restrict__ g, const float* __restrict__ dmat, const float* __restrict__ asq,
-                         const float* __restrict__ psq, int64_t n, int64_t m, float c, float* __restrict__ w_out,
-                         float* __restrict__ row_sum) {
+pairdist_bwd_fused_kernel(const float* __restrict__ g, const float* __restrict__ dmat, const float* __restrict__ asq,
+                          const float* __restrict__ psq, int64_t n, int64_t m, float c, const float* __restrict__ row_lse,
+                          const float* __restrict__ col_lse, float inv_tau, float wr, float wc,
+                          const float* __restrict__ grad_scale, float* __restrict__ w_out,
+                          float* __restrict__ row_sum, float* __restrict__ col_partial) {
+  __shared__ float s_al[BW_ROWS], s_lse[BW_ROWS];
+  __shared__ float s_red[BW_ROWS][8];
+  const int64_t i0 = (int64_t)blockIdx.x * BW_ROWS;
+  const int rows = (int)(n - i0 < BW_ROWS ? n - i0 : BW_ROWS);
+  if (threadIdx.x < BW_ROWS) {
+    const bool ok = threadIdx.x < rows;
+    s_al[threadIdx.x] = ok ? 1.0f - c * asq[i0 + threadIdx.x] : 1.0f;
+    s_lse[threadIdx.x] = (CE && ok) ? row_lse[i0 + threadIdx.x] : 0.f;
+  }
+  __syncthreads();
+  const float sc = sqrtf(c), four_sc = 4.0f * sc, half_sc = 0.5f * sc;
+  const float gsc = CE ? -(grad_scale != nullptr ? grad_scale[0] : 1.0f) * inv_tau / (float)n : 0.f;
+  float racc[BW_ROWS];
+#pragma unroll
+  for (int r = 0; r < BW_ROWS; ++r) racc[r] = 0.f;
+  for (int64_t j = threadIdx.x; j < ((m + 255) / 256) * 256; j += 256) {
+    const bool jok = j < m;
+    const float be = jok ? 1.0f - c * psq[j] : 1.0f;
+    const float lse_c = (CE && jok && wc != 0.f) ? col_lse[j] : 0.f;
+    float cacc = 0.f;
+#pragma unroll
+    for (int r = 0; r < BW_ROWS; ++r) {
+      if (r < rows && jok) {
+        const int64_t o = (i0 + r) * m + j;
+        const float dd = dmat[o];
+        float gg;
+        if (CE) {
+          const float sim = -dd * inv_tau;
+          const float diag = (i0 + r == j) ? 1.0f : 0.0f;
+          gg = wr * (expf(sim - s_lse[r]) - diag);
+          if (wc != 0.f) gg += wc * (expf(sim - lse_c) - diag);
+          gg *= gsc;
+        } else {
+          gg = g[o];
+        }
+        const float al = s_al[r];
+        const float h = sinhf(half_sc * dd);
+        const float h2 = h * h;
+        const float sh = fmaxf(2.0f * h * sqrtf(1.0f + h2), 1e-15f);
+        const float ab = al * be;
+        const float w = gg * four_sc / (ab * sh);
+        w_out[o] = w;
+        const float cs = h2 * ab;                 // c * s
+        racc[r] += w * (1.0f + cs / al);
+        cacc += w * (1.0f + cs / be);
+      }
+    }
+    if (jok) col_partial[(int64_t)blockIdx.x * m + j] = cacc;
+  }
+  // row sums: warp tree, then the 8 warps of the CTA in a fixed order
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int r = 0; r < BW_ROWS; ++r) {
+    const float v = warp_sum(racc[r]);
+    if (lane == 0) s_red[r][warp] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < rows) {
+    float v = 0.f;
+#pragma unroll
+    for (int w8 = 0; w8 < 8; ++w8) v += s_red[threadIdx.x][w8];
+    row_sum[i0 + threadIdx.x] = v;
+  }
+}
+
+// Log-sum-exp of sim = -D / tau along rows (one warp per row) and along columns (thread per column over a block of
+// rows -> partial (max, sum) pairs, combined by a second tiny kernel).  Online max/sum in fp32.
+__global__ void __launch_bounds__(256)
+lse_rows_kernel(const float* __restrict__ dmat, int64_t n, int64_t m, float inv_tau, float* __restrict__ row_lse) {
   const int lane = threadIdx.x & 31;
   const int64_t i = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
   if (i >= n) return;
-  const double cc = (double)c, sc = sqrt(cc);
-  const double al = 1.0 - cc * (double)asq[i];
-  double acc = 0.0;
+  float mx = -INFINITY, sm = 0.f;
   for (int64_t j = lane; j < m; j += 32) {
-    const double be = 1.0 - cc * (double)psq[j];
-    const double x = sc * (double)dmat[i * m + j];
-    const double sh = fmax(sinh(x), 1e-15);
-    const double hh = sinh(0.5 * x);                       // cosh(x) - 1 = 2 sinh^2(x/2), no cancellation
-    const double s = hh * hh * al * be / cc;
-    const double w = (double)g[i * m + j] * 4.0 * sc / (al * be * sh);
-    w_out[i * m + j] = (float)w;
-    acc += w * (1.0 + cc * s / al);
+    const float z = -dmat[i * m + j] * inv_tau;
+    if (z > mx) { sm = sm * expf(mx - z) + 1.0f; mx = z; }
+    else sm += expf(z - mx);
   }
-  acc = warp_sum(acc);
-  if (lane == 0) row_sum[i] = (float)acc;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float omx = __shfl_xor_sync(0xffffffffu, mx, o), osm = __shfl_xor_sync(0xffffffffu, sm, o);
+    const float nm = fmaxf(mx, omx);
+    sm = (mx == -INFINITY ? 0.f : sm * expf(mx - nm)) + (omx == -INFINITY ? 0.f : osm * expf(omx - nm));
+    mx = nm;
+  }
+  if (lane == 0) row_lse[i] = mx + logf(sm);
 }
 
 __global__ void __launch_bounds__(256)
-pairdist_bwd_cols_kernel(const float* __restrict__ w, const float* __restrict__ dmat, const float* __restrict__ asq,
-                         const float* __restrict__ psq, int64_t n, int64_t m, float c, int64_t rows_per_block,
-                         float* __restrict__ col_partial) {
-  const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+lse_cols_partial_kernel(const float* __restrict__ dmat, int64_t n, int64_t m, float inv_tau, int64_t rows_per_block,
+                        float* __restrict__ part_max, float* __restrict__ part_sum) {
+  const int64_t j = (int64_t)blockIdx.x * 256 + threadIdx.x;
   if (j >= m) return;
-  const int64_t i0 = (int64_t)blockIdx.y * rows_per_block;
-  const int64_t i1 = i0 + rows_per_block < n ? i0 + rows_per_block : n;
-  const double cc = (double)c, sc = sqrt(cc);
-  const double be = 1.0 - cc * (double)psq[j];
-  double acc = 0.0;
-  for (int64_t i = i0; i < i1; ++i) {
-    const double al = 1.0 - cc * (double)asq[i];
-    const double x = sc * (double)dmat[i * m + j];
-    const double hh = sinh(0.5 * x);
-    const double s = hh * hh * al * be / cc;
-    acc += (double)w[i * m + j] * (1.0 + cc * s / be);
+  const int64_t r0 = (int64_t)blockIdx.y * rows_per_block;
+  const int64_t r1 = r0 + rows_per_block < n ? r0 + rows_per_block : n;
+  float mx = -INFINITY, sm = 0.f;
+  for (int64_t i = r0; i < r1; ++i) {
+    const float z = -dmat[i * m + j] * inv_tau;
+    if (z > mx) { sm = sm * expf(mx - z) + 1.0f; mx = z; }
+    else sm += expf(z - mx);
   }
-  col_partial[(int64_t)blockIdx.y * m + j] = (float)acc;
+  part_max[(int64_t)blockIdx.y * m + j] = mx;
+  part_sum[(int64_t)blockIdx.y * m + j] = sm;
+}
+
+__global__ void __launch_bounds__(256)
+lse_cols_combine_kernel(const float* __restrict__ part_max, const float* __restrict__ part_sum, int64_t m, int n_part,
+                        float* __restrict__ col_lse) {
+  const int64_t j = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  if (j >= m) return;
+  float mx = -INFINITY;
+  for (int b = 0; b < n_part; ++b) mx = fmaxf(mx, part_max[(int64_t)b * m + j]);
+  float sm = 0.f;
+  for (int b = 0; b < n_part; ++b) {
+    const float pm = part_max[(int64_t)b * m + j];
+    if (pm > -INFINITY) sm += part_sum[(int64_t)b * m + j] * expf(pm - mx);
+  }
+  col_lse[j] = mx + logf(sm);
 }
 
 }  // namespace
@@ -145,12 +262,49 @@ int hypret_launch_pairdist_bwd(const float* g, const float* dmat, const float* a
                                int64_t m, float c, float* w_out, float* row_sum, float* col_partial, int n_partial,
                                cudaStream_t stream) {
   if (n == 0 || m == 0) return HYPRET_OK;
-  pairdist_bwd_rows_kernel<<<(unsigned)((n + 7) / 8), 256, 0, stream>>>(g, dmat, asq, psq, n, m, c, w_out, row_sum);
+  if ((int64_t)n_partial * BW_ROWS < n) return HYPRET_EINVAL;     // one partial row of column sums per CTA of 32 rows
+  const unsigned grid = (unsigned)((n + BW_ROWS - 1) / BW_ROWS);
+  pairdist_bwd_fused_kernel<false><<<grid, 256, 0, stream>>>(g, dmat, asq, psq, n, m, c, nullptr, nullptr, 0.f, 0.f,
+                                                            0.f, nullptr, w_out, row_sum, col_partial);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return (int)e;
-  const int64_t rpb = (n + n_partial - 1) / n_partial;
-  dim3 grid((unsigned)((m + 255) / 256), (unsigned)n_partial);
-  pairdist_bwd_cols_kernel<<<grid, 256, 0, stream>>>(w_out, dmat, asq, psq, n, m, c, rpb, col_partial);
+  if ((int64_t)n_partial > (int64_t)grid)      // partial rows no CTA writes must read as zero
+    e = cudaMemsetAsync(col_partial + (int64_t)grid * m, 0, ((int64_t)n_partial - grid) * m * sizeof(float), stream);
+  return (int)e;
+}
+
+int hypret_launch_pairdist_ce_fwd(const float* a, const float* p, int64_t n, int64_t m, int d, float c, float inv_tau,
+                                  int want_cols, float* dmat, float* row_lse, float* col_lse, float* scratch,
+                                  int n_part, cudaStream_t stream) {
+  if (n == 0 || m == 0) return HYPRET_OK;
+  dim3 grid((unsigned)((m + PD_TILE - 1) / PD_TILE), (unsigned)((n + PD_TILE - 1) / PD_TILE));
+  if (grid.y > 65535) return HYPRET_EUNSUPPORTED;
+  pairdist_kernel<true><<<grid, 256, 0, stream>>>(a, p, n, m, d, c, dmat);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return (int)e;
+  lse_rows_kernel<<<(unsigned)((n + 7) / 8), 256, 0, stream>>>(dmat, n, m, inv_tau, row_lse);
+  e = cudaGetLastError();
+  if (e != cudaSuccess) return (int)e;
+  if (want_cols) {
+    const int64_t rpb = (n + n_part - 1) / n_part;
+    dim3 g2((unsigned)((m + 255) / 256), (unsigned)n_part);
+    lse_cols_partial_kernel<<<g2, 256, 0, stream>>>(dmat, n, m, inv_tau, rpb, scratch, scratch + (int64_t)n_part * m);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return (int)e;
+    lse_cols_combine_kernel<<<(unsigned)((m + 255) / 256), 256, 0, stream>>>(scratch, scratch + (int64_t)n_part * m, m,
+                                                                            n_part, col_lse);
+  }
+  return (int)cudaGetLastError();
+}
+
+int hypret_launch_pairdist_ce_bwd(const float* dmat, const float* asq, const float* psq, int64_t n, int64_t m, float c,
+                                  const float* row_lse, const float* col_lse, float inv_tau, float wr, float wc,
+                                  const float* grad_scale, float* w_out, float* row_sum, float* col_partial,
+                                  cudaStream_t stream) {
+  if (n == 0 || m == 0) return HYPRET_OK;
+  const unsigned grid = (unsigned)((n + BW_ROWS - 1) / BW_ROWS);
+  pairdist_bwd_fused_kernel<true><<<grid, 256, 0, stream>>>(nullptr, dmat, asq, psq, n, m, c, row_lse, col_lse, inv_tau,
+                                                           wr, wc, grad_scale, w_out, row_sum, col_partial);
   return (int)cudaGetLastError();
 }
 
@@ -159,6 +313,6 @@ int hypret_launch_pairdist(const float* a, const float* p, int64_t n, int64_t m,
   if (n == 0 || m == 0) return HYPRET_OK;
   dim3 grid((unsigned)((m + PD_TILE - 1) / PD_TILE), (unsigned)((n + PD_TILE - 1) / PD_TILE));
   if (grid.y > 65535) return HYPRET_EUNSUPPORTED;
-  pairdist_kernel<<<grid, 256, 0, stream>>>(a, p, n, m, d, c, out);
+  pairdist_kernel<false><<<grid, 256, 0, stream>>>(a, p, n, m, d, c, out);
   return (int)cudaGetLastError();
 }

@@ -322,14 +322,52 @@ def ap_from_counts(pos_offsets: torch.Tensor, pos_items: torch.Tensor, pos_keys:
     return float(mean.item()), ap, valid
 
 
+def pairdist_ce_fwd(a: torch.Tensor, p: torch.Tensor, c: float, inv_tau: float, want_cols: bool):
+    """Distance matrix (fp32 tail) + row / column log-sum-exps of ``-D * inv_tau``.
+    Returns ``(dmat [n,m], row_lse [n], col_lse [m] | None)``."""
+    _need_cuda(a, p)
+    a, p = a.contiguous().float(), p.contiguous().float()
+    n, d = a.shape
+    m = p.shape[0]
+    dmat = torch.empty(n, m, dtype=torch.float32, device=a.device)
+    row_lse = torch.empty(n, dtype=torch.float32, device=a.device)
+    col_lse = torch.empty(m, dtype=torch.float32, device=a.device) if want_cols else None
+    n_part = max(1, min(64, (n + 127) // 128))
+    scratch = torch.empty(2 * n_part * m, dtype=torch.float32, device=a.device) if want_cols else None
+    with torch.cuda.device(a.device):
+        _lib.check(_lib.load().hypret_pairdist_ce_fwd(_ptr(a), _ptr(p), n, m, d, float(c), float(inv_tau),
+                                                      int(bool(want_cols)), _ptr(dmat), _ptr(row_lse), _ptr(col_lse),
+                                                      _ptr(scratch), n_part, _stream()))
+    return dmat, row_lse, col_lse
+
+
+def pairdist_ce_bwd(dmat: torch.Tensor, asq: torch.Tensor, psq: torch.Tensor, c: float, row_lse: torch.Tensor,
+                    col_lse: Optional[torch.Tensor], inv_tau: float, w_rows: float, w_cols: float,
+                    grad_scale: Optional[torch.Tensor] = None):
+    """Backward weights of the in-batch InfoNCE: ``(W [n,m], row_sum [n], col_sum [m])``; the upstream gradient is
+    formed inside the kernel from the log-sum-exps (``grad_scale``: device scalar dL/dloss)."""
+    _need_cuda(dmat, asq, psq, row_lse, col_lse, grad_scale)
+    n, m = dmat.shape
+    w = torch.empty_like(dmat)
+    rs = torch.empty(n, dtype=torch.float32, device=dmat.device)
+    cp = torch.empty((n + 31) // 32, m, dtype=torch.float32, device=dmat.device)
+    gs = grad_scale.reshape(1).contiguous().float() if grad_scale is not None else None
+    with torch.cuda.device(dmat.device):
+        _lib.check(_lib.load().hypret_pairdist_ce_bwd(_ptr(dmat.contiguous()), _ptr(asq.contiguous().float()),
+                                                      _ptr(psq.contiguous().float()), n, m, float(c), _ptr(row_lse),
+                                                      _ptr(col_lse), float(inv_tau), float(w_rows), float(w_cols),
+                                                      _ptr(gs), _ptr(w), _ptr(rs), _ptr(cp), _stream()))
+    return w, rs, cp.sum(dim=0)
+
+
 def pairdist_bwd(grad_out: torch.Tensor, dmat: torch.Tensor, asq: torch.Tensor, psq: torch.Tensor, c: float,
-                 n_partial: int = 32):
+                 n_partial: Optional[int] = None):
     """Weights of the distance-matrix backward: returns ``(W [n,m], row_sum [n], col_sum [m])``."""
     _need_cuda(grad_out, dmat, asq, psq)
     grad_out = grad_out.contiguous().float()
     dmat = dmat.contiguous()
     n, m = dmat.shape
-    n_partial = max(1, min(n_partial, n))
+    n_partial = max((n + 31) // 32, n_partial or 0, 1)
     w = torch.empty_like(dmat)
     rs = torch.empty(n, dtype=torch.float32, device=dmat.device)
     cp = torch.empty(n_partial, m, dtype=torch.float32, device=dmat.device)

@@ -52,18 +52,46 @@ def pairwise_dist(a, p, k):
     return PairwiseDistance.apply(a, p, _c_of(k))
 
 
+class InBatchInfoNCE(torch.autograd.Function):
+    """CE over the rows (``symmetric=False``) or rows and columns (``True``) of ``-D / tau`` with the diagonal as
+    targets, D the n x n Poincare distance matrix -- forward and backward in libhypret.so: no torch softmax /
+    cross-entropy passes over the [n,n] matrix and no upstream-gradient matrix (``hypret_pairdist_ce_fwd/bwd``)."""
+
+    @staticmethod
+    def forward(ctx, a, p, c: float, temperature: float, symmetric: bool):
+        a32, p32 = a.contiguous().float(), p.contiguous().float()
+        if a32.shape != p32.shape:
+            raise ValueError("anchors and positives must have the same shape")
+        inv_tau = 1.0 / float(temperature)
+        d, row_lse, col_lse = ops.pairdist_ce_fwd(a32, p32, c, inv_tau, want_cols=symmetric)
+        diag_sim = -torch.diagonal(d) * inv_tau
+        loss = (row_lse - diag_sim).mean()
+        if symmetric:
+            loss = (loss + (col_lse - diag_sim).mean()) / 2
+        ctx.save_for_backward(a32, p32, d, row_lse, col_lse if symmetric else row_lse)
+        ctx.c, ctx.inv_tau, ctx.symmetric = c, inv_tau, symmetric
+        ctx.in_dtypes = (a.dtype, p.dtype)
+        return loss
+
+    @staticmethod
+    def backward(ctx, grad_loss):
+        a, p, d, row_lse, col_lse = ctx.saved_tensors
+        wr, wc = (0.5, 0.5) if ctx.symmetric else (1.0, 0.0)
+        w, rs, cs = ops.pairdist_ce_bwd(d, ops.row_sqnorm(a), ops.row_sqnorm(p), ctx.c, row_lse,
+                                        col_lse if ctx.symmetric else None, ctx.inv_tau, wr, wc, grad_scale=grad_loss)
+        da = a * rs[:, None] - w @ p          # plain GEMMs (cuBLAS fp32)
+        dp = p * cs[:, None] - w.t() @ a
+        return da.to(ctx.in_dtypes[0]), dp.to(ctx.in_dtypes[1]), None, None, None
+
+
 def in_batch_contrastive_loss(anchors, positives, k, temperature=0.1):
     """The loss inside train_hyperbolic_contrastive (src/train.py:1832-1844): CE over rows."""
-    sim = -pairwise_dist(anchors, positives, k) / temperature
-    return F.cross_entropy(sim, torch.arange(anchors.shape[0], device=sim.device))
+    return InBatchInfoNCE.apply(anchors, positives, _c_of(k), float(temperature), False)
 
 
 def hyperbolic_contrastive_loss(anchor_embeddings, positive_embeddings, k, temperature=0.07):
     """Symmetric InfoNCE in hyperbolic space (src/train.py:2291-2336)."""
-    n = anchor_embeddings.shape[0]
-    similarities = -pairwise_dist(anchor_embeddings, positive_embeddings, k) / temperature
-    labels = torch.arange(n, device=similarities.device)
-    return (F.cross_entropy(similarities, labels) + F.cross_entropy(similarities.t(), labels)) / 2
+    return InBatchInfoNCE.apply(anchor_embeddings, positive_embeddings, _c_of(k), float(temperature), True)
 
 
 def sample_to_prototype_loss(samples, pos_prototypes, neg_prototypes, num_neg_samples, k, margin=0.1,

@@ -1,5 +1,5 @@
 """C5: train_hyp in-batch n x n Poincare distance matrix, forward + backward (BASELINE.json configs[4]).
-GPU: hypret_pairdist + hypret_pairdist_bwd (+ two cuBLAS GEMMs) through train.in_batch_contrastive_loss.
+GPU: hypret_pairdist_ce_fwd + hypret_pairdist_ce_bwd (+ two cuBLAS fp32 GEMMs) through train.in_batch_contrastive_loss.
 CPU: the reference's literal double loop (src/train.py:1833-1840) at its own batch sizes, restated by the oracle."""
 import json
 import sys
@@ -63,4 +63,7 @@ if __name__ == "__main__":
            "cpu_reference_double_loop": [cpu_case(64, 256), cpu_case(128, 256)]}
     c = out["cpu_reference_double_loop"][-1]
     out["cpu_extrapolated_to_n8192_s"] = c["s_fwd_bwd_double_loop"] * (8192 / c["n"]) ** 2
-    print(json.dumps(out, indent=1))
+    for g in out["gpu"]:
+        print(json.dumps({k: (round(v, 4) if isinstance(v, float) else v) for k, v in g.items()}))
+    print(json.dumps({"cpu_reference_double_loop": out["cpu_reference_double_loop"],
+                      "cpu_extrapolated_to_n8192_s": out["cpu_extrapolated_to_n8192_s"]}))
