@@ -85,8 +85,8 @@ typedef struct {
   int32_t pair;       /* 2: CTA pairs (tcgen05 cta_group::2) -- a scheduling unit is a cluster of 2 CTAs and a
                          strip covers 2 consecutive query tiles; 1: single-CTA MMAs            */
   int32_t epi_groups; /* epilogue warpgroups per CTA.  2 (kprime <= 16): a strip owns TWO lists per query, slots
-                         hypret_score_strip's slot and slot+1, one per warpgroup (alternate gallery tiles
-                         of the strip); n_lists already counts both                              */
+                         hypret_score_strip's slot and slot+1, one per warpgroup (the two 128-column halves
+                         of every gallery tile of the strip); n_lists already counts both                              */
 } hypret_score_plan_t;
 
 /* max_ctas: 0 = one CTA per SM; >0 caps the grid (tests use it to force multi-wave schedules).

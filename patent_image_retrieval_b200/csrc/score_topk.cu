@@ -384,10 +384,10 @@ __device__ __forceinline__ void process_chunk(const float (&v)[32], int cbase, R
 // compare-and-shift over the 16 slots (each slot's new value depends only on old values: 16-way ILP, no
 // shared-memory round trip, no rescan for the new worst entry -- it is simply the last slot), and the
 // 16 KB of shared memory the lists used to occupy pays for the pending-hit queue of a SECOND epilogue
-// warpgroup: warpgroup g consumes accumulator g, i.e. every other gallery tile, so each SM sub-partition
-// has two epilogue warps to hide each other's latencies and each warpgroup has two MMA tile times per tile.
+// warpgroup: warpgroup g scans columns [128 g, 128 g + 128) of every gallery tile, so each SM sub-partition
+// has two epilogue warps to hide each other's latencies and a tile leaves the accumulator in half the time.
 // A row therefore owns two lists per strip (slot 2*s+g); the two halves exchange their k'-th best through
-// the same L2 threshold word the strips of a query already share.
+// the same L2 threshold word the strips of a query already share, and a tighter pair bound through shared memory.
 constexpr int RL = 16;
 constexpr int WG_X_BYTES = 2 * TILE_M * 8;   // warpgroup exchange: [2][128] x {strip tag, score bits}
 constexpr int OVF = 64;      // per-thread overflow of the pending queue (local memory; cold phase only)
@@ -559,7 +559,8 @@ score_topk_kernel(const __grid_constant__ CUtensorMap map_q_main, const __grid_c
     }
     for (int a = 0; a < NUM_ACC; ++a) {
       mbar_init(&bars->tmem_full[a], 1);
-      mbar_init(&bars->tmem_empty[a], PAIR ? 2 * NUM_EPI_THREADS : NUM_EPI_THREADS);
+      // every epilogue thread that reads the accumulator arrives: one warpgroup per CTA, or both (k' <= 16)
+      mbar_init(&bars->tmem_empty[a], (PAIR ? 2 : 1) * (KPP == RL ? 2 : 1) * NUM_EPI_THREADS);
     }
     mbar_init(&bars->a_full, 1);
     mbar_init(&bars->a_empty, 1);
@@ -739,8 +740,11 @@ score_topk_kernel(const __grid_constant__ CUtensorMap map_q_main, const __grid_c
     int ovf_i[OVF];
     const int KP = p.kprime;
     const int N = (int)p.N;
-    uint32_t my_phase = 0;                     // parity of tmem_full[wg] for the next tile of this warpgroup
-    uint32_t tile_ctr = 0;                     // running tile count of this CTA == the MMA issuer's accumulator toggle
+    // Both warpgroups work on EVERY tile, warpgroup g on columns [128 g, 128 g + 128): an accumulator is needed
+    // again one MMA tile time after it was filled, so it is the epilogue's LATENCY per tile that must stay below
+    // one tile time -- splitting tiles between the warpgroups (g takes accumulator g) doubled the throughput but
+    // left the latency at 5.1 k cycles against 4.2 k, and the MMA issuer stalled 17 % of the time at C2.
+    uint32_t acc = 0, acc_phase = 0;
     unsigned long long w_acc = 0, t_begin = DEBUG ? clock64() : 0;
     int tot_ins = 0, tot_drain = 0, tot_now = 0;
     for (int step = 0; step < sc.n_steps; ++step) {
@@ -771,20 +775,17 @@ score_topk_kernel(const __grid_constant__ CUtensorMap map_q_main, const __grid_c
       }
       st.thr = fminf(st.thr_list, st.thr_g);
       for (int gt = gt0; gt < gt1; ++gt) {
-        const uint32_t acc = tile_ctr & 1u;
-        tile_ctr += 1;
-        if (acc != (uint32_t)wg) continue;       // the other warpgroup's tile
-        timed_wait<DEBUG>(&bars->tmem_full[acc], my_phase, w_acc, p.wait_mode);
-        my_phase ^= 1;
+        timed_wait<DEBUG>(&bars->tmem_full[acc], acc_phase, w_acc, p.wait_mode);
         tcgen05_fence_after();
-        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * TILE_N;
-        const int col0 = gt * TILE_N;
-        const bool ragged = col0 + TILE_N > N;               // last gallery tile: TMA zero-filled rows
+        constexpr int HALF = TILE_N / 2;          // columns per warpgroup
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * TILE_N + wg * HALF;
+        const int col0 = gt * TILE_N + wg * HALF;
+        const bool ragged = col0 + HALF > N;                 // last gallery tile: TMA zero-filled rows
         float va[32], vb[32];
         __syncwarp();
         tmem_ld_32x32(taddr, va);
 #pragma unroll 1
-        for (int cc = 0; cc < TILE_N / 32; cc += 2) {
+        for (int cc = 0; cc < HALF / 32; cc += 2) {
           tmem_ld_wait(va);
           tmem_ld_32x32(taddr + (cc + 1) * 32, vb);           // next chunk in flight while this one is scanned
           if (ragged) {
@@ -800,7 +801,7 @@ score_topk_kernel(const __grid_constant__ CUtensorMap map_q_main, const __grid_c
           process_chunk_reg(va, col0 + cc * 32, st, qs_addr, qi_addr, ovf_s, ovf_i);
           __syncwarp();                                       // tcgen05.ld/wait are warp-collective
           tmem_ld_wait(vb);
-          if (cc + 2 < TILE_N / 32) tmem_ld_32x32(taddr + (cc + 2) * 32, va);
+          if (cc + 2 < HALF / 32) tmem_ld_32x32(taddr + (cc + 2) * 32, va);
           if (ragged) {
 #pragma unroll
             for (int j = 0; j < 32; ++j)
@@ -819,6 +820,7 @@ score_topk_kernel(const __grid_constant__ CUtensorMap map_q_main, const __grid_c
         tcgen05_fence_before();
         if (PAIR) mbar_arrive_cluster(&bars->tmem_empty[acc], 0);   // the leader waits for both CTAs' epilogues
         else mbar_arrive(&bars->tmem_empty[acc]);
+        if (++acc == NUM_ACC) { acc = 0; acc_phase ^= 1; }
         // the accumulator is released: fold the pending hits in (off the MMA's critical path)
         drain_queue_reg(st, L, KP, qs_addr, qi_addr, ovf_s, ovf_i);
         // exchange thresholds with the query's other lists (other warpgroup, other strips) through L2
