@@ -115,17 +115,22 @@ int hypret_score_strip(const hypret_score_plan_t* plan, int cta, int step, int32
  *             strips start warm: the UNION of a query's lists still contains its global
  *             top-kprime, but a single list is no longer the top-kprime of its own strip.
  *             With NULL every list is exactly its strip's top-kprime (slower; tests).
+ *   list_count  [Q] int32 out, or NULL.  Given: list slots are handed out per query in arrival order (and empty
+ *             lists take none), so the lists of query q are exactly its first list_count[q] slots and nothing
+ *             else of cand_* is written or needs clearing; hypret_rerank / hypret_cand_select take the same array.
+ *             NULL: slot = the strip's slot of hypret_score_strip, unwritten slots read as empty (idx -1).
  *   debug_scores  NULL, or [Q,N] fp32 that receives every surrogate score (tests only)
  * 1 <= kprime <= 64. */
 int hypret_score_topk(const void* q_op, int64_t Q, const void* g_op, int64_t N, int d, int kprime, int n_lists,
                       int max_ctas, int min_lists, float* cand_score, int32_t* cand_idx, uint32_t* thr_workspace,
-                      float* debug_scores, void* stream);
+                      int32_t* list_count, float* debug_scores, void* stream);
 
 /* Candidate merge + exact rerank.  For each query: keep the kprime best of its
  * n_lists*kprime candidates by surrogate score, recompute their distance exactly from the
  * fp32 rows (differences formed explicitly, fp64 accumulation, arccosh closed form ==
  * pmath.dist, src/train.py:3259; or the cosine similarity, retrieval.ipynb:368), sort
  * (ascending distance / descending similarity, ties -> lower index) and emit the first k.
+ *   list_count [Q] int32 from hypret_score_topk, or NULL (all n_lists slots are scanned)
  *   q32 [Q,d], g32 [N,d] fp32   (hyperbolic: points on the ball; cosine: raw features)
  *   out_score [Q,k] fp32, out_idx [Q,k] int64 (+ idx_offset; -1 when fewer than k rows)
  *   out_margin [Q] fp32 or NULL: (smallest surrogate a NON-candidate can have) - (exact surrogate of the
@@ -135,8 +140,8 @@ int hypret_score_topk(const void* q_op, int64_t Q, const void* g_op, int64_t N, 
  * k <= n_lists*kprime): one CTA per query; requires lists built WITHOUT threshold sharing and
  * min_lists >= 3 so that the union of a query's lists contains its top-k (certified by out_margin). */
 int hypret_rerank(const float* q32, const float* g32, int64_t Q, int64_t N, int d, float c, int metric,
-                  const float* cand_score, const int32_t* cand_idx, int n_lists, int kprime, int k,
-                  int64_t idx_offset, float* out_score, int64_t* out_idx, float* out_margin, void* stream);
+                  const float* cand_score, const int32_t* cand_idx, const int32_t* list_count, int n_lists, int kprime,
+                  int k, int64_t idx_offset, float* out_score, int64_t* out_idx, float* out_margin, void* stream);
 
 /* Multi-GPU pruning (sharded serving; the reference has no distributed path).  A query's exact
  * rescoring needs only its GLOBAL approximate top-kprime, of which a shard holds kprime / n_shards on average:
@@ -149,8 +154,8 @@ int hypret_rerank(const float* q32, const float* g32, int64_t Q, int64_t N, int 
  *                         (the global kprime-th best): results of the shards then merge to exactly the list a
  *                         single-GPU hypret_rerank over the whole gallery returns (ties at the threshold kept).
  *                         k <= kprime <= 32 only. */
-int hypret_cand_select(const float* cand_score, const int32_t* cand_idx, int64_t Q, int n_lists, int kprime,
-                       float* sel_score, int32_t* sel_idx, void* stream);
+int hypret_cand_select(const float* cand_score, const int32_t* cand_idx, const int32_t* list_count, int64_t Q,
+                       int n_lists, int kprime, float* sel_score, int32_t* sel_idx, void* stream);
 int hypret_kth_smallest(const float* vals, int n_parts, int64_t Q, int m, int kth, float* out, void* stream);
 int hypret_rerank_pruned(const float* q32, const float* g32, int64_t Q, int64_t N, int d, float c, int metric,
                          const float* cand_score, const int32_t* cand_idx, int n_lists, int kprime, int k,

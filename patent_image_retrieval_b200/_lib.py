@@ -53,12 +53,12 @@ SIGNATURES = {
     "hypret_score_plan": (c_int, [c_int64, c_int64, c_int, c_int, c_int, c_int, POINTER(ScorePlan)]),
     "hypret_score_strip": (c_int, [POINTER(ScorePlan), c_int, c_int, POINTER(c_int32)]),
     "hypret_score_topk": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int, c_int, c_int, c_int, c_int, c_void_p,
-                                  c_void_p, c_void_p, c_void_p, c_void_p]),
-    "hypret_rerank": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int, c_float, c_int, c_void_p, c_void_p, c_int,
-                              c_int, c_int, c_int64, c_void_p, c_void_p, c_void_p, c_void_p]),
+                                  c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "hypret_rerank": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int, c_float, c_int, c_void_p, c_void_p,
+                              c_void_p, c_int, c_int, c_int, c_int64, c_void_p, c_void_p, c_void_p, c_void_p]),
     "hypret_rerank_pruned": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int, c_float, c_int, c_void_p, c_void_p,
                                      c_int, c_int, c_int, c_int64, c_void_p, c_void_p, c_void_p, c_void_p]),
-    "hypret_cand_select": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    "hypret_cand_select": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "hypret_kth_smallest": (c_int, [c_void_p, c_int, c_int64, c_int, c_int, c_void_p, c_void_p]),
     "hypret_mobius_epilogue": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_void_p, c_float, c_int, c_int, c_int,
                                        c_void_p, c_void_p, c_void_p]),

@@ -51,18 +51,19 @@ int hypret_project_rows(const float* u, int64_t n, int d, float c, int mode, int
 
 int hypret_score_topk(const void* q_op, int64_t Q, const void* g_op, int64_t N, int d, int kprime, int n_lists,
                       int max_ctas, int min_lists, float* cand_score, int32_t* cand_idx, uint32_t* thr_workspace,
-                      float* debug_scores, void* stream) {
+                      int32_t* list_count, float* debug_scores, void* stream) {
   if (Q < 1 || N < 1 || d < 4 || (d & 3) || d > 2048) return HYPRET_EINVAL;
   if (kprime < 1 || kprime > 64 || n_lists < 1 || max_ctas < 0 || min_lists < 0) return HYPRET_EINVAL;
   if (q_op == nullptr || g_op == nullptr || cand_score == nullptr || cand_idx == nullptr) return HYPRET_EINVAL;
   int rc = check_device();
   if (rc != HYPRET_OK) return rc;
   return hypret_launch_score_topk(q_op, Q, g_op, N, d, kprime, n_lists, max_ctas, min_lists, cand_score, cand_idx,
-                                  thr_workspace, debug_scores, static_cast<cudaStream_t>(stream));
+                                  thr_workspace, list_count, debug_scores, static_cast<cudaStream_t>(stream));
 }
 
 static int rerank_common(const float* q32, const float* g32, int64_t Q, int64_t N, int d, float c, int metric,
-                         const float* cand_score, const int32_t* cand_idx, int n_lists, int kprime, int k,
+                         const float* cand_score, const int32_t* cand_idx, const int32_t* list_count, int n_lists,
+                         int kprime, int k,
                          int64_t idx_offset, const float* prune_thr, float* out_score, int64_t* out_idx,
                          float* out_margin, void* stream) {
   if (Q < 0 || N < 1 || d < 4 || (d & 3)) return HYPRET_EINVAL;
@@ -76,16 +77,16 @@ static int rerank_common(const float* q32, const float* g32, int64_t Q, int64_t 
     return HYPRET_EINVAL;
   int rc = check_device();
   if (rc != HYPRET_OK) return rc;
-  return hypret_launch_rerank(q32, g32, Q, N, d, c, metric, cand_score, cand_idx, n_lists * kprime, kprime, k,
-                              idx_offset, prune_thr, out_score, out_idx, out_margin,
+  return hypret_launch_rerank(q32, g32, Q, N, d, c, metric, cand_score, cand_idx, list_count, n_lists * kprime,
+                              kprime, k, idx_offset, prune_thr, out_score, out_idx, out_margin,
                               static_cast<cudaStream_t>(stream));
 }
 
 int hypret_rerank(const float* q32, const float* g32, int64_t Q, int64_t N, int d, float c, int metric,
-                  const float* cand_score, const int32_t* cand_idx, int n_lists, int kprime, int k,
-                  int64_t idx_offset, float* out_score, int64_t* out_idx, float* out_margin, void* stream) {
-  return rerank_common(q32, g32, Q, N, d, c, metric, cand_score, cand_idx, n_lists, kprime, k, idx_offset, nullptr,
-                       out_score, out_idx, out_margin, stream);
+                  const float* cand_score, const int32_t* cand_idx, const int32_t* list_count, int n_lists, int kprime,
+                  int k, int64_t idx_offset, float* out_score, int64_t* out_idx, float* out_margin, void* stream) {
+  return rerank_common(q32, g32, Q, N, d, c, metric, cand_score, cand_idx, list_count, n_lists, kprime, k, idx_offset,
+                       nullptr, out_score, out_idx, out_margin, stream);
 }
 
 int hypret_rerank_pruned(const float* q32, const float* g32, int64_t Q, int64_t N, int d, float c, int metric,
@@ -93,18 +94,18 @@ int hypret_rerank_pruned(const float* q32, const float* g32, int64_t Q, int64_t 
                          int64_t idx_offset, const float* prune_thr, float* out_score, int64_t* out_idx,
                          void* stream) {
   if (prune_thr == nullptr || kprime > 32 || k > 32 || k > kprime) return HYPRET_EINVAL;
-  return rerank_common(q32, g32, Q, N, d, c, metric, cand_score, cand_idx, n_lists, kprime, k, idx_offset, prune_thr,
-                       out_score, out_idx, nullptr, stream);
+  return rerank_common(q32, g32, Q, N, d, c, metric, cand_score, cand_idx, nullptr, n_lists, kprime, k, idx_offset,
+                       prune_thr, out_score, out_idx, nullptr, stream);
 }
 
-int hypret_cand_select(const float* cand_score, const int32_t* cand_idx, int64_t Q, int n_lists, int kprime,
-                       float* sel_score, int32_t* sel_idx, void* stream) {
+int hypret_cand_select(const float* cand_score, const int32_t* cand_idx, const int32_t* list_count, int64_t Q,
+                       int n_lists, int kprime, float* sel_score, int32_t* sel_idx, void* stream) {
   if (Q < 0 || n_lists < 1 || kprime < 1 || kprime > 32 || (int64_t)n_lists * kprime > 16384) return HYPRET_EINVAL;
   if (Q == 0) return HYPRET_OK;
   if (cand_score == nullptr || cand_idx == nullptr || sel_score == nullptr || sel_idx == nullptr) return HYPRET_EINVAL;
   int rc = check_device();
   if (rc != HYPRET_OK) return rc;
-  return hypret_launch_cand_select(cand_score, cand_idx, Q, n_lists * kprime, kprime, sel_score, sel_idx,
+  return hypret_launch_cand_select(cand_score, cand_idx, list_count, Q, n_lists * kprime, kprime, sel_score, sel_idx,
                                    static_cast<cudaStream_t>(stream));
 }
 

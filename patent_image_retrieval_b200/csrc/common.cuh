@@ -309,13 +309,13 @@ int hypret_launch_project_rows(const float* u, int64_t n, int d, float c, int mo
                                void* op_bf16, float* sqnorm, cudaStream_t stream);
 int hypret_launch_score_topk(const void* q_op, int64_t Q, const void* g_op, int64_t N, int d, int kprime,
                              int n_lists, int max_ctas, int min_lists, float* cand_score, int32_t* cand_idx,
-                             uint32_t* thr_ws, float* debug_scores, cudaStream_t stream);
+                             uint32_t* thr_ws, int32_t* list_count, float* debug_scores, cudaStream_t stream);
 int hypret_launch_rerank(const float* q32, const float* g32, int64_t Q, int64_t N, int d, float c, int metric,
-                         const float* cand_score, const int32_t* cand_idx, int n_cand, int kprime, int k,
-                         int64_t idx_offset, const float* prune_thr, float* out_score, int64_t* out_idx,
-                         float* out_margin, cudaStream_t stream);
-int hypret_launch_cand_select(const float* cand_score, const int32_t* cand_idx, int64_t Q, int n_cand, int kprime,
-                              float* sel_score, int32_t* sel_idx, cudaStream_t stream);
+                         const float* cand_score, const int32_t* cand_idx, const int32_t* list_count, int n_cand,
+                         int kprime, int k, int64_t idx_offset, const float* prune_thr, float* out_score,
+                         int64_t* out_idx, float* out_margin, cudaStream_t stream);
+int hypret_launch_cand_select(const float* cand_score, const int32_t* cand_idx, const int32_t* list_count, int64_t Q,
+                              int n_cand, int kprime, float* sel_score, int32_t* sel_idx, cudaStream_t stream);
 int hypret_launch_kth_smallest(const float* vals, int n_parts, int64_t Q, int m, int kth, float* out,
                                cudaStream_t stream);
 int hypret_launch_merge_topk(const float* scores, const int64_t* idx, int W, int64_t Q, int k, int descending,

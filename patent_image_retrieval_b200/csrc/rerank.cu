@@ -79,8 +79,9 @@ __device__ __forceinline__ int select_candidates(float* cs, int* ci, int n_cand,
 template <int NV>   // float4 chunks of a row per lane: D <= NV * 128
 __global__ void __launch_bounds__(RR_WARPS * 32, NV <= 4 ? 4 : 1)
 rerank_kernel(const float* __restrict__ q32, const float* __restrict__ g32, int64_t Q, int64_t N, int d, float c,
-              int metric, const float* __restrict__ cand_score, const int32_t* __restrict__ cand_idx, int n_cand,
-              int kprime, int k, int64_t idx_offset, const float* __restrict__ prune_thr,
+              int metric, const float* __restrict__ cand_score, const int32_t* __restrict__ cand_idx,
+              const int32_t* __restrict__ list_count, int n_cand, int kprime, int k, int64_t idx_offset,
+              const float* __restrict__ prune_thr,
               float* __restrict__ out_score, int64_t* __restrict__ out_idx, float* __restrict__ out_margin) {
   extern __shared__ uint8_t smem_raw[];
   const int warp = threadIdx.x >> 5;
@@ -102,13 +103,14 @@ rerank_kernel(const float* __restrict__ q32, const float* __restrict__ g32, int6
   }
 
   // ---- 1. approximate merge: the k' best candidates by surrogate score --------------------
-  for (int t = lane; t < n_cand; t += 32) {
+  const int n_mine = list_count != nullptr ? min(list_count[q] * kprime, n_cand) : n_cand;   // compact list slots
+  for (int t = lane; t < n_mine; t += 32) {
     cs[t] = cand_score[q * n_cand + t];
     ci[t] = cand_idx[q * n_cand + t];
   }
   __syncwarp();
   float my_approx, worst_approx;
-  int my_idx = select_candidates(cs, ci, n_cand, kprime, prune_thr != nullptr ? prune_thr[q] : INFINITY, lane,
+  int my_idx = select_candidates(cs, ci, n_mine, kprime, prune_thr != nullptr ? prune_thr[q] : INFINITY, lane,
                                  &my_approx, &worst_approx);
   const int n_sel = __popc(__ballot_sync(0xffffffffu, my_idx >= 0));
 
@@ -228,8 +230,9 @@ rerank_kernel(const float* __restrict__ q32, const float* __restrict__ g32, int6
 // padded with (+inf, -1).  Multi-GPU pruning step: the surrogates of different gallery shards are comparable, so
 // the owner of a query can find its GLOBAL k'-th best surrogate from W such lists before any exact rescoring.
 __global__ void __launch_bounds__(RR_WARPS * 32)
-cand_select_kernel(const float* __restrict__ cand_score, const int32_t* __restrict__ cand_idx, int64_t Q, int n_cand,
-                   int kprime, float* __restrict__ sel_score, int32_t* __restrict__ sel_idx) {
+cand_select_kernel(const float* __restrict__ cand_score, const int32_t* __restrict__ cand_idx,
+                   const int32_t* __restrict__ list_count, int64_t Q, int n_cand, int kprime,
+                   float* __restrict__ sel_score, int32_t* __restrict__ sel_idx) {
   extern __shared__ uint8_t smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t q = (int64_t)blockIdx.x * RR_WARPS + warp;
@@ -237,13 +240,14 @@ cand_select_kernel(const float* __restrict__ cand_score, const int32_t* __restri
   float* cs = reinterpret_cast<float*>(smem_raw) + (size_t)warp * n_cand;
   int* ci = reinterpret_cast<int*>(reinterpret_cast<float*>(smem_raw) + (size_t)RR_WARPS * n_cand) +
             (size_t)warp * n_cand;
-  for (int t = lane; t < n_cand; t += 32) {
+  const int n_mine = list_count != nullptr ? min(list_count[q] * kprime, n_cand) : n_cand;
+  for (int t = lane; t < n_mine; t += 32) {
     cs[t] = cand_score[q * n_cand + t];
     ci[t] = cand_idx[q * n_cand + t];
   }
   __syncwarp();
   float my_score, worst;
-  const int my_idx = select_candidates(cs, ci, n_cand, kprime, INFINITY, lane, &my_score, &worst);
+  const int my_idx = select_candidates(cs, ci, n_mine, kprime, INFINITY, lane, &my_score, &worst);
   if (lane < kprime) {
     sel_score[q * kprime + lane] = my_score;
     sel_idx[q * kprime + lane] = my_idx;
@@ -271,8 +275,9 @@ __device__ __forceinline__ bool pair_less(float a, int ia, float b, int ib) {
 template <int NV>
 __global__ void __launch_bounds__(RW_THREADS)
 rerank_wide_kernel(const float* __restrict__ q32, const float* __restrict__ g32, int64_t Q, int64_t N, int d, float c,
-                   int metric, const float* __restrict__ cand_score, const int32_t* __restrict__ cand_idx, int n_lists,
-                   int kprime, int n_pad, int k, int64_t idx_offset, float* __restrict__ out_score,
+                   int metric, const float* __restrict__ cand_score, const int32_t* __restrict__ cand_idx,
+                   const int32_t* __restrict__ list_count, int n_lists_alloc, int kprime, int n_pad, int k,
+                   int64_t idx_offset, float* __restrict__ out_score,
                    int64_t* __restrict__ out_idx, float* __restrict__ out_margin) {
   extern __shared__ uint8_t smem_raw[];
   float* ks = reinterpret_cast<float*>(smem_raw);            // [n_pad] surrogate scores
@@ -283,7 +288,9 @@ rerank_wide_kernel(const float* __restrict__ q32, const float* __restrict__ g32,
   __shared__ unsigned hidden_key;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int64_t q = blockIdx.x;
+  const int n_lists = list_count != nullptr ? min(list_count[q], n_lists_alloc) : n_lists_alloc;   // compact slots
   const int n_cand = n_lists * kprime;
+  const int64_t row_stride = (int64_t)n_lists_alloc * kprime;
 
   __shared__ int n_valid_s;
   if (tid == 0) { hidden_key = 0xffffffffu; n_valid_s = 0; }
@@ -293,19 +300,19 @@ rerank_wide_kernel(const float* __restrict__ q32, const float* __restrict__ g32,
     bool full = true;
     float worst = -INFINITY;
     for (int e = 0; e < kprime; ++e) {
-      const int id = cand_idx[q * n_cand + l * kprime + e];
+      const int id = cand_idx[q * row_stride + l * kprime + e];
       full &= id >= 0;
-      if (id >= 0) worst = fmaxf(worst, cand_score[q * n_cand + l * kprime + e]);
+      if (id >= 0) worst = fmaxf(worst, cand_score[q * row_stride + l * kprime + e]);
     }
     if (full) atomicMin(&hidden_key, ordered_key(worst));
   }
   // compact the valid candidates to the front (most list slots of a query are empty: slots belong to
   // strips of other query tiles); the order is fixed by the sort below
   for (int t = tid; t < n_cand; t += RW_THREADS) {
-    const int id = cand_idx[q * n_cand + t];
+    const int id = cand_idx[q * row_stride + t];
     if (id >= 0) {
       const int pos = atomicAdd(&n_valid_s, 1);
-      ks[pos] = cand_score[q * n_cand + t];
+      ks[pos] = cand_score[q * row_stride + t];
       ki[pos] = id;
     }
   }
@@ -445,8 +452,8 @@ rerank_wide_kernel(const float* __restrict__ q32, const float* __restrict__ g32,
 
 }  // namespace
 
-int hypret_launch_cand_select(const float* cand_score, const int32_t* cand_idx, int64_t Q, int n_cand, int kprime,
-                              float* sel_score, int32_t* sel_idx, cudaStream_t stream) {
+int hypret_launch_cand_select(const float* cand_score, const int32_t* cand_idx, const int32_t* list_count, int64_t Q,
+                              int n_cand, int kprime, float* sel_score, int32_t* sel_idx, cudaStream_t stream) {
   if (Q == 0) return HYPRET_OK;
   const size_t smem = (size_t)RR_WARPS * n_cand * 8;
   if (smem > 200 * 1024) return HYPRET_EUNSUPPORTED;
@@ -455,14 +462,14 @@ int hypret_launch_cand_select(const float* cand_score, const int32_t* cand_idx, 
     if (e != cudaSuccess) return (int)e;
   }
   cand_select_kernel<<<(unsigned)((Q + RR_WARPS - 1) / RR_WARPS), RR_WARPS * 32, smem, stream>>>(
-      cand_score, cand_idx, Q, n_cand, kprime, sel_score, sel_idx);
+      cand_score, cand_idx, list_count, Q, n_cand, kprime, sel_score, sel_idx);
   return (int)cudaGetLastError();
 }
 
 int hypret_launch_rerank(const float* q32, const float* g32, int64_t Q, int64_t N, int d, float c, int metric,
-                         const float* cand_score, const int32_t* cand_idx, int n_cand, int kprime, int k,
-                         int64_t idx_offset, const float* prune_thr, float* out_score, int64_t* out_idx,
-                         float* out_margin, cudaStream_t stream) {
+                         const float* cand_score, const int32_t* cand_idx, const int32_t* list_count, int n_cand,
+                         int kprime, int k, int64_t idx_offset, const float* prune_thr, float* out_score,
+                         int64_t* out_idx, float* out_margin, cudaStream_t stream) {
   if (Q == 0) return HYPRET_OK;
   if (kprime > 32 || k > 32 || k > kprime) {
     if (prune_thr != nullptr) return HYPRET_EUNSUPPORTED;
@@ -479,8 +486,9 @@ int hypret_launch_rerank(const float* q32, const float* g32, int64_t Q, int64_t 
       if (e != cudaSuccess) return (int)e;                                                                          \
     }                                                                                                               \
     rerank_wide_kernel<NV><<<(unsigned)Q, RW_THREADS, smem_w, stream>>>(q32, g32, Q, N, d, c, metric, cand_score,   \
-                                                                       cand_idx, n_lists, kprime, n_pad, k,         \
-                                                                       idx_offset, out_score, out_idx, out_margin); \
+                                                                       cand_idx, list_count, n_lists, kprime,       \
+                                                                       n_pad, k, idx_offset, out_score, out_idx,    \
+                                                                       out_margin);                                 \
     return (int)cudaGetLastError();                                                                                 \
   } while (0)
     if (need_w <= 1) HYPRET_RERANK_WIDE(1);
@@ -504,8 +512,9 @@ int hypret_launch_rerank(const float* q32, const float* g32, int64_t Q, int64_t 
       if (e != cudaSuccess) return (int)e;                                                                          \
     }                                                                                                               \
     rerank_kernel<NV><<<(unsigned)grid, RR_WARPS * 32, smem, stream>>>(q32, g32, Q, N, d, c, metric, cand_score,    \
-                                                                      cand_idx, n_cand, kprime, k, idx_offset,      \
-                                                                      prune_thr, out_score, out_idx, out_margin);   \
+                                                                      cand_idx, list_count, n_cand, kprime, k,      \
+                                                                      idx_offset, prune_thr, out_score, out_idx,    \
+                                                                      out_margin);                                  \
     return (int)cudaGetLastError();                                                                                 \
   } while (0)
   if (need <= 1) HYPRET_RERANK_LAUNCH(1);

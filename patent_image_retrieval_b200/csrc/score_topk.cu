@@ -192,6 +192,8 @@ struct Params {
   Sched sched;
   float* cand_score;
   int32_t* cand_idx;
+  int32_t* list_count;    // [Q] or NULL.  Given: a strip takes the next free list slot of each query (atomicAdd) and
+                          // empty lists take none, so a query's lists are its first list_count[q] slots
   float* debug_scores;
   uint32_t* shared_thr;   // [Q] ordered-uint keys of the best known k'-th score per query, or NULL
   unsigned long long* stats;   // DEBUG builds: [grid][8] wait-cycle counters per warp role, or NULL
@@ -850,8 +852,12 @@ score_topk_kernel(const __grid_constant__ CUtensorMap map_q_main, const __grid_c
       tot_ins += st.n_ins; tot_drain += st.n_drain; tot_now += st.n_now;
       // publish this warpgroup's list of the strip: the first k' entries of the sorted register list
       if (qrow < p.Q) {
-        const int64_t o = (qrow * sc.n_lists + (slot * 2 + wg)) * KP;
-        reg_publish(L, KP, p.cand_score + o, p.cand_idx + o);
+        int pos = slot * 2 + wg;
+        if (p.list_count != nullptr) pos = L.i0 < 0 ? -1 : atomicAdd(&p.list_count[qrow], 1);
+        if (pos >= 0) {
+          const int64_t o = (qrow * sc.n_lists + pos) * KP;
+          reg_publish(L, KP, p.cand_score + o, p.cand_idx + o);
+        }
       }
     }
     if (DEBUG && p.stats != nullptr && warp == 2 && lane == 0) {
@@ -967,11 +973,18 @@ score_topk_kernel(const __grid_constant__ CUtensorMap map_q_main, const __grid_c
       tot_ins += st.n_ins; tot_drain += st.n_drain; tot_now += st.n_now;
       // publish this strip's lists: one coalesced row of k' entries per query
       __syncwarp();
+      int mypos = slot;
+      if (p.list_count != nullptr) {          // compact slots: the lane that owns the row reserves one, if not empty
+        bool any = false;
+        for (int e = 0; e < KP; ++e) any |= my_i[e * TILE_M] >= 0;
+        mypos = (any && qrow < p.Q) ? atomicAdd(&p.list_count[qrow], 1) : -1;
+      }
       for (int r = 0; r < 32; ++r) {
         const int64_t qr = (int64_t)qt * TILE_M + quad * 32 + r;
-        if (qr < p.Q) {
+        const int pos = __shfl_sync(FULL, mypos, r);
+        if (qr < p.Q && pos >= 0) {
           for (int e = lane; e < KP; e += 32) {
-            const int64_t o = (qr * sc.n_lists + slot) * KP + e;
+            const int64_t o = (qr * sc.n_lists + pos) * KP + e;
             p.cand_score[o] = list_s[e * TILE_M + quad * 32 + r];
             p.cand_idx[o] = list_i[e * TILE_M + quad * 32 + r];
           }
@@ -1180,7 +1193,7 @@ extern "C" int hypret_score_strip(const hypret_score_plan_t* plan, int cta, int 
 
 int hypret_launch_score_topk(const void* q_op, int64_t Q, const void* g_op, int64_t N, int d, int kprime,
                              int n_lists, int max_ctas, int min_lists, float* cand_score, int32_t* cand_idx,
-                             uint32_t* thr_ws, float* debug_scores, cudaStream_t stream) {
+                             uint32_t* thr_ws, int32_t* list_count, float* debug_scores, cudaStream_t stream) {
   hypret_score_plan_t plan;
   int rc = hypret_score_plan(Q, N, d, kprime, max_ctas, min_lists, &plan);
   if (rc != HYPRET_OK) return rc;
@@ -1212,6 +1225,7 @@ int hypret_launch_score_topk(const void* q_op, int64_t Q, const void* g_op, int6
   p.sched = sched_from_plan(plan);
   p.cand_score = cand_score;
   p.cand_idx = cand_idx;
+  p.list_count = list_count;
   p.debug_scores = debug_scores;
   p.shared_thr = thr_ws;
   p.stats = nullptr;
@@ -1229,8 +1243,11 @@ int hypret_launch_score_topk(const void* q_op, int64_t Q, const void* g_op, int6
     if (p.stats != nullptr) cudaMemsetAsync(p.stats, 0, (size_t)plan.grid * 8 * sizeof(unsigned long long), stream);
   }
 
-  // list slots that no strip writes (rows with fewer strips than n_lists) must read as empty
-  cudaError_t e = cudaMemsetAsync(cand_idx, 0xFF, (size_t)Q * n_lists * kprime * sizeof(int32_t), stream);
+  // list slots that no strip writes (rows with fewer strips than n_lists) must read as empty -- or, with
+  // list_count, are never read: only the [Q] counters are cleared
+  cudaError_t e = list_count != nullptr
+                      ? cudaMemsetAsync(list_count, 0, (size_t)Q * sizeof(int32_t), stream)
+                      : cudaMemsetAsync(cand_idx, 0xFF, (size_t)Q * n_lists * kprime * sizeof(int32_t), stream);
   if (e != cudaSuccess) return (int)e;
   if (thr_ws != nullptr) {   // 0xFFFFFFFF > f2key(+inf): "no bound published yet"
     e = cudaMemsetAsync(thr_ws, 0xFF, (size_t)Q * sizeof(uint32_t), stream);

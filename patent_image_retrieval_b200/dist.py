@@ -119,17 +119,18 @@ class ShardedGalleryIndex:
         kp = min(default_kprime(k) if kprime is None else int(kprime), ops.MAX_KPRIME)
         if prune is None:
             prune = k <= 32 and kp <= 32 and k <= kp
-        q32, cs, ci = self.local.score_candidates(q_all, k=k, kprime=kprime, kernel_events=kernel_events)
+        q32, cs, ci, cnt = self.local.score_candidates(q_all, k=k, kprime=kprime, kernel_events=kernel_events)
         thr_all = None
         if prune:
-            sel_s, sel_i = ops.cand_select(cs, ci)                                   # [W*Ql, k']
+            sel_s, sel_i = ops.cand_select(cs, ci, cnt)                              # [W*Ql, k']
             recv = torch.empty_like(sel_s)
             dist.all_to_all_single(recv, sel_s, group=self.group)                    # [W, Ql, k'] at the owner
             thr = ops.kth_smallest(recv.view(world, q_local.shape[0], kp), kp)       # global k'-th best surrogate
             thr_all = torch.empty(world * q_local.shape[0], dtype=torch.float32, device=thr.device)
             dist.all_gather_into_tensor(thr_all, thr, group=self.group)
-            cs, ci = sel_s.unsqueeze(1), sel_i.unsqueeze(1)                          # one merged list per query
-        score, idx = self.local.rerank_candidates(q32, cs, ci, k, prune_thr=thr_all, kernel_events=kernel_events)
+            cs, ci, cnt = sel_s.unsqueeze(1), sel_i.unsqueeze(1), None               # one merged list per query
+        score, idx = self.local.rerank_candidates(q32, cs, ci, k, prune_thr=thr_all, kernel_events=kernel_events,
+                                                  list_count=cnt)
         rs, ri = return_lists_to_owners(score, idx, self.group)
         return ops.merge_topk(rs, ri, descending=(self.metric == "cosine"))
 

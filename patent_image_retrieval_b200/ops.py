@@ -89,12 +89,18 @@ def score_strips(Q: int, N: int, d: int, kprime: int, max_ctas: int = 0, min_lis
 
 def score_topk(q_op: torch.Tensor, g_op: torch.Tensor, d: int, kprime: int, max_ctas: int = 0,
                debug: bool = False, out: Optional[Tuple[torch.Tensor, torch.Tensor]] = None,
-               share_thresholds: bool = True, thr_workspace: Optional[torch.Tensor] = None, min_lists: int = 0):
+               share_thresholds: bool = True, thr_workspace: Optional[torch.Tensor] = None, min_lists: int = 0,
+               list_count: Optional[torch.Tensor] = None):
     """tcgen05 scoring GEMM + streaming top-k'.  Returns ``(cand_score [Q,L,k'], cand_idx [Q,L,k'] int32)``
     with L = plan["n_lists"] (+ the full ``[Q,N]`` surrogate matrix when ``debug`` -- tests only).
     ``share_thresholds``: strips of a query exchange their running k'-th best score (fast path);
-    off, every list is exactly the top-k' of its own strip."""
-    _need_cuda(q_op, g_op)
+    off, every list is exactly the top-k' of its own strip.
+    ``list_count`` ([Q] int32, out): compact list slots -- the lists of query q are its first ``list_count[q]`` slots
+    (pass the same tensor to ``rerank`` / ``cand_select``); without it slots are the schedule's and unwritten ones
+    read as empty."""
+    _need_cuda(q_op, g_op, list_count)
+    if list_count is not None and (list_count.dtype != torch.int32 or list_count.numel() < q_op.shape[0]):
+        raise ValueError("list_count must be an int32 tensor with one entry per query")
     if q_op.dtype != torch.bfloat16 or g_op.dtype != torch.bfloat16:
         raise ValueError("operands must be bf16 rows from project_rows")
     kpad = operand_kpad(d)
@@ -119,18 +125,20 @@ def score_topk(q_op: torch.Tensor, g_op: torch.Tensor, d: int, kprime: int, max_
                 raise ValueError("thr_workspace must be a CUDA tensor of >= Q 32-bit elements")
         _lib.check(_lib.load().hypret_score_topk(_ptr(q_op), Q, _ptr(g_op), N, int(d), int(kprime), S,
                                                  int(max_ctas), int(min_lists), _ptr(cs), _ptr(ci), _ptr(ws),
-                                                 _ptr(dbg), _stream()))
+                                                 _ptr(list_count), _ptr(dbg), _stream()))
     return (cs, ci, dbg) if debug else (cs, ci)
 
 
 def rerank(q32: torch.Tensor, g32: torch.Tensor, cand_score: torch.Tensor, cand_idx: torch.Tensor, c: float,
            metric: str, k: int, idx_offset: int = 0, want_margin: bool = False,
-           prune_thr: Optional[torch.Tensor] = None):
+           prune_thr: Optional[torch.Tensor] = None, list_count: Optional[torch.Tensor] = None):
     """Merge candidate lists, exact fp64-accumulated rescoring, sorted top-k.
     Returns ``(score [Q,k] f32, idx [Q,k] i64[, margin [Q] f32])``.
     ``prune_thr [Q]`` (multi-GPU): candidates whose surrogate exceeds it are skipped (``hypret_rerank_pruned``)."""
-    _need_cuda(q32, g32, cand_score, cand_idx, prune_thr)
+    _need_cuda(q32, g32, cand_score, cand_idx, prune_thr, list_count)
     if prune_thr is not None:
+        if list_count is not None:
+            raise ValueError("a pruned rerank takes the selected lists of cand_select (no list_count)")
         if want_margin:
             raise ValueError("the margin certificate is not defined for a pruned rerank")
         q32, g32 = q32.contiguous(), g32.contiguous()
@@ -158,12 +166,13 @@ def rerank(q32: torch.Tensor, g32: torch.Tensor, cand_score: torch.Tensor, cand_
     margin = torch.empty(Q, dtype=torch.float32, device=q32.device) if want_margin else None
     with torch.cuda.device(q32.device):
         _lib.check(_lib.load().hypret_rerank(_ptr(q32), _ptr(g32), Q, N, d, float(c), METRIC[metric],
-                                             _ptr(cand_score), _ptr(cand_idx), S, kprime, int(k), int(idx_offset),
+                                             _ptr(cand_score), _ptr(cand_idx), _ptr(list_count), S, kprime, int(k),
+                                             int(idx_offset),
                                              _ptr(out_s), _ptr(out_i), _ptr(margin), _stream()))
     return (out_s, out_i, margin) if want_margin else (out_s, out_i)
 
 
-def cand_select(cand_score: torch.Tensor, cand_idx: torch.Tensor):
+def cand_select(cand_score: torch.Tensor, cand_idx: torch.Tensor, list_count: Optional[torch.Tensor] = None):
     """The k' best candidates of each query by surrogate score: ``[Q,L,k'] -> ([Q,k'] f32 ascending, [Q,k'] i32)``,
     padded with (+inf, -1)."""
     _need_cuda(cand_score, cand_idx)
@@ -171,8 +180,8 @@ def cand_select(cand_score: torch.Tensor, cand_idx: torch.Tensor):
     ss = torch.empty(Q, kprime, dtype=torch.float32, device=cand_score.device)
     si = torch.empty(Q, kprime, dtype=torch.int32, device=cand_score.device)
     with torch.cuda.device(cand_score.device):
-        _lib.check(_lib.load().hypret_cand_select(_ptr(cand_score.contiguous()), _ptr(cand_idx.contiguous()), Q, S,
-                                                  kprime, _ptr(ss), _ptr(si), _stream()))
+        _lib.check(_lib.load().hypret_cand_select(_ptr(cand_score.contiguous()), _ptr(cand_idx.contiguous()),
+                                                  _ptr(list_count), Q, S, kprime, _ptr(ss), _ptr(si), _stream()))
     return ss, si
 
 

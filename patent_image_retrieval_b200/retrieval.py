@@ -114,15 +114,17 @@ class GalleryIndex:
         score = Poincare distance ascending, or cosine similarity descending; ties -> lower index.
         ``kernel_events``: a list (receives a (start, end) CUDA-event pair bracketing the scoring kernel
         on the launching stream per call) or a ``StageEvents`` (all three kernels): bench.py's rooflines."""
-        q32, cs, ci = self.score_candidates(queries, k=k, kprime=kprime, max_ctas=max_ctas,
-                                            kernel_events=kernel_events)
-        return self.rerank_candidates(q32, cs, ci, k, return_margin=return_margin, kernel_events=kernel_events)
+        q32, cs, ci, cnt = self.score_candidates(queries, k=k, kprime=kprime, max_ctas=max_ctas,
+                                                 kernel_events=kernel_events)
+        return self.rerank_candidates(q32, cs, ci, k, return_margin=return_margin, kernel_events=kernel_events,
+                                      list_count=cnt)
 
     def score_candidates(self, queries: torch.Tensor, k: int = 10, kprime: Optional[int] = None, max_ctas: int = 0,
                          kernel_events: Optional[list] = None):
         """First half of ``search``: projection + tcgen05 scoring / streaming top-k'.
-        Returns ``(q32 [Q,D] exact-rerank operand, cand_score [Q,L,k'], cand_idx [Q,L,k'] int32)``; the candidate
-        buffers are reused by the next call."""
+        Returns ``(q32 [Q,D] exact-rerank operand, cand_score [Q,L,k'], cand_idx [Q,L,k'] int32, list_count [Q]
+        int32)``: the lists of query q are its first ``list_count[q]`` slots (compact, arrival order); the other
+        slots hold stale data.  The candidate buffers are reused by the next call."""
         kprime = default_kprime(k) if kprime is None else int(kprime)
         kprime = min(kprime, ops.MAX_KPRIME)
         wide = k > kprime or k > 32 or kprime > 32
@@ -145,19 +147,22 @@ class GalleryIndex:
             self._cand.clear()
             buf = (torch.empty(q.shape[0], plan["n_lists"], kprime, dtype=torch.float32, device=self.device),
                    torch.empty(q.shape[0], plan["n_lists"], kprime, dtype=torch.int32, device=self.device),
+                   torch.empty(q.shape[0], dtype=torch.int32, device=self.device),
                    torch.empty(q.shape[0], dtype=torch.int32, device=self.device))
             self._cand[key] = buf
         with _span(kernel_events, "score"):
             cs, ci = ops.score_topk(q_op, self.operand, self.d, kprime, max_ctas, out=buf[:2], thr_workspace=buf[2],
-                                    share_thresholds=not wide, min_lists=min_lists)
-        return q32, cs, ci
+                                    share_thresholds=not wide, min_lists=min_lists, list_count=buf[3])
+        return q32, cs, ci, buf[3]
 
     def rerank_candidates(self, q32, cand_score, cand_idx, k: int, return_margin: bool = False,
-                          prune_thr: Optional[torch.Tensor] = None, kernel_events: Optional[list] = None):
+                          prune_thr: Optional[torch.Tensor] = None, kernel_events: Optional[list] = None,
+                          list_count: Optional[torch.Tensor] = None):
         """Second half of ``search``: candidate merge + exact rerank against this shard's fp32 rows."""
         with _span(kernel_events, "rerank"):
             out = ops.rerank(q32, self.rows32, cand_score, cand_idx, self.c, self.metric, k,
-                             idx_offset=self.idx_offset, want_margin=return_margin, prune_thr=prune_thr)
+                             idx_offset=self.idx_offset, want_margin=return_margin, prune_thr=prune_thr,
+                             list_count=list_count)
         return out
 
 

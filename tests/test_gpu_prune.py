@@ -59,8 +59,8 @@ def test_kth_smallest_matches_sort(W, m, kth):
 def test_pruned_rerank_equals_rerank_of_surviving_candidates(metric):
     Q, N, D, kp, k = 150, 5000, 256, 16, 10
     index = GalleryIndex(synth.gaussian_features(N, D, seed=0).cuda(), metric=metric)
-    q32, cs, ci = index.score_candidates(synth.gaussian_features(Q, D, seed=1).cuda(), k=k, kprime=kp)
-    sel_s, sel_i = ops.cand_select(cs, ci)
+    q32, cs, ci, cnt = index.score_candidates(synth.gaussian_features(Q, D, seed=1).cuda(), k=k, kprime=kp)
+    sel_s, sel_i = ops.cand_select(cs, ci, cnt)
     thr = sel_s[:, 5].clone()                          # keep the 6 best (plus surrogate ties) of every query
     thr[3] = float("-inf")                             # a query that loses every candidate on this shard
     d_p, i_p = index.rerank_candidates(q32, sel_s.unsqueeze(1), sel_i.unsqueeze(1), k, prune_thr=thr)
@@ -88,8 +88,8 @@ def test_pruned_shard_protocol_on_one_gpu_equals_single_index(metric, W):
     for r in range(W):
         lo, hi = shard_range(N, r, W)
         sh = GalleryIndex(g[lo:hi], metric=metric, idx_offset=lo)
-        q32, cs, ci = sh.score_candidates(q, k=k, kprime=kp)
-        sel_s, sel_i = ops.cand_select(cs, ci)
+        q32, cs, ci, cnt = sh.score_candidates(q, k=k, kprime=kp)
+        sel_s, sel_i = ops.cand_select(cs, ci, cnt)
         shards.append(sh)
         staged.append((q32, sel_s, sel_i))
     thr = ops.kth_smallest(torch.stack([s for _, s, _ in staged]), kp)

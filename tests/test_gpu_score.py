@@ -123,3 +123,33 @@ def test_plan_mismatch_is_an_error():
     ci = torch.empty(64, 77, 16, device="cuda", dtype=torch.int32)
     with pytest.raises(ValueError):
         ops.score_topk(q_op, g_op, 128, 16, 0, out=(cs, ci))
+
+
+@pytest.mark.parametrize("Q,N,d,kprime,cap", [(200, 1000, 512, 16, 0), (900, 5000, 128, 8, 5), (257, 5000, 256, 20, 0),
+                                              (130, 700, 768, 32, 0), (700, 9000, 512, 16, 7)])
+def test_compact_list_slots_hold_the_same_candidates(Q, N, d, kprime, cap):
+    """list_count mode: slots are handed out per query in arrival order and empty lists take none -- the multiset of
+    (score, index) entries in a query's first list_count[q] slots equals the legacy layout's, and nothing is lost."""
+    q_op, g_op = _operands(Q, N, d)
+    cs0, ci0 = ops.score_topk(q_op, g_op, d, kprime, cap, share_thresholds=False)
+    cnt = torch.full((Q,), -7, dtype=torch.int32, device="cuda")
+    plan = ops.score_plan(Q, N, d, kprime, cap)
+    cs1 = torch.full((Q, plan["n_lists"], kprime), float("nan"), device="cuda")
+    ci1 = torch.full((Q, plan["n_lists"], kprime), 123456789, dtype=torch.int32, device="cuda")     # stale garbage
+    ops.score_topk(q_op, g_op, d, kprime, cap, share_thresholds=False, out=(cs1, ci1), list_count=cnt)
+    assert int(cnt.min()) >= 0 and int(cnt.max()) <= plan["n_lists"]
+    n_nonempty = (ci0 >= 0).any(dim=2).sum(dim=1)
+    assert torch.equal(cnt.long(), n_nonempty)
+    used = torch.arange(plan["n_lists"], device="cuda")[None, :] < cnt[:, None]                     # [Q, L]
+    flat0 = torch.where(ci0 >= 0, ci0, torch.full_like(ci0, 1 << 30)).reshape(Q, -1).sort(dim=1).values
+    ci1m = torch.where(used[:, :, None] & (ci1 >= 0), ci1, torch.full_like(ci1, 1 << 30))
+    flat1 = ci1m.reshape(Q, -1).sort(dim=1).values
+    assert torch.equal(flat0, flat1)
+    s0 = torch.where(ci0 >= 0, cs0, torch.full_like(cs0, float("inf"))).reshape(Q, -1).sort(dim=1).values
+    s1 = torch.where(used[:, :, None] & (ci1 >= 0), cs1, torch.full_like(cs1, float("inf"))).reshape(Q, -1).sort(dim=1).values
+    assert torch.equal(s0, s1)
+    # consumers read only the used slots: same selection from both layouts
+    a = ops.cand_select(cs0, ci0) if kprime <= 32 else None
+    b = ops.cand_select(cs1, ci1, cnt) if kprime <= 32 else None
+    if a is not None:
+        assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])
