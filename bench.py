@@ -12,7 +12,7 @@ against a gallery index that is resident in HBM (built once, untimed, like the r
 * ``e2e``    the same through the public API with HOST buffers (``SearchPipeline``): every step
              copies that step's pinned-host queries H2D, searches, and copies the [Q,k] result
              (distances + indices) D2H; copies of neighbouring steps overlap the search (three
-             streams, double buffers).  ``e2e.serial`` is the same without any overlap
+             streams, three buffer slots).  ``e2e.serial`` is the same without any overlap
 * ``roofline``  scoring kernel only: 2*Q*N_local*D algorithmic flops / its CUDA-event duration,
              against the measured bf16 tensor peak in MEASURED_PEAKS.json
 * ``cpu_baseline``  the oracle (reference torch-fp32 path restated, oracle/) timed on this
@@ -238,22 +238,25 @@ def main():
     ms_e2e_serial = e0.elapsed_time(e1) / args.steps
 
     # ---- timed: end to end with host buffers, pipelined (the serving loop) ----------------------------
-    pipe = SearchPipeline(index, Q, k=k, kprime=kprime)
+    # three buffer slots: the host consumes a step's result while the two following steps are already queued, so a
+    # late wake-up of the host thread (8 ranks share the box's cores) does not leave the GPU idle
+    pipe = SearchPipeline(index, Q, k=k, kprime=kprime, depth=3)
     q_hosts = [q_host, q_host.clone().pin_memory()]
-    for s_ in range(3):
+    for s_ in range(4):
         pipe.submit(q_hosts[s_ % 2])
     pipe.drain()
     barrier()
     t_start = torch.cuda.Event(enable_timing=True)
     t_end = torch.cuda.Event(enable_timing=True)
     t_start.record(pipe.copy_in)
-    last = None
+    pending = []
     for s_ in range(args.steps):
-        slot = pipe.submit(q_hosts[s_ % 2])
-        if last is not None:
-            pipe.result(last)                     # the host consumes the previous step's result
-        last = slot
-    pipe.result(last)
+        pending.append(pipe.submit(q_hosts[s_ % 2]))
+        if len(pending) > 2:
+            pipe.result(pending.pop(0))           # the host consumes results two steps behind the submissions
+    last = pending[-1]
+    for slot in pending:
+        pipe.result(slot)
     t_end.record(pipe.copy_out)
     barrier()
     ms_e2e = t_start.elapsed_time(t_end) / args.steps
