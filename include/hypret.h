@@ -189,14 +189,15 @@ int hypret_pairdist(const float* a, const float* p, int64_t n, int64_t m, int d,
 
 /* Backward of hypret_pairdist (the reference differentiates through ~40 elementwise autograd
  * nodes per pair, src/train.py:1846).  Given grad_out = dL/dD [n,m] and the forward matrix dmat, ONE fp32 pass:
- *   w_out [n,m]              W (see csrc/pairdist.cu)
+ *   w_out                    W (see csrc/pairdist.cu): w_format 0 = fp32 [n,m]; 1 = three bf16 planes [3,n,m] (hi, mid,
+ *                            lo; hi+mid+lo = W to fp32 accuracy) for split-bf16 tensor-core GEMMs of the two products
  *   row_sum [n]              sum_j W_ij (1 + c s_ij / alpha_i)
  *   col_partial [n_partial,m]  partial column sums of W_ij (1 + c s_ij / beta_j), one row per 32 matrix rows:
  *                            n_partial >= ceil(n/32); sum over dim 0
  * so that  dA = a * row_sum[:,None] - W P,  dP = p * col_sum[:,None] - W^T A  (two plain GEMMs
  * left to the caller).  asq / psq = squared norms of the rows of a / p. */
 int hypret_pairdist_bwd(const float* grad_out, const float* dmat, const float* asq, const float* psq, int64_t n,
-                        int64_t m, float c, float* w_out, float* row_sum, float* col_partial, int n_partial,
+                        int64_t m, float c, void* w_out, int w_format, float* row_sum, float* col_partial, int n_partial,
                         void* stream);
 
 /* In-batch InfoNCE over the distance matrix, forward and backward, without torch passes over [n,m]
@@ -212,7 +213,23 @@ int hypret_pairdist_ce_fwd(const float* a, const float* p, int64_t n, int64_t m,
                            int n_part, void* stream);
 int hypret_pairdist_ce_bwd(const float* dmat, const float* asq, const float* psq, int64_t n, int64_t m, float c,
                            const float* row_lse, const float* col_lse, float inv_tau, float w_rows, float w_cols,
-                           const float* grad_scale, float* w_out, float* row_sum, float* col_partial, void* stream);
+                           const float* grad_scale, void* w_out, int w_format, float* row_sum, float* col_partial,
+                           void* stream);
+
+/* The same n x m distance matrix on the TENSOR CORES (training path, csrc/gramdist.cu): one tcgen05 GEMM over
+ * operands that carry a 3-way bf16 split of the fp32 rows along K (six cross products = the fp32 inner product),
+ * distance formed in the epilogue, near pairs (|a-p|^2 < (|a|^2+|p|^2)/4, i.e. where |a|^2+|p|^2-2<a,p> cancels)
+ * recomputed exactly from the fp32 rows.  Accuracy ~1e-6 relative (fp32 accumulation; fp32 arccosh tail).
+ *   hypret_gram_kpad(d)   operand row length = roundup(6 d, 64) bf16 elements
+ *   hypret_gram_split     x [n,d] fp32 -> operand [n,kpad] bf16 for side 0 (rows of a) / 1 (rows of p), sqnorm [n]
+ *   hypret_gram_dist      out [n,m] fp32 from the two operands, the fp32 rows and the squared norms
+ *   hypret_neg_lse        row / column log-sum-exps of -dmat * inv_tau (the second half of hypret_pairdist_ce_fwd) */
+int64_t hypret_gram_kpad(int d);
+int hypret_gram_split(const float* x, int64_t n, int d, int side, void* out_bf16, float* sqnorm, void* stream);
+int hypret_gram_dist(const void* a_op, const void* p_op, const float* a32, const float* p32, const float* asq,
+                     const float* psq, int64_t n, int64_t m, int d, float c, float* out, void* stream);
+int hypret_neg_lse(const float* dmat, int64_t n, int64_t m, float inv_tau, int want_col_lse, float* row_lse,
+                   float* col_lse, float* scratch, int n_part, void* stream);
 
 /* Metrics of ranked lists, restating the per-query loops of notebooks/retrieval.ipynb:310-324
  * (MRR@k, Precision@k), :411-420 (AP), :430-437 (nDCG), :439-443 (Recall@k), :446-456 (means).

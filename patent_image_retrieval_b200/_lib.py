@@ -63,12 +63,19 @@ SIGNATURES = {
     "hypret_mobius_epilogue": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_void_p, c_float, c_int, c_int, c_int,
                                        c_void_p, c_void_p, c_void_p]),
     "hypret_pairdist": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int, c_float, c_void_p, c_void_p]),
-    "hypret_pairdist_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_float, c_void_p,
+    "hypret_pairdist_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_float, c_void_p, c_int,
                                     c_void_p, c_void_p, c_int, c_void_p]),
     "hypret_pairdist_ce_fwd": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int, c_float, c_float, c_int, c_void_p,
                                        c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
     "hypret_pairdist_ce_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_float, c_void_p, c_void_p,
-                                       c_float, c_float, c_float, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+                                       c_float, c_float, c_float, c_void_p, c_void_p, c_int, c_void_p, c_void_p,
+                                       c_void_p]),
+    "hypret_gram_kpad": (c_int64, [c_int]),
+    "hypret_gram_split": (c_int, [c_void_p, c_int64, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    "hypret_gram_dist": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int,
+                                 c_float, c_void_p, c_void_p]),
+    "hypret_neg_lse": (c_int, [c_void_p, c_int64, c_int64, c_float, c_int, c_void_p, c_void_p, c_void_p, c_int,
+                               c_void_p]),
     "hypret_retrieval_metrics": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p, POINTER(c_int32),
                                          c_int, c_void_p, c_void_p, c_void_p]),
     "hypret_ap_full": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p,

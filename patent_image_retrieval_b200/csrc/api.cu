@@ -151,16 +151,17 @@ int hypret_pairdist(const float* a, const float* p, int64_t n, int64_t m, int d,
 }
 
 int hypret_pairdist_bwd(const float* grad_out, const float* dmat, const float* asq, const float* psq, int64_t n,
-                        int64_t m, float c, float* w_out, float* row_sum, float* col_partial, int n_partial,
+                        int64_t m, float c, void* w_out, int w_format, float* row_sum, float* col_partial, int n_partial,
                         void* stream) {
-  if (n < 0 || m < 0 || !(c > 0.f) || n_partial < 1 || n_partial > 65535) return HYPRET_EINVAL;
+  if (n < 0 || m < 0 || !(c > 0.f) || n_partial < 1 || n_partial > 65535 || (w_format != 0 && w_format != 1))
+    return HYPRET_EINVAL;
   if (n == 0 || m == 0) return HYPRET_OK;
   if (grad_out == nullptr || dmat == nullptr || asq == nullptr || psq == nullptr || w_out == nullptr ||
       row_sum == nullptr || col_partial == nullptr)
     return HYPRET_EINVAL;
   int rc = check_device();
   if (rc != HYPRET_OK) return rc;
-  return hypret_launch_pairdist_bwd(grad_out, dmat, asq, psq, n, m, c, w_out, row_sum, col_partial, n_partial,
+  return hypret_launch_pairdist_bwd(grad_out, dmat, asq, psq, n, m, c, w_out, w_format, row_sum, col_partial, n_partial,
                                     static_cast<cudaStream_t>(stream));
 }
 
@@ -180,10 +181,46 @@ int hypret_pairdist_ce_fwd(const float* a, const float* p, int64_t n, int64_t m,
                                        static_cast<cudaStream_t>(stream));
 }
 
+int64_t hypret_gram_kpad(int d) { return d > 0 ? hypret_gram_kpad_impl(d) : 0; }
+
+int hypret_gram_split(const float* x, int64_t n, int d, int side, void* out_bf16, float* sqnorm, void* stream) {
+  if (n < 0 || d < 4 || (d & 3) || d > 1024 || (side != 0 && side != 1)) return HYPRET_EINVAL;
+  if (n == 0) return HYPRET_OK;
+  if (x == nullptr || out_bf16 == nullptr || sqnorm == nullptr || !aligned16(out_bf16)) return HYPRET_EINVAL;
+  int rc = check_device();
+  if (rc != HYPRET_OK) return rc;
+  return hypret_launch_gram_split(x, n, d, side, out_bf16, sqnorm, static_cast<cudaStream_t>(stream));
+}
+
+int hypret_gram_dist(const void* a_op, const void* p_op, const float* a32, const float* p32, const float* asq,
+                     const float* psq, int64_t n, int64_t m, int d, float c, float* out, void* stream) {
+  if (n < 0 || m < 0 || d < 4 || (d & 3) || d > 1024 || !(c > 0.f)) return HYPRET_EINVAL;
+  if (n == 0 || m == 0) return HYPRET_OK;
+  if (a_op == nullptr || p_op == nullptr || a32 == nullptr || p32 == nullptr || asq == nullptr || psq == nullptr ||
+      out == nullptr || !aligned16(a_op) || !aligned16(p_op) || !aligned16(a32) || !aligned16(p32) || !aligned16(out))
+    return HYPRET_EINVAL;
+  int rc = check_device();
+  if (rc != HYPRET_OK) return rc;
+  return hypret_launch_gram_dist(a_op, p_op, a32, p32, asq, psq, n, m, d, c, out, static_cast<cudaStream_t>(stream));
+}
+
+int hypret_neg_lse(const float* dmat, int64_t n, int64_t m, float inv_tau, int want_col_lse, float* row_lse,
+                   float* col_lse, float* scratch, int n_part, void* stream) {
+  if (n < 0 || m < 0 || !(inv_tau > 0.f) || n_part < 1 || n_part > 65535) return HYPRET_EINVAL;
+  if (n == 0 || m == 0) return HYPRET_OK;
+  if (dmat == nullptr || row_lse == nullptr || (want_col_lse && (col_lse == nullptr || scratch == nullptr)))
+    return HYPRET_EINVAL;
+  int rc = check_device();
+  if (rc != HYPRET_OK) return rc;
+  return hypret_launch_neg_lse(dmat, n, m, inv_tau, want_col_lse, row_lse, col_lse, scratch, n_part,
+                               static_cast<cudaStream_t>(stream));
+}
+
 int hypret_pairdist_ce_bwd(const float* dmat, const float* asq, const float* psq, int64_t n, int64_t m, float c,
                            const float* row_lse, const float* col_lse, float inv_tau, float w_rows, float w_cols,
-                           const float* grad_scale, float* w_out, float* row_sum, float* col_partial, void* stream) {
-  if (n < 0 || m < 0 || !(c > 0.f) || !(inv_tau > 0.f)) return HYPRET_EINVAL;
+                           const float* grad_scale, void* w_out, int w_format, float* row_sum, float* col_partial,
+                           void* stream) {
+  if (n < 0 || m < 0 || !(c > 0.f) || !(inv_tau > 0.f) || (w_format != 0 && w_format != 1)) return HYPRET_EINVAL;
   if (n == 0 || m == 0) return HYPRET_OK;
   if (dmat == nullptr || asq == nullptr || psq == nullptr || row_lse == nullptr || w_out == nullptr ||
       row_sum == nullptr || col_partial == nullptr || (w_cols != 0.f && col_lse == nullptr))
@@ -191,7 +228,7 @@ int hypret_pairdist_ce_bwd(const float* dmat, const float* asq, const float* psq
   int rc = check_device();
   if (rc != HYPRET_OK) return rc;
   return hypret_launch_pairdist_ce_bwd(dmat, asq, psq, n, m, c, row_lse, col_lse, inv_tau, w_rows, w_cols, grad_scale,
-                                       w_out, row_sum, col_partial, static_cast<cudaStream_t>(stream));
+                                       w_out, w_format, row_sum, col_partial, static_cast<cudaStream_t>(stream));
 }
 
 int hypret_retrieval_metrics(const int64_t* ranked, int64_t Q, int K, const int64_t* pos_offsets,

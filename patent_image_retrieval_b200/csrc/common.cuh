@@ -337,15 +337,21 @@ int hypret_launch_ap_from_counts(const int64_t* pos_off, const int64_t* pos_item
                                  const unsigned long long* counts, const int32_t* bad, int64_t Q, int64_t n_total,
                                  int grouped_ties, double* ap, int32_t* valid, double* mean_ap, cudaStream_t stream);
 int hypret_launch_pairdist_bwd(const float* g, const float* dmat, const float* asq, const float* psq, int64_t n,
-                               int64_t m, float c, float* w_out, float* row_sum, float* col_partial, int n_partial,
-                               cudaStream_t stream);
+                               int64_t m, float c, void* w_out, int w_format, float* row_sum, float* col_partial,
+                               int n_partial, cudaStream_t stream);
 int hypret_launch_pairdist_ce_fwd(const float* a, const float* p, int64_t n, int64_t m, int d, float c, float inv_tau,
                                   int want_cols, float* dmat, float* row_lse, float* col_lse, float* scratch,
                                   int n_part, cudaStream_t stream);
 int hypret_launch_pairdist_ce_bwd(const float* dmat, const float* asq, const float* psq, int64_t n, int64_t m, float c,
                                   const float* row_lse, const float* col_lse, float inv_tau, float wr, float wc,
-                                  const float* grad_scale, float* w_out, float* row_sum, float* col_partial,
-                                  cudaStream_t stream);
+                                  const float* grad_scale, void* w_out, int w_format, float* row_sum,
+                                  float* col_partial, cudaStream_t stream);
+int64_t hypret_gram_kpad_impl(int d);
+int hypret_launch_gram_split(const float* x, int64_t n, int d, int side, void* out_bf16, float* sq, cudaStream_t stream);
+int hypret_launch_gram_dist(const void* a_op, const void* p_op, const float* a32, const float* p32, const float* asq,
+                            const float* psq, int64_t n, int64_t m, int d, float c, float* out, cudaStream_t stream);
+int hypret_launch_neg_lse(const float* dmat, int64_t n, int64_t m, float inv_tau, int want_cols, float* row_lse,
+                          float* col_lse, float* scratch, int n_part, cudaStream_t stream);
 int hypret_launch_mobius_epilogue(const float* mx, int64_t n, int d, const float* xsq, const float* bias, float c,
                                   int hyperbolic_input, int post_tanh, int n_project, float* y, float* sqnorm,
                                   cudaStream_t stream);

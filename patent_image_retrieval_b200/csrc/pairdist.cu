@@ -129,59 +129,97 @@ pairdist_kernel(const float* __restrict__ a, const float* __restrict__ p, int64_
 // The two dense products W P and W^T A are left to the caller (plain GEMMs).
 constexpr int BW_ROWS = 32;
 
-template <bool CE>
+// SPLIT: W leaves as three bf16 planes [3][n][m] (hi, mid, lo with hi + mid + lo = W to fp32 accuracy) so that the
+// two dense products of the backward run as bf16 tensor-core GEMMs (six cross products each) instead of SGEMMs.
+template <bool CE, bool SPLIT>
 __global__ void __launch_bounds__(256)
 pairdist_bwd_fused_kernel(const float* __restrict__ g, const float* __restrict__ dmat, const float* __restrict__ asq,
                           const float* __restrict__ psq, int64_t n, int64_t m, float c, const float* __restrict__ row_lse,
                           const float* __restrict__ col_lse, float inv_tau, float wr, float wc,
-                          const float* __restrict__ grad_scale, float* __restrict__ w_out,
+                          const float* __restrict__ grad_scale, void* __restrict__ w_out_raw,
                           float* __restrict__ row_sum, float* __restrict__ col_partial) {
-  __shared__ float s_al[BW_ROWS], s_lse[BW_ROWS];
+  __shared__ float s_al[BW_ROWS], s_ial[BW_ROWS], s_lse[BW_ROWS];
   __shared__ float s_red[BW_ROWS][8];
   const int64_t i0 = (int64_t)blockIdx.x * BW_ROWS;
   const int rows = (int)(n - i0 < BW_ROWS ? n - i0 : BW_ROWS);
   if (threadIdx.x < BW_ROWS) {
     const bool ok = threadIdx.x < rows;
     s_al[threadIdx.x] = ok ? 1.0f - c * asq[i0 + threadIdx.x] : 1.0f;
+    s_ial[threadIdx.x] = 1.0f / s_al[threadIdx.x];
     s_lse[threadIdx.x] = (CE && ok) ? row_lse[i0 + threadIdx.x] : 0.f;
   }
   __syncthreads();
-  const float sc = sqrtf(c), four_sc = 4.0f * sc, half_sc = 0.5f * sc;
+  const float sc = sqrtf(c), four_sc = 4.0f * sc;
   const float gsc = CE ? -(grad_scale != nullptr ? grad_scale[0] : 1.0f) * inv_tau / (float)n : 0.f;
   float racc[BW_ROWS];
 #pragma unroll
   for (int r = 0; r < BW_ROWS; ++r) racc[r] = 0.f;
-  for (int64_t j = threadIdx.x; j < ((m + 255) / 256) * 256; j += 256) {
+  // CTAs start at different column blocks (and wrap around): with a power-of-two row pitch the 32 rows of a
+  // block land on the same memory channels, and CTAs marching through the columns in lock-step would all camp
+  // on them at once
+  const int64_t n_cb = (m + 255) / 256;
+  const int64_t cb0 = ((int64_t)blockIdx.x * 5) % n_cb;
+  for (int64_t cbi = 0; cbi < n_cb; ++cbi) {
+    const int64_t cb = cb0 + cbi < n_cb ? cb0 + cbi : cb0 + cbi - n_cb;
+    const int64_t j = cb * 256 + threadIdx.x;
     const bool jok = j < m;
     const float be = jok ? 1.0f - c * psq[j] : 1.0f;
-    const float lse_c = (CE && jok && wc != 0.f) ? col_lse[j] : 0.f;
+    const float ibe = 1.0f / be;
+    const float lse_c = (CE && jok && wc != 0.f) ? col_lse[j] : INFINITY;    // +inf: exp(sim - inf) = 0, no branch
     float cacc = 0.f;
+    // all 32 loads of the block are issued before the first use (the per-element version, with its branches, did
+    // one dependent HBM round trip per element: 1.34 ms for 0.5 GB of traffic); out-of-range rows / columns read
+    // a clamped address and are masked at the stores and sums
+    const int64_t jc = jok ? j : m - 1;
+    float dv[BW_ROWS], gv[BW_ROWS];
 #pragma unroll
     for (int r = 0; r < BW_ROWS; ++r) {
-      if (r < rows && jok) {
-        const int64_t o = (i0 + r) * m + j;
-        const float dd = dmat[o];
-        float gg;
-        if (CE) {
-          const float sim = -dd * inv_tau;
-          const float diag = (i0 + r == j) ? 1.0f : 0.0f;
-          gg = wr * (expf(sim - s_lse[r]) - diag);
-          if (wc != 0.f) gg += wc * (expf(sim - lse_c) - diag);
-          gg *= gsc;
-        } else {
-          gg = g[o];
-        }
-        const float al = s_al[r];
-        const float h = sinhf(half_sc * dd);
-        const float h2 = h * h;
-        const float sh = fmaxf(2.0f * h * sqrtf(1.0f + h2), 1e-15f);
-        const float ab = al * be;
-        const float w = gg * four_sc / (ab * sh);
-        w_out[o] = w;
-        const float cs = h2 * ab;                 // c * s
-        racc[r] += w * (1.0f + cs / al);
-        cacc += w * (1.0f + cs / be);
+      const int64_t o = (i0 + (r < rows ? r : rows - 1)) * m + jc;
+      dv[r] = dmat[o];
+      gv[r] = CE ? 0.f : g[o];
+    }
+#pragma unroll
+    for (int r = 0; r < BW_ROWS; ++r) {
+      const bool ok = r < rows && jok;
+      const float dd = dv[r];
+      float gg;
+      if (CE) {
+        const float sim = -dd * inv_tau;
+        const float diag = (i0 + r == j) ? 1.0f : 0.0f;
+        gg = gsc * (wr * (__expf(sim - s_lse[r]) - diag) + wc * (__expf(sim - lse_c) - diag));
+      } else {
+        gg = gv[r];
       }
+      // t = cosh(x) - 1 = 2 sinh^2(x/2), x = sqrt(c) d, without library calls or IEEE-division slow paths:
+      // (e^x + e^-x)/2 - 1 from one fast exp2 and one approximate reciprocal; below x = 0.35 that form
+      // cancels, so the even series x^2/2 (1 + x^2/12 (1 + x^2/30 (1 + x^2/56))) takes over (its first
+      // neglected term is < 2e-9 relative there).  sinh x = sqrt(t (t + 2)).
+      const float xx = sc * dd, x2 = xx * xx;
+      const float e = __expf(xx);
+      const float t_big = 0.5f * (e + __frcp_rn(e)) - 1.0f;
+      const float t_small = 0.5f * x2 * (1.0f + x2 * (1.0f / 12.0f) * (1.0f + x2 * (1.0f / 30.0f) * (1.0f + x2 * (1.0f / 56.0f))));
+      const float t = xx < 0.35f ? t_small : t_big;
+      const float t2 = fmaxf(t * (t + 2.0f), 1e-30f);
+      const float sh = t2 * rsqrtf(t2);         // sinh x
+      const float ab = s_al[r] * be;
+      const float w = ok ? gg * four_sc * __frcp_rn(ab * sh) : 0.f;
+      if (ok) {
+        if (SPLIT) {
+          __nv_bfloat16* wp = static_cast<__nv_bfloat16*>(w_out_raw);
+          const int64_t o = (i0 + r) * m + j, plane = n * m;
+          const __nv_bfloat16 hi = __float2bfloat16_rn(w);
+          const float r1 = w - __bfloat162float(hi);
+          const __nv_bfloat16 mid = __float2bfloat16_rn(r1);
+          wp[o] = hi;
+          wp[plane + o] = mid;
+          wp[2 * plane + o] = __float2bfloat16_rn(r1 - __bfloat162float(mid));
+        } else {
+          static_cast<float*>(w_out_raw)[(i0 + r) * m + j] = w;
+        }
+      }
+      const float cs = 0.5f * t * ab;           // c * s = h^2 alpha beta, h^2 = t / 2
+      racc[r] += w * (1.0f + cs * s_ial[r]);
+      cacc += w * (1.0f + cs * ibe);
     }
     if (jok) col_partial[(int64_t)blockIdx.x * m + j] = cacc;
   }
@@ -259,13 +297,17 @@ lse_cols_combine_kernel(const float* __restrict__ part_max, const float* __restr
 }  // namespace
 
 int hypret_launch_pairdist_bwd(const float* g, const float* dmat, const float* asq, const float* psq, int64_t n,
-                               int64_t m, float c, float* w_out, float* row_sum, float* col_partial, int n_partial,
-                               cudaStream_t stream) {
+                               int64_t m, float c, void* w_out, int w_format, float* row_sum, float* col_partial,
+                               int n_partial, cudaStream_t stream) {
   if (n == 0 || m == 0) return HYPRET_OK;
   if ((int64_t)n_partial * BW_ROWS < n) return HYPRET_EINVAL;     // one partial row of column sums per CTA of 32 rows
   const unsigned grid = (unsigned)((n + BW_ROWS - 1) / BW_ROWS);
-  pairdist_bwd_fused_kernel<false><<<grid, 256, 0, stream>>>(g, dmat, asq, psq, n, m, c, nullptr, nullptr, 0.f, 0.f,
-                                                            0.f, nullptr, w_out, row_sum, col_partial);
+  if (w_format == 1)
+    pairdist_bwd_fused_kernel<false, true><<<grid, 256, 0, stream>>>(g, dmat, asq, psq, n, m, c, nullptr, nullptr, 0.f,
+                                                                    0.f, 0.f, nullptr, w_out, row_sum, col_partial);
+  else
+    pairdist_bwd_fused_kernel<false, false><<<grid, 256, 0, stream>>>(g, dmat, asq, psq, n, m, c, nullptr, nullptr, 0.f,
+                                                                     0.f, 0.f, nullptr, w_out, row_sum, col_partial);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return (int)e;
   if ((int64_t)n_partial > (int64_t)grid)      // partial rows no CTA writes must read as zero
@@ -282,6 +324,13 @@ int hypret_launch_pairdist_ce_fwd(const float* a, const float* p, int64_t n, int
   pairdist_kernel<true><<<grid, 256, 0, stream>>>(a, p, n, m, d, c, dmat);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return (int)e;
+  return hypret_launch_neg_lse(dmat, n, m, inv_tau, want_cols, row_lse, col_lse, scratch, n_part, stream);
+}
+
+int hypret_launch_neg_lse(const float* dmat, int64_t n, int64_t m, float inv_tau, int want_cols, float* row_lse,
+                          float* col_lse, float* scratch, int n_part, cudaStream_t stream) {
+  if (n == 0 || m == 0) return HYPRET_OK;
+  cudaError_t e;
   lse_rows_kernel<<<(unsigned)((n + 7) / 8), 256, 0, stream>>>(dmat, n, m, inv_tau, row_lse);
   e = cudaGetLastError();
   if (e != cudaSuccess) return (int)e;
@@ -299,12 +348,18 @@ int hypret_launch_pairdist_ce_fwd(const float* a, const float* p, int64_t n, int
 
 int hypret_launch_pairdist_ce_bwd(const float* dmat, const float* asq, const float* psq, int64_t n, int64_t m, float c,
                                   const float* row_lse, const float* col_lse, float inv_tau, float wr, float wc,
-                                  const float* grad_scale, float* w_out, float* row_sum, float* col_partial,
-                                  cudaStream_t stream) {
+                                  const float* grad_scale, void* w_out, int w_format, float* row_sum,
+                                  float* col_partial, cudaStream_t stream) {
   if (n == 0 || m == 0) return HYPRET_OK;
   const unsigned grid = (unsigned)((n + BW_ROWS - 1) / BW_ROWS);
-  pairdist_bwd_fused_kernel<true><<<grid, 256, 0, stream>>>(nullptr, dmat, asq, psq, n, m, c, row_lse, col_lse, inv_tau,
-                                                           wr, wc, grad_scale, w_out, row_sum, col_partial);
+  if (w_format == 1)
+    pairdist_bwd_fused_kernel<true, true><<<grid, 256, 0, stream>>>(nullptr, dmat, asq, psq, n, m, c, row_lse, col_lse,
+                                                                   inv_tau, wr, wc, grad_scale, w_out, row_sum,
+                                                                   col_partial);
+  else
+    pairdist_bwd_fused_kernel<true, false><<<grid, 256, 0, stream>>>(nullptr, dmat, asq, psq, n, m, c, row_lse, col_lse,
+                                                                    inv_tau, wr, wc, grad_scale, w_out, row_sum,
+                                                                    col_partial);
   return (int)cudaGetLastError();
 }
 

@@ -331,18 +331,54 @@ def ap_from_counts(pos_offsets: torch.Tensor, pos_items: torch.Tensor, pos_keys:
     return float(mean.item()), ap, valid
 
 
-def pairdist_ce_fwd(a: torch.Tensor, p: torch.Tensor, c: float, inv_tau: float, want_cols: bool):
-    """Distance matrix (fp32 tail) + row / column log-sum-exps of ``-D * inv_tau``.
-    Returns ``(dmat [n,m], row_lse [n], col_lse [m] | None)``."""
+GRAM_MAX_D = 1024      # tensor-core distance matrix: feature dimensions it supports
+GRAM_MIN_PAIRS = 1 << 16   # below this the CUDA-core tile kernel is as fast (launch-bound either way)
+
+
+def gram_dist(a: torch.Tensor, p: torch.Tensor, c: float):
+    """Distance matrix ``[n,m]`` on the tensor cores (3-way bf16 split operands, exact recompute of near pairs);
+    training accuracy (~1e-6 relative).  Returns ``(dmat, |a|^2 [n], |p|^2 [m])``."""
     _need_cuda(a, p)
     a, p = a.contiguous().float(), p.contiguous().float()
     n, d = a.shape
     m = p.shape[0]
-    dmat = torch.empty(n, m, dtype=torch.float32, device=a.device)
+    lib = _lib.load()
+    kp = int(lib.hypret_gram_kpad(d))
+    a_op = torch.empty(n, kp, dtype=torch.bfloat16, device=a.device)
+    p_op = torch.empty(m, kp, dtype=torch.bfloat16, device=a.device)
+    asq = torch.empty(n, dtype=torch.float32, device=a.device)
+    psq = torch.empty(m, dtype=torch.float32, device=a.device)
+    out = torch.empty(n, m, dtype=torch.float32, device=a.device)
+    with torch.cuda.device(a.device):
+        _lib.check(lib.hypret_gram_split(_ptr(a), n, d, 0, _ptr(a_op), _ptr(asq), _stream()))
+        _lib.check(lib.hypret_gram_split(_ptr(p), m, d, 1, _ptr(p_op), _ptr(psq), _stream()))
+        _lib.check(lib.hypret_gram_dist(_ptr(a_op), _ptr(p_op), _ptr(a), _ptr(p), _ptr(asq), _ptr(psq), n, m, d,
+                                        float(c), _ptr(out), _stream()))
+    return out, asq, psq
+
+
+def pairdist_ce_fwd(a: torch.Tensor, p: torch.Tensor, c: float, inv_tau: float, want_cols: bool,
+                    tensor_cores: Optional[bool] = None):
+    """Distance matrix (fp32 tail) + row / column log-sum-exps of ``-D * inv_tau``.
+    ``tensor_cores`` (default: whenever the shape allows): the Gram matrix comes from the tcgen05 kernel of
+    ``gram_dist`` instead of the FP32-FMA tile kernel.  Returns ``(dmat [n,m], row_lse [n], col_lse [m] | None)``."""
+    _need_cuda(a, p)
+    a, p = a.contiguous().float(), p.contiguous().float()
+    n, d = a.shape
+    m = p.shape[0]
+    if tensor_cores is None:
+        tensor_cores = d <= GRAM_MAX_D and d % 4 == 0 and n * m >= GRAM_MIN_PAIRS
     row_lse = torch.empty(n, dtype=torch.float32, device=a.device)
     col_lse = torch.empty(m, dtype=torch.float32, device=a.device) if want_cols else None
     n_part = max(1, min(64, (n + 127) // 128))
     scratch = torch.empty(2 * n_part * m, dtype=torch.float32, device=a.device) if want_cols else None
+    if tensor_cores:
+        dmat, _, _ = gram_dist(a, p, c)
+        with torch.cuda.device(a.device):
+            _lib.check(_lib.load().hypret_neg_lse(_ptr(dmat), n, m, float(inv_tau), int(bool(want_cols)), _ptr(row_lse),
+                                                  _ptr(col_lse), _ptr(scratch), n_part, _stream()))
+        return dmat, row_lse, col_lse
+    dmat = torch.empty(n, m, dtype=torch.float32, device=a.device)
     with torch.cuda.device(a.device):
         _lib.check(_lib.load().hypret_pairdist_ce_fwd(_ptr(a), _ptr(p), n, m, d, float(c), float(inv_tau),
                                                       int(bool(want_cols)), _ptr(dmat), _ptr(row_lse), _ptr(col_lse),

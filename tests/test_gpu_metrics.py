@@ -251,3 +251,55 @@ def test_fused_head_large_and_clipped_rows():
     scale = want.norm(dim=1, keepdim=True).clamp_min(1e-20)
     assert float(((got - want).abs() / scale).max()) < 2e-5
     assert float(got.norm(dim=1).max()) <= (1 - 4e-3) / c ** 0.5 * (1 + 1e-6)
+
+
+@pytest.mark.parametrize("n,m,d,c", [(300, 520, 128, 1.0), (129, 257, 256, 0.5), (64, 64, 20, 2.0), (1000, 700, 512, 1.0)])
+def test_tensor_core_distance_matrix_matches_oracle(n, m, d, c):
+    """csrc/gramdist.cu (3-way bf16 split Gram matrix on tcgen05 + exact recompute of near pairs) against the fp64
+    oracle and the exact CUDA-core kernel, including near duplicates and ragged tiles."""
+    from oracle import head
+    a = head.embed_rows(synth.gaussian_features(n, d, seed=1, scale=1.0), c)
+    p = head.embed_rows(synth.gaussian_features(m, d, seed=0, scale=1.0), c)
+    p[:5] = a[:5] * (1 + 1e-4)                                   # near duplicates: the cancellation case
+    p[5:9] = a[5:9] * 0.9
+    got, asq, psq = ops.gram_dist(a.cuda(), p.cuda(), c)
+    got = got.cpu()
+    d64 = retrieval.hyperbolic_dist_rows(a.double(), p.double(), c, form="arcosh")
+    exact = ops.pairdist(a.cuda(), p.cuda(), c).cpu()
+    far = d64 > 1e-2
+    assert float(((got.double() - d64).abs() / d64)[far].max()) < 1e-5        # BASELINE north_star: 1e-5 relative
+    assert float(((got - exact).abs() / exact)[far].max()) < 1e-5
+    assert float(((got.double() - d64).abs() / d64)[~far].max()) < 1e-3       # near pairs: exact path, as pairdist
+    torch.testing.assert_close(asq.cpu(), a.pow(2).sum(1), rtol=1e-5, atol=0)
+    torch.testing.assert_close(psq.cpu(), p.pow(2).sum(1), rtol=1e-5, atol=0)
+
+
+def test_infonce_tensor_core_path_matches_cuda_core_path():
+    from oracle import head
+    from patent_image_retrieval_b200 import train
+    c, n, d, tau = 1.0, 384, 128, 0.5
+    mu = synth.gaussian_features(n, d, seed=2, scale=1.0)
+    a0 = head.embed_rows(mu + 0.3 * synth.gaussian_features(n, d, seed=3, scale=1.0), c).cuda()
+    p0 = head.embed_rows(mu + 0.3 * synth.gaussian_features(n, d, seed=4, scale=1.0), c).cuda()
+    inv_tau = 1.0 / tau
+    d_tc, r_tc, c_tc = ops.pairdist_ce_fwd(a0, p0, c, inv_tau, True, tensor_cores=True)
+    d_cc, r_cc, c_cc = ops.pairdist_ce_fwd(a0, p0, c, inv_tau, True, tensor_cores=False)
+    torch.testing.assert_close(d_tc, d_cc, rtol=1e-5, atol=1e-7)
+    torch.testing.assert_close(r_tc, r_cc, rtol=1e-5, atol=1e-5)
+    torch.testing.assert_close(c_tc, c_cc, rtol=1e-5, atol=1e-5)
+    k = torch.tensor([-c])
+    for sym in (False, True):
+        ag, pg = a0.clone().requires_grad_(True), p0.clone().requires_grad_(True)
+        loss = train.InBatchInfoNCE.apply(ag, pg, c, tau, sym)          # tensor-core forward (n*m >= 2^16)
+        loss.backward()
+        a64, p64 = a0.cpu().double().requires_grad_(True), p0.cpu().double().requires_grad_(True)
+        from oracle import contrastive
+        sim = -contrastive.dist_matrix(a64, p64, k.double()) / tau
+        lab = torch.arange(n)
+        ref = torch.nn.functional.cross_entropy(sim, lab)
+        if sym:
+            ref = (ref + torch.nn.functional.cross_entropy(sim.t(), lab)) / 2
+        ref.backward()
+        assert float(loss) == pytest.approx(float(ref), rel=2e-5)
+        for got, want in ((ag.grad, a64.grad), (pg.grad, p64.grad)):
+            assert float((got.cpu().double() - want).abs().max() / want.abs().max()) < 1e-4
