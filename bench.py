@@ -297,11 +297,14 @@ def main():
     flops = 2.0 * q_scored * n_local * D
     kpad = ops.operand_kpad(D)
     project_bytes = q_scored * (4 * D + 4 * D + 2 * kpad)          # read f32 row, write f32 point + bf16 operand row
+    if world > 1 and weak and getattr(index, "_exchange", None) is not None:
+        project_bytes = Q * (4 * D + 4 * D + world * 2 * kpad)     # own rows only; operand row stored to every rank
     # exact rescoring: k' gathered fp32 rows per query; with the cross-shard surrogate threshold (weak mode) the
     # W shards share one query's k' rows between them
     rerank_bytes = q_scored * kprime * D * 4 // (world if weak else 1)
-    n_own = 3 if world == 1 else (6 if weak else 4)                # own kernels per step (see gpu_launches_note)
-    n_nccl = 0 if world == 1 else (6 if weak else 2)
+    peer_x = weak and getattr(index, "_exchange", None) is not None    # query exchange through peer memory
+    n_own = 3 if world == 1 else ((10 if peer_x else 6) if weak else 4)   # own kernels per step (gpu_launches_note)
+    n_nccl = 0 if world == 1 else ((4 if peer_x else 5) if weak else 2)
     achieved = flops / (score_ms * 1e-3) / 1e12
     traffic = None
     tp = ROOT / "profiles" / "score_topk_traffic.json"
@@ -318,7 +321,10 @@ def main():
         "config": {"workload": desc, "Q": Q, "N": N, "D": D, "k": k, "c": c, "kprime": kprime,
                    "queries_per_step_total": q_total, "gallery_rows_per_gpu": n_local,
                    "parallelism": (f"gallery row-shard x{world}; " +
-                                   ("each rank fed its own Q-query batch per step: all_gather(queries) -> shard-local "
+                                   ("each rank fed its own Q-query batch per step: " +
+                                    ("projection kernel stores the operand rows into every rank's buffer over NVLink "
+                                     "(peer memory), fp32 rows follow by copy engine under the scoring kernel"
+                                     if peer_x else "all_gather(queries)") + " -> shard-local "
                                     "search of all W*Q -> all_to_all([Q,k] lists) -> merge at the owner" if weak else
                                     "queries replicated: shard-local search -> all_gather([Q,k] lists) -> merge"))
                    if world > 1 else "single GPU",
@@ -332,7 +338,8 @@ def main():
                 "serial": {"value": q_total / (ms_e2e_serial * 1e-3), "ms_per_step": ms_e2e_serial}},
         "gpu_launches": args.steps * n_own,
         "gpu_launches_note": "own kernels per step per rank: project_rows, score_topk, " +
-                             ("cand_select, kth_smallest, rerank (pruned), merge_topk" if weak else
+                             (("peer_signal x2, peer_wait x2, " if peer_x else "") +
+                              "cand_select, kth_smallest, rerank (pruned), merge_topk" if weak else
                               "rerank, merge_topk" if world > 1 else "rerank") +
                              (" (+ %d NCCL collectives)" % n_nccl if world > 1 else ""),
         "roofline": {"bound": "tensor", "achieved": achieved, "peak": peaks["tflops_sustained"], "unit": "TFLOP/s",
@@ -343,7 +350,8 @@ def main():
             {"kernel": "project_rows_kernel", "bound": "hbm", "kernel_ms": project_ms, "algorithmic_bytes": project_bytes,
              "achieved": project_bytes / (project_ms * 1e-3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
              "frac": project_bytes / (project_ms * 1e-3) / 1e9 / peaks["hbm_gbs"],
-             "note": "query side only (%d rows): launch-latency sized at this Q" % q_scored},
+             "note": ("own %d rows, operand stored into all %d ranks' buffers over NVLink + arrival wait" % (Q, world))
+                     if peer_x else "query side only (%d rows): launch-latency sized at this Q" % q_scored},
             {"kernel": "rerank_kernel", "bound": "hbm", "kernel_ms": rerank_ms, "algorithmic_bytes": rerank_bytes,
              "achieved": rerank_bytes / (rerank_ms * 1e-3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
              "frac": rerank_bytes / (rerank_ms * 1e-3) / 1e9 / peaks["hbm_gbs"],

@@ -61,6 +61,29 @@ int64_t hypret_operand_kpad(int d);
 int hypret_project_rows(const float* u, int64_t n, int d, float c, int mode, int side, float* y32, void* op_bf16,
                         float* sqnorm, void* stream);
 
+/* ---- Peer-memory exchange (multi-GPU serving on one NVLink / NVSwitch box; csrc/peer.cu) ------------------
+ * The reference is single-GPU; these replace the NCCL all_gather of the per-rank query batches in the
+ * sharded-serving protocol.  One process per GPU; every device of the box visible to every process.
+ *   hypret_peer_alloc   cudaMalloc + zero-fill `bytes`, and the 64-byte CUDA IPC handle to send to the peers
+ *   hypret_peer_open    map a peer's buffer from its handle (peer access is enabled on demand)
+ *   hypret_peer_close / hypret_peer_free   undo the two above
+ *   hypret_peer_copy    asynchronous copy between any two mapped buffers (copy engines; no SM)
+ *   hypret_project_rows_peers   hypret_project_rows for query rows, with the bf16 operand row stored into
+ *                       n_dst destination buffers (op_dsts_host: HOST array of device pointers, each already
+ *                       offset to the block of this rank) -- the projection is the all-gather
+ *   hypret_peer_signal  behind everything queued on `stream` so far: *flags_host[i] = value (release, system scope)
+ *   hypret_peer_wait    hold `stream` until flags[i] >= value for all i < n (20 s bound: then *err = 1 + i) */
+#define HYPRET_IPC_HANDLE_BYTES 64
+int hypret_peer_alloc(size_t bytes, void** dev_ptr, void* handle_out_host);
+int hypret_peer_free(void* dev_ptr);
+int hypret_peer_open(const void* handle_host, void** peer_ptr);
+int hypret_peer_close(void* peer_ptr);
+int hypret_peer_copy(void* dst, const void* src, size_t bytes, void* stream);
+int hypret_project_rows_peers(const float* u, int64_t n, int d, float c, int mode, float* y32,
+                              void* const* op_dsts_host, int n_dst, void* stream);
+int hypret_peer_signal(void* const* flags_host, int n, uint32_t value, void* stream);
+int hypret_peer_wait(const uint32_t* flags, int n, uint32_t value, uint32_t* err, void* stream);
+
 /* Work decomposition of hypret_score_topk for a problem size on the current device.
  * The gallery is swept in "strips" (query tile x contiguous gallery-tile range); a query
  * receives one candidate list per strip that visits it.  See csrc/score_topk.cu. */
@@ -191,14 +214,17 @@ int hypret_pairdist(const float* a, const float* p, int64_t n, int64_t m, int d,
  * nodes per pair, src/train.py:1846).  Given grad_out = dL/dD [n,m] and the forward matrix dmat, ONE fp32 pass:
  *   w_out                    W (see csrc/pairdist.cu): w_format 0 = fp32 [n,m]; 1 = three bf16 planes [3,n,m] (hi, mid,
  *                            lo; hi+mid+lo = W to fp32 accuracy) for split-bf16 tensor-core GEMMs of the two products
- *   row_sum [n]              sum_j W_ij (1 + c s_ij / alpha_i)
- *   col_partial [n_partial,m]  partial column sums of W_ij (1 + c s_ij / beta_j), one row per 32 matrix rows:
- *                            n_partial >= ceil(n/32); sum over dim 0
+ *   row_partial [n_row_partial,n]  partial row sums of W_ij (1 + c s_ij / alpha_i): the columns are cut into
+ *                            n_row_partial chunks (grid = ceil(n/16) x n_row_partial CTAs; pick it so that the grid
+ *                            is several waves of 2 CTAs per SM); sum over dim 0
+ *   col_partial [n_partial,m]  partial column sums of W_ij (1 + c s_ij / beta_j), one row per HYPRET_BWD_ROWS (16)
+ *                            matrix rows: n_partial >= ceil(n/16); sum over dim 0
  * so that  dA = a * row_sum[:,None] - W P,  dP = p * col_sum[:,None] - W^T A  (two plain GEMMs
  * left to the caller).  asq / psq = squared norms of the rows of a / p. */
+#define HYPRET_BWD_ROWS 16
 int hypret_pairdist_bwd(const float* grad_out, const float* dmat, const float* asq, const float* psq, int64_t n,
-                        int64_t m, float c, void* w_out, int w_format, float* row_sum, float* col_partial, int n_partial,
-                        void* stream);
+                        int64_t m, float c, void* w_out, int w_format, float* row_partial, int n_row_partial,
+                        float* col_partial, int n_partial, void* stream);
 
 /* In-batch InfoNCE over the distance matrix, forward and backward, without torch passes over [n,m]
  * (src/train.py:1832-1844 rows only; 2304-2334 symmetric).  sim = -D * inv_tau.
@@ -207,14 +233,14 @@ int hypret_pairdist_bwd(const float* grad_out, const float* dmat, const float* a
  *   mean_i(row_lse_i - sim_ii) (+ mean_j(col_lse_j - sim_jj), halved) -- O(n) work left to the caller.
  * hypret_pairdist_ce_bwd: like hypret_pairdist_bwd, but the upstream gradient is formed on the fly:
  *   g_ij = -(gs * inv_tau / n) [ w_rows (exp(sim_ij - row_lse_i) - [i==j]) + w_cols (exp(sim_ij - col_lse_j) - [i==j]) ]
- *   with gs = *grad_scale (device scalar, NULL = 1).  col_partial [ceil(n/32), m]; row_sum [n]. */
+ *   with gs = *grad_scale (device scalar, NULL = 1).  col_partial [ceil(n/16), m]; row_partial [n_row_partial, n] as above. */
 int hypret_pairdist_ce_fwd(const float* a, const float* p, int64_t n, int64_t m, int d, float c, float inv_tau,
                            int want_col_lse, float* dmat, float* row_lse, float* col_lse, float* scratch,
                            int n_part, void* stream);
 int hypret_pairdist_ce_bwd(const float* dmat, const float* asq, const float* psq, int64_t n, int64_t m, float c,
                            const float* row_lse, const float* col_lse, float inv_tau, float w_rows, float w_cols,
-                           const float* grad_scale, void* w_out, int w_format, float* row_sum, float* col_partial,
-                           void* stream);
+                           const float* grad_scale, void* w_out, int w_format, float* row_partial, int n_row_partial,
+                           float* col_partial, void* stream);
 
 /* The same n x m distance matrix on the TENSOR CORES (training path, csrc/gramdist.cu): one tcgen05 GEMM over
  * operands that carry a 3-way bf16 split of the fp32 rows along K (six cross products = the fp32 inner product),

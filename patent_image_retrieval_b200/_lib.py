@@ -7,7 +7,8 @@ first call raises.  Every wrapper checks the integer status and raises
 from __future__ import annotations
 
 import ctypes
-from ctypes import c_char_p, c_float, c_int, c_int32, c_int64, c_void_p, POINTER, Structure
+from ctypes import (c_char_p, c_float, c_int, c_int32, c_int64, c_size_t, c_uint32, c_void_p, POINTER,
+                    Structure)
 
 from . import build as _build
 
@@ -50,6 +51,15 @@ SIGNATURES = {
     "hypret_operand_kpad": (c_int64, [c_int]),
     "hypret_project_rows": (c_int, [c_void_p, c_int64, c_int, c_float, c_int, c_int, c_void_p, c_void_p, c_void_p,
                                     c_void_p]),
+    "hypret_peer_alloc": (c_int, [c_size_t, POINTER(c_void_p), c_void_p]),
+    "hypret_peer_free": (c_int, [c_void_p]),
+    "hypret_peer_open": (c_int, [c_void_p, POINTER(c_void_p)]),
+    "hypret_peer_close": (c_int, [c_void_p]),
+    "hypret_peer_copy": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p]),
+    "hypret_project_rows_peers": (c_int, [c_void_p, c_int64, c_int, c_float, c_int, c_void_p, POINTER(c_void_p), c_int,
+                                          c_void_p]),
+    "hypret_peer_signal": (c_int, [POINTER(c_void_p), c_int, c_uint32, c_void_p]),
+    "hypret_peer_wait": (c_int, [c_void_p, c_int, c_uint32, c_void_p, c_void_p]),
     "hypret_score_plan": (c_int, [c_int64, c_int64, c_int, c_int, c_int, c_int, POINTER(ScorePlan)]),
     "hypret_score_strip": (c_int, [POINTER(ScorePlan), c_int, c_int, POINTER(c_int32)]),
     "hypret_score_topk": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int, c_int, c_int, c_int, c_int, c_void_p,
@@ -64,11 +74,11 @@ SIGNATURES = {
                                        c_void_p, c_void_p, c_void_p]),
     "hypret_pairdist": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int, c_float, c_void_p, c_void_p]),
     "hypret_pairdist_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_float, c_void_p, c_int,
-                                    c_void_p, c_void_p, c_int, c_void_p]),
+                                    c_void_p, c_int, c_void_p, c_int, c_void_p]),
     "hypret_pairdist_ce_fwd": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int, c_float, c_float, c_int, c_void_p,
                                        c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
     "hypret_pairdist_ce_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_float, c_void_p, c_void_p,
-                                       c_float, c_float, c_float, c_void_p, c_void_p, c_int, c_void_p, c_void_p,
+                                       c_float, c_float, c_float, c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p,
                                        c_void_p]),
     "hypret_gram_kpad": (c_int64, [c_int]),
     "hypret_gram_split": (c_int, [c_void_p, c_int64, c_int, c_int, c_void_p, c_void_p, c_void_p]),

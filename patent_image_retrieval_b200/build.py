@@ -18,6 +18,7 @@ CSRC = PKG_DIR / "csrc"
 INCLUDE = PKG_DIR.parent / "include"
 LIB_PATH = PKG_DIR / "libhypret.so"
 STAMP = PKG_DIR / ".libhypret.stamp"
+OBJ_DIR = PKG_DIR / "build"
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
@@ -51,22 +52,46 @@ def is_fresh() -> bool:
     return LIB_PATH.exists() and STAMP.exists() and STAMP.read_text().strip() == _fingerprint()
 
 
+def _compile_one(nvcc: str, src: Path, obj: Path, verbose: bool) -> str:
+    cmd = [nvcc, *[f for f in NVCC_FLAGS if f != "-shared"], "-c", "-o", str(obj), str(src)]
+    if verbose:
+        cmd[1:1] = ["-Xptxas", "-v"]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError(f"nvcc failed on {src.name} ({res.returncode}):\n{res.stdout}\n{res.stderr}")
+    return res.stderr
+
+
 def build(force: bool = False, verbose: bool = False) -> Path:
+    """One object per ``csrc/*.cu`` (compiled in parallel, recompiled only when that source, a header or the
+    flags changed), linked into ``libhypret.so``."""
     if not force and is_fresh():
         return LIB_PATH
     nvcc = find_nvcc()
     if nvcc is None:
         raise RuntimeError("nvcc not found: cannot build libhypret.so (no CPU fallback exists)")
-    cmd = [nvcc, *NVCC_FLAGS, "-o", str(LIB_PATH), *map(str, sources())]
-    if verbose:
-        cmd.insert(1, "-Xptxas")
-        cmd.insert(2, "-v")
-        print(" ".join(cmd), file=sys.stderr)
-    res = subprocess.run(cmd, capture_output=True, text=True)
+    from concurrent.futures import ThreadPoolExecutor
+    OBJ_DIR.mkdir(exist_ok=True)
+    shared = hashlib.sha256()
+    for f in sorted(list(CSRC.glob("*.cuh")) + list(INCLUDE.glob("*.h"))):
+        shared.update(f.read_bytes())
+    shared.update(" ".join(NVCC_FLAGS).encode())
+    jobs = []
+    for src in sources():
+        obj, tag = OBJ_DIR / (src.stem + ".o"), OBJ_DIR / (src.stem + ".tag")
+        want = hashlib.sha256(shared.digest() + src.read_bytes()).hexdigest()
+        if force or not obj.exists() or not tag.exists() or tag.read_text() != want:
+            jobs.append((src, obj, tag, want))
+    with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as pool:
+        logs = list(pool.map(lambda j: _compile_one(nvcc, j[0], j[1], verbose), jobs))
+    for (src, obj, tag, want), log in zip(jobs, logs):
+        tag.write_text(want)
+        if verbose:
+            print(f"== {src.name}\n{log}", file=sys.stderr)
+    objs = [str(OBJ_DIR / (s.stem + ".o")) for s in sources()]
+    res = subprocess.run([nvcc, "-shared", "-o", str(LIB_PATH), *objs], capture_output=True, text=True)
     if res.returncode != 0:
-        raise RuntimeError(f"nvcc failed ({res.returncode}):\n{res.stdout}\n{res.stderr}")
-    if verbose:
-        print(res.stderr, file=sys.stderr)
+        raise RuntimeError(f"link failed ({res.returncode}):\n{res.stdout}\n{res.stderr}")
     STAMP.write_text(_fingerprint())
     return LIB_PATH
 

@@ -1,5 +1,7 @@
 // extern "C" boundary of libhypret.so -- argument validation and dispatch only.
 // Signatures and the reference call sites they replace are documented in include/hypret.h.
+#include <cstring>
+
 #include "common.cuh"
 
 namespace {
@@ -47,6 +49,69 @@ int hypret_project_rows(const float* u, int64_t n, int d, float c, int mode, int
   int rc = check_device();
   if (rc != HYPRET_OK) return rc;
   return hypret_launch_project_rows(u, n, d, c, mode, side, y32, op_bf16, sqnorm, static_cast<cudaStream_t>(stream));
+}
+
+int hypret_peer_alloc(size_t bytes, void** dev_ptr, void* handle_out_host) {
+  if (bytes == 0 || dev_ptr == nullptr || handle_out_host == nullptr) return HYPRET_EINVAL;
+  static_assert(sizeof(cudaIpcMemHandle_t) == HYPRET_IPC_HANDLE_BYTES, "IPC handle size");
+  void* p = nullptr;
+  cudaError_t e = cudaMalloc(&p, bytes);
+  if (e != cudaSuccess) return (int)e;
+  e = cudaMemset(p, 0, bytes);
+  if (e == cudaSuccess) e = cudaDeviceSynchronize();
+  cudaIpcMemHandle_t h;
+  if (e == cudaSuccess) e = cudaIpcGetMemHandle(&h, p);
+  if (e != cudaSuccess) {
+    cudaFree(p);
+    return (int)e;
+  }
+  memcpy(handle_out_host, &h, sizeof(h));
+  *dev_ptr = p;
+  return HYPRET_OK;
+}
+
+int hypret_peer_free(void* dev_ptr) { return dev_ptr == nullptr ? HYPRET_OK : (int)cudaFree(dev_ptr); }
+
+int hypret_peer_open(const void* handle_host, void** peer_ptr) {
+  if (handle_host == nullptr || peer_ptr == nullptr) return HYPRET_EINVAL;
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle_host, sizeof(h));
+  return (int)cudaIpcOpenMemHandle(peer_ptr, h, cudaIpcMemLazyEnablePeerAccess);
+}
+
+int hypret_peer_close(void* peer_ptr) { return peer_ptr == nullptr ? HYPRET_OK : (int)cudaIpcCloseMemHandle(peer_ptr); }
+
+int hypret_peer_copy(void* dst, const void* src, size_t bytes, void* stream) {
+  if (bytes == 0) return HYPRET_OK;
+  if (dst == nullptr || src == nullptr) return HYPRET_EINVAL;
+  return (int)cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, static_cast<cudaStream_t>(stream));
+}
+
+int hypret_project_rows_peers(const float* u, int64_t n, int d, float c, int mode, float* y32,
+                              void* const* op_dsts_host, int n_dst, void* stream) {
+  if (n < 0 || d < 4 || (d & 3) || d > 2048 || n_dst < 1 || n_dst > HYPRET_MAX_PEERS) return HYPRET_EINVAL;
+  if (mode < HYPRET_MODE_EXPMAP0 || mode > HYPRET_MODE_COSINE) return HYPRET_EINVAL;
+  if (mode != HYPRET_MODE_COSINE && !(c > 0.f)) return HYPRET_EINVAL;
+  if (n == 0) return HYPRET_OK;
+  if (u == nullptr || op_dsts_host == nullptr || !aligned16(u) || !aligned16(y32)) return HYPRET_EINVAL;
+  for (int i = 0; i < n_dst; ++i)
+    if (op_dsts_host[i] == nullptr || !aligned16(op_dsts_host[i])) return HYPRET_EINVAL;
+  int rc = check_device();
+  if (rc != HYPRET_OK) return rc;
+  return hypret_launch_project_rows_peers(u, n, d, c, mode, y32, op_dsts_host, n_dst,
+                                          static_cast<cudaStream_t>(stream));
+}
+
+int hypret_peer_signal(void* const* flags_host, int n, uint32_t value, void* stream) {
+  if (flags_host == nullptr || n < 1 || n > HYPRET_MAX_PEERS) return HYPRET_EINVAL;
+  for (int i = 0; i < n; ++i)
+    if (flags_host[i] == nullptr) return HYPRET_EINVAL;
+  return hypret_launch_peer_signal(flags_host, n, value, static_cast<cudaStream_t>(stream));
+}
+
+int hypret_peer_wait(const uint32_t* flags, int n, uint32_t value, uint32_t* err, void* stream) {
+  if (flags == nullptr || n < 1 || n > HYPRET_MAX_PEERS) return HYPRET_EINVAL;
+  return hypret_launch_peer_wait(flags, n, value, err, static_cast<cudaStream_t>(stream));
 }
 
 int hypret_score_topk(const void* q_op, int64_t Q, const void* g_op, int64_t N, int d, int kprime, int n_lists,
@@ -151,18 +216,19 @@ int hypret_pairdist(const float* a, const float* p, int64_t n, int64_t m, int d,
 }
 
 int hypret_pairdist_bwd(const float* grad_out, const float* dmat, const float* asq, const float* psq, int64_t n,
-                        int64_t m, float c, void* w_out, int w_format, float* row_sum, float* col_partial, int n_partial,
-                        void* stream) {
-  if (n < 0 || m < 0 || !(c > 0.f) || n_partial < 1 || n_partial > 65535 || (w_format != 0 && w_format != 1))
+                        int64_t m, float c, void* w_out, int w_format, float* row_partial, int n_row_partial,
+                        float* col_partial, int n_partial, void* stream) {
+  if (n < 0 || m < 0 || !(c > 0.f) || n_partial < 1 || n_partial > 65535 || (w_format != 0 && w_format != 1) ||
+      n_row_partial < 1 || n_row_partial > 65535)
     return HYPRET_EINVAL;
   if (n == 0 || m == 0) return HYPRET_OK;
   if (grad_out == nullptr || dmat == nullptr || asq == nullptr || psq == nullptr || w_out == nullptr ||
-      row_sum == nullptr || col_partial == nullptr)
+      row_partial == nullptr || col_partial == nullptr)
     return HYPRET_EINVAL;
   int rc = check_device();
   if (rc != HYPRET_OK) return rc;
-  return hypret_launch_pairdist_bwd(grad_out, dmat, asq, psq, n, m, c, w_out, w_format, row_sum, col_partial, n_partial,
-                                    static_cast<cudaStream_t>(stream));
+  return hypret_launch_pairdist_bwd(grad_out, dmat, asq, psq, n, m, c, w_out, w_format, row_partial, n_row_partial,
+                                    col_partial, n_partial, static_cast<cudaStream_t>(stream));
 }
 
 int hypret_pairdist_ce_fwd(const float* a, const float* p, int64_t n, int64_t m, int d, float c, float inv_tau,
@@ -218,17 +284,20 @@ int hypret_neg_lse(const float* dmat, int64_t n, int64_t m, float inv_tau, int w
 
 int hypret_pairdist_ce_bwd(const float* dmat, const float* asq, const float* psq, int64_t n, int64_t m, float c,
                            const float* row_lse, const float* col_lse, float inv_tau, float w_rows, float w_cols,
-                           const float* grad_scale, void* w_out, int w_format, float* row_sum, float* col_partial,
-                           void* stream) {
-  if (n < 0 || m < 0 || !(c > 0.f) || !(inv_tau > 0.f) || (w_format != 0 && w_format != 1)) return HYPRET_EINVAL;
+                           const float* grad_scale, void* w_out, int w_format, float* row_partial, int n_row_partial,
+                           float* col_partial, void* stream) {
+  if (n < 0 || m < 0 || !(c > 0.f) || !(inv_tau > 0.f) || (w_format != 0 && w_format != 1) || n_row_partial < 1 ||
+      n_row_partial > 65535)
+    return HYPRET_EINVAL;
   if (n == 0 || m == 0) return HYPRET_OK;
   if (dmat == nullptr || asq == nullptr || psq == nullptr || row_lse == nullptr || w_out == nullptr ||
-      row_sum == nullptr || col_partial == nullptr || (w_cols != 0.f && col_lse == nullptr))
+      row_partial == nullptr || col_partial == nullptr || (w_cols != 0.f && col_lse == nullptr))
     return HYPRET_EINVAL;
   int rc = check_device();
   if (rc != HYPRET_OK) return rc;
   return hypret_launch_pairdist_ce_bwd(dmat, asq, psq, n, m, c, row_lse, col_lse, inv_tau, w_rows, w_cols, grad_scale,
-                                       w_out, w_format, row_sum, col_partial, static_cast<cudaStream_t>(stream));
+                                       w_out, w_format, row_partial, n_row_partial, col_partial,
+                                       static_cast<cudaStream_t>(stream));
 }
 
 int hypret_retrieval_metrics(const int64_t* ranked, int64_t Q, int K, const int64_t* pos_offsets,

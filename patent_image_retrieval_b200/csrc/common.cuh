@@ -17,6 +17,7 @@
 // ----------------------------------------------------------------------------- geometry
 // bf16 GEMM operand row = [ Dpad main columns | 16 extension columns ], Dpad = roundup(D, 64).
 constexpr int HYPRET_KBLK = 64;   // K elements per 128B-swizzled block
+constexpr int HYPRET_MAX_PEERS = 16;   // ranks of one NVLink box an exchange buffer can address
 constexpr int HYPRET_KEXT = 16;   // extension block: one UMMA_K step (32B-swizzled)
 
 __host__ __device__ inline int hypret_dpad(int d) { return (d + HYPRET_KBLK - 1) / HYPRET_KBLK * HYPRET_KBLK; }
@@ -305,6 +306,10 @@ __device__ __forceinline__ double warp_sum(double v) {
 #endif  // __CUDACC__
 
 // ----------------------------------------------------------------------------- launchers (one per .cu)
+int hypret_launch_project_rows_peers(const float* u, int64_t n, int d, float c, int mode, float* y32,
+                                     void* const* op_dsts_host, int n_dst, cudaStream_t stream);
+int hypret_launch_peer_signal(void* const* flags_host, int n, uint32_t value, cudaStream_t stream);
+int hypret_launch_peer_wait(const uint32_t* flags, int n, uint32_t value, uint32_t* err, cudaStream_t stream);
 int hypret_launch_project_rows(const float* u, int64_t n, int d, float c, int mode, int side, float* y32,
                                void* op_bf16, float* sqnorm, cudaStream_t stream);
 int hypret_launch_score_topk(const void* q_op, int64_t Q, const void* g_op, int64_t N, int d, int kprime,
@@ -337,15 +342,15 @@ int hypret_launch_ap_from_counts(const int64_t* pos_off, const int64_t* pos_item
                                  const unsigned long long* counts, const int32_t* bad, int64_t Q, int64_t n_total,
                                  int grouped_ties, double* ap, int32_t* valid, double* mean_ap, cudaStream_t stream);
 int hypret_launch_pairdist_bwd(const float* g, const float* dmat, const float* asq, const float* psq, int64_t n,
-                               int64_t m, float c, void* w_out, int w_format, float* row_sum, float* col_partial,
-                               int n_partial, cudaStream_t stream);
+                               int64_t m, float c, void* w_out, int w_format, float* row_partial, int n_row_partial,
+                               float* col_partial, int n_partial, cudaStream_t stream);
 int hypret_launch_pairdist_ce_fwd(const float* a, const float* p, int64_t n, int64_t m, int d, float c, float inv_tau,
                                   int want_cols, float* dmat, float* row_lse, float* col_lse, float* scratch,
                                   int n_part, cudaStream_t stream);
 int hypret_launch_pairdist_ce_bwd(const float* dmat, const float* asq, const float* psq, int64_t n, int64_t m, float c,
                                   const float* row_lse, const float* col_lse, float inv_tau, float wr, float wc,
-                                  const float* grad_scale, void* w_out, int w_format, float* row_sum,
-                                  float* col_partial, cudaStream_t stream);
+                                  const float* grad_scale, void* w_out, int w_format, float* row_partial,
+                                  int n_row_partial, float* col_partial, cudaStream_t stream);
 int64_t hypret_gram_kpad_impl(int d);
 int hypret_launch_gram_split(const float* x, int64_t n, int d, int side, void* out_bf16, float* sq, cudaStream_t stream);
 int hypret_launch_gram_dist(const void* a_op, const void* p_op, const float* a32, const float* p32, const float* asq,

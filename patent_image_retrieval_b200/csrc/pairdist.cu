@@ -127,17 +127,22 @@ pairdist_kernel(const float* __restrict__ a, const float* __restrict__ p, int64_
 // sim = -D / tau (the in-batch InfoNCE losses of src/train.py:1832-1844 and 2304-2334):
 //   g_ij = -(gs / tau / n) * [ wr (exp(sim_ij - lse_r[i]) - [i==j]) + wc (exp(sim_ij - lse_c[j]) - [i==j]) ].
 // The two dense products W P and W^T A are left to the caller (plain GEMMs).
-constexpr int BW_ROWS = 32;
+constexpr int BW_ROWS = 16;     // = HYPRET_BWD_ROWS: with 32 the row accumulators spilled under the 128-register cap
+static_assert(BW_ROWS == HYPRET_BWD_ROWS, "include/hypret.h documents the row-block size");
+constexpr int BW_BATCH = 16;   // rows loaded (all loads issued) before the first use
 
 // SPLIT: W leaves as three bf16 planes [3][n][m] (hi, mid, lo with hi + mid + lo = W to fp32 accuracy) so that the
 // two dense products of the backward run as bf16 tensor-core GEMMs (six cross products each) instead of SGEMMs.
 template <bool CE, bool SPLIT>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 2)
 pairdist_bwd_fused_kernel(const float* __restrict__ g, const float* __restrict__ dmat, const float* __restrict__ asq,
                           const float* __restrict__ psq, int64_t n, int64_t m, float c, const float* __restrict__ row_lse,
                           const float* __restrict__ col_lse, float inv_tau, float wr, float wc,
                           const float* __restrict__ grad_scale, void* __restrict__ w_out_raw,
-                          float* __restrict__ row_sum, float* __restrict__ col_partial) {
+                          float* __restrict__ row_partial, float* __restrict__ col_partial) {
+  // grid (row blocks of BW_ROWS, column chunks): CTA (x, y) owns the column blocks [y * cb_per, (y+1) * cb_per)
+  // of its rows, writes row y of row_partial (its rows) and row x of col_partial (its columns) -- one writer per
+  // element, no atomics; the chunks make ~7 waves of CTAs out of the 512 row blocks of an 8192-row batch
   __shared__ float s_al[BW_ROWS], s_ial[BW_ROWS], s_lse[BW_ROWS];
   __shared__ float s_red[BW_ROWS][8];
   const int64_t i0 = (int64_t)blockIdx.x * BW_ROWS;
@@ -157,10 +162,13 @@ pairdist_bwd_fused_kernel(const float* __restrict__ g, const float* __restrict__
   // CTAs start at different column blocks (and wrap around): with a power-of-two row pitch the 32 rows of a
   // block land on the same memory channels, and CTAs marching through the columns in lock-step would all camp
   // on them at once
-  const int64_t n_cb = (m + 255) / 256;
-  const int64_t cb0 = ((int64_t)blockIdx.x * 5) % n_cb;
+  const int64_t n_cb_all = (m + 255) / 256;
+  const int64_t cb_per = (n_cb_all + gridDim.y - 1) / gridDim.y;
+  const int64_t cb_lo = (int64_t)blockIdx.y * cb_per;
+  const int64_t n_cb = cb_lo >= n_cb_all ? 0 : (n_cb_all - cb_lo < cb_per ? n_cb_all - cb_lo : cb_per);
+  const int64_t cb0 = n_cb > 0 ? ((int64_t)blockIdx.x * 5) % n_cb : 0;
   for (int64_t cbi = 0; cbi < n_cb; ++cbi) {
-    const int64_t cb = cb0 + cbi < n_cb ? cb0 + cbi : cb0 + cbi - n_cb;
+    const int64_t cb = cb_lo + (cb0 + cbi < n_cb ? cb0 + cbi : cb0 + cbi - n_cb);
     const int64_t j = cb * 256 + threadIdx.x;
     const bool jok = j < m;
     const float be = jok ? 1.0f - c * psq[j] : 1.0f;
@@ -170,25 +178,31 @@ pairdist_bwd_fused_kernel(const float* __restrict__ g, const float* __restrict__
     // all 32 loads of the block are issued before the first use (the per-element version, with its branches, did
     // one dependent HBM round trip per element: 1.34 ms for 0.5 GB of traffic); out-of-range rows / columns read
     // a clamped address and are masked at the stores and sums
-    const int64_t jc = jok ? j : m - 1;
-    float dv[BW_ROWS], gv[BW_ROWS];
+    const unsigned jcu = (unsigned)(jok ? j : m - 1), ju = (unsigned)j;
 #pragma unroll
-    for (int r = 0; r < BW_ROWS; ++r) {
-      const int64_t o = (i0 + (r < rows ? r : rows - 1)) * m + jc;
-      dv[r] = dmat[o];
-      gv[r] = CE ? 0.f : g[o];
+    for (int rb = 0; rb < BW_ROWS; rb += BW_BATCH) {
+    float dv[BW_BATCH], gv[BW_BATCH];
+#pragma unroll
+    for (int q = 0; q < BW_BATCH; ++q) {
+      const int r = rb + q;
+      // CTA-uniform 64-bit row base + one 32-bit per-thread column offset: per-row 64-bit addresses held live
+      // across the unrolled batch were what spilled
+      const int64_t ro = (i0 + (r < rows ? r : rows - 1)) * m;
+      dv[q] = (dmat + ro)[jcu];
+      gv[q] = CE ? 0.f : (g + ro)[jcu];
     }
 #pragma unroll
-    for (int r = 0; r < BW_ROWS; ++r) {
+    for (int q = 0; q < BW_BATCH; ++q) {
+      const int r = rb + q;
       const bool ok = r < rows && jok;
-      const float dd = dv[r];
+      const float dd = dv[q];
       float gg;
       if (CE) {
         const float sim = -dd * inv_tau;
         const float diag = (i0 + r == j) ? 1.0f : 0.0f;
         gg = gsc * (wr * (__expf(sim - s_lse[r]) - diag) + wc * (__expf(sim - lse_c) - diag));
       } else {
-        gg = gv[r];
+        gg = gv[q];
       }
       // t = cosh(x) - 1 = 2 sinh^2(x/2), x = sqrt(c) d, without library calls or IEEE-division slow paths:
       // (e^x + e^-x)/2 - 1 from one fast exp2 and one approximate reciprocal; below x = 0.35 that form
@@ -205,21 +219,22 @@ pairdist_bwd_fused_kernel(const float* __restrict__ g, const float* __restrict__
       const float w = ok ? gg * four_sc * __frcp_rn(ab * sh) : 0.f;
       if (ok) {
         if (SPLIT) {
-          __nv_bfloat16* wp = static_cast<__nv_bfloat16*>(w_out_raw);
-          const int64_t o = (i0 + r) * m + j, plane = n * m;
+          __nv_bfloat16* wrow = static_cast<__nv_bfloat16*>(w_out_raw) + (i0 + r) * m;     // CTA-uniform
+          const int64_t plane = n * m;
           const __nv_bfloat16 hi = __float2bfloat16_rn(w);
           const float r1 = w - __bfloat162float(hi);
           const __nv_bfloat16 mid = __float2bfloat16_rn(r1);
-          wp[o] = hi;
-          wp[plane + o] = mid;
-          wp[2 * plane + o] = __float2bfloat16_rn(r1 - __bfloat162float(mid));
+          wrow[ju] = hi;
+          (wrow + plane)[ju] = mid;
+          (wrow + 2 * plane)[ju] = __float2bfloat16_rn(r1 - __bfloat162float(mid));
         } else {
-          static_cast<float*>(w_out_raw)[(i0 + r) * m + j] = w;
+          (static_cast<float*>(w_out_raw) + (i0 + r) * m)[ju] = w;
         }
       }
       const float cs = 0.5f * t * ab;           // c * s = h^2 alpha beta, h^2 = t / 2
       racc[r] += w * (1.0f + cs * s_ial[r]);
       cacc += w * (1.0f + cs * ibe);
+    }
     }
     if (jok) col_partial[(int64_t)blockIdx.x * m + j] = cacc;
   }
@@ -235,7 +250,7 @@ pairdist_bwd_fused_kernel(const float* __restrict__ g, const float* __restrict__
     float v = 0.f;
 #pragma unroll
     for (int w8 = 0; w8 < 8; ++w8) v += s_red[threadIdx.x][w8];
-    row_sum[i0 + threadIdx.x] = v;
+    row_partial[(int64_t)blockIdx.y * n + i0 + threadIdx.x] = v;
   }
 }
 
@@ -297,21 +312,23 @@ lse_cols_combine_kernel(const float* __restrict__ part_max, const float* __restr
 }  // namespace
 
 int hypret_launch_pairdist_bwd(const float* g, const float* dmat, const float* asq, const float* psq, int64_t n,
-                               int64_t m, float c, void* w_out, int w_format, float* row_sum, float* col_partial,
-                               int n_partial, cudaStream_t stream) {
+                               int64_t m, float c, void* w_out, int w_format, float* row_partial, int n_row_partial,
+                               float* col_partial, int n_partial, cudaStream_t stream) {
   if (n == 0 || m == 0) return HYPRET_OK;
-  if ((int64_t)n_partial * BW_ROWS < n) return HYPRET_EINVAL;     // one partial row of column sums per CTA of 32 rows
-  const unsigned grid = (unsigned)((n + BW_ROWS - 1) / BW_ROWS);
+  if ((int64_t)n_partial * BW_ROWS < n) return HYPRET_EINVAL;     // one partial row of column sums per CTA of BW_ROWS rows
+  const dim3 grid((unsigned)((n + BW_ROWS - 1) / BW_ROWS), (unsigned)n_row_partial);
   if (w_format == 1)
     pairdist_bwd_fused_kernel<false, true><<<grid, 256, 0, stream>>>(g, dmat, asq, psq, n, m, c, nullptr, nullptr, 0.f,
-                                                                    0.f, 0.f, nullptr, w_out, row_sum, col_partial);
+                                                                    0.f, 0.f, nullptr, w_out, row_partial, col_partial);
   else
     pairdist_bwd_fused_kernel<false, false><<<grid, 256, 0, stream>>>(g, dmat, asq, psq, n, m, c, nullptr, nullptr, 0.f,
-                                                                     0.f, 0.f, nullptr, w_out, row_sum, col_partial);
+                                                                     0.f, 0.f, nullptr, w_out, row_partial,
+                                                                     col_partial);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return (int)e;
-  if ((int64_t)n_partial > (int64_t)grid)      // partial rows no CTA writes must read as zero
-    e = cudaMemsetAsync(col_partial + (int64_t)grid * m, 0, ((int64_t)n_partial - grid) * m * sizeof(float), stream);
+  if ((int64_t)n_partial > (int64_t)grid.x)    // partial rows no CTA writes must read as zero
+    e = cudaMemsetAsync(col_partial + (int64_t)grid.x * m, 0, ((int64_t)n_partial - grid.x) * m * sizeof(float),
+                        stream);
   return (int)e;
 }
 
@@ -348,17 +365,17 @@ int hypret_launch_neg_lse(const float* dmat, int64_t n, int64_t m, float inv_tau
 
 int hypret_launch_pairdist_ce_bwd(const float* dmat, const float* asq, const float* psq, int64_t n, int64_t m, float c,
                                   const float* row_lse, const float* col_lse, float inv_tau, float wr, float wc,
-                                  const float* grad_scale, void* w_out, int w_format, float* row_sum,
-                                  float* col_partial, cudaStream_t stream) {
+                                  const float* grad_scale, void* w_out, int w_format, float* row_partial,
+                                  int n_row_partial, float* col_partial, cudaStream_t stream) {
   if (n == 0 || m == 0) return HYPRET_OK;
-  const unsigned grid = (unsigned)((n + BW_ROWS - 1) / BW_ROWS);
+  const dim3 grid((unsigned)((n + BW_ROWS - 1) / BW_ROWS), (unsigned)n_row_partial);
   if (w_format == 1)
     pairdist_bwd_fused_kernel<true, true><<<grid, 256, 0, stream>>>(nullptr, dmat, asq, psq, n, m, c, row_lse, col_lse,
-                                                                   inv_tau, wr, wc, grad_scale, w_out, row_sum,
+                                                                   inv_tau, wr, wc, grad_scale, w_out, row_partial,
                                                                    col_partial);
   else
     pairdist_bwd_fused_kernel<true, false><<<grid, 256, 0, stream>>>(nullptr, dmat, asq, psq, n, m, c, row_lse, col_lse,
-                                                                    inv_tau, wr, wc, grad_scale, w_out, row_sum,
+                                                                    inv_tau, wr, wc, grad_scale, w_out, row_partial,
                                                                     col_partial);
   return (int)cudaGetLastError();
 }

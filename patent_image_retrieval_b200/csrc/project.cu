@@ -39,10 +39,18 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
   return *reinterpret_cast<uint32_t*>(&p);
 }
 
+// Destinations of the bf16 operand row.  n == 1: the usual local buffer.  n > 1 (multi-GPU serving,
+// hypret_project_rows_peers): the same row is stored into the exchange buffer of every rank of the box -- peer
+// memory mapped over NVLink, plain posted stores -- so the projection IS the all-gather of the query operands.
+struct OpDsts {
+  __nv_bfloat16* p[HYPRET_MAX_PEERS];
+  int n;
+};
+
 template <int NV>  // float4 chunks per lane; supports D <= NV * 128
 __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
 project_rows_kernel(const float* __restrict__ u, int64_t n, int d, float c, int mode, int side,
-                    float* __restrict__ y32, __nv_bfloat16* __restrict__ op, float* __restrict__ sqnorm) {
+                    float* __restrict__ y32, const OpDsts ops, float* __restrict__ sqnorm) {
   const int lane = threadIdx.x & 31;
   const int nvec = d >> 2;
   const int dpad = hypret_dpad(d);
@@ -114,20 +122,26 @@ project_rows_kernel(const float* __restrict__ u, int64_t n, int d, float c, int 
     }
     if (sqnorm != nullptr && lane == 0) sqnorm[row] = ysq;
 
-    if (op != nullptr) {
+    if (ops.n > 0) {
       const bool hyp = (mode != HYPRET_MODE_COSINE);
       const float rb = hyp ? 1.0f / (1.0f - c * ysq) : 1.0f;
       const float mul = (side == HYPRET_SIDE_QUERY) ? 1.0f : (hyp ? -2.0f * rb : -1.0f);
-      uint2* dst = reinterpret_cast<uint2*>(op + row * kpad);
+      uint2 packed[NV];
 #pragma unroll
-      for (int i = 0; i < NV; ++i) {
-        const int j = i * 32 + lane;
-        if (j < nvec) dst[j] = make_uint2(pack_bf16(v[i].x * mul, v[i].y * mul), pack_bf16(v[i].z * mul, v[i].w * mul));
+      for (int i = 0; i < NV; ++i)
+        packed[i] = make_uint2(pack_bf16(v[i].x * mul, v[i].y * mul), pack_bf16(v[i].z * mul, v[i].w * mul));
+      for (int t = 0; t < ops.n; ++t) {
+        uint2* dst = reinterpret_cast<uint2*>(ops.p[t] + row * kpad);
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+          const int j = i * 32 + lane;
+          if (j < nvec) dst[j] = packed[i];
+        }
+        // zero the K padding between D and Dpad
+        for (int j = nvec + lane; j < (dpad >> 2); j += 32) dst[j] = make_uint2(0u, 0u);
       }
-      // zero the K padding between D and Dpad
-      for (int j = nvec + lane; j < (dpad >> 2); j += 32) dst[j] = make_uint2(0u, 0u);
       if (lane == 0) {
-        __nv_bfloat16 e[HYPRET_KEXT];
+        __align__(16) __nv_bfloat16 e[HYPRET_KEXT];
         const __nv_bfloat16 zero = __float2bfloat16_rn(0.f);
 #pragma unroll
         for (int i = 0; i < HYPRET_KEXT; ++i) e[i] = zero;
@@ -146,17 +160,19 @@ project_rows_kernel(const float* __restrict__ u, int64_t n, int d, float c, int 
             e[6] = b1; e[7] = b2; e[8] = b3;
           }
         }
-        uint4* ext = reinterpret_cast<uint4*>(op + row * kpad + dpad);
         const uint4* es = reinterpret_cast<const uint4*>(e);
-        ext[0] = es[0];
-        ext[1] = es[1];
+        for (int t = 0; t < ops.n; ++t) {
+          uint4* ext = reinterpret_cast<uint4*>(ops.p[t] + row * kpad + dpad);
+          ext[0] = es[0];
+          ext[1] = es[1];
+        }
       }
     }
   }
 }
 
 template <int NV>
-int launch(const float* u, int64_t n, int d, float c, int mode, int side, float* y32, void* op, float* sqnorm,
+int launch(const float* u, int64_t n, int d, float c, int mode, int side, float* y32, const OpDsts& ops, float* sqnorm,
            cudaStream_t stream) {
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
@@ -167,21 +183,38 @@ int launch(const float* u, int64_t n, int d, float c, int mode, int side, float*
   if (blocks_needed < grid) grid = blocks_needed;
   if (grid < 1) grid = 1;
   project_rows_kernel<NV><<<(unsigned)grid, WARPS_PER_BLOCK * 32, 0, stream>>>(
-      u, n, d, c, mode, side, y32, reinterpret_cast<__nv_bfloat16*>(op), sqnorm);
+      u, n, d, c, mode, side, y32, ops, sqnorm);
   return (int)cudaGetLastError();
+}
+
+int dispatch(const float* u, int64_t n, int d, float c, int mode, int side, float* y32, const OpDsts& ops,
+             float* sqnorm, cudaStream_t stream) {
+  if (n == 0) return HYPRET_OK;
+  const int need = (d + 127) / 128;
+  if (need <= 1) return launch<1>(u, n, d, c, mode, side, y32, ops, sqnorm, stream);
+  if (need <= 2) return launch<2>(u, n, d, c, mode, side, y32, ops, sqnorm, stream);
+  if (need <= 4) return launch<4>(u, n, d, c, mode, side, y32, ops, sqnorm, stream);
+  if (need <= 6) return launch<6>(u, n, d, c, mode, side, y32, ops, sqnorm, stream);
+  if (need <= 8) return launch<8>(u, n, d, c, mode, side, y32, ops, sqnorm, stream);
+  if (need <= 16) return launch<16>(u, n, d, c, mode, side, y32, ops, sqnorm, stream);
+  return HYPRET_EINVAL;
 }
 
 }  // namespace
 
 int hypret_launch_project_rows(const float* u, int64_t n, int d, float c, int mode, int side, float* y32,
                                void* op_bf16, float* sqnorm, cudaStream_t stream) {
-  if (n == 0) return HYPRET_OK;
-  const int need = (d + 127) / 128;
-  if (need <= 1) return launch<1>(u, n, d, c, mode, side, y32, op_bf16, sqnorm, stream);
-  if (need <= 2) return launch<2>(u, n, d, c, mode, side, y32, op_bf16, sqnorm, stream);
-  if (need <= 4) return launch<4>(u, n, d, c, mode, side, y32, op_bf16, sqnorm, stream);
-  if (need <= 6) return launch<6>(u, n, d, c, mode, side, y32, op_bf16, sqnorm, stream);
-  if (need <= 8) return launch<8>(u, n, d, c, mode, side, y32, op_bf16, sqnorm, stream);
-  if (need <= 16) return launch<16>(u, n, d, c, mode, side, y32, op_bf16, sqnorm, stream);
-  return HYPRET_EINVAL;
+  OpDsts ops;
+  ops.n = op_bf16 != nullptr ? 1 : 0;
+  ops.p[0] = reinterpret_cast<__nv_bfloat16*>(op_bf16);
+  return dispatch(u, n, d, c, mode, side, y32, ops, sqnorm, stream);
+}
+
+int hypret_launch_project_rows_peers(const float* u, int64_t n, int d, float c, int mode, float* y32,
+                                     void* const* op_dsts_host, int n_dst, cudaStream_t stream) {
+  if (n_dst < 1 || n_dst > HYPRET_MAX_PEERS) return HYPRET_EINVAL;
+  OpDsts ops;
+  ops.n = n_dst;
+  for (int t = 0; t < n_dst; ++t) ops.p[t] = reinterpret_cast<__nv_bfloat16*>(op_dsts_host[t]);
+  return dispatch(u, n, d, c, mode, HYPRET_SIDE_QUERY, y32, ops, nullptr, stream);
 }

@@ -17,13 +17,15 @@ The reference has no distributed path at all (single process, single GPU).
 """
 from __future__ import annotations
 
+import ctypes
+import os
 from typing import Optional, Tuple
 
 import torch
 import torch.distributed as dist
 
-from . import ops
-from .retrieval import GalleryIndex
+from . import _lib, ops
+from .retrieval import GalleryIndex, _span
 
 
 def shard_range(n_rows: int, rank: int, world: int) -> Tuple[int, int]:
@@ -66,6 +68,184 @@ def return_lists_to_owners(score: torch.Tensor, idx: torch.Tensor, group=None):
     return rs.view((world, ql) + tuple(score.shape[1:])), ri.view((world, ql) + tuple(idx.shape[1:]))
 
 
+class _RawCuda:
+    """``__cuda_array_interface__`` view of raw device memory (a buffer libhypret allocated)."""
+
+    def __init__(self, ptr: int, nbytes: int):
+        self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 3,
+                                         "strides": None}
+
+
+class PeerQueryExchange:
+    """The all-gather of the per-rank query batches, done through peer memory instead of NCCL (csrc/peer.cu).
+
+    Every rank owns an exchange buffer that all ranks of the box map over NVLink (CUDA IPC).  ``publish``:
+      1. the projection kernel reads this rank's ``[Ql,D]`` raw rows once and stores each bf16 operand row into the
+         buffers of ALL ranks (posted NVLink stores) -- no rank projects another rank's queries, and the operands
+         are in place when the kernel ends;
+      2. the exact fp32 rows (needed only by the rerank) follow through the copy engines on a side stream while
+         the scoring kernel, which owns every SM, runs;
+      3. per-source step counters in the destination buffers announce arrival (``hypret_peer_signal`` behind the
+         producer, ``hypret_peer_wait`` in front of the consumer, both stream-ordered; no host synchronisation).
+    Two buffer slots: a rank cannot start step i+2 before every peer has finished step i (see csrc/peer.cu)."""
+
+    FLAGS_BYTES = 1024           # [0:64) operand counters, [64:128) point counters, [128:132) error word,
+                                 # [192:256) scratch counters (kernel preload)
+    SLOTS = 2
+
+    def __init__(self, n_queries: int, d: int, device: torch.device, group=None):
+        self.group = group
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        if self.world > 16:
+            raise ValueError("PeerQueryExchange addresses at most 16 ranks of one box")
+        self.device = torch.device(device)
+        self.ql, self.d = int(n_queries), int(d)
+        self.kpad = ops.operand_kpad(d)
+        rnd = lambda b: (b + 255) // 256 * 256
+        self.op_blk = self.ql * self.kpad * 2
+        self.pt_blk = self.ql * self.d * 4
+        self.op_bytes, self.pt_bytes = rnd(self.world * self.op_blk), rnd(self.world * self.pt_blk)
+        self.slot_bytes = self.op_bytes + self.pt_bytes
+        self.nbytes = self.FLAGS_BYTES + self.SLOTS * self.slot_bytes
+        lib = _lib.load()
+        handle = (ctypes.c_ubyte * 64)()
+        base = ctypes.c_void_p()
+        with torch.cuda.device(self.device):
+            _lib.check(lib.hypret_peer_alloc(self.nbytes, ctypes.byref(base), handle))
+        self.base = int(base.value)
+        mine = torch.tensor(list(handle), dtype=torch.uint8, device=self.device)
+        every = torch.empty(self.world * 64, dtype=torch.uint8, device=self.device)
+        dist.all_gather_into_tensor(every, mine, group=group)
+        every = every.cpu().view(self.world, 64)
+        self.peer_base = []
+        with torch.cuda.device(self.device):
+            for r in range(self.world):
+                if r == self.rank:
+                    self.peer_base.append(self.base)
+                    continue
+                h = (ctypes.c_ubyte * 64)(*every[r].tolist())
+                ptr = ctypes.c_void_p()
+                _lib.check(lib.hypret_peer_open(h, ctypes.byref(ptr)))
+                self.peer_base.append(int(ptr.value))
+        raw = torch.as_tensor(_RawCuda(self.base, self.nbytes), device=self.device)
+        self._raw = raw
+        self.op_all, self.pt_all = [], []
+        for s in range(self.SLOTS):
+            o = self.FLAGS_BYTES + s * self.slot_bytes
+            self.op_all.append(raw[o:o + self.world * self.op_blk].view(torch.bfloat16).view(self.world * self.ql,
+                                                                                              self.kpad))
+            o += self.op_bytes
+            self.pt_all.append(raw[o:o + self.world * self.pt_blk].view(torch.float32).view(self.world * self.ql,
+                                                                                            self.d))
+        self.err = raw[128:132].view(torch.int32)
+        self.side = torch.cuda.Stream(device=self.device)
+        self.projected = torch.cuda.Event()
+        self.copied = [torch.cuda.Event() for _ in range(self.SLOTS)]
+        self.step = 0
+        self._arr = ctypes.c_void_p * self.world
+        # run both flag kernels once while nothing spins: a kernel's first launch loads its module (lazy loading),
+        # and that waits for running kernels -- it must never happen behind a wait that is already spinning
+        with torch.cuda.device(self.device):
+            cur = ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+            scratch = self._arr(*[self.base + 192 + 4 * r for r in range(self.world)])
+            _lib.check(lib.hypret_peer_signal(scratch, self.world, 1, cur))
+            _lib.check(lib.hypret_peer_wait(ctypes.c_void_p(self.base + 192), self.world, 1,
+                                            ctypes.c_void_p(self.base + 128), cur))
+        torch.cuda.synchronize(self.device)
+        dist.barrier(group=group)              # every rank has mapped every buffer before the first store
+
+    def _off(self, slot: int, points: bool) -> int:
+        return self.FLAGS_BYTES + slot * self.slot_bytes + (self.op_bytes if points else 0)
+
+    def publish(self, q_local: torch.Tensor, c: float, mode: str):
+        """Queue projection + exchange of this rank's batch on the current stream.  Returns
+        ``(q_op_all [W*Ql,kpad] bf16, q32_all [W*Ql,D] fp32)`` (rank-major); ``q_op_all`` is complete for whatever is
+        queued behind this call, ``q32_all`` only behind ``wait_points()``."""
+        if tuple(q_local.shape) != (self.ql, self.d) or q_local.dtype != torch.float32 or not q_local.is_cuda:
+            raise ValueError(f"expected a CUDA float32 batch of shape [{self.ql}, {self.d}]")
+        q_local = q_local.contiguous()
+        lib = _lib.load()
+        self.step += 1
+        s = self.step % self.SLOTS
+        cur = torch.cuda.current_stream(self.device)
+        cur_p, side_p = ctypes.c_void_p(cur.cuda_stream), ctypes.c_void_p(self.side.cuda_stream)
+        W, me = self.world, self.rank
+        my_pt = self.base + self._off(s, True) + me * self.pt_blk
+        with torch.cuda.device(self.device):
+            cur.wait_event(self.copied[s])     # the copies that last read this slot's local block are done
+            dsts = self._arr(*[self.peer_base[r] + self._off(s, False) + me * self.op_blk for r in range(W)])
+            cosine = mode == "cosine"
+            _lib.check(lib.hypret_project_rows_peers(ctypes.c_void_p(q_local.data_ptr()), self.ql, self.d, float(c),
+                                                     ops.MODE[mode], None if cosine else ctypes.c_void_p(my_pt), dsts,
+                                                     W, cur_p))
+            if cosine:                         # cosine reranks from the raw rows
+                _lib.check(lib.hypret_peer_copy(ctypes.c_void_p(my_pt), ctypes.c_void_p(q_local.data_ptr()),
+                                                self.pt_blk, cur_p))
+            flags = self._arr(*[self.peer_base[r] + 4 * me for r in range(W)])
+            _lib.check(lib.hypret_peer_signal(flags, W, self.step, cur_p))
+            self.projected.record(cur)
+            self.side.wait_event(self.projected)
+            for r in range(W):
+                if r != me:
+                    _lib.check(lib.hypret_peer_copy(
+                        ctypes.c_void_p(self.peer_base[r] + self._off(s, True) + me * self.pt_blk),
+                        ctypes.c_void_p(my_pt), self.pt_blk, side_p))
+            flags = self._arr(*[self.peer_base[r] + 64 + 4 * me for r in range(W)])
+            _lib.check(lib.hypret_peer_signal(flags, W, self.step, side_p))
+            self.copied[s].record(self.side)
+            _lib.check(lib.hypret_peer_wait(ctypes.c_void_p(self.base), W, self.step, ctypes.c_void_p(self.base + 128),
+                                            cur_p))
+        q_local.record_stream(cur)
+        return self.op_all[s], self.pt_all[s]
+
+    def wait_points(self):
+        """Hold the current stream until every rank's fp32 rows of the last published step have landed."""
+        cur = torch.cuda.current_stream(self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.load().hypret_peer_wait(ctypes.c_void_p(self.base + 64), self.world, self.step,
+                                                    ctypes.c_void_p(self.base + 128),
+                                                    ctypes.c_void_p(cur.cuda_stream)))
+
+    def check(self):
+        """Synchronise and raise if a wait ran into its 20 s bound (a peer died or fell out of step)."""
+        torch.cuda.synchronize(self.device)
+        e = int(self.err.item())
+        if e:
+            raise RuntimeError(f"peer exchange: rank {self.rank} timed out waiting for rank {e - 1}")
+
+    def close(self):
+        if self.base is None:
+            return
+        torch.cuda.synchronize(self.device)
+        dist.barrier(group=self.group)         # nobody still writes into a buffer that is about to go
+        lib = _lib.load()
+        with torch.cuda.device(self.device):
+            for r, ptr in enumerate(self.peer_base):
+                if r != self.rank:
+                    lib.hypret_peer_close(ctypes.c_void_p(ptr))
+            self._raw = self.op_all = self.pt_all = self.err = None
+            lib.hypret_peer_free(ctypes.c_void_p(self.base))
+        self.base = None
+
+
+def peer_exchange_available(device: torch.device, group=None) -> bool:
+    """Peer-memory exchange needs NCCL-style deployment: one process per GPU of ONE box, every device visible to
+    every process and peer access between them.  ``HYPRET_PEER_EXCHANGE=0`` forces the NCCL all_gather."""
+    if os.environ.get("HYPRET_PEER_EXCHANGE", "1") == "0" or not dist.is_initialized():
+        return False
+    world = dist.get_world_size(group)
+    if dist.get_backend(group) != "nccl" or world < 2 or world > 16 or torch.cuda.device_count() < world:
+        return False
+    if int(os.environ.get("LOCAL_WORLD_SIZE", world)) != world:
+        return False
+    dev = torch.device(device).index
+    ok = all(r == dev or torch.cuda.can_device_access_peer(dev, r) for r in range(world))
+    flag = torch.tensor([1 if ok else 0], device=device)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+    return bool(flag.item())
+
+
 class ShardedGalleryIndex:
     """This rank's row-shard of a global gallery of ``n_total`` rows + the exchange step."""
 
@@ -80,6 +260,20 @@ class ShardedGalleryIndex:
         self.local = GalleryIndex(shard_features, c=c, metric=metric, space=space, idx_offset=row_offset,
                                   device=device)
         self.metric = metric
+        self._exchange = None
+        self._exchange_ok = None
+
+    def _peer_exchange(self, n_queries: int) -> Optional[PeerQueryExchange]:
+        """The peer-memory exchange for ``n_queries``-row batches (built at first use; collective), or None."""
+        if self._exchange_ok is None:
+            self._exchange_ok = peer_exchange_available(self.local.device, self.group)
+        if not self._exchange_ok:
+            return None
+        if self._exchange is None or self._exchange.ql != n_queries:
+            if self._exchange is not None:
+                self._exchange.close()
+            self._exchange = PeerQueryExchange(n_queries, self.local.d, self.local.device, self.group)
+        return self._exchange
 
     def _single(self) -> bool:
         return not dist.is_initialized() or dist.get_world_size(self.group) == 1
@@ -105,6 +299,8 @@ class ShardedGalleryIndex:
                        kernel_events: Optional[list] = None, prune: Optional[bool] = None):
         """Serving layout: all_gather the per-rank batches, score them all against this shard,
         all_to_all the lists back to the query owners, merge.  Returns ``[Ql,k]`` for ``q_local``.
+        On one NVLink box the all_gather is the projection kernel itself storing into every rank's exchange
+        buffer (``PeerQueryExchange``); the result is bit-identical to the NCCL path (``HYPRET_PEER_EXCHANGE=0``).
 
         ``prune`` (default: on for k <= 32): a query's exact rescoring needs only its GLOBAL approximate
         top-k', of which this shard holds k'/W on average.  The shards' k' best surrogate scores go to the
@@ -115,11 +311,17 @@ class ShardedGalleryIndex:
         from .retrieval import default_kprime
         world = dist.get_world_size(self.group)
         q_local = q_local.to(device=self.local.device, dtype=torch.float32, non_blocking=True)
-        q_all = gather_queries(q_local, self.group)
         kp = min(default_kprime(k) if kprime is None else int(kprime), ops.MAX_KPRIME)
         if prune is None:
             prune = k <= 32 and kp <= 32 and k <= kp
-        q32, cs, ci, cnt = self.local.score_candidates(q_all, k=k, kprime=kprime, kernel_events=kernel_events)
+        ex = self._peer_exchange(q_local.shape[0])
+        if ex is not None:
+            with _span(kernel_events, "project"):
+                q_op, q32 = ex.publish(q_local, self.local.c, self.local._query_mode())
+            q32, cs, ci, cnt = self.local.score_projected(q32, q_op, k=k, kprime=kprime, kernel_events=kernel_events)
+        else:
+            q_all = gather_queries(q_local, self.group)
+            q32, cs, ci, cnt = self.local.score_candidates(q_all, k=k, kprime=kprime, kernel_events=kernel_events)
         thr_all = None
         if prune:
             sel_s, sel_i = ops.cand_select(cs, ci, cnt)                              # [W*Ql, k']
@@ -129,6 +331,8 @@ class ShardedGalleryIndex:
             thr_all = torch.empty(world * q_local.shape[0], dtype=torch.float32, device=thr.device)
             dist.all_gather_into_tensor(thr_all, thr, group=self.group)
             cs, ci, cnt = sel_s.unsqueeze(1), sel_i.unsqueeze(1), None               # one merged list per query
+        if ex is not None:
+            ex.wait_points()
         score, idx = self.local.rerank_candidates(q32, cs, ci, k, prune_thr=thr_all, kernel_events=kernel_events,
                                                   list_count=cnt)
         rs, ri = return_lists_to_owners(score, idx, self.group)

@@ -386,41 +386,90 @@ def pairdist_ce_fwd(a: torch.Tensor, p: torch.Tensor, c: float, inv_tau: float, 
     return dmat, row_lse, col_lse
 
 
+BWD_ROWS = 16       # HYPRET_BWD_ROWS: matrix rows per CTA of the backward pass (one col_partial row each)
+
+
+def _bwd_chunks(n: int, m: int) -> int:
+    """Column chunks of the backward pass: ~7 waves of 2 CTAs per SM out of the ceil(n/16) row blocks."""
+    row_blocks = max(1, (n + BWD_ROWS - 1) // BWD_ROWS)
+    return max(1, min((m + 255) // 256, round(7 * 2 * 148 / row_blocks)))
+
+
+def _w_buffer(n: int, m: int, split: bool, device):
+    if split:
+        return torch.empty(3, n, m, dtype=torch.bfloat16, device=device)
+    return torch.empty(n, m, dtype=torch.float32, device=device)
+
+
 def pairdist_ce_bwd(dmat: torch.Tensor, asq: torch.Tensor, psq: torch.Tensor, c: float, row_lse: torch.Tensor,
                     col_lse: Optional[torch.Tensor], inv_tau: float, w_rows: float, w_cols: float,
-                    grad_scale: Optional[torch.Tensor] = None):
-    """Backward weights of the in-batch InfoNCE: ``(W [n,m], row_sum [n], col_sum [m])``; the upstream gradient is
-    formed inside the kernel from the log-sum-exps (``grad_scale``: device scalar dL/dloss)."""
+                    grad_scale: Optional[torch.Tensor] = None, split: bool = False):
+    """Backward weights of the in-batch InfoNCE: ``(W, row_sum [n], col_sum [m])``; the upstream gradient is
+    formed inside the kernel from the log-sum-exps (``grad_scale``: device scalar dL/dloss).  ``W`` is ``[n,m]``
+    fp32, or with ``split`` three bf16 planes ``[3,n,m]`` (hi + mid + lo = W) for ``split_products``."""
     _need_cuda(dmat, asq, psq, row_lse, col_lse, grad_scale)
     n, m = dmat.shape
-    w = torch.empty_like(dmat)
-    rs = torch.empty(n, dtype=torch.float32, device=dmat.device)
-    cp = torch.empty((n + 31) // 32, m, dtype=torch.float32, device=dmat.device)
+    w = _w_buffer(n, m, split, dmat.device)
+    n_rp = _bwd_chunks(n, m)
+    rp = torch.empty(n_rp, n, dtype=torch.float32, device=dmat.device)
+    cp = torch.empty((n + BWD_ROWS - 1) // BWD_ROWS, m, dtype=torch.float32, device=dmat.device)
     gs = grad_scale.reshape(1).contiguous().float() if grad_scale is not None else None
     with torch.cuda.device(dmat.device):
         _lib.check(_lib.load().hypret_pairdist_ce_bwd(_ptr(dmat.contiguous()), _ptr(asq.contiguous().float()),
                                                       _ptr(psq.contiguous().float()), n, m, float(c), _ptr(row_lse),
                                                       _ptr(col_lse), float(inv_tau), float(w_rows), float(w_cols),
-                                                      _ptr(gs), _ptr(w), _ptr(rs), _ptr(cp), _stream()))
-    return w, rs, cp.sum(dim=0)
+                                                      _ptr(gs), _ptr(w), int(split), _ptr(rp), n_rp, _ptr(cp),
+                                                      _stream()))
+    return w, rp.sum(dim=0), cp.sum(dim=0)
 
 
 def pairdist_bwd(grad_out: torch.Tensor, dmat: torch.Tensor, asq: torch.Tensor, psq: torch.Tensor, c: float,
-                 n_partial: Optional[int] = None):
-    """Weights of the distance-matrix backward: returns ``(W [n,m], row_sum [n], col_sum [m])``."""
+                 n_partial: Optional[int] = None, split: bool = False):
+    """Weights of the distance-matrix backward: returns ``(W, row_sum [n], col_sum [m])`` (``split`` as in
+    ``pairdist_ce_bwd``)."""
     _need_cuda(grad_out, dmat, asq, psq)
     grad_out = grad_out.contiguous().float()
     dmat = dmat.contiguous()
     n, m = dmat.shape
-    n_partial = max((n + 31) // 32, n_partial or 0, 1)
-    w = torch.empty_like(dmat)
-    rs = torch.empty(n, dtype=torch.float32, device=dmat.device)
+    n_partial = max((n + BWD_ROWS - 1) // BWD_ROWS, n_partial or 0, 1)
+    w = _w_buffer(n, m, split, dmat.device)
+    n_rp = _bwd_chunks(n, m)
+    rp = torch.empty(n_rp, n, dtype=torch.float32, device=dmat.device)
     cp = torch.empty(n_partial, m, dtype=torch.float32, device=dmat.device)
     with torch.cuda.device(dmat.device):
         _lib.check(_lib.load().hypret_pairdist_bwd(_ptr(grad_out), _ptr(dmat), _ptr(asq.contiguous()),
-                                                   _ptr(psq.contiguous()), n, m, float(c), _ptr(w), _ptr(rs), _ptr(cp),
-                                                   n_partial, _stream()))
-    return w, rs, cp.sum(dim=0)
+                                                   _ptr(psq.contiguous()), n, m, float(c), _ptr(w), int(split), _ptr(rp),
+                                                   n_rp, _ptr(cp), n_partial, _stream()))
+    return w, rp.sum(dim=0), cp.sum(dim=0)
+
+
+SPLIT_MIN_PAIRS = 1 << 20     # below this the two products are launch-bound either way: plain fp32 GEMMs
+
+
+def _split3(x: torch.Tensor) -> torch.Tensor:
+    """[r,d] fp32 -> [r,3d] bf16 = [hi | mid | lo] with hi + mid + lo = x to fp32 accuracy."""
+    hi = x.to(torch.bfloat16)
+    r1 = x - hi.float()
+    mid = r1.to(torch.bfloat16)
+    lo = (r1 - mid.float()).to(torch.bfloat16)
+    return torch.cat([hi, mid, lo], dim=1)
+
+
+def split_products(w3: torch.Tensor, a: torch.Tensor, p: torch.Tensor):
+    """``(W @ p, W.T @ a)`` for ``W = w3[0] + w3[1] + w3[2]`` (bf16 planes) at fp32 accuracy on the tensor cores: the
+    six bf16 cross products of order <= 2^-16, hi x (hi|mid|lo) + mid x (hi|mid) + lo x hi, as three library GEMMs
+    per product with fp32 accumulation (each W plane is read once per product).  The plain dense products of the
+    backward -- library GEMMs, as cuBLAS SGEMM was before, 4x fewer passes of the FP32 pipe."""
+    d = a.shape[1]
+    outs = []
+    for planes, x in (((w3[0], w3[1], w3[2]), p), ((w3[0].t(), w3[1].t(), w3[2].t()), a)):
+        x3 = _split3(x.float())
+        o = torch.mm(planes[0], x3, out_dtype=torch.float32)
+        acc = o[:, 2 * d:] + o[:, d:2 * d]                       # smallest terms first
+        o1 = torch.mm(planes[1], x3[:, :2 * d], out_dtype=torch.float32)
+        acc = acc + o1[:, d:] + torch.mm(planes[2], x3[:, :d], out_dtype=torch.float32)
+        outs.append(acc + o1[:, :d] + o[:, :d])
+    return outs[0], outs[1]
 
 
 def row_sqnorm(x: torch.Tensor) -> torch.Tensor:

@@ -125,10 +125,6 @@ class GalleryIndex:
         Returns ``(q32 [Q,D] exact-rerank operand, cand_score [Q,L,k'], cand_idx [Q,L,k'] int32, list_count [Q]
         int32)``: the lists of query q are its first ``list_count[q]`` slots (compact, arrival order); the other
         slots hold stale data.  The candidate buffers are reused by the next call."""
-        kprime = default_kprime(k) if kprime is None else int(kprime)
-        kprime = min(kprime, ops.MAX_KPRIME)
-        wide = k > kprime or k > 32 or kprime > 32
-        min_lists = WIDE_MIN_LISTS if wide else 0
         q = queries.to(device=self.device, dtype=torch.float32, non_blocking=True)
         if q.dim() != 2 or q.shape[1] != self.d:
             raise ValueError(f"queries must be [Q, {self.d}]")
@@ -138,17 +134,28 @@ class GalleryIndex:
             else:
                 q32 = q.contiguous()
                 _, q_op, _ = ops.project_rows(q, 1.0, mode="cosine", side="query", want_point=False)
-        key = (q.shape[0], kprime, max_ctas, min_lists)
-        plan = ops.score_plan(q.shape[0], self.n, self.d, kprime, max_ctas, min_lists)
+        return self.score_projected(q32, q_op, k=k, kprime=kprime, max_ctas=max_ctas, kernel_events=kernel_events)
+
+    def score_projected(self, q32: torch.Tensor, q_op: torch.Tensor, k: int = 10, kprime: Optional[int] = None,
+                        max_ctas: int = 0, kernel_events: Optional[list] = None):
+        """``score_candidates`` for queries that are already projected: ``q32`` the exact-rerank rows, ``q_op`` their
+        bf16 operand rows (``ops.project_rows`` / the peer exchange of ``dist.PeerQueryExchange``)."""
+        kprime = default_kprime(k) if kprime is None else int(kprime)
+        kprime = min(kprime, ops.MAX_KPRIME)
+        wide = k > kprime or k > 32 or kprime > 32
+        min_lists = WIDE_MIN_LISTS if wide else 0
+        n_q = q_op.shape[0]
+        key = (n_q, kprime, max_ctas, min_lists)
+        plan = ops.score_plan(n_q, self.n, self.d, kprime, max_ctas, min_lists)
         if k > plan["n_lists"] * kprime:
             raise ValueError("k exceeds the number of candidates the plan can hold")
         buf = self._cand.get(key)
         if buf is None:
             self._cand.clear()
-            buf = (torch.empty(q.shape[0], plan["n_lists"], kprime, dtype=torch.float32, device=self.device),
-                   torch.empty(q.shape[0], plan["n_lists"], kprime, dtype=torch.int32, device=self.device),
-                   torch.empty(q.shape[0], dtype=torch.int32, device=self.device),
-                   torch.empty(q.shape[0], dtype=torch.int32, device=self.device))
+            buf = (torch.empty(n_q, plan["n_lists"], kprime, dtype=torch.float32, device=self.device),
+                   torch.empty(n_q, plan["n_lists"], kprime, dtype=torch.int32, device=self.device),
+                   torch.empty(n_q, dtype=torch.int32, device=self.device),
+                   torch.empty(n_q, dtype=torch.int32, device=self.device))
             self._cand[key] = buf
         with _span(kernel_events, "score"):
             cs, ci = ops.score_topk(q_op, self.operand, self.d, kprime, max_ctas, out=buf[:2], thr_workspace=buf[2],

@@ -41,9 +41,11 @@ class PairwiseDistance(torch.autograd.Function):
     @staticmethod
     def backward(ctx, grad_out):
         a, p, d = ctx.saved_tensors
-        w, rs, cs = ops.pairdist_bwd(grad_out, d, ops.row_sqnorm(a), ops.row_sqnorm(p), ctx.c)
-        da = a * rs[:, None] - w @ p          # plain GEMMs (cuBLAS fp32)
-        dp = p * cs[:, None] - w.t() @ a
+        split = d.numel() >= ops.SPLIT_MIN_PAIRS
+        w, rs, cs = ops.pairdist_bwd(grad_out, d, ops.row_sqnorm(a), ops.row_sqnorm(p), ctx.c, split=split)
+        wp, wta = ops.split_products(w, a, p) if split else (w @ p, w.t() @ a)     # plain library GEMMs
+        da = a * rs[:, None] - wp
+        dp = p * cs[:, None] - wta
         return da.to(ctx.in_dtypes[0]), dp.to(ctx.in_dtypes[1]), None
 
 
@@ -77,10 +79,13 @@ class InBatchInfoNCE(torch.autograd.Function):
     def backward(ctx, grad_loss):
         a, p, d, row_lse, col_lse = ctx.saved_tensors
         wr, wc = (0.5, 0.5) if ctx.symmetric else (1.0, 0.0)
+        split = d.numel() >= ops.SPLIT_MIN_PAIRS
         w, rs, cs = ops.pairdist_ce_bwd(d, ops.row_sqnorm(a), ops.row_sqnorm(p), ctx.c, row_lse,
-                                        col_lse if ctx.symmetric else None, ctx.inv_tau, wr, wc, grad_scale=grad_loss)
-        da = a * rs[:, None] - w @ p          # plain GEMMs (cuBLAS fp32)
-        dp = p * cs[:, None] - w.t() @ a
+                                        col_lse if ctx.symmetric else None, ctx.inv_tau, wr, wc, grad_scale=grad_loss,
+                                        split=split)
+        wp, wta = ops.split_products(w, a, p) if split else (w @ p, w.t() @ a)     # plain library GEMMs
+        da = a * rs[:, None] - wp
+        dp = p * cs[:, None] - wta
         return da.to(ctx.in_dtypes[0]), dp.to(ctx.in_dtypes[1]), None, None, None
 
 

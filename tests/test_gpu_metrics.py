@@ -303,3 +303,73 @@ def test_infonce_tensor_core_path_matches_cuda_core_path():
         assert float(loss) == pytest.approx(float(ref), rel=2e-5)
         for got, want in ((ag.grad, a64.grad), (pg.grad, p64.grad)):
             assert float((got.cpu().double() - want).abs().max() / want.abs().max()) < 1e-4
+
+
+def _dist64(a, p, c):
+    """Differentiable fp64 closed form arccosh(1 + 2c|a-p|^2 / ((1-c|a|^2)(1-c|p|^2))) / sqrt(c) (SURVEY 8c:
+    analytically pmath.dist; the broadcast geoopt form would need [n,m,D] fp64 autograd temporaries)."""
+    a2, p2 = a.pow(2).sum(1), p.pow(2).sum(1)
+    diff = (a2[:, None] + p2[None, :] - 2 * a @ p.t()).clamp_min(0)
+    x = 1 + 2 * c * diff / ((1 - c * a2)[:, None] * (1 - c * p2)[None, :])
+    return torch.acosh(x.clamp_min(1 + 1e-15)) / c ** 0.5
+
+
+def test_infonce_split_bf16_backward_matches_fp64_autograd():
+    """n*m >= ops.SPLIT_MIN_PAIRS: the backward emits W as three bf16 planes and forms W P / W^T A as bf16
+    tensor-core GEMMs with fp32 accumulation (six cross products); gradients against fp64 autograd through the
+    oracle's distance matrix, and against the fp32-W path."""
+    from oracle import head
+    from patent_image_retrieval_b200 import train
+    c, n, d, tau = 0.8, 1100, 128, 0.2
+    assert n * n >= ops.SPLIT_MIN_PAIRS
+    mu = synth.gaussian_features(n, d, seed=2, scale=1.0)
+    a0 = head.embed_rows(mu + 0.3 * synth.gaussian_features(n, d, seed=3, scale=1.0), c).cuda()
+    p0 = head.embed_rows(mu + 0.3 * synth.gaussian_features(n, d, seed=4, scale=1.0), c).cuda()
+    for sym in (False, True):
+        ag, pg = a0.clone().requires_grad_(True), p0.clone().requires_grad_(True)
+        loss = train.InBatchInfoNCE.apply(ag, pg, c, tau, sym)
+        loss.backward()
+        a64, p64 = a0.cpu().double().requires_grad_(True), p0.cpu().double().requires_grad_(True)
+        sim = -_dist64(a64, p64, c) / tau
+        lab = torch.arange(n)
+        ref = torch.nn.functional.cross_entropy(sim, lab)
+        if sym:
+            ref = (ref + torch.nn.functional.cross_entropy(sim.t(), lab)) / 2
+        ref.backward()
+        assert float(loss) == pytest.approx(float(ref), rel=2e-5)
+        for got, want in ((ag.grad, a64.grad), (pg.grad, p64.grad)):
+            assert float((got.cpu().double() - want).abs().max() / want.abs().max()) < 1e-4
+    # the split products themselves: fp32-GEMM accuracy or better
+    dm, rl, cl = ops.pairdist_ce_fwd(a0, p0, c, 1 / tau, True)
+    asq, psq = ops.row_sqnorm(a0), ops.row_sqnorm(p0)
+    w, rs, cs = ops.pairdist_ce_bwd(dm, asq, psq, c, rl, cl, 1 / tau, 0.5, 0.5)
+    w3, rs3, cs3 = ops.pairdist_ce_bwd(dm, asq, psq, c, rl, cl, 1 / tau, 0.5, 0.5, split=True)
+    assert w3.dtype == torch.bfloat16 and tuple(w3.shape) == (3, n, n)
+    torch.testing.assert_close(w3.float().sum(0), w, rtol=3e-7, atol=0)
+    assert torch.equal(rs, rs3) and torch.equal(cs, cs3)
+    wp, wta = ops.split_products(w3, a0, p0)
+    ref_wp, ref_wta = w.double() @ p0.double(), w.double().t() @ a0.double()
+    # error against the size of the summed terms (the sums cancel: W has a negative diagonal) at fp32-GEMM level,
+    # and against the result itself well inside the 1e-4 gradient tolerance above
+    scale_wp, scale_wta = w.abs().double() @ p0.abs().double(), w.abs().double().t() @ a0.abs().double()
+    assert float(((wp - ref_wp).abs() / scale_wp).max()) < 2e-6
+    assert float(((wta - ref_wta).abs() / scale_wta).max()) < 2e-6
+    assert float((wp - ref_wp).abs().max() / ref_wp.abs().max()) < 2e-5
+    assert float((wta - ref_wta).abs().max() / ref_wta.abs().max()) < 2e-5
+
+
+def test_generic_pairdist_backward_split_and_ragged():
+    """PairwiseDistance.backward on a ragged n x m (row blocks of 16, column chunks) in both W formats."""
+    from oracle import head
+    from patent_image_retrieval_b200 import train
+    c = 1.3
+    for n, m, d in ((37, 300, 32), (1030, 1111, 64)):
+        a0 = head.embed_rows(synth.gaussian_features(n, d, seed=7, scale=1.0), c).cuda()
+        p0 = head.embed_rows(synth.gaussian_features(m, d, seed=8, scale=1.0), c).cuda()
+        g = torch.randn(n, m, generator=torch.Generator().manual_seed(3)).cuda()
+        ag, pg = a0.clone().requires_grad_(True), p0.clone().requires_grad_(True)
+        (train.PairwiseDistance.apply(ag, pg, c) * g).sum().backward()
+        a64, p64 = a0.cpu().double().requires_grad_(True), p0.cpu().double().requires_grad_(True)
+        (_dist64(a64, p64, c) * g.cpu().double()).sum().backward()
+        for got, want in ((ag.grad, a64.grad), (pg.grad, p64.grad)):
+            assert float((got.cpu().double() - want).abs().max() / want.abs().max()) < 1e-4

@@ -38,6 +38,21 @@ for metric in ("hyperbolic", "cosine"):
     d2, i2 = full.search(q_own, k=k)
     d3, i3 = shd.search(q_own, k=k)
     assert torch.equal(i2, i3) and torch.equal(d2, d3), metric + " sharded"
+    # the peer-memory exchange (projection stores into every rank's buffer, fp32 rows by copy engine) must be the
+    # path that ran, over several steps (two buffer slots), and must equal the NCCL all_gather path bit for bit
+    assert shd._exchange is not None, "peer exchange not used"
+    nccl = ShardedGalleryIndex(g[lo:hi], lo, N, metric=metric, queries="sharded")
+    nccl._exchange_ok = False
+    for step in range(5):
+        q_step = synth.gaussian_features(Ql, D, seed=100 + 10 * step + rank).to(dev)
+        d4, i4 = shd.search(q_step, k=k)
+        d5, i5 = nccl.search(q_step, k=k)
+        d6, i6 = full.search(q_step, k=k)
+        assert torch.equal(i4, i5) and torch.equal(d4, d5), metric + " peer vs nccl"
+        assert torch.equal(i4, i6) and torch.equal(d4, d6), metric + " peer vs single"
+    assert nccl._exchange is None
+    shd._exchange.check()
+    shd._exchange.close()
 # collective 2: exact full-ranking AP from all-reduced keys / rank counts == the unsharded computation
 from patent_image_retrieval_b200.dist import full_ranking_ap
 from patent_image_retrieval_b200 import ops

@@ -91,3 +91,51 @@ def test_argument_errors():
         ops.project_rows(torch.zeros(4, 64, device="cuda"), c=-1.0)
     y, op, _ = ops.project_rows(torch.zeros(0, 64, device="cuda"))   # empty input is fine
     assert y.shape == (0, 64) and op.shape == (0, 80)
+
+
+def test_project_rows_to_several_destinations_and_stream_flags():
+    """hypret_project_rows_peers stores the operand row into every destination buffer (here: three local buffers,
+    at the block offset of a middle rank) exactly as hypret_project_rows does into one; hypret_peer_signal /
+    hypret_peer_wait order two streams through counters in device memory."""
+    import ctypes
+    from patent_image_retrieval_b200 import _lib
+    lib = _lib.load()
+    n, d, c = 333, 192, 0.7
+    u = synth.gaussian_features(n, d, seed=5, scale=1.5).cuda()
+    y_ref, op_ref, _ = ops.project_rows(u, c, mode="expmap0", side="query")
+    kpad = ops.operand_kpad(d)
+    bufs = [torch.full((3 * n, kpad), 7.0, dtype=torch.bfloat16, device="cuda") for _ in range(3)]
+    y = torch.zeros(n, d, device="cuda")
+    arr = (ctypes.c_void_p * 3)(*[b.data_ptr() + n * kpad * 2 for b in bufs])
+    stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    _lib.check(lib.hypret_project_rows_peers(ctypes.c_void_p(u.data_ptr()), n, d, c, ops.MODE["expmap0"],
+                                             ctypes.c_void_p(y.data_ptr()), arr, 3, stream))
+    torch.cuda.synchronize()
+    assert torch.equal(y, y_ref)
+    for b in bufs:
+        assert torch.equal(b[n:2 * n], op_ref)
+        assert bool((b[:n] == 7.0).all()) and bool((b[2 * n:] == 7.0).all())
+    # flags: stream B waits for counters that stream A raises after its copy
+    flags = torch.zeros(33, dtype=torch.int32, device="cuda")
+    src = torch.arange(1 << 20, device="cuda", dtype=torch.float32)
+    dst = torch.zeros_like(src)
+    out = torch.zeros_like(src)
+    a, b = torch.cuda.Stream(), torch.cuda.Stream()
+    fl = (ctypes.c_void_p * 2)(flags.data_ptr(), flags.data_ptr() + 4)
+    # both kernels run once before anything spins: the first launch of a kernel loads its module (lazy loading),
+    # which waits for running kernels -- PeerQueryExchange does the same at construction
+    _lib.check(lib.hypret_peer_signal(fl, 2, 1, stream))
+    _lib.check(lib.hypret_peer_wait(ctypes.c_void_p(flags.data_ptr()), 2, 1, ctypes.c_void_p(flags.data_ptr() + 128),
+                                    stream))
+    torch.cuda.synchronize()
+    with torch.cuda.stream(b):
+        _lib.check(lib.hypret_peer_wait(ctypes.c_void_p(flags.data_ptr()), 2, 3, ctypes.c_void_p(flags.data_ptr() + 128),
+                                        ctypes.c_void_p(b.cuda_stream)))
+        out.copy_(dst)
+    with torch.cuda.stream(a):
+        _lib.check(lib.hypret_peer_copy(ctypes.c_void_p(dst.data_ptr()), ctypes.c_void_p(src.data_ptr()), src.numel() * 4,
+                                        ctypes.c_void_p(a.cuda_stream)))
+        _lib.check(lib.hypret_peer_signal(fl, 2, 4, ctypes.c_void_p(a.cuda_stream)))   # counters may run ahead: >=
+    torch.cuda.synchronize()
+    assert torch.equal(out, src)
+    assert flags[:2].tolist() == [4, 4] and int(flags[32]) == 0

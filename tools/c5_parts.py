@@ -24,3 +24,10 @@ for d in (128, 256):
           "ce_fwd cuda-core", round(tm(lambda: ops.pairdist_ce_fwd(a, p, c, 1 / 0.07, False, tensor_cores=False)), 3),
           "ce_bwd kernel", round(tm(lambda: ops.pairdist_ce_bwd(dm, asq, psq, c, rl, None, 1 / 0.07, 1.0, 0.0)), 3),
           "W@P", round(tm(lambda: w @ p), 3), "W.t@A", round(tm(lambda: w.t() @ a), 3))
+    w3, rs3, cs3 = ops.pairdist_ce_bwd(dm, asq, psq, c, rl, None, 1 / 0.07, 1.0, 0.0, split=True)
+    wp, wta = ops.split_products(w3, a, p)
+    ref_wp, ref_wta = w.double() @ p.double(), w.double().t() @ a.double()
+    print(d, "ce_bwd kernel (3 bf16 planes)", round(tm(lambda: ops.pairdist_ce_bwd(dm, asq, psq, c, rl, None, 1 / 0.07, 1.0, 0.0, split=True)), 3),
+          "split products (both)", round(tm(lambda: ops.split_products(w3, a, p)), 3),
+          "rel err split", float((wp - ref_wp).abs().max() / ref_wp.abs().max()), float((wta - ref_wta).abs().max() / ref_wta.abs().max()),
+          "rel err fp32 gemm", float(((w @ p) - ref_wp).abs().max() / ref_wp.abs().max()))
