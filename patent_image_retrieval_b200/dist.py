@@ -76,6 +76,11 @@ class _RawCuda:
                                          "strides": None}
 
 
+class PeerExchangeUnavailable(RuntimeError):
+    """Raised on EVERY rank when any rank cannot allocate or map the exchange buffers (CUDA IPC refused, devices
+    hidden from each other): the caller falls back to the NCCL all_gather."""
+
+
 class PeerQueryExchange:
     """The all-gather of the per-rank query batches, done through peer memory instead of NCCL (csrc/peer.cu).
 
@@ -111,23 +116,45 @@ class PeerQueryExchange:
         lib = _lib.load()
         handle = (ctypes.c_ubyte * 64)()
         base = ctypes.c_void_p()
+        self.base, self.peer_base, failure = None, [], None
+        # every rank goes through every collective below whatever fails locally, and all ranks agree on the outcome
         with torch.cuda.device(self.device):
-            _lib.check(lib.hypret_peer_alloc(self.nbytes, ctypes.byref(base), handle))
-        self.base = int(base.value)
+            rc = lib.hypret_peer_alloc(self.nbytes, ctypes.byref(base), handle)
+        if rc != 0:
+            failure = f"hypret_peer_alloc rc={rc}"
+        else:
+            self.base = int(base.value)
         mine = torch.tensor(list(handle), dtype=torch.uint8, device=self.device)
         every = torch.empty(self.world * 64, dtype=torch.uint8, device=self.device)
         dist.all_gather_into_tensor(every, mine, group=group)
-        every = every.cpu().view(self.world, 64)
-        self.peer_base = []
-        with torch.cuda.device(self.device):
-            for r in range(self.world):
-                if r == self.rank:
-                    self.peer_base.append(self.base)
-                    continue
-                h = (ctypes.c_ubyte * 64)(*every[r].tolist())
-                ptr = ctypes.c_void_p()
-                _lib.check(lib.hypret_peer_open(h, ctypes.byref(ptr)))
-                self.peer_base.append(int(ptr.value))
+        ok = torch.tensor([0 if failure else 1], device=self.device)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
+        if bool(ok.item()):
+            every = every.cpu().view(self.world, 64)
+            with torch.cuda.device(self.device):
+                for r in range(self.world):
+                    if r == self.rank:
+                        self.peer_base.append(self.base)
+                        continue
+                    h = (ctypes.c_ubyte * 64)(*every[r].tolist())
+                    ptr = ctypes.c_void_p()
+                    rc = lib.hypret_peer_open(h, ctypes.byref(ptr))
+                    if rc != 0:
+                        failure = failure or f"hypret_peer_open(rank {r}) rc={rc}"
+                        self.peer_base.append(None)
+                    else:
+                        self.peer_base.append(int(ptr.value))
+            ok = torch.tensor([0 if failure else 1], device=self.device)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
+        if not bool(ok.item()):
+            with torch.cuda.device(self.device):
+                for r, ptr in enumerate(self.peer_base):
+                    if r != self.rank and ptr is not None:
+                        lib.hypret_peer_close(ctypes.c_void_p(ptr))
+                if self.base is not None:
+                    lib.hypret_peer_free(ctypes.c_void_p(self.base))
+            self.base = None
+            raise PeerExchangeUnavailable(failure or "a peer could not map the exchange buffers")
         raw = torch.as_tensor(_RawCuda(self.base, self.nbytes), device=self.device)
         self._raw = raw
         self.op_all, self.pt_all = [], []
@@ -272,7 +299,13 @@ class ShardedGalleryIndex:
         if self._exchange is None or self._exchange.ql != n_queries:
             if self._exchange is not None:
                 self._exchange.close()
-            self._exchange = PeerQueryExchange(n_queries, self.local.d, self.local.device, self.group)
+                self._exchange = None
+            try:
+                self._exchange = PeerQueryExchange(n_queries, self.local.d, self.local.device, self.group)
+            except PeerExchangeUnavailable as exc:      # raised on all ranks together
+                import warnings
+                warnings.warn(f"peer-memory query exchange unavailable ({exc}); using the NCCL all_gather")
+                self._exchange_ok = False
         return self._exchange
 
     def _single(self) -> bool:

@@ -12,6 +12,7 @@ exact CUDA kernel (``hypret_pairdist``) and its backward is closed-form (``hypre
 """
 from __future__ import annotations
 
+import os
 import random
 from typing import Optional
 
@@ -20,6 +21,12 @@ import torch.nn.functional as F
 
 from . import ops
 from .geoopt_shim import pmath
+
+
+# Tensor-core training path (csrc/gramdist.cu forward, three-plane W + bf16 GEMMs backward).  The bf16 x 3 splits carry
+# fp32 values exactly, but the tensor core's fp32 accumulator truncates (<= K/16 ulps of the running sum, one-sided;
+# DESIGN 4.6).  HYPRET_TRAIN_FP32=1 keeps every product on the FP32 pipe (FFMA distance tiles, SGEMM backward).
+TENSOR_CORES = os.environ.get("HYPRET_TRAIN_FP32", "0") != "1"
 
 
 def _c_of(k) -> float:
@@ -41,7 +48,7 @@ class PairwiseDistance(torch.autograd.Function):
     @staticmethod
     def backward(ctx, grad_out):
         a, p, d = ctx.saved_tensors
-        split = d.numel() >= ops.SPLIT_MIN_PAIRS
+        split = TENSOR_CORES and d.numel() >= ops.SPLIT_MIN_PAIRS
         w, rs, cs = ops.pairdist_bwd(grad_out, d, ops.row_sqnorm(a), ops.row_sqnorm(p), ctx.c, split=split)
         wp, wta = ops.split_products(w, a, p) if split else (w @ p, w.t() @ a)     # plain library GEMMs
         da = a * rs[:, None] - wp
@@ -65,7 +72,8 @@ class InBatchInfoNCE(torch.autograd.Function):
         if a32.shape != p32.shape:
             raise ValueError("anchors and positives must have the same shape")
         inv_tau = 1.0 / float(temperature)
-        d, row_lse, col_lse = ops.pairdist_ce_fwd(a32, p32, c, inv_tau, want_cols=symmetric)
+        d, row_lse, col_lse = ops.pairdist_ce_fwd(a32, p32, c, inv_tau, want_cols=symmetric,
+                                                  tensor_cores=None if TENSOR_CORES else False)
         diag_sim = -torch.diagonal(d) * inv_tau
         loss = (row_lse - diag_sim).mean()
         if symmetric:
@@ -79,7 +87,7 @@ class InBatchInfoNCE(torch.autograd.Function):
     def backward(ctx, grad_loss):
         a, p, d, row_lse, col_lse = ctx.saved_tensors
         wr, wc = (0.5, 0.5) if ctx.symmetric else (1.0, 0.0)
-        split = d.numel() >= ops.SPLIT_MIN_PAIRS
+        split = TENSOR_CORES and d.numel() >= ops.SPLIT_MIN_PAIRS
         w, rs, cs = ops.pairdist_ce_bwd(d, ops.row_sqnorm(a), ops.row_sqnorm(p), ctx.c, row_lse,
                                         col_lse if ctx.symmetric else None, ctx.inv_tau, wr, wc, grad_scale=grad_loss,
                                         split=split)

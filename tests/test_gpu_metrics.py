@@ -349,11 +349,14 @@ def test_infonce_split_bf16_backward_matches_fp64_autograd():
     assert torch.equal(rs, rs3) and torch.equal(cs, cs3)
     wp, wta = ops.split_products(w3, a0, p0)
     ref_wp, ref_wta = w.double() @ p0.double(), w.double().t() @ a0.double()
-    # error against the size of the summed terms (the sums cancel: W has a negative diagonal) at fp32-GEMM level,
-    # and against the result itself well inside the 1e-4 gradient tolerance above
+    # error against the size of the summed terms (the sums cancel: W has a negative diagonal).  The six bf16 cross
+    # products are exact to 2^-24, but the tensor core's fp32 accumulator TRUNCATES: up to one ulp of the running sum
+    # per 16-deep MMA step, all in one direction (measured 4.4e-6 here = 69 steps x 2^-24; an FFMA SGEMM rounds to
+    # nearest, ~sqrt(K) ulps) -- well inside the 1e-4 gradient tolerance above, documented in DESIGN 4.6
+    bound = 1.5 * (n / 16 + 8) * 2.0 ** -24
     scale_wp, scale_wta = w.abs().double() @ p0.abs().double(), w.abs().double().t() @ a0.abs().double()
-    assert float(((wp - ref_wp).abs() / scale_wp).max()) < 2e-6
-    assert float(((wta - ref_wta).abs() / scale_wta).max()) < 2e-6
+    assert float(((wp - ref_wp).abs() / scale_wp).max()) < bound
+    assert float(((wta - ref_wta).abs() / scale_wta).max()) < bound
     assert float((wp - ref_wp).abs().max() / ref_wp.abs().max()) < 2e-5
     assert float((wta - ref_wta).abs().max() / ref_wta.abs().max()) < 2e-5
 
