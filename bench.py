@@ -303,8 +303,9 @@ def main():
     # W shards share one query's k' rows between them
     rerank_bytes = q_scored * kprime * D * 4 // (world if weak else 1)
     peer_x = weak and getattr(index, "_exchange", None) is not None    # query exchange through peer memory
-    n_own = 3 if world == 1 else ((10 if peer_x else 6) if weak else 4)   # own kernels per step (gpu_launches_note)
-    n_nccl = 0 if world == 1 else ((4 if peer_x else 5) if weak else 2)
+    peer_r = peer_x and os.environ.get("HYPRET_PEER_ROUTE", "1") != "0"  # every exchange fused into its producer
+    n_own = 3 if world == 1 else ((16 if peer_r else 10 if peer_x else 6) if weak else 4)   # own kernels per step
+    n_nccl = 0 if world == 1 else ((0 if peer_r else 4 if peer_x else 5) if weak else 2)
     achieved = flops / (score_ms * 1e-3) / 1e12
     traffic = None
     tp = ROOT / "profiles" / "score_topk_traffic.json"
@@ -325,7 +326,10 @@ def main():
                                     ("projection kernel stores the operand rows into every rank's buffer over NVLink "
                                      "(peer memory), fp32 rows follow by copy engine under the scoring kernel"
                                      if peer_x else "all_gather(queries)") + " -> shard-local "
-                                    "search of all W*Q -> all_to_all([Q,k] lists) -> merge at the owner" if weak else
+                                    "search of all W*Q -> " +
+                                    ("cand_select / kth_smallest / pruned rerank store their outputs into the query "
+                                     "owners' buffers (NVLink), counters instead of collectives"
+                                     if peer_r else "all_to_all([Q,k] lists)") + " -> merge at the owner" if weak else
                                     "queries replicated: shard-local search -> all_gather([Q,k] lists) -> merge"))
                    if world > 1 else "single GPU",
                    "cache": "inputs larger than L2 (bf16 gallery operand %.0f MB vs 126 MB L2); no flush" %
@@ -338,7 +342,8 @@ def main():
                 "serial": {"value": q_total / (ms_e2e_serial * 1e-3), "ms_per_step": ms_e2e_serial}},
         "gpu_launches": args.steps * n_own,
         "gpu_launches_note": "own kernels per step per rank: project_rows, score_topk, " +
-                             (("peer_signal x2, peer_wait x2, " if peer_x else "") +
+                             (("peer_signal x5, peer_wait x5, " if peer_r else "peer_signal x2, peer_wait x2, "
+                               if peer_x else "") +
                               "cand_select, kth_smallest, rerank (pruned), merge_topk" if weak else
                               "rerank, merge_topk" if world > 1 else "rerank") +
                              (" (+ %d NCCL collectives)" % n_nccl if world > 1 else ""),

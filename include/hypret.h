@@ -82,6 +82,18 @@ int hypret_peer_copy(void* dst, const void* src, size_t bytes, void* stream);
 int hypret_project_rows_peers(const float* u, int64_t n, int d, float c, int mode, float* y32,
                               void* const* op_dsts_host, int n_dst, void* stream);
 int hypret_peer_signal(void* const* flags_host, int n, uint32_t value, void* stream);
+
+/* Output routing of the sharded-serving exchange: the all_to_all / all_gather that follows a kernel is done BY that
+ * kernel with posted NVLink stores into the receivers' exchange buffers (then hypret_peer_signal / hypret_peer_wait).
+ * Row q of a [n_ranks*ql, width] result belongs to rank q / ql and is stored at row (me*ql + q % ql) of the
+ * [n_ranks*ql, width] receive region at byte offset *_off of that rank's buffer (the layout an all_to_all of
+ * equal blocks produces).  n_ranks == 0 or a NULL route: local outputs only. */
+typedef struct {
+  void* base[16];    /* exchange-buffer base of every rank, own included, as mapped in THIS process */
+  int32_t n_ranks;
+  int32_t me;
+  int64_t ql;        /* rows per rank */
+} hypret_peer_route;
 int hypret_peer_wait(const uint32_t* flags, int n, uint32_t value, uint32_t* err, void* stream);
 
 /* Work decomposition of hypret_score_topk for a problem size on the current device.
@@ -180,6 +192,22 @@ int hypret_rerank(const float* q32, const float* g32, int64_t Q, int64_t N, int 
 int hypret_cand_select(const float* cand_score, const int32_t* cand_idx, const int32_t* list_count, int64_t Q,
                        int n_lists, int kprime, float* sel_score, int32_t* sel_idx, void* stream);
 int hypret_kth_smallest(const float* vals, int n_parts, int64_t Q, int m, int kth, float* out, void* stream);
+/* The same three with their exchange fused in (hypret_peer_route above):
+ *   hypret_cand_select_route    sel_score additionally lands in the query owner's receive region (recv_off) -- the
+ *                               all_to_all of the [Q,kprime] surrogates
+ *   hypret_kth_smallest_route   out[q] (Q == route->ql own queries) additionally lands at [me*ql + q] of the [n_ranks*ql]
+ *                               region (out_off) of EVERY rank -- the all_gather of the thresholds
+ *   hypret_rerank_pruned_route  the [Q,k] lists go ONLY to the query owners' receive regions (score_off: fp32,
+ *                               idx_off: int64) -- the two all_to_alls of the result lists */
+int hypret_cand_select_route(const float* cand_score, const int32_t* cand_idx, const int32_t* list_count, int64_t Q,
+                             int n_lists, int kprime, float* sel_score, int32_t* sel_idx,
+                             const hypret_peer_route* route, int64_t recv_off, void* stream);
+int hypret_kth_smallest_route(const float* vals, int n_parts, int64_t Q, int m, int kth, float* out,
+                              const hypret_peer_route* route, int64_t out_off, void* stream);
+int hypret_rerank_pruned_route(const float* q32, const float* g32, int64_t Q, int64_t N, int d, float c, int metric,
+                               const float* cand_score, const int32_t* cand_idx, int n_lists, int kprime, int k,
+                               int64_t idx_offset, const float* prune_thr, const hypret_peer_route* route,
+                               int64_t score_off, int64_t idx_off, void* stream);
 int hypret_rerank_pruned(const float* q32, const float* g32, int64_t Q, int64_t N, int d, float c, int metric,
                          const float* cand_score, const int32_t* cand_idx, int n_lists, int kprime, int k,
                          int64_t idx_offset, const float* prune_thr, float* out_score, int64_t* out_idx,

@@ -15,6 +15,11 @@ from . import build as _build
 _LIB = None
 
 
+class PeerRoute(Structure):
+    """hypret_peer_route (include/hypret.h)."""
+    _fields_ = [("base", c_void_p * 16), ("n_ranks", c_int32), ("me", c_int32), ("ql", c_int64)]
+
+
 class ScorePlan(Structure):
     _fields_ = [
         ("n_qtiles", c_int32),
@@ -60,6 +65,13 @@ SIGNATURES = {
                                           c_void_p]),
     "hypret_peer_signal": (c_int, [POINTER(c_void_p), c_int, c_uint32, c_void_p]),
     "hypret_peer_wait": (c_int, [c_void_p, c_int, c_uint32, c_void_p, c_void_p]),
+    "hypret_cand_select_route": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int, c_void_p, c_void_p,
+                                         POINTER(PeerRoute), c_int64, c_void_p]),
+    "hypret_kth_smallest_route": (c_int, [c_void_p, c_int, c_int64, c_int, c_int, c_void_p, POINTER(PeerRoute), c_int64,
+                                          c_void_p]),
+    "hypret_rerank_pruned_route": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int, c_float, c_int, c_void_p,
+                                           c_void_p, c_int, c_int, c_int, c_int64, c_void_p, POINTER(PeerRoute), c_int64,
+                                           c_int64, c_void_p]),
     "hypret_score_plan": (c_int, [c_int64, c_int64, c_int, c_int, c_int, c_int, POINTER(ScorePlan)]),
     "hypret_score_strip": (c_int, [POINTER(ScorePlan), c_int, c_int, POINTER(c_int32)]),
     "hypret_score_topk": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int, c_int, c_int, c_int, c_int, c_void_p,

@@ -130,21 +130,33 @@ static int rerank_common(const float* q32, const float* g32, int64_t Q, int64_t 
                          const float* cand_score, const int32_t* cand_idx, const int32_t* list_count, int n_lists,
                          int kprime, int k,
                          int64_t idx_offset, const float* prune_thr, float* out_score, int64_t* out_idx,
-                         float* out_margin, void* stream) {
+                         float* out_margin, void* stream, const hypret_peer_route* route = nullptr,
+                         int64_t score_off = 0, int64_t idx_off = 0) {
   if (Q < 0 || N < 1 || d < 4 || (d & 3)) return HYPRET_EINVAL;
+  const bool routed = route != nullptr && route->n_ranks > 0;
   if (metric != HYPRET_METRIC_COSINE && metric != HYPRET_METRIC_HYPERBOLIC) return HYPRET_EINVAL;
   if (metric == HYPRET_METRIC_HYPERBOLIC && !(c > 0.f)) return HYPRET_EINVAL;
   if (kprime < 1 || kprime > 64 || k < 1 || k > 128 || n_lists < 1) return HYPRET_EINVAL;
   if (k > kprime * n_lists || (int64_t)n_lists * kprime > 16384) return HYPRET_EINVAL;
   if (Q == 0) return HYPRET_OK;
-  if (q32 == nullptr || g32 == nullptr || cand_score == nullptr || cand_idx == nullptr || out_score == nullptr ||
-      out_idx == nullptr || !aligned16(q32) || !aligned16(g32))
+  if (q32 == nullptr || g32 == nullptr || cand_score == nullptr || cand_idx == nullptr ||
+      (!routed && (out_score == nullptr || out_idx == nullptr)) || !aligned16(q32) || !aligned16(g32))
     return HYPRET_EINVAL;
   int rc = check_device();
   if (rc != HYPRET_OK) return rc;
   return hypret_launch_rerank(q32, g32, Q, N, d, c, metric, cand_score, cand_idx, list_count, n_lists * kprime,
-                              kprime, k, idx_offset, prune_thr, out_score, out_idx, out_margin,
-                              static_cast<cudaStream_t>(stream));
+                              kprime, k, idx_offset, prune_thr, out_score, out_idx, out_margin, route, score_off,
+                              idx_off, static_cast<cudaStream_t>(stream));
+}
+
+static int check_route(const hypret_peer_route* route, int64_t Q, bool rows_are_own) {
+  if (route == nullptr || route->n_ranks < 1 || route->n_ranks > HYPRET_MAX_PEERS || route->me < 0 ||
+      route->me >= route->n_ranks || route->ql < 1)
+    return HYPRET_EINVAL;
+  if (Q != (rows_are_own ? route->ql : route->ql * route->n_ranks)) return HYPRET_EINVAL;
+  for (int i = 0; i < route->n_ranks; ++i)
+    if (route->base[i] == nullptr) return HYPRET_EINVAL;
+  return HYPRET_OK;
 }
 
 int hypret_rerank(const float* q32, const float* g32, int64_t Q, int64_t N, int d, float c, int metric,
@@ -163,24 +175,62 @@ int hypret_rerank_pruned(const float* q32, const float* g32, int64_t Q, int64_t 
                        prune_thr, out_score, out_idx, nullptr, stream);
 }
 
-int hypret_cand_select(const float* cand_score, const int32_t* cand_idx, const int32_t* list_count, int64_t Q,
-                       int n_lists, int kprime, float* sel_score, int32_t* sel_idx, void* stream) {
+static int cand_select_common(const float* cand_score, const int32_t* cand_idx, const int32_t* list_count, int64_t Q,
+                              int n_lists, int kprime, float* sel_score, int32_t* sel_idx,
+                              const hypret_peer_route* route, int64_t recv_off, void* stream) {
   if (Q < 0 || n_lists < 1 || kprime < 1 || kprime > 32 || (int64_t)n_lists * kprime > 16384) return HYPRET_EINVAL;
   if (Q == 0) return HYPRET_OK;
   if (cand_score == nullptr || cand_idx == nullptr || sel_score == nullptr || sel_idx == nullptr) return HYPRET_EINVAL;
   int rc = check_device();
   if (rc != HYPRET_OK) return rc;
   return hypret_launch_cand_select(cand_score, cand_idx, list_count, Q, n_lists * kprime, kprime, sel_score, sel_idx,
-                                   static_cast<cudaStream_t>(stream));
+                                   route, recv_off, static_cast<cudaStream_t>(stream));
 }
 
-int hypret_kth_smallest(const float* vals, int n_parts, int64_t Q, int m, int kth, float* out, void* stream) {
+int hypret_cand_select(const float* cand_score, const int32_t* cand_idx, const int32_t* list_count, int64_t Q,
+                       int n_lists, int kprime, float* sel_score, int32_t* sel_idx, void* stream) {
+  return cand_select_common(cand_score, cand_idx, list_count, Q, n_lists, kprime, sel_score, sel_idx, nullptr, 0,
+                            stream);
+}
+
+int hypret_cand_select_route(const float* cand_score, const int32_t* cand_idx, const int32_t* list_count, int64_t Q,
+                             int n_lists, int kprime, float* sel_score, int32_t* sel_idx,
+                             const hypret_peer_route* route, int64_t recv_off, void* stream) {
+  if (Q > 0 && (check_route(route, Q, false) != HYPRET_OK || recv_off < 0 || (recv_off & 3))) return HYPRET_EINVAL;
+  return cand_select_common(cand_score, cand_idx, list_count, Q, n_lists, kprime, sel_score, sel_idx, route, recv_off,
+                            stream);
+}
+
+static int kth_smallest_common(const float* vals, int n_parts, int64_t Q, int m, int kth, float* out,
+                               const hypret_peer_route* route, int64_t out_off, void* stream) {
   if (n_parts < 1 || Q < 0 || m < 1 || kth < 1 || (int64_t)n_parts * m > 2048) return HYPRET_EINVAL;
   if (Q == 0) return HYPRET_OK;
   if (vals == nullptr || out == nullptr) return HYPRET_EINVAL;
   int rc = check_device();
   if (rc != HYPRET_OK) return rc;
-  return hypret_launch_kth_smallest(vals, n_parts, Q, m, kth, out, static_cast<cudaStream_t>(stream));
+  return hypret_launch_kth_smallest(vals, n_parts, Q, m, kth, out, route, out_off, static_cast<cudaStream_t>(stream));
+}
+
+int hypret_kth_smallest(const float* vals, int n_parts, int64_t Q, int m, int kth, float* out, void* stream) {
+  return kth_smallest_common(vals, n_parts, Q, m, kth, out, nullptr, 0, stream);
+}
+
+int hypret_kth_smallest_route(const float* vals, int n_parts, int64_t Q, int m, int kth, float* out,
+                              const hypret_peer_route* route, int64_t out_off, void* stream) {
+  if (Q > 0 && (check_route(route, Q, true) != HYPRET_OK || out_off < 0 || (out_off & 3))) return HYPRET_EINVAL;
+  return kth_smallest_common(vals, n_parts, Q, m, kth, out, route, out_off, stream);
+}
+
+int hypret_rerank_pruned_route(const float* q32, const float* g32, int64_t Q, int64_t N, int d, float c, int metric,
+                               const float* cand_score, const int32_t* cand_idx, int n_lists, int kprime, int k,
+                               int64_t idx_offset, const float* prune_thr, const hypret_peer_route* route,
+                               int64_t score_off, int64_t idx_off, void* stream) {
+  if (prune_thr == nullptr || kprime > 32 || k > 32 || k > kprime) return HYPRET_EINVAL;
+  if (Q > 0 && (check_route(route, Q, false) != HYPRET_OK || score_off < 0 || idx_off < 0 || (score_off & 3) ||
+                (idx_off & 7)))
+    return HYPRET_EINVAL;
+  return rerank_common(q32, g32, Q, N, d, c, metric, cand_score, cand_idx, nullptr, n_lists, kprime, k, idx_offset,
+                       prune_thr, nullptr, nullptr, nullptr, stream, route, score_off, idx_off);
 }
 
 int hypret_merge_topk(const float* scores, const int64_t* idx, int n_shards, int64_t Q, int k, int descending,

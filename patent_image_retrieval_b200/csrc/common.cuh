@@ -315,14 +315,39 @@ int hypret_launch_project_rows(const float* u, int64_t n, int d, float c, int mo
 int hypret_launch_score_topk(const void* q_op, int64_t Q, const void* g_op, int64_t N, int d, int kprime,
                              int n_lists, int max_ctas, int min_lists, float* cand_score, int32_t* cand_idx,
                              uint32_t* thr_ws, int32_t* list_count, float* debug_scores, cudaStream_t stream);
+// Kernel-side view of hypret_peer_route (passed by value); n == 0: no routing.
+struct PeerRoute {
+  char* base[HYPRET_MAX_PEERS];
+  int n, me;
+  int64_t ql;
+};
+inline PeerRoute make_route(const hypret_peer_route* r) {
+  PeerRoute o;
+  o.n = 0; o.me = 0; o.ql = 1;
+  for (int i = 0; i < HYPRET_MAX_PEERS; ++i) o.base[i] = nullptr;
+  if (r != nullptr && r->n_ranks > 0) {
+    o.n = r->n_ranks; o.me = r->me; o.ql = r->ql;
+    for (int i = 0; i < r->n_ranks && i < HYPRET_MAX_PEERS; ++i) o.base[i] = static_cast<char*>(r->base[i]);
+  }
+  return o;
+}
+// row q of a rank-major [n*ql, .] result -> (owner rank, row in the owner's receive region)
+__device__ __forceinline__ int64_t route_row(const PeerRoute& r, int64_t q, int* owner) {
+  const int64_t o = q / r.ql;
+  *owner = (int)o;
+  return (int64_t)r.me * r.ql + (q - o * r.ql);
+}
+
 int hypret_launch_rerank(const float* q32, const float* g32, int64_t Q, int64_t N, int d, float c, int metric,
                          const float* cand_score, const int32_t* cand_idx, const int32_t* list_count, int n_cand,
                          int kprime, int k, int64_t idx_offset, const float* prune_thr, float* out_score,
-                         int64_t* out_idx, float* out_margin, cudaStream_t stream);
+                         int64_t* out_idx, float* out_margin, const hypret_peer_route* route, int64_t score_off,
+                         int64_t idx_off, cudaStream_t stream);
 int hypret_launch_cand_select(const float* cand_score, const int32_t* cand_idx, const int32_t* list_count, int64_t Q,
-                              int n_cand, int kprime, float* sel_score, int32_t* sel_idx, cudaStream_t stream);
+                              int n_cand, int kprime, float* sel_score, int32_t* sel_idx,
+                              const hypret_peer_route* route, int64_t recv_off, cudaStream_t stream);
 int hypret_launch_kth_smallest(const float* vals, int n_parts, int64_t Q, int m, int kth, float* out,
-                               cudaStream_t stream);
+                               const hypret_peer_route* route, int64_t out_off, cudaStream_t stream);
 int hypret_launch_merge_topk(const float* scores, const int64_t* idx, int W, int64_t Q, int k, int descending,
                              float* out_score, int64_t* out_idx, cudaStream_t stream);
 int hypret_launch_pairdist(const float* a, const float* p, int64_t n, int64_t m, int d, float c, float* out,

@@ -72,7 +72,8 @@ merge_topk_kernel(const float* __restrict__ scores, const int64_t* __restrict__ 
 // out[q] = the kth smallest (1-based) of the n_parts * m values of query q, vals [n_parts, Q, m]; +inf when
 // fewer than kth finite values exist.  Rank counting in shared memory, one warp per query (n <= 2048).
 __global__ void __launch_bounds__(MG_WARPS * 32)
-kth_smallest_kernel(const float* __restrict__ vals, int n_parts, int64_t Q, int m, int kth, float* __restrict__ out) {
+kth_smallest_kernel(const float* __restrict__ vals, int n_parts, int64_t Q, int m, int kth, float* __restrict__ out,
+                    const PeerRoute route, int64_t out_off) {
   extern __shared__ float sm_vals[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t q = (int64_t)blockIdx.x * MG_WARPS + warp;
@@ -85,8 +86,13 @@ kth_smallest_kernel(const float* __restrict__ vals, int n_parts, int64_t Q, int 
     v[t] = (x == x) ? x : INFINITY;            // NaN counts as +inf
   }
   __syncwarp();
+  // routed: the all_gather of the thresholds -- the value also lands at [me*Q + q] of every rank's region
   if (kth > n) {
-    if (lane == 0) out[q] = INFINITY;
+    if (lane == 0) {
+      out[q] = INFINITY;
+      for (int r = 0; r < route.n; ++r)
+        reinterpret_cast<float*>(route.base[r] + out_off)[(int64_t)route.me * Q + q] = INFINITY;
+    }
     return;
   }
   for (int t = lane; t < n; t += 32) {
@@ -96,18 +102,22 @@ kth_smallest_kernel(const float* __restrict__ vals, int n_parts, int64_t Q, int 
       const float y = v[u];
       rank += (y < x) || (y == x && u < t);
     }
-    if (rank == kth - 1) out[q] = x;           // exactly one t has this rank
+    if (rank == kth - 1) {                     // exactly one t has this rank
+      out[q] = x;
+      for (int r = 0; r < route.n; ++r)
+        reinterpret_cast<float*>(route.base[r] + out_off)[(int64_t)route.me * Q + q] = x;
+    }
   }
 }
 
 }  // namespace
 
 int hypret_launch_kth_smallest(const float* vals, int n_parts, int64_t Q, int m, int kth, float* out,
-                               cudaStream_t stream) {
+                               const hypret_peer_route* route, int64_t out_off, cudaStream_t stream) {
   if (Q == 0) return HYPRET_OK;
   const size_t smem = (size_t)MG_WARPS * n_parts * m * sizeof(float);
-  kth_smallest_kernel<<<(unsigned)((Q + MG_WARPS - 1) / MG_WARPS), MG_WARPS * 32, smem, stream>>>(vals, n_parts, Q, m,
-                                                                                                 kth, out);
+  kth_smallest_kernel<<<(unsigned)((Q + MG_WARPS - 1) / MG_WARPS), MG_WARPS * 32, smem, stream>>>(
+      vals, n_parts, Q, m, kth, out, make_route(route), out_off);
   return (int)cudaGetLastError();
 }
 

@@ -82,12 +82,20 @@ rerank_kernel(const float* __restrict__ q32, const float* __restrict__ g32, int6
               int metric, const float* __restrict__ cand_score, const int32_t* __restrict__ cand_idx,
               const int32_t* __restrict__ list_count, int n_cand, int kprime, int k, int64_t idx_offset,
               const float* __restrict__ prune_thr,
-              float* __restrict__ out_score, int64_t* __restrict__ out_idx, float* __restrict__ out_margin) {
+              float* __restrict__ out_score, int64_t* __restrict__ out_idx, float* __restrict__ out_margin,
+              const PeerRoute route, int64_t score_off, int64_t idx_off) {
   extern __shared__ uint8_t smem_raw[];
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int64_t q = (int64_t)blockIdx.x * RR_WARPS + warp;
   if (q >= Q) return;
+  int64_t out_row = q;
+  if (route.n > 0) {        // the [Q,k] list goes straight into the query owner's receive region (NVLink stores)
+    int owner;
+    out_row = route_row(route, q, &owner);
+    out_score = reinterpret_cast<float*>(route.base[owner] + score_off);
+    out_idx = reinterpret_cast<int64_t*>(route.base[owner] + idx_off);
+  }
   float* cs = reinterpret_cast<float*>(smem_raw) + (size_t)warp * n_cand;
   int* ci = reinterpret_cast<int*>(reinterpret_cast<float*>(smem_raw) + (size_t)RR_WARPS * n_cand) +
             (size_t)warp * n_cand;
@@ -213,8 +221,8 @@ rerank_kernel(const float* __restrict__ q32, const float* __restrict__ g32, int6
   if (lane < k) {
     const bool valid = my_idx >= 0;
     const double val = (metric == HYPRET_METRIC_HYPERBOLIC) ? my_key : -my_key;
-    out_score[q * k + lane] = valid ? (float)val : ((metric == HYPRET_METRIC_HYPERBOLIC) ? INFINITY : -INFINITY);
-    out_idx[q * k + lane] = valid ? (int64_t)my_idx + idx_offset : (int64_t)-1;
+    out_score[out_row * k + lane] = valid ? (float)val : ((metric == HYPRET_METRIC_HYPERBOLIC) ? INFINITY : -INFINITY);
+    out_idx[out_row * k + lane] = valid ? (int64_t)my_idx + idx_offset : (int64_t)-1;
   }
   if (out_margin != nullptr) {
     const double kth = __shfl_sync(0xffffffffu, my_sur, k - 1);
@@ -232,7 +240,8 @@ rerank_kernel(const float* __restrict__ q32, const float* __restrict__ g32, int6
 __global__ void __launch_bounds__(RR_WARPS * 32)
 cand_select_kernel(const float* __restrict__ cand_score, const int32_t* __restrict__ cand_idx,
                    const int32_t* __restrict__ list_count, int64_t Q, int n_cand, int kprime,
-                   float* __restrict__ sel_score, int32_t* __restrict__ sel_idx) {
+                   float* __restrict__ sel_score, int32_t* __restrict__ sel_idx, const PeerRoute route,
+                   int64_t recv_off) {
   extern __shared__ uint8_t smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t q = (int64_t)blockIdx.x * RR_WARPS + warp;
@@ -251,6 +260,11 @@ cand_select_kernel(const float* __restrict__ cand_score, const int32_t* __restri
   if (lane < kprime) {
     sel_score[q * kprime + lane] = my_score;
     sel_idx[q * kprime + lane] = my_idx;
+    if (route.n > 0) {      // the all_to_all of the surrogates: the owner of query q receives this shard's list
+      int owner;
+      const int64_t row = route_row(route, q, &owner);
+      reinterpret_cast<float*>(route.base[owner] + recv_off)[row * kprime + lane] = my_score;
+    }
   }
 }
 
@@ -453,7 +467,8 @@ rerank_wide_kernel(const float* __restrict__ q32, const float* __restrict__ g32,
 }  // namespace
 
 int hypret_launch_cand_select(const float* cand_score, const int32_t* cand_idx, const int32_t* list_count, int64_t Q,
-                              int n_cand, int kprime, float* sel_score, int32_t* sel_idx, cudaStream_t stream) {
+                              int n_cand, int kprime, float* sel_score, int32_t* sel_idx,
+                              const hypret_peer_route* route, int64_t recv_off, cudaStream_t stream) {
   if (Q == 0) return HYPRET_OK;
   const size_t smem = (size_t)RR_WARPS * n_cand * 8;
   if (smem > 200 * 1024) return HYPRET_EUNSUPPORTED;
@@ -462,17 +477,18 @@ int hypret_launch_cand_select(const float* cand_score, const int32_t* cand_idx, 
     if (e != cudaSuccess) return (int)e;
   }
   cand_select_kernel<<<(unsigned)((Q + RR_WARPS - 1) / RR_WARPS), RR_WARPS * 32, smem, stream>>>(
-      cand_score, cand_idx, list_count, Q, n_cand, kprime, sel_score, sel_idx);
+      cand_score, cand_idx, list_count, Q, n_cand, kprime, sel_score, sel_idx, make_route(route), recv_off);
   return (int)cudaGetLastError();
 }
 
 int hypret_launch_rerank(const float* q32, const float* g32, int64_t Q, int64_t N, int d, float c, int metric,
                          const float* cand_score, const int32_t* cand_idx, const int32_t* list_count, int n_cand,
                          int kprime, int k, int64_t idx_offset, const float* prune_thr, float* out_score,
-                         int64_t* out_idx, float* out_margin, cudaStream_t stream) {
+                         int64_t* out_idx, float* out_margin, const hypret_peer_route* route, int64_t score_off,
+                         int64_t idx_off, cudaStream_t stream) {
   if (Q == 0) return HYPRET_OK;
   if (kprime > 32 || k > 32 || k > kprime) {
-    if (prune_thr != nullptr) return HYPRET_EUNSUPPORTED;
+    if (prune_thr != nullptr || (route != nullptr && route->n_ranks > 0)) return HYPRET_EUNSUPPORTED;
     const int n_lists = n_cand / kprime;
     int n_pad = RW_SURV;
     while (n_pad < n_cand) n_pad <<= 1;
@@ -514,7 +530,8 @@ int hypret_launch_rerank(const float* q32, const float* g32, int64_t Q, int64_t 
     rerank_kernel<NV><<<(unsigned)grid, RR_WARPS * 32, smem, stream>>>(q32, g32, Q, N, d, c, metric, cand_score,    \
                                                                       cand_idx, list_count, n_cand, kprime, k,      \
                                                                       idx_offset, prune_thr, out_score, out_idx,    \
-                                                                      out_margin);                                  \
+                                                                      out_margin, make_route(route), score_off,     \
+                                                                      idx_off);                                     \
     return (int)cudaGetLastError();                                                                                 \
   } while (0)
   if (need <= 1) HYPRET_RERANK_LAUNCH(1);

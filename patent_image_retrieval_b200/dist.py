@@ -95,8 +95,11 @@ class PeerQueryExchange:
     Two buffer slots: a rank cannot start step i+2 before every peer has finished step i (see csrc/peer.cu)."""
 
     FLAGS_BYTES = 1024           # [0:64) operand counters, [64:128) point counters, [128:132) error word,
-                                 # [192:256) scratch counters (kernel preload)
+                                 # [192:256) scratch counters (kernel preload), then the counters of the routed
+                                 # exchanges: [256:320) surrogate lists, [320:384) thresholds, [384:448) result lists
+    F_OP, F_PT, F_ERR, F_SCRATCH, F_SEL, F_THR, F_LST = 0, 64, 128, 192, 256, 320, 384
     SLOTS = 2
+    MAX_K = 32                   # the pruned protocol serves k <= k' <= 32
 
     def __init__(self, n_queries: int, d: int, device: torch.device, group=None):
         self.group = group
@@ -112,7 +115,14 @@ class PeerQueryExchange:
         self.pt_blk = self.ql * self.d * 4
         self.op_bytes, self.pt_bytes = rnd(self.world * self.op_blk), rnd(self.world * self.pt_blk)
         self.slot_bytes = self.op_bytes + self.pt_bytes
-        self.nbytes = self.FLAGS_BYTES + self.SLOTS * self.slot_bytes
+        # receive regions of the routed exchanges (single-buffered: everything behind the operand wait of step i+1
+        # on a peer is behind the end of step i here)
+        rows = self.world * self.ql
+        self.off_sel = self.FLAGS_BYTES + self.SLOTS * self.slot_bytes      # [W,Ql,k'] fp32 surrogates per shard
+        self.off_thr = self.off_sel + rnd(rows * self.MAX_K * 4)           # [W*Ql] fp32 global k'-th best surrogate
+        self.off_ls = self.off_thr + rnd(rows * 4)                         # [W,Ql,k] fp32 per-shard result lists
+        self.off_li = self.off_ls + rnd(rows * self.MAX_K * 4)             # [W,Ql,k] int64
+        self.nbytes = self.off_li + rnd(rows * self.MAX_K * 8)
         lib = _lib.load()
         handle = (ctypes.c_ubyte * 64)()
         base = ctypes.c_void_p()
@@ -166,6 +176,10 @@ class PeerQueryExchange:
             self.pt_all.append(raw[o:o + self.world * self.pt_blk].view(torch.float32).view(self.world * self.ql,
                                                                                             self.d))
         self.err = raw[128:132].view(torch.int32)
+        self.route = _lib.PeerRoute()
+        self.route.n_ranks, self.route.me, self.route.ql = self.world, self.rank, self.ql
+        for r in range(self.world):
+            self.route.base[r] = self.peer_base[r]
         self.side = torch.cuda.Stream(device=self.device)
         self.projected = torch.cuda.Event()
         self.copied = [torch.cuda.Event() for _ in range(self.SLOTS)]
@@ -233,6 +247,65 @@ class PeerQueryExchange:
             _lib.check(_lib.load().hypret_peer_wait(ctypes.c_void_p(self.base + 64), self.world, self.step,
                                                     ctypes.c_void_p(self.base + 128),
                                                     ctypes.c_void_p(cur.cuda_stream)))
+
+    # ---- the exchanges behind the scoring kernel, fused into the kernels that produce the data --------------
+    def _region(self, off: int, width: int, dtype) -> torch.Tensor:
+        n = self.world * self.ql * width * torch.empty((), dtype=dtype).element_size()
+        return self._raw[off:off + n].view(dtype).view(self.world, self.ql, width)
+
+    def _signal(self, flag_off: int):
+        cur = ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+        flags = self._arr(*[self.peer_base[r] + flag_off + 4 * self.rank for r in range(self.world)])
+        _lib.check(_lib.load().hypret_peer_signal(flags, self.world, self.step, cur))
+
+    def _wait(self, flag_off: int):
+        cur = ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+        _lib.check(_lib.load().hypret_peer_wait(ctypes.c_void_p(self.base + flag_off), self.world, self.step,
+                                                ctypes.c_void_p(self.base + self.F_ERR), cur))
+
+    def select_and_send(self, cand_score, cand_idx, list_count):
+        """``ops.cand_select`` whose kernel also stores every query's ``[k']`` surrogates into the receive region of
+        the query's owner (the all_to_all).  Returns the local ``(sel_score [W*Ql,k'], sel_idx)``; behind this call
+        the region ``[W,Ql,k']`` of this rank holds every shard's list of its own queries."""
+        Q, S, kp = cand_score.shape
+        if kp > self.MAX_K or Q != self.world * self.ql:
+            raise ValueError("select_and_send: shape does not match the exchange")
+        ss = torch.empty(Q, kp, dtype=torch.float32, device=self.device)
+        si = torch.empty(Q, kp, dtype=torch.int32, device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.load().hypret_cand_select_route(
+                ops._ptr(cand_score.contiguous()), ops._ptr(cand_idx.contiguous()), ops._ptr(list_count), Q, S, kp,
+                ops._ptr(ss), ops._ptr(si), ctypes.byref(self.route), self.off_sel, ops._stream()))
+            self._signal(self.F_SEL)
+            self._wait(self.F_SEL)
+        return ss, si, self._region(self.off_sel, kp, torch.float32)
+
+    def threshold_to_all(self, recv: torch.Tensor, kth: int) -> torch.Tensor:
+        """``ops.kth_smallest`` over the received lists of this rank's queries, stored into EVERY rank's threshold
+        region (the all_gather).  Returns this rank's ``[W*Ql]`` region, complete behind this call."""
+        W, Ql, m = recv.shape
+        own = torch.empty(Ql, dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.load().hypret_kth_smallest_route(ops._ptr(recv), W, Ql, m, int(kth), ops._ptr(own),
+                                                             ctypes.byref(self.route), self.off_thr, ops._stream()))
+            self._signal(self.F_THR)
+            self._wait(self.F_THR)
+        return self._region(self.off_thr, 1, torch.float32).view(self.world * self.ql)
+
+    def rerank_to_owners(self, local: GalleryIndex, q32, sel_s, sel_i, k: int, thr_all):
+        """Pruned exact rerank whose ``[k]`` result lists go straight into the query owners' receive regions (the
+        two all_to_alls).  Returns ``(scores [W,Ql,k], idx [W,Ql,k])`` of this rank's own queries."""
+        Q, kp = sel_s.shape
+        if k > self.MAX_K or kp > self.MAX_K:
+            raise ValueError("rerank_to_owners serves k <= k' <= 32")
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.load().hypret_rerank_pruned_route(
+                ops._ptr(q32), ops._ptr(local.rows32), Q, local.n, local.d, float(local.c), ops.METRIC[local.metric],
+                ops._ptr(sel_s), ops._ptr(sel_i), 1, kp, int(k), int(local.idx_offset), ops._ptr(thr_all),
+                ctypes.byref(self.route), self.off_ls, self.off_li, ops._stream()))
+            self._signal(self.F_LST)
+            self._wait(self.F_LST)
+        return self._region(self.off_ls, k, torch.float32), self._region(self.off_li, k, torch.int64)
 
     def check(self):
         """Synchronise and raise if a wait ran into its 20 s bound (a peer died or fell out of step)."""
@@ -356,6 +429,15 @@ class ShardedGalleryIndex:
             q_all = gather_queries(q_local, self.group)
             q32, cs, ci, cnt = self.local.score_candidates(q_all, k=k, kprime=kprime, kernel_events=kernel_events)
         thr_all = None
+        if prune and ex is not None and os.environ.get("HYPRET_PEER_ROUTE", "1") != "0":
+            # every exchange is done by the kernel that produces the data (NVLink stores into the receivers'
+            # regions + stream-ordered counters): no NCCL call on the data path of a step
+            sel_s, sel_i, recv = ex.select_and_send(cs, ci, cnt)
+            thr_all = ex.threshold_to_all(recv, kp)
+            ex.wait_points()
+            with _span(kernel_events, "rerank"):
+                rs, ri = ex.rerank_to_owners(self.local, q32, sel_s, sel_i, k, thr_all)
+            return ops.merge_topk(rs, ri, descending=(self.metric == "cosine"))
         if prune:
             sel_s, sel_i = ops.cand_select(cs, ci, cnt)                              # [W*Ql, k']
             recv = torch.empty_like(sel_s)

@@ -51,6 +51,11 @@ for metric in ("hyperbolic", "cosine"):
         assert torch.equal(i4, i5) and torch.equal(d4, d5), metric + " peer vs nccl"
         assert torch.equal(i4, i6) and torch.equal(d4, d6), metric + " peer vs single"
     assert nccl._exchange is None
+    # peer-memory query exchange + NCCL for the rest of the protocol
+    os.environ["HYPRET_PEER_ROUTE"] = "0"
+    d7, i7 = shd.search(q_step, k=k)
+    del os.environ["HYPRET_PEER_ROUTE"]
+    assert torch.equal(i7, i6) and torch.equal(d7, d6), metric + " peer queries + nccl lists"
     shd._exchange.check()
     shd._exchange.close()
 # collective 2: exact full-ranking AP from all-reduced keys / rank counts == the unsharded computation

@@ -100,3 +100,58 @@ def test_pruned_shard_protocol_on_one_gpu_equals_single_index(metric, W):
                                   descending=(metric == "cosine"))
     assert torch.equal(got_i, want_i) and torch.equal(got_d, want_d)
     assert n_rescored <= Q * kp * 1.05                 # the shards together rescore ~k' rows per query, not W*k'
+
+
+def test_routed_kernels_store_what_the_collectives_would_deliver():
+    """hypret_{cand_select,kth_smallest,rerank_pruned}_route with a 3-"rank" route whose receive buffers all live on
+    this GPU: every routed row must land where an all_to_all / all_gather of equal blocks would put it
+    (row me*Ql + q % Ql of the owner q // Ql), with the values of the unrouted kernels."""
+    import ctypes
+    from patent_image_retrieval_b200 import _lib
+    lib = _lib.load()
+    W, me, Ql, N, D, kp, k = 3, 1, 70, 4000, 128, 16, 10
+    Q = W * Ql
+    index = GalleryIndex(synth.gaussian_features(N, D, seed=0).cuda())
+    q32, cs, ci, cnt = index.score_candidates(synth.gaussian_features(Q, D, seed=1).cuda(), k=k, kprime=kp)
+    sel_s, sel_i = ops.cand_select(cs, ci, cnt)
+    off_sel, off_thr, off_ls, off_li = 0, 1 << 16, 1 << 17, 1 << 18
+    bufs = [torch.full((1 << 19,), 255, dtype=torch.uint8, device="cuda") for _ in range(W)]
+    route = _lib.PeerRoute()
+    route.n_ranks, route.me, route.ql = W, me, Ql
+    for r in range(W):
+        route.base[r] = bufs[r].data_ptr()
+    stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    ptr = lambda t: ctypes.c_void_p(t.data_ptr())
+    region = lambda r, off, width, dt: bufs[r][off:off + Q * width * torch.empty((), dtype=dt).element_size()].view(dt).view(W, Ql, width)
+
+    ss, si = torch.empty_like(sel_s), torch.empty_like(sel_i)
+    _lib.check(lib.hypret_cand_select_route(ptr(cs), ptr(ci), ptr(cnt), Q, cs.shape[1], kp, ptr(ss), ptr(si),
+                                            ctypes.byref(route), off_sel, stream))
+    torch.cuda.synchronize()
+    assert torch.equal(ss, sel_s) and torch.equal(si, sel_i)
+    for r in range(W):
+        assert torch.equal(region(r, off_sel, kp, torch.float32)[me], sel_s[r * Ql:(r + 1) * Ql])
+
+    recv = torch.rand(W, Ql, kp, device="cuda")
+    want = ops.kth_smallest(recv, kp)
+    own = torch.empty(Ql, device="cuda")
+    _lib.check(lib.hypret_kth_smallest_route(ptr(recv), W, Ql, kp, kp, ptr(own), ctypes.byref(route), off_thr, stream))
+    torch.cuda.synchronize()
+    assert torch.equal(own, want)
+    for r in range(W):
+        assert torch.equal(region(r, off_thr, 1, torch.float32).view(W, Ql)[me], want)
+
+    thr = sel_s[:, 5].contiguous()
+    d_w, i_w = index.rerank_candidates(q32, sel_s.unsqueeze(1), sel_i.unsqueeze(1), k, prune_thr=thr)
+    _lib.check(lib.hypret_rerank_pruned_route(ptr(q32), ptr(index.rows32), Q, N, D, 1.0, ops.METRIC["hyperbolic"],
+                                              ptr(sel_s), ptr(sel_i), 1, kp, k, 0, ptr(thr), ctypes.byref(route),
+                                              off_ls, off_li, stream))
+    torch.cuda.synchronize()
+    for r in range(W):
+        assert torch.equal(region(r, off_ls, k, torch.float32)[me], d_w[r * Ql:(r + 1) * Ql])
+        assert torch.equal(region(r, off_li, k, torch.int64)[me], i_w[r * Ql:(r + 1) * Ql])
+        other = [b for b in range(W) if b != me]
+        assert bool((bufs[r][off_ls:off_ls + Q * k * 4].view(W, -1)[other] == 255).all())     # only block `me` written
+    # argument checks: Q must match the route
+    assert lib.hypret_cand_select_route(ptr(cs), ptr(ci), ptr(cnt), Q - 1, cs.shape[1], kp, ptr(ss), ptr(si),
+                                        ctypes.byref(route), off_sel, stream) == -1
