@@ -261,14 +261,16 @@ int hypret_pairdist_bwd(const float* grad_out, const float* dmat, const float* a
  *   mean_i(row_lse_i - sim_ii) (+ mean_j(col_lse_j - sim_jj), halved) -- O(n) work left to the caller.
  * hypret_pairdist_ce_bwd: like hypret_pairdist_bwd, but the upstream gradient is formed on the fly:
  *   g_ij = -(gs * inv_tau / n) [ w_rows (exp(sim_ij - row_lse_i) - [i==j]) + w_cols (exp(sim_ij - col_lse_j) - [i==j]) ]
- *   with gs = *grad_scale (device scalar, NULL = 1).  col_partial [ceil(n/16), m]; row_partial [n_row_partial, n] as above. */
+ *   with gs = *grad_scale (device scalar, NULL = 1).  col_partial [ceil(n/16), m]; row_partial [n_row_partial, n] as above.
+ *   Row block of a larger batch (negatives sharded across ranks): the target of row i is column i + diag_offset and
+ *   the loss is a mean over n_total >= n rows (single process: diag_offset = 0, n_total = n). */
 int hypret_pairdist_ce_fwd(const float* a, const float* p, int64_t n, int64_t m, int d, float c, float inv_tau,
                            int want_col_lse, float* dmat, float* row_lse, float* col_lse, float* scratch,
                            int n_part, void* stream);
 int hypret_pairdist_ce_bwd(const float* dmat, const float* asq, const float* psq, int64_t n, int64_t m, float c,
                            const float* row_lse, const float* col_lse, float inv_tau, float w_rows, float w_cols,
                            const float* grad_scale, void* w_out, int w_format, float* row_partial, int n_row_partial,
-                           float* col_partial, void* stream);
+                           float* col_partial, int64_t diag_offset, int64_t n_total, void* stream);
 
 /* The same n x m distance matrix on the TENSOR CORES (training path, csrc/gramdist.cu): one tcgen05 GEMM over
  * operands that carry a 3-way bf16 split of the fp32 rows along K (six cross products = the fp32 inner product),

@@ -91,7 +91,7 @@ SIGNATURES = {
                                        c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
     "hypret_pairdist_ce_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_float, c_void_p, c_void_p,
                                        c_float, c_float, c_float, c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p,
-                                       c_void_p]),
+                                       c_int64, c_int64, c_void_p]),
     "hypret_gram_kpad": (c_int64, [c_int]),
     "hypret_gram_split": (c_int, [c_void_p, c_int64, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "hypret_gram_dist": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int,

@@ -335,9 +335,9 @@ int hypret_neg_lse(const float* dmat, int64_t n, int64_t m, float inv_tau, int w
 int hypret_pairdist_ce_bwd(const float* dmat, const float* asq, const float* psq, int64_t n, int64_t m, float c,
                            const float* row_lse, const float* col_lse, float inv_tau, float w_rows, float w_cols,
                            const float* grad_scale, void* w_out, int w_format, float* row_partial, int n_row_partial,
-                           float* col_partial, void* stream) {
+                           float* col_partial, int64_t diag_offset, int64_t n_total, void* stream) {
   if (n < 0 || m < 0 || !(c > 0.f) || !(inv_tau > 0.f) || (w_format != 0 && w_format != 1) || n_row_partial < 1 ||
-      n_row_partial > 65535)
+      n_row_partial > 65535 || diag_offset < 0 || n_total < n)
     return HYPRET_EINVAL;
   if (n == 0 || m == 0) return HYPRET_OK;
   if (dmat == nullptr || asq == nullptr || psq == nullptr || row_lse == nullptr || w_out == nullptr ||
@@ -346,7 +346,7 @@ int hypret_pairdist_ce_bwd(const float* dmat, const float* asq, const float* psq
   int rc = check_device();
   if (rc != HYPRET_OK) return rc;
   return hypret_launch_pairdist_ce_bwd(dmat, asq, psq, n, m, c, row_lse, col_lse, inv_tau, w_rows, w_cols, grad_scale,
-                                       w_out, w_format, row_partial, n_row_partial, col_partial,
+                                       w_out, w_format, row_partial, n_row_partial, col_partial, diag_offset, n_total,
                                        static_cast<cudaStream_t>(stream));
 }
 

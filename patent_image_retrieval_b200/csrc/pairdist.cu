@@ -139,7 +139,8 @@ pairdist_bwd_fused_kernel(const float* __restrict__ g, const float* __restrict__
                           const float* __restrict__ psq, int64_t n, int64_t m, float c, const float* __restrict__ row_lse,
                           const float* __restrict__ col_lse, float inv_tau, float wr, float wc,
                           const float* __restrict__ grad_scale, void* __restrict__ w_out_raw,
-                          float* __restrict__ row_partial, float* __restrict__ col_partial) {
+                          float* __restrict__ row_partial, float* __restrict__ col_partial, int64_t diag_offset,
+                          int64_t n_total) {
   // grid (row blocks of BW_ROWS, column chunks): CTA (x, y) owns the column blocks [y * cb_per, (y+1) * cb_per)
   // of its rows, writes row y of row_partial (its rows) and row x of col_partial (its columns) -- one writer per
   // element, no atomics; the chunks make ~7 waves of CTAs out of the 512 row blocks of an 8192-row batch
@@ -155,7 +156,7 @@ pairdist_bwd_fused_kernel(const float* __restrict__ g, const float* __restrict__
   }
   __syncthreads();
   const float sc = sqrtf(c), four_sc = 4.0f * sc;
-  const float gsc = CE ? -(grad_scale != nullptr ? grad_scale[0] : 1.0f) * inv_tau / (float)n : 0.f;
+  const float gsc = CE ? -(grad_scale != nullptr ? grad_scale[0] : 1.0f) * inv_tau / (float)n_total : 0.f;
   float racc[BW_ROWS];
 #pragma unroll
   for (int r = 0; r < BW_ROWS; ++r) racc[r] = 0.f;
@@ -199,7 +200,7 @@ pairdist_bwd_fused_kernel(const float* __restrict__ g, const float* __restrict__
       float gg;
       if (CE) {
         const float sim = -dd * inv_tau;
-        const float diag = (i0 + r == j) ? 1.0f : 0.0f;
+        const float diag = (i0 + r + diag_offset == j) ? 1.0f : 0.0f;   // target column of row i
         gg = gsc * (wr * (__expf(sim - s_lse[r]) - diag) + wc * (__expf(sim - lse_c) - diag));
       } else {
         gg = gv[q];
@@ -319,11 +320,12 @@ int hypret_launch_pairdist_bwd(const float* g, const float* dmat, const float* a
   const dim3 grid((unsigned)((n + BW_ROWS - 1) / BW_ROWS), (unsigned)n_row_partial);
   if (w_format == 1)
     pairdist_bwd_fused_kernel<false, true><<<grid, 256, 0, stream>>>(g, dmat, asq, psq, n, m, c, nullptr, nullptr, 0.f,
-                                                                    0.f, 0.f, nullptr, w_out, row_partial, col_partial);
+                                                                    0.f, 0.f, nullptr, w_out, row_partial, col_partial,
+                                                                    0, n);
   else
     pairdist_bwd_fused_kernel<false, false><<<grid, 256, 0, stream>>>(g, dmat, asq, psq, n, m, c, nullptr, nullptr, 0.f,
                                                                      0.f, 0.f, nullptr, w_out, row_partial,
-                                                                     col_partial);
+                                                                     col_partial, 0, n);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return (int)e;
   if ((int64_t)n_partial > (int64_t)grid.x)    // partial rows no CTA writes must read as zero
@@ -366,17 +368,18 @@ int hypret_launch_neg_lse(const float* dmat, int64_t n, int64_t m, float inv_tau
 int hypret_launch_pairdist_ce_bwd(const float* dmat, const float* asq, const float* psq, int64_t n, int64_t m, float c,
                                   const float* row_lse, const float* col_lse, float inv_tau, float wr, float wc,
                                   const float* grad_scale, void* w_out, int w_format, float* row_partial,
-                                  int n_row_partial, float* col_partial, cudaStream_t stream) {
+                                  int n_row_partial, float* col_partial, int64_t diag_offset, int64_t n_total,
+                                  cudaStream_t stream) {
   if (n == 0 || m == 0) return HYPRET_OK;
   const dim3 grid((unsigned)((n + BW_ROWS - 1) / BW_ROWS), (unsigned)n_row_partial);
   if (w_format == 1)
     pairdist_bwd_fused_kernel<true, true><<<grid, 256, 0, stream>>>(nullptr, dmat, asq, psq, n, m, c, row_lse, col_lse,
                                                                    inv_tau, wr, wc, grad_scale, w_out, row_partial,
-                                                                   col_partial);
+                                                                   col_partial, diag_offset, n_total);
   else
     pairdist_bwd_fused_kernel<true, false><<<grid, 256, 0, stream>>>(nullptr, dmat, asq, psq, n, m, c, row_lse, col_lse,
                                                                     inv_tau, wr, wc, grad_scale, w_out, row_partial,
-                                                                    col_partial);
+                                                                    col_partial, diag_offset, n_total);
   return (int)cudaGetLastError();
 }
 

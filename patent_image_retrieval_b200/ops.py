@@ -403,10 +403,13 @@ def _w_buffer(n: int, m: int, split: bool, device):
 
 def pairdist_ce_bwd(dmat: torch.Tensor, asq: torch.Tensor, psq: torch.Tensor, c: float, row_lse: torch.Tensor,
                     col_lse: Optional[torch.Tensor], inv_tau: float, w_rows: float, w_cols: float,
-                    grad_scale: Optional[torch.Tensor] = None, split: bool = False):
+                    grad_scale: Optional[torch.Tensor] = None, split: bool = False, diag_offset: int = 0,
+                    n_total: Optional[int] = None):
     """Backward weights of the in-batch InfoNCE: ``(W, row_sum [n], col_sum [m])``; the upstream gradient is
     formed inside the kernel from the log-sum-exps (``grad_scale``: device scalar dL/dloss).  ``W`` is ``[n,m]``
-    fp32, or with ``split`` three bf16 planes ``[3,n,m]`` (hi + mid + lo = W) for ``split_products``."""
+    fp32, or with ``split`` three bf16 planes ``[3,n,m]`` (hi + mid + lo = W) for ``split_products``.
+    ``diag_offset`` / ``n_total``: this is the row block ``[diag_offset, diag_offset + n)`` of an ``n_total``-row
+    batch whose negatives are sharded across ranks (``train.ShardedInBatchInfoNCE``)."""
     _need_cuda(dmat, asq, psq, row_lse, col_lse, grad_scale)
     n, m = dmat.shape
     w = _w_buffer(n, m, split, dmat.device)
@@ -419,6 +422,7 @@ def pairdist_ce_bwd(dmat: torch.Tensor, asq: torch.Tensor, psq: torch.Tensor, c:
                                                       _ptr(psq.contiguous().float()), n, m, float(c), _ptr(row_lse),
                                                       _ptr(col_lse), float(inv_tau), float(w_rows), float(w_cols),
                                                       _ptr(gs), _ptr(w), int(split), _ptr(rp), n_rp, _ptr(cp),
+                                                      int(diag_offset), int(n if n_total is None else n_total),
                                                       _stream()))
     return w, rp.sum(dim=0), cp.sum(dim=0)
 

@@ -97,6 +97,68 @@ class InBatchInfoNCE(torch.autograd.Function):
         return da.to(ctx.in_dtypes[0]), dp.to(ctx.in_dtypes[1]), None, None, None
 
 
+class ShardedInBatchInfoNCE(torch.autograd.Function):
+    """``InBatchInfoNCE`` over a batch whose rows are sharded across the ranks of ``group`` (sharded negatives;
+    SURVEY 8e "next"): rank r holds anchors / positives ``[nl,D]`` = rows ``[r*nl, (r+1)*nl)`` of the global batch of
+    ``n = W*nl`` pairs.  Forward: all_gather the positives, this rank's ``[nl,n]`` row block of the distance matrix
+    (same kernels; the target of local row i is column ``r*nl + i``), row log-sum-exps local, column log-sum-exps
+    combined across ranks (all_gather of the per-rank partials), loss all-reduced: every rank returns the GLOBAL
+    mean.  Backward: dA is complete locally; the partial dP of all n positives is reduce-scattered to the owners.
+    Gradients are those of the global loss with respect to the local rows (no further averaging)."""
+
+    @staticmethod
+    def forward(ctx, a, p, c: float, temperature: float, symmetric: bool, group):
+        import torch.distributed as dist
+        a32, p32 = a.contiguous().float(), p.contiguous().float()
+        if a32.shape != p32.shape:
+            raise ValueError("anchors and positives must have the same shape")
+        world, rank = dist.get_world_size(group), dist.get_rank(group)
+        nl, d = a32.shape
+        n = world * nl
+        p_all = torch.empty(n, d, dtype=torch.float32, device=a32.device)
+        dist.all_gather_into_tensor(p_all, p32, group=group)
+        inv_tau = 1.0 / float(temperature)
+        dm, row_lse, col_part = ops.pairdist_ce_fwd(a32, p_all, c, inv_tau, want_cols=symmetric,
+                                                    tensor_cores=None if TENSOR_CORES else False)
+        off = rank * nl
+        diag_sim = -torch.diagonal(dm, offset=off) * inv_tau                    # sim[i, off + i]
+        local = (row_lse - diag_sim).sum()
+        col_lse = None
+        if symmetric:
+            parts = torch.empty(world, n, dtype=torch.float32, device=a32.device)
+            dist.all_gather_into_tensor(parts, col_part, group=group)
+            col_lse = torch.logsumexp(parts, dim=0)                             # over the row blocks of all ranks
+            local = (local + (col_lse[off:off + nl] - diag_sim).sum()) / 2
+        total = local.clone()
+        dist.all_reduce(total, op=dist.ReduceOp.SUM, group=group)
+        ctx.save_for_backward(a32, p_all, dm, row_lse, col_lse if symmetric else row_lse)
+        ctx.c, ctx.inv_tau, ctx.symmetric, ctx.group = c, inv_tau, symmetric, group
+        ctx.off, ctx.n, ctx.nl = off, n, nl
+        ctx.in_dtypes = (a.dtype, p.dtype)
+        return total / n
+
+    @staticmethod
+    def backward(ctx, grad_loss):
+        import torch.distributed as dist
+        a, p_all, dm, row_lse, col_lse = ctx.saved_tensors
+        wr, wc = (0.5, 0.5) if ctx.symmetric else (1.0, 0.0)
+        split = TENSOR_CORES and dm.numel() >= ops.SPLIT_MIN_PAIRS
+        w, rs, cs = ops.pairdist_ce_bwd(dm, ops.row_sqnorm(a), ops.row_sqnorm(p_all), ctx.c, row_lse,
+                                        col_lse if ctx.symmetric else None, ctx.inv_tau, wr, wc, grad_scale=grad_loss,
+                                        split=split, diag_offset=ctx.off, n_total=ctx.n)
+        wp, wta = ops.split_products(w, a, p_all) if split else (w @ p_all, w.t() @ a)
+        da = a * rs[:, None] - wp
+        dp_all = (p_all * cs[:, None] - wta).contiguous()                       # this rank's rows' share, all n positives
+        dp = torch.empty(ctx.nl, dp_all.shape[1], dtype=torch.float32, device=dp_all.device)
+        dist.reduce_scatter_tensor(dp, dp_all, op=dist.ReduceOp.SUM, group=ctx.group)
+        return da.to(ctx.in_dtypes[0]), dp.to(ctx.in_dtypes[1]), None, None, None, None
+
+
+def sharded_in_batch_contrastive_loss(anchors, positives, k, temperature=0.1, symmetric=False, group=None):
+    """The in-batch loss of src/train.py:1832-1844 (``symmetric``: 2304-2334) over a batch sharded across ranks."""
+    return ShardedInBatchInfoNCE.apply(anchors, positives, _c_of(k), float(temperature), bool(symmetric), group)
+
+
 def in_batch_contrastive_loss(anchors, positives, k, temperature=0.1):
     """The loss inside train_hyperbolic_contrastive (src/train.py:1832-1844): CE over rows."""
     return InBatchInfoNCE.apply(anchors, positives, _c_of(k), float(temperature), False)

@@ -73,6 +73,26 @@ for grouped in (True, False):
     want = ops.ap_from_counts(off, items, single_keys, c1, b1, N, grouped_ties=grouped)
     got = full_ranking_ap(qp, pts[lo:hi].contiguous(), off, items, row_offset=lo, n_total=N, grouped_ties=grouped)
     assert torch.equal(got[1], want[1]) and torch.equal(got[2], want[2]) and got[0] == want[0], "full_ranking_ap"
+# sharded negatives: the in-batch InfoNCE over a batch split across the ranks == the single-GPU loss / gradients
+from patent_image_retrieval_b200 import train
+from oracle import head
+nl, dd, cc, tau = 640, 64, 0.9, 0.2
+n_all = nl * world
+mu = synth.gaussian_features(n_all, dd, seed=21, scale=1.0)
+a_all = head.embed_rows(mu + 0.3 * synth.gaussian_features(n_all, dd, seed=22, scale=1.0), cc).to(dev)
+p_all = head.embed_rows(mu + 0.3 * synth.gaussian_features(n_all, dd, seed=23, scale=1.0), cc).to(dev)
+kk = torch.tensor([-cc])
+for sym in (False, True):
+    ag, pg = a_all.clone().requires_grad_(True), p_all.clone().requires_grad_(True)
+    ref = train.InBatchInfoNCE.apply(ag, pg, cc, tau, sym)
+    ref.backward()
+    al = a_all[rank * nl:(rank + 1) * nl].clone().requires_grad_(True)
+    pl = p_all[rank * nl:(rank + 1) * nl].clone().requires_grad_(True)
+    got = train.sharded_in_batch_contrastive_loss(al, pl, kk, tau, symmetric=sym)
+    got.backward()
+    assert abs(float(got) - float(ref)) <= 2e-6 * abs(float(ref)), ("sharded loss", float(got), float(ref))
+    for g_, w_ in ((al.grad, ag.grad[rank * nl:(rank + 1) * nl]), (pl.grad, pg.grad[rank * nl:(rank + 1) * nl])):
+        assert float((g_ - w_).abs().max() / w_.abs().max()) < 2e-5, "sharded grads"
 torch.cuda.synchronize()
 dist.barrier()
 dist.destroy_process_group()
