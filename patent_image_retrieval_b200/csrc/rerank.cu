@@ -286,13 +286,20 @@ __device__ __forceinline__ bool pair_less(float a, int ia, float b, int ib) {
   return (a < b) || (a == b && ia < ib);
 }
 
+// Two launches share the queries by candidate count (size_class): the lists a query actually has (list_count) are
+// far fewer than the slots the schedule reserves, so class 0 -- queries with at most RW_SMALL candidates -- runs with
+// 8 KB of dynamic shared memory and 4 resident CTAs per SM (ncu of the single-launch version: 64 KB of candidate
+// space per CTA and 168 registers held it at 3 CTAs = 12 warps per SM, DRAM at 17 % of peak: latency-bound), class 1
+// takes the rest with the full-size buffer.  A CTA whose query belongs to the other class exits at once.
+constexpr int RW_SMALL = 1024;
+
 template <int NV>
-__global__ void __launch_bounds__(RW_THREADS)
+__global__ void __launch_bounds__(RW_THREADS, NV <= 6 ? 4 : 1)
 rerank_wide_kernel(const float* __restrict__ q32, const float* __restrict__ g32, int64_t Q, int64_t N, int d, float c,
                    int metric, const float* __restrict__ cand_score, const int32_t* __restrict__ cand_idx,
                    const int32_t* __restrict__ list_count, int n_lists_alloc, int kprime, int n_pad, int k,
                    int64_t idx_offset, float* __restrict__ out_score,
-                   int64_t* __restrict__ out_idx, float* __restrict__ out_margin) {
+                   int64_t* __restrict__ out_idx, float* __restrict__ out_margin, int size_class) {
   extern __shared__ uint8_t smem_raw[];
   float* ks = reinterpret_cast<float*>(smem_raw);            // [n_pad] surrogate scores
   int* ki = reinterpret_cast<int*>(ks + n_pad);              // [n_pad] gallery ids
@@ -305,6 +312,7 @@ rerank_wide_kernel(const float* __restrict__ q32, const float* __restrict__ g32,
   const int n_lists = list_count != nullptr ? min(list_count[q], n_lists_alloc) : n_lists_alloc;   // compact slots
   const int n_cand = n_lists * kprime;
   const int64_t row_stride = (int64_t)n_lists_alloc * kprime;
+  if (size_class >= 0 && (n_cand <= RW_SMALL) != (size_class == 0)) return;       // the other launch's query
 
   __shared__ int n_valid_s;
   if (tid == 0) { hidden_key = 0xffffffffu; n_valid_s = 0; }
@@ -501,10 +509,16 @@ int hypret_launch_rerank(const float* q32, const float* g32, int64_t Q, int64_t 
                                            (int)smem_w);                                                            \
       if (e != cudaSuccess) return (int)e;                                                                          \
     }                                                                                                               \
-    rerank_wide_kernel<NV><<<(unsigned)Q, RW_THREADS, smem_w, stream>>>(q32, g32, Q, N, d, c, metric, cand_score,   \
-                                                                       cand_idx, list_count, n_lists, kprime,       \
-                                                                       n_pad, k, idx_offset, out_score, out_idx,    \
-                                                                       out_margin);                                 \
+    if (n_pad > RW_SMALL && list_count != nullptr) {                                                                \
+      rerank_wide_kernel<NV><<<(unsigned)Q, RW_THREADS, (size_t)RW_SMALL * 8, stream>>>(                            \
+          q32, g32, Q, N, d, c, metric, cand_score, cand_idx, list_count, n_lists, kprime, RW_SMALL, k, idx_offset, \
+          out_score, out_idx, out_margin, 0);                                                                       \
+      cudaError_t e0 = cudaGetLastError();                                                                          \
+      if (e0 != cudaSuccess) return (int)e0;                                                                        \
+    }                                                                                                               \
+    rerank_wide_kernel<NV><<<(unsigned)Q, RW_THREADS, smem_w, stream>>>(                                            \
+        q32, g32, Q, N, d, c, metric, cand_score, cand_idx, list_count, n_lists, kprime, n_pad, k, idx_offset,      \
+        out_score, out_idx, out_margin, (n_pad > RW_SMALL && list_count != nullptr) ? 1 : -1);                      \
     return (int)cudaGetLastError();                                                                                 \
   } while (0)
     if (need_w <= 1) HYPRET_RERANK_WIDE(1);
