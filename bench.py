@@ -378,6 +378,22 @@ def main():
                                 "sample": f"first {n_q} queries of the same workload against the full {N}-row "
                                           f"gallery (points pre-embedded), {secs:.1f} s",
                                 "topk_lists_identical_frac": same, "max_rel_dist_diff": rel}
+        # the two other CPU paths beside the faithful per-query loop -- (ii) a best-effort blocked
+        # closed-form arccosh + top-k, (iii) the notebook's cosine_similarity + argsort -- on 64 queries each
+        from oracle import head, retrieval
+        n_b = min(64, Q)
+        qb = head.embed_rows(q_host[:n_b], c)
+        t0 = time.perf_counter()
+        _, i_b = retrieval.hyperbolic_topk(qb, g_pts_cpu, c, k, form="arcosh")
+        t_b = time.perf_counter() - t0
+        g_raw = g_u.cpu().numpy()
+        t0 = time.perf_counter()
+        retrieval.cosine_topk(q_host[:n_b].numpy(), g_raw, k)
+        t_c = time.perf_counter() - t0
+        line["cpu_baseline"]["other_paths"] = {
+            "best_effort_blocked_arccosh": {"value": n_b / t_b, "unit": UNIT, "queries": n_b,
+                                            "topk_lists_identical_frac": float((i_b == ii[:n_b].cpu()).all(dim=1).float().mean())},
+            "cosine_similarity_argsort": {"value": n_b / t_c, "unit": UNIT, "queries": n_b}}
     emit(line)
     if world > 1:
         dist.barrier()

@@ -14,7 +14,7 @@
 // elsewhere the cancellation costs at most 1 / NEAR_FRAC ulps of fp32.
 // Structure = the single-CTA skeleton of score_topk.cu: persistent CTAs, warp 0 TMA producer (A' block 128 x 64 and
 // P' block 256 x 64 per stage, 128B swizzle, 4 stages), warp 1 MMA issuer (M=128, N=256, K=16 into one of two TMEM
-// accumulators), warps 2-5 epilogue (tcgen05.ld 32x32b: lane = row).  Tiles are walked column-major so that the
+// accumulators), warps 2-9 epilogue in two warpgroups (tcgen05.ld 32x32b: lane = row; odd / even column chunks).  Tiles are walked column-major so that the
 // CTAs running together share the P' tile; both operands (25 MB at n = 8192, D = 128) live in L2.
 #include <cuda.h>
 #include <math.h>
@@ -23,13 +23,16 @@
 
 namespace {
 
-constexpr int GT_M = 128, GT_N = 256, GT_ACC = 2, GT_STAGES = 4;
+constexpr int GT_M = 128, GT_N = 256, GT_ACC = 2, GT_STAGES = 3;
 constexpr int GA_BLK = GT_M * HYPRET_KBLK * 2;   // 16 KB
 constexpr int GB_BLK = GT_N * HYPRET_KBLK * 2;   // 32 KB
 constexpr int G_STAGE = GA_BLK + GB_BLK;
-constexpr int G_THREADS = 192;
+constexpr int G_THREADS = 320;     // warp 0 TMA, warp 1 MMA, warps 2-9 epilogue (two warpgroups)
+constexpr int G_EPI = G_THREADS - 64;
 constexpr float NEAR_FRAC = 0.25f;
-constexpr int G_SMEM = 1024 + GT_STAGES * G_STAGE + GT_ACC * GT_N * 4 + 256;
+constexpr int G_PITCH = 36;       // floats per staged row: 16-byte aligned, 128-bit accesses conflict-free
+constexpr int G_STAGING = 32 * G_PITCH * 4;                     // one 32 x 32 fp32 block per epilogue warp
+constexpr int G_SMEM = 1024 + GT_STAGES * G_STAGE + GT_ACC * GT_N * 4 + 256 + (G_THREADS / 32 - 2) * G_STAGING;
 
 __host__ __device__ inline int gram_kpad(int d) { return (6 * d + HYPRET_KBLK - 1) / HYPRET_KBLK * HYPRET_KBLK; }
 
@@ -96,6 +99,7 @@ gram_dist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   uint8_t* ring = smem;
   float* psq_s = reinterpret_cast<float*>(smem + GT_STAGES * G_STAGE);          // [GT_ACC][GT_N]
   GBarriers* bars = reinterpret_cast<GBarriers*>(smem + GT_STAGES * G_STAGE + GT_ACC * GT_N * 4);
+  float* staging = reinterpret_cast<float*>(smem + GT_STAGES * G_STAGE + GT_ACC * GT_N * 4 + 256);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_rt = (int)((n + GT_M - 1) / GT_M), n_ct = (int)((m + GT_N - 1) / GT_N);
   const int n_tiles = n_rt * n_ct;
@@ -106,7 +110,7 @@ gram_dist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < GT_STAGES; ++s) { mbar_init(&bars->full[s], 1); mbar_init(&bars->empty[s], 1); }
-    for (int a = 0; a < GT_ACC; ++a) { mbar_init(&bars->tmem_full[a], 1); mbar_init(&bars->tmem_empty[a], 128); }
+    for (int a = 0; a < GT_ACC; ++a) { mbar_init(&bars->tmem_full[a], 1); mbar_init(&bars->tmem_empty[a], G_EPI); }
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc(&bars->tmem_ptr, GT_ACC * GT_N);
@@ -162,7 +166,12 @@ gram_dist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     }
   } else {
     // ===================================================================== epilogue: Gram entry -> distance
-    const int quad = warp & 3, row = quad * 32 + lane, et = threadIdx.x - 64;     // et: 0..127
+    // two warpgroups share every accumulator: warpgroup g takes the odd / even 32-column chunks.  With one
+    // warpgroup each SM sub-partition held a single epilogue warp, whose dependent MUFU / FMA chains issue one
+    // instruction every few cycles (ncu: 0.24 ms per 8192 x 8192 matrix, tensor pipe 7 % active, 9 % of the warp
+    // slots in use); two warps per sub-partition hide each other's latencies
+    const int quad = warp & 3, row = quad * 32 + lane, et = threadIdx.x - 64;     // et: 0..G_EPI-1
+    const int wg = (warp - 2) >> 2;
     const float rs = 1.0f / sqrtf(c), two_c = 2.0f * c;
     uint32_t acc = 0, acc_phase = 0;
     for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
@@ -171,8 +180,8 @@ gram_dist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       const int64_t j0 = (int64_t)ct * GT_N;
       // this tile's column norms (the buffer of accumulator `acc` was last read two tiles ago)
       float* pq = psq_s + acc * GT_N;
-      for (int u = et; u < GT_N; u += 128) pq[u] = (j0 + u < m) ? psq[j0 + u] : 0.f;
-      asm volatile("bar.sync 1, 128;" ::: "memory");
+      for (int u = et; u < GT_N; u += G_EPI) pq[u] = (j0 + u < m) ? psq[j0 + u] : 0.f;
+      asm volatile("bar.sync 1, %0;" ::"n"(G_EPI) : "memory");
       const float na = i < n ? asq[i] : 0.f;
       const float al = 1.0f - c * na;
       mbar_wait(&bars->tmem_full[acc], acc_phase);
@@ -180,12 +189,12 @@ gram_dist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * GT_N;
       float v[32];
 #pragma unroll 1
-      for (int cc = 0; cc < GT_N / 32; ++cc) {
+      for (int cc = wg; cc < GT_N / 32; cc += 2) {
         __syncwarp();
         tmem_ld_32x32(taddr + cc * 32, v);
         tmem_ld_wait(v);
         const int64_t jb = j0 + cc * 32;
-        if (i < n && jb < m) {
+        if (jb < m) {        // warp-uniform; rows past n compute on zero-filled operands and are masked at the stores
           // main pass: no branches, the 32 entries are independent (their MUFU chains overlap); entries whose
           // |a|^2 + |p|^2 - 2<a,p> cancels are only flagged here and recomputed exactly below
           uint32_t near = 0;
@@ -196,21 +205,44 @@ gram_dist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             near |= (s < NEAR_FRAC * (na + nb) ? 1u : 0u) << j;
             v[j] = dist_from_sq(s, al, 1.0f - c * nb, two_c, rs);
           }
+          if (i >= n) near = 0u;
           float* o = out + i * m + jb;
           if (jb + 32 <= m && (m & 3) == 0) {
+            // lane = row here, so a direct float4 store touches 32 different lines per instruction (ncu: the
+            // warps sat behind the store queue, 14 % of all stall samples on the first instruction that reuses a
+            // store's data register).  The 32 x 32 block goes through a per-warp staging buffer instead and leaves
+            // as 8 stores of 4 full 128-byte lines each.
+            float* st = staging + (warp - 2) * (32 * G_PITCH);
 #pragma unroll
-            for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(o + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-          } else {
+            for (int j = 0; j < 32; j += 4)
+              *reinterpret_cast<float4*>(st + lane * G_PITCH + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+            while (near != 0u) {                  // rare: the diagonal of a contrastive batch, duplicates
+              const int j = __ffs((int)near) - 1;
+              near &= near - 1u;
+              const float s = exact_sqdist(a32 + i * d, p32 + (jb + j) * d, d);
+              st[lane * G_PITCH + j] = dist_from_sq(s, al, 1.0f - c * pq[cc * 32 + j], two_c, rs);
+            }
+            __syncwarp();
+            const int64_t r_base = (int64_t)rt * GT_M + quad * 32;
+            const int sub = lane >> 3, col = (lane & 7) * 4;
+#pragma unroll
+            for (int it = 0; it < 8; ++it) {
+              const int r = it * 4 + sub;
+              const float4 x = *reinterpret_cast<const float4*>(st + r * G_PITCH + col);
+              if (r_base + r < n) *reinterpret_cast<float4*>(out + (r_base + r) * m + jb + col) = x;
+            }
+            __syncwarp();                         // the buffer is rewritten by the next chunk
+          } else if (i < n) {
 #pragma unroll
             for (int j = 0; j < 32; ++j)
               if (jb + j < m) o[j] = v[j];
-          }
-          while (near != 0u) {                    // rare: the diagonal of a contrastive batch, duplicates
-            const int j = __ffs((int)near) - 1;
-            near &= near - 1u;
-            if (jb + j < m) {
-              const float s = exact_sqdist(a32 + i * d, p32 + (jb + j) * d, d);
-              o[j] = dist_from_sq(s, al, 1.0f - c * pq[cc * 32 + j], two_c, rs);
+            while (near != 0u) {
+              const int j = __ffs((int)near) - 1;
+              near &= near - 1u;
+              if (jb + j < m) {
+                const float s = exact_sqdist(a32 + i * d, p32 + (jb + j) * d, d);
+                o[j] = dist_from_sq(s, al, 1.0f - c * pq[cc * 32 + j], two_c, rs);
+              }
             }
           }
         }
