@@ -194,9 +194,62 @@ gram_dist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         tmem_ld_32x32(taddr + cc * 32, v);
         tmem_ld_wait(v);
         const int64_t jb = j0 + cc * 32;
-        if (jb < m) {        // warp-uniform; rows past n compute on zero-filled operands and are masked at the stores
-          // main pass: no branches, the 32 entries are independent (their MUFU chains overlap); entries whose
-          // |a|^2 + |p|^2 - 2<a,p> cancels are only flagged here and recomputed exactly below
+        if (jb + 32 <= m && (m & 3) == 0) {        // warp-uniform: a full chunk of an aligned matrix
+          // Rows past n compute on zero-filled operands and are masked at the stores.  Main pass: no branches, the
+          // 32 entries are independent (their MUFU chains overlap), log(1 + x) from the fast lg2 (absolute error
+          // 2^-21.4: below 1e-6 relative once x > 0.5).  Two kinds of entries are only flagged here and redone below:
+          // near pairs, whose |a|^2 + |p|^2 - 2<a,p> cancels (exact differences from the fp32 rows), and entries
+          // with x <= 0.5, i.e. d sqrt(c) < 0.41 (accurate log1pf on the value already at hand).
+          // lane = row, so a direct float4 store would touch 32 different lines per instruction (ncu: the warps
+          // sat behind the store queue, 14 % of all stall samples on the first instruction that reuses a store's
+          // data register): the 32 x 32 block goes through a per-warp staging buffer and leaves as 8 stores of 4
+          // full 128-byte lines each.
+          float* st = staging + (warp - 2) * (32 * G_PITCH);
+          uint32_t near = 0, slow = 0;
+#pragma unroll
+          for (int j4 = 0; j4 < 32; j4 += 4) {
+            float r[4];
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj) {
+              const int j = j4 + jj;
+              const float nb = pq[cc * 32 + j];
+              const float s = fmaxf(na + nb - 2.0f * v[j], 0.f);
+              near |= (s < NEAR_FRAC * (na + nb) ? 1u : 0u) << j;
+              const float tt = __fdividef(two_c * s, al * (1.0f - c * nb));
+              const float t2 = fmaxf(tt * (tt + 2.0f), 1e-37f);
+              const float x = tt + t2 * rsqrtf(t2);
+              slow |= (x <= 0.5f ? 1u : 0u) << j;
+              r[jj] = __logf(1.0f + x) * rs;
+            }
+            *reinterpret_cast<float4*>(st + lane * G_PITCH + j4) = make_float4(r[0], r[1], r[2], r[3]);
+          }
+          if (i >= n) near = slow = 0u;
+          slow &= ~near;
+          if (slow != 0u) {                       // close pairs that do not cancel: same s, accurate logarithm
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if ((slow >> j) & 1u) {
+                const float nb = pq[cc * 32 + j];
+                st[lane * G_PITCH + j] = dist_from_sq(fmaxf(na + nb - 2.0f * v[j], 0.f), al, 1.0f - c * nb, two_c, rs);
+              }
+          }
+          while (near != 0u) {                    // rare: the diagonal of a contrastive batch, duplicates
+            const int j = __ffs((int)near) - 1;
+            near &= near - 1u;
+            const float s = exact_sqdist(a32 + i * d, p32 + (jb + j) * d, d);
+            st[lane * G_PITCH + j] = dist_from_sq(s, al, 1.0f - c * pq[cc * 32 + j], two_c, rs);
+          }
+          __syncwarp();
+          const int64_t r_base = (int64_t)rt * GT_M + quad * 32;
+          const int sub = lane >> 3, col = (lane & 7) * 4;
+#pragma unroll
+          for (int it = 0; it < 8; ++it) {
+            const int r = it * 4 + sub;
+            const float4 x = *reinterpret_cast<const float4*>(st + r * G_PITCH + col);
+            if (r_base + r < n) *reinterpret_cast<float4*>(out + (r_base + r) * m + jb + col) = x;
+          }
+          __syncwarp();                           // the buffer is rewritten by the next chunk
+        } else if (jb < m && i < n) {             // ragged edge / unaligned matrix: accurate path, direct stores
           uint32_t near = 0;
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
@@ -205,44 +258,16 @@ gram_dist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             near |= (s < NEAR_FRAC * (na + nb) ? 1u : 0u) << j;
             v[j] = dist_from_sq(s, al, 1.0f - c * nb, two_c, rs);
           }
-          if (i >= n) near = 0u;
           float* o = out + i * m + jb;
-          if (jb + 32 <= m && (m & 3) == 0) {
-            // lane = row here, so a direct float4 store touches 32 different lines per instruction (ncu: the
-            // warps sat behind the store queue, 14 % of all stall samples on the first instruction that reuses a
-            // store's data register).  The 32 x 32 block goes through a per-warp staging buffer instead and leaves
-            // as 8 stores of 4 full 128-byte lines each.
-            float* st = staging + (warp - 2) * (32 * G_PITCH);
 #pragma unroll
-            for (int j = 0; j < 32; j += 4)
-              *reinterpret_cast<float4*>(st + lane * G_PITCH + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-            while (near != 0u) {                  // rare: the diagonal of a contrastive batch, duplicates
-              const int j = __ffs((int)near) - 1;
-              near &= near - 1u;
+          for (int j = 0; j < 32; ++j)
+            if (jb + j < m) o[j] = v[j];
+          while (near != 0u) {
+            const int j = __ffs((int)near) - 1;
+            near &= near - 1u;
+            if (jb + j < m) {
               const float s = exact_sqdist(a32 + i * d, p32 + (jb + j) * d, d);
-              st[lane * G_PITCH + j] = dist_from_sq(s, al, 1.0f - c * pq[cc * 32 + j], two_c, rs);
-            }
-            __syncwarp();
-            const int64_t r_base = (int64_t)rt * GT_M + quad * 32;
-            const int sub = lane >> 3, col = (lane & 7) * 4;
-#pragma unroll
-            for (int it = 0; it < 8; ++it) {
-              const int r = it * 4 + sub;
-              const float4 x = *reinterpret_cast<const float4*>(st + r * G_PITCH + col);
-              if (r_base + r < n) *reinterpret_cast<float4*>(out + (r_base + r) * m + jb + col) = x;
-            }
-            __syncwarp();                         // the buffer is rewritten by the next chunk
-          } else if (i < n) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (jb + j < m) o[j] = v[j];
-            while (near != 0u) {
-              const int j = __ffs((int)near) - 1;
-              near &= near - 1u;
-              if (jb + j < m) {
-                const float s = exact_sqdist(a32 + i * d, p32 + (jb + j) * d, d);
-                o[j] = dist_from_sq(s, al, 1.0f - c * pq[cc * 32 + j], two_c, rs);
-              }
+              o[j] = dist_from_sq(s, al, 1.0f - c * pq[cc * 32 + j], two_c, rs);
             }
           }
         }

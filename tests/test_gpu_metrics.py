@@ -253,13 +253,16 @@ def test_fused_head_large_and_clipped_rows():
     assert float(got.norm(dim=1).max()) <= (1 - 4e-3) / c ** 0.5 * (1 + 1e-6)
 
 
-@pytest.mark.parametrize("n,m,d,c", [(300, 520, 128, 1.0), (129, 257, 256, 0.5), (64, 64, 20, 2.0), (1000, 700, 512, 1.0)])
-def test_tensor_core_distance_matrix_matches_oracle(n, m, d, c):
+@pytest.mark.parametrize("n,m,d,c,scale", [(300, 520, 128, 1.0, 1.0), (129, 257, 256, 0.5, 1.0), (64, 64, 20, 2.0, 1.0),
+                                           (1000, 700, 512, 1.0, 1.0), (260, 512, 128, 1.0, 0.15),
+                                           (200, 384, 64, 0.7, 0.03), (150, 256, 128, 1.0, 0.3)])
+def test_tensor_core_distance_matrix_matches_oracle(n, m, d, c, scale):
     """csrc/gramdist.cu (3-way bf16 split Gram matrix on tcgen05 + exact recompute of near pairs) against the fp64
-    oracle and the exact CUDA-core kernel, including near duplicates and ragged tiles."""
+    oracle and the exact CUDA-core kernel, including near duplicates and ragged tiles.  The small scales put the
+    distances below / around d sqrt(c) = 0.41, where the epilogue swaps its fast lg2 for the accurate log1pf."""
     from oracle import head
-    a = head.embed_rows(synth.gaussian_features(n, d, seed=1, scale=1.0), c)
-    p = head.embed_rows(synth.gaussian_features(m, d, seed=0, scale=1.0), c)
+    a = head.embed_rows(synth.gaussian_features(n, d, seed=1, scale=1.0) * scale, c)
+    p = head.embed_rows(synth.gaussian_features(m, d, seed=0, scale=1.0) * scale, c)
     p[:5] = a[:5] * (1 + 1e-4)                                   # near duplicates: the cancellation case
     p[5:9] = a[5:9] * 0.9
     got, asq, psq = ops.gram_dist(a.cuda(), p.cuda(), c)
