@@ -281,6 +281,10 @@ int hypret_pairdist_ce_bwd(const float* dmat, const float* asq, const float* psq
  *   hypret_gram_dist      out [n,m] fp32 from the two operands, the fp32 rows and the squared norms
  *   hypret_neg_lse        row / column log-sum-exps of -dmat * inv_tau (the second half of hypret_pairdist_ce_fwd) */
 int64_t hypret_gram_kpad(int d);
+/* x [count] fp32 -> out [3, count] bf16 planes (hi, mid, lo; hi + mid + lo = x to fp32 accuracy): the W format
+ * (w_format 1) of the two functions above, cut from an fp32 W in one streaming pass -- faster than emitting the
+ * planes from inside the backward pass.  count % 4 == 0. */
+int hypret_split3(const float* x, int64_t count, void* out_bf16, void* stream);
 int hypret_gram_split(const float* x, int64_t n, int d, int side, void* out_bf16, float* sqnorm, void* stream);
 int hypret_gram_dist(const void* a_op, const void* p_op, const float* a32, const float* p32, const float* asq,
                      const float* psq, int64_t n, int64_t m, int d, float c, float* out, void* stream);

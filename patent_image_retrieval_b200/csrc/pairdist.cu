@@ -127,6 +127,24 @@ pairdist_kernel(const float* __restrict__ a, const float* __restrict__ p, int64_
 // sim = -D / tau (the in-batch InfoNCE losses of src/train.py:1832-1844 and 2304-2334):
 //   g_ij = -(gs / tau / n) * [ wr (exp(sim_ij - lse_r[i]) - [i==j]) + wc (exp(sim_ij - lse_c[j]) - [i==j]) ].
 // The two dense products W P and W^T A are left to the caller (plain GEMMs).
+// MUFU approximations with flush-to-zero (1-2 ulp): the IEEE-rounded __frcp_rn and the denormal handling of __expf
+// cost ~10 instructions and a branch each in a kernel that is bound by its instruction count
+__device__ __forceinline__ float fast_exp(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x * 1.4426950408889634f));
+  return y;
+}
+__device__ __forceinline__ float fast_rcp(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float fast_rsq(float x) {
+  float y;
+  asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 constexpr int BW_ROWS = 16;     // = HYPRET_BWD_ROWS: with 32 the row accumulators spilled under the 128-register cap
 static_assert(BW_ROWS == HYPRET_BWD_ROWS, "include/hypret.h documents the row-block size");
 constexpr int BW_BATCH = 16;   // rows loaded (all loads issued) before the first use
@@ -179,18 +197,24 @@ pairdist_bwd_fused_kernel(const float* __restrict__ g, const float* __restrict__
     // all 32 loads of the block are issued before the first use (the per-element version, with its branches, did
     // one dependent HBM round trip per element: 1.34 ms for 0.5 GB of traffic); out-of-range rows / columns read
     // a clamped address and are masked at the stores and sums
-    const unsigned jcu = (unsigned)(jok ? j : m - 1), ju = (unsigned)j;
+    // addresses: one per-thread pointer per stream, walked down the rows by the (CTA-uniform) pitch -- the
+    // per-element 64-bit index arithmetic was 43 of the 156 instructions per element (ncu source page)
+    const int64_t jc = jok ? j : m - 1;
+    const float* dcur = dmat + i0 * m + jc;
+    const float* gcur = CE ? nullptr : g + i0 * m + jc;
+    char* wcur = static_cast<char*>(w_out_raw) + (i0 * m + j) * (SPLIT ? 2 : 4);
+    const int64_t w_pitch = m * (SPLIT ? 2 : 4), plane_bytes = n * m * 2;
 #pragma unroll
     for (int rb = 0; rb < BW_ROWS; rb += BW_BATCH) {
     float dv[BW_BATCH], gv[BW_BATCH];
 #pragma unroll
     for (int q = 0; q < BW_BATCH; ++q) {
       const int r = rb + q;
-      // CTA-uniform 64-bit row base + one 32-bit per-thread column offset: per-row 64-bit addresses held live
-      // across the unrolled batch were what spilled
-      const int64_t ro = (i0 + (r < rows ? r : rows - 1)) * m;
-      dv[q] = (dmat + ro)[jcu];
-      gv[q] = CE ? 0.f : (g + ro)[jcu];
+      dv[q] = *dcur;
+      gv[q] = CE ? 0.f : *gcur;
+      const int64_t step = (r + 1 < rows) ? m : 0;      // rows past the end re-read the last valid row (masked below)
+      dcur += step;
+      if (!CE) gcur += step;
     }
 #pragma unroll
     for (int q = 0; q < BW_BATCH; ++q) {
@@ -201,7 +225,7 @@ pairdist_bwd_fused_kernel(const float* __restrict__ g, const float* __restrict__
       if (CE) {
         const float sim = -dd * inv_tau;
         const float diag = (i0 + r + diag_offset == j) ? 1.0f : 0.0f;   // target column of row i
-        gg = gsc * (wr * (__expf(sim - s_lse[r]) - diag) + wc * (__expf(sim - lse_c) - diag));
+        gg = gsc * (wr * (fast_exp(sim - s_lse[r]) - diag) + wc * (fast_exp(sim - lse_c) - diag));
       } else {
         gg = gv[q];
       }
@@ -210,28 +234,27 @@ pairdist_bwd_fused_kernel(const float* __restrict__ g, const float* __restrict__
       // cancels, so the even series x^2/2 (1 + x^2/12 (1 + x^2/30 (1 + x^2/56))) takes over (its first
       // neglected term is < 2e-9 relative there).  sinh x = sqrt(t (t + 2)).
       const float xx = sc * dd, x2 = xx * xx;
-      const float e = __expf(xx);
-      const float t_big = 0.5f * (e + __frcp_rn(e)) - 1.0f;
+      const float e = fast_exp(xx);
+      const float t_big = 0.5f * (e + fast_rcp(e)) - 1.0f;
       const float t_small = 0.5f * x2 * (1.0f + x2 * (1.0f / 12.0f) * (1.0f + x2 * (1.0f / 30.0f) * (1.0f + x2 * (1.0f / 56.0f))));
       const float t = xx < 0.35f ? t_small : t_big;
       const float t2 = fmaxf(t * (t + 2.0f), 1e-30f);
-      const float sh = t2 * rsqrtf(t2);         // sinh x
+      const float sh = t2 * fast_rsq(t2);       // sinh x
       const float ab = s_al[r] * be;
-      const float w = ok ? gg * four_sc * __frcp_rn(ab * sh) : 0.f;
+      const float w = ok ? gg * four_sc * fast_rcp(ab * sh) : 0.f;
       if (ok) {
         if (SPLIT) {
-          __nv_bfloat16* wrow = static_cast<__nv_bfloat16*>(w_out_raw) + (i0 + r) * m;     // CTA-uniform
-          const int64_t plane = n * m;
           const __nv_bfloat16 hi = __float2bfloat16_rn(w);
           const float r1 = w - __bfloat162float(hi);
           const __nv_bfloat16 mid = __float2bfloat16_rn(r1);
-          wrow[ju] = hi;
-          (wrow + plane)[ju] = mid;
-          (wrow + 2 * plane)[ju] = __float2bfloat16_rn(r1 - __bfloat162float(mid));
+          *reinterpret_cast<__nv_bfloat16*>(wcur) = hi;
+          *reinterpret_cast<__nv_bfloat16*>(wcur + plane_bytes) = mid;
+          *reinterpret_cast<__nv_bfloat16*>(wcur + 2 * plane_bytes) = __float2bfloat16_rn(r1 - __bfloat162float(mid));
         } else {
-          (static_cast<float*>(w_out_raw) + (i0 + r) * m)[ju] = w;
+          *reinterpret_cast<float*>(wcur) = w;
         }
       }
+      wcur += w_pitch;
       const float cs = 0.5f * t * ab;           // c * s = h^2 alpha beta, h^2 = t / 2
       racc[r] += w * (1.0f + cs * s_ial[r]);
       cacc += w * (1.0f + cs * ibe);
@@ -310,7 +333,51 @@ lse_cols_combine_kernel(const float* __restrict__ part_max, const float* __restr
   col_lse[j] = mx + logf(sm);
 }
 
+// fp32 [count] -> three bf16 planes [3][count] (hi, mid, lo; hi + mid + lo = x to fp32 accuracy), 16-byte loads and
+// 8-byte stores.  The backward pass emits W fastest as plain fp32 (one 128-byte line per warp store; 0.23 ms at
+// 8192^2) -- writing the planes from inside it costs three 64-byte stores per warp and element and the registers
+// spill (0.44 ms) -- so the planes are cut in this streaming pass instead (0.67 GB of traffic).
+__global__ void __launch_bounds__(256)
+split3_kernel(const float* __restrict__ x, int64_t count, __nv_bfloat16* __restrict__ out) {
+  const int64_t n4 = count >> 2;
+  for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < n4; v += (int64_t)gridDim.x * blockDim.x) {
+    const float4 a = __ldcs(reinterpret_cast<const float4*>(x) + v);
+    const float in[4] = {a.x, a.y, a.z, a.w};
+    __nv_bfloat16 h[4], m[4], l[4];
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      h[t] = __float2bfloat16_rn(in[t]);
+      const float r1 = in[t] - __bfloat162float(h[t]);
+      m[t] = __float2bfloat16_rn(r1);
+      l[t] = __float2bfloat16_rn(r1 - __bfloat162float(m[t]));
+    }
+    *reinterpret_cast<uint2*>(out + 4 * v) = *reinterpret_cast<const uint2*>(h);
+    *reinterpret_cast<uint2*>(out + count + 4 * v) = *reinterpret_cast<const uint2*>(m);
+    *reinterpret_cast<uint2*>(out + 2 * count + 4 * v) = *reinterpret_cast<const uint2*>(l);
+  }
+  if (blockIdx.x == 0 && threadIdx.x < (count & 3)) {          // tail
+    const int64_t i = (n4 << 2) + threadIdx.x;
+    const __nv_bfloat16 h = __float2bfloat16_rn(x[i]);
+    const float r1 = x[i] - __bfloat162float(h);
+    const __nv_bfloat16 m = __float2bfloat16_rn(r1);
+    out[i] = h;
+    out[count + i] = m;
+    out[2 * count + i] = __float2bfloat16_rn(r1 - __bfloat162float(m));
+  }
+}
+
 }  // namespace
+
+int hypret_launch_split3(const float* x, int64_t count, void* out_bf16, cudaStream_t stream) {
+  if (count == 0) return HYPRET_OK;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int64_t want = (count / 4 + 255) / 256;
+  const unsigned grid = (unsigned)(want < (int64_t)sms * 8 ? (want < 1 ? 1 : want) : (int64_t)sms * 8);
+  split3_kernel<<<grid, 256, 0, stream>>>(x, count, static_cast<__nv_bfloat16*>(out_bf16));
+  return (int)cudaGetLastError();
+}
 
 int hypret_launch_pairdist_bwd(const float* g, const float* dmat, const float* asq, const float* psq, int64_t n,
                                int64_t m, float c, void* w_out, int w_format, float* row_partial, int n_row_partial,

@@ -401,6 +401,23 @@ def _w_buffer(n: int, m: int, split: bool, device):
     return torch.empty(n, m, dtype=torch.float32, device=device)
 
 
+def split3(x: torch.Tensor) -> torch.Tensor:
+    """fp32 ``[...]`` -> bf16 ``[3, ...]`` planes with hi + mid + lo = x to fp32 accuracy (``hypret_split3``)."""
+    _need_cuda(x)
+    x = x.contiguous().float()
+    if x.numel() % 4:
+        raise ValueError("split3 needs a multiple of 4 elements")
+    out = torch.empty((3,) + tuple(x.shape), dtype=torch.bfloat16, device=x.device)
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.load().hypret_split3(_ptr(x), x.numel(), _ptr(out), _stream()))
+    return out
+
+
+def _two_pass_split(n: int, m: int) -> bool:
+    """Planes from an fp32 W + ``split3`` (faster) unless the element count is not a multiple of 4."""
+    return (n * m) % 4 == 0
+
+
 def pairdist_ce_bwd(dmat: torch.Tensor, asq: torch.Tensor, psq: torch.Tensor, c: float, row_lse: torch.Tensor,
                     col_lse: Optional[torch.Tensor], inv_tau: float, w_rows: float, w_cols: float,
                     grad_scale: Optional[torch.Tensor] = None, split: bool = False, diag_offset: int = 0,
@@ -412,6 +429,9 @@ def pairdist_ce_bwd(dmat: torch.Tensor, asq: torch.Tensor, psq: torch.Tensor, c:
     batch whose negatives are sharded across ranks (``train.ShardedInBatchInfoNCE``)."""
     _need_cuda(dmat, asq, psq, row_lse, col_lse, grad_scale)
     n, m = dmat.shape
+    two_pass = split and _two_pass_split(n, m)
+    if two_pass:
+        split = False
     w = _w_buffer(n, m, split, dmat.device)
     n_rp = _bwd_chunks(n, m)
     rp = torch.empty(n_rp, n, dtype=torch.float32, device=dmat.device)
@@ -424,6 +444,8 @@ def pairdist_ce_bwd(dmat: torch.Tensor, asq: torch.Tensor, psq: torch.Tensor, c:
                                                       _ptr(gs), _ptr(w), int(split), _ptr(rp), n_rp, _ptr(cp),
                                                       int(diag_offset), int(n if n_total is None else n_total),
                                                       _stream()))
+    if two_pass:
+        w = split3(w)
     return w, rp.sum(dim=0), cp.sum(dim=0)
 
 
@@ -436,6 +458,9 @@ def pairdist_bwd(grad_out: torch.Tensor, dmat: torch.Tensor, asq: torch.Tensor, 
     dmat = dmat.contiguous()
     n, m = dmat.shape
     n_partial = max((n + BWD_ROWS - 1) // BWD_ROWS, n_partial or 0, 1)
+    two_pass = split and _two_pass_split(n, m)
+    if two_pass:
+        split = False
     w = _w_buffer(n, m, split, dmat.device)
     n_rp = _bwd_chunks(n, m)
     rp = torch.empty(n_rp, n, dtype=torch.float32, device=dmat.device)
@@ -444,6 +469,8 @@ def pairdist_bwd(grad_out: torch.Tensor, dmat: torch.Tensor, asq: torch.Tensor, 
         _lib.check(_lib.load().hypret_pairdist_bwd(_ptr(grad_out), _ptr(dmat), _ptr(asq.contiguous()),
                                                    _ptr(psq.contiguous()), n, m, float(c), _ptr(w), int(split), _ptr(rp),
                                                    n_rp, _ptr(cp), n_partial, _stream()))
+    if two_pass:
+        w = split3(w)
     return w, rp.sum(dim=0), cp.sum(dim=0)
 
 
