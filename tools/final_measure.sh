@@ -7,6 +7,7 @@ O=gpurun_out
 python bench.py > $O/${T}_bench_c2_n1.json 2> $O/${T}_bench_c2_n1.err || { echo "bench failed"; tail -5 $O/${T}_bench_c2_n1.err; exit 1; }
 python bench.py --workload c1 --steps 50 > $O/${T}_bench_c1_n1.json 2> $O/${T}_bench_c1_n1.err
 python bench.py --workload c3 --steps 5 --warmup 3 > $O/${T}_bench_c3_n1.json 2> $O/${T}_bench_c3_n1.err
+python bench.py --workload c5 --steps 20 > $O/${T}_bench_c5_n1.json 2> $O/${T}_bench_c5_n1.err
 python bench.py --impl reference --steps 5 --warmup 1 > $O/${T}_bench_reference.json 2> $O/${T}_bench_reference.err
 python tools/bench_train_hyp.py > $O/${T}_train_hyp_c5.json 2> $O/${T}_train_hyp_c5.err
 python tools/c5_parts.py > $O/${T}_c5_parts.txt 2>&1
@@ -19,5 +20,5 @@ ncu --set full --clock-control none --import-source on -k regex:gram_dist -s 2 -
     python tools/bench_train_hyp.py > $O/${T}_ncu_gram.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:pairdist_bwd_fused -s 2 -c 1 -o $O/prof_bwd_${T} \
     python tools/bench_train_hyp.py > $O/${T}_ncu_bwd.log 2>&1
-for f in c2_n1 c1_n1 c3_n1 reference; do echo "== $f"; cut -c1-600 $O/${T}_bench_$f.json; done
+for f in c2_n1 c1_n1 c3_n1 c5_n1 reference; do echo "== $f"; cut -c1-600 $O/${T}_bench_$f.json; done
 cat $O/${T}_train_hyp_c5.json | head -3
