@@ -138,3 +138,29 @@ def test_cpu_tensor_is_rejected():
     from patent_image_retrieval_b200 import ops
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         ops.project_rows(torch.zeros(4, 64))
+
+
+def test_ctypes_structs_match_the_c_header_layout(tmp_path):
+    """sizeof / offsetof of the two structs that cross the ABI, as gcc lays them out from include/hypret.h, against
+    the ctypes mirrors in _lib.py (a silent mismatch would corrupt the routing table or the score plan)."""
+    import shutil
+    import subprocess
+    from patent_image_retrieval_b200 import _lib
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("gcc not available")
+    fields_route = ["base", "n_ranks", "me", "ql"]
+    fields_plan = [name for name, _ in _lib.ScorePlan._fields_]
+    src = ['#include <stdio.h>', '#include <stddef.h>', f'#include "{ROOT / "include" / "hypret.h"}"', "int main(void) {",
+           '  printf("%zu\\n", sizeof(hypret_peer_route));']
+    src += [f'  printf("%zu\\n", offsetof(hypret_peer_route, {f}));' for f in fields_route]
+    src += ['  printf("%zu\\n", sizeof(hypret_score_plan_t));']
+    src += [f'  printf("%zu\\n", offsetof(hypret_score_plan_t, {f}));' for f in fields_plan]
+    src += ["  return 0;", "}"]
+    c_file, exe = tmp_path / "layout.c", tmp_path / "layout"
+    c_file.write_text("\n".join(src))
+    subprocess.run([gcc, "-std=c99", "-o", str(exe), str(c_file)], check=True)
+    got = [int(x) for x in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()]
+    want = [ctypes.sizeof(_lib.PeerRoute)] + [getattr(_lib.PeerRoute, f).offset for f in fields_route]
+    want += [ctypes.sizeof(_lib.ScorePlan)] + [getattr(_lib.ScorePlan, f).offset for f in fields_plan]
+    assert got == want
