@@ -173,10 +173,16 @@ int hypret_score_topk(const void* q_op, int64_t Q, const void* g_op, int64_t N, 
  *              up to the bf16 filter error
  * k <= kprime <= 32: one warp per query.  Wide top-k (kprime <= 64, k <= 128, n_lists*kprime <= 16384,
  * k <= n_lists*kprime): one CTA per query; requires lists built WITHOUT threshold sharing and
- * min_lists >= 3 so that the union of a query's lists contains its top-k (certified by out_margin). */
+ * min_lists >= 3 so that the union of a query's lists contains its top-k (certified by out_margin).
+ *   g_sqnorm64 [N] fp64 or NULL: ||g_j||^2 from hypret_row_sqnorm64 (once per index).  The wide path rescoring 256
+ *              survivors per query then skips the per-survivor norm (half of its fp64 work); NULL: computed in
+ *              the kernel.  The one-warp path ignores it. */
 int hypret_rerank(const float* q32, const float* g32, int64_t Q, int64_t N, int d, float c, int metric,
                   const float* cand_score, const int32_t* cand_idx, const int32_t* list_count, int n_lists, int kprime,
-                  int k, int64_t idx_offset, float* out_score, int64_t* out_idx, float* out_margin, void* stream);
+                  int k, int64_t idx_offset, float* out_score, int64_t* out_idx, float* out_margin,
+                  const double* g_sqnorm64, void* stream);
+/* out[i] = ||x_i||^2 accumulated in fp64 (x [n,d] fp32, d % 4 == 0), in the summation order of the rerank kernels. */
+int hypret_row_sqnorm64(const float* x, int64_t n, int d, double* out, void* stream);
 
 /* Multi-GPU pruning (sharded serving; the reference has no distributed path).  A query's exact
  * rescoring needs only its GLOBAL approximate top-kprime, of which a shard holds kprime / n_shards on average:

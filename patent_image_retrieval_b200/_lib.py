@@ -77,7 +77,9 @@ SIGNATURES = {
     "hypret_score_topk": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int, c_int, c_int, c_int, c_int, c_void_p,
                                   c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "hypret_rerank": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int, c_float, c_int, c_void_p, c_void_p,
-                              c_void_p, c_int, c_int, c_int, c_int64, c_void_p, c_void_p, c_void_p, c_void_p]),
+                              c_void_p, c_int, c_int, c_int, c_int64, c_void_p, c_void_p, c_void_p, c_void_p,
+                              c_void_p]),
+    "hypret_row_sqnorm64": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_void_p]),
     "hypret_rerank_pruned": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int, c_float, c_int, c_void_p, c_void_p,
                                      c_int, c_int, c_int, c_int64, c_void_p, c_void_p, c_void_p, c_void_p]),
     "hypret_cand_select": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int, c_void_p, c_void_p, c_void_p]),

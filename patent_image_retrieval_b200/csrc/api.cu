@@ -131,7 +131,7 @@ static int rerank_common(const float* q32, const float* g32, int64_t Q, int64_t 
                          int kprime, int k,
                          int64_t idx_offset, const float* prune_thr, float* out_score, int64_t* out_idx,
                          float* out_margin, void* stream, const hypret_peer_route* route = nullptr,
-                         int64_t score_off = 0, int64_t idx_off = 0) {
+                         int64_t score_off = 0, int64_t idx_off = 0, const double* g_sq64 = nullptr) {
   if (Q < 0 || N < 1 || d < 4 || (d & 3)) return HYPRET_EINVAL;
   const bool routed = route != nullptr && route->n_ranks > 0;
   if (metric != HYPRET_METRIC_COSINE && metric != HYPRET_METRIC_HYPERBOLIC) return HYPRET_EINVAL;
@@ -146,7 +146,7 @@ static int rerank_common(const float* q32, const float* g32, int64_t Q, int64_t 
   if (rc != HYPRET_OK) return rc;
   return hypret_launch_rerank(q32, g32, Q, N, d, c, metric, cand_score, cand_idx, list_count, n_lists * kprime,
                               kprime, k, idx_offset, prune_thr, out_score, out_idx, out_margin, route, score_off,
-                              idx_off, static_cast<cudaStream_t>(stream));
+                              idx_off, g_sq64, static_cast<cudaStream_t>(stream));
 }
 
 static int check_route(const hypret_peer_route* route, int64_t Q, bool rows_are_own) {
@@ -161,9 +161,19 @@ static int check_route(const hypret_peer_route* route, int64_t Q, bool rows_are_
 
 int hypret_rerank(const float* q32, const float* g32, int64_t Q, int64_t N, int d, float c, int metric,
                   const float* cand_score, const int32_t* cand_idx, const int32_t* list_count, int n_lists, int kprime,
-                  int k, int64_t idx_offset, float* out_score, int64_t* out_idx, float* out_margin, void* stream) {
+                  int k, int64_t idx_offset, float* out_score, int64_t* out_idx, float* out_margin,
+                  const double* g_sqnorm64, void* stream) {
   return rerank_common(q32, g32, Q, N, d, c, metric, cand_score, cand_idx, list_count, n_lists, kprime, k, idx_offset,
-                       nullptr, out_score, out_idx, out_margin, stream);
+                       nullptr, out_score, out_idx, out_margin, stream, nullptr, 0, 0, g_sqnorm64);
+}
+
+int hypret_row_sqnorm64(const float* x, int64_t n, int d, double* out, void* stream) {
+  if (n < 0 || d < 4 || (d & 3)) return HYPRET_EINVAL;
+  if (n == 0) return HYPRET_OK;
+  if (x == nullptr || out == nullptr || !aligned16(x)) return HYPRET_EINVAL;
+  int rc = check_device();
+  if (rc != HYPRET_OK) return rc;
+  return hypret_launch_row_sqnorm64(x, n, d, out, static_cast<cudaStream_t>(stream));
 }
 
 int hypret_rerank_pruned(const float* q32, const float* g32, int64_t Q, int64_t N, int d, float c, int metric,

@@ -342,7 +342,8 @@ int hypret_launch_rerank(const float* q32, const float* g32, int64_t Q, int64_t 
                          const float* cand_score, const int32_t* cand_idx, const int32_t* list_count, int n_cand,
                          int kprime, int k, int64_t idx_offset, const float* prune_thr, float* out_score,
                          int64_t* out_idx, float* out_margin, const hypret_peer_route* route, int64_t score_off,
-                         int64_t idx_off, cudaStream_t stream);
+                         int64_t idx_off, const double* g_sq64, cudaStream_t stream);
+int hypret_launch_row_sqnorm64(const float* x, int64_t n, int d, double* out, cudaStream_t stream);
 int hypret_launch_cand_select(const float* cand_score, const int32_t* cand_idx, const int32_t* list_count, int64_t Q,
                               int n_cand, int kprime, float* sel_score, int32_t* sel_idx,
                               const hypret_peer_route* route, int64_t recv_off, cudaStream_t stream);

@@ -293,13 +293,18 @@ __device__ __forceinline__ bool pair_less(float a, int ia, float b, int ib) {
 // takes the rest with the full-size buffer.  A CTA whose query belongs to the other class exits at once.
 constexpr int RW_SMALL = 1024;
 
-template <int NV>
+// YPRE: ||g||^2 of the gallery rows comes precomputed in fp64 (hypret_row_sqnorm64, once per index) instead of
+// being re-accumulated for each of the 256 survivors of each query: ncu's source page had the float -> double
+// conversions (F2F, a quarter-rate pipe: 13k warp-instructions per query, 7 % of all stall samples on one of them)
+// and the DFMAs (20k) at the top; the row norm was half of both.
+template <int NV, bool YPRE>
 __global__ void __launch_bounds__(RW_THREADS, NV <= 6 ? 4 : 1)
 rerank_wide_kernel(const float* __restrict__ q32, const float* __restrict__ g32, int64_t Q, int64_t N, int d, float c,
                    int metric, const float* __restrict__ cand_score, const int32_t* __restrict__ cand_idx,
                    const int32_t* __restrict__ list_count, int n_lists_alloc, int kprime, int n_pad, int k,
                    int64_t idx_offset, float* __restrict__ out_score,
-                   int64_t* __restrict__ out_idx, float* __restrict__ out_margin, int size_class) {
+                   int64_t* __restrict__ out_idx, float* __restrict__ out_margin, int size_class,
+                   const double* __restrict__ g_sq64) {
   extern __shared__ uint8_t smem_raw[];
   float* ks = reinterpret_cast<float*>(smem_raw);            // [n_pad] surrogate scores
   int* ki = reinterpret_cast<int*>(ks + n_pad);              // [n_pad] gallery ids
@@ -415,13 +420,14 @@ rerank_wide_kernel(const float* __restrict__ q32, const float* __restrict__ g32,
             sacc[t] += (double)qv[i].x * bb.x + (double)qv[i].y * bb.y + (double)qv[i].z * bb.z +
                        (double)qv[i].w * bb.w;
           }
-          yacc[t] += (double)bb.x * bb.x + (double)bb.y * bb.y + (double)bb.z * bb.z + (double)bb.w * bb.w;
+          if (!YPRE) yacc[t] += (double)bb.x * bb.x + (double)bb.y * bb.y + (double)bb.z * bb.z + (double)bb.w * bb.w;
         }
       }
     }
 #pragma unroll
     for (int t = 0; t < PASS; ++t) {
-      const double s0 = warp_sum(sacc[t]), y0 = warp_sum(yacc[t]);
+      const double s0 = warp_sum(sacc[t]);
+      const double y0 = YPRE ? (val[t] ? g_sq64[idx[t]] : 0.0) : warp_sum(yacc[t]);
       double key0 = INFINITY, sur0 = INFINITY;
       if (val[t]) {
         if (metric == HYPRET_METRIC_HYPERBOLIC) {
@@ -493,7 +499,7 @@ int hypret_launch_rerank(const float* q32, const float* g32, int64_t Q, int64_t 
                          const float* cand_score, const int32_t* cand_idx, const int32_t* list_count, int n_cand,
                          int kprime, int k, int64_t idx_offset, const float* prune_thr, float* out_score,
                          int64_t* out_idx, float* out_margin, const hypret_peer_route* route, int64_t score_off,
-                         int64_t idx_off, cudaStream_t stream) {
+                         int64_t idx_off, const double* g_sq64, cudaStream_t stream) {
   if (Q == 0) return HYPRET_OK;
   if (kprime > 32 || k > 32 || k > kprime) {
     if (prune_thr != nullptr || (route != nullptr && route->n_ranks > 0)) return HYPRET_EUNSUPPORTED;
@@ -502,24 +508,29 @@ int hypret_launch_rerank(const float* q32, const float* g32, int64_t Q, int64_t 
     while (n_pad < n_cand) n_pad <<= 1;
     const size_t smem_w = (size_t)n_pad * 8;
     const int need_w = (d + 127) / 128;
-#define HYPRET_RERANK_WIDE(NV)                                                                                      \
+#define HYPRET_RERANK_WIDE_Y(NV, YP)                                                                                \
   do {                                                                                                              \
     if (smem_w > 40 * 1024) {                                                                                       \
-      cudaError_t e = cudaFuncSetAttribute(rerank_wide_kernel<NV>, cudaFuncAttributeMaxDynamicSharedMemorySize,     \
+      cudaError_t e = cudaFuncSetAttribute(rerank_wide_kernel<NV, YP>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                            (int)smem_w);                                                            \
       if (e != cudaSuccess) return (int)e;                                                                          \
     }                                                                                                               \
     if (n_pad > RW_SMALL && list_count != nullptr) {                                                                \
-      rerank_wide_kernel<NV><<<(unsigned)Q, RW_THREADS, (size_t)RW_SMALL * 8, stream>>>(                            \
+      rerank_wide_kernel<NV, YP><<<(unsigned)Q, RW_THREADS, (size_t)RW_SMALL * 8, stream>>>(                        \
           q32, g32, Q, N, d, c, metric, cand_score, cand_idx, list_count, n_lists, kprime, RW_SMALL, k, idx_offset, \
-          out_score, out_idx, out_margin, 0);                                                                       \
+          out_score, out_idx, out_margin, 0, g_sq64);                                                               \
       cudaError_t e0 = cudaGetLastError();                                                                          \
       if (e0 != cudaSuccess) return (int)e0;                                                                        \
     }                                                                                                               \
-    rerank_wide_kernel<NV><<<(unsigned)Q, RW_THREADS, smem_w, stream>>>(                                            \
+    rerank_wide_kernel<NV, YP><<<(unsigned)Q, RW_THREADS, smem_w, stream>>>(                                        \
         q32, g32, Q, N, d, c, metric, cand_score, cand_idx, list_count, n_lists, kprime, n_pad, k, idx_offset,      \
-        out_score, out_idx, out_margin, (n_pad > RW_SMALL && list_count != nullptr) ? 1 : -1);                      \
+        out_score, out_idx, out_margin, (n_pad > RW_SMALL && list_count != nullptr) ? 1 : -1, g_sq64);              \
     return (int)cudaGetLastError();                                                                                 \
+  } while (0)
+#define HYPRET_RERANK_WIDE(NV)                                                                                      \
+  do {                                                                                                              \
+    if (g_sq64 != nullptr) HYPRET_RERANK_WIDE_Y(NV, true);                                                          \
+    HYPRET_RERANK_WIDE_Y(NV, false);                                                                                \
   } while (0)
     if (need_w <= 1) HYPRET_RERANK_WIDE(1);
     if (need_w <= 2) HYPRET_RERANK_WIDE(2);
@@ -528,6 +539,7 @@ int hypret_launch_rerank(const float* q32, const float* g32, int64_t Q, int64_t 
     if (need_w <= 8) HYPRET_RERANK_WIDE(8);
     if (need_w <= 16) HYPRET_RERANK_WIDE(16);
 #undef HYPRET_RERANK_WIDE
+#undef HYPRET_RERANK_WIDE_Y
     return HYPRET_EUNSUPPORTED;
   }
   const size_t smem = (size_t)RR_WARPS * n_cand * 8;
@@ -556,4 +568,29 @@ int hypret_launch_rerank(const float* q32, const float* g32, int64_t Q, int64_t 
   if (need <= 16) HYPRET_RERANK_LAUNCH(16);
 #undef HYPRET_RERANK_LAUNCH
   return HYPRET_EUNSUPPORTED;
+}
+
+namespace {
+// ||x_i||^2 in fp64, one warp per row, lanes striding the row's float4 chunks and the butterfly sum of the rerank
+// kernels (same accumulation order as the in-kernel version it replaces).
+__global__ void __launch_bounds__(256)
+row_sqnorm64_kernel(const float* __restrict__ x, int64_t n, int d, double* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int64_t i = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (i >= n) return;
+  const float4* row = reinterpret_cast<const float4*>(x + i * d);
+  double acc = 0.0;
+  for (int j = lane; j < (d >> 2); j += 32) {
+    const float4 b = __ldg(row + j);
+    acc += (double)b.x * b.x + (double)b.y * b.y + (double)b.z * b.z + (double)b.w * b.w;
+  }
+  acc = warp_sum(acc);
+  if (lane == 0) out[i] = acc;
+}
+}  // namespace
+
+int hypret_launch_row_sqnorm64(const float* x, int64_t n, int d, double* out, cudaStream_t stream) {
+  if (n == 0) return HYPRET_OK;
+  row_sqnorm64_kernel<<<(unsigned)((n + 7) / 8), 256, 0, stream>>>(x, n, d, out);
+  return (int)cudaGetLastError();
 }

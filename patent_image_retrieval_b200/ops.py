@@ -131,9 +131,12 @@ def score_topk(q_op: torch.Tensor, g_op: torch.Tensor, d: int, kprime: int, max_
 
 def rerank(q32: torch.Tensor, g32: torch.Tensor, cand_score: torch.Tensor, cand_idx: torch.Tensor, c: float,
            metric: str, k: int, idx_offset: int = 0, want_margin: bool = False,
-           prune_thr: Optional[torch.Tensor] = None, list_count: Optional[torch.Tensor] = None):
+           prune_thr: Optional[torch.Tensor] = None, list_count: Optional[torch.Tensor] = None,
+           g_sqnorm64: Optional[torch.Tensor] = None):
     """Merge candidate lists, exact fp64-accumulated rescoring, sorted top-k.
     Returns ``(score [Q,k] f32, idx [Q,k] i64[, margin [Q] f32])``.
+    ``g_sqnorm64 [N]`` fp64 (``row_sqnorm64(g32)``, once per index): lets the wide path (k > 32) skip the
+    per-survivor row norm.
     ``prune_thr [Q]`` (multi-GPU): candidates whose surrogate exceeds it are skipped (``hypret_rerank_pruned``)."""
     _need_cuda(q32, g32, cand_score, cand_idx, prune_thr, list_count)
     if prune_thr is not None:
@@ -164,12 +167,25 @@ def rerank(q32: torch.Tensor, g32: torch.Tensor, cand_score: torch.Tensor, cand_
     out_s = torch.empty(Q, k, dtype=torch.float32, device=q32.device)
     out_i = torch.empty(Q, k, dtype=torch.int64, device=q32.device)
     margin = torch.empty(Q, dtype=torch.float32, device=q32.device) if want_margin else None
+    if g_sqnorm64 is not None and (g_sqnorm64.dtype != torch.float64 or g_sqnorm64.numel() != N or
+                                   not g_sqnorm64.is_cuda or not g_sqnorm64.is_contiguous()):
+        raise ValueError("g_sqnorm64 must be a contiguous CUDA float64 tensor with one entry per gallery row")
     with torch.cuda.device(q32.device):
         _lib.check(_lib.load().hypret_rerank(_ptr(q32), _ptr(g32), Q, N, d, float(c), METRIC[metric],
                                              _ptr(cand_score), _ptr(cand_idx), _ptr(list_count), S, kprime, int(k),
                                              int(idx_offset),
-                                             _ptr(out_s), _ptr(out_i), _ptr(margin), _stream()))
+                                             _ptr(out_s), _ptr(out_i), _ptr(margin), _ptr(g_sqnorm64), _stream()))
     return (out_s, out_i, margin) if want_margin else (out_s, out_i)
+
+
+def row_sqnorm64(x: torch.Tensor) -> torch.Tensor:
+    """``||x_i||^2`` accumulated in fp64 (``hypret_row_sqnorm64``): the per-row constant of the exact rerank."""
+    _need_cuda(x)
+    x = x.contiguous().float()
+    out = torch.empty(x.shape[0], dtype=torch.float64, device=x.device)
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.load().hypret_row_sqnorm64(_ptr(x), x.shape[0], x.shape[1], _ptr(out), _stream()))
+    return out
 
 
 def cand_select(cand_score: torch.Tensor, cand_idx: torch.Tensor, list_count: Optional[torch.Tensor] = None):

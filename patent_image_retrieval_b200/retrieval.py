@@ -101,6 +101,7 @@ class GalleryIndex:
         else:
             self.rows32 = feats.contiguous()
             _, self.operand, _ = ops.project_rows(feats, 1.0, mode="cosine", side="gallery", want_point=False)
+        self.rows_sq64 = ops.row_sqnorm64(self.rows32)       # fp64 row norms for the wide exact rerank (8 B per row)
         self._cand = {}
 
     def _query_mode(self):
@@ -169,7 +170,7 @@ class GalleryIndex:
         with _span(kernel_events, "rerank"):
             out = ops.rerank(q32, self.rows32, cand_score, cand_idx, self.c, self.metric, k,
                              idx_offset=self.idx_offset, want_margin=return_margin, prune_thr=prune_thr,
-                             list_count=list_count)
+                             list_count=list_count, g_sqnorm64=self.rows_sq64 if prune_thr is None else None)
         return out
 
 
