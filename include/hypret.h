@@ -291,6 +291,10 @@ int64_t hypret_gram_kpad(int d);
  * (w_format 1) of the two functions above, cut from an fp32 W in one streaming pass -- faster than emitting the
  * planes from inside the backward pass.  count % 4 == 0. */
 int hypret_split3(const float* x, int64_t count, void* out_bf16, void* stream);
+/* The same with the planes interleaved per row: x [n,m] fp32 (m % 4 == 0) -> out [n,3,m] bf16.  Row i of the [n,3m]
+ * view is [hi_i | mid_i | lo_i] and row 3i+p of the [3n,m] view is plane p of row i: each dense product of the backward
+ * (W P and W^T A) is then ONE bf16 GEMM with the three planes concatenated along K. */
+int hypret_split3_rows(const float* x, int64_t n, int64_t m, void* out_bf16, void* stream);
 int hypret_gram_split(const float* x, int64_t n, int d, int side, void* out_bf16, float* sqnorm, void* stream);
 int hypret_gram_dist(const void* a_op, const void* p_op, const float* a32, const float* p32, const float* asq,
                      const float* psq, int64_t n, int64_t m, int d, float c, float* out, void* stream);

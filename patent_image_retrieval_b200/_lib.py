@@ -96,6 +96,7 @@ SIGNATURES = {
                                        c_int64, c_int64, c_void_p]),
     "hypret_gram_kpad": (c_int64, [c_int]),
     "hypret_split3": (c_int, [c_void_p, c_int64, c_void_p, c_void_p]),
+    "hypret_split3_rows": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_void_p]),
     "hypret_gram_split": (c_int, [c_void_p, c_int64, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "hypret_gram_dist": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int,
                                  c_float, c_void_p, c_void_p]),
