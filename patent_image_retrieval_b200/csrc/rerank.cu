@@ -76,8 +76,11 @@ __device__ __forceinline__ int select_candidates(float* cs, int* ci, int n_cand,
   return my_idx;
 }
 
-template <int NV>   // float4 chunks of a row per lane: D <= NV * 128
-__global__ void __launch_bounds__(RR_WARPS * 32, NV <= 4 ? 4 : 1)
+// PRUNED (sharded serving: only the ~k'/W candidates at or below the global threshold are rescored): two rows per
+// pass instead of four -- half the row registers, so 6 CTAs fit an SM instead of 4; the kernel is a chain of
+// dependent latencies per query (list -> select -> rows -> sort), and only more resident warps hide it.
+template <int NV, bool PRUNED>   // float4 chunks of a row per lane: D <= NV * 128
+__global__ void __launch_bounds__(RR_WARPS * 32, NV <= 4 ? (PRUNED ? 6 : 4) : 1)
 rerank_kernel(const float* __restrict__ q32, const float* __restrict__ g32, int64_t Q, int64_t N, int d, float c,
               int metric, const float* __restrict__ cand_score, const int32_t* __restrict__ cand_idx,
               const int32_t* __restrict__ list_count, int n_cand, int kprime, int k, int64_t idx_offset,
@@ -134,7 +137,7 @@ rerank_kernel(const float* __restrict__ q32, const float* __restrict__ g32, int6
   xsq = warp_sum(xsq);
 
   double my_s = 0.0, my_y = 0.0;
-  constexpr int PASS = 4;
+  constexpr int PASS = PRUNED ? 2 : 4;
   constexpr int CH = NV < 4 ? NV : 4;            // float4 chunks per lane and row in flight at once
   for (int r0 = 0; r0 < n_sel; r0 += PASS) {
     const float4* g[PASS];
@@ -546,19 +549,22 @@ int hypret_launch_rerank(const float* q32, const float* g32, int64_t Q, int64_t 
   if (smem > 200 * 1024) return HYPRET_EUNSUPPORTED;
   const int64_t grid = (Q + RR_WARPS - 1) / RR_WARPS;
   const int need = (d + 127) / 128;
-#define HYPRET_RERANK_LAUNCH(NV)                                                                                    \
+#define HYPRET_RERANK_LAUNCH_P(NV, PR)                                                                              \
   do {                                                                                                              \
     if (smem > 48 * 1024) {                                                                                         \
       cudaError_t e =                                                                                               \
-          cudaFuncSetAttribute(rerank_kernel<NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);          \
+          cudaFuncSetAttribute(rerank_kernel<NV, PR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);      \
       if (e != cudaSuccess) return (int)e;                                                                          \
     }                                                                                                               \
-    rerank_kernel<NV><<<(unsigned)grid, RR_WARPS * 32, smem, stream>>>(q32, g32, Q, N, d, c, metric, cand_score,    \
-                                                                      cand_idx, list_count, n_cand, kprime, k,      \
-                                                                      idx_offset, prune_thr, out_score, out_idx,    \
-                                                                      out_margin, make_route(route), score_off,     \
-                                                                      idx_off);                                     \
+    rerank_kernel<NV, PR><<<(unsigned)grid, RR_WARPS * 32, smem, stream>>>(                                         \
+        q32, g32, Q, N, d, c, metric, cand_score, cand_idx, list_count, n_cand, kprime, k, idx_offset, prune_thr,   \
+        out_score, out_idx, out_margin, make_route(route), score_off, idx_off);                                     \
     return (int)cudaGetLastError();                                                                                 \
+  } while (0)
+#define HYPRET_RERANK_LAUNCH(NV)                                                                                    \
+  do {                                                                                                              \
+    if (prune_thr != nullptr) HYPRET_RERANK_LAUNCH_P(NV, true);                                                     \
+    HYPRET_RERANK_LAUNCH_P(NV, false);                                                                              \
   } while (0)
   if (need <= 1) HYPRET_RERANK_LAUNCH(1);
   if (need <= 2) HYPRET_RERANK_LAUNCH(2);
@@ -567,6 +573,7 @@ int hypret_launch_rerank(const float* q32, const float* g32, int64_t Q, int64_t 
   if (need <= 8) HYPRET_RERANK_LAUNCH(8);
   if (need <= 16) HYPRET_RERANK_LAUNCH(16);
 #undef HYPRET_RERANK_LAUNCH
+#undef HYPRET_RERANK_LAUNCH_P
   return HYPRET_EUNSUPPORTED;
 }
 
