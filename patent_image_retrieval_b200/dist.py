@@ -13,6 +13,13 @@ contiguously.  Two query layouts:
   each query's W per-shard lists to the rank that owns the query, which merges them.  Per-GPU
   work is Ql x N_total pairs whatever W is, so query throughput grows with the number of GPUs.
 
+On one NVLink / NVSwitch box (the default deployment) no exchange of ``queries="sharded"`` is an NCCL call: the
+projection kernel stores the operand rows into every rank's exchange buffer (``PeerQueryExchange``, CUDA IPC +
+plain NVLink stores), the fp32 rows follow by copy engine under the scoring kernel, and ``cand_select`` /
+``kth_smallest`` / the pruned rerank store their outputs into the receivers' regions, with stream-ordered step
+counters instead of collectives (csrc/peer.cu).  ``HYPRET_PEER_EXCHANGE=0`` / ``HYPRET_PEER_ROUTE=0`` select the NCCL
+forms; all variants return bit-identical lists.
+
 The reference has no distributed path at all (single process, single GPU).
 """
 from __future__ import annotations
