@@ -45,7 +45,7 @@ extern "C" {
 const char* hypret_strerror(int rc);
 int hypret_version(void);
 
-/* Row length (elements) of the bf16 GEMM operand for feature dimension d:
+/* Row length (elements) of the fp16 GEMM operand for feature dimension d:
  * roundup(d, 64) + 16 extension columns. */
 int64_t hypret_operand_kpad(int d);
 
@@ -55,11 +55,20 @@ int64_t hypret_operand_kpad(int d);
  * normalisation inside sklearn cosine_similarity (notebooks/retrieval.ipynb:368).
  *   u        [n,d] fp32 in
  *   y32      [n,d] fp32 out or NULL  (the point; exact-rerank operand)
- *   op_bf16  [n,kpad] bf16 out or NULL (tensor-core operand, see csrc/project.cu)
+ *   op_f16   [n,kpad] fp16 out or NULL (tensor-core operand in unit-ball coordinates, see csrc/project.cu)
  *   sqnorm   [n] fp32 out or NULL    (||y||^2)
  * d % 4 == 0, d <= 2048. */
-int hypret_project_rows(const float* u, int64_t n, int d, float c, int mode, int side, float* y32, void* op_bf16,
+int hypret_project_rows(const float* u, int64_t n, int d, float c, int mode, int side, float* y32, void* op_f16,
                         float* sqnorm, void* stream);
+/* The same, plus the inputs of the exact-top-k certificate (hypret_rerank_cert).  With m_i the fp32 row that is rounded
+ * to the fp16 main columns of the operand (x^_i = sqrt(c) x_i for a query; -2 rb_j y^_j for a gallery row; the unit
+ * vector for cosine):
+ *   op_err [n] fp32 out or NULL   || fp16(m_i) - m_i ||_2, rounded up
+ *   stats  [4] fp32 in/out or NULL  running maxima over the rows (caller zeroes once per gallery; atomicMax):
+ *          max ||fp16(m)||, max op_err, max rb, max rb ||y^||^2   (rb = 1 / (1 - c ||y||^2); 0 for cosine)
+ * |<fp16 x, fp16 z> - <x, z>| <= op_err(x) ||fp16 z|| + ||x|| op_err(z) then bounds the filter's error for every pair. */
+int hypret_project_rows_cert(const float* u, int64_t n, int d, float c, int mode, int side, float* y32, void* op_f16,
+                             float* sqnorm, float* op_err, float* stats, void* stream);
 
 /* ---- Peer-memory exchange (multi-GPU serving on one NVLink / NVSwitch box; csrc/peer.cu) ------------------
  * The reference is single-GPU; these replace the NCCL all_gather of the per-rank query batches in the
@@ -68,9 +77,10 @@ int hypret_project_rows(const float* u, int64_t n, int d, float c, int mode, int
  *   hypret_peer_open    map a peer's buffer from its handle (peer access is enabled on demand)
  *   hypret_peer_close / hypret_peer_free   undo the two above
  *   hypret_peer_copy    asynchronous copy between any two mapped buffers (copy engines; no SM)
- *   hypret_project_rows_peers   hypret_project_rows for query rows, with the bf16 operand row stored into
+ *   hypret_project_rows_peers   hypret_project_rows for query rows, with the fp16 operand row stored into
  *                       n_dst destination buffers (op_dsts_host: HOST array of device pointers, each already
- *                       offset to the block of this rank) -- the projection is the all-gather
+ *                       offset to the block of this rank) -- the projection is the all-gather; op_err [n] fp32 out or
+ *                       NULL as in hypret_project_rows_cert
  *   hypret_peer_signal  behind everything queued on `stream` so far: *flags_host[i] = value (release, system scope)
  *   hypret_peer_wait    hold `stream` until flags[i] >= value for all i < n (20 s bound: then *err = 1 + i) */
 #define HYPRET_IPC_HANDLE_BYTES 64
@@ -80,7 +90,7 @@ int hypret_peer_open(const void* handle_host, void** peer_ptr);
 int hypret_peer_close(void* peer_ptr);
 int hypret_peer_copy(void* dst, const void* src, size_t bytes, void* stream);
 int hypret_project_rows_peers(const float* u, int64_t n, int d, float c, int mode, float* y32,
-                              void* const* op_dsts_host, int n_dst, void* stream);
+                              void* const* op_dsts_host, int n_dst, float* op_err, void* stream);
 int hypret_peer_signal(void* const* flags_host, int n, uint32_t value, void* stream);
 
 /* Output routing of the sharded-serving exchange: the all_to_all / all_gather that follows a kernel is done BY that
@@ -140,9 +150,9 @@ int hypret_score_strip(const hypret_score_plan_t* plan, int cta, int step, int32
  * Replaces the one-vs-all scoring loops  pmath.dist(q[1,D], G[P,D])  (src/train.py:3259)
  * and  cosine_similarity(Q, G)  (notebooks/retrieval.ipynb:368) together with the ranking
  * that follows them (np.argsort, retrieval.ipynb:383,202; torch.topk, src/auxiliary.py:374)
- * as a *candidate filter*: per query and strip it keeps the kprime smallest bf16-operand
+ * as a *candidate filter*: per query and strip it keeps the kprime smallest fp16-operand
  * surrogate scores.  The [Q,N] matrix is never written to memory.
- *   q_op [Q,kpad] bf16, g_op [N,kpad] bf16   operands from hypret_project_rows
+ *   q_op [Q,kpad] fp16, g_op [N,kpad] fp16   operands from hypret_project_rows
  *   cand_score [Q, n_lists, kprime] fp32 out, cand_idx same shape int32 out (-1 = empty)
  *   n_lists   must equal plan.n_lists of hypret_score_plan(Q, N, d, kprime, max_ctas, min_lists)
  *   thr_workspace  [Q] uint32 scratch, or NULL.  When given, the strips of a query exchange
@@ -169,8 +179,8 @@ int hypret_score_topk(const void* q_op, int64_t Q, const void* g_op, int64_t N, 
  *   q32 [Q,d], g32 [N,d] fp32   (hyperbolic: points on the ball; cosine: raw features)
  *   out_score [Q,k] fp32, out_idx [Q,k] int64 (+ idx_offset; -1 when fewer than k rows)
  *   out_margin [Q] fp32 or NULL: (smallest surrogate a NON-candidate can have) - (exact surrogate of the
- *              k-th result); > 0 certifies that no gallery row outside the candidate set can beat the result
- *              up to the bf16 filter error
+ *              k-th result) in unit-ball coordinates (c * rb * ||x - y||^2); hypret_rerank_cert compares it with a
+ *              bound on the fp16 filter's error
  * k <= kprime <= 32: one warp per query.  Wide top-k (kprime <= 64, k <= 128, n_lists*kprime <= 16384,
  * k <= n_lists*kprime): one CTA per query; requires lists built WITHOUT threshold sharing and
  * min_lists >= 3 so that the union of a query's lists contains its top-k (certified by out_margin).
@@ -181,6 +191,28 @@ int hypret_rerank(const float* q32, const float* g32, int64_t Q, int64_t N, int 
                   const float* cand_score, const int32_t* cand_idx, const int32_t* list_count, int n_lists, int kprime,
                   int k, int64_t idx_offset, float* out_score, int64_t* out_idx, float* out_margin,
                   const double* g_sqnorm64, void* stream);
+/* hypret_rerank (k <= kprime <= 32) with the EXACT-TOP-K GUARANTEE.  The filter is an fp16 GEMM, so a gallery row outside
+ * the candidate set could in principle precede the k-th result.  Per query the kernel bounds the filter's error,
+ *   E = q_err[q] * stats[0] + ||x_q|| * stats[1] + slack * (||x_q|| stats[0] + ||x_q||^2 stats[2] + stats[3]),
+ * (q_err / stats from hypret_project_rows_cert; slack covers the fp32 accumulation of the tensor core), and accepts the
+ * result only if  (k'-th best filter score) - (exact surrogate of the k-th result) > E  -- then no non-candidate can
+ * have an exact surrogate at or below the k-th result's.  Otherwise the query id is appended to fb_list (fb_count
+ * counts them; zeroed by this call) and its two lock words in fb_state [2Q] are cleared: hypret_exact_topk, queued
+ * behind this call, recomputes exactly those queries from all gallery rows.  certified [Q] uint8 out or NULL. */
+int hypret_rerank_cert(const float* q32, const float* g32, int64_t Q, int64_t N, int d, float c, int metric,
+                       const float* cand_score, const int32_t* cand_idx, const int32_t* list_count, int n_lists,
+                       int kprime, int k, int64_t idx_offset, float* out_score, int64_t* out_idx, float* out_margin,
+                       const float* q_err, const float* g_stats, int32_t* fb_state, int32_t* fb_count, int32_t* fb_list,
+                       uint8_t* certified, void* stream);
+/* Exact top-k of the listed queries by a scan of ALL gallery rows -- what the reference's per-query loop does
+ * (pmath.dist one-vs-all + torch.topk, src/train.py:3259, src/auxiliary.py:374; cosine: retrieval.ipynb:368,202) --
+ * with the arithmetic and ordering of hypret_rerank; overwrites rows q_list[0 .. *q_count) of out_score / out_idx
+ * ([Q,k], + idx_offset).  *q_count is read on the device (no host synchronisation; an empty list costs one launch of
+ * CTAs that exit at once).  g_sqnorm64 [N] from hypret_row_sqnorm64; fb_state [2Q] as left by hypret_rerank_cert.
+ * k <= 32. */
+int hypret_exact_topk(const float* q32, const float* g32, const double* g_sqnorm64, int64_t Q, int64_t N, int d,
+                      float c, int metric, int k, int64_t idx_offset, const int32_t* q_list, const int32_t* q_count,
+                      int32_t* fb_state, float* out_score, int64_t* out_idx, void* stream);
 /* out[i] = ||x_i||^2 accumulated in fp64 (x [n,d] fp32, d % 4 == 0), in the summation order of the rerank kernels. */
 int hypret_row_sqnorm64(const float* x, int64_t n, int d, double* out, void* stream);
 

@@ -56,13 +56,20 @@ SIGNATURES = {
     "hypret_operand_kpad": (c_int64, [c_int]),
     "hypret_project_rows": (c_int, [c_void_p, c_int64, c_int, c_float, c_int, c_int, c_void_p, c_void_p, c_void_p,
                                     c_void_p]),
+    "hypret_project_rows_cert": (c_int, [c_void_p, c_int64, c_int, c_float, c_int, c_int, c_void_p, c_void_p, c_void_p,
+                                         c_void_p, c_void_p, c_void_p]),
+    "hypret_rerank_cert": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int, c_float, c_int, c_void_p, c_void_p,
+                                   c_void_p, c_int, c_int, c_int, c_int64, c_void_p, c_void_p, c_void_p, c_void_p,
+                                   c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "hypret_exact_topk": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int, c_float, c_int, c_int, c_int64,
+                                  c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "hypret_peer_alloc": (c_int, [c_size_t, POINTER(c_void_p), c_void_p]),
     "hypret_peer_free": (c_int, [c_void_p]),
     "hypret_peer_open": (c_int, [c_void_p, POINTER(c_void_p)]),
     "hypret_peer_close": (c_int, [c_void_p]),
     "hypret_peer_copy": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p]),
     "hypret_project_rows_peers": (c_int, [c_void_p, c_int64, c_int, c_float, c_int, c_void_p, POINTER(c_void_p), c_int,
-                                          c_void_p]),
+                                          c_void_p, c_void_p]),
     "hypret_peer_signal": (c_int, [POINTER(c_void_p), c_int, c_uint32, c_void_p]),
     "hypret_peer_wait": (c_int, [c_void_p, c_int, c_uint32, c_void_p, c_void_p]),
     "hypret_cand_select_route": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int, c_void_p, c_void_p,

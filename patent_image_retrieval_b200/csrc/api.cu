@@ -38,17 +38,32 @@ int hypret_version(void) { return 100; }
 
 int64_t hypret_operand_kpad(int d) { return d > 0 ? (int64_t)hypret_kpad(d) : 0; }
 
-int hypret_project_rows(const float* u, int64_t n, int d, float c, int mode, int side, float* y32, void* op_bf16,
+static int project_rows_common(const float* u, int64_t n, int d, float c, int mode, int side, float* y32,
+                               void* op_f16, float* sqnorm, float* op_err, float* stats, void* stream);
+
+int hypret_project_rows(const float* u, int64_t n, int d, float c, int mode, int side, float* y32, void* op_f16,
                         float* sqnorm, void* stream) {
+  return project_rows_common(u, n, d, c, mode, side, y32, op_f16, sqnorm, nullptr, nullptr, stream);
+}
+
+int hypret_project_rows_cert(const float* u, int64_t n, int d, float c, int mode, int side, float* y32, void* op_f16,
+                             float* sqnorm, float* op_err, float* stats, void* stream) {
+  if ((op_err != nullptr || stats != nullptr) && op_f16 == nullptr) return HYPRET_EINVAL;
+  return project_rows_common(u, n, d, c, mode, side, y32, op_f16, sqnorm, op_err, stats, stream);
+}
+
+static int project_rows_common(const float* u, int64_t n, int d, float c, int mode, int side, float* y32,
+                               void* op_f16, float* sqnorm, float* op_err, float* stats, void* stream) {
   if (n < 0 || d < 4 || (d & 3) || d > 2048) return HYPRET_EINVAL;
   if (mode < HYPRET_MODE_EXPMAP0 || mode > HYPRET_MODE_COSINE) return HYPRET_EINVAL;
   if (side != HYPRET_SIDE_QUERY && side != HYPRET_SIDE_GALLERY) return HYPRET_EINVAL;
   if (mode != HYPRET_MODE_COSINE && !(c > 0.f)) return HYPRET_EINVAL;
   if (n == 0) return HYPRET_OK;
-  if (u == nullptr || !aligned16(u) || !aligned16(y32) || !aligned16(op_bf16)) return HYPRET_EINVAL;
+  if (u == nullptr || !aligned16(u) || !aligned16(y32) || !aligned16(op_f16)) return HYPRET_EINVAL;
   int rc = check_device();
   if (rc != HYPRET_OK) return rc;
-  return hypret_launch_project_rows(u, n, d, c, mode, side, y32, op_bf16, sqnorm, static_cast<cudaStream_t>(stream));
+  return hypret_launch_project_rows(u, n, d, c, mode, side, y32, op_f16, sqnorm, op_err, stats,
+                                    static_cast<cudaStream_t>(stream));
 }
 
 int hypret_peer_alloc(size_t bytes, void** dev_ptr, void* handle_out_host) {
@@ -88,7 +103,7 @@ int hypret_peer_copy(void* dst, const void* src, size_t bytes, void* stream) {
 }
 
 int hypret_project_rows_peers(const float* u, int64_t n, int d, float c, int mode, float* y32,
-                              void* const* op_dsts_host, int n_dst, void* stream) {
+                              void* const* op_dsts_host, int n_dst, float* op_err, void* stream) {
   if (n < 0 || d < 4 || (d & 3) || d > 2048 || n_dst < 1 || n_dst > HYPRET_MAX_PEERS) return HYPRET_EINVAL;
   if (mode < HYPRET_MODE_EXPMAP0 || mode > HYPRET_MODE_COSINE) return HYPRET_EINVAL;
   if (mode != HYPRET_MODE_COSINE && !(c > 0.f)) return HYPRET_EINVAL;
@@ -98,7 +113,7 @@ int hypret_project_rows_peers(const float* u, int64_t n, int d, float c, int mod
     if (op_dsts_host[i] == nullptr || !aligned16(op_dsts_host[i])) return HYPRET_EINVAL;
   int rc = check_device();
   if (rc != HYPRET_OK) return rc;
-  return hypret_launch_project_rows_peers(u, n, d, c, mode, y32, op_dsts_host, n_dst,
+  return hypret_launch_project_rows_peers(u, n, d, c, mode, y32, op_dsts_host, n_dst, op_err,
                                           static_cast<cudaStream_t>(stream));
 }
 
@@ -131,7 +146,8 @@ static int rerank_common(const float* q32, const float* g32, int64_t Q, int64_t 
                          int kprime, int k,
                          int64_t idx_offset, const float* prune_thr, float* out_score, int64_t* out_idx,
                          float* out_margin, void* stream, const hypret_peer_route* route = nullptr,
-                         int64_t score_off = 0, int64_t idx_off = 0, const double* g_sq64 = nullptr) {
+                         int64_t score_off = 0, int64_t idx_off = 0, const double* g_sq64 = nullptr,
+                         const CertArgs& cert = no_cert()) {
   if (Q < 0 || N < 1 || d < 4 || (d & 3)) return HYPRET_EINVAL;
   const bool routed = route != nullptr && route->n_ranks > 0;
   if (metric != HYPRET_METRIC_COSINE && metric != HYPRET_METRIC_HYPERBOLIC) return HYPRET_EINVAL;
@@ -146,7 +162,7 @@ static int rerank_common(const float* q32, const float* g32, int64_t Q, int64_t 
   if (rc != HYPRET_OK) return rc;
   return hypret_launch_rerank(q32, g32, Q, N, d, c, metric, cand_score, cand_idx, list_count, n_lists * kprime,
                               kprime, k, idx_offset, prune_thr, out_score, out_idx, out_margin, route, score_off,
-                              idx_off, g_sq64, static_cast<cudaStream_t>(stream));
+                              idx_off, g_sq64, cert, static_cast<cudaStream_t>(stream));
 }
 
 static int check_route(const hypret_peer_route* route, int64_t Q, bool rows_are_own) {
@@ -165,6 +181,43 @@ int hypret_rerank(const float* q32, const float* g32, int64_t Q, int64_t N, int 
                   const double* g_sqnorm64, void* stream) {
   return rerank_common(q32, g32, Q, N, d, c, metric, cand_score, cand_idx, list_count, n_lists, kprime, k, idx_offset,
                        nullptr, out_score, out_idx, out_margin, stream, nullptr, 0, 0, g_sqnorm64);
+}
+
+int hypret_rerank_cert(const float* q32, const float* g32, int64_t Q, int64_t N, int d, float c, int metric,
+                       const float* cand_score, const int32_t* cand_idx, const int32_t* list_count, int n_lists,
+                       int kprime, int k, int64_t idx_offset, float* out_score, int64_t* out_idx, float* out_margin,
+                       const float* q_err, const float* g_stats, int32_t* fb_state, int32_t* fb_count, int32_t* fb_list,
+                       uint8_t* certified, void* stream) {
+  if (kprime > 32 || k > 32 || k > kprime) return HYPRET_EUNSUPPORTED;
+  if (q_err == nullptr || g_stats == nullptr || fb_state == nullptr || fb_count == nullptr || fb_list == nullptr)
+    return HYPRET_EINVAL;
+  CertArgs cert;
+  cert.q_err = q_err; cert.g_stats = g_stats; cert.state = fb_state; cert.count = fb_count; cert.list = fb_list;
+  cert.flags = certified;
+  // fp32 accumulation in the tensor core (truncating: up to 2 ulps of the running sum per 16-deep MMA step) and the
+  // 2^-24 tails of the 3-way splits of the extension columns
+  cert.slack = (float)(hypret_kpad(d) / 16 + 8) * 2.384185791015625e-07f;
+  cudaError_t e = cudaMemsetAsync(fb_count, 0, sizeof(int32_t), static_cast<cudaStream_t>(stream));
+  if (e != cudaSuccess) return (int)e;
+  return rerank_common(q32, g32, Q, N, d, c, metric, cand_score, cand_idx, list_count, n_lists, kprime, k, idx_offset,
+                       nullptr, out_score, out_idx, out_margin, stream, nullptr, 0, 0, nullptr, cert);
+}
+
+int hypret_exact_topk(const float* q32, const float* g32, const double* g_sqnorm64, int64_t Q, int64_t N, int d,
+                      float c, int metric, int k, int64_t idx_offset, const int32_t* q_list, const int32_t* q_count,
+                      int32_t* fb_state, float* out_score, int64_t* out_idx, void* stream) {
+  if (Q < 0 || N < 1 || d < 4 || (d & 3) || k < 1 || k > 32) return HYPRET_EINVAL;
+  if (N > 0x7fffffffll) return HYPRET_EUNSUPPORTED;
+  if (metric != HYPRET_METRIC_COSINE && metric != HYPRET_METRIC_HYPERBOLIC) return HYPRET_EINVAL;
+  if (metric == HYPRET_METRIC_HYPERBOLIC && !(c > 0.f)) return HYPRET_EINVAL;
+  if (Q == 0) return HYPRET_OK;
+  if (q32 == nullptr || g32 == nullptr || g_sqnorm64 == nullptr || q_list == nullptr || q_count == nullptr ||
+      fb_state == nullptr || out_score == nullptr || out_idx == nullptr || !aligned16(q32) || !aligned16(g32))
+    return HYPRET_EINVAL;
+  int rc = check_device();
+  if (rc != HYPRET_OK) return rc;
+  return hypret_launch_exact_topk(q32, g32, g_sqnorm64, Q, N, d, c, metric, k, idx_offset, q_list, q_count, fb_state,
+                                  out_score, out_idx, static_cast<cudaStream_t>(stream));
 }
 
 int hypret_row_sqnorm64(const float* x, int64_t n, int d, double* out, void* stream) {

@@ -15,7 +15,7 @@
 #include "../../include/hypret.h"
 
 // ----------------------------------------------------------------------------- geometry
-// bf16 GEMM operand row = [ Dpad main columns | 16 extension columns ], Dpad = roundup(D, 64).
+// fp16 GEMM operand row (scoring) = [ Dpad main columns | 16 extension columns ], Dpad = roundup(D, 64).
 constexpr int HYPRET_KBLK = 64;   // K elements per 128B-swizzled block
 constexpr int HYPRET_MAX_PEERS = 16;   // ranks of one NVLink box an exchange buffer can address
 constexpr int HYPRET_KEXT = 16;   // extension block: one UMMA_K step (32B-swizzled)
@@ -142,7 +142,8 @@ __device__ __forceinline__ void tcgen05_fence_before() {
 __device__ __forceinline__ void tcgen05_fence_after() {
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 }
-// D[tmem] (+)= A[smem] * B[smem]^T, bf16 inputs, fp32 accumulate; one thread issues.
+// D[tmem] (+)= A[smem] * B[smem]^T, 16-bit inputs (kind::f16: bf16 or fp16 as the instruction descriptor says), fp32
+// accumulate; one thread issues.
 __device__ __forceinline__ void umma_bf16_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
                                              uint32_t accumulate) {
   asm volatile(
@@ -286,6 +287,10 @@ __device__ __forceinline__ uint64_t umma_smem_desc(uint32_t smem_addr, uint32_t 
 // Instruction descriptor (cute::UMMA::InstrDescriptor) for kind::f16, bf16 x bf16 -> fp32,
 // both operands K-major: c_format=F32 [4,6) | a_format=BF16 [7,10) | b_format=BF16 [10,13) |
 // N>>3 [17,23) | M>>4 [24,29).
+// the same with fp16 operands (a_format = b_format = F16 = 0): the scoring kernel's operands (csrc/project.cu)
+__host__ __device__ constexpr uint32_t umma_idesc_f16(int m, int n) {
+  return (1u << 4) | (static_cast<uint32_t>(n >> 3) << 17) | (static_cast<uint32_t>(m >> 4) << 24);
+}
 __host__ __device__ constexpr uint32_t umma_idesc_bf16(int m, int n) {
   return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(n >> 3) << 17) |
          (static_cast<uint32_t>(m >> 4) << 24);
@@ -307,11 +312,11 @@ __device__ __forceinline__ double warp_sum(double v) {
 
 // ----------------------------------------------------------------------------- launchers (one per .cu)
 int hypret_launch_project_rows_peers(const float* u, int64_t n, int d, float c, int mode, float* y32,
-                                     void* const* op_dsts_host, int n_dst, cudaStream_t stream);
+                                     void* const* op_dsts_host, int n_dst, float* op_err, cudaStream_t stream);
 int hypret_launch_peer_signal(void* const* flags_host, int n, uint32_t value, cudaStream_t stream);
 int hypret_launch_peer_wait(const uint32_t* flags, int n, uint32_t value, uint32_t* err, cudaStream_t stream);
 int hypret_launch_project_rows(const float* u, int64_t n, int d, float c, int mode, int side, float* y32,
-                               void* op_bf16, float* sqnorm, cudaStream_t stream);
+                               void* op_f16, float* sqnorm, float* op_err, float* stats, cudaStream_t stream);
 int hypret_launch_score_topk(const void* q_op, int64_t Q, const void* g_op, int64_t N, int d, int kprime,
                              int n_lists, int max_ctas, int min_lists, float* cand_score, int32_t* cand_idx,
                              uint32_t* thr_ws, int32_t* list_count, float* debug_scores, cudaStream_t stream);
@@ -338,11 +343,33 @@ __device__ __forceinline__ int64_t route_row(const PeerRoute& r, int64_t q, int*
   return (int64_t)r.me * r.ql + (q - o * r.ql);
 }
 
+// Exact-top-k certificate of the rerank kernels (hypret_rerank_cert): per-query bound E on |tensor-core surrogate - exact
+// surrogate| from the projection kernel's rounding residuals; a query whose margin does not exceed E is appended to
+// `list` (and its lock words in `state` cleared) for hypret_exact_topk.  q_err == nullptr: no certificate.
+struct CertArgs {
+  const float* q_err;     // [Q] rounding residual norm of each query operand row
+  const float* g_stats;   // [4] gallery maxima (csrc/project.cu)
+  float slack;            // relative allowance for fp32 accumulation / split truncation
+  int32_t* state;         // [2Q] {lock, initialised} words of the fallback merge
+  int32_t* count;         // [1] number of uncertified queries
+  int32_t* list;          // [Q] their ids
+  uint8_t* flags;         // [Q] or NULL: 1 = certified by the filter pass, 0 = sent to the exact scan
+};
+inline CertArgs no_cert() {
+  CertArgs a;
+  a.q_err = nullptr; a.g_stats = nullptr; a.slack = 0.f; a.state = nullptr; a.count = nullptr; a.list = nullptr;
+  a.flags = nullptr;
+  return a;
+}
 int hypret_launch_rerank(const float* q32, const float* g32, int64_t Q, int64_t N, int d, float c, int metric,
                          const float* cand_score, const int32_t* cand_idx, const int32_t* list_count, int n_cand,
                          int kprime, int k, int64_t idx_offset, const float* prune_thr, float* out_score,
                          int64_t* out_idx, float* out_margin, const hypret_peer_route* route, int64_t score_off,
-                         int64_t idx_off, const double* g_sq64, cudaStream_t stream);
+                         int64_t idx_off, const double* g_sq64, const CertArgs& cert, cudaStream_t stream);
+int hypret_launch_exact_topk(const float* q32, const float* g32, const double* g_sq64, int64_t Q, int64_t N, int d,
+                             float c, int metric, int k, int64_t idx_offset, const int32_t* q_list,
+                             const int32_t* q_count, int32_t* state, float* out_score, int64_t* out_idx,
+                             cudaStream_t stream);
 int hypret_launch_row_sqnorm64(const float* x, int64_t n, int d, double* out, cudaStream_t stream);
 int hypret_launch_cand_select(const float* cand_score, const int32_t* cand_idx, const int32_t* list_count, int64_t Q,
                               int n_cand, int kprime, float* sel_score, int32_t* sel_idx,

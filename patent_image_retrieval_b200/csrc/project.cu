@@ -8,49 +8,63 @@
 //
 // One warp owns one row: 128-bit coalesced loads, the whole row stays in registers, two
 // warp-shuffle reductions (||u||^2, then ||y||^2 of the rounded result, as torch does),
-// and up to three coalesced stores: the fp32 point (rerank operand), the bf16 GEMM operand
+// and up to three coalesced stores: the fp32 point (rerank operand), the fp16 GEMM operand
 // row and ||y||^2.  HBM-bound: (4 + 4 + 2) * D bytes per row when all outputs are taken.
 //
-// bf16 operand row layout (Kpad = roundup(D,64) + 16 columns):
-//   query   (side 0): [ x_0..x_{D-1} | 0.. | x1 x1 x2 x1 x2 x3  1  1  1  0 0 0 0 0 0 0 ]
-//   gallery (side 1): [ -2*rb*y_0..  | 0.. | r1 r2 r1 r3 r2 r1  b1 b2 b3 0 0 0 0 0 0 0 ]
-// with x1+x2+x3 = ||x||^2, r1+r2+r3 = rb = 1/(1-c||y||^2), b1+b2+b3 = rb*||y||^2 (3-way bf16
+// fp16 operand row layout (Kpad = roundup(D,64) + 16 columns), in UNIT-BALL coordinates x^ = sqrt(c) x:
+//   query   (side 0): [ x^_0..x^_{D-1} | 0.. | x1 x1 x2 x1 x2 x3  1  1  1  0 0 0 0 0 0 0 ]
+//   gallery (side 1): [ -2*rb*y^_0..   | 0.. | r1 r2 r1 r3 r2 r1  b1 b2 b3 0 0 0 0 0 0 0 ]
+// with x1+x2+x3 = ||x^||^2, r1+r2+r3 = rb = 1/(1-||y^||^2), b1+b2+b3 = rb*||y^||^2 (3-way fp16
 // splits), so that the tensor-core inner product of a query row and a gallery row is the
-// ranking surrogate  rb_j * ||x_i - y_j||^2  (monotone in the Poincare distance for fixed i)
-// with only the main-column products carrying bf16 rounding error.
+// ranking surrogate  rb_j * ||x^_i - y^_j||^2 = c * rb_j * ||x_i - y_j||^2  (monotone in the Poincare distance for
+// fixed i) with only the main-column products carrying rounding error.  fp16, not bf16: both run at the same
+// tensor rate (kind::f16), but fp16 keeps 11 significant bits against 8, which makes the rounding bound of the
+// exact-top-k certificate 8x tighter (with bf16 only 73 % of C2's queries could be certified at k' = 16, with fp16
+// > 99.9 %).  The unit-ball scaling bounds every entry whatever c is (|x^_i| < 1, |2 rb y^_i| < 250, rb ||y^||^2 < 125
+// with geoopt's eps = 4e-3 clip), far inside fp16's range.
 // Cosine: query row = unit vector, gallery row = minus the unit vector, extension zero, so the
 // inner product is  -cos(x, y)  (smaller = better, same as the hyperbolic surrogate).
+//
+// Certificate inputs (hypret_project_rows_cert; used by the exact-top-k guarantee of hypret_rerank_cert): with m the
+// fp32 main-column row that is rounded to fp16 (x^ for a query, z = -2 rb y^ for a gallery row), the kernel can also emit
+//   op_err[i]  = || fp16(m_i) - m_i ||_2          the rounding residual of the row, and
+//   stats[0..3] (atomicMax over the rows: gallery side) = max ||fp16(m)||, max op_err, max rb, max rb ||y^||^2
+// so that |<fp16 x, fp16 z> - <x, z>| = |<dx, z~> + <x, dz>| <= op_err_i * stats[0] + ||x_i|| * stats[1] bounds the error of
+// the tensor-core surrogate of EVERY gallery row for query i (Cauchy-Schwarz; no distributional assumption).
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 
 namespace {
 
 constexpr int WARPS_PER_BLOCK = 8;
 
-__device__ __forceinline__ void split3(float v, __nv_bfloat16& a, __nv_bfloat16& b, __nv_bfloat16& c) {
-  a = __float2bfloat16_rn(v);
-  float r = v - __bfloat162float(a);
-  b = __float2bfloat16_rn(r);
-  r -= __bfloat162float(b);
-  c = __float2bfloat16_rn(r);
+__device__ __forceinline__ void split3(float v, __half& a, __half& b, __half& c) {
+  a = __float2half_rn(v);
+  float r = v - __half2float(a);
+  b = __float2half_rn(r);
+  r -= __half2float(b);
+  c = __float2half_rn(r);
 }
 
-__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
-  __nv_bfloat162 p = __floats2bfloat162_rn(lo, hi);
+__device__ __forceinline__ uint32_t pack_f16(float lo, float hi) {
+  __half2 p = __floats2half2_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&p);
 }
 
-// Destinations of the bf16 operand row.  n == 1: the usual local buffer.  n > 1 (multi-GPU serving,
+// Destinations of the fp16 operand row.  n == 1: the usual local buffer.  n > 1 (multi-GPU serving,
 // hypret_project_rows_peers): the same row is stored into the exchange buffer of every rank of the box -- peer
 // memory mapped over NVLink, plain posted stores -- so the projection IS the all-gather of the query operands.
 struct OpDsts {
-  __nv_bfloat16* p[HYPRET_MAX_PEERS];
+  __half* p[HYPRET_MAX_PEERS];
   int n;
 };
 
 template <int NV>  // float4 chunks per lane; supports D <= NV * 128
 __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
 project_rows_kernel(const float* __restrict__ u, int64_t n, int d, float c, int mode, int side,
-                    float* __restrict__ y32, const OpDsts ops, float* __restrict__ sqnorm) {
+                    float* __restrict__ y32, const OpDsts ops, float* __restrict__ sqnorm,
+                    float* __restrict__ op_err, unsigned* __restrict__ stats) {
   const int lane = threadIdx.x & 31;
   const int nvec = d >> 2;
   const int dpad = hypret_dpad(d);
@@ -124,12 +138,43 @@ project_rows_kernel(const float* __restrict__ u, int64_t n, int d, float c, int 
 
     if (ops.n > 0) {
       const bool hyp = (mode != HYPRET_MODE_COSINE);
-      const float rb = hyp ? 1.0f / (1.0f - c * ysq) : 1.0f;
-      const float mul = (side == HYPRET_SIDE_QUERY) ? 1.0f : (hyp ? -2.0f * rb : -1.0f);
+      const float ysq_u = hyp ? c * ysq : ysq;                 // squared norm in unit-ball coordinates
+      const float rb = hyp ? 1.0f / (1.0f - ysq_u) : 1.0f;
+      const float mul = (side == HYPRET_SIDE_QUERY) ? (hyp ? sc : 1.0f) : (hyp ? -2.0f * rb * sc : -1.0f);
       uint2 packed[NV];
 #pragma unroll
       for (int i = 0; i < NV; ++i)
-        packed[i] = make_uint2(pack_bf16(v[i].x * mul, v[i].y * mul), pack_bf16(v[i].z * mul, v[i].w * mul));
+        packed[i] = make_uint2(pack_f16(v[i].x * mul, v[i].y * mul), pack_f16(v[i].z * mul, v[i].w * mul));
+      if (op_err != nullptr || stats != nullptr) {
+        // rounding residual and norm of the row as the tensor core sees it (lanes past the row hold zeros)
+        float e2 = 0.f, r2 = 0.f;
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+          const float m4[4] = {v[i].x * mul, v[i].y * mul, v[i].z * mul, v[i].w * mul};
+          const uint32_t w2[2] = {packed[i].x, packed[i].y};
+#pragma unroll
+          for (int t = 0; t < 4; ++t) {
+            const float r = __half2float(__ushort_as_half((unsigned short)((t & 1) ? (w2[t >> 1] >> 16) : (w2[t >> 1] & 0xffffu))));
+            const float e = r - m4[t];
+            e2 = fmaf(e, e, e2);
+            r2 = fmaf(r, r, r2);
+          }
+        }
+        e2 = warp_sum(e2);
+        r2 = warp_sum(r2);
+        // round the norms UP (they are upper bounds): one ulp covers the fp32 summation error of <= 2048 terms
+        // of one sign only approximately, so scale by (1 + 2^-10)
+        const float en = sqrtf(e2) * 1.001f, rn = sqrtf(r2) * 1.001f;
+        if (lane == 0) {
+          if (op_err != nullptr) op_err[row] = en;
+          if (stats != nullptr) {      // non-negative floats order like their bit patterns
+            atomicMax(stats + 0, __float_as_uint(rn));
+            atomicMax(stats + 1, __float_as_uint(en));
+            atomicMax(stats + 2, __float_as_uint(hyp ? rb : 0.f));
+            atomicMax(stats + 3, __float_as_uint(hyp ? rb * ysq_u : 0.f));
+          }
+        }
+      }
       for (int t = 0; t < ops.n; ++t) {
         uint2* dst = reinterpret_cast<uint2*>(ops.p[t] + row * kpad);
 #pragma unroll
@@ -141,21 +186,21 @@ project_rows_kernel(const float* __restrict__ u, int64_t n, int d, float c, int 
         for (int j = nvec + lane; j < (dpad >> 2); j += 32) dst[j] = make_uint2(0u, 0u);
       }
       if (lane == 0) {
-        __align__(16) __nv_bfloat16 e[HYPRET_KEXT];
-        const __nv_bfloat16 zero = __float2bfloat16_rn(0.f);
+        __align__(16) __half e[HYPRET_KEXT];
+        const __half zero = __float2half_rn(0.f);
 #pragma unroll
         for (int i = 0; i < HYPRET_KEXT; ++i) e[i] = zero;
         if (hyp) {
           if (side == HYPRET_SIDE_QUERY) {
-            __nv_bfloat16 x1, x2, x3;
-            split3(ysq, x1, x2, x3);
-            const __nv_bfloat16 one = __float2bfloat16_rn(1.f);
+            __half x1, x2, x3;
+            split3(ysq_u, x1, x2, x3);
+            const __half one = __float2half_rn(1.f);
             e[0] = x1; e[1] = x1; e[2] = x2; e[3] = x1; e[4] = x2; e[5] = x3;
             e[6] = one; e[7] = one; e[8] = one;
           } else {
-            __nv_bfloat16 r1, r2, r3, b1, b2, b3;
+            __half r1, r2, r3, b1, b2, b3;
             split3(rb, r1, r2, r3);
-            split3(rb * ysq, b1, b2, b3);
+            split3(rb * ysq_u, b1, b2, b3);
             e[0] = r1; e[1] = r2; e[2] = r1; e[3] = r3; e[4] = r2; e[5] = r1;
             e[6] = b1; e[7] = b2; e[8] = b3;
           }
@@ -173,7 +218,7 @@ project_rows_kernel(const float* __restrict__ u, int64_t n, int d, float c, int 
 
 template <int NV>
 int launch(const float* u, int64_t n, int d, float c, int mode, int side, float* y32, const OpDsts& ops, float* sqnorm,
-           cudaStream_t stream) {
+           float* op_err, unsigned* stats, cudaStream_t stream) {
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -183,38 +228,38 @@ int launch(const float* u, int64_t n, int d, float c, int mode, int side, float*
   if (blocks_needed < grid) grid = blocks_needed;
   if (grid < 1) grid = 1;
   project_rows_kernel<NV><<<(unsigned)grid, WARPS_PER_BLOCK * 32, 0, stream>>>(
-      u, n, d, c, mode, side, y32, ops, sqnorm);
+      u, n, d, c, mode, side, y32, ops, sqnorm, op_err, stats);
   return (int)cudaGetLastError();
 }
 
 int dispatch(const float* u, int64_t n, int d, float c, int mode, int side, float* y32, const OpDsts& ops,
-             float* sqnorm, cudaStream_t stream) {
+             float* sqnorm, float* op_err, unsigned* stats, cudaStream_t stream) {
   if (n == 0) return HYPRET_OK;
   const int need = (d + 127) / 128;
-  if (need <= 1) return launch<1>(u, n, d, c, mode, side, y32, ops, sqnorm, stream);
-  if (need <= 2) return launch<2>(u, n, d, c, mode, side, y32, ops, sqnorm, stream);
-  if (need <= 4) return launch<4>(u, n, d, c, mode, side, y32, ops, sqnorm, stream);
-  if (need <= 6) return launch<6>(u, n, d, c, mode, side, y32, ops, sqnorm, stream);
-  if (need <= 8) return launch<8>(u, n, d, c, mode, side, y32, ops, sqnorm, stream);
-  if (need <= 16) return launch<16>(u, n, d, c, mode, side, y32, ops, sqnorm, stream);
+  if (need <= 1) return launch<1>(u, n, d, c, mode, side, y32, ops, sqnorm, op_err, stats, stream);
+  if (need <= 2) return launch<2>(u, n, d, c, mode, side, y32, ops, sqnorm, op_err, stats, stream);
+  if (need <= 4) return launch<4>(u, n, d, c, mode, side, y32, ops, sqnorm, op_err, stats, stream);
+  if (need <= 6) return launch<6>(u, n, d, c, mode, side, y32, ops, sqnorm, op_err, stats, stream);
+  if (need <= 8) return launch<8>(u, n, d, c, mode, side, y32, ops, sqnorm, op_err, stats, stream);
+  if (need <= 16) return launch<16>(u, n, d, c, mode, side, y32, ops, sqnorm, op_err, stats, stream);
   return HYPRET_EINVAL;
 }
 
 }  // namespace
 
 int hypret_launch_project_rows(const float* u, int64_t n, int d, float c, int mode, int side, float* y32,
-                               void* op_bf16, float* sqnorm, cudaStream_t stream) {
+                               void* op_f16, float* sqnorm, float* op_err, float* stats, cudaStream_t stream) {
   OpDsts ops;
-  ops.n = op_bf16 != nullptr ? 1 : 0;
-  ops.p[0] = reinterpret_cast<__nv_bfloat16*>(op_bf16);
-  return dispatch(u, n, d, c, mode, side, y32, ops, sqnorm, stream);
+  ops.n = op_f16 != nullptr ? 1 : 0;
+  ops.p[0] = reinterpret_cast<__half*>(op_f16);
+  return dispatch(u, n, d, c, mode, side, y32, ops, sqnorm, op_err, reinterpret_cast<unsigned*>(stats), stream);
 }
 
 int hypret_launch_project_rows_peers(const float* u, int64_t n, int d, float c, int mode, float* y32,
-                                     void* const* op_dsts_host, int n_dst, cudaStream_t stream) {
+                                     void* const* op_dsts_host, int n_dst, float* op_err, cudaStream_t stream) {
   if (n_dst < 1 || n_dst > HYPRET_MAX_PEERS) return HYPRET_EINVAL;
   OpDsts ops;
   ops.n = n_dst;
-  for (int t = 0; t < n_dst; ++t) ops.p[t] = reinterpret_cast<__nv_bfloat16*>(op_dsts_host[t]);
-  return dispatch(u, n, d, c, mode, HYPRET_SIDE_QUERY, y32, ops, nullptr, stream);
+  for (int t = 0; t < n_dst; ++t) ops.p[t] = reinterpret_cast<__half*>(op_dsts_host[t]);
+  return dispatch(u, n, d, c, mode, HYPRET_SIDE_QUERY, y32, ops, nullptr, op_err, nullptr, stream);
 }

@@ -131,7 +131,7 @@ rerank_kernel(const float* __restrict__ q32, const float* __restrict__ g32, int6
               const int32_t* __restrict__ list_count, int n_cand, int kprime, int k, int64_t idx_offset,
               const float* __restrict__ prune_thr,
               float* __restrict__ out_score, int64_t* __restrict__ out_idx, float* __restrict__ out_margin,
-              const PeerRoute route, int64_t score_off, int64_t idx_off) {
+              const PeerRoute route, int64_t score_off, int64_t idx_off, const CertArgs cert) {
   extern __shared__ uint8_t smem_raw[];
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -238,7 +238,7 @@ rerank_kernel(const float* __restrict__ q32, const float* __restrict__ g32, int6
       const double al = 1.0 - cc * xsq;
       const double t0 = 2.0 * cc * my_s / (al * (1.0 - cc * my_y));
       my_key = log1p(t0 + sqrt(t0 * (t0 + 2.0))) / sqrt(cc);
-      my_sur = my_s / (1.0 - cc * my_y);
+      my_sur = cc * my_s / (1.0 - cc * my_y);          // unit-ball coordinates, like the filter's surrogate
     } else {
       const double nx = sqrt(xsq);
       const double d0 = (nx == 0.0 ? 1.0 : nx) * (my_y == 0.0 ? 1.0 : sqrt(my_y));
@@ -272,13 +272,32 @@ rerank_kernel(const float* __restrict__ q32, const float* __restrict__ g32, int6
     out_score[out_row * k + lane] = valid ? (float)val : ((metric == HYPRET_METRIC_HYPERBOLIC) ? INFINITY : -INFINITY);
     out_idx[out_row * k + lane] = valid ? (int64_t)my_idx + idx_offset : (int64_t)-1;
   }
-  if (out_margin != nullptr) {
+  if (out_margin != nullptr || cert.q_err != nullptr) {
     const double kth = __shfl_sync(0xffffffffu, my_sur, k - 1);
     const int kth_idx = __shfl_sync(0xffffffffu, my_idx, k - 1);
     // +inf: the candidate set was not truncated (fewer than k' valid candidates survive)
     const int n_valid = __popc(__ballot_sync(0xffffffffu, my_idx >= 0));
-    if (lane == 0)
-      out_margin[q] = (n_valid < kprime || kth_idx < 0) ? INFINITY : (float)((double)worst_approx - kth);
+    if (lane == 0) {
+      const bool open_set = n_valid < kprime || kth_idx < 0;
+      const double margin = (double)worst_approx - kth;
+      if (out_margin != nullptr) out_margin[q] = open_set ? INFINITY : (float)margin;
+      if (cert.q_err != nullptr) {
+        // Every row outside the candidate set has a tensor-core surrogate >= worst_approx and an exact surrogate within
+        // E of it, so margin > E proves that none of them precedes the k-th result.  qn = norm of the
+        // query operand's main columns (x on the ball; a unit vector for cosine).
+        const double qn = metric == HYPRET_METRIC_HYPERBOLIC ? sqrt((double)c * xsq) : 1.0;
+        const double zmax = cert.g_stats[0], dzmax = cert.g_stats[1], rbmax = cert.g_stats[2], bmax = cert.g_stats[3];
+        const double E = (double)cert.q_err[q] * zmax + qn * dzmax +
+                         (double)cert.slack * (qn * zmax + qn * qn * rbmax + bmax);
+        const bool ok = open_set || margin > E;
+        if (cert.flags != nullptr) cert.flags[q] = ok ? 1 : 0;
+        if (!ok) {
+          cert.state[2 * q] = 0;
+          cert.state[2 * q + 1] = 0;
+          cert.list[atomicAdd(cert.count, 1)] = (int)q;
+        }
+      }
+    }
   }
 }
 
@@ -483,7 +502,7 @@ rerank_wide_kernel(const float* __restrict__ q32, const float* __restrict__ g32,
           const double al = 1.0 - cc * xsq;
           const double t0 = 2.0 * cc * s0 / (al * (1.0 - cc * y0));
           key0 = log1p(t0 + sqrt(t0 * (t0 + 2.0))) / sqrt(cc);
-          sur0 = s0 / (1.0 - cc * y0);
+          sur0 = cc * s0 / (1.0 - cc * y0);
         } else {
           const double nx = sqrt(xsq);
           const double d0 = (nx == 0.0 ? 1.0 : nx) * (y0 == 0.0 ? 1.0 : sqrt(y0));
@@ -547,10 +566,11 @@ int hypret_launch_rerank(const float* q32, const float* g32, int64_t Q, int64_t 
                          const float* cand_score, const int32_t* cand_idx, const int32_t* list_count, int n_cand,
                          int kprime, int k, int64_t idx_offset, const float* prune_thr, float* out_score,
                          int64_t* out_idx, float* out_margin, const hypret_peer_route* route, int64_t score_off,
-                         int64_t idx_off, const double* g_sq64, cudaStream_t stream) {
+                         int64_t idx_off, const double* g_sq64, const CertArgs& cert, cudaStream_t stream) {
   if (Q == 0) return HYPRET_OK;
   if (kprime > 32 || k > 32 || k > kprime) {
     if (prune_thr != nullptr || (route != nullptr && route->n_ranks > 0)) return HYPRET_EUNSUPPORTED;
+    if (cert.q_err != nullptr) return HYPRET_EUNSUPPORTED;     // the wide path has its own hidden-bound certificate
     const int n_lists = n_cand / kprime;
     int n_pad = RW_SURV;
     while (n_pad < n_cand) n_pad <<= 1;
@@ -603,7 +623,7 @@ int hypret_launch_rerank(const float* q32, const float* g32, int64_t Q, int64_t 
     }                                                                                                               \
     rerank_kernel<NV, PR><<<(unsigned)grid, RR_WARPS * 32, smem, stream>>>(                                         \
         q32, g32, Q, N, d, c, metric, cand_score, cand_idx, list_count, n_cand, kprime, k, idx_offset, prune_thr,   \
-        out_score, out_idx, out_margin, make_route(route), score_off, idx_off);                                     \
+        out_score, out_idx, out_margin, make_route(route), score_off, idx_off, cert);                               \
     return (int)cudaGetLastError();                                                                                 \
   } while (0)
 #define HYPRET_RERANK_LAUNCH(NV)                                                                                    \

@@ -5,7 +5,7 @@
 //   cosine_similarity(Q, G)               /root/reference/notebooks/retrieval.ipynb:368
 //   np.argsort / torch.topk               retrieval.ipynb:383,202 ; src/auxiliary.py:374
 // as a candidate filter: S[i,j] = <q_op[i,:], g_op[j,:]> is the ranking surrogate built by
-// project.cu (rb_j * ||x_i - y_j||^2 for the Poincare ball, -cos for cosine); per query the
+// project.cu (c * rb_j * ||x_i - y_j||^2 for the Poincare ball, -cos for cosine); per query the
 // kernel keeps the k' smallest S of every gallery strip it visits.  S lives only in TMEM and
 // registers.
 //
@@ -14,7 +14,7 @@
 //                           shared-memory ring; the 128-row query tile is loaded ONCE per strip
 //                           and stays resident in shared memory when D <= 512 (RESIDENT),
 //                           otherwise it streams through the ring next to the gallery block
-//   warp 1   MMA issuer     one thread issues tcgen05.mma (M=128, N=256, K=16, bf16 -> fp32)
+//   warp 1   MMA issuer     one thread issues tcgen05.mma (M=128, N=256, K=16, fp16 -> fp32)
 //                           into one of two 256-column TMEM accumulators; tcgen05.commit
 //                           releases ring stages and publishes finished accumulators
 //   warps 2-5 epilogue      tcgen05.ld 32x32b: lane t of a warp owns query row t of its TMEM
@@ -663,7 +663,7 @@ score_topk_kernel(const __grid_constant__ CUtensorMap map_q_main, const __grid_c
     // Warp-uniform control flow; one elected lane issues tcgen05.mma / tcgen05.commit.  The
     // shared-memory descriptors are a constant high word plus (address >> 4): stepping K by 16
     // elements inside the 128-byte swizzle span is "+2" on the low word.
-    constexpr uint32_t idesc = umma_idesc_bf16(PAIR ? 2 * TILE_M : TILE_M, TILE_N);
+    constexpr uint32_t idesc = umma_idesc_f16(PAIR ? 2 * TILE_M : TILE_M, TILE_N);
     constexpr uint64_t DESC_SW128 = (uint64_t(1) << 16) | (uint64_t(1024 >> 4) << 32) | (uint64_t(1) << 46) |
                                     (UMMA_LAYOUT_SW128 << 61);
     constexpr uint64_t DESC_SW32 = (uint64_t(1) << 16) | (uint64_t(256 >> 4) << 32) | (uint64_t(1) << 46) |
@@ -1026,7 +1026,7 @@ EncodeTiledFn get_encode_tiled() {
   return fn;
 }
 
-// 2-D bf16 tensor [rows, kpad] row-major; box = box_cols x box_rows starting at (col, row).
+// 2-D fp16 tensor [rows, kpad] row-major; box = box_cols x box_rows starting at (col, row).
 int make_map(CUtensorMap* map, const void* base, int64_t rows, int kpad, int box_cols, int box_rows,
              CUtensorMapSwizzle swizzle) {
   EncodeTiledFn enc = get_encode_tiled();
@@ -1035,7 +1035,7 @@ int make_map(CUtensorMap* map, const void* base, int64_t rows, int kpad, int box
   cuuint64_t gstride[1] = {(cuuint64_t)kpad * 2};
   cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? HYPRET_OK : HYPRET_EINVAL;

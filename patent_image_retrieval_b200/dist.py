@@ -92,7 +92,7 @@ class PeerQueryExchange:
     """The all-gather of the per-rank query batches, done through peer memory instead of NCCL (csrc/peer.cu).
 
     Every rank owns an exchange buffer that all ranks of the box map over NVLink (CUDA IPC).  ``publish``:
-      1. the projection kernel reads this rank's ``[Ql,D]`` raw rows once and stores each bf16 operand row into the
+      1. the projection kernel reads this rank's ``[Ql,D]`` raw rows once and stores each fp16 operand row into the
          buffers of ALL ranks (posted NVLink stores) -- no rank projects another rank's queries, and the operands
          are in place when the kernel ends;
       2. the exact fp32 rows (needed only by the rerank) follow through the copy engines on a side stream while
@@ -177,7 +177,7 @@ class PeerQueryExchange:
         self.op_all, self.pt_all = [], []
         for s in range(self.SLOTS):
             o = self.FLAGS_BYTES + s * self.slot_bytes
-            self.op_all.append(raw[o:o + self.world * self.op_blk].view(torch.bfloat16).view(self.world * self.ql,
+            self.op_all.append(raw[o:o + self.world * self.op_blk].view(torch.float16).view(self.world * self.ql,
                                                                                               self.kpad))
             o += self.op_bytes
             self.pt_all.append(raw[o:o + self.world * self.pt_blk].view(torch.float32).view(self.world * self.ql,
@@ -208,7 +208,7 @@ class PeerQueryExchange:
 
     def publish(self, q_local: torch.Tensor, c: float, mode: str):
         """Queue projection + exchange of this rank's batch on the current stream.  Returns
-        ``(q_op_all [W*Ql,kpad] bf16, q32_all [W*Ql,D] fp32)`` (rank-major); ``q_op_all`` is complete for whatever is
+        ``(q_op_all [W*Ql,kpad] fp16, q32_all [W*Ql,D] fp32)`` (rank-major); ``q_op_all`` is complete for whatever is
         queued behind this call, ``q32_all`` only behind ``wait_points()``."""
         if tuple(q_local.shape) != (self.ql, self.d) or q_local.dtype != torch.float32 or not q_local.is_cuda:
             raise ValueError(f"expected a CUDA float32 batch of shape [{self.ql}, {self.d}]")
@@ -226,7 +226,7 @@ class PeerQueryExchange:
             cosine = mode == "cosine"
             _lib.check(lib.hypret_project_rows_peers(ctypes.c_void_p(q_local.data_ptr()), self.ql, self.d, float(c),
                                                      ops.MODE[mode], None if cosine else ctypes.c_void_p(my_pt), dsts,
-                                                     W, cur_p))
+                                                     W, None, cur_p))
             if cosine:                         # cosine reranks from the raw rows
                 _lib.check(lib.hypret_peer_copy(ctypes.c_void_p(my_pt), ctypes.c_void_p(q_local.data_ptr()),
                                                 self.pt_blk, cur_p))
@@ -434,7 +434,7 @@ class ShardedGalleryIndex:
             q32, cs, ci, cnt = self.local.score_projected(q32, q_op, k=k, kprime=kprime, kernel_events=kernel_events)
         else:
             q_all = gather_queries(q_local, self.group)
-            q32, cs, ci, cnt = self.local.score_candidates(q_all, k=k, kprime=kprime, kernel_events=kernel_events)
+            q32, cs, ci, cnt, _ = self.local.score_candidates(q_all, k=k, kprime=kprime, kernel_events=kernel_events)
         thr_all = None
         if prune and ex is not None and os.environ.get("HYPRET_PEER_ROUTE", "1") != "0":
             # every exchange is done by the kernel that produces the data (NVLink stores into the receivers'
@@ -461,9 +461,17 @@ class ShardedGalleryIndex:
         return ops.merge_topk(rs, ri, descending=(self.metric == "cosine"))
 
 
+def _explicitly_sharded(sharded: Optional[bool], group) -> bool:
+    """The row-shard collectives of the full-ranking metrics run only when the caller asks for them."""
+    want = bool(sharded) if sharded is not None else group is not None
+    if want and not dist.is_initialized():
+        raise RuntimeError("sharded=True needs an initialised torch.distributed process group")
+    return want and dist.get_world_size(group) > 1
+
+
 def full_ranking_ap(q32: torch.Tensor, shard_rows32: torch.Tensor, pos_offsets: torch.Tensor, pos_items: torch.Tensor,
                     c: float = 1.0, metric: str = "hyperbolic", row_offset: int = 0, n_total: Optional[int] = None,
-                    grouped_ties: bool = True, group=None):
+                    grouped_ties: bool = True, group=None, sharded: Optional[bool] = None):
     """Exact AP over the FULL ranking of every query (reference src/train.py:3259-3293, grouped ties; or
     notebooks/retrieval.ipynb:411-420, index tie-break) without ever forming the [Q,N] score matrix, with the
     gallery row-sharded across ranks ("collective 2").
@@ -471,8 +479,12 @@ def full_ranking_ap(q32: torch.Tensor, shard_rows32: torch.Tensor, pos_offsets: 
     ``q32`` [Q,D] replicated exact query rows (points on the ball / raw features), ``shard_rows32`` this rank's
     gallery rows (global ids ``row_offset ..``), positives as a CSR of GLOBAL gallery ids.  Two all-reduces cross
     NVLink: the [nnz] keys of the (query, positive) pairs (each computed by the shard that owns the positive) and
-    the [nnz,3] rank counts.  Works unsharded too (no process group).  Returns ``(mean_ap, ap [Q], valid [Q])``."""
-    sharded = dist.is_initialized() and dist.get_world_size(group) > 1
+    the [nnz,3] rank counts.  Returns ``(mean_ap, ap [Q], valid [Q])``.
+
+    Sharding is EXPLICIT: the collectives run only with ``sharded=True`` (or a ``group``); a call without either is
+    the unsharded path even inside an initialised multi-rank job -- ``evaluate_retrieval`` passes the whole patent
+    table on every rank, and reducing that would multiply keys and counts by the world size."""
+    sharded = _explicitly_sharded(sharded, group)
     n_total = int(n_total) if n_total is not None else int(shard_rows32.shape[0])
     keys = ops.pair_keys(q32, shard_rows32, pos_offsets, pos_items, c, metric, idx_offset=row_offset)
     if sharded:

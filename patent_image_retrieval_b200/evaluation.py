@@ -18,6 +18,7 @@ from typing import Dict, List, Optional, Sequence
 
 import numpy as np
 import torch
+import torch.nn.functional as F
 
 from . import ops
 from .retrieval import GalleryIndex
@@ -89,15 +90,27 @@ def evaluate_retrieval(model, X_figures_tensor, eval_indices, figure_to_pos_pate
             cand = entry
         else:
             cand = [entry] if entry != -1 else []
-        pos_lists.append([int(p) for p in cand if 0 <= p < num_patents])
+        # target[idx] = 1 in the reference is idempotent: a patent listed twice counts once
+        pos_lists.append(sorted({int(p) for p in cand if 0 <= p < num_patents}))
     offsets, items = _csr_from_lists(pos_lists, device)
 
     # ---- exact one-vs-all distances + sklearn-style AP: rank counting, no [Q,P] matrix, no per-query sync ----
     from .dist import full_ranking_ap
     if items.numel() == 0:
         return 0.0
-    mean_ap, _, valid = full_ranking_ap(figure_embeddings.contiguous(), patents, offsets, items, c=c,
-                                        metric="hyperbolic", n_total=num_patents, grouped_ties=True)
+    figure_embeddings = figure_embeddings.contiguous()
+    if figure_embeddings.shape[1] != patents.shape[1]:
+        return -1.0                                   # the reference's pmath.dist raises -> its except returns -1.0
+    pad = (-patents.shape[1]) % 4                     # the tile kernels read 128-bit chunks: zero columns change nothing
+    if pad:
+        figure_embeddings = F.pad(figure_embeddings, (0, pad))
+        patents = F.pad(patents, (0, pad))
+    try:
+        # always the unsharded path: every rank holds the whole patent table (sharded=False even under torchrun)
+        mean_ap, _, valid = full_ranking_ap(figure_embeddings, patents, offsets, items, c=c, metric="hyperbolic",
+                                            n_total=num_patents, grouped_ties=True, sharded=False)
+    except Exception:
+        return -1.0
     return mean_ap if int(valid.sum().item()) > 0 else 0.0
 
 
@@ -170,21 +183,22 @@ def evaluate_queries(retrieval: ImageRetrieval, query_embeddings, query_names: S
 def full_ranking_metrics(query_rows: torch.Tensor, gallery_rows: torch.Tensor, pos_offsets: torch.Tensor,
                          pos_items: torch.Tensor, n_pos_total: Optional[torch.Tensor] = None, metric: str = "cosine",
                          c: float = 1.0, ks=(5, 10, 20), row_offset: int = 0, n_total: Optional[int] = None,
-                         group=None):
+                         group=None, sharded: Optional[bool] = None):
     """The notebook's whole metric suite over the FULL ranking (retrieval.ipynb:383-456: MRR, MRR@k, Precision@k,
     AP, nDCG, Recall@k) without ranking anything: every one of them is a function of the RANKS of a query's
     positives, and a rank is a count -- ``hypret_rank_count`` (ranking convention: descending similarity /
-    ascending distance, ties -> lower gallery index).  Works on a gallery row-shard per rank (two all-reduces,
-    ``dist.full_ranking_ap``'s collectives).  ``query_rows`` / ``gallery_rows``: raw features (cosine) or points on
+    ascending distance, ties -> lower gallery index).  Works on a gallery row-shard per rank with ``sharded=True`` (two
+    all-reduces, ``dist.full_ranking_ap``'s collectives).  ``query_rows`` / ``gallery_rows``: raw features (cosine) or points on
     the ball (hyperbolic).  Returns ``(means: dict, per_query [Q, 3+3*len(ks)] fp64)`` with the columns of
     ``ops.metric_names(ks)`` -- the layout ``io.evaluation_results`` turns into the reference's results JSON."""
     import torch.distributed as dist
+    from .dist import _explicitly_sharded
     dev = query_rows.device
     Q = query_rows.shape[0]
     n_total = int(n_total) if n_total is not None else int(gallery_rows.shape[0])
     off = pos_offsets.to(dev, torch.int64)
     items = pos_items.to(dev, torch.int64)
-    sharded = dist.is_initialized() and dist.get_world_size(group) > 1
+    sharded = _explicitly_sharded(sharded, group)     # explicit, like dist.full_ranking_ap
     keys = ops.pair_keys(query_rows, gallery_rows, off, items, c, metric, idx_offset=row_offset)
     if sharded:
         dist.all_reduce(keys, op=dist.ReduceOp.SUM, group=group)

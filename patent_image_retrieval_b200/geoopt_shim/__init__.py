@@ -15,24 +15,40 @@ import torch
 from . import pmath  # noqa: F401
 
 
-class PoincareBall:
+class PoincareBall(torch.nn.Module):
     """geoopt.PoincareBall(c): curvature holder + the handful of methods the reference uses
-    (src/models.py:258,360,381,461,520,547,612-634,794,806)."""
+    (src/models.py:258,360,381,461,520,547,612-634,794,806).
+
+    As in geoopt it is an ``nn.Module`` whose curvature lives in the parameter ``isp_c = log(exp(c) - 1)``
+    (``c = softplus(isp_c)``, ``requires_grad = learnable``), so a model that owns a ball has the reference's
+    state-dict keys ``ball.isp_c``, ``encoder.ball.isp_c``, ``encoder.{first,final}_layer.ball.isp_c`` and
+    checkpoints written by the real reference load strictly.  Checkpoints written without those keys (round 1 of
+    this repo kept the ball outside the module tree) load too: a pre-hook fills a missing ``isp_c`` with the
+    constructed value."""
 
     name = "Poincare ball"
     ndim = 1
 
     def __init__(self, c=1.0, learnable=False):
-        self.c = torch.as_tensor(c, dtype=torch.get_default_dtype())
-        self.isp_c = self.c
+        super().__init__()
+        c = torch.as_tensor(c)
+        if not torch.is_floating_point(c):
+            c = c.to(torch.get_default_dtype())
+        with torch.no_grad():
+            isp = c.detach().clone().exp_().sub_(1).log_()
+        self.isp_c = torch.nn.Parameter(isp, requires_grad=bool(learnable))
+        self._register_load_state_dict_pre_hook(self._fill_missing_curvature)
+
+    def _fill_missing_curvature(self, state_dict, prefix, *unused):
+        state_dict.setdefault(prefix + "isp_c", self.isp_c.detach())
+
+    @property
+    def c(self):
+        return torch.nn.functional.softplus(self.isp_c)
 
     @property
     def k(self):
         return -self.c
-
-    def to(self, *args, **kwargs):
-        self.c = self.c.to(*args, **kwargs)
-        return self
 
     def projx(self, x, *, dim=-1):
         return pmath.project(x, k=self.k, dim=dim)

@@ -39,19 +39,30 @@ def operand_kpad(d: int) -> int:
 
 
 def project_rows(u: torch.Tensor, c: float = 1.0, mode: str = "expmap0", side: str = "query",
-                 want_point: bool = True, want_operand: bool = True, want_sqnorm: bool = False):
-    """Fused expmap0/project (or project only, or L2-normalise) + bf16 GEMM operand + ||y||^2.
+                 want_point: bool = True, want_operand: bool = True, want_sqnorm: bool = False,
+                 want_err: bool = False, stats: Optional[torch.Tensor] = None):
+    """Fused expmap0/project (or project only, or L2-normalise) + fp16 GEMM operand + ||y||^2.
 
-    Returns ``(y32 | None, operand | None, sqnorm | None)``.
+    Returns ``(y32 | None, operand | None, sqnorm | None)`` -- with ``want_err`` a fourth element, the ``[n]`` fp32
+    rounding-residual norms of the operand rows; ``stats`` (``[4]`` fp32, zeroed once per gallery) accumulates the
+    gallery maxima.  Both feed the exact-top-k certificate of ``rerank_cert`` (``hypret_project_rows_cert``).
     Mirrors pmath.expmap0 -> pmath.project (reference src/models.py:310,317)."""
-    _need_cuda(u)
+    _need_cuda(u, stats)
     if u.dtype != torch.float32 or u.dim() != 2:
         raise ValueError("u must be a [n, d] float32 tensor")
     u = u.contiguous()
     n, d = u.shape
     y = torch.empty_like(u) if want_point else None
-    op = torch.empty(n, operand_kpad(d), dtype=torch.bfloat16, device=u.device) if want_operand else None
+    op = torch.empty(n, operand_kpad(d), dtype=torch.float16, device=u.device) if want_operand else None
     sq = torch.empty(n, dtype=torch.float32, device=u.device) if want_sqnorm else None
+    if want_err or stats is not None:
+        if stats is not None and (stats.dtype != torch.float32 or stats.numel() != 4 or not stats.is_contiguous()):
+            raise ValueError("stats must be a contiguous [4] float32 CUDA tensor")
+        err = torch.empty(n, dtype=torch.float32, device=u.device) if want_err else None
+        with torch.cuda.device(u.device):
+            _lib.check(_lib.load().hypret_project_rows_cert(_ptr(u), n, d, float(c), MODE[mode], SIDE[side], _ptr(y),
+                                                            _ptr(op), _ptr(sq), _ptr(err), _ptr(stats), _stream()))
+        return (y, op, sq, err) if want_err else (y, op, sq)
     with torch.cuda.device(u.device):
         _lib.check(_lib.load().hypret_project_rows(_ptr(u), n, d, float(c), MODE[mode], SIDE[side], _ptr(y), _ptr(op),
                                                    _ptr(sq), _stream()))
@@ -101,8 +112,8 @@ def score_topk(q_op: torch.Tensor, g_op: torch.Tensor, d: int, kprime: int, max_
     _need_cuda(q_op, g_op, list_count)
     if list_count is not None and (list_count.dtype != torch.int32 or list_count.numel() < q_op.shape[0]):
         raise ValueError("list_count must be an int32 tensor with one entry per query")
-    if q_op.dtype != torch.bfloat16 or g_op.dtype != torch.bfloat16:
-        raise ValueError("operands must be bf16 rows from project_rows")
+    if q_op.dtype != torch.float16 or g_op.dtype != torch.float16:
+        raise ValueError("operands must be fp16 rows from project_rows")
     kpad = operand_kpad(d)
     if q_op.shape[1] != kpad or g_op.shape[1] != kpad or not q_op.is_contiguous() or not g_op.is_contiguous():
         raise ValueError(f"operands must be contiguous [rows, {kpad}]")
@@ -176,6 +187,73 @@ def rerank(q32: torch.Tensor, g32: torch.Tensor, cand_score: torch.Tensor, cand_
                                              int(idx_offset),
                                              _ptr(out_s), _ptr(out_i), _ptr(margin), _ptr(g_sqnorm64), _stream()))
     return (out_s, out_i, margin) if want_margin else (out_s, out_i)
+
+
+class CertBuffers:
+    """Device state of the exact-top-k guarantee for batches of up to ``Q`` queries: the uncertified-query list and its
+    count, the lock words of the fallback merge, and the per-query ``certified`` flags (1 = the filter pass was proven
+    exact, 0 = recomputed by the full scan).  Nothing here is read by the host on the search path."""
+
+    def __init__(self, Q: int, device):
+        self.Q = int(Q)
+        self.state = torch.empty(2 * Q, dtype=torch.int32, device=device)
+        self.count = torch.zeros(1, dtype=torch.int32, device=device)
+        self.list = torch.empty(Q, dtype=torch.int32, device=device)
+        self.certified = torch.empty(Q, dtype=torch.uint8, device=device)
+
+
+def rerank_cert(q32: torch.Tensor, g32: torch.Tensor, cand_score: torch.Tensor, cand_idx: torch.Tensor, c: float,
+                metric: str, k: int, q_err: torch.Tensor, g_stats: torch.Tensor, g_sqnorm64: torch.Tensor,
+                bufs: CertBuffers, idx_offset: int = 0, want_margin: bool = False,
+                list_count: Optional[torch.Tensor] = None, fallback: bool = True):
+    """``rerank`` (k <= k' <= 32) with the exact-top-k guarantee: ``hypret_rerank_cert`` proves per query that no row
+    outside the fp16-filtered candidate set can precede the k-th result, and ``hypret_exact_topk`` -- queued right
+    behind it, reading the list length on the device -- recomputes the queries it could not prove from all gallery
+    rows.  Returns ``(score [Q,k], idx [Q,k][, margin [Q]])``; ``bufs.certified`` / ``bufs.count`` tell what happened.
+    ``fallback=False`` (tests): certificate only."""
+    _need_cuda(q32, g32, cand_score, cand_idx, q_err, g_stats, g_sqnorm64, list_count)
+    q32, g32 = q32.contiguous(), g32.contiguous()
+    Q, d = q32.shape
+    N = g32.shape[0]
+    _, S, kprime = cand_score.shape
+    if bufs.Q < Q:
+        raise ValueError("CertBuffers too small for this batch")
+    out_s = torch.empty(Q, k, dtype=torch.float32, device=q32.device)
+    out_i = torch.empty(Q, k, dtype=torch.int64, device=q32.device)
+    margin = torch.empty(Q, dtype=torch.float32, device=q32.device) if want_margin else None
+    lib = _lib.load()
+    with torch.cuda.device(q32.device):
+        _lib.check(lib.hypret_rerank_cert(_ptr(q32), _ptr(g32), Q, N, d, float(c), METRIC[metric], _ptr(cand_score),
+                                          _ptr(cand_idx), _ptr(list_count), S, kprime, int(k), int(idx_offset),
+                                          _ptr(out_s), _ptr(out_i), _ptr(margin), _ptr(q_err), _ptr(g_stats),
+                                          _ptr(bufs.state), _ptr(bufs.count), _ptr(bufs.list), _ptr(bufs.certified),
+                                          _stream()))
+        if fallback:
+            _lib.check(lib.hypret_exact_topk(_ptr(q32), _ptr(g32), _ptr(g_sqnorm64), Q, N, d, float(c), METRIC[metric],
+                                             int(k), int(idx_offset), _ptr(bufs.list), _ptr(bufs.count),
+                                             _ptr(bufs.state), _ptr(out_s), _ptr(out_i), _stream()))
+    return (out_s, out_i, margin) if want_margin else (out_s, out_i)
+
+
+def exact_topk(q32: torch.Tensor, g32: torch.Tensor, g_sqnorm64: torch.Tensor, c: float, metric: str, k: int,
+               idx_offset: int = 0):
+    """Exact top-k of EVERY query by a full scan (``hypret_exact_topk`` over the identity list): the reference's
+    per-query loop + ``torch.topk`` (src/train.py:3259, src/auxiliary.py:374) as one kernel.  Returns
+    ``(score [Q,k], idx [Q,k])``."""
+    _need_cuda(q32, g32, g_sqnorm64)
+    q32, g32 = q32.contiguous().float(), g32.contiguous().float()
+    Q, d = q32.shape
+    dev = q32.device
+    out_s = torch.empty(Q, k, dtype=torch.float32, device=dev)
+    out_i = torch.empty(Q, k, dtype=torch.int64, device=dev)
+    lst = torch.arange(Q, dtype=torch.int32, device=dev)
+    cnt = torch.full((1,), Q, dtype=torch.int32, device=dev)
+    state = torch.zeros(2 * Q, dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.load().hypret_exact_topk(_ptr(q32), _ptr(g32), _ptr(g_sqnorm64), Q, g32.shape[0], d, float(c),
+                                                 METRIC[metric], int(k), int(idx_offset), _ptr(lst), _ptr(cnt),
+                                                 _ptr(state), _ptr(out_s), _ptr(out_i), _stream()))
+    return out_s, out_i
 
 
 def row_sqnorm64(x: torch.Tensor) -> torch.Tensor:

@@ -7,7 +7,7 @@ Replaces, in the reference:
   * ``ImageRetrieval.retrieve_similar_images``     (notebooks/retrieval.ipynb:190-206)
 
 ``GalleryIndex`` keeps, resident in HBM, the fp32 gallery rows (exact-rerank operand) and
-the bf16 tensor-core operand built by the fused projection kernel.  ``search`` runs
+the fp16 tensor-core operand built by the fused projection kernel.  ``search`` runs
 projection(queries) -> tcgen05 scoring + streaming top-k' -> exact rerank.  All compute is
 in libhypret.so; torch only owns the buffers.
 """
@@ -95,14 +95,19 @@ class GalleryIndex:
         self.idx_offset = int(idx_offset)
         self.device = device
         self.n, self.d = feats.shape
+        # gallery maxima for the exact-top-k certificate (csrc/project.cu): filled by the projection pass itself
+        self.stats = torch.zeros(4, dtype=torch.float32, device=device)
         if metric == "hyperbolic":
             mode = "expmap0" if space == "euclidean" else "onball"
-            self.rows32, self.operand, _ = ops.project_rows(feats, c, mode=mode, side="gallery")
+            self.rows32, self.operand, _ = ops.project_rows(feats, c, mode=mode, side="gallery", stats=self.stats)
         else:
             self.rows32 = feats.contiguous()
-            _, self.operand, _ = ops.project_rows(feats, 1.0, mode="cosine", side="gallery", want_point=False)
-        self.rows_sq64 = ops.row_sqnorm64(self.rows32)       # fp64 row norms for the wide exact rerank (8 B per row)
+            _, self.operand, _ = ops.project_rows(feats, 1.0, mode="cosine", side="gallery", want_point=False,
+                                                  stats=self.stats)
+        self.rows_sq64 = ops.row_sqnorm64(self.rows32)       # fp64 row norms: exact scan, wide exact rerank (8 B per row)
         self._cand = {}
+        self._cert = None
+        self.certificate = None     # CertBuffers of the last exact search (device-side; see ops.rerank_cert)
 
     def _query_mode(self):
         if self.metric == "cosine":
@@ -110,37 +115,50 @@ class GalleryIndex:
         return "expmap0" if self.space == "euclidean" else "onball"
 
     def search(self, queries: torch.Tensor, k: int = 10, kprime: Optional[int] = None, return_margin: bool = False,
-               max_ctas: int = 0, kernel_events: Optional[list] = None):
+               max_ctas: int = 0, kernel_events: Optional[list] = None, exact: bool = True):
         """queries [Q,D] fp32 (host or device) -> (score [Q,k] f32, idx [Q,k] i64) on the device.
         score = Poincare distance ascending, or cosine similarity descending; ties -> lower index.
+
+        ``exact`` (default): the result is GUARANTEED to be the exact top-k (by exact distance; equal fp32 distances
+        in index order).  The fp16 tensor-core pass is only a filter: per query the rerank kernel proves, from the
+        rounding residuals of the operands, that no row outside the candidate set can precede the k-th result, and the
+        queries it cannot prove (near-duplicate galleries) are recomputed by a full exact scan queued on the same
+        stream -- no host synchronisation either way.  ``self.certificate`` (``ops.CertBuffers``) holds the per-query
+        flags and the count of rescanned queries.  k <= 26; wider k returns the filtered result with its own
+        ``margin`` diagnostic.
         ``kernel_events``: a list (receives a (start, end) CUDA-event pair bracketing the scoring kernel
         on the launching stream per call) or a ``StageEvents`` (all three kernels): bench.py's rooflines."""
-        q32, cs, ci, cnt = self.score_candidates(queries, k=k, kprime=kprime, max_ctas=max_ctas,
-                                                 kernel_events=kernel_events)
+        q32, cs, ci, cnt, q_err = self.score_candidates(queries, k=k, kprime=kprime, max_ctas=max_ctas,
+                                                        kernel_events=kernel_events, want_err=exact)
         return self.rerank_candidates(q32, cs, ci, k, return_margin=return_margin, kernel_events=kernel_events,
-                                      list_count=cnt)
+                                      list_count=cnt, q_err=q_err if exact else None)
 
     def score_candidates(self, queries: torch.Tensor, k: int = 10, kprime: Optional[int] = None, max_ctas: int = 0,
-                         kernel_events: Optional[list] = None):
+                         kernel_events: Optional[list] = None, want_err: bool = False):
         """First half of ``search``: projection + tcgen05 scoring / streaming top-k'.
         Returns ``(q32 [Q,D] exact-rerank operand, cand_score [Q,L,k'], cand_idx [Q,L,k'] int32, list_count [Q]
-        int32)``: the lists of query q are its first ``list_count[q]`` slots (compact, arrival order); the other
-        slots hold stale data.  The candidate buffers are reused by the next call."""
+        int32, q_err [Q] | None)``: the lists of query q are its first ``list_count[q]`` slots (compact, arrival
+        order); the other slots hold stale data; ``q_err`` (``want_err``) = rounding-residual norms of the query
+        operand rows for the certificate.  The candidate buffers are reused by the next call."""
         q = queries.to(device=self.device, dtype=torch.float32, non_blocking=True)
         if q.dim() != 2 or q.shape[1] != self.d:
             raise ValueError(f"queries must be [Q, {self.d}]")
         with _span(kernel_events, "project"):
             if self.metric == "hyperbolic":
-                q32, q_op, _ = ops.project_rows(q, self.c, mode=self._query_mode(), side="query")
+                res = ops.project_rows(q, self.c, mode=self._query_mode(), side="query", want_err=want_err)
+                q32, q_op = res[0], res[1]
             else:
                 q32 = q.contiguous()
-                _, q_op, _ = ops.project_rows(q, 1.0, mode="cosine", side="query", want_point=False)
-        return self.score_projected(q32, q_op, k=k, kprime=kprime, max_ctas=max_ctas, kernel_events=kernel_events)
+                res = ops.project_rows(q, 1.0, mode="cosine", side="query", want_point=False, want_err=want_err)
+                q_op = res[1]
+        q_err = res[3] if want_err else None
+        return self.score_projected(q32, q_op, k=k, kprime=kprime, max_ctas=max_ctas,
+                                    kernel_events=kernel_events) + (q_err,)
 
     def score_projected(self, q32: torch.Tensor, q_op: torch.Tensor, k: int = 10, kprime: Optional[int] = None,
                         max_ctas: int = 0, kernel_events: Optional[list] = None):
         """``score_candidates`` for queries that are already projected: ``q32`` the exact-rerank rows, ``q_op`` their
-        bf16 operand rows (``ops.project_rows`` / the peer exchange of ``dist.PeerQueryExchange``)."""
+        fp16 operand rows (``ops.project_rows`` / the peer exchange of ``dist.PeerQueryExchange``)."""
         kprime = default_kprime(k) if kprime is None else int(kprime)
         kprime = min(kprime, ops.MAX_KPRIME)
         wide = k > kprime or k > 32 or kprime > 32
@@ -165,8 +183,19 @@ class GalleryIndex:
 
     def rerank_candidates(self, q32, cand_score, cand_idx, k: int, return_margin: bool = False,
                           prune_thr: Optional[torch.Tensor] = None, kernel_events: Optional[list] = None,
-                          list_count: Optional[torch.Tensor] = None):
-        """Second half of ``search``: candidate merge + exact rerank against this shard's fp32 rows."""
+                          list_count: Optional[torch.Tensor] = None, q_err: Optional[torch.Tensor] = None):
+        """Second half of ``search``: candidate merge + exact rerank against this shard's fp32 rows.  With ``q_err``
+        (and k <= k' <= 32, no pruning): the certified rerank + exact-scan fallback of ``ops.rerank_cert``."""
+        kprime = cand_score.shape[2]
+        if q_err is not None and prune_thr is None and k <= kprime <= 32:
+            n_q = q32.shape[0]
+            if self._cert is None or self._cert.Q < n_q:
+                self._cert = ops.CertBuffers(n_q, self.device)
+            self.certificate = self._cert
+            with _span(kernel_events, "rerank"):
+                return ops.rerank_cert(q32, self.rows32, cand_score, cand_idx, self.c, self.metric, k, q_err,
+                                       self.stats, self.rows_sq64, self._cert, idx_offset=self.idx_offset,
+                                       want_margin=return_margin, list_count=list_count)
         with _span(kernel_events, "rerank"):
             out = ops.rerank(q32, self.rows32, cand_score, cand_idx, self.c, self.metric, k,
                              idx_offset=self.idx_offset, want_margin=return_margin, prune_thr=prune_thr,

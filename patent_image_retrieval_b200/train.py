@@ -201,8 +201,11 @@ def create_n_pair_batch(indices, batch_size, figure_to_pos_figures, X_figures_te
 
 def train_hyperbolic_contrastive(model, X_figures, figure_to_pos_figures, train_indices, val_indices, epochs=1,
                                  batch_size=128, lr=1e-3, temperature=0.07, device=None, save_path="best_model.pt",
-                                 patience=5):
-    """src/train.py:1792-1910 with the double loop replaced by the CUDA distance matrix."""
+                                 patience=5, return_history=False):
+    """src/train.py:1792-1910 with the double loop replaced by the CUDA distance matrix.  Returns the trained model,
+    as the reference does (its caller: ``trained_model = train_hyperbolic_contrastive(...)``, src/train.py:3900);
+    the per-epoch ``(epoch, train_loss, val_loss)`` list is kept on ``model._train_history`` (and returned as a
+    second value only with ``return_history=True``)."""
     device = torch.device(device) if device is not None else torch.device("cuda")
     model = model.to(device)
     model.k = model.k.to(device)
@@ -243,4 +246,5 @@ def train_hyperbolic_contrastive(model, X_figures, figure_to_pos_figures, train_
             model.load_state_dict(torch.load(save_path))
         except Exception:
             pass
-    return model, history
+    model._train_history = history
+    return (model, history) if return_history else model

@@ -39,16 +39,24 @@ def test_dropin_model_loads_reference_state_dict(golden, c):
     from patent_image_retrieval_b200 import models
     tag = str(c).replace(".", "p")
     m = models.FigureOnlyHyperbolicModel(32, 16, hidden_dims=[24], c=c, dropout_rate=0.3).eval()
-    sd = {k: _t(golden, f"refshim_head_{k}_c{tag}") for k in m.state_dict().keys()}
-    assert sorted(sd) == ["encoder.final_layer.bias", "encoder.final_layer.weight", "encoder.first_layer.bias",
-                          "encoder.first_layer.weight"]
-    m.load_state_dict(sd)
+    # geoopt-shaped key set (PoincareBall is an nn.Module there: curvature parameter ``isp_c`` per ball)
+    ball_keys = ["ball.isp_c", "encoder.ball.isp_c", "encoder.final_layer.ball.isp_c", "encoder.first_layer.ball.isp_c"]
+    weight_keys = ["encoder.final_layer.bias", "encoder.final_layer.weight", "encoder.first_layer.bias",
+                   "encoder.first_layer.weight"]
+    assert sorted(m.state_dict().keys()) == sorted(ball_keys + weight_keys)
+    sd = {k: _t(golden, f"refshim_head_{k}_c{tag}") for k in weight_keys}
+    m.load_state_dict(sd)                      # a checkpoint without the curvature keys (round-1 layout) still loads
+    # ... and so does one with them, as the real reference writes it: isp_c = log(exp(c) - 1), 0-dim
+    ref_style = dict(sd, **{k: torch.tensor(c, dtype=torch.float64).exp().sub(1).log() for k in ball_keys})
+    m.load_state_dict(ref_style, strict=True)
+    assert float(m.ball.c) == pytest.approx(c, rel=1e-6) and float(m.encoder.first_layer.ball.k) == pytest.approx(-c, rel=1e-6)
     with torch.no_grad():
         y = m(_t(golden, f"refshim_head_x_c{tag}"))
     torch.testing.assert_close(y, _t(golden, f"refshim_head_y_c{tag}"), rtol=2e-6, atol=1e-7)
     assert m.k.dtype == torch.float32 and "k" not in m.state_dict()
     full = models.HyperbolicEmbeddingModel(32, 16, label_num=7, hidden_dims=[24], c=c)
     assert "label_emb" in full.state_dict() and full.label_emb.shape == (7, 16)
+    assert "ball.isp_c" in full.state_dict() and not full.ball.isp_c.requires_grad
 
 
 def test_oracle_contrastive_matches_reference_train_py(golden):
@@ -127,7 +135,11 @@ def _gloo_worker(rank, world, port, q):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
-    from patent_image_retrieval_b200.dist import gather_candidates, shard_range
+    from patent_image_retrieval_b200.dist import _explicitly_sharded, gather_candidates, shard_range
+    # the full-ranking metrics reduce across ranks only when the caller says the rows are sharded --
+    # evaluate_retrieval (whole patent table on every rank) must stay collective-free under an initialised group
+    assert not _explicitly_sharded(None, None) and not _explicitly_sharded(False, None)
+    assert _explicitly_sharded(True, None) and _explicitly_sharded(None, dist.group.WORLD)
     torch.manual_seed(3)
     Q, N, D, k, c = 12, 301, 16, 5, 1.0
     qu = torch.randn(Q, D) * 0.2

@@ -151,7 +151,7 @@ def test_evaluate_retrieval_dropin_matches_reference(golden):
     f2p = {int(k): v for k, v in json.loads(bytes(golden["refshim_eval_f2p_json"]).decode()).items()}
     X = torch.from_numpy(golden["refshim_eval_X"])
     model = models.HyperbolicEmbeddingModel(32, 16, label_num=60, hidden_dims=[24], c=2.0)
-    sd = {k: torch.from_numpy(np.array(golden["refshim_eval_" + k])).float() for k in model.state_dict().keys()}
+    sd = {k: torch.from_numpy(np.array(golden["refshim_eval_" + k])).float() for k in model.state_dict().keys() if not k.endswith("isp_c")}      # golden: weights; curvature from c
     model.load_state_dict(sd)
     model = model.cuda()
     offsets = {"patents": 0, "medium_cpcs": 45, "big_cpcs": 55, "main_cpcs": 58}
@@ -219,7 +219,7 @@ def test_fused_head_matches_reference_models_py(golden, c):
     tag = str(c).replace(".", "p")
     m = models.FigureOnlyHyperbolicModel(32, 16, hidden_dims=[24], c=c, dropout_rate=0.3).eval()
     m.load_state_dict({k: torch.from_numpy(np.array(golden[f"refshim_head_{k}_c{tag}"])).float()
-                       for k in m.state_dict().keys()})
+                       for k in m.state_dict().keys() if not k.endswith("isp_c")})
     m = m.cuda()
     x = torch.from_numpy(golden[f"refshim_head_x_c{tag}"]).cuda()
     with torch.no_grad():

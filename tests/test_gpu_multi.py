@@ -71,7 +71,11 @@ for grouped in (True, False):
     single_keys = ops.pair_keys(qp, pts, off, items, 1.0, "hyperbolic")
     c1, b1 = ops.rank_count(qp, pts, off, items, single_keys, 1.0, "hyperbolic")
     want = ops.ap_from_counts(off, items, single_keys, c1, b1, N, grouped_ties=grouped)
-    got = full_ranking_ap(qp, pts[lo:hi].contiguous(), off, items, row_offset=lo, n_total=N, grouped_ties=grouped)
+    got = full_ranking_ap(qp, pts[lo:hi].contiguous(), off, items, row_offset=lo, n_total=N, grouped_ties=grouped,
+                          sharded=True)
+    # unsharded call under an initialised multi-rank group: no collective, the single-GPU result
+    solo = full_ranking_ap(qp, pts, off, items, n_total=N, grouped_ties=grouped)
+    assert torch.equal(solo[1], want[1]) and solo[0] == want[0], "unsharded full_ranking_ap under a process group"
     assert torch.equal(got[1], want[1]) and torch.equal(got[2], want[2]) and got[0] == want[0], "full_ranking_ap"
 # sharded negatives: the in-batch InfoNCE over a batch split across the ranks == the single-GPU loss / gradients
 from patent_image_retrieval_b200 import train

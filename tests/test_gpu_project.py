@@ -9,10 +9,10 @@ from patent_image_retrieval_b200 import ops, synth
 pytestmark = pytest.mark.gpu
 
 
-def _bf16_split3(v):
-    a = v.to(torch.bfloat16).float()
-    b = (v - a).to(torch.bfloat16).float()
-    c = (v - a - b).to(torch.bfloat16).float()
+def _f16_split3(v):
+    a = v.to(torch.float16).float()
+    b = (v - a).to(torch.float16).float()
+    c = (v - a - b).to(torch.float16).float()
     return a, b, c
 
 
@@ -37,32 +37,35 @@ def test_expmap0_project_matches_oracle(d, c):
     unclipped = want64.norm(dim=1) < (1 - 5e-3) / c ** 0.5
     assert float(((y.double() - want64)[unclipped].abs().max())) < 1e-6
     torch.testing.assert_close(sq.cpu(), y.pow(2).sum(1), rtol=2e-6, atol=1e-12)
-    # operand row: main columns = bf16(y), padding zero, extension = 3-way split of ||y||^2 and ones
+    # operand row (unit-ball coordinates): main columns = fp16(sqrt(c) y), padding zero, extension = 3-way split of
+    # c ||y||^2 and ones
     kpad = ops.operand_kpad(d)
+    assert op.dtype == torch.float16
     op = op.cpu().float()
     assert op.shape == (777, kpad)
-    torch.testing.assert_close(op[:, :d], y.to(torch.bfloat16).float(), rtol=0, atol=0)
+    sc = torch.tensor(c, dtype=torch.float32).sqrt()
+    torch.testing.assert_close(op[:, :d], (y * sc).to(torch.float16).float(), rtol=0, atol=0)
     assert float(op[:, d:kpad - 16].abs().max() if kpad - 16 > d else 0.0) == 0.0
-    x1, x2, x3 = _bf16_split3(sq.cpu())
+    x1, x2, x3 = _f16_split3(torch.tensor(c, dtype=torch.float32) * sq.cpu())
     ext = op[:, kpad - 16:]
     want_ext = torch.stack([x1, x1, x2, x1, x2, x3] + [torch.ones_like(x1)] * 3 + [torch.zeros_like(x1)] * 7, 1)
     torch.testing.assert_close(ext, want_ext, rtol=0, atol=0)
 
 
 def test_gallery_operand_is_surrogate():
-    """<query operand, gallery operand> == rb_j * ||x_i - y_j||^2 up to bf16 rounding of the main columns."""
-    c, d = 1.0, 512
+    """<query operand, gallery operand> == c * rb_j * ||x_i - y_j||^2 up to fp16 rounding of the main columns."""
+    c, d = 0.6, 512
     u = synth.gaussian_features(64, d, seed=1)
     v = synth.gaussian_features(96, d, seed=0)
     x, q_op, _ = ops.project_rows(u.cuda(), c, "expmap0", "query")
     y, g_op, _ = ops.project_rows(v.cuda(), c, "expmap0", "gallery")
     s = q_op.double() @ g_op.double().t()
     xd, yd = x.double(), y.double()
-    want = torch.cdist(xd, yd).pow(2) / (1 - c * yd.pow(2).sum(1))[None]
-    # error budget: bf16 rounding of both operands on the 2*rb*<x,y> term only
-    assert float((s - want).abs().max()) < 2e-3
+    want = c * torch.cdist(xd, yd).pow(2) / (1 - c * yd.pow(2).sum(1))[None]
+    # error budget: fp16 rounding (2^-11) of both operands on the 2*rb*<x,y> term only
+    assert float((s - want).abs().max()) < 2.5e-4
     ext_only = q_op[:, -16:].double() @ g_op[:, -16:].double().t()
-    want_ext = (xd.pow(2).sum(1)[:, None] + yd.pow(2).sum(1)[None]) / (1 - c * yd.pow(2).sum(1))[None]
+    want_ext = c * (xd.pow(2).sum(1)[:, None] + yd.pow(2).sum(1)[None]) / (1 - c * yd.pow(2).sum(1))[None]
     assert float(((ext_only - want_ext).abs() / want_ext).max()) < 2e-6
 
 
@@ -78,7 +81,7 @@ def test_onball_and_cosine_modes():
     _, opg, _ = ops.project_rows(raw.cuda(), 1.0, "cosine", "gallery", want_point=False)
     nrm = raw.norm(dim=1, keepdim=True)
     unit = raw / torch.where(nrm == 0, torch.ones_like(nrm), nrm)
-    torch.testing.assert_close(opq.cpu().float()[:, :d], unit.to(torch.bfloat16).float(), rtol=1e-2, atol=1e-6)
+    torch.testing.assert_close(opq.cpu().float()[:, :d], unit.to(torch.float16).float(), rtol=2e-3, atol=1e-6)
     torch.testing.assert_close(opg.cpu().float()[:, :d], -opq.cpu().float()[:, :d], rtol=0, atol=0)
     assert float(opq.cpu().float()[:, d:].abs().max()) == 0.0
     assert sq.cpu()[4] == 0.0 and float((sq.cpu()[5:] - 1).abs().max()) == 0.0
@@ -104,14 +107,17 @@ def test_project_rows_to_several_destinations_and_stream_flags():
     u = synth.gaussian_features(n, d, seed=5, scale=1.5).cuda()
     y_ref, op_ref, _ = ops.project_rows(u, c, mode="expmap0", side="query")
     kpad = ops.operand_kpad(d)
-    bufs = [torch.full((3 * n, kpad), 7.0, dtype=torch.bfloat16, device="cuda") for _ in range(3)]
+    bufs = [torch.full((3 * n, kpad), 7.0, dtype=torch.float16, device="cuda") for _ in range(3)]
     y = torch.zeros(n, d, device="cuda")
     arr = (ctypes.c_void_p * 3)(*[b.data_ptr() + n * kpad * 2 for b in bufs])
     stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    err = torch.zeros(n, device="cuda")
     _lib.check(lib.hypret_project_rows_peers(ctypes.c_void_p(u.data_ptr()), n, d, c, ops.MODE["expmap0"],
-                                             ctypes.c_void_p(y.data_ptr()), arr, 3, stream))
+                                             ctypes.c_void_p(y.data_ptr()), arr, 3, ctypes.c_void_p(err.data_ptr()),
+                                             stream))
     torch.cuda.synchronize()
     assert torch.equal(y, y_ref)
+    assert torch.equal(err, ops.project_rows(u, c, mode="expmap0", side="query", want_err=True)[3])
     for b in bufs:
         assert torch.equal(b[n:2 * n], op_ref)
         assert bool((b[:n] == 7.0).all()) and bool((b[2 * n:] == 7.0).all())

@@ -59,7 +59,7 @@ def test_kth_smallest_matches_sort(W, m, kth):
 def test_pruned_rerank_equals_rerank_of_surviving_candidates(metric):
     Q, N, D, kp, k = 150, 5000, 256, 16, 10
     index = GalleryIndex(synth.gaussian_features(N, D, seed=0).cuda(), metric=metric)
-    q32, cs, ci, cnt = index.score_candidates(synth.gaussian_features(Q, D, seed=1).cuda(), k=k, kprime=kp)
+    q32, cs, ci, cnt, _ = index.score_candidates(synth.gaussian_features(Q, D, seed=1).cuda(), k=k, kprime=kp)
     sel_s, sel_i = ops.cand_select(cs, ci, cnt)
     thr = sel_s[:, 5].clone()                          # keep the 6 best (plus surrogate ties) of every query
     thr[3] = float("-inf")                             # a query that loses every candidate on this shard
@@ -88,7 +88,7 @@ def test_pruned_shard_protocol_on_one_gpu_equals_single_index(metric, W):
     for r in range(W):
         lo, hi = shard_range(N, r, W)
         sh = GalleryIndex(g[lo:hi], metric=metric, idx_offset=lo)
-        q32, cs, ci, cnt = sh.score_candidates(q, k=k, kprime=kp)
+        q32, cs, ci, cnt, _ = sh.score_candidates(q, k=k, kprime=kp)
         sel_s, sel_i = ops.cand_select(cs, ci, cnt)
         shards.append(sh)
         staged.append((q32, sel_s, sel_i))
@@ -112,7 +112,7 @@ def test_routed_kernels_store_what_the_collectives_would_deliver():
     W, me, Ql, N, D, kp, k = 3, 1, 70, 4000, 128, 16, 10
     Q = W * Ql
     index = GalleryIndex(synth.gaussian_features(N, D, seed=0).cuda())
-    q32, cs, ci, cnt = index.score_candidates(synth.gaussian_features(Q, D, seed=1).cuda(), k=k, kprime=kp)
+    q32, cs, ci, cnt, _ = index.score_candidates(synth.gaussian_features(Q, D, seed=1).cuda(), k=k, kprime=kp)
     sel_s, sel_i = ops.cand_select(cs, ci, cnt)
     off_sel, off_thr, off_ls, off_li = 0, 1 << 16, 1 << 17, 1 << 18
     bufs = [torch.full((1 << 19,), 255, dtype=torch.uint8, device="cuda") for _ in range(W)]

@@ -8,14 +8,14 @@ Q, N, D, kp, k = 200, 12001, 128, 16, 10
 g = synth.gaussian_features(N, D, seed=0).cuda()
 q = synth.gaussian_features(Q, D, seed=1).cuda()
 full = GalleryIndex(g, metric=metric)
-q32f, csf, cif, cntf = full.score_candidates(q, k=k, kprime=kp)
+q32f, csf, cif, cntf, _ = full.score_candidates(q, k=k, kprime=kp)
 self_s, self_i = ops.cand_select(csf, cif, cntf)
 want_d, want_i = full.rerank_candidates(q32f, csf, cif, k, list_count=cntf)
 staged, shards = [], []
 for r in range(W):
     lo, hi = shard_range(N, r, W)
     sh = GalleryIndex(g[lo:hi], metric=metric, idx_offset=lo)
-    q32, cs, ci, cnt = sh.score_candidates(q, k=k, kprime=kp)
+    q32, cs, ci, cnt, _ = sh.score_candidates(q, k=k, kprime=kp)
     s, i = ops.cand_select(cs, ci, cnt)
     shards.append(sh); staged.append((q32, s, i, lo))
 thr = ops.kth_smallest(torch.stack([s for _, s, _, _ in staged]), kp)
