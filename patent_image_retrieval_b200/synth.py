@@ -38,6 +38,27 @@ def gaussian_features(n: int, d: int, seed: int, device="cpu", scale: float = 0.
     return out
 
 
+GALLERY_BLOCK = 1 << 18
+
+
+def gallery_rows(lo: int, hi: int, d: int, device="cpu", scale: float = 0.45, seed: int = SEED_GALLERY) -> torch.Tensor:
+    """Rows ``[lo, hi)`` of THE bench gallery: ``N(0, (scale/sqrt(d))^2)`` in blocks of 2^18 rows, block b seeded
+    ``seed + 7919 * (b + 1)`` -- so the gallery is the same whatever the number of GPUs it is sharded over (a rank
+    generates the blocks its row range touches).  Reproducible per device type, like ``gaussian_features``."""
+    out = torch.empty(max(hi - lo, 0), d, dtype=torch.float32, device=device)
+    sigma = scale / (d ** 0.5)
+    for b in range(lo // GALLERY_BLOCK, (max(hi, lo + 1) - 1) // GALLERY_BLOCK + 1 if hi > lo else 0):
+        b0 = b * GALLERY_BLOCK
+        r0, r1 = max(lo, b0), min(hi, b0 + GALLERY_BLOCK)
+        if r0 == b0 and r1 == b0 + GALLERY_BLOCK:
+            out[r0 - lo:r1 - lo].normal_(0.0, sigma, generator=_gen(seed + 7919 * (b + 1), device))
+        else:                                     # partial block: generate it whole, keep the slice
+            blk = torch.empty(GALLERY_BLOCK, d, dtype=torch.float32, device=device)
+            blk.normal_(0.0, sigma, generator=_gen(seed + 7919 * (b + 1), device))
+            out[r0 - lo:r1 - lo] = blk[r0 - b0:r1 - b0]
+    return out
+
+
 def clustered_features(n_gallery: int, n_query: int, d: int, device="cpu", per_class: int = 8,
                        noise: float = 0.3, scale: float = 0.45):
     """Returns (gallery_u [N,d], query_u [Q,d], gallery_cls [N] i64, query_cls [Q] i64)."""
