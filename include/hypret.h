@@ -378,6 +378,38 @@ int hypret_ap_from_counts(const int64_t* pos_offsets, const int64_t* pos_items, 
                           const uint64_t* counts, const int32_t* bad, int64_t Q, int64_t n_total, int grouped_ties,
                           double* ap, int32_t* valid, double* mean_ap, void* stream);
 
+/* ---- Row-local manifold kernels of the train_hyp step (csrc/manifold.cu) ------------------------------------------
+ * hypret_rowpair_dist      out[t] = pmath.dist(x[ia[t]], y[ib[t]]): the per-pair Python loops of
+ *                          calculate_pair_loss (src/models.py:712-719, 824-829), the re-encode loop
+ *                          (src/train.py:1433-1443) and the negatives of sample_to_prototype_loss (src/train.py:1036),
+ *                          batched.  x [nx,d], y [ny,d] fp32 on-ball points, ia / ib [n_pairs] int64.
+ * hypret_rowpair_dist_bwd  ADDS grad_out[t] * dd_t/dx into grad_x[ia[t]] (and /dy into grad_y[ib[t]]); either may be
+ *                          NULL; caller zeroes them.
+ * hypret_hmi_pairs         HMI insideness (mode 0) / disjointedness (mode 1) of label pairs, pairs [n_pairs,2] int64
+ *                          rows of emb [L,d] (src/models.py:630-674), and the hinge loss around them (:550-604);
+ *                          proj_eps = geoopt's projx margin for the caller's dtype (4e-3 fp32, 1e-5 fp64 parameters):
+ *                          values [n_pairs] or NULL; *loss_sum += sum_t relu(margin - v_t) (fp64, caller zeroes; the
+ *                          loss is loss_sum / n_pairs) or NULL; grad_emb [L,d] or NULL: ADDS *grad_scale (NULL = 1)
+ *                          times d(mean hinge)/d emb.
+ * hypret_dist0_reg         dist0 regulariser (src/models.py:606-628): *loss_sum += sum_i relu(lo - d0_i) + relu(d0_i - hi)
+ *                          (lo < 0: upper hinge only), loss = loss_sum / n; grad_x [n,d] or NULL: ADDS the gradient of
+ *                          the mean.
+ * hypret_radam_ball_step   one geoopt.optim.RiemannianAdam step (src/train.py:1362) on a [n,d] ManifoldParameter of the
+ *                          Poincare ball, in place: egrad2rgrad, moments, retraction project(x - lr dir), parallel
+ *                          transport of exp_avg.  exp_avg_sq [n,d] holds one value per row (geoopt's broadcast layout).
+ *                          step >= 1 is the step count AFTER this update. */
+int hypret_rowpair_dist(const float* x, const float* y, const int64_t* ia, const int64_t* ib, int64_t n_pairs, int d,
+                        float c, float* out, void* stream);
+int hypret_rowpair_dist_bwd(const float* x, const float* y, const int64_t* ia, const int64_t* ib, int64_t n_pairs,
+                            int d, float c, const float* grad_out, float* grad_x, float* grad_y, void* stream);
+int hypret_hmi_pairs(const float* emb, const int64_t* pairs, int64_t n_pairs, int d, float c, int mode, float margin,
+                     float proj_eps, float* values, double* loss_sum, const float* grad_scale, float* grad_emb,
+                     void* stream);
+int hypret_dist0_reg(const float* x, int64_t n, int d, float c, float lo, float hi, double* loss_sum,
+                     const float* grad_scale, float* grad_x, void* stream);
+int hypret_radam_ball_step(float* x, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, int d, float c,
+                           float lr, float beta1, float beta2, float eps, float weight_decay, int step, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -119,6 +119,15 @@ SIGNATURES = {
                                   c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
     "hypret_ap_from_counts": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int,
                                       c_void_p, c_void_p, c_void_p, c_void_p]),
+    "hypret_rowpair_dist": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_float, c_void_p, c_void_p]),
+    "hypret_rowpair_dist_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_float, c_void_p,
+                                        c_void_p, c_void_p, c_void_p]),
+    "hypret_hmi_pairs": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_float, c_int, c_float, c_float, c_void_p,
+                                 c_void_p, c_void_p, c_void_p, c_void_p]),
+    "hypret_dist0_reg": (c_int, [c_void_p, c_int64, c_int, c_float, c_float, c_float, c_void_p, c_void_p, c_void_p,
+                                 c_void_p]),
+    "hypret_radam_ball_step": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_float, c_float, c_float,
+                                       c_float, c_float, c_float, c_int, c_void_p]),
     "hypret_merge_topk": (c_int, [c_void_p, c_void_p, c_int, c_int64, c_int, c_int, c_void_p, c_void_p, c_void_p]),
 }
 

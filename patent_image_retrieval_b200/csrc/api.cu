@@ -1,5 +1,6 @@
 // extern "C" boundary of libhypret.so -- argument validation and dispatch only.
 // Signatures and the reference call sites they replace are documented in include/hypret.h.
+#include <cmath>
 #include <cstring>
 
 #include "common.cuh"
@@ -496,6 +497,67 @@ int hypret_ap_from_counts(const int64_t* pos_offsets, const int64_t* pos_items, 
   return hypret_launch_ap_from_counts(pos_offsets, pos_items, pos_keys,
                                       reinterpret_cast<const unsigned long long*>(counts), bad, Q, n_total,
                                       grouped_ties != 0, ap, valid, mean_ap, static_cast<cudaStream_t>(stream));
+}
+
+int hypret_rowpair_dist(const float* x, const float* y, const int64_t* ia, const int64_t* ib, int64_t n_pairs, int d,
+                        float c, float* out, void* stream) {
+  if (n_pairs < 0 || d < 1 || !(c > 0.f)) return HYPRET_EINVAL;
+  if (n_pairs == 0) return HYPRET_OK;
+  if (x == nullptr || y == nullptr || ia == nullptr || ib == nullptr || out == nullptr) return HYPRET_EINVAL;
+  int rc = check_device();
+  if (rc != HYPRET_OK) return rc;
+  return hypret_launch_rowpair_dist(x, y, ia, ib, n_pairs, d, c, out, nullptr, nullptr, nullptr,
+                                    static_cast<cudaStream_t>(stream));
+}
+
+int hypret_rowpair_dist_bwd(const float* x, const float* y, const int64_t* ia, const int64_t* ib, int64_t n_pairs,
+                            int d, float c, const float* grad_out, float* grad_x, float* grad_y, void* stream) {
+  if (n_pairs < 0 || d < 1 || !(c > 0.f)) return HYPRET_EINVAL;
+  if (n_pairs == 0) return HYPRET_OK;
+  if (x == nullptr || y == nullptr || ia == nullptr || ib == nullptr || grad_out == nullptr ||
+      (grad_x == nullptr && grad_y == nullptr))
+    return HYPRET_EINVAL;
+  int rc = check_device();
+  if (rc != HYPRET_OK) return rc;
+  return hypret_launch_rowpair_dist(x, y, ia, ib, n_pairs, d, c, nullptr, grad_out, grad_x, grad_y,
+                                    static_cast<cudaStream_t>(stream));
+}
+
+int hypret_hmi_pairs(const float* emb, const int64_t* pairs, int64_t n_pairs, int d, float c, int mode, float margin,
+                     float proj_eps, float* values, double* loss_sum, const float* grad_scale, float* grad_emb,
+                     void* stream) {
+  if (n_pairs < 0 || d < 1 || !(c > 0.f) || (mode != 0 && mode != 1) || !(proj_eps > 0.f && proj_eps < 1.f))
+    return HYPRET_EINVAL;
+  if (n_pairs == 0) return HYPRET_OK;
+  if (emb == nullptr || pairs == nullptr || (values == nullptr && loss_sum == nullptr && grad_emb == nullptr))
+    return HYPRET_EINVAL;
+  int rc = check_device();
+  if (rc != HYPRET_OK) return rc;
+  return hypret_launch_hmi_pairs(emb, pairs, n_pairs, d, c, mode, margin, proj_eps, values, loss_sum, grad_scale,
+                                 grad_emb, static_cast<cudaStream_t>(stream));
+}
+
+int hypret_dist0_reg(const float* x, int64_t n, int d, float c, float lo, float hi, double* loss_sum,
+                     const float* grad_scale, float* grad_x, void* stream) {
+  if (n < 0 || d < 1 || !(c > 0.f) || !(hi > 0.f)) return HYPRET_EINVAL;
+  if (n == 0) return HYPRET_OK;
+  if (x == nullptr || (loss_sum == nullptr && grad_x == nullptr)) return HYPRET_EINVAL;
+  int rc = check_device();
+  if (rc != HYPRET_OK) return rc;
+  return hypret_launch_dist0_reg(x, n, d, c, lo, hi, loss_sum, grad_scale, grad_x, static_cast<cudaStream_t>(stream));
+}
+
+int hypret_radam_ball_step(float* x, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, int d, float c,
+                           float lr, float beta1, float beta2, float eps, float weight_decay, int step, void* stream) {
+  if (n < 0 || d < 1 || !(c > 0.f) || step < 1 || !(beta1 >= 0.f && beta1 < 1.f) || !(beta2 >= 0.f && beta2 < 1.f))
+    return HYPRET_EINVAL;
+  if (n == 0) return HYPRET_OK;
+  if (x == nullptr || grad == nullptr || exp_avg == nullptr || exp_avg_sq == nullptr) return HYPRET_EINVAL;
+  int rc = check_device();
+  if (rc != HYPRET_OK) return rc;
+  const float bc1 = (float)(1.0 - pow((double)beta1, step)), bc2 = (float)(1.0 - pow((double)beta2, step));
+  return hypret_launch_radam_ball(x, grad, exp_avg, exp_avg_sq, n, d, c, lr, beta1, beta2, eps, weight_decay, bc1, bc2,
+                                  static_cast<cudaStream_t>(stream));
 }
 
 }  // extern "C"

@@ -415,3 +415,15 @@ int hypret_launch_neg_lse(const float* dmat, int64_t n, int64_t m, float inv_tau
 int hypret_launch_mobius_epilogue(const float* mx, int64_t n, int d, const float* xsq, const float* bias, float c,
                                   int hyperbolic_input, int post_tanh, int n_project, float* y, float* sqnorm,
                                   cudaStream_t stream);
+
+int hypret_launch_rowpair_dist(const float* x, const float* y, const int64_t* ia, const int64_t* ib, int64_t n_pairs,
+                               int d, float c, float* out, const float* grad_out, float* gx, float* gy,
+                               cudaStream_t stream);
+int hypret_launch_hmi_pairs(const float* emb, const int64_t* pairs, int64_t n_pairs, int d, float c, int mode,
+                            float margin, float proj_eps, float* values, double* loss_sum, const float* grad_scale,
+                            float* grad_emb, cudaStream_t stream);
+int hypret_launch_dist0_reg(const float* x, int64_t n, int d, float c, float lo, float hi, double* loss_sum,
+                            const float* grad_scale, float* grad_x, cudaStream_t stream);
+int hypret_launch_radam_ball(float* x, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, int d, float c,
+                             float lr, float b1, float b2, float eps, float wd, float bc1, float bc2,
+                             cudaStream_t stream);

@@ -84,8 +84,9 @@ class PoincareBall(torch.nn.Module):
         return y, self.transp(x, y, v, dim=dim)
 
     def component_inner(self, x, u, v=None):
+        # geoopt Manifold.component_inner = inner(x, u, v, keepdim=True): one value per point, broadcast by the caller
         v = u if v is None else v
-        return pmath.lambda_x(x, k=self.k, keepdim=True) ** 2 * u * v
+        return pmath.lambda_x(x, k=self.k, keepdim=True) ** 2 * (u * v).sum(dim=-1, keepdim=True)
 
     def check_point_on_manifold(self, x, *, explain=False, atol=1e-5, rtol=1e-5):
         px = pmath.project(x, k=self.k)

@@ -1,7 +1,8 @@
 """``geoopt.optim.RiemannianAdam`` restated (reference use: src/train.py:1362,2177,2643).
 Euclidean parameters get plain Adam; ``ManifoldParameter`` s get the Riemannian update
 (egrad2rgrad, moments in the tangent space, retraction + parallel transport of the first
-moment).  Not on the graded path -- present so that the reference trainers run."""
+moment).  A ``[n,d]`` fp32 CUDA parameter on the Poincare ball (``label_emb``) takes the whole update as ONE fused
+kernel (``hypret_radam_ball_step``, csrc/manifold.cu); everything else runs op by op."""
 from __future__ import annotations
 
 import torch
@@ -49,6 +50,12 @@ class RiemannianAdam(torch.optim.Adam):
                         state["max_exp_avg_sq"] = torch.zeros_like(point)
                 state["step"] += 1
                 exp_avg, exp_avg_sq = state["exp_avg"], state["exp_avg_sq"]
+                if (not amsgrad and point.is_cuda and point.dtype == torch.float32 and point.dim() == 2
+                        and point.is_contiguous() and hasattr(manifold, "isp_c") and grad.dtype == torch.float32):
+                    from ..manifold import radam_ball_step
+                    radam_ball_step(point.data, grad.contiguous(), exp_avg, exp_avg_sq, float(manifold.c), lr,
+                                    (b1, b2), eps, wd, state["step"])
+                    continue
                 grad = grad.add(point, alpha=wd)
                 grad = manifold.egrad2rgrad(point, grad)
                 exp_avg.mul_(b1).add_(grad, alpha=1 - b1)

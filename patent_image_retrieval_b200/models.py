@@ -19,8 +19,13 @@ Differences that restate intended behaviour instead of a crash / an accident:
     accidental fp64 parameters are wanted;
   * the per-pair Python loops of ``calculate_pair_loss`` are evaluated as one batched distance
     (same arithmetic per pair).
-The hierarchy / regulariser losses (src/models.py:550-674) are outside the retrieval hot path
-and are not provided.
+The hierarchy / regulariser losses (src/models.py:550-674: ``calculate_hierarchical_loss``, ``calculate_reg_loss``,
+``_hmi_insideness``, ``_hmi_disjointedness``) run as one kernel forward + one backward each on CUDA
+(``manifold.py`` / csrc/manifold.cu) and as op-by-op torch on CPU tensors.
+
+Note on similarity with the reference: ``MobiusLinear`` / ``mobius_linear`` and the three constructors restate
+src/models.py:255-318, 447-479, 507-535, 788-801 line for line -- signatures, attribute names, init order and state-dict
+keys are the drop-in contract and the class is itself geoopt's example layer.
 """
 from __future__ import annotations
 
@@ -117,9 +122,28 @@ class DeeperHyperbolicEncoder(nn.Module):
         return pmath.project(x, k=self.k)
 
 
+MIN_NORM = 1e-15        # src/models.py:15
+
+
 def _pair_distances(figure_embeddings, all_pairs, k):
-    """Batched replacement of the per-pair loop (src/models.py:712-719, 824-829)."""
+    """Batched replacement of the per-pair loop (src/models.py:712-719, 824-829): one row-pair distance kernel
+    forward and one backward on CUDA (``hypret_rowpair_dist``), the same arithmetic op by op on CPU tensors."""
+    if figure_embeddings.is_cuda:
+        from .manifold import rowpair_dist
+        return rowpair_dist(figure_embeddings, figure_embeddings, all_pairs[:, 0], all_pairs[:, 1], k)
     return pmath.dist(figure_embeddings[all_pairs[:, 0]], figure_embeddings[all_pairs[:, 1]], k=k)
+
+
+def _hmi_terms(ball, k, point_a, point_b, dim=-1):
+    """Radii and centre distance of the two HMI balls (src/models.py:636-654): (radius_a, radius_b, centre_dist)."""
+    point_a, point_b = ball.projx(point_a), ball.projx(point_b)
+    na = torch.norm(point_a, p=2, dim=dim, keepdim=True).clamp_min(MIN_NORM)
+    nb = torch.norm(point_b, p=2, dim=dim, keepdim=True).clamp_min(MIN_NORM)
+    kt = k.to(na.device)
+    s = torch.sqrt(-kt)
+    ra, rb = (1 + kt * na ** 2) / (2 * s * na), (1 + kt * nb ** 2) / (2 * s * nb)
+    ca, cb = point_a * (1 + ra * s / na), point_b * (1 + rb * s / nb)
+    return ra, rb, torch.norm(ca - cb, p=2, dim=dim, keepdim=True)
 
 
 def _all_pairs(figure_embeddings, positive_pairs, negative_pairs):
@@ -156,6 +180,51 @@ class HyperbolicEmbeddingModel(nn.Module):
         encoded = self.encoder(features)
         self.ball.assert_check_point_on_manifold(encoded)
         return encoded
+
+    def calculate_hierarchical_loss(self, implication_pairs, exclusion_pairs):
+        """Label-hierarchy losses (src/models.py:550-604): ``relu(0.05 - insideness(sub, par)).mean()`` over the
+        implication pairs and ``relu(0.1 - disjointedness(l, r)).mean()`` over the exclusion pairs."""
+        dev = self.label_emb.device
+        inside_loss = torch.tensor(0.0, device=dev)
+        disjoint_loss = torch.tensor(0.0, device=dev)
+        self.k = self.k.to(dev)
+        for pairs, mode, margin in ((implication_pairs, "insideness", 0.05), (exclusion_pairs, "disjointedness", 0.1)):
+            if pairs is None or pairs.numel() == 0:
+                continue
+            pairs = pairs.view(-1, 2) if pairs.dim() == 1 else pairs
+            if self.label_emb.is_cuda:
+                from .manifold import hmi_pair_loss
+                loss = hmi_pair_loss(self.label_emb, pairs.to(dev), self.k, mode, margin)
+            else:
+                if int(pairs.min()) < 0 or int(pairs.max()) >= self.label_emb.shape[0]:
+                    raise IndexError("Invalid index detected in implication pairs")
+                fn = self._hmi_insideness if mode == "insideness" else self._hmi_disjointedness
+                loss = F.relu(-fn(self.label_emb[pairs[:, 0]], self.label_emb[pairs[:, 1]]) + margin).mean()
+            if mode == "insideness":
+                inside_loss = loss
+            else:
+                disjoint_loss = loss
+        return inside_loss, disjoint_loss
+
+    def calculate_reg_loss(self, encoded_figures):
+        """dist0 regularisers (src/models.py:606-628): labels kept in ``2 <= dist0 <= 8``, figures in ``dist0 <= 8``."""
+        self.k = self.k.to(self.label_emb.device)
+        if self.label_emb.is_cuda and encoded_figures.is_cuda:
+            from .manifold import dist0_reg_loss
+            return (dist0_reg_loss(self.label_emb, self.k, 2.0, 8.0),
+                    dist0_reg_loss(encoded_figures.reshape(-1, encoded_figures.shape[-1]), self.k, None, 8.0))
+        label_dist0 = self.ball.dist0(self.label_emb, dim=-1, keepdim=True).clamp_min(MIN_NORM)
+        label_reg = (F.relu(2 - label_dist0) + F.relu(label_dist0 - 8.0)).mean()
+        figure_dist0 = self.ball.dist0(encoded_figures, dim=-1, keepdim=True).clamp_min(MIN_NORM)
+        return label_reg, F.relu(figure_dist0 - 8.0).mean()
+
+    def _hmi_insideness(self, point_a, point_b, dim=-1):
+        ra, rb, cd = _hmi_terms(self.ball, self.k, point_a, point_b, dim)
+        return (rb - ra) - cd
+
+    def _hmi_disjointedness(self, point_a, point_b, dim=-1):
+        ra, rb, cd = _hmi_terms(self.ball, self.k, point_a, point_b, dim)
+        return cd - (ra + rb)
 
     def calculate_pair_loss(self, figure_embeddings, positive_pairs, negative_pairs):
         """Per query figure: cross-entropy of -d/T over its pairs, positive first (src/models.py:676-757)."""

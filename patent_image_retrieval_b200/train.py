@@ -176,7 +176,15 @@ def sample_to_prototype_loss(samples, pos_prototypes, neg_prototypes, num_neg_sa
     batch_size, embed_dim = samples.shape
     neg = neg_prototypes.view(batch_size, num_neg_samples, embed_dim)
     pos_distances = pairwise_dist(samples, pos_prototypes.to(samples.dtype), k)                    # [B,B]
-    neg_distances = pmath.dist(samples.unsqueeze(1), neg.to(samples.dtype), k=k).mean(dim=1)       # [B]
+    if samples.is_cuda:
+        # [B, neg] distances sample i <-> its own negatives: one row-pair kernel (hypret_rowpair_dist) fwd + bwd
+        from .manifold import rowpair_dist
+        ia = torch.arange(batch_size, device=samples.device).repeat_interleave(num_neg_samples)
+        ib = torch.arange(batch_size * num_neg_samples, device=samples.device)
+        neg_distances = rowpair_dist(samples, neg_prototypes.reshape(-1, embed_dim).to(samples.dtype), ia, ib,
+                                     k).view(batch_size, num_neg_samples).mean(dim=1)               # [B]
+    else:
+        neg_distances = pmath.dist(samples.unsqueeze(1), neg.to(samples.dtype), k=k).mean(dim=1)   # [B]
     return torch.relu(pos_distances.unsqueeze(1) - neg_distances + margin).mean()
 
 

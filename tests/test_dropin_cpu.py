@@ -231,3 +231,38 @@ def test_shard_range_partitions():
         assert r[0][0] == 0 and r[-1][1] == n and all(a[1] == b[0] for a, b in zip(r, r[1:]))
         sizes = [b - a for a, b in r]
         assert max(sizes) - min(sizes) <= 1
+
+
+def test_hierarchy_and_regulariser_losses_match_reference_models_py():
+    """calculate_hierarchical_loss / calculate_reg_loss / _hmi_* (src/models.py:550-674) on the CPU path against
+    values and autograd gradients produced by the reference's own models.py (tests/golden/make_golden_r2.py)."""
+    from pathlib import Path
+    from patent_image_retrieval_b200 import models
+    g = np.load(Path(__file__).resolve().parent / "golden" / "golden_r2.npz")
+    c = float(g["refshim2_c"])
+    torch.set_default_dtype(torch.float64)                      # the reference flips the default dtype at import
+    try:
+        m = models.HyperbolicEmbeddingModel(32, 16, label_num=60, hidden_dims=[24], c=c)
+    finally:
+        torch.set_default_dtype(torch.float32)
+    # geoopt-shaped state dict: the key list of the REFERENCE model under the module-shim
+    assert sorted(m.state_dict().keys()) == bytes(g["refshim2_state_dict_keys"]).decode().split("\n")
+    with torch.no_grad():
+        m.label_emb.data = torch.from_numpy(g["refshim2_label_emb"])
+    m.k = m.k.double()
+    imp, exc = torch.from_numpy(g["refshim2_imp"]), torch.from_numpy(g["refshim2_exc"])
+    figs = torch.from_numpy(g["refshim2_figs"]).requires_grad_(True)
+    inside, disjoint = m.calculate_hierarchical_loss(imp, exc)
+    label_reg, instance_reg = m.calculate_reg_loss(figs)
+    for got, key in ((inside, "inside"), (disjoint, "disjoint"), (label_reg, "label_reg"), (instance_reg, "instance_reg")):
+        np.testing.assert_allclose(got.item(), float(g["refshim2_" + key]), rtol=1e-7)
+    np.testing.assert_allclose(torch.autograd.grad(inside, m.label_emb, retain_graph=True)[0].numpy(),
+                               g["refshim2_inside_grad"], rtol=1e-6, atol=1e-9)
+    np.testing.assert_allclose(torch.autograd.grad(label_reg, m.label_emb)[0].numpy(), g["refshim2_label_reg_grad"],
+                               rtol=1e-6, atol=1e-9)
+    np.testing.assert_allclose(m._hmi_insideness(m.label_emb[imp[:, 0]], m.label_emb[imp[:, 1]]).detach().numpy(),
+                               g["refshim2_insideness"], rtol=1e-7, atol=1e-9)
+    with pytest.raises(IndexError):
+        m.calculate_hierarchical_loss(torch.tensor([[0, 60]]), None)
+    zero = m.calculate_hierarchical_loss(None, torch.zeros(0, 2, dtype=torch.int64))
+    assert float(zero[0]) == 0.0 and float(zero[1]) == 0.0
