@@ -378,6 +378,36 @@ int hypret_ap_from_counts(const int64_t* pos_offsets, const int64_t* pos_items, 
                           const uint64_t* counts, const int32_t* bad, int64_t Q, int64_t n_total, int grouped_ties,
                           double* ap, int32_t* valid, double* mean_ap, void* stream);
 
+/* ---- Flash-style train_hyp step (csrc/flash.cu): the in-batch InfoNCE over the n x m Poincare distance matrix, forward
+ * and backward, WITHOUT ever writing the matrix (or any other [n,m] array) to memory, all dense products on tcgen05.
+ * Replaces the O(n^2) double loop of 1x1 pmath.dist + autograd (src/train.py:1832-1846; symmetric: 2304-2334).
+ * 16 <= d <= 128, d % 16 == 0 (larger d: hypret_gram_dist / hypret_pairdist_ce_*).
+ *   hypret_flash_kpad(d)      Gram operand row length: roundup(3 d, 64) fp16 elements
+ *   hypret_flash_workspace    fp32 elements of workspace hypret_flash_lse / hypret_flash_grad need for n x m
+ *   hypret_flash_prep         x [n,d] fp32 -> row_op [n,kpad] fp16 ([hi|lo|hi]), col_op [n,kpad] fp16 ([hi|hi|lo]),
+ *                             t_planes [2, d, t_cols] bf16 (transposed hi / mid planes; t_cols >= n, % 8 == 0, columns
+ *                             >= n zero), sqnorm [n]; any output may be NULL
+ *   hypret_flash_lse          lse_out[i] = logsumexp_j(-dist(x_i, y_j) * inv_tau), i < n, j < m
+ *   hypret_flash_grad         dx_out [n,d] = d loss / d x for
+ *                               loss = (gs / n_total) sum_i [ w_rows (x_lse_i - sim_i,t(i)) + w_cols (y_lse_t(i) - sim_i,t(i)) ],
+ *                             sim = -dist * inv_tau, t(i) = i + diag_offset (rows without a target column in [0,m)
+ *                             contribute only their softmax terms), gs = *grad_scale (NULL = 1); x_lse [n] / y_lse [m]
+ *                             natural-log log-sum-exps over the columns of row i / over the rows of column j.
+ *                             One call per operand: d loss / d y is the same call with the roles (and w_rows / w_cols,
+ *                             the two lse arrays, the sign of diag_offset) swapped. */
+int64_t hypret_flash_kpad(int d);
+int64_t hypret_flash_workspace(int64_t n, int64_t m, int d);
+int hypret_flash_prep(const float* x, int64_t n, int d, void* row_op, void* col_op, void* t_planes, int64_t t_cols,
+                      float* sqnorm, void* stream);
+int hypret_flash_lse(const void* x_row_op, const void* y_col_op, const float* x32, const float* y32, const float* xsq,
+                     const float* ysq, int64_t n, int64_t m, int d, float c, float inv_tau, float* workspace,
+                     float* lse_out, void* stream);
+int hypret_flash_grad(const void* x_row_op, const void* y_col_op, const void* y_t_planes, int64_t t_cols,
+                      const float* x32, const float* y32, const float* xsq, const float* ysq, const float* x_lse,
+                      const float* y_lse, int64_t n, int64_t m, int d, float c, float inv_tau, float w_rows,
+                      float w_cols, const float* grad_scale, int64_t diag_offset, int64_t n_total, float* workspace,
+                      float* dx_out, void* stream);
+
 /* ---- Row-local manifold kernels of the train_hyp step (csrc/manifold.cu) ------------------------------------------
  * hypret_rowpair_dist      out[t] = pmath.dist(x[ia[t]], y[ib[t]]): the per-pair Python loops of
  *                          calculate_pair_loss (src/models.py:712-719, 824-829), the re-encode loop

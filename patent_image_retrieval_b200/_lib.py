@@ -119,6 +119,14 @@ SIGNATURES = {
                                   c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
     "hypret_ap_from_counts": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int,
                                       c_void_p, c_void_p, c_void_p, c_void_p]),
+    "hypret_flash_kpad": (c_int64, [c_int]),
+    "hypret_flash_workspace": (c_int64, [c_int64, c_int64, c_int]),
+    "hypret_flash_prep": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p]),
+    "hypret_flash_lse": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int,
+                                 c_float, c_float, c_void_p, c_void_p, c_void_p]),
+    "hypret_flash_grad": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p,
+                                  c_void_p, c_void_p, c_int64, c_int64, c_int, c_float, c_float, c_float, c_float,
+                                  c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_void_p]),
     "hypret_rowpair_dist": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_float, c_void_p, c_void_p]),
     "hypret_rowpair_dist_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_float, c_void_p,
                                         c_void_p, c_void_p, c_void_p]),

@@ -1,6 +1,7 @@
 // extern "C" boundary of libhypret.so -- argument validation and dispatch only.
 // Signatures and the reference call sites they replace are documented in include/hypret.h.
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 
 #include "common.cuh"
@@ -11,6 +12,14 @@ int check_device() {
   int dev = 0, major = 0;
   cudaError_t e = cudaGetDevice(&dev);
   if (e != cudaSuccess) return (int)e;
+  // Driver-API calls (cuTensorMapEncodeTiled) need the primary context CURRENT on the calling thread; a thread that
+  // has only queried the runtime so far (autograd's backward thread) has none yet -> CUDA_ERROR_INVALID_CONTEXT.
+  static thread_local int bound_dev = -1;
+  if (bound_dev != dev) {
+    e = cudaFree(nullptr);
+    if (e != cudaSuccess) return (int)e;
+    bound_dev = dev;
+  }
   e = cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
   if (e != cudaSuccess) return (int)e;
   return major == 10 ? HYPRET_OK : HYPRET_ENOTSM100;
@@ -497,6 +506,62 @@ int hypret_ap_from_counts(const int64_t* pos_offsets, const int64_t* pos_items, 
   return hypret_launch_ap_from_counts(pos_offsets, pos_items, pos_keys,
                                       reinterpret_cast<const unsigned long long*>(counts), bad, Q, n_total,
                                       grouped_ties != 0, ap, valid, mean_ap, static_cast<cudaStream_t>(stream));
+}
+
+int64_t hypret_flash_kpad(int d) { return d > 0 ? hypret_flash_kpad_impl(d) : 0; }
+
+int64_t hypret_flash_workspace(int64_t n, int64_t m, int d) {
+  if (n < 1 || m < 1 || d < 1) return 0;
+  return hypret_flash_workspace_floats(n, m, d);
+}
+
+int hypret_flash_prep(const float* x, int64_t n, int d, void* row_op, void* col_op, void* t_planes, int64_t t_cols,
+                      float* sqnorm, void* stream) {
+  if (n < 0 || d < 16 || (d & 15) || d > 128) return HYPRET_EINVAL;
+  if (n == 0) return HYPRET_OK;
+  if (x == nullptr || !aligned16(row_op) || !aligned16(col_op) || !aligned16(t_planes)) return HYPRET_EINVAL;
+  if (t_planes != nullptr && (t_cols < n || (t_cols & 7))) return HYPRET_EINVAL;
+  int rc = check_device();
+  if (rc != HYPRET_OK) return rc;
+  return hypret_launch_flash_prep(x, n, d, row_op, col_op, t_planes, t_cols, sqnorm, static_cast<cudaStream_t>(stream));
+}
+
+static int flash_common(int bwd, const void* x_row_op, const void* y_col_op, const void* y_t_planes, int64_t t_cols,
+                        const float* x32, const float* y32, const float* xsq, const float* ysq, const float* x_lse,
+                        const float* y_lse, int64_t n, int64_t m, int d, float c, float inv_tau, float wx, float wy,
+                        const float* grad_scale, int64_t diag_offset, int64_t n_total, float* workspace, float* out,
+                        void* stream) {
+  const bool dbg = getenv("HYPRET_DEBUG_FLASH") != nullptr;
+  if (n < 0 || m < 0 || d < 16 || (d & 15) || d > 128 || !(c > 0.f) || !(inv_tau > 0.f)) return dbg ? -11 : HYPRET_EINVAL;
+  if (n == 0 || m == 0) return HYPRET_OK;
+  if (x_row_op == nullptr || y_col_op == nullptr || x32 == nullptr || y32 == nullptr || xsq == nullptr ||
+      ysq == nullptr || workspace == nullptr || out == nullptr || !aligned16(x_row_op) || !aligned16(y_col_op) ||
+      !aligned16(x32) || !aligned16(y32) || !aligned16(workspace) || !aligned16(out))
+    return dbg ? -12 : HYPRET_EINVAL;
+  if (bwd && (y_t_planes == nullptr || !aligned16(y_t_planes) || t_cols < m || (t_cols & 7) || n_total < 1 ||
+              (wx != 0.f && x_lse == nullptr) || (wy != 0.f && y_lse == nullptr)))
+    return dbg ? -13 : HYPRET_EINVAL;
+  int rc = check_device();
+  if (rc != HYPRET_OK) return rc;
+  return hypret_launch_flash(bwd, x_row_op, y_col_op, y_t_planes, t_cols, x32, y32, xsq, ysq, x_lse, y_lse, n, m, d, c,
+                             inv_tau, wx, wy, grad_scale, diag_offset, n_total, workspace, out,
+                             static_cast<cudaStream_t>(stream));
+}
+
+int hypret_flash_lse(const void* x_row_op, const void* y_col_op, const float* x32, const float* y32, const float* xsq,
+                     const float* ysq, int64_t n, int64_t m, int d, float c, float inv_tau, float* workspace,
+                     float* lse_out, void* stream) {
+  return flash_common(0, x_row_op, y_col_op, nullptr, 0, x32, y32, xsq, ysq, nullptr, nullptr, n, m, d, c, inv_tau, 0.f,
+                      0.f, nullptr, 0, 1, workspace, lse_out, stream);
+}
+
+int hypret_flash_grad(const void* x_row_op, const void* y_col_op, const void* y_t_planes, int64_t t_cols,
+                      const float* x32, const float* y32, const float* xsq, const float* ysq, const float* x_lse,
+                      const float* y_lse, int64_t n, int64_t m, int d, float c, float inv_tau, float w_rows,
+                      float w_cols, const float* grad_scale, int64_t diag_offset, int64_t n_total, float* workspace,
+                      float* dx_out, void* stream) {
+  return flash_common(1, x_row_op, y_col_op, y_t_planes, t_cols, x32, y32, xsq, ysq, x_lse, y_lse, n, m, d, c, inv_tau,
+                      w_rows, w_cols, grad_scale, diag_offset, n_total, workspace, dx_out, stream);
 }
 
 int hypret_rowpair_dist(const float* x, const float* y, const int64_t* ia, const int64_t* ib, int64_t n_pairs, int d,

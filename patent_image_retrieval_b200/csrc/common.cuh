@@ -427,3 +427,13 @@ int hypret_launch_dist0_reg(const float* x, int64_t n, int d, float c, float lo,
 int hypret_launch_radam_ball(float* x, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, int d, float c,
                              float lr, float b1, float b2, float eps, float wd, float bc1, float bc2,
                              cudaStream_t stream);
+
+int64_t hypret_flash_kpad_impl(int d);
+int64_t hypret_flash_workspace_floats(int64_t n, int64_t m, int d);
+int hypret_launch_flash_prep(const float* x, int64_t n, int d, void* row_op, void* col_op, void* t_planes, int64_t n_pad,
+                             float* sq, cudaStream_t stream);
+int hypret_launch_flash(int bwd, const void* x_row_op, const void* y_col_op, const void* y_t_planes, int64_t yt_cols,
+                        const float* x32, const float* y32, const float* xsq, const float* ysq, const float* x_lse,
+                        const float* y_lse, int64_t n, int64_t m, int d, float c, float inv_tau, float wx, float wy,
+                        const float* grad_scale, int64_t diag_offset, int64_t n_total, float* workspace, float* out,
+                        cudaStream_t stream);

@@ -480,6 +480,70 @@ def pairdist_ce_fwd(a: torch.Tensor, p: torch.Tensor, c: float, inv_tau: float, 
     return dmat, row_lse, col_lse
 
 
+# ---- flash-style train_hyp step (csrc/flash.cu): no [n,m] array in memory, every dense product on tcgen05 -----------
+FLASH_MAX_D = 128
+FLASH_MIN_PAIRS = 1 << 16
+
+
+def flash_ok(n: int, m: int, d: int) -> bool:
+    """Shapes the flash kernels serve (others use the matrix kernels above)."""
+    return 16 <= d <= FLASH_MAX_D and d % 16 == 0 and n * m >= FLASH_MIN_PAIRS
+
+
+class FlashOperands:
+    """Per-tensor operands of the flash kernels (``hypret_flash_prep``): fp16 2-way split Gram operands in the row and
+    the column layout, transposed bf16 hi/mid planes for the gradient product, squared norms."""
+
+    def __init__(self, x: torch.Tensor, want_row=True, want_col=True, want_t=True):
+        _need_cuda(x)
+        self.x = x.contiguous().float()
+        n, d = self.x.shape
+        lib = _lib.load()
+        kp = int(lib.hypret_flash_kpad(d))
+        dev = x.device
+        self.n, self.d = n, d
+        self.row = torch.empty(n, kp, dtype=torch.float16, device=dev) if want_row else None
+        self.col = torch.empty(n, kp, dtype=torch.float16, device=dev) if want_col else None
+        self.t_cols = (n + 63) // 64 * 64
+        self.t = torch.empty(2, d, self.t_cols, dtype=torch.bfloat16, device=dev) if want_t else None
+        self.sq = torch.empty(n, dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            _lib.check(lib.hypret_flash_prep(_ptr(self.x), n, d, _ptr(self.row), _ptr(self.col), _ptr(self.t),
+                                             self.t_cols, _ptr(self.sq), _stream()))
+
+
+def _flash_workspace(n: int, m: int, d: int, device) -> torch.Tensor:
+    return torch.empty(int(_lib.load().hypret_flash_workspace(n, m, d)), dtype=torch.float32, device=device)
+
+
+def flash_lse(xo: FlashOperands, yo: FlashOperands, c: float, inv_tau: float) -> torch.Tensor:
+    """``lse[i] = logsumexp_j(-dist(x_i, y_j) * inv_tau)`` without the distance matrix (``hypret_flash_lse``)."""
+    out = torch.empty(xo.n, dtype=torch.float32, device=xo.x.device)
+    ws = _flash_workspace(xo.n, yo.n, xo.d, xo.x.device)
+    with torch.cuda.device(xo.x.device):
+        _lib.check(_lib.load().hypret_flash_lse(_ptr(xo.row), _ptr(yo.col), _ptr(xo.x), _ptr(yo.x), _ptr(xo.sq),
+                                                _ptr(yo.sq), xo.n, yo.n, xo.d, float(c), float(inv_tau), _ptr(ws),
+                                                _ptr(out), _stream()))
+    return out
+
+
+def flash_grad(xo: FlashOperands, yo: FlashOperands, c: float, inv_tau: float, x_lse: Optional[torch.Tensor],
+               y_lse: Optional[torch.Tensor], w_rows: float, w_cols: float, grad_scale: Optional[torch.Tensor] = None,
+               diag_offset: int = 0, n_total: Optional[int] = None) -> torch.Tensor:
+    """Gradient of the in-batch InfoNCE with respect to the ROW operand ``x`` (``hypret_flash_grad``); the gradient
+    with respect to ``y`` is the same call with the roles swapped."""
+    out = torch.empty(xo.n, xo.d, dtype=torch.float32, device=xo.x.device)
+    ws = _flash_workspace(xo.n, yo.n, xo.d, xo.x.device)
+    gs = grad_scale.reshape(1).contiguous().float() if grad_scale is not None else None
+    with torch.cuda.device(xo.x.device):
+        _lib.check(_lib.load().hypret_flash_grad(_ptr(xo.row), _ptr(yo.col), _ptr(yo.t), yo.t_cols, _ptr(xo.x),
+                                                 _ptr(yo.x), _ptr(xo.sq), _ptr(yo.sq), _ptr(x_lse), _ptr(y_lse), xo.n,
+                                                 yo.n, xo.d, float(c), float(inv_tau), float(w_rows), float(w_cols),
+                                                 _ptr(gs), int(diag_offset), int(xo.n if n_total is None else n_total),
+                                                 _ptr(ws), _ptr(out), _stream()))
+    return out
+
+
 BWD_ROWS = 16       # HYPRET_BWD_ROWS: matrix rows per CTA of the backward pass (one col_partial row each)
 
 

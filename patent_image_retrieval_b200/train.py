@@ -61,10 +61,21 @@ def pairwise_dist(a, p, k):
     return PairwiseDistance.apply(a, p, _c_of(k))
 
 
+def _diag_distance(a32, p32, c: float, offset: int = 0):
+    """Exact d(a_i, p_{i+offset}) for every local row (``hypret_rowpair_dist``, fp64 inside): the targets' logits."""
+    from .manifold import RowPairDistance
+    ia = torch.arange(a32.shape[0], device=a32.device)
+    return RowPairDistance.apply(a32.detach(), p32.detach(), ia, ia + offset, c)
+
+
 class InBatchInfoNCE(torch.autograd.Function):
     """CE over the rows (``symmetric=False``) or rows and columns (``True``) of ``-D / tau`` with the diagonal as
-    targets, D the n x n Poincare distance matrix -- forward and backward in libhypret.so: no torch softmax /
-    cross-entropy passes over the [n,n] matrix and no upstream-gradient matrix (``hypret_pairdist_ce_fwd/bwd``)."""
+    targets, D the n x n Poincare distance matrix -- forward and backward in libhypret.so.
+
+    Flash path (16 <= D <= 128, D % 16 == 0; csrc/flash.cu): D is NEVER written to memory.  Forward = row (and column)
+    log-sum-exps from tcgen05 Gram tiles; backward = the tiles recomputed, the weights W formed in registers, written
+    to shared memory as bf16 planes and multiplied by the other operand with a second tcgen05.mma (one launch per
+    operand, roles swapped).  Other shapes: the matrix kernels (``hypret_pairdist_ce_fwd/bwd`` + split products)."""
 
     @staticmethod
     def forward(ctx, a, p, c: float, temperature: float, symmetric: bool):
@@ -72,6 +83,24 @@ class InBatchInfoNCE(torch.autograd.Function):
         if a32.shape != p32.shape:
             raise ValueError("anchors and positives must have the same shape")
         inv_tau = 1.0 / float(temperature)
+        n, d = a32.shape
+        ctx.flash = TENSOR_CORES and ops.flash_ok(n, n, d)
+        if ctx.flash:
+            need_grad = ctx.needs_input_grad[0] or ctx.needs_input_grad[1]
+            ao = ops.FlashOperands(a32, want_col=symmetric or need_grad, want_t=need_grad)
+            po = ops.FlashOperands(p32, want_row=symmetric or need_grad, want_t=need_grad)
+            row_lse = ops.flash_lse(ao, po, c, inv_tau)
+            diag_sim = -_diag_distance(a32, p32, c) * inv_tau
+            loss = (row_lse - diag_sim).mean()
+            col_lse = None
+            if symmetric:
+                col_lse = ops.flash_lse(po, ao, c, inv_tau)
+                loss = (loss + (col_lse - diag_sim).mean()) / 2
+            ctx.ops = (ao, po)
+            ctx.save_for_backward(row_lse, col_lse if symmetric else row_lse)
+            ctx.c, ctx.inv_tau, ctx.symmetric = c, inv_tau, symmetric
+            ctx.in_dtypes = (a.dtype, p.dtype)
+            return loss
         d, row_lse, col_lse = ops.pairdist_ce_fwd(a32, p32, c, inv_tau, want_cols=symmetric,
                                                   tensor_cores=None if TENSOR_CORES else False)
         diag_sim = -torch.diagonal(d) * inv_tau
@@ -85,8 +114,15 @@ class InBatchInfoNCE(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, grad_loss):
-        a, p, d, row_lse, col_lse = ctx.saved_tensors
         wr, wc = (0.5, 0.5) if ctx.symmetric else (1.0, 0.0)
+        if ctx.flash:
+            row_lse, col_lse = ctx.saved_tensors
+            ao, po = ctx.ops
+            cl = col_lse if ctx.symmetric else None
+            da = ops.flash_grad(ao, po, ctx.c, ctx.inv_tau, row_lse, cl, wr, wc, grad_scale=grad_loss)
+            dp = ops.flash_grad(po, ao, ctx.c, ctx.inv_tau, cl, row_lse, wc, wr, grad_scale=grad_loss)
+            return da.to(ctx.in_dtypes[0]), dp.to(ctx.in_dtypes[1]), None, None, None
+        a, p, d, row_lse, col_lse = ctx.saved_tensors
         split = TENSOR_CORES and d.numel() >= ops.SPLIT_MIN_PAIRS
         w, rs, cs = ops.pairdist_ce_bwd(d, ops.row_sqnorm(a), ops.row_sqnorm(p), ctx.c, row_lse,
                                         col_lse if ctx.symmetric else None, ctx.inv_tau, wr, wc, grad_scale=grad_loss,
