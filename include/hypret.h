@@ -395,6 +395,9 @@ int hypret_ap_from_counts(const int64_t* pos_offsets, const int64_t* pos_items, 
  *                             natural-log log-sum-exps over the columns of row i / over the rows of column j.
  *                             One call per operand: d loss / d y is the same call with the roles (and w_rows / w_cols,
  *                             the two lse arrays, the sign of diag_offset) swapped. */
+/* out[j] = ln sum_r exp(parts[r, j]), parts [n_parts, n] fp32: the column log-sum-exps of a batch whose rows are
+ * sharded across ranks, from the per-rank partials (train.ShardedInBatchInfoNCE). */
+int hypret_lse_combine(const float* parts, int n_parts, int64_t n, float* out, void* stream);
 int64_t hypret_flash_kpad(int d);
 int64_t hypret_flash_workspace(int64_t n, int64_t m, int d);
 int hypret_flash_prep(const float* x, int64_t n, int d, void* row_op, void* col_op, void* t_planes, int64_t t_cols,

@@ -531,16 +531,15 @@ static int flash_common(int bwd, const void* x_row_op, const void* y_col_op, con
                         const float* y_lse, int64_t n, int64_t m, int d, float c, float inv_tau, float wx, float wy,
                         const float* grad_scale, int64_t diag_offset, int64_t n_total, float* workspace, float* out,
                         void* stream) {
-  const bool dbg = getenv("HYPRET_DEBUG_FLASH") != nullptr;
-  if (n < 0 || m < 0 || d < 16 || (d & 15) || d > 128 || !(c > 0.f) || !(inv_tau > 0.f)) return dbg ? -11 : HYPRET_EINVAL;
+  if (n < 0 || m < 0 || d < 16 || (d & 15) || d > 128 || !(c > 0.f) || !(inv_tau > 0.f)) return HYPRET_EINVAL;
   if (n == 0 || m == 0) return HYPRET_OK;
   if (x_row_op == nullptr || y_col_op == nullptr || x32 == nullptr || y32 == nullptr || xsq == nullptr ||
       ysq == nullptr || workspace == nullptr || out == nullptr || !aligned16(x_row_op) || !aligned16(y_col_op) ||
       !aligned16(x32) || !aligned16(y32) || !aligned16(workspace) || !aligned16(out))
-    return dbg ? -12 : HYPRET_EINVAL;
+    return HYPRET_EINVAL;
   if (bwd && (y_t_planes == nullptr || !aligned16(y_t_planes) || t_cols < m || (t_cols & 7) || n_total < 1 ||
               (wx != 0.f && x_lse == nullptr) || (wy != 0.f && y_lse == nullptr)))
-    return dbg ? -13 : HYPRET_EINVAL;
+    return HYPRET_EINVAL;
   int rc = check_device();
   if (rc != HYPRET_OK) return rc;
   return hypret_launch_flash(bwd, x_row_op, y_col_op, y_t_planes, t_cols, x32, y32, xsq, ysq, x_lse, y_lse, n, m, d, c,
@@ -562,6 +561,15 @@ int hypret_flash_grad(const void* x_row_op, const void* y_col_op, const void* y_
                       float* dx_out, void* stream) {
   return flash_common(1, x_row_op, y_col_op, y_t_planes, t_cols, x32, y32, xsq, ysq, x_lse, y_lse, n, m, d, c, inv_tau,
                       w_rows, w_cols, grad_scale, diag_offset, n_total, workspace, dx_out, stream);
+}
+
+int hypret_lse_combine(const float* parts, int n_parts, int64_t n, float* out, void* stream) {
+  if (n_parts < 1 || n < 0) return HYPRET_EINVAL;
+  if (n == 0) return HYPRET_OK;
+  if (parts == nullptr || out == nullptr) return HYPRET_EINVAL;
+  int rc = check_device();
+  if (rc != HYPRET_OK) return rc;
+  return hypret_launch_lse_combine(parts, n_parts, n, out, static_cast<cudaStream_t>(stream));
 }
 
 int hypret_rowpair_dist(const float* x, const float* y, const int64_t* ia, const int64_t* ib, int64_t n_pairs, int d,

@@ -437,3 +437,4 @@ int hypret_launch_flash(int bwd, const void* x_row_op, const void* y_col_op, con
                         const float* y_lse, int64_t n, int64_t m, int d, float c, float inv_tau, float wx, float wy,
                         const float* grad_scale, int64_t diag_offset, int64_t n_total, float* workspace, float* out,
                         cudaStream_t stream);
+int hypret_launch_lse_combine(const float* parts, int w, int64_t n, float* out, cudaStream_t stream);

@@ -37,8 +37,10 @@ namespace {
 
 constexpr int FT_M = 128;                 // rows per tile (TMEM lanes)
 constexpr int FT_N = 128;                 // columns per tile
-constexpr int F_THREADS = 320;            // warp 0 TMA, warp 1 MMA, warps 2-9 epilogue (two warpgroups)
-constexpr int F_EPI = 256;
+constexpr int F_NWG = 2;                  // epilogue warpgroups: each takes FT_N / F_NWG columns of every tile
+constexpr int F_CW = FT_N / F_NWG;        // columns per warpgroup and tile (a multiple of 32)
+constexpr int F_EPI = 128 * F_NWG;
+constexpr int F_THREADS = 64 + F_EPI;     // warp 0 TMA, warp 1 MMA, then the epilogue warpgroups
 constexpr int F_STAGES_FWD = 4, F_STAGES_BWD = 2;
 constexpr int FA_BLK = FT_M * HYPRET_KBLK * 2;      // 16 KB: one K-block of the row operand
 constexpr int FB_BLK = FT_N * HYPRET_KBLK * 2;      // 16 KB: ... of the column operand
@@ -121,9 +123,10 @@ struct FParams {
   float coef;                              // BWD: 1 / (tau n_total)
   int64_t diag_offset;                     // the target of row i is column i + diag_offset
   int n_rt, n_ct, n_slots;
-  float* part;                             // FWD: [n_rt, n_slots, 2, 2, 128] (max, sum); BWD: [n_slots, n_rt*128, d]
-  float* part_rs;                          // BWD: [n_slots, 2, n_rt*128] partial row sums
+  float* part;                             // FWD: [n_rt, n_slots, F_NWG, 2, 128] (max, sum); BWD: [n_slots, n_rt*128, d]
+  float* part_rs;                          // BWD: [n_slots, F_NWG, n_rt*128] partial row sums
   int64_t yt_cols;                         // BWD: padded column count of the transposed planes
+  unsigned long long* stats;               // HYPRET_FLASH_STATS=1: [grid][8] wait-cycle counters of epilogue warp 2, or NULL
 };
 
 __device__ __forceinline__ float ex2_approx(float x) {
@@ -174,22 +177,38 @@ __device__ __forceinline__ float chunk_sqdist(float (&v)[32], const float4* __re
   return smin;
 }
 
-// forward: v[] <- L = lg2(z + sqrt(z^2 - 1)), z - 1 = s (2c/beta) / alpha; returns min L  (logit = -kappa L, log2 units)
+// The arithmetic below is written STAGE-WISE over sub-chunks of F_SUB entries (F_SUB independent instructions per
+// stage), so that no instruction waits on the one before it.  Measured (ncu, n = 8192, D = 128): 23 warp instructions
+// per entry in the forward pass, issue slots 48 % busy, XU (rsqrt / lg2 / ex2) 53 %, FMA 25 %, ALU 23 %, tensor 25 %:
+// the pass is latency-bound with 2.5 resident warps per scheduler, not bound by any one pipe; neither four epilogue
+// warpgroups (96 registers, spills) nor other block sizes (4 / 16) moved it.
+//
+// forward: v[] <- L = lg2(z + sqrt(z^2 - 1)), z = 1 + s (2c/beta) / alpha; returns min L  (logit = -kappa L, log2 units)
+constexpr int F_SUB = 8;                  // entries per stage block (see above); multiple of 4, divides 32
+
 __device__ __forceinline__ float chunk_logits(float (&v)[32], const float4* __restrict__ ca, float rho) {
   float lmin = INFINITY;
 #pragma unroll
-  for (int j4 = 0; j4 < 8; ++j4) {
-    const float4 a1 = ca[j4];
-    const float aa[4] = {a1.x, a1.y, a1.z, a1.w};
+  for (int h = 0; h < 32 / F_SUB; ++h) {
+    float z[F_SUB], q[F_SUB];
 #pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      const int j = 4 * j4 + e;
-      const float tt = v[j] * (aa[e] * rho);
-      const float q = fmaxf(fmaf(tt, tt, tt + tt), 1e-30f);
-      const float L = lg2_approx(1.0f + tt + q * rsqrt_approx(q));
-      v[j] = L;
-      lmin = fminf(lmin, L);
+    for (int j4 = 0; j4 < F_SUB / 4; ++j4) {
+      const float4 a1 = ca[(F_SUB / 4) * h + j4];
+      z[4 * j4 + 0] = v[F_SUB * h + 4 * j4 + 0] * (a1.x * rho);          // z - 1
+      z[4 * j4 + 1] = v[F_SUB * h + 4 * j4 + 1] * (a1.y * rho);
+      z[4 * j4 + 2] = v[F_SUB * h + 4 * j4 + 2] * (a1.z * rho);
+      z[4 * j4 + 3] = v[F_SUB * h + 4 * j4 + 3] * (a1.w * rho);
     }
+#pragma unroll
+    for (int j = 0; j < F_SUB; ++j) q[j] = fmaxf(fmaf(z[j], z[j], z[j] + z[j]), 1e-30f);      // z^2 - 1 without cancellation
+#pragma unroll
+    for (int j = 0; j < F_SUB; ++j) q[j] *= rsqrt_approx(q[j]);          // sqrt(z^2 - 1)
+#pragma unroll
+    for (int j = 0; j < F_SUB; ++j) z[j] = (1.0f + z[j]) + q[j];
+#pragma unroll
+    for (int j = 0; j < F_SUB; ++j) z[j] = lg2_approx(z[j]);
+#pragma unroll
+    for (int j = 0; j < F_SUB; ++j) { v[F_SUB * h + j] = z[j]; lmin = fminf(lmin, z[j]); }
   }
   return lmin;
 }
@@ -204,37 +223,59 @@ __device__ __forceinline__ void chunk_weights(const float (&v)[32], const float4
                                               float gx, float gy, float gd, int dj, float& rowsum, uint32_t (&hp)[16],
                                               uint32_t (&mp)[16]) {
 #pragma unroll
-  for (int j4 = 0; j4 < 8; ++j4) {
-    const float4 a1 = ca[j4];
-    const float aa[4] = {a1.x, a1.y, a1.z, a1.w};
-    float ll[4] = {0.f, 0.f, 0.f, 0.f};
-    if (COLS) { const float4 l4 = cl[j4]; ll[0] = l4.x; ll[1] = l4.y; ll[2] = l4.z; ll[3] = l4.w; }
-    float w[4];
+  for (int h = 0; h < 32 / F_SUB; ++h) {
+    float ar[F_SUB], z[F_SUB], q[F_SUB], g[F_SUB];
 #pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      const int j = 4 * j4 + e;
-      const float ar = aa[e] * rho;
-      const float tt = v[j] * ar;
-      const float q = fmaxf(fmaf(tt, tt, tt + tt), 1e-30f);
-      const float r = rsqrt_approx(q);
-      const float L = lg2_approx(1.0f + tt + q * r);
-      // softmax probabilities are <= 1: the clamp changes nothing for real entries, and keeps the padding columns
-      // (logit 0 against a possibly very negative log-sum-exp) from overflowing into inf * 0
-      float g = gx * ex2_approx(fminf(fmaf(-kappa, L, -lx), 0.f));
-      if (COLS) g = fmaf(gy, ex2_approx(fminf(fmaf(-kappa, L, -ll[e]), 0.f)), g);
-      if (DIAG) g += j == dj ? gd : 0.f;
-      w[e] = g * r * ar;
+    for (int j4 = 0; j4 < F_SUB / 4; ++j4) {
+      const float4 a1 = ca[(F_SUB / 4) * h + j4];
+      ar[4 * j4 + 0] = a1.x * rho; ar[4 * j4 + 1] = a1.y * rho; ar[4 * j4 + 2] = a1.z * rho; ar[4 * j4 + 3] = a1.w * rho;
     }
 #pragma unroll
-    for (int e = 0; e < 4; e += 2) {
-      const __nv_bfloat162 h = __floats2bfloat162_rn(w[e], w[e + 1]);
-      const float h0 = __low2float(h), h1 = __high2float(h);
-      const __nv_bfloat162 md = __floats2bfloat162_rn(w[e] - h0, w[e + 1] - h1);
-      hp[2 * j4 + (e >> 1)] = *reinterpret_cast<const uint32_t*>(&h);
-      mp[2 * j4 + (e >> 1)] = *reinterpret_cast<const uint32_t*>(&md);
-      rowsum = fmaf(h0 + __low2float(md), fmaf(crho, v[4 * j4 + e], 1.0f), rowsum);
-      rowsum = fmaf(h1 + __high2float(md), fmaf(crho, v[4 * j4 + e + 1], 1.0f), rowsum);
+    for (int j = 0; j < F_SUB; ++j) z[j] = v[F_SUB * h + j] * ar[j];          // z - 1
+#pragma unroll
+    for (int j = 0; j < F_SUB; ++j) q[j] = fmaxf(fmaf(z[j], z[j], z[j] + z[j]), 1e-30f);      // z^2 - 1 without cancellation
+#pragma unroll
+    for (int j = 0; j < F_SUB; ++j) g[j] = rsqrt_approx(q[j]);            // 1 / sqrt(z^2 - 1)
+#pragma unroll
+    for (int j = 0; j < F_SUB; ++j) { z[j] = (1.0f + z[j]) + q[j] * g[j]; ar[j] *= g[j]; }    // z + sqrt(z^2-1);  ar / sqrt(z^2-1)
+#pragma unroll
+    for (int j = 0; j < F_SUB; ++j) z[j] = lg2_approx(z[j]);
+    // softmax probabilities are <= 1: the clamp changes nothing for real entries, and keeps the padding columns
+    // (logit 0 against a possibly very negative log-sum-exp) from overflowing into inf * 0
+#pragma unroll
+    for (int j = 0; j < F_SUB; ++j) q[j] = fminf(fmaf(-kappa, z[j], -lx), 0.f);
+#pragma unroll
+    for (int j = 0; j < F_SUB; ++j) g[j] = gx * ex2_approx(q[j]);
+    if (COLS) {
+#pragma unroll
+      for (int j4 = 0; j4 < F_SUB / 4; ++j4) {
+        const float4 l4 = cl[(F_SUB / 4) * h + j4];
+        q[4 * j4 + 0] = fminf(fmaf(-kappa, z[4 * j4 + 0], -l4.x), 0.f);
+        q[4 * j4 + 1] = fminf(fmaf(-kappa, z[4 * j4 + 1], -l4.y), 0.f);
+        q[4 * j4 + 2] = fminf(fmaf(-kappa, z[4 * j4 + 2], -l4.z), 0.f);
+        q[4 * j4 + 3] = fminf(fmaf(-kappa, z[4 * j4 + 3], -l4.w), 0.f);
+      }
+#pragma unroll
+      for (int j = 0; j < F_SUB; ++j) g[j] = fmaf(gy, ex2_approx(q[j]), g[j]);
     }
+    if (DIAG) {
+#pragma unroll
+      for (int j = 0; j < F_SUB; ++j) g[j] += (F_SUB * h + j) == dj ? gd : 0.f;
+    }
+#pragma unroll
+    for (int j = 0; j < F_SUB; ++j) g[j] *= ar[j];                        // w
+#pragma unroll
+    for (int j = 0; j < F_SUB; j += 2) {
+      const __nv_bfloat162 hh = __floats2bfloat162_rn(g[j], g[j + 1]);
+      const float h0 = __low2float(hh), h1 = __high2float(hh);
+      const __nv_bfloat162 md = __floats2bfloat162_rn(g[j] - h0, g[j + 1] - h1);
+      hp[(F_SUB / 2) * h + (j >> 1)] = *reinterpret_cast<const uint32_t*>(&hh);
+      mp[(F_SUB / 2) * h + (j >> 1)] = *reinterpret_cast<const uint32_t*>(&md);
+      z[j] = h0 + __low2float(md);
+      z[j + 1] = h1 + __high2float(md);
+    }
+#pragma unroll
+    for (int j = 0; j < F_SUB; ++j) rowsum = fmaf(z[j], fmaf(crho, v[F_SUB * h + j], 1.0f), rowsum);
   }
 }
 
@@ -257,7 +298,10 @@ flash_tile_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t T = (int64_t)p.n_rt * p.n_ct;
   const int P = gridDim.x;
-  const int64_t t_begin = (int64_t)blockIdx.x * T / P, t_end = (int64_t)(blockIdx.x + 1) * T / P;
+  // tile indices are 32-bit and (rt, ct) are tracked incrementally: 64-bit divisions by a run-time n_ct in every role's
+  // tile loop cost several hundred instructions per tile (ncu: I2F / IMAD.WIDE chains among the hottest lines)
+  const int t_begin = (int)((int64_t)blockIdx.x * T / P), t_end = (int)((int64_t)(blockIdx.x + 1) * T / P);
+  const int rt_begin = t_begin / p.n_ct, ct_begin = t_begin - rt_begin * p.n_ct;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&map_x);
@@ -284,8 +328,8 @@ flash_tile_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
   if (warp == 0) {
     // ===================================================================== TMA producer
     uint32_t stage = 0, phase = 0, wfree_par = 0;
-    for (int64_t t = t_begin; t < t_end; ++t) {
-      const int rt = (int)(t / p.n_ct), ct = (int)(t - (int64_t)rt * p.n_ct);
+    int rt = rt_begin, ct = ct_begin;
+    for (int t = t_begin; t < t_end; ++t, ct = ct + 1 == p.n_ct ? 0 : ct + 1, rt += ct == 0 ? 1 : 0) {
       for (int k = 0; k < p.kb; ++k) {
         mbar_wait(&bars->empty[stage], phase ^ 1);
         if (elect_one()) {
@@ -318,7 +362,7 @@ flash_tile_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
                                     (UMMA_LAYOUT_SW128 << 61);
     const uint32_t ring_lo = smem_u32(ring) >> 4, w_lo = smem_u32(w_sm) >> 4, yt_lo = smem_u32(yt_sm) >> 4;
     uint32_t stage = 0, phase = 0, sempty_par[2] = {0, 0}, wfull_par = 0, ytfull_par = 0, accfree_par = 0;
-    auto gram = [&](int64_t t) {
+    auto gram = [&](int t) {
       const uint32_t a = (uint32_t)((t - t_begin) & 1);
       mbar_wait(&bars->s_empty[a], sempty_par[a] ^ 1);
       sempty_par[a] ^= 1;
@@ -341,12 +385,12 @@ flash_tile_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
       }
     };
     if (t_begin < t_end) gram(t_begin);
-    for (int64_t t = t_begin; t < t_end; ++t) {
+    int ct = ct_begin;
+    for (int t = t_begin; t < t_end; ++t, ct = ct + 1 == p.n_ct ? 0 : ct + 1) {
       if (t + 1 < t_end) gram(t + 1);                    // the next Gram tile runs under this tile's epilogue
       if (BWD) {
-        const int rt = (int)(t / p.n_ct);
-        const bool seg_first = t == t_begin || (int)((t - 1) / p.n_ct) != rt;
-        const bool seg_last = t + 1 == t_end || (int)((t + 1) / p.n_ct) != rt;
+        const bool seg_first = t == t_begin || ct == 0;
+        const bool seg_last = t + 1 == t_end || ct + 1 == p.n_ct;
         mbar_wait(&bars->w_full, wfull_par); wfull_par ^= 1;
         mbar_wait(&bars->yt_full, ytfull_par); ytfull_par ^= 1;
         if (seg_first && t != t_begin) { mbar_wait(&bars->acc_free, accfree_par); accfree_par ^= 1; }
@@ -379,7 +423,7 @@ flash_tile_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
     // and no bounds tests in the entry loops (full tiles take a path without them), near-pair detection as one
     // min-reduction per chunk, the logit never leaves log2 units.
     const int quad = warp & 3, row = quad * 32 + lane, et = threadIdx.x - 64;
-    const int wg = (warp - 2) >> 2;                       // warpgroup: columns [64 wg, 64 wg + 64) of every tile
+    const int wg = (warp - 2) >> 2;                       // warpgroup: columns [F_CW wg, F_CW wg + F_CW) of every tile
     const float two_c = 2.0f * p.c;
     const float gs = BWD ? (p.grad_scale != nullptr ? *p.grad_scale : 1.0f) * p.coef * 2.0f * rsqrtf(p.c) : 0.f;
     uint32_t sfull_par[2] = {0, 0}, wfree_par = 0, accfull_par = 0;
@@ -387,54 +431,79 @@ flash_tile_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
     float rowsum = 0.f;                                   // BWD: sum_j w_ij (1 + c s_ij / alpha_i)
     // per-column constants of a tile, double-buffered by tile parity and staged ONE TILE AHEAD (their global loads hide
     // behind the current tile's arithmetic):  [0] |y|^2   [1] 2c / beta (0 for columns >= m)   [2] BWD: column lse, log2
-    auto stage_cols = [&](int64_t tile) {
-      const int ct_ = (int)(tile % p.n_ct);
-      float* cq_ = cols + ((tile - t_begin) & 1) * F_COLS * FT_N;
-      for (int u = et; u < FT_N; u += F_EPI) {
-        const int64_t j = (int64_t)ct_ * FT_N + u;
+    // Global loads are issued one tile AHEAD and consumed one tile later (a dependent L2 round trip per tile cost ~1 us
+    // of the ~3 us a tile takes): cols_load() puts the next tile's column norms / log-sum-exps into registers right
+    // after the barrier, cols_store() turns them into the shared-memory constants at the END of the tile.
+    float pre_nb = 0.f, pre_ll = 0.f;
+    auto cols_load = [&](int ct_) {
+      if (et < FT_N) {
+        const int64_t j = (int64_t)ct_ * FT_N + et;
         const bool in = j < p.m;
-        const float nb = in ? p.ysq[j] : 0.f;
-        cq_[u] = nb;
-        cq_[FT_N + u] = in ? two_c / (1.0f - p.c * nb) : 0.f;
-        if (BWD) cq_[2 * FT_N + u] = (p.y_lse != nullptr && in) ? p.y_lse[j] * 1.4426950408889634f : 0.f;
+        pre_nb = in ? p.ysq[j] : -1.0f;
+        if (BWD) pre_ll = (p.y_lse != nullptr && in) ? p.y_lse[j] : 0.f;
       }
     };
-    if (t_begin < t_end) stage_cols(t_begin);
-    for (int64_t t = t_begin; t < t_end; ++t) {
-      const int rt = (int)(t / p.n_ct), ct = (int)(t - (int64_t)rt * p.n_ct);
+    auto cols_store = [&](int tile) {
+      if (et < FT_N) {
+        float* cq_ = cols + ((tile - t_begin) & 1) * F_COLS * FT_N;
+        const bool in = pre_nb >= 0.f;
+        cq_[et] = in ? pre_nb : 0.f;
+        cq_[FT_N + et] = in ? two_c / (1.0f - p.c * pre_nb) : 0.f;
+        if (BWD) cq_[2 * FT_N + et] = pre_ll * 1.4426950408889634f;
+      }
+    };
+    if (t_begin < t_end) { cols_load(ct_begin); cols_store(t_begin); }
+    int cur_rt = -1;
+    float na = 0.f, rho = 1.f, near_thr = -1.f, lx = 0.f;
+    int rt = rt_begin, ct = ct_begin;
+    for (int t = t_begin; t < t_end; ++t, ct = ct + 1 == p.n_ct ? 0 : ct + 1, rt += ct == 0 ? 1 : 0) {
       const uint32_t a = (uint32_t)((t - t_begin) & 1);
       const int64_t i = (int64_t)rt * FT_M + row;
       const int64_t j0 = (int64_t)ct * FT_N;
-      const bool seg_last = t + 1 == t_end || (int)((t + 1) / p.n_ct) != rt;
+      const bool seg_last = t + 1 == t_end || ct + 1 == p.n_ct;
       const bool row_ok = i < p.n;
       const int n_cols = (int)(p.m - j0 < FT_N ? p.m - j0 : FT_N);     // valid columns of this tile
       const float* cq = cols + a * F_COLS * FT_N;
       // all threads are past tile t-1 here: buffer a^1 is free for tile t+1, buffer a is complete
+      const long long c0 = p.stats ? clock64() : 0;
       asm volatile("bar.sync 1, %0;" ::"n"(F_EPI) : "memory");
-      if (t + 1 < t_end) stage_cols(t + 1);
-      const float na = row_ok ? p.xsq[i] : 0.f;
-      const float rho = 1.0f / (1.0f - p.c * na);
-      const float near_thr = row_ok ? F_NEAR * na : -1.0f;             // s below this: the Gram form has cancelled
-      const float lx = (BWD && p.x_lse != nullptr && row_ok) ? p.x_lse[i] * 1.4426950408889634f : 0.f;
+      const long long c1 = p.stats ? clock64() : 0;
+      if (t + 1 < t_end) cols_load(ct + 1 == p.n_ct ? 0 : ct + 1);
+      if (rt != cur_rt) {                                               // per-row constants: once per row block
+        cur_rt = rt;
+        na = row_ok ? p.xsq[i] : 0.f;
+        rho = 1.0f / (1.0f - p.c * na);
+        near_thr = row_ok ? F_NEAR * na : -1.0f;                        // s below this: the Gram form has cancelled
+        lx = (BWD && p.x_lse != nullptr && row_ok) ? p.x_lse[i] * 1.4426950408889634f : 0.f;
+      }
       const int64_t jd64 = i + p.diag_offset - j0;                     // this row's target column inside the tile
       const int jd = (row_ok && jd64 >= 0 && jd64 < n_cols) ? (int)jd64 : -1;
       const bool tile_has_diag = __any_sync(0xffffffffu, jd >= 0);     // warp-uniform: 1 tile in n_ct
+      const long long c2 = p.stats ? clock64() : 0;
       mbar_wait(&bars->s_full[a], sfull_par[a]);
       sfull_par[a] ^= 1;
       tcgen05_fence_after();
-      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + a * FT_N + wg * 64;
-      float v0[32], v1[32];
+      const long long c3 = p.stats ? clock64() : 0;
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + a * FT_N + wg * F_CW;
+      constexpr int HALVES = F_CW / 32;
+      float vv[HALVES][32];
       __syncwarp();
-      tmem_ld_32x32(taddr, v0);
-      tmem_ld_32x32(taddr + 32, v1);
-      tmem_ld_wait(v0);
-      tmem_ld_wait(v1);
+#pragma unroll
+      for (int h = 0; h < HALVES; ++h) tmem_ld_32x32(taddr + 32 * h, vv[h]);
+#pragma unroll
+      for (int h = 0; h < HALVES; ++h) tmem_ld_wait(vv[h]);
       tcgen05_fence_before();
       mbar_arrive(&bars->s_empty[a]);                     // the accumulator is in registers: the next Gram tile may land
+      const long long c4 = p.stats ? clock64() : 0;
+      if (p.stats && warp == 2 && lane == 0) {
+        unsigned long long* st = p.stats + (size_t)blockIdx.x * 8;
+        st[0] += (unsigned long long)(c1 - c0); st[1] += (unsigned long long)(c3 - c2); st[2] += (unsigned long long)(c4 - c3);
+        st[3] += 1; if (st[4] == 0) st[4] = (unsigned long long)c0; st[5] = (unsigned long long)c4;
+      }
 #pragma unroll
-      for (int half = 0; half < 2; ++half) {
-        float (&v)[32] = half == 0 ? v0 : v1;             // Gram entries, overwritten in place
-        const int cb = wg * 64 + half * 32;               // first column of the chunk inside the tile
+      for (int half = 0; half < HALVES; ++half) {
+        float (&v)[32] = vv[half];                        // Gram entries, overwritten in place
+        const int cb = wg * F_CW + half * 32;             // first column of the chunk inside the tile
         const float4* cn = reinterpret_cast<const float4*>(cq + cb);
         const float4* ca = reinterpret_cast<const float4*>(cq + FT_N + cb);
         const float smin = chunk_sqdist(v, cn, na);
@@ -482,10 +551,10 @@ flash_tile_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
           // the W buffer is rewritten now: the previous tile's product must have retired
           if (half == 0 && t > t_begin) { mbar_wait(&bars->w_free, wfree_par); wfree_par ^= 1; }
           // W planes, UMMA K-major 128B swizzle: [kblk = col / 64][row][64 cols]; 16-byte chunk index XOR (row & 7)
-          const uint32_t base = smem_u32(w_sm) + (uint32_t)(wg * FA_BLK) + (uint32_t)row * 128u;
+          const uint32_t base = smem_u32(w_sm) + (uint32_t)((cb >> 6) * FA_BLK) + (uint32_t)row * 128u;
 #pragma unroll
           for (int ch = 0; ch < 4; ++ch) {
-            const uint32_t off = ((((uint32_t)(half * 4 + ch)) ^ (uint32_t)(row & 7)) << 4);
+            const uint32_t off = ((((uint32_t)(((cb & 63) >> 3) + ch)) ^ (uint32_t)(row & 7)) << 4);
             asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(base + off), "r"(hp[4 * ch]), "r"(hp[4 * ch + 1]),
                          "r"(hp[4 * ch + 2]), "r"(hp[4 * ch + 3]) : "memory");
             asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(base + FW_PLANE + off), "r"(mp[4 * ch]),
@@ -493,6 +562,7 @@ flash_tile_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
           }
         }
       }
+      if (t + 1 < t_end) cols_store(t + 1);
       if (BWD) {
         fence_proxy_async_smem();                         // generic-proxy stores -> visible to the tensor core (async proxy)
         mbar_arrive(&bars->w_full);
@@ -500,14 +570,14 @@ flash_tile_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
       if (seg_last) {
         const int slot = (int)blockIdx.x - flash_cta_of_tile((int64_t)rt * p.n_ct, T, P);
         if (!BWD) {
-          float* o = p.part + ((((int64_t)rt * p.n_slots + slot) * 2 + wg) * 2) * FT_M;
+          float* o = p.part + ((((int64_t)rt * p.n_slots + slot) * F_NWG + wg) * 2) * FT_M;
           o[row] = -p.kappa * run_m;                      // max logit (log2 units); -inf when no column was seen
           o[FT_M + row] = run_s;
           run_m = INFINITY;
           run_s = 0.f;
         } else {
           const int64_t rows_pad = (int64_t)p.n_rt * FT_M;
-          p.part_rs[((int64_t)slot * 2 + wg) * rows_pad + (int64_t)rt * FT_M + row] = rowsum;
+          p.part_rs[((int64_t)slot * F_NWG + wg) * rows_pad + (int64_t)rt * FT_M + row] = rowsum;
           rowsum = 0.f;
           mbar_wait(&bars->acc_full, accfull_par);
           accfull_par ^= 1;
@@ -515,7 +585,7 @@ flash_tile_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
           // the [128, D] partial product: warpgroup g takes the 32-column chunks g, g+2, ...
           float* o = p.part + ((int64_t)slot * rows_pad + (int64_t)rt * FT_M + row) * p.d;
           const uint32_t tacc = tmem_acc + (static_cast<uint32_t>(quad * 32) << 16);
-          for (int cc = wg; cc * 32 < p.d; cc += 2) {
+          for (int cc = wg; cc * 32 < p.d; cc += F_NWG) {
             float v[32];
             __syncwarp();
             tmem_ld_32x32(tacc + cc * 32, v);
@@ -546,11 +616,11 @@ __global__ void flash_lse_finish_kernel(const float* __restrict__ part, int64_t 
   const int c0 = flash_cta_of_tile((int64_t)rt * n_ct, T, P), c1 = flash_cta_of_tile((int64_t)(rt + 1) * n_ct - 1, T, P);
   float m = -INFINITY;
   for (int s = 0; s <= c1 - c0; ++s)
-    for (int g = 0; g < 2; ++g) m = fmaxf(m, part[((((int64_t)rt * n_slots + s) * 2 + g) * 2) * FT_M + row]);
+    for (int g = 0; g < F_NWG; ++g) m = fmaxf(m, part[((((int64_t)rt * n_slots + s) * F_NWG + g) * 2) * FT_M + row]);
   float acc = 0.f;
   for (int s = 0; s <= c1 - c0; ++s)
-    for (int g = 0; g < 2; ++g) {
-      const float* o = part + ((((int64_t)rt * n_slots + s) * 2 + g) * 2) * FT_M;
+    for (int g = 0; g < F_NWG; ++g) {
+      const float* o = part + ((((int64_t)rt * n_slots + s) * F_NWG + g) * 2) * FT_M;
       if (o[row] > -INFINITY) acc += o[FT_M + row] * exp2f(o[row] - m);
     }
   lse[i] = (m + log2f(acc)) * 0.6931471805599453f;
@@ -565,12 +635,24 @@ __global__ void flash_grad_finish_kernel(const float* __restrict__ x, const floa
   const int64_t T = (int64_t)n_rt * n_ct, rows_pad = (int64_t)n_rt * FT_M;
   const int c0 = flash_cta_of_tile((int64_t)rt * n_ct, T, P), c1 = flash_cta_of_tile((int64_t)(rt + 1) * n_ct - 1, T, P);
   float rs = 0.f;
-  for (int s = 0; s <= c1 - c0; ++s) rs += part_rs[((int64_t)s * 2) * rows_pad + i] + part_rs[((int64_t)s * 2 + 1) * rows_pad + i];
+  for (int s = 0; s <= c1 - c0; ++s)
+    for (int g = 0; g < F_NWG; ++g) rs += part_rs[((int64_t)s * F_NWG + g) * rows_pad + i];
   for (int k = threadIdx.x; k < d; k += blockDim.x) {
     float acc = 0.f;
     for (int s = 0; s <= c1 - c0; ++s) acc += part[((int64_t)s * rows_pad + i) * d + k];
     dx[i * d + k] = x[i * d + k] * rs - acc;
   }
+}
+
+// out[j] = ln sum_w exp(parts[w, j]): combines per-rank partial log-sum-exps (sharded negatives), fixed order
+__global__ void lse_combine_kernel(const float* __restrict__ parts, int w, int64_t n, float* __restrict__ out) {
+  const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n) return;
+  float m = -INFINITY;
+  for (int r = 0; r < w; ++r) m = fmaxf(m, parts[(int64_t)r * n + j]);
+  float acc = 0.f;
+  for (int r = 0; r < w; ++r) acc += expf(parts[(int64_t)r * n + j] - m);
+  out[j] = m > -INFINITY ? m + logf(acc) : -INFINITY;
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -593,7 +675,7 @@ int flash_make_map(CUtensorMap* map, const void* base, CUtensorMapDataType dt, i
   cuuint32_t estr[2] = {1, 1};
   CUresult r = enc(map, dt, 2, const_cast<void*>(base), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS && getenv("HYPRET_DEBUG_FLASH") != nullptr)
+  if (r != CUDA_SUCCESS && getenv("HYPRET_FLASH_STATS") != nullptr)
     fprintf(stderr, "flash_make_map: CUresult %d base %p dt %d rows %lld cols %lld box_rows %d\n", (int)r, base, (int)dt,
             (long long)rows, (long long)cols, box_rows);
   return r == CUDA_SUCCESS ? HYPRET_OK : HYPRET_EINVAL;
@@ -620,6 +702,12 @@ int flash_slots(int n_rt, int n_ct, int P) {
 
 int64_t hypret_flash_kpad_impl(int d) { return flash_kpad(d); }
 
+int hypret_launch_lse_combine(const float* parts, int w, int64_t n, float* out, cudaStream_t stream) {
+  if (n == 0) return HYPRET_OK;
+  lse_combine_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(parts, w, n, out);
+  return (int)cudaGetLastError();
+}
+
 int hypret_launch_flash_prep(const float* x, int64_t n, int d, void* row_op, void* col_op, void* t_planes, int64_t n_pad,
                              float* sq, cudaStream_t stream) {
   if (n == 0) return HYPRET_OK;
@@ -638,12 +726,12 @@ int hypret_launch_flash_prep(const float* x, int64_t n, int d, void* row_op, voi
   return HYPRET_OK;
 }
 
-// workspace (floats): forward n_rt * slots * 4 * 128; backward slots * n_rt*128 * (d + 2)
+// workspace (floats): forward n_rt * slots * F_NWG * 2 * 128; backward slots * n_rt*128 * (d + F_NWG)
 int64_t hypret_flash_workspace_floats(int64_t n, int64_t m, int d) {
   const int n_rt = (int)((n + FT_M - 1) / FT_M), n_ct = (int)((m + FT_N - 1) / FT_N);
   const int P = flash_grid((int64_t)n_rt * n_ct);
   const int64_t slots = flash_slots(n_rt, n_ct, P);
-  const int64_t fwd = (int64_t)n_rt * slots * 4 * FT_M, bwd = slots * (int64_t)n_rt * FT_M * (d + 2);
+  const int64_t fwd = (int64_t)n_rt * slots * F_NWG * 2 * FT_M, bwd = slots * (int64_t)n_rt * FT_M * (d + F_NWG);
   return fwd > bwd ? fwd : bwd;
 }
 
@@ -671,6 +759,12 @@ int hypret_launch_flash(int bwd, const void* x_row_op, const void* y_col_op, con
   const int P = flash_grid((int64_t)p.n_rt * p.n_ct);
   p.n_slots = flash_slots(p.n_rt, p.n_ct, P);
   p.yt_cols = yt_cols;
+  p.stats = nullptr;
+  const char* st_env = getenv("HYPRET_FLASH_STATS");      // instrumentation only: synchronises and prints to stderr
+  if (st_env != nullptr && st_env[0] == '1') {
+    if (cudaMalloc(&p.stats, (size_t)P * 64) == cudaSuccess) cudaMemsetAsync(p.stats, 0, (size_t)P * 64, stream);
+    else p.stats = nullptr;
+  }
   const int64_t rows_pad = (int64_t)p.n_rt * FT_M;
   p.part = workspace;
   p.part_rs = workspace + (int64_t)p.n_slots * rows_pad * d;
@@ -691,6 +785,19 @@ int hypret_launch_flash(int bwd, const void* x_row_op, const void* y_col_op, con
     e = cudaGetLastError();
     if (e != cudaSuccess) return (int)e;
     flash_lse_finish_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(p.part, n, p.n_rt, p.n_ct, p.n_slots, P, out);
+  }
+  if (p.stats != nullptr) {
+    static unsigned long long h[148 * 8];
+    cudaStreamSynchronize(stream);
+    cudaMemcpy(h, p.stats, (size_t)P * 64, cudaMemcpyDeviceToHost);
+    cudaFree(p.stats);
+    double s[6] = {0};
+    for (int c = 0; c < P; ++c) {
+      for (int i = 0; i < 4; ++i) s[i] += (double)h[c * 8 + i] / P;
+      s[4] += (double)(h[c * 8 + 5] - h[c * 8 + 4]) / P;
+    }
+    fprintf(stderr, "flash stats (%s): per CTA, epilogue warp 2: tiles %.1f, cycles: barrier %.0f, wait S %.0f, tmem ld %.0f of %.0f\n",
+            bwd ? "bwd" : "fwd", s[3], s[0], s[1], s[2], s[4]);
   }
   return (int)cudaGetLastError();
 }

@@ -544,6 +544,16 @@ def flash_grad(xo: FlashOperands, yo: FlashOperands, c: float, inv_tau: float, x
     return out
 
 
+def lse_combine(parts: torch.Tensor) -> torch.Tensor:
+    """``logsumexp(parts, dim=0)`` for per-rank partial log-sum-exps ``[W, n]`` (``hypret_lse_combine``)."""
+    _need_cuda(parts)
+    parts = parts.contiguous().float()
+    out = torch.empty(parts.shape[1], dtype=torch.float32, device=parts.device)
+    with torch.cuda.device(parts.device):
+        _lib.check(_lib.load().hypret_lse_combine(_ptr(parts), parts.shape[0], parts.shape[1], _ptr(out), _stream()))
+    return out
+
+
 BWD_ROWS = 16       # HYPRET_BWD_ROWS: matrix rows per CTA of the backward pass (one col_partial row each)
 
 

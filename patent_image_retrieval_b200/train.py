@@ -154,20 +154,30 @@ class ShardedInBatchInfoNCE(torch.autograd.Function):
         p_all = torch.empty(n, d, dtype=torch.float32, device=a32.device)
         dist.all_gather_into_tensor(p_all, p32, group=group)
         inv_tau = 1.0 / float(temperature)
-        dm, row_lse, col_part = ops.pairdist_ce_fwd(a32, p_all, c, inv_tau, want_cols=symmetric,
-                                                    tensor_cores=None if TENSOR_CORES else False)
         off = rank * nl
-        diag_sim = -torch.diagonal(dm, offset=off) * inv_tau                    # sim[i, off + i]
+        ctx.flash = TENSOR_CORES and ops.flash_ok(nl, n, d)
+        dm = ao = po = None
+        if ctx.flash:                                                           # no [nl, n] array (csrc/flash.cu)
+            ao, po = ops.FlashOperands(a32), ops.FlashOperands(p_all)
+            row_lse = ops.flash_lse(ao, po, c, inv_tau)
+            col_part = ops.flash_lse(po, ao, c, inv_tau) if symmetric else None  # over this rank's rows only
+            diag_sim = -_diag_distance(a32, p_all, c, off) * inv_tau            # sim[i, off + i]
+        else:
+            dm, row_lse, col_part = ops.pairdist_ce_fwd(a32, p_all, c, inv_tau, want_cols=symmetric,
+                                                        tensor_cores=None if TENSOR_CORES else False)
+            diag_sim = -torch.diagonal(dm, offset=off) * inv_tau
         local = (row_lse - diag_sim).sum()
         col_lse = None
         if symmetric:
             parts = torch.empty(world, n, dtype=torch.float32, device=a32.device)
             dist.all_gather_into_tensor(parts, col_part, group=group)
-            col_lse = torch.logsumexp(parts, dim=0)                             # over the row blocks of all ranks
+            col_lse = ops.lse_combine(parts)                                    # over the row blocks of all ranks
             local = (local + (col_lse[off:off + nl] - diag_sim).sum()) / 2
         total = local.clone()
         dist.all_reduce(total, op=dist.ReduceOp.SUM, group=group)
-        ctx.save_for_backward(a32, p_all, dm, row_lse, col_lse if symmetric else row_lse)
+        ctx.ops = (ao, po)
+        ctx.save_for_backward(a32, p_all, dm if dm is not None else row_lse, row_lse,
+                              col_lse if symmetric else row_lse)
         ctx.c, ctx.inv_tau, ctx.symmetric, ctx.group = c, inv_tau, symmetric, group
         ctx.off, ctx.n, ctx.nl = off, n, nl
         ctx.in_dtypes = (a.dtype, p.dtype)
@@ -178,6 +188,16 @@ class ShardedInBatchInfoNCE(torch.autograd.Function):
         import torch.distributed as dist
         a, p_all, dm, row_lse, col_lse = ctx.saved_tensors
         wr, wc = (0.5, 0.5) if ctx.symmetric else (1.0, 0.0)
+        if ctx.flash:
+            ao, po = ctx.ops
+            cl = col_lse if ctx.symmetric else None
+            da = ops.flash_grad(ao, po, ctx.c, ctx.inv_tau, row_lse, cl, wr, wc, grad_scale=grad_loss,
+                                diag_offset=ctx.off, n_total=ctx.n)
+            dp_all = ops.flash_grad(po, ao, ctx.c, ctx.inv_tau, cl, row_lse, wc, wr, grad_scale=grad_loss,
+                                    diag_offset=-ctx.off, n_total=ctx.n)
+            dp = torch.empty(ctx.nl, dp_all.shape[1], dtype=torch.float32, device=dp_all.device)
+            dist.reduce_scatter_tensor(dp, dp_all, op=dist.ReduceOp.SUM, group=ctx.group)
+            return da.to(ctx.in_dtypes[0]), dp.to(ctx.in_dtypes[1]), None, None, None, None
         split = TENSOR_CORES and dm.numel() >= ops.SPLIT_MIN_PAIRS
         w, rs, cs = ops.pairdist_ce_bwd(dm, ops.row_sqnorm(a), ops.row_sqnorm(p_all), ctx.c, row_lse,
                                         col_lse if ctx.symmetric else None, ctx.inv_tau, wr, wc, grad_scale=grad_loss,
