@@ -9,14 +9,13 @@
 // per-query loop + torch.topk (src/auxiliary.py:374) does, and overwrites the query's result rows.  No host
 // round trip: the list length is read on the device, the grid is fixed, and with an empty list every CTA exits at once.
 //
-// Work decomposition: grid = (row chunks, slots).  CTA (c, s) serves list entries s, s + slots, ...; for each it scans
-// gallery rows [c * chunk, (c+1) * chunk): 8 warps take groups of 32 rows (4 rows per pass with all their 128-bit loads
-// issued before the first use; lane t keeps the sums of row t of the group and evaluates its own key), each warp keeps
-// its best k as packed 64-bit keys (ordered fp32 score << 32 | row id: one unsigned compare = the (score, id) order of
+// Work decomposition: grid = (row chunks, slots).  CTA (c, s) serves GROUPS of up to 4 list entries (a gallery row is
+// read once per group); for each group it scans gallery rows [c * chunk, (c+1) * chunk): 8 warps take groups of 32 rows
+// (4 rows per pass with all their 128-bit loads issued before the first use; an fp32 lower bound decides whether a row
+// needs the fp64 arithmetic at all), each warp keeps per query its best k as packed 64-bit keys (ordered fp32 score << 32 | row id: one unsigned compare = the (score, id) order of
 // the rerank), one per lane, sorted.  The CTA's list is merged into the query's result rows under a per-query spin
 // lock (the holder never waits on anything, so the lock cannot deadlock whatever part of the grid is resident); the
-// first merger of a query discards the filtered result that is there.  FP64-pipe bound (16 F2F + 16 DFMA per row and
-// lane): ~40 cycles per row and SM, 300k rows x 1 query = 45 us of the whole GPU.
+// first merger of a query discards the filtered result that is there.
 #include <math.h>
 
 #include "common.cuh"
@@ -56,8 +55,14 @@ __device__ __forceinline__ unsigned long long ex_merge(unsigned long long a, uns
   return v;
 }
 
-template <int NV>
-__global__ void __launch_bounds__(EX_WARPS * 32)
+// QB listed queries share every gallery row a warp reads, and a row reaches the fp64 arithmetic only if an fp32
+// lower bound of its key can still enter the query's list: per (row, query) the warp forms ||x - y||^2 (or <x,y>) in fp32
+// -- 21 roundings of non-negative terms, relative error < 2e-6 -- and compares it with the list's k-th best turned back
+// into a squared-distance threshold (d = arccosh(1 + 2 c s / (alpha beta)) / sqrt(c) is increasing in s).  The scan is
+// then HBM-bound (N * d * 4 bytes per pass over the shard, whatever QB is); before, the float -> double conversions of
+// every element (a quarter-rate pipe) made it 0.6 ms per query and 5M rows.
+template <int NV, int QB>
+__global__ void __launch_bounds__(EX_WARPS * 32, NV <= 4 ? 2 : 1)
 exact_topk_kernel(const float* __restrict__ q32, const float* __restrict__ g32, const double* __restrict__ g_sq64,
                   int64_t N, int d, float c, int metric, int k, int64_t idx_offset,
                   const int32_t* __restrict__ q_list, const int32_t* __restrict__ q_count, int32_t* state,
@@ -69,134 +74,171 @@ exact_topk_kernel(const float* __restrict__ q32, const float* __restrict__ g32, 
   const int64_t r_hi = r_lo + chunk < N ? r_lo + chunk : N;
   const int nvec = d >> 2;
   const double cc = (double)c;
-  for (int it = blockIdx.y; it < count; it += gridDim.y) {
-    const int64_t q = q_list[it];
-    const float4* qrow = reinterpret_cast<const float4*>(q32 + q * d);
-    float4 qv[NV];
-    double xsq = 0.0;
+  const bool hyp = metric == HYPRET_METRIC_HYPERBOLIC;
+  for (int it0 = blockIdx.y * QB; it0 < count; it0 += gridDim.y * QB) {
+    const int nq = count - it0 < QB ? count - it0 : QB;      // queries of this group (block-uniform)
+    float4 qv[QB][NV];
+    double xsq[QB];
 #pragma unroll
-    for (int i = 0; i < NV; ++i) {
-      const int j = i * 32 + lane;
-      qv[i] = (j < nvec) ? __ldg(qrow + j) : make_float4(0.f, 0.f, 0.f, 0.f);
-      xsq += (double)qv[i].x * qv[i].x + (double)qv[i].y * qv[i].y + (double)qv[i].z * qv[i].z +
-             (double)qv[i].w * qv[i].w;
+    for (int u = 0; u < QB; ++u) {
+      const int64_t qid = q_list[it0 + (u < nq ? u : 0)];    // pad the group with its first query (never inserted)
+      const float4* qrow = reinterpret_cast<const float4*>(q32 + qid * d);
+      double acc = 0.0;
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        const int j = i * 32 + lane;
+        qv[u][i] = (j < nvec) ? __ldg(qrow + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+        acc += (double)qv[u][i].x * qv[u][i].x + (double)qv[u][i].y * qv[u][i].y + (double)qv[u][i].z * qv[u][i].z +
+               (double)qv[u][i].w * qv[u][i].w;
+      }
+      xsq[u] = warp_sum(acc);
     }
-    xsq = warp_sum(xsq);
-    unsigned long long mine = EX_NONE;                       // this warp's best k, lane r = r-th best
-    for (int64_t g0 = r_lo + (int64_t)warp * 32; g0 < r_hi; g0 += EX_WARPS * 32) {
-      double my_s = 0.0;
-      constexpr int PASS = 4;
-      constexpr int CH = NV < 4 ? NV : 4;
-#pragma unroll 1
-      for (int r0 = 0; r0 < 32; r0 += PASS) {
-        if (g0 + r0 >= r_hi) break;                          // warp-uniform
-        const float4* g[PASS];
-        bool val[PASS];
+    unsigned long long mine[QB];                             // per query: this warp's best k, lane r = r-th best
+    // a row can enter query u's list only if  s32 * (1 - 2e-6) <= sthr[u] * beta_row  (hyperbolic: s = ||x-y||^2,
+    // sthr = (cosh(sqrt(c) d_k) - 1) alpha / (2c));  dot32 + 2e-6 |x||y| >= cthr[u] |y|  (cosine).  +inf / -inf: list not full
+    float thr[QB];
 #pragma unroll
-        for (int t = 0; t < PASS; ++t) {
-          val[t] = g0 + r0 + t < r_hi;
-          g[t] = reinterpret_cast<const float4*>(g32 + (val[t] ? g0 + r0 + t : r_lo) * d);
-        }
-        double sacc[PASS];
+    for (int u = 0; u < QB; ++u) { mine[u] = EX_NONE; thr[u] = hyp ? INFINITY : -INFINITY; }
+    constexpr int PASS = NV <= 8 ? 2 : 1;                   // rows in flight per warp: their registers bound it
+    constexpr int CH = NV < 4 ? NV : 4;
+    for (int64_t g0 = r_lo + (int64_t)warp * PASS; g0 < r_hi; g0 += EX_WARPS * PASS) {
+      const float4* g[PASS];
+      bool val[PASS];
 #pragma unroll
-        for (int t = 0; t < PASS; ++t) sacc[t] = 0.0;
+      for (int t = 0; t < PASS; ++t) {
+        val[t] = g0 + t < r_hi;
+        g[t] = reinterpret_cast<const float4*>(g32 + (val[t] ? g0 + t : r_lo) * d);
+      }
+      double ysq[PASS];                                      // requested with the rows, used after them
 #pragma unroll
-        for (int i0 = 0; i0 < NV; i0 += CH) {
-          float4 b[PASS][CH];
+      for (int t = 0; t < PASS; ++t) ysq[t] = val[t] ? g_sq64[g0 + t] : 0.0;
+      float s32[QB][PASS];
 #pragma unroll
-          for (int t = 0; t < PASS; ++t)
+      for (int u = 0; u < QB; ++u)
 #pragma unroll
-            for (int ii = 0; ii < CH; ++ii) {
-              const int j = (i0 + ii) * 32 + lane;
-              b[t][ii] = (i0 + ii < NV && val[t] && j < nvec) ? __ldg(g[t] + j) : make_float4(0.f, 0.f, 0.f, 0.f);
-            }
+        for (int t = 0; t < PASS; ++t) s32[u][t] = 0.f;
+      float4 b[PASS][NV];                                    // the rows stay in registers for the fp64 pass
+#pragma unroll
+      for (int i0 = 0; i0 < NV; i0 += CH) {
+#pragma unroll
+        for (int t = 0; t < PASS; ++t)
 #pragma unroll
           for (int ii = 0; ii < CH; ++ii) {
-            const int i = i0 + ii < NV ? i0 + ii : NV - 1;
-            if (i0 + ii >= NV) continue;
+            const int j = (i0 + ii) * 32 + lane;
+            if (i0 + ii < NV) b[t][i0 + ii] = (val[t] && j < nvec) ? __ldg(g[t] + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
 #pragma unroll
-            for (int t = 0; t < PASS; ++t) {
-              const float4 bb = b[t][ii];
-              if (metric == HYPRET_METRIC_HYPERBOLIC) {
-                const float e0 = qv[i].x - bb.x, e1 = qv[i].y - bb.y, e2 = qv[i].z - bb.z, e3 = qv[i].w - bb.w;
-                sacc[t] += (double)e0 * e0 + (double)e1 * e1 + (double)e2 * e2 + (double)e3 * e3;
+        for (int ii = 0; ii < CH; ++ii) {
+          if (i0 + ii >= NV) continue;
+          const int i = i0 + ii;
+#pragma unroll
+          for (int t = 0; t < PASS; ++t) {
+            const float4 bb = b[t][i];
+#pragma unroll
+            for (int u = 0; u < QB; ++u) {
+              if (hyp) {
+                const float e0 = qv[u][i].x - bb.x, e1 = qv[u][i].y - bb.y, e2 = qv[u][i].z - bb.z, e3 = qv[u][i].w - bb.w;
+                s32[u][t] = fmaf(e0, e0, fmaf(e1, e1, fmaf(e2, e2, fmaf(e3, e3, s32[u][t]))));
               } else {
-                sacc[t] += (double)qv[i].x * bb.x + (double)qv[i].y * bb.y + (double)qv[i].z * bb.z +
-                           (double)qv[i].w * bb.w;
+                s32[u][t] = fmaf(qv[u][i].x, bb.x, fmaf(qv[u][i].y, bb.y, fmaf(qv[u][i].z, bb.z, fmaf(qv[u][i].w, bb.w, s32[u][t]))));
               }
             }
           }
         }
+      }
 #pragma unroll
-        for (int t = 0; t < PASS; ++t) {
-          const double s0 = warp_sum(sacc[t]);
-          if (lane == r0 + t) my_s = s0;
+      for (int t = 0; t < PASS; ++t) {
+        if (!val[t]) continue;                               // warp-uniform
+        const double y0 = ysq[t];
+        const float beta = (float)(1.0 - cc * y0), ynorm = sqrtf((float)y0);
+#pragma unroll
+        for (int u = 0; u < QB; ++u) {
+          if (u >= nq) continue;                             // block-uniform
+          const float s = warp_sum(s32[u][t]);
+          const bool cand = hyp ? s * (1.0f - 2e-6f) <= thr[u] * beta
+                                : s + 2e-6f * (float)sqrt(xsq[u]) * ynorm >= thr[u] * ynorm;
+          if (!cand) continue;                               // warp-uniform: s is the same in every lane
+          // exact key of this row, with the arithmetic (and summation order) of the rerank kernel
+          double acc = 0.0;
+#pragma unroll
+          for (int i = 0; i < NV; ++i) {
+            const float4 bb = b[t][i];
+            if (hyp) {
+              const float e0 = qv[u][i].x - bb.x, e1 = qv[u][i].y - bb.y, e2 = qv[u][i].z - bb.z, e3 = qv[u][i].w - bb.w;
+              acc += (double)e0 * e0 + (double)e1 * e1 + (double)e2 * e2 + (double)e3 * e3;
+            } else {
+              acc += (double)qv[u][i].x * bb.x + (double)qv[u][i].y * bb.y + (double)qv[u][i].z * bb.z +
+                     (double)qv[u][i].w * bb.w;
+            }
+          }
+          acc = warp_sum(acc);
+          double kd;
+          if (hyp) {
+            const double t0 = 2.0 * cc * acc / ((1.0 - cc * xsq[u]) * (1.0 - cc * y0));
+            kd = log1p(t0 + sqrt(t0 * (t0 + 2.0))) / sqrt(cc);
+          } else {
+            const double nx = sqrt(xsq[u]);
+            kd = -(acc / ((nx == 0.0 ? 1.0 : nx) * (y0 == 0.0 ? 1.0 : sqrt(y0))));
+          }
+          const unsigned long long key = ((unsigned long long)ex_ordered_key((float)kd) << 32) | (unsigned)(g0 + t);
+          ex_insert(mine[u], key, k, lane);
+          // refresh the prefilter threshold from the list's k-th best (fp32 value, widened by one part in 1e5)
+          const unsigned long long worst = __shfl_sync(0xffffffffu, mine[u], k - 1);
+          if (worst != EX_NONE) {
+            const double dk = (double)ex_ordered_val((unsigned)(worst >> 32));
+            if (hyp) thr[u] = (float)((cosh(sqrt(cc) * dk * (1.0 + 1e-5)) - 1.0) * (1.0 - cc * xsq[u]) / (2.0 * cc) * (1.0 + 1e-5));
+            else thr[u] = (float)(-dk * sqrt(xsq[u]) - 1e-5 * fabs(dk * sqrt(xsq[u])) - 1e-30);
+          }
         }
-      }
-      // lane t evaluates row g0 + t: the fp32 value the rerank kernel emits, as an ordered key
-      const int64_t row = g0 + lane;
-      unsigned long long key = EX_NONE;
-      if (row < r_hi) {
-        const double y0 = g_sq64[row];
-        double kd;
-        if (metric == HYPRET_METRIC_HYPERBOLIC) {
-          const double t0 = 2.0 * cc * my_s / ((1.0 - cc * xsq) * (1.0 - cc * y0));
-          kd = log1p(t0 + sqrt(t0 * (t0 + 2.0))) / sqrt(cc);
-        } else {
-          const double nx = sqrt(xsq);
-          kd = -(my_s / ((nx == 0.0 ? 1.0 : nx) * (y0 == 0.0 ? 1.0 : sqrt(y0))));
-        }
-        key = ((unsigned long long)ex_ordered_key((float)kd) << 32) | (unsigned)row;
-      }
-      const unsigned long long worst = __shfl_sync(0xffffffffu, mine, k - 1);
-      unsigned hits = __ballot_sync(0xffffffffu, key < worst);
-      while (hits != 0u) {                                   // warp-uniform; rare once the list is warm
-        const int src = __ffs((int)hits) - 1;
-        hits &= hits - 1u;
-        ex_insert(mine, __shfl_sync(0xffffffffu, key, src), k, lane);
       }
     }
-    // ---- the CTA's best k: warp 0 folds the eight lists ---------------------------------------------------------
-    lists[warp][lane] = lane < k ? mine : EX_NONE;
-    __syncthreads();
-    if (warp == 0) {
-      unsigned long long best = lists[0][lane];
+    // ---- per query: the CTA's best k (warp 0 folds the eight lists), merged into the result rows under its lock -------
+#pragma unroll 1
+    for (int u = 0; u < nq; ++u) {
+      unsigned long long mu = EX_NONE;
 #pragma unroll
-      for (int w = 1; w < EX_WARPS; ++w) best = ex_merge(best, lists[w][lane], lane);
-      // ---- merge into the query's result rows under its lock -----------------------------------------------------
-      int32_t* lock = state + 2 * q;
-      if (lane == 0) {
-        while (atomicCAS(lock, 0, 1) != 0) __nanosleep(100);
-      }
-      __syncwarp();
-      __threadfence();
-      const int initialised = *reinterpret_cast<volatile int32_t*>(lock + 1);
-      unsigned long long cur = EX_NONE;
-      if (initialised && lane < k) {
-        const float sc = __ldcg(out_score + q * k + lane);
-        const int64_t id = __ldcg(out_idx + q * k + lane);
-        if (id >= 0) {
-          const float kf = metric == HYPRET_METRIC_HYPERBOLIC ? sc : -sc;
-          cur = ((unsigned long long)ex_ordered_key(kf) << 32) | (unsigned)(id - idx_offset);
+      for (int uu = 0; uu < QB; ++uu) mu = uu == u ? mine[uu] : mu;
+      lists[warp][lane] = lane < k ? mu : EX_NONE;
+      __syncthreads();
+      if (warp == 0) {
+        const int64_t q = q_list[it0 + u];
+        unsigned long long best = lists[0][lane];
+#pragma unroll
+        for (int w = 1; w < EX_WARPS; ++w) best = ex_merge(best, lists[w][lane], lane);
+        int32_t* lock = state + 2 * q;
+        if (lane == 0) {
+          while (atomicCAS(lock, 0, 1) != 0) __nanosleep(100);
         }
-      }
-      best = ex_merge(best, cur, lane);
-      if (lane < k) {
-        const bool valid = best != EX_NONE;
-        const float kf = ex_ordered_val((unsigned)(best >> 32));
-        const float sc = metric == HYPRET_METRIC_HYPERBOLIC ? kf : -kf;
-        out_score[q * k + lane] = valid ? sc : (metric == HYPRET_METRIC_HYPERBOLIC ? INFINITY : -INFINITY);
-        out_idx[q * k + lane] = valid ? (int64_t)(unsigned)(best & 0xffffffffull) + idx_offset : (int64_t)-1;
-      }
-      __threadfence();
-      __syncwarp();
-      if (lane == 0) {
-        *reinterpret_cast<volatile int32_t*>(lock + 1) = 1;
+        __syncwarp();
         __threadfence();
-        atomicExch(lock, 0);
+        const int initialised = *reinterpret_cast<volatile int32_t*>(lock + 1);
+        unsigned long long cur = EX_NONE;
+        if (initialised && lane < k) {
+          const float sc = __ldcg(out_score + q * k + lane);
+          const int64_t id = __ldcg(out_idx + q * k + lane);
+          if (id >= 0) {
+            const float kf = hyp ? sc : -sc;
+            cur = ((unsigned long long)ex_ordered_key(kf) << 32) | (unsigned)(id - idx_offset);
+          }
+        }
+        best = ex_merge(best, cur, lane);
+        if (lane < k) {
+          const bool valid = best != EX_NONE;
+          const float kf = ex_ordered_val((unsigned)(best >> 32));
+          const float sc = hyp ? kf : -kf;
+          out_score[q * k + lane] = valid ? sc : (hyp ? INFINITY : -INFINITY);
+          out_idx[q * k + lane] = valid ? (int64_t)(unsigned)(best & 0xffffffffull) + idx_offset : (int64_t)-1;
+        }
+        __threadfence();
+        __syncwarp();
+        if (lane == 0) {
+          *reinterpret_cast<volatile int32_t*>(lock + 1) = 1;
+          __threadfence();
+          atomicExch(lock, 0);
+        }
       }
+      __syncthreads();                                       // lists[] is rewritten by the next query
     }
-    __syncthreads();                                         // lists[] is rewritten by the next entry
   }
 }
 
@@ -213,18 +255,18 @@ int hypret_launch_exact_topk(const float* q32, const float* g32, const double* g
   // ~2 chunks per SM so that a single listed query already spreads over the whole GPU; a chunk is a multiple of the
   // 256 rows one pass of the 8 warps covers
   int64_t chunk = (N + 2 * sms - 1) / (2 * sms);
-  chunk = (chunk + 255) / 256 * 256;
+  chunk = (chunk + 31) / 32 * 32;
   const int64_t n_chunks = (N + chunk - 1) / chunk;
-  int64_t slots = (4 * (int64_t)sms + n_chunks - 1) / n_chunks;      // ~4 CTAs per SM in flight
-  if (slots > Q) slots = Q;
+  int64_t slots = (2 * (int64_t)sms + n_chunks - 1) / n_chunks;      // query groups in flight: ~2 CTAs per SM
+  if (slots > (Q + 3) / 4) slots = (Q + 3) / 4;
   if (slots < 1) slots = 1;
   if (slots > 65535) slots = 65535;
   const dim3 grid((unsigned)n_chunks, (unsigned)slots);
   const int need = (d + 127) / 128;
 #define HYPRET_EXACT_LAUNCH(NV)                                                                                     \
   do {                                                                                                              \
-    exact_topk_kernel<NV><<<grid, EX_WARPS * 32, 0, stream>>>(q32, g32, g_sq64, N, d, c, metric, k, idx_offset,     \
-                                                              q_list, q_count, state, out_score, out_idx, chunk);   \
+    exact_topk_kernel<NV, (NV <= 4 ? 4 : 2)><<<grid, EX_WARPS * 32, 0, stream>>>(                                   \
+        q32, g32, g_sq64, N, d, c, metric, k, idx_offset, q_list, q_count, state, out_score, out_idx, chunk);      \
     return (int)cudaGetLastError();                                                                                 \
   } while (0)
   if (need <= 1) HYPRET_EXACT_LAUNCH(1);
