@@ -213,6 +213,13 @@ int hypret_rerank_cert(const float* q32, const float* g32, int64_t Q, int64_t N,
 int hypret_exact_topk(const float* q32, const float* g32, const double* g_sqnorm64, int64_t Q, int64_t N, int d,
                       float c, int metric, int k, int64_t idx_offset, const int32_t* q_list, const int32_t* q_count,
                       int32_t* fb_state, float* out_score, int64_t* out_idx, void* stream);
+/* The next page of the same exact ranking: only rows whose key (ordered fp32 score << 32 | local row id, the order of the
+ * result lists) lies ABOVE after[i] for list entry i are taken.  Paging through the ranking 32 rows at a time gives the
+ * exact top-k for any k (notebooks/retrieval.ipynb:202 with k beyond the 128 the filtered path serves). */
+int hypret_exact_topk_after(const float* q32, const float* g32, const double* g_sqnorm64, int64_t Q, int64_t N, int d,
+                            float c, int metric, int k, int64_t idx_offset, const int32_t* q_list,
+                            const int32_t* q_count, int32_t* fb_state, const uint64_t* after, float* out_score,
+                            int64_t* out_idx, void* stream);
 /* out[i] = ||x_i||^2 accumulated in fp64 (x [n,d] fp32, d % 4 == 0), in the summation order of the rerank kernels. */
 int hypret_row_sqnorm64(const float* x, int64_t n, int d, double* out, void* stream);
 

@@ -63,6 +63,8 @@ SIGNATURES = {
                                    c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "hypret_exact_topk": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int, c_float, c_int, c_int, c_int64,
                                   c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "hypret_exact_topk_after": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int, c_float, c_int, c_int,
+                                        c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "hypret_peer_alloc": (c_int, [c_size_t, POINTER(c_void_p), c_void_p]),
     "hypret_peer_free": (c_int, [c_void_p]),
     "hypret_peer_open": (c_int, [c_void_p, POINTER(c_void_p)]),

@@ -227,7 +227,26 @@ int hypret_exact_topk(const float* q32, const float* g32, const double* g_sqnorm
   int rc = check_device();
   if (rc != HYPRET_OK) return rc;
   return hypret_launch_exact_topk(q32, g32, g_sqnorm64, Q, N, d, c, metric, k, idx_offset, q_list, q_count, fb_state,
-                                  out_score, out_idx, static_cast<cudaStream_t>(stream));
+                                  out_score, out_idx, nullptr, static_cast<cudaStream_t>(stream));
+}
+
+int hypret_exact_topk_after(const float* q32, const float* g32, const double* g_sqnorm64, int64_t Q, int64_t N, int d,
+                            float c, int metric, int k, int64_t idx_offset, const int32_t* q_list,
+                            const int32_t* q_count, int32_t* fb_state, const uint64_t* after, float* out_score,
+                            int64_t* out_idx, void* stream) {
+  if (Q < 0 || N < 1 || d < 4 || (d & 3) || k < 1 || k > 32 || N > 0x7fffffffll) return HYPRET_EINVAL;
+  if (metric != HYPRET_METRIC_COSINE && metric != HYPRET_METRIC_HYPERBOLIC) return HYPRET_EINVAL;
+  if (metric == HYPRET_METRIC_HYPERBOLIC && !(c > 0.f)) return HYPRET_EINVAL;
+  if (Q == 0) return HYPRET_OK;
+  if (q32 == nullptr || g32 == nullptr || g_sqnorm64 == nullptr || q_list == nullptr || q_count == nullptr ||
+      fb_state == nullptr || after == nullptr || out_score == nullptr || out_idx == nullptr || !aligned16(q32) ||
+      !aligned16(g32))
+    return HYPRET_EINVAL;
+  int rc = check_device();
+  if (rc != HYPRET_OK) return rc;
+  return hypret_launch_exact_topk(q32, g32, g_sqnorm64, Q, N, d, c, metric, k, idx_offset, q_list, q_count, fb_state,
+                                  out_score, out_idx, reinterpret_cast<const unsigned long long*>(after),
+                                  static_cast<cudaStream_t>(stream));
 }
 
 int hypret_row_sqnorm64(const float* x, int64_t n, int d, double* out, void* stream) {

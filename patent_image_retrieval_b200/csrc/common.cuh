@@ -369,7 +369,7 @@ int hypret_launch_rerank(const float* q32, const float* g32, int64_t Q, int64_t 
 int hypret_launch_exact_topk(const float* q32, const float* g32, const double* g_sq64, int64_t Q, int64_t N, int d,
                              float c, int metric, int k, int64_t idx_offset, const int32_t* q_list,
                              const int32_t* q_count, int32_t* state, float* out_score, int64_t* out_idx,
-                             cudaStream_t stream);
+                             const unsigned long long* after, cudaStream_t stream);
 int hypret_launch_row_sqnorm64(const float* x, int64_t n, int d, double* out, cudaStream_t stream);
 int hypret_launch_cand_select(const float* cand_score, const int32_t* cand_idx, const int32_t* list_count, int64_t Q,
                               int n_cand, int kprime, float* sel_score, int32_t* sel_idx,

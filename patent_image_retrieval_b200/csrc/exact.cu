@@ -66,7 +66,7 @@ __global__ void __launch_bounds__(EX_WARPS * 32, NV <= 4 ? 2 : 1)
 exact_topk_kernel(const float* __restrict__ q32, const float* __restrict__ g32, const double* __restrict__ g_sq64,
                   int64_t N, int d, float c, int metric, int k, int64_t idx_offset,
                   const int32_t* __restrict__ q_list, const int32_t* __restrict__ q_count, int32_t* state,
-                  float* out_score, int64_t* out_idx, int64_t chunk) {
+                  float* out_score, int64_t* out_idx, int64_t chunk, const unsigned long long* __restrict__ after) {
   __shared__ unsigned long long lists[EX_WARPS][32];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int count = *q_count;
@@ -79,8 +79,10 @@ exact_topk_kernel(const float* __restrict__ q32, const float* __restrict__ g32, 
     const int nq = count - it0 < QB ? count - it0 : QB;      // queries of this group (block-uniform)
     float4 qv[QB][NV];
     double xsq[QB];
+    unsigned long long aft[QB];                              // paging: only rows whose key is ABOVE this one are taken
 #pragma unroll
     for (int u = 0; u < QB; ++u) {
+      aft[u] = (after != nullptr && u < nq) ? after[it0 + u] : 0ull;
       const int64_t qid = q_list[it0 + (u < nq ? u : 0)];    // pad the group with its first query (never inserted)
       const float4* qrow = reinterpret_cast<const float4*>(q32 + qid * d);
       double acc = 0.0;
@@ -181,6 +183,7 @@ exact_topk_kernel(const float* __restrict__ q32, const float* __restrict__ g32, 
             kd = -(acc / ((nx == 0.0 ? 1.0 : nx) * (y0 == 0.0 ? 1.0 : sqrt(y0))));
           }
           const unsigned long long key = ((unsigned long long)ex_ordered_key((float)kd) << 32) | (unsigned)(g0 + t);
+          if (after != nullptr && key <= aft[u]) continue;   // warp-uniform: already returned by an earlier page
           ex_insert(mine[u], key, k, lane);
           // refresh the prefilter threshold from the list's k-th best (fp32 value, widened by one part in 1e5)
           const unsigned long long worst = __shfl_sync(0xffffffffu, mine[u], k - 1);
@@ -247,7 +250,7 @@ exact_topk_kernel(const float* __restrict__ q32, const float* __restrict__ g32, 
 int hypret_launch_exact_topk(const float* q32, const float* g32, const double* g_sq64, int64_t Q, int64_t N, int d,
                              float c, int metric, int k, int64_t idx_offset, const int32_t* q_list,
                              const int32_t* q_count, int32_t* state, float* out_score, int64_t* out_idx,
-                             cudaStream_t stream) {
+                             const unsigned long long* after, cudaStream_t stream) {
   if (Q == 0 || N == 0) return HYPRET_OK;
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
@@ -266,7 +269,7 @@ int hypret_launch_exact_topk(const float* q32, const float* g32, const double* g
 #define HYPRET_EXACT_LAUNCH(NV)                                                                                     \
   do {                                                                                                              \
     exact_topk_kernel<NV, (NV <= 4 ? 4 : 2)><<<grid, EX_WARPS * 32, 0, stream>>>(                                   \
-        q32, g32, g_sq64, N, d, c, metric, k, idx_offset, q_list, q_count, state, out_score, out_idx, chunk);      \
+        q32, g32, g_sq64, N, d, c, metric, k, idx_offset, q_list, q_count, state, out_score, out_idx, chunk, after); \
     return (int)cudaGetLastError();                                                                                 \
   } while (0)
   if (need <= 1) HYPRET_EXACT_LAUNCH(1);

@@ -256,6 +256,51 @@ def exact_topk(q32: torch.Tensor, g32: torch.Tensor, g_sqnorm64: torch.Tensor, c
     return out_s, out_i
 
 
+def _packed_keys(score: torch.Tensor, idx: torch.Tensor, metric: str, idx_offset: int) -> torch.Tensor:
+    """The 64-bit ordering keys of result entries: ordered fp32 key << 32 | local row id (csrc/exact.cu)."""
+    key = score if metric == "hyperbolic" else -score
+    bits = key.contiguous().view(torch.int32).to(torch.int64) & 0xFFFFFFFF
+    hi = torch.where(bits >= 0x80000000, (~bits) & 0xFFFFFFFF, bits | 0x80000000)
+    packed = (hi << 32) | ((idx - idx_offset) & 0xFFFFFFFF)
+    return torch.where(idx >= 0, packed, torch.full_like(packed, -1))       # -1 = all ones: nothing lies above it
+
+
+def exact_topk_any(q32: torch.Tensor, g32: torch.Tensor, g_sqnorm64: torch.Tensor, c: float, metric: str, k: int,
+                   idx_offset: int = 0):
+    """Exact top-k for ANY k by paging through the exact ranking 32 rows at a time (``hypret_exact_topk_after``): one
+    full scan per page.  For the k beyond the filtered path's 128 (``retrieve_similar_images(k=500)``)."""
+    _need_cuda(q32, g32, g_sqnorm64)
+    q32, g32 = q32.contiguous().float(), g32.contiguous().float()
+    Q, d = q32.shape
+    dev = q32.device
+    lst = torch.arange(Q, dtype=torch.int32, device=dev)
+    cnt = torch.full((1,), Q, dtype=torch.int32, device=dev)
+    after = torch.zeros(Q, dtype=torch.int64, device=dev)
+    pages_s, pages_i = [], []
+    lib = _lib.load()
+    first = True
+    for k0 in range(0, k, 32):
+        kk = min(32, k - k0)
+        out_s = torch.empty(Q, kk, dtype=torch.float32, device=dev)
+        out_i = torch.empty(Q, kk, dtype=torch.int64, device=dev)
+        state = torch.zeros(2 * Q, dtype=torch.int32, device=dev)
+        with torch.cuda.device(dev):
+            if first:
+                _lib.check(lib.hypret_exact_topk(_ptr(q32), _ptr(g32), _ptr(g_sqnorm64), Q, g32.shape[0], d, float(c),
+                                                 METRIC[metric], kk, int(idx_offset), _ptr(lst), _ptr(cnt), _ptr(state),
+                                                 _ptr(out_s), _ptr(out_i), _stream()))
+            else:
+                _lib.check(lib.hypret_exact_topk_after(_ptr(q32), _ptr(g32), _ptr(g_sqnorm64), Q, g32.shape[0], d,
+                                                       float(c), METRIC[metric], kk, int(idx_offset), _ptr(lst),
+                                                       _ptr(cnt), _ptr(state), _ptr(after), _ptr(out_s), _ptr(out_i),
+                                                       _stream()))
+        first = False
+        pages_s.append(out_s)
+        pages_i.append(out_i)
+        after = _packed_keys(out_s[:, -1], out_i[:, -1], metric, idx_offset)
+    return torch.cat(pages_s, dim=1), torch.cat(pages_i, dim=1)
+
+
 def row_sqnorm64(x: torch.Tensor) -> torch.Tensor:
     """``||x_i||^2`` accumulated in fp64 (``hypret_row_sqnorm64``): the per-row constant of the exact rerank."""
     _need_cuda(x)

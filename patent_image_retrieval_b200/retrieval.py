@@ -128,6 +128,15 @@ class GalleryIndex:
         ``margin`` diagnostic.
         ``kernel_events``: a list (receives a (start, end) CUDA-event pair bracketing the scoring kernel
         on the launching stream per call) or a ``StageEvents`` (all three kernels): bench.py's rooflines."""
+        if k > ops.MAX_K:
+            # beyond the filtered path: page through the exact ranking by full scans (the reference ranks the whole
+            # gallery, notebooks/retrieval.ipynb:383; its metrics are served by rank counting, this serves its lists)
+            q = queries.to(device=self.device, dtype=torch.float32, non_blocking=True)
+            if self.metric == "hyperbolic":
+                q = ops.project_rows(q, self.c, mode=self._query_mode(), side="query", want_operand=False)[0]
+            res = ops.exact_topk_any(q, self.rows32, self.rows_sq64, self.c, self.metric, min(k, self.n),
+                                     idx_offset=self.idx_offset)
+            return res + (torch.full((q.shape[0],), float("inf"), device=self.device),) if return_margin else res
         q32, cs, ci, cnt, q_err = self.score_candidates(queries, k=k, kprime=kprime, max_ctas=max_ctas,
                                                         kernel_events=kernel_events, want_err=exact)
         return self.rerank_candidates(q32, cs, ci, k, return_margin=return_margin, kernel_events=kernel_events,

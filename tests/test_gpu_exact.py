@@ -210,3 +210,22 @@ def test_exact_search_overhead_is_device_side_only():
         g.replay()
     torch.cuda.synchronize()
     assert torch.equal(out[1], want)
+
+
+@pytest.mark.parametrize("metric", ["hyperbolic", "cosine"])
+def test_search_beyond_128_pages_through_the_exact_ranking(metric):
+    """k > 128 (the reference ranks the whole gallery, notebooks/retrieval.ipynb:383,202): exact lists by paging."""
+    d, c, k, Q, N = 128, 1.0, 300, 9, 2500
+    gal, qry = _near_duplicates(N, Q, d, 0.05, c, metric)
+    index = GalleryIndex(gal.cuda(), c=c, metric=metric, space="ball" if metric == "hyperbolic" else "euclidean")
+    score, idx = index.search(qry.cuda(), k=k)
+    assert tuple(idx.shape) == (Q, k)
+    d64 = _oracle_d64(qry, gal, c, metric)
+    _assert_lists(idx.cpu(), d64, k, "paged:")
+    got = score.cpu().double() if metric == "hyperbolic" else -score.cpu().double()
+    ref = torch.gather(d64, 1, idx.cpu())
+    assert float(((got - ref).abs() / ref.abs().clamp_min(1e-30)).max()) < 2e-6
+    # more rows requested than the gallery has: padded with -1
+    small = GalleryIndex(gal[:150].cuda(), c=c, metric=metric, space="ball" if metric == "hyperbolic" else "euclidean")
+    _, i2 = small.search(qry.cuda(), k=200)
+    assert tuple(i2.shape) == (Q, 150) and bool((i2 >= 0).all())
