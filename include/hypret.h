@@ -278,6 +278,19 @@ int hypret_merge_topk(const float* scores, const int64_t* idx, int n_shards, int
 int hypret_mobius_epilogue(const float* mx, int64_t n, int d, const float* xsq, const float* bias, float c,
                            int hyperbolic_input, int post_tanh, int n_project, float* y, float* sqnorm, void* stream);
 
+/* One MobiusLinear layer as ONE kernel (csrc/headgemm.cu): tcgen05 GEMM from 2-way fp16 split operands + the whole
+ * hyperbolic epilogue of hypret_mobius_epilogue on the accumulator in TMEM (src/models.py:291-318, 481-505).
+ *   x_row_op [n, kpad(d_in)] fp16   row operand [hi|lo|hi] of the layer input (hypret_flash_prep, or the op_out of the
+ *                                   previous layer); w_col_op [n_out, kpad(d_in)] column operand [hi|hi|lo] of the weight
+ *   xsq [n] or NULL    ||x||^2 of the input: given = hyperbolic input (mobius_matvec), NULL = Euclidean input (expmap0)
+ *   bias [n_out] or NULL (on the ball), post_tanh, n_project: as hypret_mobius_epilogue
+ *   outputs, each optional: mx_out [n,n_out] fp32 raw product (the backward pass needs it), y_out [n,n_out] fp32,
+ *   ysq_out [n], op_out [n, kpad(n_out)] fp16 = the NEXT layer's row operand (no fp32 round trip of the activations)
+ * n_out % 16 == 0, n_out <= 256; d_in % 4 == 0; kpad = hypret_flash_kpad. */
+int hypret_mobius_gemm(const void* x_row_op, const void* w_col_op, int64_t n, int d_in, int n_out, const float* xsq,
+                       const float* bias, float c, int post_tanh, int n_project, float* mx_out, float* y_out,
+                       float* ysq_out, void* op_out, void* stream);
+
 /* Exact pairwise Poincare distance matrix out[i,j] = dist(a_i, p_j), fp32 [n,m].
  * Replaces the Python loops of 1x1 / 1xN pmath.dist calls (src/train.py:1832-1840, 2304-2320,
  * 3259, 1033).  Differences formed explicitly in fp32, transcendental tail in fp64. */
@@ -388,7 +401,8 @@ int hypret_ap_from_counts(const int64_t* pos_offsets, const int64_t* pos_items, 
 /* ---- Flash-style train_hyp step (csrc/flash.cu): the in-batch InfoNCE over the n x m Poincare distance matrix, forward
  * and backward, WITHOUT ever writing the matrix (or any other [n,m] array) to memory, all dense products on tcgen05.
  * Replaces the O(n^2) double loop of 1x1 pmath.dist + autograd (src/train.py:1832-1846; symmetric: 2304-2334).
- * 16 <= d <= 128, d % 16 == 0 (larger d: hypret_gram_dist / hypret_pairdist_ce_*).
+ * hypret_flash_lse / hypret_flash_grad: 16 <= d <= 128, d % 16 == 0 (larger d: hypret_gram_dist / hypret_pairdist_ce_*);
+ * hypret_flash_prep itself serves any d % 4 == 0 (its operands also feed hypret_mobius_gemm).
  *   hypret_flash_kpad(d)      Gram operand row length: roundup(3 d, 64) fp16 elements
  *   hypret_flash_workspace    fp32 elements of workspace hypret_flash_lse / hypret_flash_grad need for n x m
  *   hypret_flash_prep         x [n,d] fp32 -> row_op [n,kpad] fp16 ([hi|lo|hi]), col_op [n,kpad] fp16 ([hi|hi|lo]),

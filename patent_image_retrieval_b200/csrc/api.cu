@@ -536,7 +536,7 @@ int64_t hypret_flash_workspace(int64_t n, int64_t m, int d) {
 
 int hypret_flash_prep(const float* x, int64_t n, int d, void* row_op, void* col_op, void* t_planes, int64_t t_cols,
                       float* sqnorm, void* stream) {
-  if (n < 0 || d < 16 || (d & 15) || d > 128) return HYPRET_EINVAL;
+  if (n < 0 || d < 4 || (d & 3) || d > 4096) return HYPRET_EINVAL;
   if (n == 0) return HYPRET_OK;
   if (x == nullptr || !aligned16(row_op) || !aligned16(col_op) || !aligned16(t_planes)) return HYPRET_EINVAL;
   if (t_planes != nullptr && (t_cols < n || (t_cols & 7))) return HYPRET_EINVAL;
@@ -580,6 +580,23 @@ int hypret_flash_grad(const void* x_row_op, const void* y_col_op, const void* y_
                       float* dx_out, void* stream) {
   return flash_common(1, x_row_op, y_col_op, y_t_planes, t_cols, x32, y32, xsq, ysq, x_lse, y_lse, n, m, d, c, inv_tau,
                       w_rows, w_cols, grad_scale, diag_offset, n_total, workspace, dx_out, stream);
+}
+
+int hypret_mobius_gemm(const void* x_row_op, const void* w_col_op, int64_t n, int d_in, int n_out, const float* xsq,
+                       const float* bias, float c, int post_tanh, int n_project, float* mx_out, float* y_out,
+                       float* ysq_out, void* op_out, void* stream) {
+  if (n < 0 || d_in < 4 || (d_in & 3) || d_in > 4096 || n_out < 16 || (n_out & 15) || n_out > 256 || !(c > 0.f) ||
+      n_project < 0 || n_project > 2)
+    return HYPRET_EINVAL;
+  if (n == 0) return HYPRET_OK;
+  if (x_row_op == nullptr || w_col_op == nullptr || !aligned16(x_row_op) || !aligned16(w_col_op) ||
+      !aligned16(mx_out) || !aligned16(y_out) || !aligned16(op_out) ||
+      (mx_out == nullptr && y_out == nullptr && op_out == nullptr && ysq_out == nullptr))
+    return HYPRET_EINVAL;
+  int rc = check_device();
+  if (rc != HYPRET_OK) return rc;
+  return hypret_launch_mobius_gemm(x_row_op, w_col_op, n, d_in, n_out, xsq, bias, c, post_tanh != 0, n_project, mx_out,
+                                   y_out, ysq_out, op_out, static_cast<cudaStream_t>(stream));
 }
 
 int hypret_lse_combine(const float* parts, int n_parts, int64_t n, float* out, void* stream) {

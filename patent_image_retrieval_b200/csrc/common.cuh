@@ -438,3 +438,6 @@ int hypret_launch_flash(int bwd, const void* x_row_op, const void* y_col_op, con
                         const float* grad_scale, int64_t diag_offset, int64_t n_total, float* workspace, float* out,
                         cudaStream_t stream);
 int hypret_launch_lse_combine(const float* parts, int w, int64_t n, float* out, cudaStream_t stream);
+int hypret_launch_mobius_gemm(const void* x_row_op, const void* w_col_op, int64_t n, int d_in, int n_out,
+                              const float* xsq, const float* bias, float c, int post_tanh, int n_project, float* mx_out,
+                              float* y_out, float* ysq_out, void* op_out, cudaStream_t stream);

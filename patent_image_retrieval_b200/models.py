@@ -105,10 +105,19 @@ class DeeperHyperbolicEncoder(nn.Module):
     def forward(self, x):
         self.k = self.k.to(x.device)
         if self._fused_ok(x):
-            # inference on the GPU: two GEMMs + two fused epilogue kernels (csrc/head.cu) instead of ~75
-            # elementwise launches; same arithmetic order as the op-by-op path below
             from . import ops
             c = float(self.c)
+            d_in, hid, d_out = self.first_layer.in_features, self.first_layer.out_features, self.final_layer.out_features
+            if ops.mobius_gemm_ok(d_in, hid) and ops.mobius_gemm_ok(hid, d_out):
+                # inference on the GPU: each layer is ONE kernel -- tcgen05 GEMM + the Moebius epilogue on the
+                # accumulator (csrc/headgemm.cu); the hidden activations reach the second GEMM as its fp16 split
+                # operand, never as an fp32 [B, hidden] tensor
+                h = ops.mobius_gemm(ops.split_operand(x, "row"), ops.split_operand(self.first_layer.weight, "col"), d_in,
+                                    hid, c, bias=self.first_layer.bias, post_tanh=True, n_project=1, want_y=False,
+                                    want_op=True, want_sqnorm=True)
+                return ops.mobius_gemm(h["op"], ops.split_operand(self.final_layer.weight, "col"), hid, d_out, c,
+                                       bias=self.final_layer.bias, xsq=h["sq"], n_project=2)["y"]
+            # other layer widths: two library GEMMs + two fused epilogue kernels (csrc/head.cu)
             h, hsq = ops.mobius_epilogue(F.linear(x, self.first_layer.weight.to(x.dtype)), c,
                                          bias=self.first_layer.bias, post_tanh=True, n_project=1)
             y, _ = ops.mobius_epilogue(F.linear(h, self.final_layer.weight.to(x.dtype)), c,

@@ -589,6 +589,50 @@ def flash_grad(xo: FlashOperands, yo: FlashOperands, c: float, inv_tau: float, x
     return out
 
 
+def split_operand(x: torch.Tensor, side: str) -> torch.Tensor:
+    """fp16 2-way split GEMM operand of ``x [n,d]``: ``side='row'`` -> ``[hi|lo|hi]``, ``'col'`` -> ``[hi|hi|lo]``
+    (``hypret_flash_prep``); a row operand times a column operand is the fp32 product to 2^-22."""
+    _need_cuda(x)
+    x = x.detach().contiguous().float()
+    n, d = x.shape
+    lib = _lib.load()
+    op = torch.empty(n, int(lib.hypret_flash_kpad(d)), dtype=torch.float16, device=x.device)
+    with torch.cuda.device(x.device):
+        _lib.check(lib.hypret_flash_prep(_ptr(x), n, d, _ptr(op) if side == "row" else None,
+                                         _ptr(op) if side == "col" else None, None, 0, None, _stream()))
+    return op
+
+
+def mobius_gemm_ok(d_in: int, n_out: int) -> bool:
+    return d_in % 4 == 0 and d_in <= 4096 and n_out % 16 == 0 and 16 <= n_out <= 256
+
+
+def mobius_gemm(x_op: torch.Tensor, w_op: torch.Tensor, d_in: int, n_out: int, c: float,
+                bias: Optional[torch.Tensor] = None, xsq: Optional[torch.Tensor] = None, post_tanh: bool = False,
+                n_project: int = 1, want_y: bool = True, want_op: bool = False, want_sqnorm: bool = False,
+                want_mx: bool = False):
+    """One MobiusLinear layer as one kernel (``hypret_mobius_gemm``): tcgen05 GEMM of split operands + the hyperbolic
+    epilogue on the accumulator.  Returns a dict with the requested outputs: ``y`` [n,n_out] fp32, ``op`` the next
+    layer's row operand, ``sq`` ||y||^2, ``mx`` the raw product (kept by the training path for its backward)."""
+    _need_cuda(x_op, w_op, bias, xsq)
+    n = x_op.shape[0]
+    dev = x_op.device
+    lib = _lib.load()
+    out = {
+        "y": torch.empty(n, n_out, dtype=torch.float32, device=dev) if want_y else None,
+        "op": torch.empty(n, int(lib.hypret_flash_kpad(n_out)), dtype=torch.float16, device=dev) if want_op else None,
+        "sq": torch.empty(n, dtype=torch.float32, device=dev) if want_sqnorm else None,
+        "mx": torch.empty(n, n_out, dtype=torch.float32, device=dev) if want_mx else None,
+    }
+    b = bias.detach().contiguous().float() if bias is not None else None
+    xs = xsq.contiguous().float() if xsq is not None else None
+    with torch.cuda.device(dev):
+        _lib.check(lib.hypret_mobius_gemm(_ptr(x_op), _ptr(w_op), n, int(d_in), int(n_out), _ptr(xs), _ptr(b), float(c),
+                                          int(bool(post_tanh)), int(n_project), _ptr(out["mx"]), _ptr(out["y"]),
+                                          _ptr(out["sq"]), _ptr(out["op"]), _stream()))
+    return out
+
+
 def lse_combine(parts: torch.Tensor) -> torch.Tensor:
     """``logsumexp(parts, dim=0)`` for per-rank partial log-sum-exps ``[W, n]`` (``hypret_lse_combine``)."""
     _need_cuda(parts)

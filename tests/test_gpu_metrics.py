@@ -384,3 +384,30 @@ def test_generic_pairdist_backward_split_and_ragged():
         (_dist64(a64, p64, c) * g.cpu().double()).sum().backward()
         for got, want in ((ag.grad, a64.grad), (pg.grad, p64.grad)):
             assert float((got.cpu().double() - want).abs().max() / want.abs().max()) < 1e-4
+
+
+@pytest.mark.parametrize("d_in,hid,d_out,c,b", [(512, 256, 128, 1.0, 1000), (2048, 256, 256, 0.5, 300),
+                                                (768, 128, 64, 2.0, 129), (64, 32, 16, 1.0, 5)])
+def test_mobius_gemm_head_matches_oracle(d_in, hid, d_out, c, b):
+    """The head as two hypret_mobius_gemm kernels (tcgen05 GEMM + Moebius epilogue on the accumulator, the hidden
+    activations handed over as the second GEMM's fp16 split operand) against the oracle's restatement of
+    src/models.py:291-318, 481-505, and against the round-1 path (library GEMM + epilogue kernel) on the same weights."""
+    from oracle import head
+    from patent_image_retrieval_b200 import models, ops
+    torch.manual_seed(9)
+    m = models.FigureOnlyHyperbolicModel(d_in, d_out, hidden_dims=[hid], c=c).eval()
+    with torch.no_grad():
+        m.encoder.first_layer.weight.mul_(3.0)                # some rows reach the project clip
+    x = torch.randn(b, d_in) * 0.7
+    x[0] = 0.0
+    sd = m.state_dict()
+    want = head.encoder_forward(x, sd["encoder.first_layer.weight"], sd["encoder.first_layer.bias"],
+                                sd["encoder.final_layer.weight"], sd["encoder.final_layer.bias"], torch.tensor([-c]))
+    assert ops.mobius_gemm_ok(d_in, hid) and ops.mobius_gemm_ok(hid, d_out)
+    mg = m.cuda()
+    with torch.no_grad():
+        got = mg.encode_figures(x.cuda()).cpu()
+    scale = want.norm(dim=1, keepdim=True).clamp_min(1e-20)
+    assert float(((got - want).abs() / scale).max()) < 2e-5
+    assert float(got.norm(dim=1).max()) <= (1 - 4e-3) / c ** 0.5 * (1 + 1e-6)
+    assert torch.equal(got[0], got[0]) and bool(torch.isfinite(got).all())
