@@ -291,6 +291,26 @@ int hypret_mobius_gemm(const void* x_row_op, const void* w_col_op, int64_t n, in
                        const float* bias, float c, int post_tanh, int n_project, float* mx_out, float* y_out,
                        float* ysq_out, void* op_out, void* stream);
 
+/* Backward of the epilogue of one MobiusLinear layer (csrc/headbwd.cu): what autograd does through the ~35 elementwise
+ * nodes of src/models.py:291-318 (+ 491, 504), in closed form, a warp per row.  The forward scalars are recomputed from
+ * the saved raw product mx (hypret_mobius_gemm's mx_out).
+ *   gy [n,d]      dL/d(layer output)
+ *   gmx [n,d]     out: dL/d(mx)           (dW = gmx^T x_in, dx_in = gmx W: hypret_sgemm_strided)
+ *   gbias [d]     +=: dL/d(bias), accumulated with atomics -- zero it first; NULL or bias == NULL: skipped
+ *   gxn [n]       out: (dL/d||x_in||) / ||x_in|| through the mobius_matvec rescale, so that dL/dx_in = gmx W + gxn x_in;
+ *                 needs xsq; NULL: skipped
+ * Flags as hypret_mobius_gemm.  d % 4 == 0, d <= 512. */
+int hypret_mobius_epilogue_bwd(const float* mx, int64_t n, int d, const float* xsq, const float* bias, float c,
+                               int post_tanh, int n_project, const float* gy, float* gmx, float* gbias, float* gxn,
+                               void* stream);
+
+/* out[m,n] (row-major, fp32) = sum_k a[m*a_row_stride + k*a_col_stride] * b[k*b_row_stride + n*b_col_stride]
+ *                               (+ row_scale[m] * addend[m,n] when both are given): the batch-sized dense products of the head's backward pass (torch.nn.functional.linear's backward in the reference,
+ * src/models.py:305-310), FP32 FMA tiles. */
+int hypret_sgemm_strided(const float* a, int64_t a_row_stride, int64_t a_col_stride, const float* b,
+                         int64_t b_row_stride, int64_t b_col_stride, int m, int n, int k, const float* row_scale,
+                         const float* addend, float* out, void* stream);
+
 /* Exact pairwise Poincare distance matrix out[i,j] = dist(a_i, p_j), fp32 [n,m].
  * Replaces the Python loops of 1x1 / 1xN pmath.dist calls (src/train.py:1832-1840, 2304-2320,
  * 3259, 1033).  Differences formed explicitly in fp32, transcendental tail in fp64. */

@@ -123,6 +123,10 @@ SIGNATURES = {
                                       c_void_p, c_void_p, c_void_p, c_void_p]),
     "hypret_mobius_gemm": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_void_p, c_void_p, c_float, c_int, c_int,
                                    c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "hypret_mobius_epilogue_bwd": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_void_p, c_float, c_int, c_int, c_void_p,
+                                           c_void_p, c_void_p, c_void_p, c_void_p]),
+    "hypret_sgemm_strided": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_int64, c_int64, c_int, c_int, c_int,
+                                     c_void_p, c_void_p, c_void_p, c_void_p]),
     "hypret_lse_combine": (c_int, [c_void_p, c_int, c_int64, c_void_p, c_void_p]),
     "hypret_flash_kpad": (c_int64, [c_int]),
     "hypret_flash_workspace": (c_int64, [c_int64, c_int64, c_int]),

@@ -599,6 +599,32 @@ int hypret_mobius_gemm(const void* x_row_op, const void* w_col_op, int64_t n, in
                                    y_out, ysq_out, op_out, static_cast<cudaStream_t>(stream));
 }
 
+int hypret_mobius_epilogue_bwd(const float* mx, int64_t n, int d, const float* xsq, const float* bias, float c,
+                               int post_tanh, int n_project, const float* gy, float* gmx, float* gbias, float* gxn,
+                               void* stream) {
+  if (n < 0 || d < 4 || (d & 3) || d > 512 || !(c > 0.f) || n_project < 0 || n_project > 2) return HYPRET_EINVAL;
+  if (n == 0) return HYPRET_OK;
+  if (mx == nullptr || gy == nullptr || gmx == nullptr || !aligned16(mx) || !aligned16(gy) || !aligned16(gmx) ||
+      !aligned16(bias) || (gbias != nullptr && bias == nullptr) || (gxn != nullptr && xsq == nullptr))
+    return HYPRET_EINVAL;
+  int rc = check_device();
+  if (rc != HYPRET_OK) return rc;
+  return hypret_launch_mobius_epilogue_bwd(mx, n, d, xsq, bias, c, post_tanh, n_project, gy, gmx, gbias, gxn,
+                                           static_cast<cudaStream_t>(stream));
+}
+
+int hypret_sgemm_strided(const float* a, int64_t a_row_stride, int64_t a_col_stride, const float* b,
+                         int64_t b_row_stride, int64_t b_col_stride, int m, int n, int k, const float* row_scale,
+                         const float* addend, float* out, void* stream) {
+  if (m < 0 || n < 0 || k < 0 || ((row_scale == nullptr) != (addend == nullptr))) return HYPRET_EINVAL;
+  if (m == 0 || n == 0) return HYPRET_OK;
+  if (out == nullptr || (k > 0 && (a == nullptr || b == nullptr))) return HYPRET_EINVAL;
+  int rc = check_device();
+  if (rc != HYPRET_OK) return rc;
+  return hypret_launch_sgemm_strided(a, a_row_stride, a_col_stride, b, b_row_stride, b_col_stride, m, n, k, row_scale,
+                                     addend, out, static_cast<cudaStream_t>(stream));
+}
+
 int hypret_lse_combine(const float* parts, int n_parts, int64_t n, float* out, void* stream) {
   if (n_parts < 1 || n < 0) return HYPRET_EINVAL;
   if (n == 0) return HYPRET_OK;

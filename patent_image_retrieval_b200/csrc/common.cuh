@@ -437,6 +437,12 @@ int hypret_launch_flash(int bwd, const void* x_row_op, const void* y_col_op, con
                         const float* y_lse, int64_t n, int64_t m, int d, float c, float inv_tau, float wx, float wy,
                         const float* grad_scale, int64_t diag_offset, int64_t n_total, float* workspace, float* out,
                         cudaStream_t stream);
+int hypret_launch_mobius_epilogue_bwd(const float* mx, int64_t n, int d, const float* xsq, const float* bias, float c,
+                                      int post_tanh, int n_project, const float* gy, float* gmx, float* gbias,
+                                      float* gxn, cudaStream_t stream);
+int hypret_launch_sgemm_strided(const float* A, int64_t sam, int64_t sak, const float* B, int64_t sbk, int64_t sbn,
+                                int M, int N, int K, const float* row_scale, const float* addend, float* C,
+                                cudaStream_t stream);
 int hypret_launch_lse_combine(const float* parts, int w, int64_t n, float* out, cudaStream_t stream);
 int hypret_launch_mobius_gemm(const void* x_row_op, const void* w_col_op, int64_t n, int d_in, int n_out,
                               const float* xsq, const float* bias, float c, int post_tanh, int n_project, float* mx_out,

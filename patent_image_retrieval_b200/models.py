@@ -102,6 +102,14 @@ class DeeperHyperbolicEncoder(nn.Module):
                 and self.first_layer.bias is not None and self.final_layer.bias is not None
                 and self.first_layer.out_features % 4 == 0 and self.final_layer.out_features % 4 == 0)
 
+    def _kernel_train_ok(self, x):
+        from . import ops
+        return (x.is_cuda and x.dtype == torch.float32 and x.dim() == 2 and x.shape[0] > 0
+                and self.first_layer.bias is not None and self.final_layer.bias is not None
+                and self.first_layer.hyperbolic_bias and self.final_layer.hyperbolic_bias
+                and ops.mobius_gemm_ok(self.first_layer.in_features, self.first_layer.out_features)
+                and ops.mobius_gemm_ok(self.first_layer.out_features, self.final_layer.out_features))
+
     def forward(self, x):
         self.k = self.k.to(x.device)
         if self._fused_ok(x):
@@ -123,6 +131,16 @@ class DeeperHyperbolicEncoder(nn.Module):
             y, _ = ops.mobius_epilogue(F.linear(h, self.final_layer.weight.to(x.dtype)), c,
                                        bias=self.final_layer.bias, xsq=hsq, n_project=2, want_sqnorm=False)
             return y
+        if self._kernel_train_ok(x):
+            # training on the GPU: each layer is one autograd node whose forward is the fused GEMM kernel and whose
+            # backward is one closed-form epilogue kernel + the dense products (ops.MobiusLinearFn); only the two
+            # dropouts stay with torch
+            from . import ops
+            c = float(self.c)
+            x = F.dropout(x, p=self.dropout_rate, training=self.training)
+            x = ops.MobiusLinearFn.apply(x, self.first_layer.weight, self.first_layer.bias, c, False, True, 1)
+            x = F.dropout(x, p=self.dropout_rate, training=self.training)
+            return ops.MobiusLinearFn.apply(x, self.final_layer.weight, self.final_layer.bias, c, True, False, 2)
         x = F.dropout(x, p=self.dropout_rate, training=self.training)
         x = self.first_layer(x)
         x = pmath.mobius_fn_apply(torch.tanh, x, k=self.k)

@@ -589,18 +589,91 @@ def flash_grad(xo: FlashOperands, yo: FlashOperands, c: float, inv_tau: float, x
     return out
 
 
-def split_operand(x: torch.Tensor, side: str) -> torch.Tensor:
+def split_operand(x: torch.Tensor, side: str, want_sqnorm: bool = False):
     """fp16 2-way split GEMM operand of ``x [n,d]``: ``side='row'`` -> ``[hi|lo|hi]``, ``'col'`` -> ``[hi|hi|lo]``
-    (``hypret_flash_prep``); a row operand times a column operand is the fp32 product to 2^-22."""
+    (``hypret_flash_prep``); a row operand times a column operand is the fp32 product to 2^-22.
+    ``want_sqnorm``: also return ``||x_i||^2`` from the same pass."""
     _need_cuda(x)
     x = x.detach().contiguous().float()
     n, d = x.shape
     lib = _lib.load()
     op = torch.empty(n, int(lib.hypret_flash_kpad(d)), dtype=torch.float16, device=x.device)
+    sq = torch.empty(n, dtype=torch.float32, device=x.device) if want_sqnorm else None
     with torch.cuda.device(x.device):
         _lib.check(lib.hypret_flash_prep(_ptr(x), n, d, _ptr(op) if side == "row" else None,
-                                         _ptr(op) if side == "col" else None, None, 0, None, _stream()))
-    return op
+                                         _ptr(op) if side == "col" else None, None, 0, _ptr(sq), _stream()))
+    return (op, sq) if want_sqnorm else op
+
+
+def sgemm(a: torch.Tensor, b: torch.Tensor, row_scale: Optional[torch.Tensor] = None,
+          addend: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """``a @ b (+ row_scale[:, None] * addend)`` for fp32 2-D tensors of ANY strides (transposed views cost nothing):
+    the batch-sized products of the head's backward pass (``hypret_sgemm_strided``)."""
+    _need_cuda(a, b, row_scale, addend)
+    if a.dtype != torch.float32 or b.dtype != torch.float32 or a.dim() != 2 or b.dim() != 2 or a.shape[1] != b.shape[0]:
+        raise ValueError("sgemm: fp32 [m,k] @ [k,n]")
+    m, k = a.shape
+    n = b.shape[1]
+    out = torch.empty(m, n, dtype=torch.float32, device=a.device)
+    if row_scale is not None:
+        row_scale, addend = row_scale.contiguous().float(), addend.contiguous().float()
+        if row_scale.numel() != m or tuple(addend.shape) != (m, n):
+            raise ValueError("sgemm: row_scale [m], addend [m,n]")
+    with torch.cuda.device(a.device):
+        _lib.check(_lib.load().hypret_sgemm_strided(_ptr(a), a.stride(0), a.stride(1), _ptr(b), b.stride(0), b.stride(1),
+                                                    m, n, k, _ptr(row_scale), _ptr(addend), _ptr(out), _stream()))
+    return out
+
+
+def mobius_epilogue_bwd(mx: torch.Tensor, gy: torch.Tensor, c: float, bias: Optional[torch.Tensor] = None,
+                        xsq: Optional[torch.Tensor] = None, post_tanh: bool = False, n_project: int = 1):
+    """Backward of one MobiusLinear epilogue (``hypret_mobius_epilogue_bwd``): ``(gmx, gbias | None, gxn | None)`` with
+    ``dL/dx_in = gmx @ W + gxn[:, None] * x_in`` for a hyperbolic input."""
+    _need_cuda(mx, gy, bias, xsq)
+    mx, gy = mx.contiguous().float(), gy.contiguous().float()
+    n, d = mx.shape
+    gmx = torch.empty_like(mx)
+    b = bias.detach().contiguous().float() if bias is not None else None
+    gb = torch.zeros(d, dtype=torch.float32, device=mx.device) if bias is not None else None
+    xs = xsq.contiguous().float() if xsq is not None else None
+    gxn = torch.empty(n, dtype=torch.float32, device=mx.device) if xsq is not None else None
+    with torch.cuda.device(mx.device):
+        _lib.check(_lib.load().hypret_mobius_epilogue_bwd(_ptr(mx), n, d, _ptr(xs), _ptr(b), float(c),
+                                                          int(bool(post_tanh)), int(n_project), _ptr(gy), _ptr(gmx),
+                                                          _ptr(gb), _ptr(gxn), _stream()))
+    return gmx, gb, gxn
+
+
+class MobiusLinearFn(torch.autograd.Function):
+    """One MobiusLinear layer, forward AND backward, as kernels of this library: forward = two operand splits + one
+    ``hypret_mobius_gemm``; backward = one ``hypret_mobius_epilogue_bwd`` + the dense products dW = gmx^T x and
+    dx = gmx W (+ gxn x).  Replaces the ~35 autograd nodes per layer of src/models.py:291-318."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, c: float, hyperbolic_input: bool, post_tanh: bool, n_project: int):
+        x32 = x.detach().contiguous().float()
+        w32 = weight.detach().contiguous().float()
+        n_out, d_in = w32.shape
+        xo, xsq = split_operand(x32, "row", want_sqnorm=True)
+        out = mobius_gemm(xo, split_operand(w32, "col"), d_in, n_out, c, bias=bias,
+                          xsq=xsq if hyperbolic_input else None, post_tanh=post_tanh, n_project=n_project, want_y=True,
+                          want_mx=True)
+        ctx.save_for_backward(x32, w32, bias.detach() if bias is not None else None, out["mx"], xsq)
+        ctx.cfg = (float(c), bool(hyperbolic_input), bool(post_tanh), int(n_project), x.dtype, weight.dtype,
+                   bias.dtype if bias is not None else None)
+        return out["y"].to(x.dtype)
+
+    @staticmethod
+    def backward(ctx, gy):
+        x32, w32, bias, mx, xsq = ctx.saved_tensors
+        c, hyp, post_tanh, n_project, xdt, wdt, bdt = ctx.cfg
+        gmx, gb, gxn = mobius_epilogue_bwd(mx, gy, c, bias=bias, xsq=xsq if hyp else None, post_tanh=post_tanh,
+                                           n_project=n_project)
+        gw = sgemm(gmx.t(), x32).to(wdt) if ctx.needs_input_grad[1] else None
+        gx = None
+        if ctx.needs_input_grad[0]:
+            gx = sgemm(gmx, w32, gxn, x32 if gxn is not None else None).to(xdt)
+        return gx, gw, (gb.to(bdt) if gb is not None and ctx.needs_input_grad[2] else None), None, None, None, None
 
 
 def mobius_gemm_ok(d_in: int, n_out: int) -> bool:

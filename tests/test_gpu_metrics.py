@@ -411,3 +411,73 @@ def test_mobius_gemm_head_matches_oracle(d_in, hid, d_out, c, b):
     assert float(((got - want).abs() / scale).max()) < 2e-5
     assert float(got.norm(dim=1).max()) <= (1 - 4e-3) / c ** 0.5 * (1 + 1e-6)
     assert torch.equal(got[0], got[0]) and bool(torch.isfinite(got).all())
+
+
+@pytest.mark.parametrize("d_in,hid,d_out,c,b,wscale", [(512, 256, 128, 1.0, 128, 1.0), (768, 128, 64, 0.5, 77, 1.0),
+                                                       (64, 32, 16, 2.0, 200, 4.0)])
+def test_head_training_step_matches_autograd(d_in, hid, d_out, c, b, wscale, monkeypatch):
+    """train_hyp's head on the kernel path (ops.MobiusLinearFn: fused GEMM kernel forward, closed-form epilogue kernel +
+    dense products backward) against autograd through the op-by-op path of the same module on the CPU
+    (src/models.py:291-318, 481-505): output, dL/dW1, dL/db1, dL/dW2, dL/db2 and dL/dx.  Truth is the fp64 run (with
+    geoopt's fp32 project margin); the bar is 5e-5 of the tensor's scale or twice the error of the reference's own fp32
+    autograd, whichever is larger -- the first layer saturates (tanh(|mx|) ~ 1), where dL/db1 is ~1e-6 and fp32 noise
+    dominates it in BOTH implementations."""
+    import copy
+    from patent_image_retrieval_b200 import models
+    from patent_image_retrieval_b200.geoopt_shim import pmath
+    real_project = pmath.project
+    monkeypatch.setattr(pmath, "project", lambda x, *, k, dim=-1, eps=-1.0: real_project(x, k=k, dim=dim, eps=4e-3))
+    torch.manual_seed(21)
+    m = models.DeeperHyperbolicEncoder(d_in, [hid], d_out, c=c, dropout_rate=0.0).train()
+    with torch.no_grad():
+        m.first_layer.weight.mul_(wscale)                    # wscale 4: rows reach the project clip
+    x = torch.randn(b, d_in) * 0.5
+    r = torch.randn(b, d_out)
+    names = [n for n, _ in m.named_parameters() if not n.endswith("isp_c")]
+    res = {}
+    for tag in ("f64", "f32", "gpu"):
+        mod = copy.deepcopy(m)
+        if tag == "f64":
+            mod, xx, rr = mod.double(), x.double().requires_grad_(True), r.double()
+        elif tag == "f32":
+            xx, rr = x.clone().requires_grad_(True), r
+        else:
+            mod, xx, rr = mod.cuda(), x.cuda().requires_grad_(True), r.cuda()
+            assert mod._kernel_train_ok(xx)
+        y = mod(xx)
+        (y * rr).sum().backward()
+        res[tag] = [y.detach().cpu().double(), xx.grad.cpu().double()] + \
+                   [mod.get_parameter(n).grad.cpu().double() for n in names]
+    for i, what in enumerate(["y", "dx"] + names):
+        truth = res["f64"][i]
+        scale = float(truth.abs().max())
+        e32 = float((res["f32"][i] - truth).abs().max())
+        egpu = float((res["gpu"][i] - truth).abs().max())
+        assert egpu <= max(5e-5 * scale, 2.0 * e32), (what, egpu, e32, scale)
+
+
+def test_head_training_step_dropout_same_masks_as_eager():
+    """With dropout on, the kernel path draws its masks with the same two F.dropout calls as the op-by-op path, so under
+    one seed both see identical masks: outputs and gradients agree to fp32 rounding (the biases: to the noise floor of
+    their saturated gradients, see the test above)."""
+    import copy
+    from patent_image_retrieval_b200 import models
+    torch.manual_seed(3)
+    m = models.DeeperHyperbolicEncoder(512, [256], 128, c=1.0, dropout_rate=0.3).cuda().train()
+    eager = copy.deepcopy(m)
+    eager._kernel_train_ok = lambda x: False
+    x = torch.randn(128, 512, device="cuda") * 0.5
+    r = torch.randn(128, 128, device="cuda")
+    names = [n for n, _ in m.named_parameters() if not n.endswith("isp_c")]
+    outs = []
+    for mod in (m, eager):
+        torch.manual_seed(77)
+        torch.cuda.manual_seed(77)
+        y = mod(x)
+        (y * r).sum().backward()
+        outs.append((y.detach(), {n: mod.get_parameter(n).grad.clone() for n in names}))
+    assert float((outs[0][0] - outs[1][0]).abs().max()) < 2e-5
+    for n in names:
+        a, w = outs[0][1][n], outs[1][1][n]
+        floor = 1e-4 if n.endswith("bias") else 0.0       # saturated layers: bias gradients ~1e-4 and below
+        assert float((a - w).abs().max()) <= max(floor, 5e-4 * float(w.abs().max())), (n, float((a - w).abs().max()), float(w.abs().max()))
