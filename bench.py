@@ -293,6 +293,7 @@ def main():
 
     from patent_image_retrieval_b200 import SearchPipeline, StageEvents, ops, synth
     from patent_image_retrieval_b200.dist import ShardedGalleryIndex, shard_range
+    from patent_image_retrieval_b200.retrieval import default_kprime
     import torch.distributed as dist
 
     torch.cuda.set_device(local_rank)
@@ -328,7 +329,7 @@ def main():
     q_host.copy_(q_dev)
     out_d_host = torch.empty(Q, k, dtype=torch.float32, pin_memory=True)
     out_i_host = torch.empty(Q, k, dtype=torch.int64, pin_memory=True)
-    kprime = 16
+    kprime = default_kprime(k)                  # what search() uses when the caller does not choose (24 at k=10)
     plan = ops.score_plan(q_total if weak else Q, hi - lo, D, kprime)
 
     def barrier():

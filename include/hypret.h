@@ -213,6 +213,21 @@ int hypret_rerank_cert(const float* q32, const float* g32, int64_t Q, int64_t N,
 int hypret_exact_topk(const float* q32, const float* g32, const double* g_sqnorm64, int64_t Q, int64_t N, int d,
                       float c, int metric, int k, int64_t idx_offset, const int32_t* q_list, const int32_t* q_count,
                       int32_t* fb_state, float* out_score, int64_t* out_idx, void* stream);
+/* Exact-top-k certificate of a MERGED result, for a row-sharded gallery whose queries are owned by one rank each
+ * (dist.ShardedGalleryIndex.search_sharded): score/idx [Q,k] = the merged exact lists, thr [Q] = the global k'-th best
+ * filter score of each query (hypret_kth_smallest over every shard's list), q_err [Q] = the rounding residuals of the
+ * owner's query operands (hypret_project_rows_cert / _peers), g_stats [4] = the MAXIMA over all shards of the gallery
+ * statistics.  flags [Q] int32 out: 0 = proven exact (as hypret_rerank_cert: thr - S_kth > E), 1 = not proven -- those
+ * queries go through hypret_exact_topk on every shard.  out_margin [Q] or NULL. */
+int hypret_cert_merged(const float* q32, int64_t Q, int d, float c, int metric, const float* score, const int64_t* idx,
+                       int k, const float* thr, const float* q_err, const float* g_stats, int32_t* flags,
+                       float* out_margin, void* stream);
+
+/* flags [n] int32 (non-zero = listed) -> q_list (the flagged positions, any order), *q_count, and the fb_state words of
+ * the flagged queries reset: the inputs hypret_exact_topk expects, built on the device. */
+int hypret_flag_compact(const int32_t* flags, int64_t n, int32_t* q_list, int32_t* q_count, int32_t* fb_state,
+                        void* stream);
+
 /* The next page of the same exact ranking: only rows whose key (ordered fp32 score << 32 | local row id, the order of the
  * result lists) lies ABOVE after[i] for list entry i are taken.  Paging through the ranking 32 rows at a time gives the
  * exact top-k for any k (notebooks/retrieval.ipynb:202 with k beyond the 128 the filtered path serves). */

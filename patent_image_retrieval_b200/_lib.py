@@ -127,6 +127,9 @@ SIGNATURES = {
                                            c_void_p, c_void_p, c_void_p, c_void_p]),
     "hypret_sgemm_strided": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_int64, c_int64, c_int, c_int, c_int,
                                      c_void_p, c_void_p, c_void_p, c_void_p]),
+    "hypret_cert_merged": (c_int, [c_void_p, c_int64, c_int, c_float, c_int, c_void_p, c_void_p, c_int, c_void_p,
+                                   c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "hypret_flag_compact": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p]),
     "hypret_lse_combine": (c_int, [c_void_p, c_int, c_int64, c_void_p, c_void_p]),
     "hypret_flash_kpad": (c_int64, [c_int]),
     "hypret_flash_workspace": (c_int64, [c_int64, c_int64, c_int]),

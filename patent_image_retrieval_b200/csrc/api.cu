@@ -249,6 +249,32 @@ int hypret_exact_topk_after(const float* q32, const float* g32, const double* g_
                                   static_cast<cudaStream_t>(stream));
 }
 
+int hypret_cert_merged(const float* q32, int64_t Q, int d, float c, int metric, const float* score, const int64_t* idx,
+                       int k, const float* thr, const float* q_err, const float* g_stats, int32_t* flags,
+                       float* out_margin, void* stream) {
+  if (Q < 0 || d < 4 || (d & 3) || k < 1) return HYPRET_EINVAL;
+  if (metric != HYPRET_METRIC_COSINE && metric != HYPRET_METRIC_HYPERBOLIC) return HYPRET_EINVAL;
+  if (metric == HYPRET_METRIC_HYPERBOLIC && !(c > 0.f)) return HYPRET_EINVAL;
+  if (Q == 0) return HYPRET_OK;
+  if (q32 == nullptr || score == nullptr || idx == nullptr || thr == nullptr || q_err == nullptr ||
+      g_stats == nullptr || flags == nullptr || !aligned16(q32))
+    return HYPRET_EINVAL;
+  int rc = check_device();
+  if (rc != HYPRET_OK) return rc;
+  const float slack = (float)(hypret_kpad(d) / 16 + 8) * 2.384185791015625e-07f;     // as hypret_rerank_cert
+  return hypret_launch_cert_merged(q32, Q, d, c, metric, score, idx, k, thr, q_err, g_stats, slack, flags, out_margin,
+                                   static_cast<cudaStream_t>(stream));
+}
+
+int hypret_flag_compact(const int32_t* flags, int64_t n, int32_t* list, int32_t* count, int32_t* fb_state,
+                        void* stream) {
+  if (n < 0 || n > 0x7fffffffll) return HYPRET_EINVAL;
+  if (count == nullptr || (n > 0 && (flags == nullptr || list == nullptr || fb_state == nullptr))) return HYPRET_EINVAL;
+  int rc = check_device();
+  if (rc != HYPRET_OK) return rc;
+  return hypret_launch_flag_compact(flags, n, list, count, fb_state, static_cast<cudaStream_t>(stream));
+}
+
 int hypret_row_sqnorm64(const float* x, int64_t n, int d, double* out, void* stream) {
   if (n < 0 || d < 4 || (d & 3)) return HYPRET_EINVAL;
   if (n == 0) return HYPRET_OK;

@@ -443,6 +443,11 @@ int hypret_launch_mobius_epilogue_bwd(const float* mx, int64_t n, int d, const f
 int hypret_launch_sgemm_strided(const float* A, int64_t sam, int64_t sak, const float* B, int64_t sbk, int64_t sbn,
                                 int M, int N, int K, const float* row_scale, const float* addend, float* C,
                                 cudaStream_t stream);
+int hypret_launch_cert_merged(const float* q32, int64_t Q, int d, float c, int metric, const float* score,
+                              const int64_t* idx, int k, const float* thr, const float* q_err, const float* g_stats,
+                              float slack, int32_t* flags, float* out_margin, cudaStream_t stream);
+int hypret_launch_flag_compact(const int32_t* flags, int64_t n, int32_t* list, int32_t* count, int32_t* state,
+                               cudaStream_t stream);
 int hypret_launch_lse_combine(const float* parts, int w, int64_t n, float* out, cudaStream_t stream);
 int hypret_launch_mobius_gemm(const void* x_row_op, const void* w_col_op, int64_t n, int d_in, int n_out,
                               const float* xsq, const float* bias, float c, int post_tanh, int n_project, float* mx_out,

@@ -245,6 +245,66 @@ exact_topk_kernel(const float* __restrict__ q32, const float* __restrict__ g32, 
   }
 }
 
+// ---- the certificate of a MERGED result (row-sharded gallery, queries owned by one rank) ---------------------------
+// The owner of query q holds its merged exact top-k (from every shard's pruned rerank) and the global k'-th best filter
+// score thr[q] (hypret_kth_smallest over the shards' lists): every row of every shard outside the global candidate set
+// has a filter score >= thr[q], and an exact surrogate within E of it (E from the query's own rounding residual and
+// the MAXIMA over all shards of the gallery statistics).  thr - S_kth > E proves the merged list exact, as in
+// rerank_kernel; S_kth is recovered from the emitted distance: S = (cosh(sqrt(c) d) - 1) (1 - c |x|^2) / 2.
+// flags[q] = 1 when the proof FAILS (the query then goes through the exact scan of every shard).
+__global__ void __launch_bounds__(128)
+cert_merged_kernel(const float* __restrict__ q32, int64_t Q, int d, float c, int metric, const float* __restrict__ score,
+                   const int64_t* __restrict__ idx, int k, const float* __restrict__ thr,
+                   const float* __restrict__ q_err, const float* __restrict__ g_stats, float slack,
+                   int32_t* __restrict__ flags, float* __restrict__ out_margin) {
+  const int lane = threadIdx.x & 31;
+  const int64_t q = (int64_t)blockIdx.x * 4 + (threadIdx.x >> 5);
+  if (q >= Q) return;
+  double xsq = 0.0;
+  for (int j = lane; j < (d >> 2); j += 32) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(q32 + q * d) + j);
+    xsq += (double)v.x * v.x + (double)v.y * v.y + (double)v.z * v.z + (double)v.w * v.w;
+  }
+  xsq = warp_sum(xsq);
+  if (lane != 0) return;
+  const double cc = (double)c;
+  const bool hyp = metric == HYPRET_METRIC_HYPERBOLIC;
+  const double dk = (double)score[q * k + k - 1];
+  const bool open_set = idx[q * k + k - 1] < 0 || !(thr[q] < INFINITY);   // fewer than k rows / k' candidates in all
+  double sur;
+  if (hyp) {
+    const double a = sqrt(cc) * dk;
+    sur = (cosh(a) - 1.0) * (1.0 - cc * xsq) * 0.5 * (1.0 + 4e-7);      // d is the fp32 rounding of the fp64 distance
+  } else {
+    sur = -dk + 1e-7 * fabs(dk);
+  }
+  const double qn = hyp ? sqrt(cc * xsq) : 1.0;
+  const double zmax = g_stats[0], dzmax = g_stats[1], rbmax = g_stats[2], bmax = g_stats[3];
+  const double E = (double)q_err[q] * zmax + qn * dzmax + (double)slack * (qn * zmax + qn * qn * rbmax + bmax);
+  const double margin = (double)thr[q] - sur;
+  if (out_margin != nullptr) out_margin[q] = open_set ? INFINITY : (float)margin;
+  flags[q] = (open_set || margin > E) ? 0 : 1;
+}
+
+// flags [n] (non-zero = listed) -> list of the flagged positions + count, and the lock words of those queries reset
+// for exact_topk_kernel.  One CTA; the order of the list does not matter.
+__global__ void __launch_bounds__(256)
+flag_compact_kernel(const int32_t* __restrict__ flags, int64_t n, int32_t* __restrict__ list,
+                    int32_t* __restrict__ count, int32_t* __restrict__ state) {
+  __shared__ int total;
+  if (threadIdx.x == 0) total = 0;
+  __syncthreads();
+  for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
+    if (flags[i] != 0) {
+      list[atomicAdd(&total, 1)] = (int32_t)i;
+      state[2 * i] = 0;
+      state[2 * i + 1] = 0;
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) *count = total;
+}
+
 }  // namespace
 
 int hypret_launch_exact_topk(const float* q32, const float* g32, const double* g_sq64, int64_t Q, int64_t N, int d,
@@ -280,4 +340,19 @@ int hypret_launch_exact_topk(const float* q32, const float* g32, const double* g
   if (need <= 16) HYPRET_EXACT_LAUNCH(16);
 #undef HYPRET_EXACT_LAUNCH
   return HYPRET_EUNSUPPORTED;
+}
+
+int hypret_launch_cert_merged(const float* q32, int64_t Q, int d, float c, int metric, const float* score,
+                              const int64_t* idx, int k, const float* thr, const float* q_err, const float* g_stats,
+                              float slack, int32_t* flags, float* out_margin, cudaStream_t stream) {
+  if (Q == 0) return HYPRET_OK;
+  cert_merged_kernel<<<(unsigned)((Q + 3) / 4), 128, 0, stream>>>(q32, Q, d, c, metric, score, idx, k, thr, q_err,
+                                                                  g_stats, slack, flags, out_margin);
+  return (int)cudaGetLastError();
+}
+
+int hypret_launch_flag_compact(const int32_t* flags, int64_t n, int32_t* list, int32_t* count, int32_t* state,
+                               cudaStream_t stream) {
+  flag_compact_kernel<<<1, 256, 0, stream>>>(flags, n, list, count, state);
+  return (int)cudaGetLastError();
 }

@@ -206,10 +206,11 @@ class PeerQueryExchange:
     def _off(self, slot: int, points: bool) -> int:
         return self.FLAGS_BYTES + slot * self.slot_bytes + (self.op_bytes if points else 0)
 
-    def publish(self, q_local: torch.Tensor, c: float, mode: str):
+    def publish(self, q_local: torch.Tensor, c: float, mode: str, op_err: Optional[torch.Tensor] = None):
         """Queue projection + exchange of this rank's batch on the current stream.  Returns
         ``(q_op_all [W*Ql,kpad] fp16, q32_all [W*Ql,D] fp32)`` (rank-major); ``q_op_all`` is complete for whatever is
-        queued behind this call, ``q32_all`` only behind ``wait_points()``."""
+        queued behind this call, ``q32_all`` only behind ``wait_points()``.  ``op_err`` [Ql] fp32 (optional) receives the
+        rounding-residual norms of this rank's operand rows (the certificate's ``q_err``)."""
         if tuple(q_local.shape) != (self.ql, self.d) or q_local.dtype != torch.float32 or not q_local.is_cuda:
             raise ValueError(f"expected a CUDA float32 batch of shape [{self.ql}, {self.d}]")
         q_local = q_local.contiguous()
@@ -226,7 +227,7 @@ class PeerQueryExchange:
             cosine = mode == "cosine"
             _lib.check(lib.hypret_project_rows_peers(ctypes.c_void_p(q_local.data_ptr()), self.ql, self.d, float(c),
                                                      ops.MODE[mode], None if cosine else ctypes.c_void_p(my_pt), dsts,
-                                                     W, None, cur_p))
+                                                     W, ops._ptr(op_err), cur_p))
             if cosine:                         # cosine reranks from the raw rows
                 _lib.check(lib.hypret_peer_copy(ctypes.c_void_p(my_pt), ctypes.c_void_p(q_local.data_ptr()),
                                                 self.pt_blk, cur_p))
@@ -369,6 +370,17 @@ class ShardedGalleryIndex:
         self.metric = metric
         self._exchange = None
         self._exchange_ok = None
+        self._stats_all = None          # maxima over ALL shards of the gallery statistics (certificate of merged lists)
+        self.uncertified = None         # [Ql] int32 of the last search_sharded: 1 = recomputed by the exact scan
+
+    def stats_all(self) -> torch.Tensor:
+        """``local.stats`` maximised over the shards (one all_reduce, at first use; collective)."""
+        if self._stats_all is None:
+            st = self.local.stats.clone()
+            if not self._single():
+                dist.all_reduce(st, op=dist.ReduceOp.MAX, group=self.group)
+            self._stats_all = st
+        return self._stats_all
 
     def _peer_exchange(self, n_queries: int) -> Optional[PeerQueryExchange]:
         """The peer-memory exchange for ``n_queries``-row batches (built at first use; collective), or None."""
@@ -409,7 +421,7 @@ class ShardedGalleryIndex:
         return ops.merge_topk(gs, gi, descending=(self.metric == "cosine"))
 
     def search_sharded(self, q_local: torch.Tensor, k: int = 10, kprime: Optional[int] = None,
-                       kernel_events: Optional[list] = None, prune: Optional[bool] = None):
+                       kernel_events: Optional[list] = None, prune: Optional[bool] = None, exact: bool = True):
         """Serving layout: all_gather the per-rank batches, score them all against this shard,
         all_to_all the lists back to the query owners, merge.  Returns ``[Ql,k]`` for ``q_local``.
         On one NVLink box the all_gather is the projection kernel itself storing into every rank's exchange
@@ -420,21 +432,53 @@ class ShardedGalleryIndex:
         query owner (all_to_all), which takes the k'-th smallest of the W*k' values (``hypret_kth_smallest``)
         and all_gathers that threshold; each shard then rescores exactly only the candidates at or below it
         (``hypret_rerank_pruned``), so the gather traffic of the rerank is shared between the shards instead
-        of being repeated on each of them.  The merged result is the list the single-GPU path returns."""
+        of being repeated on each of them.  The merged result is the list the single-GPU path returns.
+
+        ``exact`` (with ``prune``): the owner proves its merged lists exact (``hypret_cert_merged``: global k'-th best
+        filter score minus the exact surrogate of the k-th result against the rounding bound); the flags of the queries
+        it cannot prove are all_gathered, every shard rescans those queries exactly (``hypret_exact_topk``, list
+        built on the device) and the owners merge the scans -- fixed-size collectives, no host round trip;
+        ``self.uncertified`` keeps the flags."""
         from .retrieval import default_kprime
         world = dist.get_world_size(self.group)
         q_local = q_local.to(device=self.local.device, dtype=torch.float32, non_blocking=True)
         kp = min(default_kprime(k) if kprime is None else int(kprime), ops.MAX_KPRIME)
         if prune is None:
             prune = k <= 32 and kp <= 32 and k <= kp
-        ex = self._peer_exchange(q_local.shape[0])
+        exact = bool(exact and prune)
+        ql, me = q_local.shape[0], dist.get_rank(self.group)
+        stats_all = self.stats_all() if exact else None
+        ex = self._peer_exchange(ql)
+        q_err = None
         if ex is not None:
+            q_err = torch.empty(ql, dtype=torch.float32, device=q_local.device) if exact else None
             with _span(kernel_events, "project"):
-                q_op, q32 = ex.publish(q_local, self.local.c, self.local._query_mode())
+                q_op, q32 = ex.publish(q_local, self.local.c, self.local._query_mode(), op_err=q_err)
             q32, cs, ci, cnt = self.local.score_projected(q32, q_op, k=k, kprime=kprime, kernel_events=kernel_events)
         else:
             q_all = gather_queries(q_local, self.group)
-            q32, cs, ci, cnt, _ = self.local.score_candidates(q_all, k=k, kprime=kprime, kernel_events=kernel_events)
+            q32, cs, ci, cnt, q_err = self.local.score_candidates(q_all, k=k, kprime=kprime,
+                                                                  kernel_events=kernel_events, want_err=exact)
+            q_err = q_err[me * ql:(me + 1) * ql] if exact else None
+
+        def finish(rs, ri, thr_all):
+            score, idx = ops.merge_topk(rs, ri, descending=(self.metric == "cosine"))
+            if not exact:
+                self.uncertified = None
+                return score, idx
+            with _span(kernel_events, "certify"):
+                own = slice(me * ql, (me + 1) * ql)
+                flags = ops.cert_merged(q32[own], score, idx, thr_all[own], q_err, stats_all, self.local.c, self.metric)
+                flags_all = torch.empty(world * ql, dtype=torch.int32, device=flags.device)
+                dist.all_gather_into_tensor(flags_all, flags, group=self.group)
+                xs, xi = ops.exact_topk_flagged(q32, self.local.rows32, self.local.rows_sq64, flags_all, self.local.c,
+                                                self.metric, k, idx_offset=self.local.idx_offset)
+                xs, xi = return_lists_to_owners(xs, xi, self.group)
+                xs, xi = ops.merge_topk(xs, xi, descending=(self.metric == "cosine"))
+                redo = flags.bool()[:, None]
+                self.uncertified = flags
+                return torch.where(redo, xs, score), torch.where(redo, xi, idx)
+
         thr_all = None
         if prune and ex is not None and os.environ.get("HYPRET_PEER_ROUTE", "1") != "0":
             # every exchange is done by the kernel that produces the data (NVLink stores into the receivers'
@@ -444,7 +488,7 @@ class ShardedGalleryIndex:
             ex.wait_points()
             with _span(kernel_events, "rerank"):
                 rs, ri = ex.rerank_to_owners(self.local, q32, sel_s, sel_i, k, thr_all)
-            return ops.merge_topk(rs, ri, descending=(self.metric == "cosine"))
+            return finish(rs, ri, thr_all)
         if prune:
             sel_s, sel_i = ops.cand_select(cs, ci, cnt)                              # [W*Ql, k']
             recv = torch.empty_like(sel_s)
@@ -458,7 +502,10 @@ class ShardedGalleryIndex:
         score, idx = self.local.rerank_candidates(q32, cs, ci, k, prune_thr=thr_all, kernel_events=kernel_events,
                                                   list_count=cnt)
         rs, ri = return_lists_to_owners(score, idx, self.group)
-        return ops.merge_topk(rs, ri, descending=(self.metric == "cosine"))
+        if thr_all is None:
+            self.uncertified = None
+            return ops.merge_topk(rs, ri, descending=(self.metric == "cosine"))
+        return finish(rs, ri, thr_all)
 
 
 def _explicitly_sharded(sharded: Optional[bool], group) -> bool:

@@ -256,6 +256,43 @@ def exact_topk(q32: torch.Tensor, g32: torch.Tensor, g_sqnorm64: torch.Tensor, c
     return out_s, out_i
 
 
+def cert_merged(q32: torch.Tensor, score: torch.Tensor, idx: torch.Tensor, thr: torch.Tensor, q_err: torch.Tensor,
+                g_stats: torch.Tensor, c: float, metric: str, want_margin: bool = False):
+    """Certificate of merged lists (``hypret_cert_merged``): ``flags [Q] int32``, 1 = NOT proven exact."""
+    _need_cuda(q32, score, idx, thr, q_err, g_stats)
+    q32, score, idx = q32.contiguous(), score.contiguous(), idx.contiguous()
+    Q, d = q32.shape
+    flags = torch.empty(Q, dtype=torch.int32, device=q32.device)
+    margin = torch.empty(Q, dtype=torch.float32, device=q32.device) if want_margin else None
+    with torch.cuda.device(q32.device):
+        _lib.check(_lib.load().hypret_cert_merged(_ptr(q32), Q, d, float(c), METRIC[metric], _ptr(score), _ptr(idx),
+                                                  score.shape[1], _ptr(thr.contiguous()), _ptr(q_err.contiguous()),
+                                                  _ptr(g_stats), _ptr(flags), _ptr(margin), _stream()))
+    return (flags, margin) if want_margin else flags
+
+
+def exact_topk_flagged(q32: torch.Tensor, g32: torch.Tensor, g_sqnorm64: torch.Tensor, flags: torch.Tensor, c: float,
+                       metric: str, k: int, idx_offset: int = 0):
+    """Exact top-k over this shard of the FLAGGED queries only (``hypret_flag_compact`` + ``hypret_exact_topk``, the
+    list built and read on the device).  Returns ``(score [Q,k], idx [Q,k])``; rows of unflagged queries are +-inf / -1."""
+    _need_cuda(q32, g32, g_sqnorm64, flags)
+    q32, g32 = q32.contiguous(), g32.contiguous()
+    Q, d = q32.shape
+    dev = q32.device
+    out_s = torch.full((Q, k), float("inf") if metric == "hyperbolic" else float("-inf"), dtype=torch.float32, device=dev)
+    out_i = torch.full((Q, k), -1, dtype=torch.int64, device=dev)
+    lst = torch.empty(Q, dtype=torch.int32, device=dev)
+    cnt = torch.empty(1, dtype=torch.int32, device=dev)
+    state = torch.empty(2 * Q, dtype=torch.int32, device=dev)
+    lib = _lib.load()
+    with torch.cuda.device(dev):
+        _lib.check(lib.hypret_flag_compact(_ptr(flags.contiguous()), Q, _ptr(lst), _ptr(cnt), _ptr(state), _stream()))
+        _lib.check(lib.hypret_exact_topk(_ptr(q32), _ptr(g32), _ptr(g_sqnorm64), Q, g32.shape[0], d, float(c),
+                                         METRIC[metric], int(k), int(idx_offset), _ptr(lst), _ptr(cnt), _ptr(state),
+                                         _ptr(out_s), _ptr(out_i), _stream()))
+    return out_s, out_i
+
+
 def _packed_keys(score: torch.Tensor, idx: torch.Tensor, metric: str, idx_offset: int) -> torch.Tensor:
     """The 64-bit ordering keys of result entries: ordered fp32 key << 32 | local row id (csrc/exact.cu)."""
     key = score if metric == "hyperbolic" else -score

@@ -63,13 +63,16 @@ WIDE_MIN_LISTS = 4     # wide top-k: candidate lists per query (4 x 64 = 256 can
 
 
 def default_kprime(k: int) -> int:
-    """List slots per strip.  k <= 26: one list of k+6 (>= 16) slots suffices (threshold sharing keeps the
-    union equal to the global approximate top-k').  Larger k ("wide", up to 128): 64-slot lists, at least
+    """List slots per strip.  k <= 26: one list of k+14 slots (24..32; threshold sharing keeps the union equal to the
+    global approximate top-k').  The 14 spare slots are what the certificate needs: at k' = k+6 about 1e-4 of the
+    (query, 1M..10M-row shard) pairs have their k-th..k'-th candidates within the rounding bound E and fall to the
+    exact scan (4.5 ms for one query over 5M rows); at k+14 the 1 % margin quantile is 8 E and the scoring kernel is no
+    slower (tools/diag_cert.py, profiles/README.md).  Larger k ("wide", up to 128): 64-slot lists, at least
     ``WIDE_MIN_LISTS`` independent lists per query, no threshold sharing -- the top-k is in the union unless
     one strip holds more than 64 of the k best rows, which ``margin`` certifies per query."""
     if k > ops.MAX_K:
         raise ValueError(f"k={k} exceeds the supported maximum {ops.MAX_K}")
-    return max(16, k + 6) if k <= 26 else 64
+    return min(32, max(24, k + 14)) if k <= 26 else 64
 
 
 class GalleryIndex:

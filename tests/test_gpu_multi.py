@@ -58,6 +58,37 @@ for metric in ("hyperbolic", "cosine"):
     assert torch.equal(i7, i6) and torch.equal(d7, d6), metric + " peer queries + nccl lists"
     shd._exchange.check()
     shd._exchange.close()
+# the exact-top-k guarantee of the sharded path: on a near-duplicate gallery the owners cannot certify most merged lists;
+# the flagged queries are rescanned exactly on every shard and the result must be the exact scan of the whole gallery
+from oracle import head as ohead
+for metric in ("hyperbolic", "cosine"):
+    gal, qry, _, _ = synth.clustered_features(6000, 2 * 128, 256, noise=1e-3, per_class=24)
+    space = "euclidean"
+    if metric == "hyperbolic":
+        gal, qry, space = ohead.embed_rows(gal, 1.0), ohead.embed_rows(qry, 1.0), "ball"
+    gal, qry = gal.to(dev), qry.to(dev)
+    lo2, hi2 = shard_range(gal.shape[0], rank, world)
+    full = GalleryIndex(gal, c=1.0, metric=metric, space=space)
+    want_d, want_i = ops.exact_topk(qry[rank * 128:(rank + 1) * 128].contiguous(), full.rows32, full.rows_sq64,
+                                    1.0, metric, k)
+    for peer in (True, False):
+        shd = ShardedGalleryIndex(gal[lo2:hi2], lo2, gal.shape[0], metric=metric, space=space, queries="sharded")
+        if not peer:
+            shd._exchange_ok = False
+        got_d, got_i = shd.search(qry[rank * 128:(rank + 1) * 128], k=k)
+        n_unc = int(shd.uncertified.sum())
+        assert n_unc > 0, "near-duplicate gallery: expected uncertified merged lists"
+        assert torch.equal(got_i, want_i) and torch.equal(got_d, want_d), (metric, peer, "sharded exactness", n_unc)
+        loose_d, loose_i = shd.search_sharded(qry[rank * 128:(rank + 1) * 128], k=k, exact=False)
+        assert shd.uncertified is None
+        if shd._exchange is not None:
+            shd._exchange.check()
+            shd._exchange.close()
+    # gaussian data: everything certified, flags all zero
+shd = ShardedGalleryIndex(g[lo:hi], lo, N, queries="sharded")
+shd.search(synth.gaussian_features(Ql, D, seed=10 + rank).to(dev), k=k)
+assert int(shd.uncertified.sum()) == 0
+shd._exchange.close()
 # collective 2: exact full-ranking AP from all-reduced keys / rank counts == the unsharded computation
 from patent_image_retrieval_b200.dist import full_ranking_ap
 from patent_image_retrieval_b200 import ops

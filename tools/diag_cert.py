@@ -8,12 +8,19 @@ import torch
 sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
 from patent_image_retrieval_b200 import GalleryIndex, ops, synth  # noqa: E402
 
-d, c, k, Q = 512, 1.0, 10, 2048
+import os
+d, c, k, Q = 512, 1.0, 10, int(os.environ.get('DIAG_Q', 2048))
 for N in [int(a) for a in sys.argv[1:]] or [30_000, 300_000]:
-    index = GalleryIndex(synth.gaussian_features(N, d, seed=0, device="cuda"), c=c)
+    index = GalleryIndex(synth.gallery_rows(0, N, d, "cuda"), c=c)
     qry = synth.gaussian_features(Q, d, seed=1, device="cuda")
     for kp in (16, 24, 32):
-        q32, cs, ci, cnt, q_err = index.score_candidates(qry, k=k, kprime=kp, want_err=True)
+        for _ in range(2):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            q32, cs, ci, cnt, q_err = index.score_candidates(qry, k=k, kprime=kp, want_err=True)
+            e1.record()
+            torch.cuda.synchronize()
+        print(f"   score_candidates k'={kp}: {e0.elapsed_time(e1):.2f} ms")
         bufs = ops.CertBuffers(Q, index.device)
         _, _, margin = ops.rerank_cert(q32, index.rows32, cs, ci, c, "hyperbolic", k, q_err, index.stats,
                                        index.rows_sq64, bufs, list_count=cnt, fallback=False, want_margin=True)
