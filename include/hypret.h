@@ -378,10 +378,6 @@ int64_t hypret_gram_kpad(int d);
  * (w_format 1) of the two functions above, cut from an fp32 W in one streaming pass -- faster than emitting the
  * planes from inside the backward pass.  count % 4 == 0. */
 int hypret_split3(const float* x, int64_t count, void* out_bf16, void* stream);
-/* The same with the planes interleaved per row: x [n,m] fp32 (m % 4 == 0) -> out [n,3,m] bf16.  Row i of the [n,3m]
- * view is [hi_i | mid_i | lo_i] and row 3i+p of the [3n,m] view is plane p of row i: each dense product of the backward
- * (W P and W^T A) is then ONE bf16 GEMM with the three planes concatenated along K. */
-int hypret_split3_rows(const float* x, int64_t n, int64_t m, void* out_bf16, void* stream);
 int hypret_gram_split(const float* x, int64_t n, int d, int side, void* out_bf16, float* sqnorm, void* stream);
 int hypret_gram_dist(const void* a_op, const void* p_op, const float* a32, const float* p32, const float* asq,
                      const float* psq, int64_t n, int64_t m, int d, float c, float* out, void* stream);
@@ -454,6 +450,9 @@ int hypret_ap_from_counts(const int64_t* pos_offsets, const int64_t* pos_items, 
 /* out[j] = ln sum_r exp(parts[r, j]), parts [n_parts, n] fp32: the column log-sum-exps of a batch whose rows are
  * sharded across ranks, from the per-rank partials (train.ShardedInBatchInfoNCE). */
 int hypret_lse_combine(const float* parts, int n_parts, int64_t n, float* out, void* stream);
+/* out[j] = sum_r parts[r, j] in a fixed order: folds the per-CTA row / column partial sums of hypret_pairdist_bwd /
+ * hypret_pairdist_ce_bwd (the terms the reference's autograd adds up in its diagonal corrections). */
+int hypret_sum_parts(const float* parts, int n_parts, int64_t n, float* out, void* stream);
 int64_t hypret_flash_kpad(int d);
 int64_t hypret_flash_workspace(int64_t n, int64_t m, int d);
 int hypret_flash_prep(const float* x, int64_t n, int d, void* row_op, void* col_op, void* t_planes, int64_t t_cols,

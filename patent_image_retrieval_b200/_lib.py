@@ -105,7 +105,6 @@ SIGNATURES = {
                                        c_int64, c_int64, c_void_p]),
     "hypret_gram_kpad": (c_int64, [c_int]),
     "hypret_split3": (c_int, [c_void_p, c_int64, c_void_p, c_void_p]),
-    "hypret_split3_rows": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_void_p]),
     "hypret_gram_split": (c_int, [c_void_p, c_int64, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "hypret_gram_dist": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int,
                                  c_float, c_void_p, c_void_p]),
@@ -131,6 +130,7 @@ SIGNATURES = {
                                    c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "hypret_flag_compact": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p]),
     "hypret_lse_combine": (c_int, [c_void_p, c_int, c_int64, c_void_p, c_void_p]),
+    "hypret_sum_parts": (c_int, [c_void_p, c_int, c_int64, c_void_p, c_void_p]),
     "hypret_flash_kpad": (c_int64, [c_int]),
     "hypret_flash_workspace": (c_int64, [c_int64, c_int64, c_int]),
     "hypret_flash_prep": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p]),

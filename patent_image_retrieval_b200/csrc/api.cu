@@ -421,16 +421,7 @@ int hypret_split3(const float* x, int64_t count, void* out_bf16, void* stream) {
   if (x == nullptr || out_bf16 == nullptr || !aligned16(x) || !aligned16(out_bf16) || (count & 3)) return HYPRET_EINVAL;
   int rc = check_device();
   if (rc != HYPRET_OK) return rc;
-  return hypret_launch_split3(x, count, 0, out_bf16, static_cast<cudaStream_t>(stream));
-}
-
-int hypret_split3_rows(const float* x, int64_t n, int64_t m, void* out_bf16, void* stream) {
-  if (n < 0 || m < 0 || (m & 3)) return HYPRET_EINVAL;
-  if (n == 0 || m == 0) return HYPRET_OK;
-  if (x == nullptr || out_bf16 == nullptr || !aligned16(x) || !aligned16(out_bf16)) return HYPRET_EINVAL;
-  int rc = check_device();
-  if (rc != HYPRET_OK) return rc;
-  return hypret_launch_split3(x, n * m, m, out_bf16, static_cast<cudaStream_t>(stream));
+  return hypret_launch_split3(x, count, out_bf16, static_cast<cudaStream_t>(stream));
 }
 
 int64_t hypret_gram_kpad(int d) { return d > 0 ? hypret_gram_kpad_impl(d) : 0; }
@@ -658,6 +649,15 @@ int hypret_lse_combine(const float* parts, int n_parts, int64_t n, float* out, v
   int rc = check_device();
   if (rc != HYPRET_OK) return rc;
   return hypret_launch_lse_combine(parts, n_parts, n, out, static_cast<cudaStream_t>(stream));
+}
+
+int hypret_sum_parts(const float* parts, int n_parts, int64_t n, float* out, void* stream) {
+  if (n_parts < 1 || n < 0) return HYPRET_EINVAL;
+  if (n == 0) return HYPRET_OK;
+  if (parts == nullptr || out == nullptr) return HYPRET_EINVAL;
+  int rc = check_device();
+  if (rc != HYPRET_OK) return rc;
+  return hypret_launch_sum_parts(parts, n_parts, n, out, static_cast<cudaStream_t>(stream));
 }
 
 int hypret_rowpair_dist(const float* x, const float* y, const int64_t* ia, const int64_t* ib, int64_t n_pairs, int d,

@@ -405,7 +405,7 @@ int hypret_launch_pairdist_ce_bwd(const float* dmat, const float* asq, const flo
                                   const float* grad_scale, void* w_out, int w_format, float* row_partial,
                                   int n_row_partial, float* col_partial, int64_t diag_offset, int64_t n_total,
                                   cudaStream_t stream);
-int hypret_launch_split3(const float* x, int64_t count, int64_t row_len, void* out_bf16, cudaStream_t stream);
+int hypret_launch_split3(const float* x, int64_t count, void* out_bf16, cudaStream_t stream);
 int64_t hypret_gram_kpad_impl(int d);
 int hypret_launch_gram_split(const float* x, int64_t n, int d, int side, void* out_bf16, float* sq, cudaStream_t stream);
 int hypret_launch_gram_dist(const void* a_op, const void* p_op, const float* a32, const float* p32, const float* asq,
@@ -448,6 +448,7 @@ int hypret_launch_cert_merged(const float* q32, int64_t Q, int d, float c, int m
                               float slack, int32_t* flags, float* out_margin, cudaStream_t stream);
 int hypret_launch_flag_compact(const int32_t* flags, int64_t n, int32_t* list, int32_t* count, int32_t* state,
                                cudaStream_t stream);
+int hypret_launch_sum_parts(const float* parts, int w, int64_t n, float* out, cudaStream_t stream);
 int hypret_launch_lse_combine(const float* parts, int w, int64_t n, float* out, cudaStream_t stream);
 int hypret_launch_mobius_gemm(const void* x_row_op, const void* w_col_op, int64_t n, int d_in, int n_out,
                               const float* xsq, const float* bias, float c, int post_tanh, int n_project, float* mx_out,

@@ -655,6 +655,15 @@ __global__ void lse_combine_kernel(const float* __restrict__ parts, int w, int64
   out[j] = m > -INFINITY ? m + logf(acc) : -INFINITY;
 }
 
+// out[j] = sum_r parts[r, j], fixed order (the row / column sums of the W tiles of the non-flash backward)
+__global__ void sum_parts_kernel(const float* __restrict__ parts, int w, int64_t n, float* __restrict__ out) {
+  const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n) return;
+  float acc = 0.f;
+  for (int r = 0; r < w; ++r) acc += parts[(int64_t)r * n + j];
+  out[j] = acc;
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -705,6 +714,12 @@ int64_t hypret_flash_kpad_impl(int d) { return flash_kpad(d); }
 int hypret_launch_lse_combine(const float* parts, int w, int64_t n, float* out, cudaStream_t stream) {
   if (n == 0) return HYPRET_OK;
   lse_combine_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(parts, w, n, out);
+  return (int)cudaGetLastError();
+}
+
+int hypret_launch_sum_parts(const float* parts, int w, int64_t n, float* out, cudaStream_t stream) {
+  if (n == 0) return HYPRET_OK;
+  sum_parts_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(parts, w, n, out);
   return (int)cudaGetLastError();
 }
 

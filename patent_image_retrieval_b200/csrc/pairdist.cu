@@ -337,12 +337,8 @@ lse_cols_combine_kernel(const float* __restrict__ part_max, const float* __restr
 // 8-byte stores.  The backward pass emits W fastest as plain fp32 (one 128-byte line per warp store; 0.23 ms at
 // 8192^2) -- writing the planes from inside it costs three 64-byte stores per warp and element and the registers
 // spill (0.44 ms) -- so the planes are cut in this streaming pass instead (0.67 GB of traffic).
-// ROWS: x is [n, m] (m % 4 == 0, count = n * m) and the planes are interleaved per row, out [n][3][m]: row i of the
-// [n, 3m] view is [hi_i | mid_i | lo_i] and row 3i+p of the [3n, m] view is plane p of row i, so that each of the two
-// products of the backward is ONE GEMM with the planes concatenated along K (ops.split_products).
-template <bool ROWS>
 __global__ void __launch_bounds__(256)
-split3_kernel(const float* __restrict__ x, int64_t count, int64_t m, __nv_bfloat16* __restrict__ out) {
+split3_kernel(const float* __restrict__ x, int64_t count, __nv_bfloat16* __restrict__ out) {
   const int64_t n4 = count >> 2;
   for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < n4; v += (int64_t)gridDim.x * blockDim.x) {
     const float4 a = __ldcs(reinterpret_cast<const float4*>(x) + v);
@@ -355,19 +351,11 @@ split3_kernel(const float* __restrict__ x, int64_t count, int64_t m, __nv_bfloat
       mid[t] = __float2bfloat16_rn(r1);
       l[t] = __float2bfloat16_rn(r1 - __bfloat162float(mid[t]));
     }
-    if (ROWS) {
-      const int64_t e = 4 * v, i = e / m, j = e - i * m;
-      __nv_bfloat16* o = out + i * 3 * m + j;
-      *reinterpret_cast<uint2*>(o) = *reinterpret_cast<const uint2*>(h);
-      *reinterpret_cast<uint2*>(o + m) = *reinterpret_cast<const uint2*>(mid);
-      *reinterpret_cast<uint2*>(o + 2 * m) = *reinterpret_cast<const uint2*>(l);
-    } else {
-      *reinterpret_cast<uint2*>(out + 4 * v) = *reinterpret_cast<const uint2*>(h);
-      *reinterpret_cast<uint2*>(out + count + 4 * v) = *reinterpret_cast<const uint2*>(mid);
-      *reinterpret_cast<uint2*>(out + 2 * count + 4 * v) = *reinterpret_cast<const uint2*>(l);
-    }
+    *reinterpret_cast<uint2*>(out + 4 * v) = *reinterpret_cast<const uint2*>(h);
+    *reinterpret_cast<uint2*>(out + count + 4 * v) = *reinterpret_cast<const uint2*>(mid);
+    *reinterpret_cast<uint2*>(out + 2 * count + 4 * v) = *reinterpret_cast<const uint2*>(l);
   }
-  if (!ROWS && blockIdx.x == 0 && threadIdx.x < (count & 3)) {          // tail
+  if (blockIdx.x == 0 && threadIdx.x < (count & 3)) {          // tail
     const int64_t i = (n4 << 2) + threadIdx.x;
     const __nv_bfloat16 h = __float2bfloat16_rn(x[i]);
     const float r1 = x[i] - __bfloat162float(h);
@@ -380,17 +368,14 @@ split3_kernel(const float* __restrict__ x, int64_t count, int64_t m, __nv_bfloat
 
 }  // namespace
 
-int hypret_launch_split3(const float* x, int64_t count, int64_t row_len, void* out_bf16, cudaStream_t stream) {
+int hypret_launch_split3(const float* x, int64_t count, void* out_bf16, cudaStream_t stream) {
   if (count == 0) return HYPRET_OK;
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int64_t want = (count / 4 + 255) / 256;
   const unsigned grid = (unsigned)(want < (int64_t)sms * 8 ? (want < 1 ? 1 : want) : (int64_t)sms * 8);
-  if (row_len > 0)
-    split3_kernel<true><<<grid, 256, 0, stream>>>(x, count, row_len, static_cast<__nv_bfloat16*>(out_bf16));
-  else
-    split3_kernel<false><<<grid, 256, 0, stream>>>(x, count, 0, static_cast<__nv_bfloat16*>(out_bf16));
+  split3_kernel<<<grid, 256, 0, stream>>>(x, count, static_cast<__nv_bfloat16*>(out_bf16));
   return (int)cudaGetLastError();
 }
 

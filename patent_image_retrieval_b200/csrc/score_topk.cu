@@ -1114,8 +1114,7 @@ extern "C" int hypret_score_plan(int64_t Q, int64_t N, int d, int kprime, int ma
   // CTA pairs (tcgen05 cta_group::2) whenever there are at least two query tiles to pair up
   int ctas = sms;
   if (max_ctas > 0 && max_ctas < ctas) ctas = max_ctas;
-  const char* pair_env = getenv("HYPRET_PAIR");                  // experiments: 0 forces single-CTA MMAs
-  const bool pair = n_qtiles >= 2 && ctas >= 2 && !(pair_env != nullptr && pair_env[0] == '0');
+  const bool pair = n_qtiles >= 2 && ctas >= 2;
   const int b_blk = pair ? B_BLK_BYTES / 2 : B_BLK_BYTES;
 
   // shared-memory carve-up
@@ -1127,11 +1126,9 @@ extern "C" int hypret_score_plan(int64_t Q, int64_t N, int d, int kprime, int ma
   int resident = 0, stages = 0, stage_bytes = 0;
   {
     const int avail = SMEM_LIMIT - 1024 - BAR_BYTES - lists - a_res_bytes;
-    const char* force = getenv("HYPRET_FORCE_STREAM");   // experiments only
     // Resident query tile only when the gallery ring is still >= 4 stages deep; with the two
     // stages that D=512 leaves in single-CTA mode the MMA pipe starves (measured 863 vs 1103 TFLOP/s).
-    const bool force_res = force != nullptr && force[0] == '0';
-    if (kb <= 8 && avail >= (force_res ? 2 : 4) * b_blk && !(force != nullptr && force[0] == '1')) {
+    if (kb <= 8 && avail >= 4 * b_blk) {
       resident = 1;
       stage_bytes = b_blk;
       stages = avail / b_blk;
@@ -1231,13 +1228,11 @@ int hypret_launch_score_topk(const void* q_op, int64_t Q, const void* g_op, int6
   p.stats = nullptr;
   p.wait_mode = 0;
   p.pf_tiles = 0;      // measured at C2 and on 37.5k-row shards: no gain from 2 or 4 tiles of L2 lookahead
-  if (const char* pf = getenv("HYPRET_PF_TILES")) p.pf_tiles = atoi(pf);     // experiments
   p.wg_off = p.bar_off - WG_X_BYTES;
   // Experiments only: HYPRET_STATS=1 runs the instrumented kernel variant, synchronises and prints
-  // per-role wait-cycle totals to stderr.  HYPRET_WAIT_MODE selects the wait flavour in that variant.
+  // per-role wait-cycle totals to stderr.
   const char* stats_env = getenv("HYPRET_STATS");
   const bool want_stats = stats_env != nullptr && stats_env[0] == '1' && debug_scores == nullptr;
-  if (const char* wm = getenv("HYPRET_WAIT_MODE")) p.wait_mode = atoi(wm);
   if (want_stats) {
     if (cudaMalloc(&p.stats, (size_t)plan.grid * 8 * sizeof(unsigned long long)) != cudaSuccess) p.stats = nullptr;
     if (p.stats != nullptr) cudaMemsetAsync(p.stats, 0, (size_t)plan.grid * 8 * sizeof(unsigned long long), stream);

@@ -322,11 +322,17 @@ class PeerQueryExchange:
         if e:
             raise RuntimeError(f"peer exchange: rank {self.rank} timed out waiting for rank {e - 1}")
 
-    def close(self):
+    def release(self):
+        """``close`` without the barrier, for an owner that is being garbage-collected: the caller vouches that no
+        peer is still inside a step that writes here."""
+        self.close(barrier=False)
+
+    def close(self, barrier: bool = True):
         if self.base is None:
             return
         torch.cuda.synchronize(self.device)
-        dist.barrier(group=self.group)         # nobody still writes into a buffer that is about to go
+        if barrier:
+            dist.barrier(group=self.group)     # nobody still writes into a buffer that is about to go
         lib = _lib.load()
         with torch.cuda.device(self.device):
             for r, ptr in enumerate(self.peer_base):
@@ -403,6 +409,32 @@ class ShardedGalleryIndex:
     def _single(self) -> bool:
         return not dist.is_initialized() or dist.get_world_size(self.group) == 1
 
+    def check(self) -> None:
+        """Synchronise and raise if a peer-exchange wait ran into its time bound since the last check."""
+        if self._exchange is not None:
+            self._exchange.check()
+
+    def exchange_failed(self) -> bool:
+        """The exchange's error word, read WITHOUT a device synchronise of its own (call it where the results of a
+        step have already been waited for, e.g. SearchPipeline.result)."""
+        return self._exchange is not None and self._exchange.err is not None and bool(int(self._exchange.err.item()))
+
+    def close(self) -> None:
+        """Release the peer-memory exchange buffers (collective: every rank of the group calls it)."""
+        if self._exchange is not None:
+            self._exchange.close()
+            self._exchange = None
+
+    def __del__(self):
+        # an index dropped without close(): unmap what this rank mapped, without the collective barrier -- the peers'
+        # own buffers stay valid until they drop theirs
+        ex = getattr(self, "_exchange", None)
+        if ex is not None:
+            try:
+                ex.release()
+            except Exception:
+                pass
+
     def search(self, queries: torch.Tensor, k: int = 10, kprime: Optional[int] = None,
                kernel_events: Optional[list] = None):
         """``queries`` = the replicated batch, or this rank's own batch when the index was built with
@@ -461,11 +493,19 @@ class ShardedGalleryIndex:
                                                                   kernel_events=kernel_events, want_err=exact)
             q_err = q_err[me * ql:(me + 1) * ql] if exact else None
 
+        def poisoned(score, idx):
+            # a wait of the peer exchange that ran into its time bound (dead / out-of-step peer) leaves stale data in
+            # the exchange buffers: such a step hands out idx = -1 everywhere instead of plausible wrong lists, and
+            # SearchPipeline.result / PeerQueryExchange.check raise (no host sync here: the error word is read on the device)
+            if ex is None:
+                return score, idx
+            return score, torch.where(ex.err.view(1, 1) != 0, -1, idx)
+
         def finish(rs, ri, thr_all):
             score, idx = ops.merge_topk(rs, ri, descending=(self.metric == "cosine"))
             if not exact:
                 self.uncertified = None
-                return score, idx
+                return poisoned(score, idx)
             with _span(kernel_events, "certify"):
                 own = slice(me * ql, (me + 1) * ql)
                 flags = ops.cert_merged(q32[own], score, idx, thr_all[own], q_err, stats_all, self.local.c, self.metric)
@@ -477,7 +517,7 @@ class ShardedGalleryIndex:
                 xs, xi = ops.merge_topk(xs, xi, descending=(self.metric == "cosine"))
                 redo = flags.bool()[:, None]
                 self.uncertified = flags
-                return torch.where(redo, xs, score), torch.where(redo, xi, idx)
+                return poisoned(torch.where(redo, xs, score), torch.where(redo, xi, idx))
 
         thr_all = None
         if prune and ex is not None and os.environ.get("HYPRET_PEER_ROUTE", "1") != "0":
@@ -504,7 +544,7 @@ class ShardedGalleryIndex:
         rs, ri = return_lists_to_owners(score, idx, self.group)
         if thr_all is None:
             self.uncertified = None
-            return ops.merge_topk(rs, ri, descending=(self.metric == "cosine"))
+            return poisoned(*ops.merge_topk(rs, ri, descending=(self.metric == "cosine")))
         return finish(rs, ri, thr_all)
 
 

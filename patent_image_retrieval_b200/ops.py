@@ -743,6 +743,16 @@ def mobius_gemm(x_op: torch.Tensor, w_op: torch.Tensor, d_in: int, n_out: int, c
     return out
 
 
+def sum_parts(parts: torch.Tensor) -> torch.Tensor:
+    """``parts.sum(dim=0)`` in a fixed order for per-CTA partials ``[P, n]`` (``hypret_sum_parts``)."""
+    _need_cuda(parts)
+    parts = parts.contiguous().float()
+    out = torch.empty(parts.shape[1], dtype=torch.float32, device=parts.device)
+    with torch.cuda.device(parts.device):
+        _lib.check(_lib.load().hypret_sum_parts(_ptr(parts), parts.shape[0], parts.shape[1], _ptr(out), _stream()))
+    return out
+
+
 def lse_combine(parts: torch.Tensor) -> torch.Tensor:
     """``logsumexp(parts, dim=0)`` for per-rank partial log-sum-exps ``[W, n]`` (``hypret_lse_combine``)."""
     _need_cuda(parts)
@@ -768,43 +778,33 @@ def _w_buffer(n: int, m: int, split: bool, device):
     return torch.empty(n, m, dtype=torch.float32, device=device)
 
 
-def split3(x: torch.Tensor, rows: bool = False) -> torch.Tensor:
-    """fp32 -> bf16 planes with hi + mid + lo = x to fp32 accuracy.  ``rows=False``: ``[...] -> [3, ...]``
-    (``hypret_split3``); ``rows=True``: ``[n,m] -> [n,3,m]``, planes interleaved per row (``hypret_split3_rows``)."""
+def split3(x: torch.Tensor) -> torch.Tensor:
+    """fp32 ``[...]`` -> bf16 planes ``[3, ...]`` with hi + mid + lo = x to fp32 accuracy (``hypret_split3``)."""
     _need_cuda(x)
     x = x.contiguous().float()
-    lib = _lib.load()
+    if x.numel() % 4:
+        raise ValueError("split3 needs a multiple of 4 elements")
+    out = torch.empty((3,) + tuple(x.shape), dtype=torch.bfloat16, device=x.device)
     with torch.cuda.device(x.device):
-        if rows:
-            n, m = x.shape
-            if m % 4:
-                raise ValueError("split3(rows=True) needs a row length that is a multiple of 4")
-            out = torch.empty(n, 3, m, dtype=torch.bfloat16, device=x.device)
-            _lib.check(lib.hypret_split3_rows(_ptr(x), n, m, _ptr(out), _stream()))
-        else:
-            if x.numel() % 4:
-                raise ValueError("split3 needs a multiple of 4 elements")
-            out = torch.empty((3,) + tuple(x.shape), dtype=torch.bfloat16, device=x.device)
-            _lib.check(lib.hypret_split3(_ptr(x), x.numel(), _ptr(out), _stream()))
+        _lib.check(_lib.load().hypret_split3(_ptr(x), x.numel(), _ptr(out), _stream()))
     return out
 
 
 class SplitW:
-    """W of the distance-matrix backward as three bf16 planes (hi + mid + lo = W): ``data`` is ``[3,n,m]`` (cut from
-    the fp32 W by ``hypret_split3``, or written by the backward kernel itself, ``w_format`` 1, when n*m is not a
-    multiple of 4) or, ``interleaved``, ``[n,3,m]`` (``hypret_split3_rows``: one GEMM per product)."""
+    """W of the distance-matrix backward as three bf16 planes (hi + mid + lo = W): ``data`` is ``[3,n,m]``, cut from
+    the fp32 W by ``hypret_split3``, or written by the backward kernel itself (``w_format`` 1) when n*m is not a
+    multiple of 4."""
 
-    def __init__(self, data: torch.Tensor, interleaved: bool):
-        self.data, self.interleaved = data, interleaved
+    def __init__(self, data: torch.Tensor):
+        self.data = data
 
     def float(self) -> torch.Tensor:
-        return self.data.float().sum(dim=1 if self.interleaved else 0)
+        return self.data.float().sum(dim=0)
 
 
 def _two_pass_split(n: int, m: int) -> bool:
     """Planes cut from an fp32 W by ``split3`` (faster than writing them from inside the backward pass) unless the
-    element count is not a multiple of 4.  Plane-major: the one-GEMM-per-product form of the interleaved layout
-    measured no faster (0.40 vs 0.39-0.42 ms at D=128) or slower (0.56 vs 0.48 ms at D=256) than three GEMMs."""
+    element count is not a multiple of 4."""
     return (n * m) % 4 == 0
 
 
@@ -835,10 +835,10 @@ def pairdist_ce_bwd(dmat: torch.Tensor, asq: torch.Tensor, psq: torch.Tensor, c:
                                                       int(diag_offset), int(n if n_total is None else n_total),
                                                       _stream()))
     if two_pass:
-        w = SplitW(split3(w), False)
+        w = SplitW(split3(w))
     elif split:
-        w = SplitW(w, False)
-    return w, rp.sum(dim=0), cp.sum(dim=0)
+        w = SplitW(w)
+    return w, sum_parts(rp), sum_parts(cp)
 
 
 def pairdist_bwd(grad_out: torch.Tensor, dmat: torch.Tensor, asq: torch.Tensor, psq: torch.Tensor, c: float,
@@ -862,10 +862,10 @@ def pairdist_bwd(grad_out: torch.Tensor, dmat: torch.Tensor, asq: torch.Tensor, 
                                                    _ptr(psq.contiguous()), n, m, float(c), _ptr(w), int(split), _ptr(rp),
                                                    n_rp, _ptr(cp), n_partial, _stream()))
     if two_pass:
-        w = SplitW(split3(w), False)
+        w = SplitW(split3(w))
     elif split:
-        w = SplitW(w, False)
-    return w, rp.sum(dim=0), cp.sum(dim=0)
+        w = SplitW(w)
+    return w, sum_parts(rp), sum_parts(cp)
 
 
 SPLIT_MIN_PAIRS = 1 << 20     # below this the two products are launch-bound either way: plain fp32 GEMMs
@@ -891,26 +891,10 @@ def _split_parts(x: torch.Tensor):
 def split_products(w: SplitW, a: torch.Tensor, p: torch.Tensor):
     """``(W @ p, W.T @ a)`` for ``W = hi + mid + lo`` (bf16 planes) at fp32-GEMM accuracy on the tensor cores: the six
     bf16 cross products of order <= 2^-16, hi x (hi|mid|lo) + mid x (hi|mid) + lo x hi, as library GEMMs with fp32
-    accumulation (the plain dense products of the backward; cuBLAS SGEMM before).
-    Interleaved planes ``[n,3,m]``: ONE GEMM per product with the planes concatenated along K --
-    ``W3.view(n, 3m) @ [[ph|pm|pl], [ph|pm|0], [ph|0|0]]`` and ``W3.view(3n, m).T @ rows(3i+p)`` -- and a sum of the
-    three column blocks.  Plane-major ``[3,n,m]``: three GEMMs per product."""
+    accumulation (the plain dense products of the backward; cuBLAS SGEMM before): three GEMMs per product.
+    The non-flash path only (D not served by ``flash_ok``); the flash backward does these products on-chip."""
     d = a.shape[1]
     a, p = a.float(), p.float()
-    if w.interleaved:
-        n, _, m = w.data.shape
-        outs = []
-        ph, pm, pl = _split_parts(p)
-        z = torch.zeros_like(ph)
-        b1 = torch.cat([torch.cat([ph, pm, pl], 1), torch.cat([ph, pm, z], 1), torch.cat([ph, z, z], 1)], 0)   # [3m,3d]
-        o = torch.mm(w.data.view(n, 3 * m), b1, out_dtype=torch.float32)
-        outs.append(o[:, 2 * d:] + o[:, d:2 * d] + o[:, :d])
-        ah, am, al = _split_parts(a)
-        za = torch.zeros_like(ah)
-        b2 = torch.stack([torch.cat([ah, am, al], 1), torch.cat([ah, am, za], 1), torch.cat([ah, za, za], 1)], 1)
-        o = torch.mm(w.data.view(3 * n, m).t(), b2.view(3 * n, 3 * d), out_dtype=torch.float32)
-        outs.append(o[:, 2 * d:] + o[:, d:2 * d] + o[:, :d])
-        return outs[0], outs[1]
     w3 = w.data
     outs = []
     for planes, x in (((w3[0], w3[1], w3[2]), p), ((w3[0].t(), w3[1].t(), w3[2].t()), a)):
@@ -924,8 +908,16 @@ def split_products(w: SplitW, a: torch.Tensor, p: torch.Tensor):
 
 
 def row_sqnorm(x: torch.Tensor) -> torch.Tensor:
-    """||x_i||^2 per row ([n,D] reduction; negligible next to the [n,n] work)."""
-    return x.float().pow(2).sum(dim=1)
+    """||x_i||^2 per row, fp32 (the sq output of ``hypret_flash_prep``)."""
+    _need_cuda(x)
+    x = x.detach().contiguous().float()
+    n, d = x.shape
+    if d % 4 or d > 4096:
+        raise ValueError("row_sqnorm: D % 4 == 0, D <= 4096")
+    out = torch.empty(n, dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.load().hypret_flash_prep(_ptr(x), n, d, None, None, None, 0, _ptr(out), _stream()))
+    return out
 
 
 def mobius_epilogue(mx: torch.Tensor, c: float, bias: Optional[torch.Tensor] = None,

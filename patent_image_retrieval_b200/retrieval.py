@@ -271,6 +271,9 @@ class SearchPipeline:
 
     def result(self, slot: int):
         self.ev_out[slot].synchronize()
+        failed = getattr(self.index, "exchange_failed", None)
+        if failed is not None and failed():      # sharded index: a peer-exchange wait timed out, the lists are poisoned
+            raise RuntimeError("peer exchange timed out during this batch (a rank died or fell out of step)")
         return self.out_s[slot], self.out_i[slot]
 
     def drain(self):

@@ -347,16 +347,11 @@ def test_infonce_split_bf16_backward_matches_fp64_autograd():
     asq, psq = ops.row_sqnorm(a0), ops.row_sqnorm(p0)
     w, rs, cs = ops.pairdist_ce_bwd(dm, asq, psq, c, rl, cl, 1 / tau, 0.5, 0.5)
     w3, rs3, cs3 = ops.pairdist_ce_bwd(dm, asq, psq, c, rl, cl, 1 / tau, 0.5, 0.5, split=True)
-    assert not w3.interleaved and w3.data.dtype == torch.bfloat16 and tuple(w3.data.shape) == (3, n, n)
+    assert w3.data.dtype == torch.bfloat16 and tuple(w3.data.shape) == (3, n, n)
     torch.testing.assert_close(w3.float(), w, rtol=3e-7, atol=0)
-    rows = ops.split3(w, rows=True)                              # the same planes interleaved per row: [n,3,n]
-    assert torch.equal(rows.permute(1, 0, 2), w3.data)
-    wp_p, wta_p = ops.split_products(ops.SplitW(rows, True), a0, p0)             # one GEMM per product
     assert torch.equal(rs, rs3) and torch.equal(cs, cs3)
     wp, wta = ops.split_products(w3, a0, p0)
     ref_wp, ref_wta = w.double() @ p0.double(), w.double().t() @ a0.double()
-    assert float((wp_p - ref_wp).abs().max() / ref_wp.abs().max()) < 2e-5
-    assert float((wta_p - ref_wta).abs().max() / ref_wta.abs().max()) < 2e-5
     # error against the size of the summed terms (the sums cancel: W has a negative diagonal).  The six bf16 cross
     # products are exact to 2^-24, but the tensor core's fp32 accumulator TRUNCATES: up to one ulp of the running sum
     # per 16-deep MMA step, all in one direction (measured 4.4e-6 here = 69 steps x 2^-24; an FFMA SGEMM rounds to

@@ -16,7 +16,7 @@ ROOT = Path(__file__).resolve().parents[1]
 WORKER = r"""
 import os, sys, torch, torch.distributed as dist
 sys.path.insert(0, os.environ["HYPRET_ROOT"])
-from patent_image_retrieval_b200 import GalleryIndex, synth
+from patent_image_retrieval_b200 import GalleryIndex, ops, synth
 from patent_image_retrieval_b200.dist import ShardedGalleryIndex, shard_range
 rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
 torch.cuda.set_device(rank)
@@ -143,5 +143,5 @@ def test_two_gpu_exchange_patterns_equal_single_gpu(tmp_path):
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr",
            "127.0.0.1", "--master-port", str(29800 + os.getpid() % 100), str(script)]
     out = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=300)
-    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-8000:]
     assert out.stdout.count("OK") == 2
