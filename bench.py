@@ -293,7 +293,7 @@ def main():
 
     from patent_image_retrieval_b200 import SearchPipeline, StageEvents, ops, synth
     from patent_image_retrieval_b200.dist import ShardedGalleryIndex, shard_range
-    from patent_image_retrieval_b200.retrieval import default_kprime
+    from patent_image_retrieval_b200.retrieval import default_kbound, default_kprime
     import torch.distributed as dist
 
     torch.cuda.set_device(local_rank)
@@ -329,7 +329,8 @@ def main():
     q_host.copy_(q_dev)
     out_d_host = torch.empty(Q, k, dtype=torch.float32, pin_memory=True)
     out_i_host = torch.empty(Q, k, dtype=torch.int64, pin_memory=True)
-    kprime = default_kprime(k)                  # what search() uses when the caller does not choose (24 at k=10)
+    kprime = default_kprime(k)                  # what search() uses when the caller does not choose (16-slot lists at
+                                                # k=10, sharing the bound of the 24th best score: default_kbound)
     plan = ops.score_plan(q_total if weak else Q, hi - lo, D, kprime)
 
     def barrier():
@@ -487,7 +488,7 @@ def main():
         "vs_baseline": None, "dtype": "fp16 tensor-core filter (fp32 accumulate) + fp32/fp64 exact rerank, certified",
         "data": "synthetic",
         "config": search_config(args.workload, world, args.scaling),
-        "run": {"kprime": kprime, "gallery_rows_per_gpu": n_local,
+        "run": {"kprime": kprime, "kbound": default_kbound(k, kprime), "gallery_rows_per_gpu": n_local,
                 "parallelism": (f"gallery row-shard x{world}; " +
                                 ("each rank fed its own Q-query batch per step: " +
                                  ("projection kernel stores the operand rows into every rank's buffer over NVLink "

@@ -169,6 +169,14 @@ int hypret_score_strip(const hypret_score_plan_t* plan, int cta, int step, int32
 int hypret_score_topk(const void* q_op, int64_t Q, const void* g_op, int64_t N, int d, int kprime, int n_lists,
                       int max_ctas, int min_lists, float* cand_score, int32_t* cand_idx, uint32_t* thr_workspace,
                       int32_t* list_count, float* debug_scores, void* stream);
+/* hypret_score_topk whose lists share the bound of the query's kbound-th best score instead of the kprime-th
+ * (kprime <= 16 < kbound <= 32, thr_workspace required): the union of a query's 16-slot register lists then holds its
+ * global top-kbound unless one half-strip alone holds more than 16 of them -- the spare candidates the exact-top-k
+ * certificate needs (hypret_rerank_cert, ksel = kbound) at the speed of the 16-slot kernel.  kbound == kprime: as
+ * hypret_score_topk. */
+int hypret_score_topk_bound(const void* q_op, int64_t Q, const void* g_op, int64_t N, int d, int kprime, int kbound,
+                            int n_lists, int max_ctas, int min_lists, float* cand_score, int32_t* cand_idx,
+                            uint32_t* thr_workspace, int32_t* list_count, float* debug_scores, void* stream);
 
 /* Candidate merge + exact rerank.  For each query: keep the kprime best of its
  * n_lists*kprime candidates by surrogate score, recompute their distance exactly from the
@@ -198,12 +206,15 @@ int hypret_rerank(const float* q32, const float* g32, int64_t Q, int64_t N, int 
  * result only if  (k'-th best filter score) - (exact surrogate of the k-th result) > E  -- then no non-candidate can
  * have an exact surrogate at or below the k-th result's.  Otherwise the query id is appended to fb_list (fb_count
  * counts them; zeroed by this call) and its two lock words in fb_state [2Q] are cleared: hypret_exact_topk, queued
- * behind this call, recomputes exactly those queries from all gallery rows.  certified [Q] uint8 out or NULL. */
+ * behind this call, recomputes exactly those queries from all gallery rows.  certified [Q] uint8 out or NULL.
+ *   ksel  0, or kprime < ksel <= 32 for lists built by hypret_score_topk_bound(kbound = ksel): the ksel best candidates
+ *         of the union of the kprime-slot lists are rescored, and the margin is taken against the smaller of the
+ *         ksel-th best filter score and the worst entry of any FULL list (rows a full list had no slot for). */
 int hypret_rerank_cert(const float* q32, const float* g32, int64_t Q, int64_t N, int d, float c, int metric,
                        const float* cand_score, const int32_t* cand_idx, const int32_t* list_count, int n_lists,
-                       int kprime, int k, int64_t idx_offset, float* out_score, int64_t* out_idx, float* out_margin,
-                       const float* q_err, const float* g_stats, int32_t* fb_state, int32_t* fb_count, int32_t* fb_list,
-                       uint8_t* certified, void* stream);
+                       int kprime, int ksel, int k, int64_t idx_offset, float* out_score, int64_t* out_idx,
+                       float* out_margin, const float* q_err, const float* g_stats, int32_t* fb_state, int32_t* fb_count,
+                       int32_t* fb_list, uint8_t* certified, void* stream);
 /* Exact top-k of the listed queries by a scan of ALL gallery rows -- what the reference's per-query loop does
  * (pmath.dist one-vs-all + torch.topk, src/train.py:3259, src/auxiliary.py:374; cosine: retrieval.ipynb:368,202) --
  * with the arithmetic and ordering of hypret_rerank; overwrites rows q_list[0 .. *q_count) of out_score / out_idx

@@ -59,7 +59,7 @@ SIGNATURES = {
     "hypret_project_rows_cert": (c_int, [c_void_p, c_int64, c_int, c_float, c_int, c_int, c_void_p, c_void_p, c_void_p,
                                          c_void_p, c_void_p, c_void_p]),
     "hypret_rerank_cert": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int, c_float, c_int, c_void_p, c_void_p,
-                                   c_void_p, c_int, c_int, c_int, c_int64, c_void_p, c_void_p, c_void_p, c_void_p,
+                                   c_void_p, c_int, c_int, c_int, c_int, c_int64, c_void_p, c_void_p, c_void_p, c_void_p,
                                    c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "hypret_exact_topk": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int, c_float, c_int, c_int, c_int64,
                                   c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
@@ -83,6 +83,8 @@ SIGNATURES = {
                                            c_int64, c_void_p]),
     "hypret_score_plan": (c_int, [c_int64, c_int64, c_int, c_int, c_int, c_int, POINTER(ScorePlan)]),
     "hypret_score_strip": (c_int, [POINTER(ScorePlan), c_int, c_int, POINTER(c_int32)]),
+    "hypret_score_topk_bound": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int, c_int, c_int, c_int, c_int, c_int,
+                                        c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "hypret_score_topk": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int, c_int, c_int, c_int, c_int, c_void_p,
                                   c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "hypret_rerank": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int, c_float, c_int, c_void_p, c_void_p,

@@ -139,16 +139,25 @@ int hypret_peer_wait(const uint32_t* flags, int n, uint32_t value, uint32_t* err
   return hypret_launch_peer_wait(flags, n, value, err, static_cast<cudaStream_t>(stream));
 }
 
-int hypret_score_topk(const void* q_op, int64_t Q, const void* g_op, int64_t N, int d, int kprime, int n_lists,
-                      int max_ctas, int min_lists, float* cand_score, int32_t* cand_idx, uint32_t* thr_workspace,
-                      int32_t* list_count, float* debug_scores, void* stream) {
+int hypret_score_topk_bound(const void* q_op, int64_t Q, const void* g_op, int64_t N, int d, int kprime, int kbound,
+                            int n_lists, int max_ctas, int min_lists, float* cand_score, int32_t* cand_idx,
+                            uint32_t* thr_workspace, int32_t* list_count, float* debug_scores, void* stream) {
   if (Q < 1 || N < 1 || d < 4 || (d & 3) || d > 2048) return HYPRET_EINVAL;
   if (kprime < 1 || kprime > 64 || n_lists < 1 || max_ctas < 0 || min_lists < 0) return HYPRET_EINVAL;
+  if (kbound < kprime || (kbound > kprime && (kprime > 16 || kbound > 32 || thr_workspace == nullptr)))
+    return HYPRET_EINVAL;
   if (q_op == nullptr || g_op == nullptr || cand_score == nullptr || cand_idx == nullptr) return HYPRET_EINVAL;
   int rc = check_device();
   if (rc != HYPRET_OK) return rc;
-  return hypret_launch_score_topk(q_op, Q, g_op, N, d, kprime, n_lists, max_ctas, min_lists, cand_score, cand_idx,
-                                  thr_workspace, list_count, debug_scores, static_cast<cudaStream_t>(stream));
+  return hypret_launch_score_topk(q_op, Q, g_op, N, d, kprime, kbound, n_lists, max_ctas, min_lists, cand_score,
+                                  cand_idx, thr_workspace, list_count, debug_scores, static_cast<cudaStream_t>(stream));
+}
+
+int hypret_score_topk(const void* q_op, int64_t Q, const void* g_op, int64_t N, int d, int kprime, int n_lists,
+                      int max_ctas, int min_lists, float* cand_score, int32_t* cand_idx, uint32_t* thr_workspace,
+                      int32_t* list_count, float* debug_scores, void* stream) {
+  return hypret_score_topk_bound(q_op, Q, g_op, N, d, kprime, kprime, n_lists, max_ctas, min_lists, cand_score,
+                                 cand_idx, thr_workspace, list_count, debug_scores, stream);
 }
 
 static int rerank_common(const float* q32, const float* g32, int64_t Q, int64_t N, int d, float c, int metric,
@@ -195,15 +204,17 @@ int hypret_rerank(const float* q32, const float* g32, int64_t Q, int64_t N, int 
 
 int hypret_rerank_cert(const float* q32, const float* g32, int64_t Q, int64_t N, int d, float c, int metric,
                        const float* cand_score, const int32_t* cand_idx, const int32_t* list_count, int n_lists,
-                       int kprime, int k, int64_t idx_offset, float* out_score, int64_t* out_idx, float* out_margin,
-                       const float* q_err, const float* g_stats, int32_t* fb_state, int32_t* fb_count, int32_t* fb_list,
-                       uint8_t* certified, void* stream) {
+                       int kprime, int ksel, int k, int64_t idx_offset, float* out_score, int64_t* out_idx,
+                       float* out_margin, const float* q_err, const float* g_stats, int32_t* fb_state, int32_t* fb_count,
+                       int32_t* fb_list, uint8_t* certified, void* stream) {
   if (kprime > 32 || k > 32 || k > kprime) return HYPRET_EUNSUPPORTED;
+  if (ksel != 0 && (ksel < kprime || ksel > 32)) return HYPRET_EINVAL;
   if (q_err == nullptr || g_stats == nullptr || fb_state == nullptr || fb_count == nullptr || fb_list == nullptr)
     return HYPRET_EINVAL;
   CertArgs cert;
   cert.q_err = q_err; cert.g_stats = g_stats; cert.state = fb_state; cert.count = fb_count; cert.list = fb_list;
   cert.flags = certified;
+  cert.ksel = ksel;
   // fp32 accumulation in the tensor core (truncating: up to 2 ulps of the running sum per 16-deep MMA step) and the
   // 2^-24 tails of the 3-way splits of the extension columns
   cert.slack = (float)(hypret_kpad(d) / 16 + 8) * 2.384185791015625e-07f;

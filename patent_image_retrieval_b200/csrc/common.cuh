@@ -317,7 +317,7 @@ int hypret_launch_peer_signal(void* const* flags_host, int n, uint32_t value, cu
 int hypret_launch_peer_wait(const uint32_t* flags, int n, uint32_t value, uint32_t* err, cudaStream_t stream);
 int hypret_launch_project_rows(const float* u, int64_t n, int d, float c, int mode, int side, float* y32,
                                void* op_f16, float* sqnorm, float* op_err, float* stats, cudaStream_t stream);
-int hypret_launch_score_topk(const void* q_op, int64_t Q, const void* g_op, int64_t N, int d, int kprime,
+int hypret_launch_score_topk(const void* q_op, int64_t Q, const void* g_op, int64_t N, int d, int kprime, int kbound,
                              int n_lists, int max_ctas, int min_lists, float* cand_score, int32_t* cand_idx,
                              uint32_t* thr_ws, int32_t* list_count, float* debug_scores, cudaStream_t stream);
 // Kernel-side view of hypret_peer_route (passed by value); n == 0: no routing.
@@ -354,11 +354,12 @@ struct CertArgs {
   int32_t* count;         // [1] number of uncertified queries
   int32_t* list;          // [Q] their ids
   uint8_t* flags;         // [Q] or NULL: 1 = certified by the filter pass, 0 = sent to the exact scan
+  int ksel;               // candidates rescored per query (0 = k'); > k': lists of k' slots sharing a ksel-th-best bound
 };
 inline CertArgs no_cert() {
   CertArgs a;
   a.q_err = nullptr; a.g_stats = nullptr; a.slack = 0.f; a.state = nullptr; a.count = nullptr; a.list = nullptr;
-  a.flags = nullptr;
+  a.flags = nullptr; a.ksel = 0;
   return a;
 }
 int hypret_launch_rerank(const float* q32, const float* g32, int64_t Q, int64_t N, int d, float c, int metric,

@@ -165,8 +165,26 @@ rerank_kernel(const float* __restrict__ q32, const float* __restrict__ g32, int6
     ci[t] = cand_idx[q * n_cand + t];
   }
   __syncwarp();
+  // ksel > k' (register-list scoring: 16-slot lists that share the bound of the ksel-th best score): the ksel best of
+  // the union are rescored; a FULL list may have dropped rows for lack of slots, and those are bounded only by the
+  // list's own worst entry -- the certificate below takes the smaller of the two limits
+  const int ksel = (cert.ksel > kprime && cert.ksel <= 32) ? cert.ksel : kprime;
+  float w_trunc = INFINITY;
+  if (ksel > kprime) {
+    for (int t = lane; t < n_mine / kprime; t += 32) {
+      bool full = true;
+      float w = -INFINITY;
+      for (int e = 0; e < kprime; ++e) {
+        full = full && ci[t * kprime + e] >= 0;
+        w = fmaxf(w, cs[t * kprime + e]);
+      }
+      if (full) w_trunc = fminf(w_trunc, w);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) w_trunc = fminf(w_trunc, __shfl_xor_sync(0xffffffffu, w_trunc, o));
+  }
   float my_approx, worst_approx;
-  int my_idx = select_candidates(cs, ci, n_mine, kprime, prune_thr != nullptr ? prune_thr[q] : INFINITY, lane,
+  int my_idx = select_candidates(cs, ci, n_mine, ksel, prune_thr != nullptr ? prune_thr[q] : INFINITY, lane,
                                  &my_approx, &worst_approx);
   const int n_sel = __popc(__ballot_sync(0xffffffffu, my_idx >= 0));
 
@@ -278,8 +296,10 @@ rerank_kernel(const float* __restrict__ q32, const float* __restrict__ g32, int6
     // +inf: the candidate set was not truncated (fewer than k' valid candidates survive)
     const int n_valid = __popc(__ballot_sync(0xffffffffu, my_idx >= 0));
     if (lane == 0) {
-      const bool open_set = n_valid < kprime || kth_idx < 0;
-      const double margin = (double)worst_approx - kth;
+      // limit = a lower bound of the filter score of every row OUTSIDE the rescored set (+inf: nothing was left out)
+      const float limit = fminf(n_valid >= ksel ? worst_approx : INFINITY, w_trunc);
+      const bool open_set = !(limit < INFINITY);
+      const double margin = (double)limit - kth;
       if (out_margin != nullptr) out_margin[q] = open_set ? INFINITY : (float)margin;
       if (cert.q_err != nullptr) {
         // Every row outside the candidate set has a tensor-core surrogate >= worst_approx and an exact surrogate within
@@ -289,7 +309,7 @@ rerank_kernel(const float* __restrict__ q32, const float* __restrict__ g32, int6
         const double zmax = cert.g_stats[0], dzmax = cert.g_stats[1], rbmax = cert.g_stats[2], bmax = cert.g_stats[3];
         const double E = (double)cert.q_err[q] * zmax + qn * dzmax +
                          (double)cert.slack * (qn * zmax + qn * qn * rbmax + bmax);
-        const bool ok = open_set || margin > E;
+        const bool ok = open_set || (kth_idx >= 0 && margin > E);
         if (cert.flags != nullptr) cert.flags[q] = ok ? 1 : 0;
         if (!ok) {
           cert.state[2 * q] = 0;

@@ -184,6 +184,7 @@ struct Params {
   int has_ext;          // 1: extension K block present (hyperbolic surrogate constants)
   int dpad;
   int kprime;
+  int kbound;          // rank of the score bound the query's lists share (>= kprime; > kprime only with register lists)
   int stages;
   int stage_bytes;
   int ring_off;         // byte offsets from the 1024-aligned shared-memory base
@@ -762,7 +763,7 @@ score_topk_kernel(const __grid_constant__ CUtensorMap map_q_main, const __grid_c
       // best of their union -- about half the hits of filtering with min(k'-th best, k'-th best).
       const uint32_t my_x = smem_u32(smem + p.wg_off) + (uint32_t)(wg * TILE_M + row) * 8u;
       const uint32_t peer_x = smem_u32(smem + p.wg_off) + (uint32_t)((wg ^ 1) * TILE_M + row) * 8u;
-      const int half_k = (KP + 1) >> 1;
+      const int half_k = (p.kbound + 1) >> 1;       // <= RL: kbound <= 2 RL
       asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(my_x), "r"(step), "r"(0x7f800000u) : "memory");
       RowStateR st;
       st.thr_list = INFINITY;
@@ -827,7 +828,9 @@ score_topk_kernel(const __grid_constant__ CUtensorMap map_q_main, const __grid_c
         drain_queue_reg(st, L, KP, qs_addr, qi_addr, ovf_s, ovf_i);
         // exchange thresholds with the query's other lists (other warpgroup, other strips) through L2
         if (gthr != nullptr) {
-          if (st.thr_list < published) {
+          // this list's k'-th best bounds the query's k'-th best -- but not its kbound-th when kbound > k' (lists of
+          // 16 sharing the bound of the 24th best: the certificate's spare candidates at the cost of 16-slot lists)
+          if (p.kbound <= KP && st.thr_list < published) {
             atomicMin(gthr, f2key(st.thr_list));
             published = st.thr_list;
           }
@@ -1188,13 +1191,14 @@ extern "C" int hypret_score_strip(const hypret_score_plan_t* plan, int cta, int 
   return ok ? 1 : 0;
 }
 
-int hypret_launch_score_topk(const void* q_op, int64_t Q, const void* g_op, int64_t N, int d, int kprime,
+int hypret_launch_score_topk(const void* q_op, int64_t Q, const void* g_op, int64_t N, int d, int kprime, int kbound,
                              int n_lists, int max_ctas, int min_lists, float* cand_score, int32_t* cand_idx,
                              uint32_t* thr_ws, int32_t* list_count, float* debug_scores, cudaStream_t stream) {
   hypret_score_plan_t plan;
   int rc = hypret_score_plan(Q, N, d, kprime, max_ctas, min_lists, &plan);
   if (rc != HYPRET_OK) return rc;
   if (plan.n_lists != n_lists) return HYPRET_EINVAL;   // caller sized cand_* for a different plan
+  if (kbound > kprime && (kpp_of(kprime) != RL || kbound > 2 * RL)) return HYPRET_EINVAL;
   if ((reinterpret_cast<uintptr_t>(q_op) & 15) || (reinterpret_cast<uintptr_t>(g_op) & 15)) return HYPRET_EINVAL;
 
   const int dpad = hypret_dpad(d);
@@ -1213,6 +1217,7 @@ int hypret_launch_score_topk(const void* q_op, int64_t Q, const void* g_op, int6
   p.has_ext = 1;
   p.dpad = dpad;
   p.kprime = kprime;
+  p.kbound = kbound > kprime ? kbound : kprime;
   p.stages = plan.stages;
   p.stage_bytes = plan.resident ? B_BLK_BYTES / plan.pair : A_BLK_BYTES + B_BLK_BYTES / plan.pair;
   p.ring_off = plan.resident ? p.kb_main * A_BLK_BYTES + A_EXT_BYTES : 0;

@@ -101,15 +101,20 @@ def score_strips(Q: int, N: int, d: int, kprime: int, max_ctas: int = 0, min_lis
 def score_topk(q_op: torch.Tensor, g_op: torch.Tensor, d: int, kprime: int, max_ctas: int = 0,
                debug: bool = False, out: Optional[Tuple[torch.Tensor, torch.Tensor]] = None,
                share_thresholds: bool = True, thr_workspace: Optional[torch.Tensor] = None, min_lists: int = 0,
-               list_count: Optional[torch.Tensor] = None):
+               list_count: Optional[torch.Tensor] = None, kbound: Optional[int] = None):
     """tcgen05 scoring GEMM + streaming top-k'.  Returns ``(cand_score [Q,L,k'], cand_idx [Q,L,k'] int32)``
     with L = plan["n_lists"] (+ the full ``[Q,N]`` surrogate matrix when ``debug`` -- tests only).
     ``share_thresholds``: strips of a query exchange their running k'-th best score (fast path);
     off, every list is exactly the top-k' of its own strip.
     ``list_count`` ([Q] int32, out): compact list slots -- the lists of query q are its first ``list_count[q]`` slots
     (pass the same tensor to ``rerank`` / ``cand_select``); without it slots are the schedule's and unwritten ones
-    read as empty."""
+    read as empty.
+    ``kbound`` (k' <= 16 < kbound <= 32, shared thresholds): the lists share the bound of the kbound-th best score -- the
+    union holds the query's top-kbound (``hypret_score_topk_bound``; ``rerank_cert(ksel=kbound)`` certifies it)."""
     _need_cuda(q_op, g_op, list_count)
+    kbound = int(kprime) if kbound is None else int(kbound)
+    if kbound != kprime and not (share_thresholds and kprime <= 16 < kbound <= 32):
+        raise ValueError("kbound needs shared thresholds and k' <= 16 < kbound <= 32")
     if list_count is not None and (list_count.dtype != torch.int32 or list_count.numel() < q_op.shape[0]):
         raise ValueError("list_count must be an int32 tensor with one entry per query")
     if q_op.dtype != torch.float16 or g_op.dtype != torch.float16:
@@ -134,9 +139,9 @@ def score_topk(q_op: torch.Tensor, g_op: torch.Tensor, d: int, kprime: int, max_
             ws = thr_workspace if thr_workspace is not None else torch.empty(Q, dtype=torch.int32, device=q_op.device)
             if ws.numel() < Q or ws.element_size() != 4 or not ws.is_cuda:
                 raise ValueError("thr_workspace must be a CUDA tensor of >= Q 32-bit elements")
-        _lib.check(_lib.load().hypret_score_topk(_ptr(q_op), Q, _ptr(g_op), N, int(d), int(kprime), S,
-                                                 int(max_ctas), int(min_lists), _ptr(cs), _ptr(ci), _ptr(ws),
-                                                 _ptr(list_count), _ptr(dbg), _stream()))
+        _lib.check(_lib.load().hypret_score_topk_bound(_ptr(q_op), Q, _ptr(g_op), N, int(d), int(kprime), kbound, S,
+                                                       int(max_ctas), int(min_lists), _ptr(cs), _ptr(ci), _ptr(ws),
+                                                       _ptr(list_count), _ptr(dbg), _stream()))
     return (cs, ci, dbg) if debug else (cs, ci)
 
 
@@ -205,12 +210,12 @@ class CertBuffers:
 def rerank_cert(q32: torch.Tensor, g32: torch.Tensor, cand_score: torch.Tensor, cand_idx: torch.Tensor, c: float,
                 metric: str, k: int, q_err: torch.Tensor, g_stats: torch.Tensor, g_sqnorm64: torch.Tensor,
                 bufs: CertBuffers, idx_offset: int = 0, want_margin: bool = False,
-                list_count: Optional[torch.Tensor] = None, fallback: bool = True):
+                list_count: Optional[torch.Tensor] = None, fallback: bool = True, ksel: int = 0):
     """``rerank`` (k <= k' <= 32) with the exact-top-k guarantee: ``hypret_rerank_cert`` proves per query that no row
     outside the fp16-filtered candidate set can precede the k-th result, and ``hypret_exact_topk`` -- queued right
     behind it, reading the list length on the device -- recomputes the queries it could not prove from all gallery
     rows.  Returns ``(score [Q,k], idx [Q,k][, margin [Q]])``; ``bufs.certified`` / ``bufs.count`` tell what happened.
-    ``fallback=False`` (tests): certificate only."""
+    ``fallback=False`` (tests): certificate only.  ``ksel`` (> k'): the lists were built with ``score_topk(kbound=ksel)``."""
     _need_cuda(q32, g32, cand_score, cand_idx, q_err, g_stats, g_sqnorm64, list_count)
     q32, g32 = q32.contiguous(), g32.contiguous()
     Q, d = q32.shape
@@ -224,8 +229,9 @@ def rerank_cert(q32: torch.Tensor, g32: torch.Tensor, cand_score: torch.Tensor, 
     lib = _lib.load()
     with torch.cuda.device(q32.device):
         _lib.check(lib.hypret_rerank_cert(_ptr(q32), _ptr(g32), Q, N, d, float(c), METRIC[metric], _ptr(cand_score),
-                                          _ptr(cand_idx), _ptr(list_count), S, kprime, int(k), int(idx_offset),
-                                          _ptr(out_s), _ptr(out_i), _ptr(margin), _ptr(q_err), _ptr(g_stats),
+                                          _ptr(cand_idx), _ptr(list_count), S, kprime, int(ksel), int(k),
+                                          int(idx_offset), _ptr(out_s), _ptr(out_i), _ptr(margin), _ptr(q_err),
+                                          _ptr(g_stats),
                                           _ptr(bufs.state), _ptr(bufs.count), _ptr(bufs.list), _ptr(bufs.certified),
                                           _stream()))
         if fallback:

@@ -63,16 +63,26 @@ WIDE_MIN_LISTS = 4     # wide top-k: candidate lists per query (4 x 64 = 256 can
 
 
 def default_kprime(k: int) -> int:
-    """List slots per strip.  k <= 26: one list of k+14 slots (24..32; threshold sharing keeps the union equal to the
-    global approximate top-k').  The 14 spare slots are what the certificate needs: at k' = k+6 about 1e-4 of the
-    (query, 1M..10M-row shard) pairs have their k-th..k'-th candidates within the rounding bound E and fall to the
-    exact scan (4.5 ms for one query over 5M rows); at k+14 the 1 % margin quantile is 8 E and the scoring kernel is no
-    slower (tools/diag_cert.py, profiles/README.md).  Larger k ("wide", up to 128): 64-slot lists, at least
-    ``WIDE_MIN_LISTS`` independent lists per query, no threshold sharing -- the top-k is in the union unless
-    one strip holds more than 64 of the k best rows, which ``margin`` certifies per query."""
+    """List slots per strip.  k <= 10: 16-slot lists (the register-list epilogue of the scoring kernel, query tile
+    resident in shared memory); k <= 26: one list of k+14 slots (<= 32; threshold sharing keeps the union equal to the
+    global approximate top-k').  Larger k ("wide", up to 128): 64-slot lists, at least ``WIDE_MIN_LISTS`` independent
+    lists per query, no threshold sharing -- the top-k is in the union unless one strip holds more than 64 of the k
+    best rows, which ``margin`` certifies per query."""
     if k > ops.MAX_K:
         raise ValueError(f"k={k} exceeds the supported maximum {ops.MAX_K}")
-    return min(32, max(24, k + 14)) if k <= 26 else 64
+    if k <= 10:
+        return 16
+    return min(32, k + 14) if k <= 26 else 64
+
+
+def default_kbound(k: int, kprime: int) -> int:
+    """Candidates the exact-top-k certificate works with: k+14 (<= 32).  The certificate needs the k'-th..k-th best
+    candidates to be further apart than the rounding bound E; with k+6 candidates about 1.5e-4 of the (query,
+    1M..10M-row shard) pairs fail that and fall to the exact scan (4.5 ms for a few queries over 5M rows), with k+14 the
+    1 % margin quantile is 8 E (tools/diag_cert.py).  16-slot lists reach k+14 by sharing the bound of the (k+14)-th
+    best score (``ops.score_topk(kbound=...)``): measured 10 % faster at C4 and 20 % at C2 than 24-slot lists in shared
+    memory, which lose the resident query tile."""
+    return max(kprime, min(32, k + 14)) if kprime <= 16 else kprime
 
 
 class GalleryIndex:
@@ -118,7 +128,8 @@ class GalleryIndex:
         return "expmap0" if self.space == "euclidean" else "onball"
 
     def search(self, queries: torch.Tensor, k: int = 10, kprime: Optional[int] = None, return_margin: bool = False,
-               max_ctas: int = 0, kernel_events: Optional[list] = None, exact: bool = True):
+               max_ctas: int = 0, kernel_events: Optional[list] = None, exact: bool = True,
+               kbound: Optional[int] = None):
         """queries [Q,D] fp32 (host or device) -> (score [Q,k] f32, idx [Q,k] i64) on the device.
         score = Poincare distance ascending, or cosine similarity descending; ties -> lower index.
 
@@ -128,7 +139,7 @@ class GalleryIndex:
         queries it cannot prove (near-duplicate galleries) are recomputed by a full exact scan queued on the same
         stream -- no host synchronisation either way.  ``self.certificate`` (``ops.CertBuffers``) holds the per-query
         flags and the count of rescanned queries.  k <= 26; wider k returns the filtered result with its own
-        ``margin`` diagnostic.
+        ``margin`` diagnostic.  ``kbound``: see ``default_kbound`` (None = default; = k' for plain k'-slot semantics).
         ``kernel_events``: a list (receives a (start, end) CUDA-event pair bracketing the scoring kernel
         on the launching stream per call) or a ``StageEvents`` (all three kernels): bench.py's rooflines."""
         if k > ops.MAX_K:
@@ -140,13 +151,16 @@ class GalleryIndex:
             res = ops.exact_topk_any(q, self.rows32, self.rows_sq64, self.c, self.metric, min(k, self.n),
                                      idx_offset=self.idx_offset)
             return res + (torch.full((q.shape[0],), float("inf"), device=self.device),) if return_margin else res
-        q32, cs, ci, cnt, q_err = self.score_candidates(queries, k=k, kprime=kprime, max_ctas=max_ctas,
-                                                        kernel_events=kernel_events, want_err=exact)
+        kp = min(default_kprime(k) if kprime is None else int(kprime), ops.MAX_KPRIME)
+        if kbound is None:
+            kbound = default_kbound(k, kp) if (exact and k <= kp) else kp
+        q32, cs, ci, cnt, q_err = self.score_candidates(queries, k=k, kprime=kp, max_ctas=max_ctas,
+                                                        kernel_events=kernel_events, want_err=exact, kbound=kbound)
         return self.rerank_candidates(q32, cs, ci, k, return_margin=return_margin, kernel_events=kernel_events,
-                                      list_count=cnt, q_err=q_err if exact else None)
+                                      list_count=cnt, q_err=q_err if exact else None, ksel=kbound)
 
     def score_candidates(self, queries: torch.Tensor, k: int = 10, kprime: Optional[int] = None, max_ctas: int = 0,
-                         kernel_events: Optional[list] = None, want_err: bool = False):
+                         kernel_events: Optional[list] = None, want_err: bool = False, kbound: Optional[int] = None):
         """First half of ``search``: projection + tcgen05 scoring / streaming top-k'.
         Returns ``(q32 [Q,D] exact-rerank operand, cand_score [Q,L,k'], cand_idx [Q,L,k'] int32, list_count [Q]
         int32, q_err [Q] | None)``: the lists of query q are its first ``list_count[q]`` slots (compact, arrival
@@ -165,10 +179,10 @@ class GalleryIndex:
                 q_op = res[1]
         q_err = res[3] if want_err else None
         return self.score_projected(q32, q_op, k=k, kprime=kprime, max_ctas=max_ctas,
-                                    kernel_events=kernel_events) + (q_err,)
+                                    kernel_events=kernel_events, kbound=kbound) + (q_err,)
 
     def score_projected(self, q32: torch.Tensor, q_op: torch.Tensor, k: int = 10, kprime: Optional[int] = None,
-                        max_ctas: int = 0, kernel_events: Optional[list] = None):
+                        max_ctas: int = 0, kernel_events: Optional[list] = None, kbound: Optional[int] = None):
         """``score_candidates`` for queries that are already projected: ``q32`` the exact-rerank rows, ``q_op`` their
         fp16 operand rows (``ops.project_rows`` / the peer exchange of ``dist.PeerQueryExchange``)."""
         kprime = default_kprime(k) if kprime is None else int(kprime)
@@ -190,12 +204,14 @@ class GalleryIndex:
             self._cand[key] = buf
         with _span(kernel_events, "score"):
             cs, ci = ops.score_topk(q_op, self.operand, self.d, kprime, max_ctas, out=buf[:2], thr_workspace=buf[2],
-                                    share_thresholds=not wide, min_lists=min_lists, list_count=buf[3])
+                                    share_thresholds=not wide, min_lists=min_lists, list_count=buf[3],
+                                    kbound=None if wide else kbound)
         return q32, cs, ci, buf[3]
 
     def rerank_candidates(self, q32, cand_score, cand_idx, k: int, return_margin: bool = False,
                           prune_thr: Optional[torch.Tensor] = None, kernel_events: Optional[list] = None,
-                          list_count: Optional[torch.Tensor] = None, q_err: Optional[torch.Tensor] = None):
+                          list_count: Optional[torch.Tensor] = None, q_err: Optional[torch.Tensor] = None,
+                          ksel: int = 0):
         """Second half of ``search``: candidate merge + exact rerank against this shard's fp32 rows.  With ``q_err``
         (and k <= k' <= 32, no pruning): the certified rerank + exact-scan fallback of ``ops.rerank_cert``."""
         kprime = cand_score.shape[2]
@@ -207,7 +223,8 @@ class GalleryIndex:
             with _span(kernel_events, "rerank"):
                 return ops.rerank_cert(q32, self.rows32, cand_score, cand_idx, self.c, self.metric, k, q_err,
                                        self.stats, self.rows_sq64, self._cert, idx_offset=self.idx_offset,
-                                       want_margin=return_margin, list_count=list_count)
+                                       want_margin=return_margin, list_count=list_count,
+                                       ksel=ksel if ksel > kprime else 0)
         with _span(kernel_events, "rerank"):
             out = ops.rerank(q32, self.rows32, cand_score, cand_idx, self.c, self.metric, k,
                              idx_offset=self.idx_offset, want_margin=return_margin, prune_thr=prune_thr,

@@ -229,3 +229,51 @@ def test_search_beyond_128_pages_through_the_exact_ranking(metric):
     small = GalleryIndex(gal[:150].cuda(), c=c, metric=metric, space="ball" if metric == "hyperbolic" else "euclidean")
     _, i2 = small.search(qry.cuda(), k=200)
     assert tuple(i2.shape) == (Q, 150) and bool((i2 >= 0).all())
+
+
+@pytest.mark.parametrize("metric", ["hyperbolic", "cosine"])
+def test_lists_of_16_sharing_the_bound_of_the_24th_best(metric):
+    """score_topk(kbound=24) with 16-slot register lists: the union of a query's lists holds its 24 best filter scores
+    unless one list ran out of slots, and rerank_cert(ksel=24) measures its margin against the smaller of the 24th best
+    filter score and the worst entry of any full list -- checked against the full [Q,N] filter-score matrix."""
+    Q, N, d, c, k, kp, kb = 300, 40000, 256, 1.0, 10, 16, 24
+    index = GalleryIndex(synth.gaussian_features(N, d, seed=0).cuda(), c=c, metric=metric)
+    qry = synth.gaussian_features(Q, d, seed=1).cuda()
+    if metric == "hyperbolic":
+        q32, q_op, _, q_err = ops.project_rows(qry, c, mode=index._query_mode(), side="query", want_err=True)
+    else:
+        _, q_op, _, q_err = ops.project_rows(qry, 1.0, mode="cosine", side="query", want_point=False, want_err=True)
+        q32 = qry
+    cnt = torch.zeros(Q, dtype=torch.int32, device="cuda")
+    cs, ci, dbg = ops.score_topk(q_op, index.operand, d, kp, debug=True, share_thresholds=True, list_count=cnt, kbound=kb)
+    torch.cuda.synchronize()
+    L = cs.shape[1]
+    valid = (torch.arange(L, device="cuda")[None, :, None] < cnt[:, None, None]) & (ci >= 0)
+    full = valid.all(dim=2)                                                     # [Q,L]
+    worst_full = torch.where(full, torch.where(valid, cs, torch.full_like(cs, float("-inf"))).amax(dim=2),
+                             torch.full((Q, L), float("inf"), device="cuda")).amin(dim=1)
+    top_s, top_i = torch.sort(dbg, dim=1, stable=True)
+    top_s, top_i = top_s[:, :kb], top_i[:, :kb]
+    held = torch.zeros(Q, N, dtype=torch.bool, device="cuda")
+    rows = torch.arange(Q, device="cuda")[:, None, None].expand_as(ci)
+    held[rows[valid], ci[valid].long()] = True
+    # every one of the 24 best filter scores below the truncation limit is in the union
+    need = top_s < worst_full[:, None]
+    assert bool((held.gather(1, top_i) | ~need).all())
+    assert float((worst_full >= top_s[:, -1]).float().mean()) > 0.95            # truncation is the exception
+    bufs = ops.CertBuffers(Q, "cuda")
+    out_s, out_i, margin = ops.rerank_cert(q32, index.rows32, cs, ci, c, metric, k, q_err, index.stats, index.rows_sq64,
+                                           bufs, list_count=cnt, fallback=False, want_margin=True, ksel=kb)
+    want_s, want_i = ops.exact_topk(q32, index.rows32, index.rows_sq64, c, metric, k)
+    ok = bufs.certified[:Q].bool()
+    assert float(ok.float().mean()) > 0.99
+    assert torch.equal(out_i[ok], want_i[ok]) and torch.equal(out_s[ok], want_s[ok])
+    # the margin's limit: min(24th best filter score, worst entry of a full list), minus the exact surrogate of the
+    # k-th result
+    x, y = q32.double(), index.rows32.double()[want_i[:, k - 1]]
+    if metric == "hyperbolic":
+        sur = c * (x - y).pow(2).sum(1) / (1 - c * y.pow(2).sum(1))
+    else:
+        sur = -(x * y).sum(1) / (x.norm(dim=1) * y.norm(dim=1))
+    limit = torch.minimum(top_s[:, -1], worst_full).double()
+    assert float(((limit - sur) - margin.double()).abs().max()) < 1e-5
