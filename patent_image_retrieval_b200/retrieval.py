@@ -22,10 +22,11 @@ from . import ops
 
 
 class StageEvents:
-    """CUDA-event pairs around the three kernels of a search, recorded on the launching stream
-    (bench.py's roofline measurements).  ``ms(name)`` = mean duration after a synchronize."""
+    """CUDA-event pairs around the kernels of a search, recorded on the launching stream (bench.py's roofline
+    measurements; "certify" = the merged-list certificate + flagged rescans of the sharded path).  ``ms(name)`` = mean
+    duration after a synchronize."""
 
-    STAGES = ("project", "score", "rerank")
+    STAGES = ("project", "score", "rerank", "certify")
 
     def __init__(self):
         self.pairs = {s: [] for s in self.STAGES}
