@@ -309,7 +309,8 @@ def main():
     g_u = synth.gallery_rows(lo, hi, D, device=dev)
     weak = world > 1 and args.scaling == "weak"
     index = ShardedGalleryIndex(g_u, row_offset=lo, n_total=N, c=c, metric="hyperbolic", space="euclidean",
-                                queries="sharded" if weak else "replicated")
+                                queries="sharded" if weak else "replicated",
+                                exact=os.environ.get("HYPRET_BENCH_EXACT", "1") != "0")   # 0: diagnostics only
     torch.cuda.synchronize()
     build_s = time.perf_counter() - t_build
     # gallery-side projection roofline: the same kernel call the index build made, timed alone
@@ -365,6 +366,7 @@ def main():
     barrier()
     ms_resident = e0.elapsed_time(e1) / args.steps
     score_ms, project_ms, rerank_ms = (kernel_events.ms(n_) for n_ in ("score", "project", "rerank"))
+    certify_ms = kernel_events.ms("certify")                    # sharded serving: owner's certificate + flagged rescans
 
     # ---- timed: end to end with host buffers, no overlap ----------------------------------------------
     for _ in range(2):
@@ -499,6 +501,8 @@ def main():
         "data": "synthetic",
         "config": search_config(args.workload, world, args.scaling),
         "run": {"kprime": kprime, "kbound": default_kbound(k, kprime), "gallery_rows_per_gpu": n_local,
+                "stage_ms": {"project": project_ms, "score": score_ms, "rerank": rerank_ms,
+                             "certify": None if certify_ms != certify_ms else certify_ms},
                 "parallelism": (f"gallery row-shard x{world}; " +
                                 ("each rank fed its own Q-query batch per step: " +
                                  ("projection kernel stores the operand rows into every rank's buffer over NVLink "

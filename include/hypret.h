@@ -207,6 +207,8 @@ int hypret_rerank(const float* q32, const float* g32, int64_t Q, int64_t N, int 
  * have an exact surrogate at or below the k-th result's.  Otherwise the query id is appended to fb_list (fb_count
  * counts them; zeroed by this call) and its two lock words in fb_state [2Q] are cleared: hypret_exact_topk, queued
  * behind this call, recomputes exactly those queries from all gallery rows.  certified [Q] uint8 out or NULL.
+ *   fb_bound [Q] fp32 out or NULL: for an uncertified query, the k-th score of its filtered result (an exact score of
+ *         a real row, so no better than the true k-th best) -- hypret_exact_topk's init_bound.
  *   ksel  0, or kprime < ksel <= 32 for lists built by hypret_score_topk_bound(kbound = ksel): the ksel best candidates
  *         of the union of the kprime-slot lists are rescored, and the margin is taken against the smaller of the
  *         ksel-th best filter score and the worst entry of any FULL list (rows a full list had no slot for). */
@@ -214,16 +216,19 @@ int hypret_rerank_cert(const float* q32, const float* g32, int64_t Q, int64_t N,
                        const float* cand_score, const int32_t* cand_idx, const int32_t* list_count, int n_lists,
                        int kprime, int ksel, int k, int64_t idx_offset, float* out_score, int64_t* out_idx,
                        float* out_margin, const float* q_err, const float* g_stats, int32_t* fb_state, int32_t* fb_count,
-                       int32_t* fb_list, uint8_t* certified, void* stream);
+                       int32_t* fb_list, float* fb_bound, uint8_t* certified, void* stream);
 /* Exact top-k of the listed queries by a scan of ALL gallery rows -- what the reference's per-query loop does
  * (pmath.dist one-vs-all + torch.topk, src/train.py:3259, src/auxiliary.py:374; cosine: retrieval.ipynb:368,202) --
  * with the arithmetic and ordering of hypret_rerank; overwrites rows q_list[0 .. *q_count) of out_score / out_idx
  * ([Q,k], + idx_offset).  *q_count is read on the device (no host synchronisation; an empty list costs one launch of
  * CTAs that exit at once).  g_sqnorm64 [N] from hypret_row_sqnorm64; fb_state [2Q] as left by hypret_rerank_cert.
- * k <= 32. */
+ * k <= 32. 
+ *   init_bound [Q] fp32 or NULL: per query a score that is no better than its true k-th best (distance: >=, similarity:
+ *         <=; +-inf = none).  The scan then starts warm -- only rows at or inside the bound are contenders and CTAs
+ *         that see none skip the merge -- and still returns the exact top-k. */
 int hypret_exact_topk(const float* q32, const float* g32, const double* g_sqnorm64, int64_t Q, int64_t N, int d,
                       float c, int metric, int k, int64_t idx_offset, const int32_t* q_list, const int32_t* q_count,
-                      int32_t* fb_state, float* out_score, int64_t* out_idx, void* stream);
+                      int32_t* fb_state, const float* init_bound, float* out_score, int64_t* out_idx, void* stream);
 /* Exact-top-k certificate of a MERGED result, for a row-sharded gallery whose queries are owned by one rank each
  * (dist.ShardedGalleryIndex.search_sharded): score/idx [Q,k] = the merged exact lists, thr [Q] = the global k'-th best
  * filter score of each query (hypret_kth_smallest over every shard's list), q_err [Q] = the rounding residuals of the

@@ -206,7 +206,7 @@ int hypret_rerank_cert(const float* q32, const float* g32, int64_t Q, int64_t N,
                        const float* cand_score, const int32_t* cand_idx, const int32_t* list_count, int n_lists,
                        int kprime, int ksel, int k, int64_t idx_offset, float* out_score, int64_t* out_idx,
                        float* out_margin, const float* q_err, const float* g_stats, int32_t* fb_state, int32_t* fb_count,
-                       int32_t* fb_list, uint8_t* certified, void* stream) {
+                       int32_t* fb_list, float* fb_bound, uint8_t* certified, void* stream) {
   if (kprime > 32 || k > 32 || k > kprime) return HYPRET_EUNSUPPORTED;
   if (ksel != 0 && (ksel < kprime || ksel > 32)) return HYPRET_EINVAL;
   if (q_err == nullptr || g_stats == nullptr || fb_state == nullptr || fb_count == nullptr || fb_list == nullptr)
@@ -215,6 +215,7 @@ int hypret_rerank_cert(const float* q32, const float* g32, int64_t Q, int64_t N,
   cert.q_err = q_err; cert.g_stats = g_stats; cert.state = fb_state; cert.count = fb_count; cert.list = fb_list;
   cert.flags = certified;
   cert.ksel = ksel;
+  cert.bound = fb_bound;
   // fp32 accumulation in the tensor core (truncating: up to 2 ulps of the running sum per 16-deep MMA step) and the
   // 2^-24 tails of the 3-way splits of the extension columns
   cert.slack = (float)(hypret_kpad(d) / 16 + 8) * 2.384185791015625e-07f;
@@ -226,7 +227,7 @@ int hypret_rerank_cert(const float* q32, const float* g32, int64_t Q, int64_t N,
 
 int hypret_exact_topk(const float* q32, const float* g32, const double* g_sqnorm64, int64_t Q, int64_t N, int d,
                       float c, int metric, int k, int64_t idx_offset, const int32_t* q_list, const int32_t* q_count,
-                      int32_t* fb_state, float* out_score, int64_t* out_idx, void* stream) {
+                      int32_t* fb_state, const float* init_bound, float* out_score, int64_t* out_idx, void* stream) {
   if (Q < 0 || N < 1 || d < 4 || (d & 3) || k < 1 || k > 32) return HYPRET_EINVAL;
   if (N > 0x7fffffffll) return HYPRET_EUNSUPPORTED;
   if (metric != HYPRET_METRIC_COSINE && metric != HYPRET_METRIC_HYPERBOLIC) return HYPRET_EINVAL;
@@ -238,7 +239,7 @@ int hypret_exact_topk(const float* q32, const float* g32, const double* g_sqnorm
   int rc = check_device();
   if (rc != HYPRET_OK) return rc;
   return hypret_launch_exact_topk(q32, g32, g_sqnorm64, Q, N, d, c, metric, k, idx_offset, q_list, q_count, fb_state,
-                                  out_score, out_idx, nullptr, static_cast<cudaStream_t>(stream));
+                                  out_score, out_idx, nullptr, init_bound, static_cast<cudaStream_t>(stream));
 }
 
 int hypret_exact_topk_after(const float* q32, const float* g32, const double* g_sqnorm64, int64_t Q, int64_t N, int d,
@@ -256,7 +257,7 @@ int hypret_exact_topk_after(const float* q32, const float* g32, const double* g_
   int rc = check_device();
   if (rc != HYPRET_OK) return rc;
   return hypret_launch_exact_topk(q32, g32, g_sqnorm64, Q, N, d, c, metric, k, idx_offset, q_list, q_count, fb_state,
-                                  out_score, out_idx, reinterpret_cast<const unsigned long long*>(after),
+                                  out_score, out_idx, reinterpret_cast<const unsigned long long*>(after), nullptr,
                                   static_cast<cudaStream_t>(stream));
 }
 

@@ -354,12 +354,13 @@ struct CertArgs {
   int32_t* count;         // [1] number of uncertified queries
   int32_t* list;          // [Q] their ids
   uint8_t* flags;         // [Q] or NULL: 1 = certified by the filter pass, 0 = sent to the exact scan
+  float* bound;           // [Q] or NULL: k-th score of the filtered result of an uncertified query (warm start of the scan)
   int ksel;               // candidates rescored per query (0 = k'); > k': lists of k' slots sharing a ksel-th-best bound
 };
 inline CertArgs no_cert() {
   CertArgs a;
   a.q_err = nullptr; a.g_stats = nullptr; a.slack = 0.f; a.state = nullptr; a.count = nullptr; a.list = nullptr;
-  a.flags = nullptr; a.ksel = 0;
+  a.flags = nullptr; a.ksel = 0; a.bound = nullptr;
   return a;
 }
 int hypret_launch_rerank(const float* q32, const float* g32, int64_t Q, int64_t N, int d, float c, int metric,
@@ -370,7 +371,7 @@ int hypret_launch_rerank(const float* q32, const float* g32, int64_t Q, int64_t 
 int hypret_launch_exact_topk(const float* q32, const float* g32, const double* g_sq64, int64_t Q, int64_t N, int d,
                              float c, int metric, int k, int64_t idx_offset, const int32_t* q_list,
                              const int32_t* q_count, int32_t* state, float* out_score, int64_t* out_idx,
-                             const unsigned long long* after, cudaStream_t stream);
+                             const unsigned long long* after, const float* init_bound, cudaStream_t stream);
 int hypret_launch_row_sqnorm64(const float* x, int64_t n, int d, double* out, cudaStream_t stream);
 int hypret_launch_cand_select(const float* cand_score, const int32_t* cand_idx, const int32_t* list_count, int64_t Q,
                               int n_cand, int kprime, float* sel_score, int32_t* sel_idx,

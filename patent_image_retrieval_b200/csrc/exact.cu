@@ -66,7 +66,8 @@ __global__ void __launch_bounds__(EX_WARPS * 32, NV <= 4 ? 2 : 1)
 exact_topk_kernel(const float* __restrict__ q32, const float* __restrict__ g32, const double* __restrict__ g_sq64,
                   int64_t N, int d, float c, int metric, int k, int64_t idx_offset,
                   const int32_t* __restrict__ q_list, const int32_t* __restrict__ q_count, int32_t* state,
-                  float* out_score, int64_t* out_idx, int64_t chunk, const unsigned long long* __restrict__ after) {
+                  float* out_score, int64_t* out_idx, int64_t chunk, const unsigned long long* __restrict__ after,
+                  const float* __restrict__ init_bound) {
   __shared__ unsigned long long lists[EX_WARPS][32];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int count = *q_count;
@@ -100,7 +101,21 @@ exact_topk_kernel(const float* __restrict__ q32, const float* __restrict__ g32, 
     // sthr = (cosh(sqrt(c) d_k) - 1) alpha / (2c));  dot32 + 2e-6 |x||y| >= cthr[u] |y|  (cosine).  +inf / -inf: list not full
     float thr[QB];
 #pragma unroll
-    for (int u = 0; u < QB; ++u) { mine[u] = EX_NONE; thr[u] = hyp ? INFINITY : -INFINITY; }
+    for (int u = 0; u < QB; ++u) {
+      mine[u] = EX_NONE;
+      thr[u] = hyp ? INFINITY : -INFINITY;
+      // init_bound[q]: a score no better than the query's true k-th best (the k-th entry of the filtered result, whose
+      // rows are real gallery rows with exact scores).  The scan then starts warm: only rows at or inside that bound
+      // are contenders, CTAs that see none skip the merge and its lock, and the union of the CTA lists still holds
+      // every row of the true top-k.
+      if (init_bound != nullptr && u < nq) {
+        const double b = (double)init_bound[q_list[it0 + u]];
+        if (hyp && b >= 0.0 && b < (double)INFINITY)
+          thr[u] = (float)((cosh(sqrt(cc) * b * (1.0 + 1e-5)) - 1.0) * (1.0 - cc * xsq[u]) / (2.0 * cc) * (1.0 + 1e-5));
+        else if (!hyp && b > -(double)INFINITY && b == b)
+          thr[u] = (float)(b * sqrt(xsq[u]) - 1e-5 * fabs(b * sqrt(xsq[u])) - 1e-30);
+      }
+    }
     constexpr int PASS = NV <= 8 ? 2 : 1;                   // rows in flight per warp: their registers bound it
     constexpr int CH = NV < 4 ? NV : 4;
     for (int64_t g0 = r_lo + (int64_t)warp * PASS; g0 < r_hi; g0 += EX_WARPS * PASS) {
@@ -209,6 +224,7 @@ exact_topk_kernel(const float* __restrict__ q32, const float* __restrict__ g32, 
 #pragma unroll
         for (int w = 1; w < EX_WARPS; ++w) best = ex_merge(best, lists[w][lane], lane);
         int32_t* lock = state + 2 * q;
+        if (__any_sync(0xffffffffu, best != EX_NONE)) {      // nothing to contribute: no lock, no traffic
         if (lane == 0) {
           while (atomicCAS(lock, 0, 1) != 0) __nanosleep(100);
         }
@@ -238,6 +254,7 @@ exact_topk_kernel(const float* __restrict__ q32, const float* __restrict__ g32, 
           *reinterpret_cast<volatile int32_t*>(lock + 1) = 1;
           __threadfence();
           atomicExch(lock, 0);
+        }
         }
       }
       __syncthreads();                                       // lists[] is rewritten by the next query
@@ -310,7 +327,7 @@ flag_compact_kernel(const int32_t* __restrict__ flags, int64_t n, int32_t* __res
 int hypret_launch_exact_topk(const float* q32, const float* g32, const double* g_sq64, int64_t Q, int64_t N, int d,
                              float c, int metric, int k, int64_t idx_offset, const int32_t* q_list,
                              const int32_t* q_count, int32_t* state, float* out_score, int64_t* out_idx,
-                             const unsigned long long* after, cudaStream_t stream) {
+                             const unsigned long long* after, const float* init_bound, cudaStream_t stream) {
   if (Q == 0 || N == 0) return HYPRET_OK;
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
@@ -329,7 +346,8 @@ int hypret_launch_exact_topk(const float* q32, const float* g32, const double* g
 #define HYPRET_EXACT_LAUNCH(NV)                                                                                     \
   do {                                                                                                              \
     exact_topk_kernel<NV, (NV <= 4 ? 4 : 2)><<<grid, EX_WARPS * 32, 0, stream>>>(                                   \
-        q32, g32, g_sq64, N, d, c, metric, k, idx_offset, q_list, q_count, state, out_score, out_idx, chunk, after); \
+        q32, g32, g_sq64, N, d, c, metric, k, idx_offset, q_list, q_count, state, out_score, out_idx, chunk, after,  \
+        init_bound);                                                                                                \
     return (int)cudaGetLastError();                                                                                 \
   } while (0)
   if (need <= 1) HYPRET_EXACT_LAUNCH(1);

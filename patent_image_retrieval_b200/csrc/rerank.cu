@@ -292,6 +292,7 @@ rerank_kernel(const float* __restrict__ q32, const float* __restrict__ g32, int6
   }
   if (out_margin != nullptr || cert.q_err != nullptr) {
     const double kth = __shfl_sync(0xffffffffu, my_sur, k - 1);
+    const float kth_val = __shfl_sync(0xffffffffu, (float)((metric == HYPRET_METRIC_HYPERBOLIC) ? my_key : -my_key), k - 1);
     const int kth_idx = __shfl_sync(0xffffffffu, my_idx, k - 1);
     // +inf: the candidate set was not truncated (fewer than k' valid candidates survive)
     const int n_valid = __popc(__ballot_sync(0xffffffffu, my_idx >= 0));
@@ -312,6 +313,7 @@ rerank_kernel(const float* __restrict__ q32, const float* __restrict__ g32, int6
         const bool ok = open_set || (kth_idx >= 0 && margin > E);
         if (cert.flags != nullptr) cert.flags[q] = ok ? 1 : 0;
         if (!ok) {
+          if (cert.bound != nullptr) cert.bound[q] = kth_idx >= 0 ? kth_val : (metric == HYPRET_METRIC_HYPERBOLIC ? INFINITY : -INFINITY);
           cert.state[2 * q] = 0;
           cert.state[2 * q + 1] = 0;
           cert.list[atomicAdd(cert.count, 1)] = (int)q;

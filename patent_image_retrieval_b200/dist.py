@@ -365,10 +365,11 @@ class ShardedGalleryIndex:
 
     def __init__(self, shard_features: torch.Tensor, row_offset: int, n_total: int, c: float = 1.0,
                  metric: str = "hyperbolic", space: str = "euclidean", group=None,
-                 device: Optional[torch.device] = None, queries: str = "replicated"):
+                 device: Optional[torch.device] = None, queries: str = "replicated", exact: bool = True):
         if queries not in ("replicated", "sharded"):
             raise ValueError(queries)
         self.queries = queries
+        self.exact = bool(exact)        # sharded queries: certify the merged lists and rescan what cannot be proven
         self.group = group
         self.n_total = int(n_total)
         self.local = GalleryIndex(shard_features, c=c, metric=metric, space=space, idx_offset=row_offset,
@@ -440,7 +441,7 @@ class ShardedGalleryIndex:
         """``queries`` = the replicated batch, or this rank's own batch when the index was built with
         ``queries="sharded"``.  Returns the global top-k of the queries passed in."""
         if self.queries == "sharded" and not self._single():
-            return self.search_sharded(queries, k=k, kprime=kprime, kernel_events=kernel_events)
+            return self.search_sharded(queries, k=k, kprime=kprime, kernel_events=kernel_events, exact=self.exact)
         return self.search_replicated(queries, k=k, kprime=kprime, kernel_events=kernel_events)
 
     def search_replicated(self, queries: torch.Tensor, k: int = 10, kprime: Optional[int] = None,
@@ -509,10 +510,14 @@ class ShardedGalleryIndex:
             with _span(kernel_events, "certify"):
                 own = slice(me * ql, (me + 1) * ql)
                 flags = ops.cert_merged(q32[own], score, idx, thr_all[own], q_err, stats_all, self.local.c, self.metric)
-                flags_all = torch.empty(world * ql, dtype=torch.int32, device=flags.device)
-                dist.all_gather_into_tensor(flags_all, flags, group=self.group)
+                # one all_gather carries the flag and the owner's k-th merged score (the rescans' warm-start bound)
+                fb = torch.stack([flags.float(), score[:, k - 1]], dim=1)
+                fb_all = torch.empty(world * ql, 2, dtype=torch.float32, device=flags.device)
+                dist.all_gather_into_tensor(fb_all, fb, group=self.group)
+                flags_all = (fb_all[:, 0] != 0).to(torch.int32)
                 xs, xi = ops.exact_topk_flagged(q32, self.local.rows32, self.local.rows_sq64, flags_all, self.local.c,
-                                                self.metric, k, idx_offset=self.local.idx_offset)
+                                                self.metric, k, idx_offset=self.local.idx_offset,
+                                                init_bound=fb_all[:, 1])
                 xs, xi = return_lists_to_owners(xs, xi, self.group)
                 xs, xi = ops.merge_topk(xs, xi, descending=(self.metric == "cosine"))
                 redo = flags.bool()[:, None]

@@ -205,6 +205,7 @@ class CertBuffers:
         self.count = torch.zeros(1, dtype=torch.int32, device=device)
         self.list = torch.empty(Q, dtype=torch.int32, device=device)
         self.certified = torch.empty(Q, dtype=torch.uint8, device=device)
+        self.bound = torch.empty(Q, dtype=torch.float32, device=device)      # k-th filtered score of uncertified queries
 
 
 def rerank_cert(q32: torch.Tensor, g32: torch.Tensor, cand_score: torch.Tensor, cand_idx: torch.Tensor, c: float,
@@ -232,12 +233,12 @@ def rerank_cert(q32: torch.Tensor, g32: torch.Tensor, cand_score: torch.Tensor, 
                                           _ptr(cand_idx), _ptr(list_count), S, kprime, int(ksel), int(k),
                                           int(idx_offset), _ptr(out_s), _ptr(out_i), _ptr(margin), _ptr(q_err),
                                           _ptr(g_stats),
-                                          _ptr(bufs.state), _ptr(bufs.count), _ptr(bufs.list), _ptr(bufs.certified),
-                                          _stream()))
+                                          _ptr(bufs.state), _ptr(bufs.count), _ptr(bufs.list), _ptr(bufs.bound),
+                                          _ptr(bufs.certified), _stream()))
         if fallback:
             _lib.check(lib.hypret_exact_topk(_ptr(q32), _ptr(g32), _ptr(g_sqnorm64), Q, N, d, float(c), METRIC[metric],
                                              int(k), int(idx_offset), _ptr(bufs.list), _ptr(bufs.count),
-                                             _ptr(bufs.state), _ptr(out_s), _ptr(out_i), _stream()))
+                                             _ptr(bufs.state), _ptr(bufs.bound), _ptr(out_s), _ptr(out_i), _stream()))
     return (out_s, out_i, margin) if want_margin else (out_s, out_i)
 
 
@@ -258,7 +259,7 @@ def exact_topk(q32: torch.Tensor, g32: torch.Tensor, g_sqnorm64: torch.Tensor, c
     with torch.cuda.device(dev):
         _lib.check(_lib.load().hypret_exact_topk(_ptr(q32), _ptr(g32), _ptr(g_sqnorm64), Q, g32.shape[0], d, float(c),
                                                  METRIC[metric], int(k), int(idx_offset), _ptr(lst), _ptr(cnt),
-                                                 _ptr(state), _ptr(out_s), _ptr(out_i), _stream()))
+                                                 _ptr(state), None, _ptr(out_s), _ptr(out_i), _stream()))
     return out_s, out_i
 
 
@@ -278,10 +279,11 @@ def cert_merged(q32: torch.Tensor, score: torch.Tensor, idx: torch.Tensor, thr: 
 
 
 def exact_topk_flagged(q32: torch.Tensor, g32: torch.Tensor, g_sqnorm64: torch.Tensor, flags: torch.Tensor, c: float,
-                       metric: str, k: int, idx_offset: int = 0):
+                       metric: str, k: int, idx_offset: int = 0, init_bound: Optional[torch.Tensor] = None):
     """Exact top-k over this shard of the FLAGGED queries only (``hypret_flag_compact`` + ``hypret_exact_topk``, the
-    list built and read on the device).  Returns ``(score [Q,k], idx [Q,k])``; rows of unflagged queries are +-inf / -1."""
-    _need_cuda(q32, g32, g_sqnorm64, flags)
+    list built and read on the device).  Returns ``(score [Q,k], idx [Q,k])``; rows of unflagged queries are +-inf / -1.
+    ``init_bound [Q]``: a score no better than each query's true k-th best (warm start, ``hypret_exact_topk``)."""
+    _need_cuda(q32, g32, g_sqnorm64, flags, init_bound)
     q32, g32 = q32.contiguous(), g32.contiguous()
     Q, d = q32.shape
     dev = q32.device
@@ -295,6 +297,7 @@ def exact_topk_flagged(q32: torch.Tensor, g32: torch.Tensor, g_sqnorm64: torch.T
         _lib.check(lib.hypret_flag_compact(_ptr(flags.contiguous()), Q, _ptr(lst), _ptr(cnt), _ptr(state), _stream()))
         _lib.check(lib.hypret_exact_topk(_ptr(q32), _ptr(g32), _ptr(g_sqnorm64), Q, g32.shape[0], d, float(c),
                                          METRIC[metric], int(k), int(idx_offset), _ptr(lst), _ptr(cnt), _ptr(state),
+                                         _ptr(init_bound.contiguous().float() if init_bound is not None else None),
                                          _ptr(out_s), _ptr(out_i), _stream()))
     return out_s, out_i
 
@@ -331,7 +334,7 @@ def exact_topk_any(q32: torch.Tensor, g32: torch.Tensor, g_sqnorm64: torch.Tenso
             if first:
                 _lib.check(lib.hypret_exact_topk(_ptr(q32), _ptr(g32), _ptr(g_sqnorm64), Q, g32.shape[0], d, float(c),
                                                  METRIC[metric], kk, int(idx_offset), _ptr(lst), _ptr(cnt), _ptr(state),
-                                                 _ptr(out_s), _ptr(out_i), _stream()))
+                                                 None, _ptr(out_s), _ptr(out_i), _stream()))
             else:
                 _lib.check(lib.hypret_exact_topk_after(_ptr(q32), _ptr(g32), _ptr(g_sqnorm64), Q, g32.shape[0], d,
                                                        float(c), METRIC[metric], kk, int(idx_offset), _ptr(lst),

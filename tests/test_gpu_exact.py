@@ -277,3 +277,28 @@ def test_lists_of_16_sharing_the_bound_of_the_24th_best(metric):
         sur = -(x * y).sum(1) / (x.norm(dim=1) * y.norm(dim=1))
     limit = torch.minimum(top_s[:, -1], worst_full).double()
     assert float(((limit - sur) - margin.double()).abs().max()) < 1e-5
+
+
+@pytest.mark.parametrize("metric", ["hyperbolic", "cosine"])
+def test_exact_scan_warm_start_bound(metric):
+    """hypret_exact_topk with init_bound (the k-th score of any list of real rows): CTAs whose chunk holds no contender
+    skip the merge, and the result is still the exact top-k -- for a loose bound, the TIGHT bound (the true k-th score
+    itself: ties at the bound must stay contenders), no bound (+-inf) and a mixture; unflagged rows stay untouched."""
+    Q, N, d, c, k = 37, 30000, 256, 1.0, 10
+    gal = synth.gaussian_features(N, d, seed=0).cuda()
+    qry = synth.gaussian_features(Q, d, seed=1).cuda()
+    if metric == "hyperbolic":
+        gal = ops.project_rows(gal, c, want_operand=False)[0]
+        qry = ops.project_rows(qry, c, want_operand=False)[0]
+    sq = ops.row_sqnorm64(gal)
+    want_s, want_i = ops.exact_topk(qry, gal, sq, c, metric, k)
+    deep_s, _ = ops.exact_topk(qry, gal, sq, c, metric, 32)
+    none = float("inf") if metric == "hyperbolic" else float("-inf")
+    flags = torch.ones(Q, dtype=torch.int32, device="cuda")
+    flags[5] = 0
+    for bound in (deep_s[:, 31], want_s[:, k - 1], torch.full((Q,), none, device="cuda"),
+                  torch.where(torch.arange(Q, device="cuda") % 2 == 0, want_s[:, k - 1], deep_s[:, 20])):
+        got_s, got_i = ops.exact_topk_flagged(qry, gal, sq, flags, c, metric, k, init_bound=bound.contiguous())
+        keep = flags.bool()
+        assert torch.equal(got_i[keep], want_i[keep]) and torch.equal(got_s[keep], want_s[keep])
+        assert bool((got_i[5] == -1).all())
