@@ -7,6 +7,7 @@ first call raises.  Every wrapper checks the integer status and raises
 from __future__ import annotations
 
 import ctypes
+import os
 from ctypes import (c_char_p, c_float, c_int, c_int32, c_int64, c_size_t, c_uint32, c_void_p, POINTER,
                     Structure)
 
@@ -159,7 +160,8 @@ def load() -> ctypes.CDLL:
     if _LIB is not None:
         return _LIB
     try:
-        path = _build.build()
+        # HYPRET_CHECKED=1: the library built with -DHYPRET_CHECKED (device-side asserts on every guarded index)
+        path = _build.build(checked=os.environ.get("HYPRET_CHECKED", "0") == "1")
     except Exception as exc:  # no silent fallback: surface the build failure
         raise RuntimeError(f"libhypret.so is not built and cannot be built here: {exc}") from exc
     lib = ctypes.CDLL(str(path))

@@ -19,6 +19,10 @@ INCLUDE = PKG_DIR.parent / "include"
 LIB_PATH = PKG_DIR / "libhypret.so"
 STAMP = PKG_DIR / ".libhypret.stamp"
 OBJ_DIR = PKG_DIR / "build"
+# the CHECKED build: the same sources with -DHYPRET_CHECKED, which turns every HYPRET_CHECK(...) in the kernels into a
+# device-side assert on the index about to be used (compute-sanitizer is closed on this GPU pool; tests/test_gpu_checked.py
+# runs the ragged-shape cases through this library: an out-of-range index traps instead of corrupting memory)
+CHECKED_LIB_PATH = PKG_DIR / "libhypret_checked.so"
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
@@ -32,8 +36,9 @@ def sources():
     return sorted(CSRC.glob("*.cu"))
 
 
-def _fingerprint() -> str:
+def _fingerprint(extra: str = "") -> str:
     h = hashlib.sha256()
+    h.update(extra.encode())
     for f in sorted(list(CSRC.glob("*.cu")) + list(CSRC.glob("*.cuh")) + list(INCLUDE.glob("*.h"))):
         h.update(f.name.encode())
         h.update(f.read_bytes())
@@ -48,12 +53,13 @@ def find_nvcc() -> str | None:
     return None
 
 
-def is_fresh() -> bool:
-    return LIB_PATH.exists() and STAMP.exists() and STAMP.read_text().strip() == _fingerprint()
+def is_fresh(checked: bool = False) -> bool:
+    lib, stamp = (CHECKED_LIB_PATH, PKG_DIR / ".libhypret_checked.stamp") if checked else (LIB_PATH, STAMP)
+    return lib.exists() and stamp.exists() and stamp.read_text().strip() == _fingerprint("checked" if checked else "")
 
 
-def _compile_one(nvcc: str, src: Path, obj: Path, verbose: bool) -> str:
-    cmd = [nvcc, *[f for f in NVCC_FLAGS if f != "-shared"], "-c", "-o", str(obj), str(src)]
+def _compile_one(nvcc: str, src: Path, obj: Path, verbose: bool, extra=()) -> str:
+    cmd = [nvcc, *[f for f in NVCC_FLAGS if f != "-shared"], *extra, "-c", "-o", str(obj), str(src)]
     if verbose:
         cmd[1:1] = ["-Xptxas", "-v"]
     res = subprocess.run(cmd, capture_output=True, text=True)
@@ -62,39 +68,43 @@ def _compile_one(nvcc: str, src: Path, obj: Path, verbose: bool) -> str:
     return res.stderr
 
 
-def build(force: bool = False, verbose: bool = False) -> Path:
+def build(force: bool = False, verbose: bool = False, checked: bool = False) -> Path:
     """One object per ``csrc/*.cu`` (compiled in parallel, recompiled only when that source, a header or the
-    flags changed), linked into ``libhypret.so``."""
-    if not force and is_fresh():
-        return LIB_PATH
+    flags changed), linked into ``libhypret.so`` (``checked``: ``libhypret_checked.so``, device-side index asserts on)."""
+    lib_path = CHECKED_LIB_PATH if checked else LIB_PATH
+    stamp = PKG_DIR / ".libhypret_checked.stamp" if checked else STAMP
+    obj_dir = PKG_DIR / "build_checked" if checked else OBJ_DIR
+    extra = ("-DHYPRET_CHECKED",) if checked else ()
+    if not force and is_fresh(checked):
+        return lib_path
     nvcc = find_nvcc()
     if nvcc is None:
         raise RuntimeError("nvcc not found: cannot build libhypret.so (no CPU fallback exists)")
     from concurrent.futures import ThreadPoolExecutor
-    OBJ_DIR.mkdir(exist_ok=True)
+    obj_dir.mkdir(exist_ok=True)
     shared = hashlib.sha256()
     for f in sorted(list(CSRC.glob("*.cuh")) + list(INCLUDE.glob("*.h"))):
         shared.update(f.read_bytes())
-    shared.update(" ".join(NVCC_FLAGS).encode())
+    shared.update(" ".join(NVCC_FLAGS + list(extra)).encode())
     jobs = []
     for src in sources():
-        obj, tag = OBJ_DIR / (src.stem + ".o"), OBJ_DIR / (src.stem + ".tag")
+        obj, tag = obj_dir / (src.stem + ".o"), obj_dir / (src.stem + ".tag")
         want = hashlib.sha256(shared.digest() + src.read_bytes()).hexdigest()
         if force or not obj.exists() or not tag.exists() or tag.read_text() != want:
             jobs.append((src, obj, tag, want))
     with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as pool:
-        logs = list(pool.map(lambda j: _compile_one(nvcc, j[0], j[1], verbose), jobs))
+        logs = list(pool.map(lambda j: _compile_one(nvcc, j[0], j[1], verbose, extra), jobs))
     for (src, obj, tag, want), log in zip(jobs, logs):
         tag.write_text(want)
         if verbose:
             print(f"== {src.name}\n{log}", file=sys.stderr)
-    objs = [str(OBJ_DIR / (s.stem + ".o")) for s in sources()]
-    res = subprocess.run([nvcc, "-shared", "-o", str(LIB_PATH), *objs], capture_output=True, text=True)
+    objs = [str(obj_dir / (s.stem + ".o")) for s in sources()]
+    res = subprocess.run([nvcc, "-shared", "-o", str(lib_path), *objs], capture_output=True, text=True)
     if res.returncode != 0:
         raise RuntimeError(f"link failed ({res.returncode}):\n{res.stdout}\n{res.stderr}")
-    STAMP.write_text(_fingerprint())
-    return LIB_PATH
+    stamp.write_text(_fingerprint("checked" if checked else ""))
+    return lib_path
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, checked="--checked" in sys.argv))

@@ -14,6 +14,16 @@
 
 #include "../../include/hypret.h"
 
+// Checked build (python -m patent_image_retrieval_b200.build --checked, -DHYPRET_CHECKED): every HYPRET_CHECK guards
+// an index or a count right before it is used -- a violation traps the kernel (cudaErrorAssert at the next
+// synchronisation) instead of reading or writing out of bounds.  The product build compiles them away.
+#ifdef HYPRET_CHECKED
+#include <assert.h>
+#define HYPRET_CHECK(cond) assert(cond)
+#else
+#define HYPRET_CHECK(cond) ((void)0)
+#endif
+
 // ----------------------------------------------------------------------------- geometry
 // fp16 GEMM operand row (scoring) = [ Dpad main columns | 16 extension columns ], Dpad = roundup(D, 64).
 constexpr int HYPRET_KBLK = 64;   // K elements per 128B-swizzled block

@@ -85,6 +85,7 @@ exact_topk_kernel(const float* __restrict__ q32, const float* __restrict__ g32, 
     for (int u = 0; u < QB; ++u) {
       aft[u] = (after != nullptr && u < nq) ? after[it0 + u] : 0ull;
       const int64_t qid = q_list[it0 + (u < nq ? u : 0)];    // pad the group with its first query (never inserted)
+      HYPRET_CHECK(qid >= 0 && it0 + u < count + QB);
       const float4* qrow = reinterpret_cast<const float4*>(q32 + qid * d);
       double acc = 0.0;
 #pragma unroll
@@ -124,6 +125,7 @@ exact_topk_kernel(const float* __restrict__ q32, const float* __restrict__ g32, 
 #pragma unroll
       for (int t = 0; t < PASS; ++t) {
         val[t] = g0 + t < r_hi;
+        HYPRET_CHECK(!val[t] || (g0 + t >= 0 && g0 + t < N));
         g[t] = reinterpret_cast<const float4*>(g32 + (val[t] ? g0 + t : r_lo) * d);
       }
       double ysq[PASS];                                      // requested with the rows, used after them
@@ -313,7 +315,9 @@ flag_compact_kernel(const int32_t* __restrict__ flags, int64_t n, int32_t* __res
   __syncthreads();
   for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
     if (flags[i] != 0) {
-      list[atomicAdd(&total, 1)] = (int32_t)i;
+      const int at = atomicAdd(&total, 1);
+      HYPRET_CHECK(at >= 0 && at < n);
+      list[at] = (int32_t)i;
       state[2 * i] = 0;
       state[2 * i + 1] = 0;
     }

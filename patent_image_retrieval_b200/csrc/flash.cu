@@ -514,6 +514,7 @@ flash_tile_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
 #pragma unroll
             for (int jj = 0; jj < 32; ++jj) sj = jj == j ? v[jj] : sj;
             if (sj < near_thr && cb + j < n_cols) {
+              HYPRET_CHECK(i >= 0 && i < p.n && j0 + cb + j < p.m);
               const float ex = flash_exact_sq(p.x32 + i * p.d, p.y32 + (j0 + cb + j) * p.d, p.d);
 #pragma unroll
               for (int jj = 0; jj < 32; ++jj) v[jj] = jj == j ? ex : v[jj];     // keeps v[] in registers
@@ -569,6 +570,7 @@ flash_tile_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
       }
       if (seg_last) {
         const int slot = (int)blockIdx.x - flash_cta_of_tile((int64_t)rt * p.n_ct, T, P);
+        HYPRET_CHECK(slot >= 0 && slot < p.n_slots && rt >= 0 && rt < p.n_rt);
         if (!BWD) {
           float* o = p.part + ((((int64_t)rt * p.n_slots + slot) * F_NWG + wg) * 2) * FT_M;
           o[row] = -p.kappa * run_m;                      // max logit (log2 units); -inf when no column was seen

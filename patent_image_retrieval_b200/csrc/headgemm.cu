@@ -228,6 +228,7 @@ mobius_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
 #pragma unroll
           for (int j = 0; j < 32; j += 8) {
             if (cc * 32 + j >= p.n_out) continue;
+            HYPRET_CHECK(i >= 0 && i < p.n && cc * 32 + j + 8 <= p.n_out && 3 * p.n_out <= p.op_kpad);
             if (p.y_out != nullptr) {
               float* o = p.y_out + i * p.n_out + cc * 32 + j;
               *reinterpret_cast<float4*>(o) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);

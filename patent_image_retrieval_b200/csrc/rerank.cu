@@ -160,6 +160,7 @@ rerank_kernel(const float* __restrict__ q32, const float* __restrict__ g32, int6
 
   // ---- 1. approximate merge: the k' best candidates by surrogate score --------------------
   const int n_mine = list_count != nullptr ? min(list_count[q] * kprime, n_cand) : n_cand;   // compact list slots
+  HYPRET_CHECK(n_mine >= 0 && n_mine <= n_cand && (list_count == nullptr || list_count[q] * kprime <= n_cand));
   for (int t = lane; t < n_mine; t += 32) {
     cs[t] = cand_score[q * n_cand + t];
     ci[t] = cand_idx[q * n_cand + t];
@@ -209,6 +210,7 @@ rerank_kernel(const float* __restrict__ q32, const float* __restrict__ g32, int6
     for (int t = 0; t < PASS; ++t) {
       const int id = __shfl_sync(0xffffffffu, my_idx, (r0 + t) & 31);
       val[t] = (r0 + t < n_sel);
+      HYPRET_CHECK(!val[t] || (id >= 0 && id < N));
       g[t] = reinterpret_cast<const float4*>(g32 + (int64_t)(val[t] ? id : 0) * d);
     }
     double sacc[PASS], yacc[PASS];
@@ -316,7 +318,9 @@ rerank_kernel(const float* __restrict__ q32, const float* __restrict__ g32, int6
           if (cert.bound != nullptr) cert.bound[q] = kth_idx >= 0 ? kth_val : (metric == HYPRET_METRIC_HYPERBOLIC ? INFINITY : -INFINITY);
           cert.state[2 * q] = 0;
           cert.state[2 * q + 1] = 0;
-          cert.list[atomicAdd(cert.count, 1)] = (int)q;
+          const int at = atomicAdd(cert.count, 1);
+          HYPRET_CHECK(at >= 0 && at < Q);
+          cert.list[at] = (int)q;
         }
       }
     }

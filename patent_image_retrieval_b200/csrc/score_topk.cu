@@ -506,6 +506,7 @@ __device__ __forceinline__ void process_chunk_reg(const float (&v)[32], int cbas
               sts_b32(qi_addr + st.cnt * LIST_SLOT_STRIDE, cbase + g * 8 + j);
             } else {
               st.n_now += 1;
+              HYPRET_CHECK(st.cnt - QCAP_R < OVF);
               ovf_s[st.cnt - QCAP_R] = x;
               ovf_i[st.cnt - QCAP_R] = cbase + g * 8 + j;
             }
@@ -859,6 +860,7 @@ score_topk_kernel(const __grid_constant__ CUtensorMap map_q_main, const __grid_c
         if (p.list_count != nullptr) pos = L.i0 < 0 ? -1 : atomicAdd(&p.list_count[qrow], 1);
         if (pos >= 0) {
           const int64_t o = (qrow * sc.n_lists + pos) * KP;
+          HYPRET_CHECK(pos < sc.n_lists && qrow >= 0 && qrow < p.Q && KP <= RL);
           reg_publish(L, KP, p.cand_score + o, p.cand_idx + o);
         }
       }
@@ -988,6 +990,7 @@ score_topk_kernel(const __grid_constant__ CUtensorMap map_q_main, const __grid_c
         if (qr < p.Q && pos >= 0) {
           for (int e = lane; e < KP; e += 32) {
             const int64_t o = (qr * sc.n_lists + pos) * KP + e;
+            HYPRET_CHECK(pos < sc.n_lists && e < KPP && o < p.Q * sc.n_lists * KP);
             p.cand_score[o] = list_s[e * TILE_M + quad * 32 + r];
             p.cand_idx[o] = list_i[e * TILE_M + quad * 32 + r];
           }
