@@ -245,7 +245,7 @@ int hypret_flag_compact(const int32_t* flags, int64_t n, int32_t* q_list, int32_
                         void* stream);
 
 /* The next page of the same exact ranking: only rows whose key (ordered fp32 score << 32 | local row id, the order of the
- * result lists) lies ABOVE after[i] for list entry i are taken.  Paging through the ranking 32 rows at a time gives the
+ * result lists) lies ABOVE after[q] of the listed query q (after is indexed by query id, [Q]) are taken.  Paging through the ranking 32 rows at a time gives the
  * exact top-k for any k (notebooks/retrieval.ipynb:202 with k beyond the 128 the filtered path serves). */
 int hypret_exact_topk_after(const float* q32, const float* g32, const double* g_sqnorm64, int64_t Q, int64_t N, int d,
                             float c, int metric, int k, int64_t idx_offset, const int32_t* q_list,

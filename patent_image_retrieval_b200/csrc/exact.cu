@@ -83,8 +83,8 @@ exact_topk_kernel(const float* __restrict__ q32, const float* __restrict__ g32, 
     unsigned long long aft[QB];                              // paging: only rows whose key is ABOVE this one are taken
 #pragma unroll
     for (int u = 0; u < QB; ++u) {
-      aft[u] = (after != nullptr && u < nq) ? after[it0 + u] : 0ull;
       const int64_t qid = q_list[it0 + (u < nq ? u : 0)];    // pad the group with its first query (never inserted)
+      aft[u] = (after != nullptr && u < nq) ? after[qid] : 0ull;      // indexed by QUERY id, like every per-query array
       HYPRET_CHECK(qid >= 0 && it0 + u < count + QB);
       const float4* qrow = reinterpret_cast<const float4*>(q32 + qid * d);
       double acc = 0.0;

@@ -347,6 +347,53 @@ def exact_topk_any(q32: torch.Tensor, g32: torch.Tensor, g_sqnorm64: torch.Tenso
     return torch.cat(pages_s, dim=1), torch.cat(pages_i, dim=1)
 
 
+def exact_topk_any_flagged(q32: torch.Tensor, g32: torch.Tensor, g_sqnorm64: torch.Tensor, flags: torch.Tensor, c: float,
+                           metric: str, k: int, idx_offset: int = 0):
+    """``exact_topk_any`` for the FLAGGED queries only (list built on the device, nothing read by the host): pages of 32
+    through the exact ranking.  Returns ``(score [Q,k], idx [Q,k])``; rows of unflagged queries are +-inf / -1."""
+    _need_cuda(q32, g32, g_sqnorm64, flags)
+    q32, g32 = q32.contiguous().float(), g32.contiguous().float()
+    Q, d = q32.shape
+    dev = q32.device
+    fill = float("inf") if metric == "hyperbolic" else float("-inf")
+    lst = torch.empty(Q, dtype=torch.int32, device=dev)
+    cnt = torch.empty(1, dtype=torch.int32, device=dev)
+    state = torch.empty(2 * Q, dtype=torch.int32, device=dev)
+    flags = flags.contiguous().to(torch.int32)
+    after = torch.zeros(Q, dtype=torch.int64, device=dev)
+    pages_s, pages_i = [], []
+    lib = _lib.load()
+    for k0 in range(0, k, 32):
+        kk = min(32, k - k0)
+        out_s = torch.full((Q, kk), fill, dtype=torch.float32, device=dev)
+        out_i = torch.full((Q, kk), -1, dtype=torch.int64, device=dev)
+        with torch.cuda.device(dev):
+            _lib.check(lib.hypret_flag_compact(_ptr(flags), Q, _ptr(lst), _ptr(cnt), _ptr(state), _stream()))
+            if k0 == 0:
+                _lib.check(lib.hypret_exact_topk(_ptr(q32), _ptr(g32), _ptr(g_sqnorm64), Q, g32.shape[0], d, float(c),
+                                                 METRIC[metric], kk, int(idx_offset), _ptr(lst), _ptr(cnt), _ptr(state),
+                                                 None, _ptr(out_s), _ptr(out_i), _stream()))
+            else:
+                _lib.check(lib.hypret_exact_topk_after(_ptr(q32), _ptr(g32), _ptr(g_sqnorm64), Q, g32.shape[0], d,
+                                                       float(c), METRIC[metric], kk, int(idx_offset), _ptr(lst),
+                                                       _ptr(cnt), _ptr(state), _ptr(after), _ptr(out_s), _ptr(out_i),
+                                                       _stream()))
+        pages_s.append(out_s)
+        pages_i.append(out_i)
+        after = _packed_keys(out_s[:, -1], out_i[:, -1], metric, idx_offset)
+    return torch.cat(pages_s, dim=1), torch.cat(pages_i, dim=1)
+
+
+def certificate_bound(q32: torch.Tensor, q_err: torch.Tensor, g_stats: torch.Tensor, c: float, metric: str,
+                      d: int) -> torch.Tensor:
+    """The rounding bound E of the fp16 filter per query (the formula hypret_rerank_cert evaluates in the
+    kernel), for paths that compare a margin with it on the device: ``[Q]`` fp32."""
+    st = g_stats.double()
+    qn = (float(c) * row_sqnorm(q32).double()).sqrt() if metric == "hyperbolic" else torch.ones_like(q_err, dtype=torch.float64)
+    slack = (operand_kpad(d) / 16 + 8) * 2.0 ** -22
+    return (q_err.double() * st[0] + qn * st[1] + slack * (qn * st[0] + qn * qn * st[2] + st[3])).float()
+
+
 def row_sqnorm64(x: torch.Tensor) -> torch.Tensor:
     """``||x_i||^2`` accumulated in fp64 (``hypret_row_sqnorm64``): the per-row constant of the exact rerank."""
     _need_cuda(x)

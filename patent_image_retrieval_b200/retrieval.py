@@ -122,6 +122,7 @@ class GalleryIndex:
         self._cand = {}
         self._cert = None
         self.certificate = None     # CertBuffers of the last exact search (device-side; see ops.rerank_cert)
+        self.uncertified_wide = None   # [Q] int32 flags of the last exact wide search (26 < k <= 128)
 
     def _query_mode(self):
         if self.metric == "cosine":
@@ -139,8 +140,8 @@ class GalleryIndex:
         rounding residuals of the operands, that no row outside the candidate set can precede the k-th result, and the
         queries it cannot prove (near-duplicate galleries) are recomputed by a full exact scan queued on the same
         stream -- no host synchronisation either way.  ``self.certificate`` (``ops.CertBuffers``) holds the per-query
-        flags and the count of rescanned queries.  k <= 26; wider k returns the filtered result with its own
-        ``margin`` diagnostic.  ``kbound``: see ``default_kbound`` (None = default; = k' for plain k'-slot semantics).
+        flags and the count of rescanned queries (k <= 26; for 26 < k <= 128 ``self.uncertified_wide`` holds the flags
+        of the queries that were paged through the exact ranking instead).  ``kbound``: see ``default_kbound`` (None = default; = k' for plain k'-slot semantics).
         ``kernel_events``: a list (receives a (start, end) CUDA-event pair bracketing the scoring kernel
         on the launching stream per call) or a ``StageEvents`` (all three kernels): bench.py's rooflines."""
         if k > ops.MAX_K:
@@ -157,6 +158,20 @@ class GalleryIndex:
             kbound = default_kbound(k, kp) if (exact and k <= kp) else kp
         q32, cs, ci, cnt, q_err = self.score_candidates(queries, k=k, kprime=kp, max_ctas=max_ctas,
                                                         kernel_events=kernel_events, want_err=exact, kbound=kbound)
+        if exact and (k > kp or k > 32 or kp > 32):
+            # wide top-k (26 < k <= 128): the wide rerank's margin (smallest filter score a non-candidate can have - exact
+            # surrogate of the k-th result) against the same rounding bound E; queries it does not clear are paged
+            # through the exact ranking by full scans (device list, no host round trip) and overwrite their rows
+            score, idx, margin = self.rerank_candidates(q32, cs, ci, k, return_margin=True, kernel_events=kernel_events,
+                                                        list_count=cnt)
+            bound = ops.certificate_bound(q32, q_err, self.stats, self.c, self.metric, self.d)
+            flags = (~(margin > bound)).to(torch.int32)
+            xs, xi = ops.exact_topk_any_flagged(q32, self.rows32, self.rows_sq64, flags, self.c, self.metric,
+                                                min(k, self.n), idx_offset=self.idx_offset)
+            redo = flags.bool()[:, None]
+            self.uncertified_wide = flags
+            score, idx = torch.where(redo, xs, score), torch.where(redo, xi, idx)
+            return (score, idx, margin) if return_margin else (score, idx)
         return self.rerank_candidates(q32, cs, ci, k, return_margin=return_margin, kernel_events=kernel_events,
                                       list_count=cnt, q_err=q_err if exact else None, ksel=kbound)
 

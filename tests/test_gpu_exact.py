@@ -302,3 +302,20 @@ def test_exact_scan_warm_start_bound(metric):
         keep = flags.bool()
         assert torch.equal(got_i[keep], want_i[keep]) and torch.equal(got_s[keep], want_s[keep])
         assert bool((got_i[5] == -1).all())
+
+
+@pytest.mark.parametrize("metric", ["hyperbolic", "cosine"])
+def test_wide_topk_is_exact_too(metric):
+    """26 < k <= 128: search() compares the wide rerank's margin with the rounding bound and pages the queries that do
+    not clear it through the exact ranking; on a near-duplicate gallery most queries take that path, and every list
+    equals the full exact scan's (ops.exact_topk_any)."""
+    Q, d, c, k = 48, 128, 1.0, 100
+    for N, noise, per_class in ((6000, 0.3, 50), (30000, 1e-4, 600)):
+        gal, qry = _near_duplicates(N, Q, d, noise, c, metric, per_class=per_class)
+        index = GalleryIndex(gal.cuda(), c=c, metric=metric, space="ball" if metric == "hyperbolic" else "euclidean")
+        got_s, got_i = index.search(qry.cuda(), k=k)
+        want_s, want_i = ops.exact_topk_any(qry.cuda().contiguous(), index.rows32, index.rows_sq64, c, metric, k)
+        assert torch.equal(got_i, want_i), (metric, noise, int((got_i != want_i).any(dim=1).sum()))
+        assert torch.equal(got_s, want_s)
+        if noise < 1e-2:      # 600 rows per class inside the rounding band: more than the 256 rescored survivors
+            assert int(index.uncertified_wide.sum()) > 0
