@@ -164,3 +164,16 @@ def test_ctypes_structs_match_the_c_header_layout(tmp_path):
     want = [ctypes.sizeof(_lib.PeerRoute)] + [getattr(_lib.PeerRoute, f).offset for f in fields_route]
     want += [ctypes.sizeof(_lib.ScorePlan)] + [getattr(_lib.ScorePlan, f).offset for f in fields_plan]
     assert got == want
+
+
+def test_default_list_sizes_and_certificate_candidates():
+    """k <= 10 keeps the 16-slot register lists and certifies with k+14 candidates (the bound of the 24th best at k=10);
+    11 <= k <= 26 uses k+14 slots (<= 32) directly; beyond that the 64-slot wide lists."""
+    from patent_image_retrieval_b200.retrieval import default_kbound, default_kprime
+    assert [default_kprime(k) for k in (1, 5, 10, 11, 18, 26, 27, 100, 128)] == [16, 16, 16, 25, 32, 32, 64, 64, 64]
+    assert [default_kbound(k, default_kprime(k)) for k in (1, 5, 10, 11, 26, 100)] == [16, 19, 24, 25, 32, 64]
+    for k in range(1, 27):
+        kp, kb = default_kprime(k), default_kbound(k, default_kprime(k))
+        assert k <= kp <= 32 and kp <= kb <= 32
+    with pytest.raises(ValueError):
+        default_kprime(129)
