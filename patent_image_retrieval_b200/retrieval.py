@@ -144,6 +144,10 @@ class GalleryIndex:
         of the queries that were paged through the exact ranking instead).  ``kbound``: see ``default_kbound`` (None = default; = k' for plain k'-slot semantics).
         ``kernel_events``: a list (receives a (start, end) CUDA-event pair bracketing the scoring kernel
         on the launching stream per call) or a ``StageEvents`` (all three kernels): bench.py's rooflines."""
+        if queries.shape[0] == 0:                 # an empty batch is an empty result (sklearn / torch.topk semantics)
+            empty = (torch.empty(0, k, dtype=torch.float32, device=self.device),
+                     torch.empty(0, k, dtype=torch.int64, device=self.device))
+            return empty + (torch.empty(0, dtype=torch.float32, device=self.device),) if return_margin else empty
         if k > ops.MAX_K:
             # beyond the filtered path: page through the exact ranking by full scans (the reference ranks the whole
             # gallery, notebooks/retrieval.ipynb:383; its metrics are served by rank counting, this serves its lists)
@@ -168,6 +172,11 @@ class GalleryIndex:
             flags = (~(margin > bound)).to(torch.int32)
             xs, xi = ops.exact_topk_any_flagged(q32, self.rows32, self.rows_sq64, flags, self.c, self.metric,
                                                 min(k, self.n), idx_offset=self.idx_offset)
+            if xs.shape[1] < k:                   # fewer gallery rows than k: the tail reads as empty, like the rerank's
+                pad = k - xs.shape[1]
+                fill = float("inf") if self.metric == "hyperbolic" else float("-inf")
+                xs = torch.nn.functional.pad(xs, (0, pad), value=fill)
+                xi = torch.nn.functional.pad(xi, (0, pad), value=-1)
             redo = flags.bool()[:, None]
             self.uncertified_wide = flags
             score, idx = torch.where(redo, xs, score), torch.where(redo, xi, idx)

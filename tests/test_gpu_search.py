@@ -148,3 +148,12 @@ def test_wide_topk_k33_to_k128_and_short_galleries():
     small = GalleryIndex(synth.gaussian_features(40, 64, seed=0).cuda())
     ds, is_ = small.search(synth.gaussian_features(3, 64, seed=1).cuda(), k=100)
     assert bool((is_[:, 40:] == -1).all()) and sorted(is_[0, :40].tolist()) == list(range(40))
+
+
+def test_empty_query_batch_and_single_row_gallery():
+    """Degenerate shapes the reference's numpy / torch calls accept: no queries -> empty lists; one gallery row."""
+    index = GalleryIndex(synth.gaussian_features(1, 64, seed=0).cuda(), c=1.0)
+    d, i = index.search(torch.empty(0, 64, device="cuda"), k=5)
+    assert tuple(d.shape) == (0, 5) and tuple(i.shape) == (0, 5) and i.dtype == torch.int64
+    d, i = index.search(synth.gaussian_features(3, 64, seed=1).cuda(), k=5)
+    assert i[:, 0].tolist() == [0, 0, 0] and bool((i[:, 1:] == -1).all()) and bool(torch.isinf(d[:, 1:]).all())
