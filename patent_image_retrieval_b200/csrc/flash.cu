@@ -213,6 +213,44 @@ __device__ __forceinline__ float chunk_logits(float (&v)[32], const float4* __re
   return lmin;
 }
 
+// forward, software-pipelined by one chunk: the logits of THIS chunk (FMA-heavy, 2 MUFU per entry) together with the
+// exponential sum of the PREVIOUS chunk (pv[], 1 MUFU + 2 FP32 per entry) in one branch-free block.  On their own the 32
+// ex2 of a chunk's sum issue back to back -- the XU pipe (8 cycles per warp instruction) is the only unit working and
+// the other warp of the scheduler, in the same phase, wants it too -- while the logits' FMA stages leave it idle: ncu
+// put 34 % of all warp samples on MUFU instructions at an XU utilisation of 56 %.  Interleaved, the FMA work of one
+// chunk hides behind the XU time of the other.  km = kappa * (running min), 0 while nothing has been seen.
+__device__ __forceinline__ float chunk_logits_sum(float (&v)[32], const float4* __restrict__ ca, float rho,
+                                                  const float (&pv)[32], float km, float kappa, float& run_s) {
+  float lmin = INFINITY;
+#pragma unroll
+  for (int h = 0; h < 32 / F_SUB; ++h) {
+    float z[F_SUB], q[F_SUB], e[F_SUB];
+#pragma unroll
+    for (int j4 = 0; j4 < F_SUB / 4; ++j4) {
+      const float4 a1 = ca[(F_SUB / 4) * h + j4];
+      z[4 * j4 + 0] = v[F_SUB * h + 4 * j4 + 0] * (a1.x * rho);          // z - 1
+      z[4 * j4 + 1] = v[F_SUB * h + 4 * j4 + 1] * (a1.y * rho);
+      z[4 * j4 + 2] = v[F_SUB * h + 4 * j4 + 2] * (a1.z * rho);
+      z[4 * j4 + 3] = v[F_SUB * h + 4 * j4 + 3] * (a1.w * rho);
+    }
+#pragma unroll
+    for (int j = 0; j < F_SUB; ++j) e[j] = fmaf(-kappa, pv[F_SUB * h + j], km);               // previous chunk: exponents
+#pragma unroll
+    for (int j = 0; j < F_SUB; ++j) q[j] = fmaxf(fmaf(z[j], z[j], z[j] + z[j]), 1e-30f);      // z^2 - 1 without cancellation
+#pragma unroll
+    for (int j = 0; j < F_SUB; ++j) { q[j] *= rsqrt_approx(q[j]); e[j] = ex2_approx(e[j]); }  // sqrt(z^2 - 1) | 2^e
+#pragma unroll
+    for (int j = 0; j < F_SUB; ++j) z[j] = (1.0f + z[j]) + q[j];
+#pragma unroll
+    for (int j = 0; j < F_SUB; ++j) z[j] = lg2_approx(z[j]);
+#pragma unroll
+    for (int j = 0; j < F_SUB; j += 2) run_s += e[j] + e[j + 1];
+#pragma unroll
+    for (int j = 0; j < F_SUB; ++j) { v[F_SUB * h + j] = z[j]; lmin = fminf(lmin, z[j]); }
+  }
+  return lmin;
+}
+
 // backward: the weights w_ij of the chunk, rounded to two bf16 planes (packed pairs hp / mp), and the row sum of the
 // ROUNDED weights times (1 + c s / alpha): the two terms of dX = x rowsum - W Y then carry the same perturbation of w
 // and their (large) common part still cancels.  gx / gy / gd already contain gs * 2 / sqrt(c).  Invalid columns have
@@ -428,6 +466,9 @@ flash_tile_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
     const float gs = BWD ? (p.grad_scale != nullptr ? *p.grad_scale : 1.0f) * p.coef * 2.0f * rsqrtf(p.c) : 0.f;
     uint32_t sfull_par[2] = {0, 0}, wfree_par = 0, accfull_par = 0;
     float run_m = INFINITY, run_s = 0.f;                  // FWD: running MIN of L = lg2(1+u) (max logit = -kappa min L), sum
+    float pv[32];                                         // FWD: the previous chunk's L values, summed one chunk later
+#pragma unroll
+    for (int j = 0; j < 32; ++j) pv[j] = INFINITY;        // +inf contributes 2^-inf = 0
     float rowsum = 0.f;                                   // BWD: sum_j w_ij (1 + c s_ij / alpha_i)
     // per-column constants of a tile, double-buffered by tile parity and staged ONE TILE AHEAD (their global loads hide
     // behind the current tile's arithmetic):  [0] |y|^2   [1] 2c / beta (0 for columns >= m)   [2] BWD: column lse, log2
@@ -522,7 +563,8 @@ flash_tile_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
           }
         }
         if (!BWD) {
-          float lmin = chunk_logits(v, ca, rho);
+          // this chunk's logits + the previous chunk's exponential sum (against the running min that already covers it)
+          float lmin = chunk_logits_sum(v, ca, rho, pv, run_m < INFINITY ? p.kappa * run_m : 0.f, p.kappa, run_s);
           if (cb + 32 > n_cols) {                         // warp-uniform, last column tile only: drop the padding columns
             lmin = INFINITY;
 #pragma unroll
@@ -531,12 +573,12 @@ flash_tile_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
               lmin = fminf(lmin, v[j]);
             }
           }
-          if (lmin < run_m) { run_s *= ex2_approx(p.kappa * (lmin - run_m)); run_m = lmin; }
-          if (run_m < INFINITY) {
-            const float km = p.kappa * run_m;
+          // branch-free update of the running min: the sum is rescaled to the new reference (x 1 when it does not move)
+          const float nm = fminf(run_m, lmin);
+          run_s *= run_m < INFINITY ? ex2_approx(p.kappa * (nm - run_m)) : 0.f;
+          run_m = nm;
 #pragma unroll
-            for (int j = 0; j < 32; ++j) run_s += ex2_approx(fmaf(-p.kappa, v[j], km));
-          }
+          for (int j = 0; j < 32; ++j) pv[j] = v[j];
         } else {
           const float crho = p.c * rho;
           const float gx = row_ok ? -gs * p.wx : 0.f, gy = row_ok ? -gs * p.wy : 0.f, gd = gs * (p.wx + p.wy);
@@ -572,6 +614,13 @@ flash_tile_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
         const int slot = (int)blockIdx.x - flash_cta_of_tile((int64_t)rt * p.n_ct, T, P);
         HYPRET_CHECK(slot >= 0 && slot < p.n_slots && rt >= 0 && rt < p.n_rt);
         if (!BWD) {
+          if (run_m < INFINITY) {                         // the last chunk of the segment is still pending
+            const float km = p.kappa * run_m;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) run_s += ex2_approx(fmaf(-p.kappa, pv[j], km));
+          }
+#pragma unroll
+          for (int j = 0; j < 32; ++j) pv[j] = INFINITY;
           float* o = p.part + ((((int64_t)rt * p.n_slots + slot) * F_NWG + wg) * 2) * FT_M;
           o[row] = -p.kappa * run_m;                      // max logit (log2 units); -inf when no column was seen
           o[FT_M + row] = run_s;
