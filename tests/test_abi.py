@@ -177,3 +177,51 @@ def test_default_list_sizes_and_certificate_candidates():
         assert k <= kp <= 32 and kp <= kb <= 32
     with pytest.raises(ValueError):
         default_kprime(129)
+
+
+def test_argument_validation_happens_before_any_device_work():
+    """Every entry point validates shapes / enums / pointers first and returns HYPRET_EINVAL (-1) or HYPRET_EUNSUPPORTED
+    (-2) without touching a device, so the error behaviour of the C ABI is testable on a CPU-only box; an empty problem
+    is HYPRET_OK.  (Valid arguments would go on to check_device() and fail with a CUDA error here: not called.)"""
+    from patent_image_retrieval_b200 import _lib
+    lib = _lib.load()
+    P = 0x1000          # a non-NULL, 16-byte aligned dummy: validation never dereferences it
+    EINVAL, EUNSUP, OK = -1, -2, 0
+    # exact top-k: k > 32, bad metric, missing pointers; Q == 0 is an empty problem
+    assert lib.hypret_exact_topk(P, P, P, 4, 100, 64, 1.0, 1, 33, 0, P, P, P, None, P, P, None) == EINVAL
+    assert lib.hypret_exact_topk(P, P, P, 4, 100, 64, 1.0, 7, 10, 0, P, P, P, None, P, P, None) == EINVAL
+    assert lib.hypret_exact_topk(P, P, P, 4, 100, 62, 1.0, 1, 10, 0, P, P, P, None, P, P, None) == EINVAL
+    assert lib.hypret_exact_topk(P, P, None, 4, 100, 64, 1.0, 1, 10, 0, P, P, P, None, P, P, None) == EINVAL
+    assert lib.hypret_exact_topk(P, P, P, 0, 100, 64, 1.0, 1, 10, 0, P, P, P, None, P, P, None) == OK
+    assert lib.hypret_exact_topk(P, P, P, 4, 2 ** 31, 64, 1.0, 1, 10, 0, P, P, P, None, P, P, None) == EUNSUP
+    # scoring with a shared bound: kbound < kprime, kbound > 32, 24-slot lists, no threshold workspace
+    args = lambda kp, kb, ws: (P, 10, P, 10, 64, kp, kb, 1, 0, 0, P, P, ws, None, None, None)
+    assert lib.hypret_score_topk_bound(*args(16, 8, P)) == EINVAL
+    assert lib.hypret_score_topk_bound(*args(16, 40, P)) == EINVAL
+    assert lib.hypret_score_topk_bound(*args(24, 32, P)) == EINVAL
+    assert lib.hypret_score_topk_bound(*args(16, 24, None)) == EINVAL
+    # certified rerank: k' > 32 is the wide path (unsupported with a certificate); ksel outside (k', 32]
+    cert = lambda kp, ksel, k: (P, P, 4, 100, 64, 1.0, 1, P, P, None, 2, kp, ksel, k, 0, P, P, None, P, P, P, P, P, None,
+                                None, None)
+    assert lib.hypret_rerank_cert(*cert(64, 0, 10)) == EUNSUP
+    assert lib.hypret_rerank_cert(*cert(16, 12, 10)) == EINVAL
+    assert lib.hypret_rerank_cert(*cert(16, 40, 10)) == EINVAL
+    # fused MobiusLinear layer: n_out % 16, n_out > 256, d_in % 4, curvature, n_project
+    mg = lambda d_in, n_out, c, npj: (P, P, 8, d_in, n_out, None, None, c, 0, npj, None, P, None, None, None)
+    assert lib.hypret_mobius_gemm(*mg(64, 24, 1.0, 1)) == EINVAL
+    assert lib.hypret_mobius_gemm(*mg(64, 272, 1.0, 1)) == EINVAL
+    assert lib.hypret_mobius_gemm(*mg(62, 32, 1.0, 1)) == EINVAL
+    assert lib.hypret_mobius_gemm(*mg(64, 32, 0.0, 1)) == EINVAL
+    assert lib.hypret_mobius_gemm(*mg(64, 32, 1.0, 3)) == EINVAL
+    assert lib.hypret_mobius_gemm(P, P, 0, 64, 32, None, None, 1.0, 0, 1, None, P, None, None, None) == OK
+    # its backward: gbias without bias, gxn without xsq
+    assert lib.hypret_mobius_epilogue_bwd(P, 8, 32, None, None, 1.0, 0, 1, P, P, P, None, None) == EINVAL
+    assert lib.hypret_mobius_epilogue_bwd(P, 8, 32, None, P, 1.0, 0, 1, P, P, None, P, None) == EINVAL
+    assert lib.hypret_sgemm_strided(P, 1, 1, P, 1, 1, 4, 4, 4, P, None, P, None) == EINVAL      # row_scale without addend
+    assert lib.hypret_sgemm_strided(P, 1, 1, P, 1, 1, 0, 4, 4, None, None, P, None) == OK
+    # flash train_hyp: D > 128 / D % 16 belong to the generic path
+    fl = lambda d: (P, P, P, P, P, P, 8, 8, d, 1.0, 10.0, P, P, None)
+    assert lib.hypret_flash_lse(*fl(256)) == EINVAL
+    assert lib.hypret_flash_lse(*fl(72)) == EINVAL
+    assert lib.hypret_flag_compact(P, -1, P, P, P, None) == EINVAL
+    assert lib.hypret_cert_merged(P, 4, 64, 1.0, 9, P, P, 10, P, P, P, P, None, None) == EINVAL
