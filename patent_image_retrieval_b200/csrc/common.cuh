@@ -154,7 +154,7 @@ __device__ __forceinline__ void tcgen05_fence_after() {
 }
 // D[tmem] (+)= A[smem] * B[smem]^T, 16-bit inputs (kind::f16: bf16 or fp16 as the instruction descriptor says), fp32
 // accumulate; one thread issues.
-__device__ __forceinline__ void umma_bf16_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+__device__ __forceinline__ void umma_f16_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
                                              uint32_t accumulate) {
   asm volatile(
       "{\n\t"
@@ -244,7 +244,7 @@ __device__ __forceinline__ void tma_load_2d_pair(void* smem_dst, const CUtensorM
         "r"(c1), "l"(policy)
       : "memory");
 }
-__device__ __forceinline__ void umma_bf16_ss_pair(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+__device__ __forceinline__ void umma_f16_ss_pair(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
                                                   uint32_t accumulate) {
   asm volatile(
       "{\n\t"

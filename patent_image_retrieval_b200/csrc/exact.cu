@@ -1,8 +1,8 @@
 // Exact top-k by full scan: the guarantee behind the tensor-core filter.
 //
-// hypret_rerank_cert certifies, per query, that no gallery row outside the bf16-filtered candidate set can precede the
+// hypret_rerank_cert certifies, per query, that no gallery row outside the fp16-filtered candidate set can precede the
 // k-th result (margin > rounding-error bound E, csrc/rerank.cu).  Queries it cannot certify -- near-duplicate
-// galleries, where more than k' - k rows sit inside the bf16 error band of the k-th best -- are listed on the device,
+// galleries, where more than k' - k rows sit inside the fp16 rounding band of the k-th best -- are listed on the device,
 // and this kernel recomputes their top-k from ALL gallery rows with the arithmetic of the rerank kernel (explicit
 // differences, fp64 accumulation in the same order, arccosh closed form == pmath.dist,
 // /root/reference/src/train.py:3259; cosine of notebooks/retrieval.ipynb:368), i.e. exactly what the reference's

@@ -413,7 +413,7 @@ flash_tile_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
           const uint32_t a_lo = ring_lo + stage * (F_STAGE >> 4), b_lo = a_lo + (FA_BLK >> 4);
 #pragma unroll
           for (int kk = 0; kk < HYPRET_KBLK / 16; ++kk)
-            umma_bf16_ss(d_tmem, DESC_SW128 | (a_lo + 2 * kk), DESC_SW128 | (b_lo + 2 * kk), idesc_g,
+            umma_f16_ss(d_tmem, DESC_SW128 | (a_lo + 2 * kk), DESC_SW128 | (b_lo + 2 * kk), idesc_g,
                          (k | kk) != 0 ? 1u : 0u);
           umma_commit(&bars->empty[stage]);
           if (k == p.kb - 1) umma_commit(&bars->s_full[a]);
@@ -443,7 +443,7 @@ flash_tile_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
             const uint32_t yb = yt_lo + (prod == 1 ? ypl : 0);
             for (int kk = 0; kk < FT_N / 16; ++kk) {
               const uint32_t blk = kk >> 2, in = (kk & 3) * 2;
-              umma_bf16_ss(tmem_acc, DESC_SW128 | (wa + blk * (FA_BLK >> 4) + in), DESC_SW128 | (yb + blk * ykb + in),
+              umma_f16_ss(tmem_acc, DESC_SW128 | (wa + blk * (FA_BLK >> 4) + in), DESC_SW128 | (yb + blk * ykb + in),
                            idesc_p, first ? 0u : 1u);
               first = false;
             }

@@ -119,7 +119,7 @@ mobius_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
           const uint32_t a_lo = ring_lo + stage * (stage_bytes >> 4), b_lo = a_lo + (HG_A_BLK >> 4);
 #pragma unroll
           for (int kk = 0; kk < HYPRET_KBLK / 16; ++kk)
-            umma_bf16_ss(d_tmem, DESC_SW128 | (a_lo + 2 * kk), DESC_SW128 | (b_lo + 2 * kk), idesc,
+            umma_f16_ss(d_tmem, DESC_SW128 | (a_lo + 2 * kk), DESC_SW128 | (b_lo + 2 * kk), idesc,
                          (k | kk) != 0 ? 1u : 0u);
           umma_commit(&bars->empty[stage]);
           if (k == p.kb - 1) umma_commit(&bars->acc_full[acc]);

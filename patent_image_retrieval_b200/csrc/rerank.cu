@@ -370,7 +370,7 @@ cand_select_kernel(const float* __restrict__ cand_score, const int32_t* __restri
 // k-th result): a non-candidate is either cut by the 256-survivor truncation or hidden behind a FULL
 // list's worst entry.
 constexpr int RW_THREADS = 128;
-constexpr int RW_SURV = 256;   // survivors rescored exactly: 2x the largest k, the bf16 filter error is comparable
+constexpr int RW_SURV = 256;   // survivors rescored exactly: 2x the largest k, the fp16 filter error is comparable
                                // with the score gap between rank k and rank 1.3k on concentrated data
 
 __device__ __forceinline__ bool pair_less(float a, int ia, float b, int ib) {

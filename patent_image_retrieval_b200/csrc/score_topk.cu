@@ -10,7 +10,7 @@
 // registers.
 //
 // Structure (one persistent CTA per SM, 192 threads, warp-specialised):
-//   warp 0   TMA producer   gallery K-blocks (256 rows x 64 bf16, 128B swizzle) into a
+//   warp 0   TMA producer   gallery K-blocks (256 rows x 64 fp16, 128B swizzle) into a
 //                           shared-memory ring; the 128-row query tile is loaded ONCE per strip
 //                           and stays resident in shared memory when D <= 512 (RESIDENT),
 //                           otherwise it streams through the ring next to the gallery block
@@ -695,15 +695,15 @@ score_topk_kernel(const __grid_constant__ CUtensorMap map_q_main, const __grid_c
               const uint32_t a_lo = RESIDENT ? ares_lo + ks * (A_BLK_BYTES >> 4) : st_lo;
 #pragma unroll
               for (int k = 0; k < HYPRET_KBLK / 16; ++k) {
-                if (PAIR) umma_bf16_ss_pair(d_tmem, DESC_SW128 | (a_lo + 2 * k), DESC_SW128 | (b_lo + 2 * k), idesc,
+                if (PAIR) umma_f16_ss_pair(d_tmem, DESC_SW128 | (a_lo + 2 * k), DESC_SW128 | (b_lo + 2 * k), idesc,
                                             (ks | k) != 0 ? 1u : 0u);
-                else umma_bf16_ss(d_tmem, DESC_SW128 | (a_lo + 2 * k), DESC_SW128 | (b_lo + 2 * k), idesc,
+                else umma_f16_ss(d_tmem, DESC_SW128 | (a_lo + 2 * k), DESC_SW128 | (b_lo + 2 * k), idesc,
                                   (ks | k) != 0 ? 1u : 0u);
               }
             } else {
               const uint32_t a_lo = RESIDENT ? ares_lo + KB * (A_BLK_BYTES >> 4) : st_lo;
-              if (PAIR) umma_bf16_ss_pair(d_tmem, DESC_SW32 | a_lo, DESC_SW32 | b_lo, idesc, 1u);
-              else umma_bf16_ss(d_tmem, DESC_SW32 | a_lo, DESC_SW32 | b_lo, idesc, 1u);
+              if (PAIR) umma_f16_ss_pair(d_tmem, DESC_SW32 | a_lo, DESC_SW32 | b_lo, idesc, 1u);
+              else umma_f16_ss(d_tmem, DESC_SW32 | a_lo, DESC_SW32 | b_lo, idesc, 1u);
             }
             // ring stage reusable once these MMAs retire; last K step: accumulator complete -> epilogue
             // (PAIR: the arrivals are multicast to the same barriers of both CTAs)
