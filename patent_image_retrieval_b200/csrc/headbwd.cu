@@ -48,18 +48,24 @@ mobius_epilogue_bwd_kernel(const float* __restrict__ mx, int64_t n, int d, const
                            float* __restrict__ gxn) {
   const int lane = threadIdx.x & 31;
   const int nvec = d >> 2;
-  const int64_t row = (int64_t)blockIdx.x * HB_WARPS + (threadIdx.x >> 5);
-  if (row >= n) return;
   const float sc = sqrtf(c), k = -c;
   const float maxnorm = (1.0f - 4e-3f) / sc;
-  float4 m[NV], b[NV], g[NV];
+  float4 b[NV], gb_acc[NV];                    // bias row; this warp's sum of dL/dbias over the rows it serves
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int j = i * 32 + lane;
+    b[i] = (j < nvec && bias != nullptr) ? __ldg(reinterpret_cast<const float4*>(bias) + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+    gb_acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  // rows are taken grid-stride, so that the bias gradient costs one atomic per column and CTA, not per column and row
+  for (int64_t row = (int64_t)blockIdx.x * HB_WARPS + (threadIdx.x >> 5); row < n; row += (int64_t)gridDim.x * HB_WARPS) {
+  float4 m[NV], g[NV];
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
     const int j = i * 32 + lane;
     const bool in = j < nvec;
     m[i] = in ? __ldg(reinterpret_cast<const float4*>(mx + row * d) + j) : make_float4(0.f, 0.f, 0.f, 0.f);
     g[i] = in ? __ldg(reinterpret_cast<const float4*>(gy + row * d) + j) : make_float4(0.f, 0.f, 0.f, 0.f);
-    b[i] = (in && bias != nullptr) ? __ldg(reinterpret_cast<const float4*>(bias) + j) : make_float4(0.f, 0.f, 0.f, 0.f);
   }
   // ------------------------------------------------------------------ forward scalars (as csrc/headgemm.cu)
   const float mm = hb_dot<NV>(m, m), mb = hb_dot<NV>(m, b), b2 = hb_dot<NV>(b, b);
@@ -172,15 +178,9 @@ mobius_epilogue_bwd_kernel(const float* __restrict__ mx, int64_t n, int d, const
       gb[i].z = cb * inv_den * g[i].z + g_xy * u[i].z + 2.f * g_b2 * b[i].z;
       gb[i].w = cb * inv_den * g[i].w + g_xy * u[i].w + 2.f * g_b2 * b[i].w;
     }
-    if (gbias != nullptr) {
 #pragma unroll
-      for (int i = 0; i < NV; ++i) {
-        const int j = i * 32 + lane;
-        if (j < nvec) {
-          atomicAdd(gbias + 4 * j + 0, gb[i].x); atomicAdd(gbias + 4 * j + 1, gb[i].y);
-          atomicAdd(gbias + 4 * j + 2, gb[i].z); atomicAdd(gbias + 4 * j + 3, gb[i].w);
-        }
-      }
+    for (int i = 0; i < NV; ++i) {
+      gb_acc[i].x += gb[i].x; gb_acc[i].y += gb[i].y; gb_acc[i].z += gb[i].z; gb_acc[i].w += gb[i].w;
     }
   } else {
     hb_axpby<NV>(gu, 1.f, g, 0.f, g);
@@ -200,6 +200,20 @@ mobius_epilogue_bwd_kernel(const float* __restrict__ mx, int64_t n, int d, const
   }
   if (gxn != nullptr && lane == 0)
     gxn[row] = zero_row ? 0.f : dphi_dxn * gum / fmaxf(sqrtf(xsq_in[row]), 1e-15f);   // so that dL/dx_in += gxn x_in
+  }   // rows
+  if (gbias != nullptr && bias != nullptr) {
+    __shared__ float4 red[HB_WARPS][NV * 32];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) red[threadIdx.x >> 5][i * 32 + lane] = gb_acc[i];
+    __syncthreads();
+    for (int j = threadIdx.x; j < nvec; j += HB_WARPS * 32) {
+      float4 t = red[0][j];
+#pragma unroll
+      for (int w = 1; w < HB_WARPS; ++w) { t.x += red[w][j].x; t.y += red[w][j].y; t.z += red[w][j].z; t.w += red[w][j].w; }
+      atomicAdd(gbias + 4 * j + 0, t.x); atomicAdd(gbias + 4 * j + 1, t.y);
+      atomicAdd(gbias + 4 * j + 2, t.z); atomicAdd(gbias + 4 * j + 3, t.w);
+    }
+  }
 }
 
 // C[m,n] = sum_k A[m*sam + k*sak] * B[k*sbk + n*sbn] (+ row_scale[m] * addend[m,n]); 64 x 64 tile, 16-deep steps, 4 x 4 per thread
@@ -210,12 +224,16 @@ sgemm_strided_kernel(const float* __restrict__ A, int64_t sam, int64_t sak, cons
   __shared__ float As[16][64 + 4], Bs[16][64 + 4];
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
   const int m0 = blockIdx.y * 64, n0 = blockIdx.x * 64;
+  // split-K (gridDim.z > 1): this CTA takes K range [k_lo, k_hi) and adds its partial tile into C (zeroed by the
+  // launcher) with atomics -- dW = gmx^T x has K = batch rows and only (N_out/64) x (D_in/64) output tiles
+  const int k_per = (((K + (int)gridDim.z - 1) / (int)gridDim.z) + 15) / 16 * 16;
+  const int k_lo = (int)blockIdx.z * k_per, k_hi = k_lo + k_per < K ? k_lo + k_per : K;
   float acc[4][4] = {};
-  for (int k0 = 0; k0 < K; k0 += 16) {
+  for (int k0 = k_lo; k0 < k_hi; k0 += 16) {
     for (int t = threadIdx.x; t < 16 * 64; t += 256) {
       const int kk = t >> 6, mmi = t & 63;
-      As[kk][mmi] = (m0 + mmi < M && k0 + kk < K) ? A[(int64_t)(m0 + mmi) * sam + (int64_t)(k0 + kk) * sak] : 0.f;
-      Bs[kk][mmi] = (n0 + mmi < N && k0 + kk < K) ? B[(int64_t)(k0 + kk) * sbk + (int64_t)(n0 + mmi) * sbn] : 0.f;
+      As[kk][mmi] = (m0 + mmi < M && k0 + kk < k_hi) ? A[(int64_t)(m0 + mmi) * sam + (int64_t)(k0 + kk) * sak] : 0.f;
+      Bs[kk][mmi] = (n0 + mmi < N && k0 + kk < k_hi) ? B[(int64_t)(k0 + kk) * sbk + (int64_t)(n0 + mmi) * sbn] : 0.f;
     }
     __syncthreads();
 #pragma unroll
@@ -236,7 +254,9 @@ sgemm_strided_kernel(const float* __restrict__ A, int64_t sam, int64_t sak, cons
     for (int j = 0; j < 4; ++j)
       if (m0 + ty * 4 + i < M && n0 + tx * 4 + j < N) {
         const int64_t at = (int64_t)(m0 + ty * 4 + i) * N + n0 + tx * 4 + j;
-        C[at] = acc[i][j] + (row_scale != nullptr ? row_scale[m0 + ty * 4 + i] * addend[at] : 0.f);
+        const float v = acc[i][j] + ((row_scale != nullptr && blockIdx.z == 0) ? row_scale[m0 + ty * 4 + i] * addend[at] : 0.f);
+        if (gridDim.z > 1) atomicAdd(C + at, v);
+        else C[at] = v;
       }
 }
 
@@ -246,7 +266,11 @@ int hypret_launch_mobius_epilogue_bwd(const float* mx, int64_t n, int d, const f
                                       int post_tanh, int n_project, const float* gy, float* gmx, float* gbias,
                                       float* gxn, cudaStream_t stream) {
   if (n == 0) return HYPRET_OK;
-  const unsigned grid = (unsigned)((n + HB_WARPS - 1) / HB_WARPS);
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int64_t want = (n + HB_WARPS - 1) / HB_WARPS;
+  const unsigned grid = (unsigned)(want < (int64_t)sms * 8 ? want : (int64_t)sms * 8);      // grid-stride beyond
   const int need = (d + 127) / 128;
   if (need <= 1) mobius_epilogue_bwd_kernel<1><<<grid, HB_WARPS * 32, 0, stream>>>(mx, n, d, xsq, bias, c, post_tanh, n_project, gy, gmx, gbias, gxn);
   else if (need <= 2) mobius_epilogue_bwd_kernel<2><<<grid, HB_WARPS * 32, 0, stream>>>(mx, n, d, xsq, bias, c, post_tanh, n_project, gy, gmx, gbias, gxn);
@@ -259,7 +283,22 @@ int hypret_launch_sgemm_strided(const float* A, int64_t sam, int64_t sak, const 
                                 int M, int N, int K, const float* row_scale, const float* addend, float* C,
                                 cudaStream_t stream) {
   if (M == 0 || N == 0) return HYPRET_OK;
-  const dim3 grid((unsigned)((N + 63) / 64), (unsigned)((M + 63) / 64));
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int tiles = ((N + 63) / 64) * ((M + 63) / 64);
+  int splits = 1;                                             // split K when the output tiles cannot fill the GPU
+  if (tiles < 2 * sms && K >= 1024) {
+    splits = (2 * sms + tiles - 1) / tiles;
+    if (splits > K / 256) splits = K / 256;
+    if (splits > 65535) splits = 65535;
+    if (splits < 1) splits = 1;
+  }
+  if (splits > 1) {
+    cudaError_t e = cudaMemsetAsync(C, 0, (size_t)M * N * sizeof(float), stream);
+    if (e != cudaSuccess) return (int)e;
+  }
+  const dim3 grid((unsigned)((N + 63) / 64), (unsigned)((M + 63) / 64), (unsigned)splits);
   sgemm_strided_kernel<<<grid, 256, 0, stream>>>(A, sam, sak, B, sbk, sbn, M, N, K, row_scale, addend, C);
   return (int)cudaGetLastError();
 }

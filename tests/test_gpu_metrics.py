@@ -409,7 +409,8 @@ def test_mobius_gemm_head_matches_oracle(d_in, hid, d_out, c, b):
 
 
 @pytest.mark.parametrize("d_in,hid,d_out,c,b,wscale", [(512, 256, 128, 1.0, 128, 1.0), (768, 128, 64, 0.5, 77, 1.0),
-                                                       (64, 32, 16, 2.0, 200, 4.0)])
+                                                       (64, 32, 16, 2.0, 200, 4.0),
+                                                       (256, 128, 64, 1.0, 6001, 1.0)])   # grid-stride rows, split-K dW
 def test_head_training_step_matches_autograd(d_in, hid, d_out, c, b, wscale, monkeypatch):
     """train_hyp's head on the kernel path (ops.MobiusLinearFn: fused GEMM kernel forward, closed-form epilogue kernel +
     dense products backward) against autograd through the op-by-op path of the same module on the CPU
