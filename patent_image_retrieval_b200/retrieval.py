@@ -61,6 +61,9 @@ def _span(events, name):
 
 
 WIDE_MIN_LISTS = 4     # wide top-k: candidate lists per query (4 x 64 = 256 candidates for k <= 128)
+WIDE_SWITCH_RATE = 0.02        # adaptive list width: share of uncertified queries above which the wide lists are cheaper
+WIDE_SWITCH_MIN_ROWS = 1024    # ... only for galleries where a full scan per query costs more than the wide pass
+WIDE_PROBE_EVERY = 32          # ... and how often the narrow path is tried again
 
 
 def default_kprime(k: int) -> int:
@@ -122,7 +125,15 @@ class GalleryIndex:
         self._cand = {}
         self._cert = None
         self.certificate = None     # CertBuffers of the last exact search (device-side; see ops.rerank_cert)
-        self.uncertified_wide = None   # [Q] int32 flags of the last exact wide search (26 < k <= 128)
+        self.uncertified_wide = None   # [Q] int32 flags of the last exact wide search (26 < k <= 128, or wide mode)
+        # adaptive list width (search(kprime=None, k <= 26)): the share of queries the narrow certificate could not
+        # prove, mirrored to pinned host memory by an asynchronous copy and read WITHOUT synchronising
+        self.adaptive = True
+        self.fallback_rate = 0.0       # of the last narrow search whose count has arrived
+        self.last_mode = "narrow"
+        self._h_count = None
+        self._pending = None           # (event, n_queries) of the copy in flight
+        self._since_probe = 0
 
     def _query_mode(self):
         if self.metric == "cosine":
@@ -157,6 +168,17 @@ class GalleryIndex:
             res = ops.exact_topk_any(q, self.rows32, self.rows_sq64, self.c, self.metric, min(k, self.n),
                                      idx_offset=self.idx_offset)
             return res + (torch.full((q.shape[0],), float("inf"), device=self.device),) if return_margin else res
+        auto = (kprime is None and exact and self.adaptive and k <= 26 and self.n > 4 * WIDE_SWITCH_MIN_ROWS
+                and not torch.cuda.is_current_stream_capturing())
+        if auto and self._wide_mode():
+            if self._since_probe == 0:     # now and then: the narrow filter + certificate alone (no scans), for the rate
+                pq32, pcs, pci, pcnt, perr = self.score_candidates(queries, k=k, want_err=True,
+                                                                   kbound=default_kbound(k, default_kprime(k)))
+                self.rerank_candidates(pq32, pcs, pci, k, list_count=pcnt, q_err=perr,
+                                       ksel=default_kbound(k, default_kprime(k)), fallback=False)
+                self._mirror_fallback_count(pq32.shape[0])
+            kprime = 64                # tight classes: 64-slot lists + 256 exactly rescored survivors certify them
+        self.last_mode = "wide" if (kprime is not None and int(kprime) > 32) else "narrow"
         kp = min(default_kprime(k) if kprime is None else int(kprime), ops.MAX_KPRIME)
         if kbound is None:
             kbound = default_kbound(k, kp) if (exact and k <= kp) else kp
@@ -181,8 +203,45 @@ class GalleryIndex:
             self.uncertified_wide = flags
             score, idx = torch.where(redo, xs, score), torch.where(redo, xi, idx)
             return (score, idx, margin) if return_margin else (score, idx)
-        return self.rerank_candidates(q32, cs, ci, k, return_margin=return_margin, kernel_events=kernel_events,
-                                      list_count=cnt, q_err=q_err if exact else None, ksel=kbound)
+        out = self.rerank_candidates(q32, cs, ci, k, return_margin=return_margin, kernel_events=kernel_events,
+                                     list_count=cnt, q_err=q_err if exact else None, ksel=kbound)
+        if auto and self.certificate is not None:
+            self._mirror_fallback_count(q32.shape[0])
+        return out
+
+    # ---- adaptive list width -------------------------------------------------------------------------------------
+    # The certificate needs the k-th .. k_b-th candidates to be further apart than the rounding bound E.  On galleries of
+    # tight classes (the reference's figures of one patent family) a class of more than k_b - k near-equidistant rows
+    # defeats it, and every such query costs a full exact scan: 10k queries x 300k rows, 30 rows per class at 10 % noise:
+    # 21 % uncertified, 112 ms per search instead of 2.3.  The wide path (64-slot lists, 256 survivors rescored exactly,
+    # the same bound) proves all of them in 9.6 ms (tools/bench_clustered.py).  So the index watches the share of
+    # uncertified queries -- an asynchronous 4-byte copy per search, read one or more searches later, never waited
+    # for -- and serves a gallery that keeps defeating the narrow certificate with the wide lists, probing the narrow
+    # certificate (filter + proof only, no scans: +1 narrow pass) every WIDE_PROBE_EVERY searches.  The results are exact
+    # either way; only the cost moves.
+    def _mirror_fallback_count(self, n_queries: int) -> None:
+        if self._h_count is None:
+            self._h_count = torch.zeros(1, dtype=torch.int32, pin_memory=True)
+        if self._pending is not None and not self._pending[0].query():
+            return                                 # the previous copy is still in flight: keep its buffer untouched
+        self._consume_pending()
+        self._h_count.copy_(self.certificate.count, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        self._pending = (ev, int(n_queries))
+
+    def _consume_pending(self) -> None:
+        if self._pending is not None and self._pending[0].query():
+            self.fallback_rate = float(self._h_count[0]) / max(self._pending[1], 1)
+            self._pending = None
+
+    def _wide_mode(self) -> bool:
+        self._consume_pending()
+        if self.fallback_rate <= WIDE_SWITCH_RATE:
+            self._since_probe = 0
+            return False
+        self._since_probe = (self._since_probe + 1) % WIDE_PROBE_EVERY     # 0: this call also probes the narrow path
+        return True
 
     def score_candidates(self, queries: torch.Tensor, k: int = 10, kprime: Optional[int] = None, max_ctas: int = 0,
                          kernel_events: Optional[list] = None, want_err: bool = False, kbound: Optional[int] = None):
@@ -236,7 +295,7 @@ class GalleryIndex:
     def rerank_candidates(self, q32, cand_score, cand_idx, k: int, return_margin: bool = False,
                           prune_thr: Optional[torch.Tensor] = None, kernel_events: Optional[list] = None,
                           list_count: Optional[torch.Tensor] = None, q_err: Optional[torch.Tensor] = None,
-                          ksel: int = 0):
+                          ksel: int = 0, fallback: bool = True):
         """Second half of ``search``: candidate merge + exact rerank against this shard's fp32 rows.  With ``q_err``
         (and k <= k' <= 32, no pruning): the certified rerank + exact-scan fallback of ``ops.rerank_cert``."""
         kprime = cand_score.shape[2]
@@ -249,7 +308,7 @@ class GalleryIndex:
                 return ops.rerank_cert(q32, self.rows32, cand_score, cand_idx, self.c, self.metric, k, q_err,
                                        self.stats, self.rows_sq64, self._cert, idx_offset=self.idx_offset,
                                        want_margin=return_margin, list_count=list_count,
-                                       ksel=ksel if ksel > kprime else 0)
+                                       ksel=ksel if ksel > kprime else 0, fallback=fallback)
         with _span(kernel_events, "rerank"):
             out = ops.rerank(q32, self.rows32, cand_score, cand_idx, self.c, self.metric, k,
                              idx_offset=self.idx_offset, want_margin=return_margin, prune_thr=prune_thr,

@@ -319,3 +319,32 @@ def test_wide_topk_is_exact_too(metric):
         assert torch.equal(got_s, want_s)
         if noise < 1e-2:      # 600 rows per class inside the rounding band: more than the 256 rescored survivors
             assert int(index.uncertified_wide.sum()) > 0
+
+
+@pytest.mark.parametrize("metric", ["hyperbolic", "cosine"])
+def test_adaptive_list_width_on_tight_classes(metric):
+    """A gallery of tight classes defeats the narrow certificate (classes of ~30 near-equidistant rows against k_b = 24
+    candidates); the index notices from the mirrored count (no synchronisation of its own) and serves the next searches
+    with the wide lists, which certify them.  Same exact lists either way; easy data stays on the narrow path."""
+    Q, N, d, c, k = 256, 20000, 128, 1.0, 10
+    gal, qry = _near_duplicates(N, Q, d, 0.03, c, metric, per_class=30)
+    space = "ball" if metric == "hyperbolic" else "euclidean"
+    index = GalleryIndex(gal.cuda(), c=c, metric=metric, space=space)
+    want_s, want_i = ops.exact_topk(qry.cuda().contiguous(), index.rows32, index.rows_sq64, c, metric, k)
+    got_s, got_i = index.search(qry.cuda(), k=k)
+    assert index.last_mode == "narrow" and torch.equal(got_i, want_i) and torch.equal(got_s, want_s)
+    narrow_scans = int(index.certificate.count[0])                  # synchronises: the mirrored count has arrived
+    assert narrow_scans > 0.02 * Q
+    for _ in range(3):
+        got_s, got_i = index.search(qry.cuda(), k=k)
+        assert index.last_mode == "wide" and index.fallback_rate > 0.02
+        assert torch.equal(got_i, want_i) and torch.equal(got_s, want_s)
+        assert int(index.uncertified_wide.sum()) < narrow_scans
+    index.adaptive = False
+    got_s, got_i = index.search(qry.cuda(), k=k)
+    assert index.last_mode == "narrow" and torch.equal(got_i, want_i) and torch.equal(got_s, want_s)
+    easy = GalleryIndex(synth.gaussian_features(N, d, seed=0).cuda(), c=c, metric=metric)
+    for _ in range(3):
+        easy.search(synth.gaussian_features(Q, d, seed=1).cuda(), k=k)
+        torch.cuda.synchronize()
+        assert easy.last_mode == "narrow"
