@@ -59,7 +59,9 @@ constexpr int NUM_EPI_THREADS = 128;
 constexpr int MAX_STAGES = 8;
 constexpr int SMEM_LIMIT = 232448;                        // 227 KB opt-in maximum per CTA
 constexpr int BAR_BYTES = 256;
-constexpr int MIN_STRIP_TILES = 4;                        // do not spread tiny problems over all SMs
+constexpr int MIN_STRIP_TILES = 4;                        // do not spread tiny problems over all SMs (C1, measured with
+                                                          // the dense cold start: floor 4 / 3 / 2 -> scoring 83 / 77 / 76 us
+                                                          // but rerank 74 / 78 / 79 us for the extra lists: a wash)
 constexpr unsigned FULL = 0xffffffffu;
 
 struct Sched {
@@ -257,6 +259,13 @@ __device__ __forceinline__ uint32_t ld_cg_u32(const uint32_t* p) {
 }
 constexpr uint32_t KEY_INF = 0xff800000u;   // f2key(+inf)
 
+// smallest float above a FINITE x (the libm next-after toward +inf without its special-case branches: the
+// threshold exchange runs it twice per tile and row)
+__device__ __forceinline__ float next_up(float x) {
+  const int b = __float_as_int(x);
+  return x >= 0.0f ? __int_as_float((b & 0x7fffffff) + 1) : __int_as_float(b - 1);
+}
+
 // Lists live in shared memory as [slot][row] (row = thread of the epilogue, 0..127): when all
 // lanes of a warp touch the same slot the access is conflict-free.  Shared-state-space
 // addresses (32-bit) + explicit ld/st.shared keep the non-inlined helper free of generic loads.
@@ -446,6 +455,77 @@ __device__ __forceinline__ void reg_publish(const RegList& L, int kp, float* cs,
 #undef RL_PUB
 }
 
+// Cold strip start, dense path.  A list that starts with no bound (nothing published for its query yet) lets every
+// column through: streaming inserts cost one ~100-instruction drain pass per hit, the passes of a warp are as many as
+// its unluckiest lane has hits, and the first 52 hits of a lane spill from the 12-slot queue into local memory --
+// ~90 passes and ~11k warp-instructions for the first tile of a strip, most of the epilogue's time on short strips
+// (C1: 4-tile strips; 37.5k-row shards).  The first DENSE_COLS columns of such a strip therefore skip the filter:
+// 16 columns at a time are sorted by a 63-exchange odd-even merge network (Batcher) on (score, column) pairs and
+// merged into the sorted register list by one half-cleaner + a 4-stage bitonic merge -- branch-free, the same
+// ~520 instructions for every lane, no queue, no local memory.  After 64 columns the list's own threshold sits at
+// the 25 % quantile and the streaming path (a pass per hit) is the cheaper one again.
+constexpr int DENSE_COLS = 64;
+static_assert(DENSE_COLS % 64 == 0 && DENSE_COLS <= TILE_N / 2, "dense prefix: whole chunk pairs of a warpgroup's half tile");
+
+__device__ __forceinline__ void tmem_ld_32x16_sync(uint32_t taddr, float (&v)[16]) {
+  uint32_t* r = reinterpret_cast<uint32_t*>(v);
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n\t"
+      "tcgen05.wait::ld.sync.aligned;"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+
+// compare-exchange on (score, column) pairs: afterwards a <= b
+__device__ __forceinline__ void pair_ce(float& as, int& ai, float& bs, int& bi) {
+  const bool sw = bs < as;
+  const float s0 = sw ? bs : as, s1 = sw ? as : bs;
+  const int i0 = sw ? bi : ai, i1 = sw ? ai : bi;
+  as = s0; ai = i0; bs = s1; bi = i1;
+}
+
+// Batcher's odd-even merge sort of 16 pairs, ascending (63 exchanges; the pairs are compile-time constants, so the
+// arrays stay in registers)
+__device__ __forceinline__ void sort16_pairs(float (&s)[16], int (&i)[16]) {
+  constexpr int A[63] = {0, 2, 4, 6, 8, 10, 12, 14, 0, 1, 4, 5, 8, 9, 12, 13, 1, 5, 9, 13, 0,
+                         1, 2, 3, 8, 9, 10, 11, 2, 3, 10, 11, 1, 3, 5, 9, 11, 13, 0, 1, 2, 3,
+                         4, 5, 6, 7, 4, 5, 6, 7, 2, 3, 6, 7, 10, 11, 1, 3, 5, 7, 9, 11, 13};
+  constexpr int B[63] = {1, 3, 5, 7, 9, 11, 13, 15, 2, 3, 6, 7, 10, 11, 14, 15, 2, 6, 10, 14, 4,
+                         5, 6, 7, 12, 13, 14, 15, 4, 5, 12, 13, 2, 4, 6, 10, 12, 14, 8, 9, 10, 11,
+                         12, 13, 14, 15, 8, 9, 10, 11, 4, 5, 8, 9, 12, 13, 2, 4, 6, 8, 10, 12, 14};
+#pragma unroll
+  for (int c = 0; c < 63; ++c) pair_ce(s[A[c]], i[A[c]], s[B[c]], i[B[c]]);
+}
+
+// L <- the 16 smallest of L (sorted) and h (sorted): min(L[t], h[15-t]) is those 16 as a bitonic sequence, four
+// half-cleaner stages sort it.  Ties keep the list's entry, like reg_insert.
+__device__ __forceinline__ void reg_merge16(RegList& L, const float (&hs)[16], const int (&hi)[16]) {
+  float ls[16];
+  int li[16];
+#define RL_GET(t) ls[t] = L.s##t; li[t] = L.i##t;
+  RL_FOR_EACH(RL_GET)
+#undef RL_GET
+#pragma unroll
+  for (int t = 0; t < 16; ++t) {
+    const bool tk = hs[15 - t] < ls[t];
+    ls[t] = tk ? hs[15 - t] : ls[t];
+    li[t] = tk ? hi[15 - t] : li[t];
+  }
+#pragma unroll
+  for (int j = 8; j > 0; j >>= 1) {
+#pragma unroll
+    for (int a = 0; a < 16; ++a) {
+      if ((a ^ j) > a) pair_ce(ls[a], li[a], ls[a ^ j], li[a ^ j]);
+    }
+  }
+#define RL_PUT(t) L.s##t = ls[t]; L.i##t = li[t];
+  RL_FOR_EACH(RL_PUT)
+#undef RL_PUT
+}
+
 struct RowStateR {
   float thr;        // effective filter threshold = min(thr_list, thr_g)
   float thr_list;   // k'-th best score currently kept (+inf until k' scores are in)
@@ -456,6 +536,8 @@ struct RowStateR {
 
 // warp-uniform and branch-free per pass: every lane pops one pending hit (+inf when it has none) and runs
 // the register insert; lanes that run dry idle until the longest queue is empty
+// KFULL: kp == RL (the default k' = 16) -- the list's threshold is simply its last slot, not a 16-way select
+template <bool KFULL>
 __device__ __forceinline__ void drain_queue_reg(RowStateR& st, RegList& L, int kp, uint32_t qs_addr, uint32_t qi_addr,
                                                 const float* ovf_s, const int* ovf_i) {
   while (__any_sync(FULL, st.cnt > 0)) {
@@ -475,7 +557,7 @@ __device__ __forceinline__ void drain_queue_reg(RowStateR& st, RegList& L, int k
     }
     x = (x < st.thr) ? x : INFINITY;          // the threshold may have tightened since the hit was queued
     reg_insert(L, x, col);
-    st.thr_list = reg_kth(L, kp);
+    st.thr_list = KFULL ? L.s15 : reg_kth(L, kp);
     st.thr = fminf(st.thr_list, st.thr_g);
   }
 }
@@ -775,9 +857,11 @@ score_topk_kernel(const __grid_constant__ CUtensorMap map_q_main, const __grid_c
       uint32_t gk_inflight = 0xffffffffu;
       if (gthr != nullptr) {
         const uint32_t gk = ld_cg_u32(gthr);
-        if (gk < KEY_INF) st.thr_g = nextafterf(key2f(gk), INFINITY);
+        if (gk < KEY_INF) st.thr_g = next_up(key2f(gk));
       }
       st.thr = fminf(st.thr_list, st.thr_g);
+      // a row of this warp without any bound: the strip's first columns take the dense path (warp-uniform)
+      bool dense = __any_sync(FULL, st.thr == INFINITY);
       for (int gt = gt0; gt < gt1; ++gt) {
         timed_wait<DEBUG>(&bars->tmem_full[acc], acc_phase, w_acc, p.wait_mode);
         tcgen05_fence_after();
@@ -787,9 +871,38 @@ score_topk_kernel(const __grid_constant__ CUtensorMap map_q_main, const __grid_c
         const bool ragged = col0 + HALF > N;                 // last gallery tile: TMA zero-filled rows
         float va[32], vb[32];
         __syncwarp();
-        tmem_ld_32x32(taddr, va);
+        int cc0 = 0;
+        if (dense) {
+          dense = false;
 #pragma unroll 1
-        for (int cc = 0; cc < HALF / 32; cc += 2) {
+          for (int h = 0; h < DENSE_COLS / 16; ++h) {
+            float hs[16];
+            int hi[16];
+            const int cb = col0 + h * 16;
+            tmem_ld_32x16_sync(taddr + h * 16, hs);
+            if (DEBUG && p.debug_scores != nullptr && qrow < p.Q) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j)
+                if (cb + j < N) p.debug_scores[qrow * p.N + cb + j] = hs[j];
+            }
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const bool ok = hs[j] < INFINITY && cb + j < N;   // NaN / +inf / zero-filled rows never enter a list
+              hs[j] = ok ? hs[j] : INFINITY;
+              hi[j] = ok ? cb + j : -1;
+            }
+            sort16_pairs(hs, hi);
+            reg_merge16(L, hs, hi);
+            __syncwarp();
+          }
+          st.n_ins += DENSE_COLS;
+          st.thr_list = reg_kth(L, KP);
+          st.thr = fminf(st.thr_list, st.thr_g);
+          cc0 = DENSE_COLS / 32;
+        }
+        if (cc0 < HALF / 32) tmem_ld_32x32(taddr + cc0 * 32, va);
+#pragma unroll 1
+        for (int cc = cc0; cc < HALF / 32; cc += 2) {
           tmem_ld_wait(va);
           tmem_ld_32x32(taddr + (cc + 1) * 32, vb);           // next chunk in flight while this one is scanned
           if (ragged) {
@@ -819,14 +932,20 @@ score_topk_kernel(const __grid_constant__ CUtensorMap map_q_main, const __grid_c
           process_chunk_reg(vb, col0 + (cc + 1) * 32, st, qs_addr, qi_addr, ovf_s, ovf_i);
           __syncwarp();
           // drain early when a queue is half full, so that thresholds do not go stale in the cold phase
-          if (__any_sync(FULL, st.cnt >= QCAP_R / 2)) drain_queue_reg(st, L, KP, qs_addr, qi_addr, ovf_s, ovf_i);
+          if (__any_sync(FULL, st.cnt >= QCAP_R / 2)) {
+            if (KP == RL) drain_queue_reg<true>(st, L, KP, qs_addr, qi_addr, ovf_s, ovf_i);
+            else drain_queue_reg<false>(st, L, KP, qs_addr, qi_addr, ovf_s, ovf_i);
+          }
         }
         tcgen05_fence_before();
         if (PAIR) mbar_arrive_cluster(&bars->tmem_empty[acc], 0);   // the leader waits for both CTAs' epilogues
         else mbar_arrive(&bars->tmem_empty[acc]);
         if (++acc == NUM_ACC) { acc = 0; acc_phase ^= 1; }
         // the accumulator is released: fold the pending hits in (off the MMA's critical path)
-        drain_queue_reg(st, L, KP, qs_addr, qi_addr, ovf_s, ovf_i);
+        // (measured, no gain: draining only once a queue holds 2-3 hits; exchanging thresholds every 4th / 8th tile
+        // once a strip is 8 tiles old -- the steady-state epilogue is not what bounds the kernel)
+        if (KP == RL) drain_queue_reg<true>(st, L, KP, qs_addr, qi_addr, ovf_s, ovf_i);
+        else drain_queue_reg<false>(st, L, KP, qs_addr, qi_addr, ovf_s, ovf_i);
         // exchange thresholds with the query's other lists (other warpgroup, other strips) through L2
         if (gthr != nullptr) {
           // this list's k'-th best bounds the query's k'-th best -- but not its kbound-th when kbound > k' (lists of
@@ -835,16 +954,19 @@ score_topk_kernel(const __grid_constant__ CUtensorMap map_q_main, const __grid_c
             atomicMin(gthr, f2key(st.thr_list));
             published = st.thr_list;
           }
-          if (gk_inflight < KEY_INF) st.thr_g = fminf(st.thr_g, nextafterf(key2f(gk_inflight), INFINITY));
+          if (gk_inflight < KEY_INF) st.thr_g = fminf(st.thr_g, next_up(key2f(gk_inflight)));
           gk_inflight = ld_cg_u32(gthr);
           // ... and with the other warpgroup of this CTA through shared memory
-          const float mine = reg_kth(L, half_k);
+          float mine;
+          if (half_k == 12) mine = L.s11;            // kbound = 24, the search path's default (warp-uniform branches)
+          else if (half_k == 8) mine = L.s7;         // kbound = k' = 16
+          else mine = reg_kth(L, half_k);
           uint32_t tag, bits;
           asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(my_x), "r"(step), "r"(__float_as_uint(mine)) : "memory");
           asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(tag), "=r"(bits) : "r"(peer_x) : "memory");
           if (tag == (uint32_t)step) {                 // the peer is on the same strip (same query rows)
             const float both = fmaxf(mine, __uint_as_float(bits));
-            if (both < INFINITY) st.thr_g = fminf(st.thr_g, nextafterf(both, INFINITY));
+            if (both < INFINITY) st.thr_g = fminf(st.thr_g, next_up(both));
             if (both < published) {                    // also a bound for the query's other strips
               atomicMin(gthr, f2key(both));
               published = both;
@@ -910,7 +1032,7 @@ score_topk_kernel(const __grid_constant__ CUtensorMap map_q_main, const __grid_c
       uint32_t gk_inflight = 0xffffffffu;      // bound loaded during the previous tile, consumed one tile later
       if (gthr != nullptr) {
         const uint32_t gk = ld_cg_u32(gthr);
-        if (gk < KEY_INF) st.thr_g = nextafterf(key2f(gk), INFINITY);
+        if (gk < KEY_INF) st.thr_g = next_up(key2f(gk));
       }
       st.thr = fminf(st.thr_list, st.thr_g);
       __syncwarp();
@@ -970,7 +1092,7 @@ score_topk_kernel(const __grid_constant__ CUtensorMap map_q_main, const __grid_c
           }
           // consume the load issued one tile ago (its latency is hidden behind a whole tile),
           // then put the next one in flight
-          if (gk_inflight < KEY_INF) st.thr_g = fminf(st.thr_g, nextafterf(key2f(gk_inflight), INFINITY));
+          if (gk_inflight < KEY_INF) st.thr_g = fminf(st.thr_g, next_up(key2f(gk_inflight)));
           st.thr = fminf(st.thr_list, st.thr_g);
           gk_inflight = ld_cg_u32(gthr);
         }
