@@ -30,6 +30,16 @@ CASES = [
     (900, 5000, 128, 8, 5),      # forced small grid: full wave + phase 1 + phase 2 in one CTA
     (700, 9000, 512, 16, 7),     # resident tile reloaded between strips
     (128 * 3, 256 * 40, 64, 16, 6),
+    # the dense cold start of a strip (first 64 columns of each warpgroup's half tile through the sorting network):
+    # galleries that end inside / at / just after its 16-column groups, k' below the 16 register slots
+    (130, 15, 128, 16, 0),
+    (130, 17, 128, 10, 0),
+    (256, 63, 512, 16, 0),
+    (256, 65, 512, 12, 0),
+    (140, 130, 256, 16, 0),
+    (300, 257, 128, 5, 0),
+    (260, 300, 2048, 16, 0),
+    (260, 193, 64, 16, 0),
 ]
 
 

@@ -19,6 +19,10 @@ ncu --set full --clock-control none --import-source on -k regex:score_topk -s 3 
     python bench.py --steps 2 --warmup 3 --no-cpu-baseline > $O/${T}_ncu_score.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:score_topk -s 3 -c 1 -f -o $O/prof_score_c2_${T} \
     python bench.py --workload c2 --steps 2 --warmup 3 --no-cpu-baseline > $O/${T}_ncu_score_c2.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:score_topk -s 3 -c 1 -f -o $O/prof_score_c1_${T} \
+    python bench.py --workload c1 --steps 2 --warmup 3 --no-cpu-baseline > $O/${T}_ncu_score_c1.log 2>&1
+python tools/bench_score_shapes.py > $O/${T}_score_shapes.txt 2>&1
+HYPRET_STATS=1 python bench.py --workload c1 --steps 1 --warmup 1 --no-cpu-baseline 2>&1 | grep "hypret stats" | tail -2 > $O/${T}_score_c1_stats.txt
 ncu --set full --clock-control none --import-source on -k flash_tile_kernel -s 4 -c 1 -f -o $O/prof_flash_fwd_${T} \
     python tools/c5_parts.py > $O/${T}_ncu_flash_fwd.log 2>&1
 ncu --set full --clock-control none --import-source on -k flash_tile_kernel -s 30 -c 1 -f -o $O/prof_flash_bwd_${T} \
