@@ -9,21 +9,23 @@
 // kernel keeps the k' smallest S of every gallery strip it visits.  S lives only in TMEM and
 // registers.
 //
-// Structure (one persistent CTA per SM, 192 threads, warp-specialised):
-//   warp 0   TMA producer   gallery K-blocks (256 rows x 64 fp16, 128B swizzle) into a
-//                           shared-memory ring; the 128-row query tile is loaded ONCE per strip
-//                           and stays resident in shared memory when D <= 512 (RESIDENT),
-//                           otherwise it streams through the ring next to the gallery block
-//   warp 1   MMA issuer     one thread issues tcgen05.mma (M=128, N=256, K=16, fp16 -> fp32)
-//                           into one of two 256-column TMEM accumulators; tcgen05.commit
-//                           releases ring stages and publishes finished accumulators
-//   warps 2-5 epilogue      tcgen05.ld 32x32b: lane t of a warp owns query row t of its TMEM
-//                           quadrant, so the running k'-th best score of a query is a private
-//                           register.  Fast path: 3-input min tree + one ballot per 32 columns.
-//                           Slow path (rare): the warp inserts cooperatively -- the owner lane
-//                           overwrites its worst slot in shared memory, all lanes re-read the
-//                           row's slots (one word each) and a single redux.max finds the new
-//                           threshold.
+// Structure (one persistent CTA per SM, warp-specialised; CTAs run as PAIRS -- tcgen05 cta_group::2 -- whenever there
+// are two query tiles to pair up; 320 threads for k' <= 16, 192 otherwise):
+//   warp 0   TMA producer   gallery K-blocks (each CTA of a pair its half: 128 rows x 64 fp16, 128B swizzle) into a
+//                           shared-memory ring; the CTA's 128-row query tile is loaded ONCE per strip and stays
+//                           resident in shared memory when D <= 512 (RESIDENT), otherwise it streams through the
+//                           ring next to the gallery block
+//   warp 1   MMA issuer     one thread of the leader CTA issues tcgen05.mma (M=256 across the pair, N=256, K=16,
+//                           fp16 -> fp32) into one of two 256-column TMEM accumulators; tcgen05.commit releases ring
+//                           stages and publishes finished accumulators (multicast to both CTAs)
+//   warps 2+ epilogue       tcgen05.ld 32x32b: lane t of a warp owns query row t of its TMEM quadrant, so the
+//                           running k'-th best score of a query is a private register.  Fast path: 3-input min tree
+//                           + one compare per 32 columns.  Hits go to a per-lane pending queue in shared memory and
+//                           the warp drains all queues together.
+//                           k' <= 16 (the search path): TWO epilogue warpgroups, each on its half of every tile,
+//                           the candidate list of a row in the owning thread's REGISTERS (sorted, branch-free
+//                           insert); a cold strip's first 64 columns go through a sorting network instead
+//                           (sort16_pairs / reg_merge16).  k' > 16: one warpgroup, lists in shared memory.
 //
 // Strip schedule.  Work unit = (query tile, contiguous range of gallery tiles) = "strip"; a
 // strip owns one candidate list per query row, so every strip start is a cold threshold and a
