@@ -6,9 +6,11 @@
     train_hyperbolic_contrastive(...)                                 src/train.py:1792-1910
 
 The reference builds the n x n matrix with an O(n^2) Python double loop of 1x1 ``pmath.dist``
-calls (~40 kernel launches each) and differentiates through all of them.  Here the matrix is one
-exact CUDA kernel (``hypret_pairdist``) and its backward is closed-form (``hypret_pairdist_bwd``
-+ two dense products), wrapped in one autograd Function.  CUDA tensors only.
+calls (~40 kernel launches each) and differentiates through all of them.  Here the in-batch loss is
+one autograd Function over the flash kernels (``hypret_flash_lse`` / ``hypret_flash_grad``: no
+``[n,n]`` array, closed-form backward on the tensor cores) for 16 <= D <= 128, D % 16 == 0,
+and over the matrix kernels (``hypret_pairdist_ce_fwd/bwd`` + split products) for other widths;
+``pairwise_dist`` is the explicit matrix (``hypret_pairdist`` + ``hypret_pairdist_bwd``).  CUDA tensors only.
 """
 from __future__ import annotations
 
